@@ -1,0 +1,253 @@
+/*
+ * gysketch.h — C ABI of libgysketch.so, the B200-native streaming-sketch aggregation engine that sits
+ * behind Gyeeta's madhava ingest path.
+ *
+ * Every entry point replaces (or is what a cgo/ctypes/C++ shim would bind for) a named piece of the
+ * reference; citations are relative to the reference tree:
+ *
+ *   gysk_ingest()         the per-message dispatch of MCONN_HANDLER::handle_l2_misc  server/gy_mconnhdlr.cc:4745-4800
+ *                         (phdr/pevtnot/recs/nevents/pendptr arithmetic) and the record walks of
+ *                         partha_tcp_conn_info :9052/:9130, partha_listener_state :10993/:11175,
+ *                         partha_aggr_task_state :9959, incl. the L1 validators common/gy_comm_proto.cc:840-996
+ *   gysk_ingest_raw()     the per-sample reduction lifted off partha: TCP_SOCK_HANDLER::handle_ipv4_resp_event /
+ *                         handle_tcp_resp_event  common/gy_socket_stat.cc:1517-1677, handle_ipv4_conn_event :241,
+ *                         SVC_INFO_CAP::upd_stats_on_req  common/gy_proto_parser.cc:2678-2694
+ *   gysk_ingest_device()  same reduction for event batches already resident in HBM (bench / device generators)
+ *   gysk_flush()          the 5-second reducer TCP_SOCK_HANDLER::listener_stats_update  common/gy_socket_stat.cc:3898-4445
+ *   gysk_query_svcs()     readers of MTCP_LISTENER::state_ (server/gy_msocket.h:1304) through SvcStateFields
+ *                         (server/gy_mfields.h:1383-1412): qps5s, nqry5s, resp5s, p95resp5s ...
+ *   gysk_export_hist()    GY_HISTOGRAM::get_serialized  common/gy_statistics.h:656-673 (HIST_SERIAL byte-compatible)
+ *   gysk_hist_percentiles GY_HISTOGRAM::get_percentiles common/gy_statistics.h:707-791
+ *   gysk_query_flows()    new capability: count-min point query replacing the exact two-level group-by of
+ *                         partha_tcp_conn_info  server/gy_mconnhdlr.cc:9245-9311
+ *   gysk_export_hll()     new capability: distinct clients per service, replacing the exact client sets
+ *                         (cli_aggr_task_tbl_, server/gy_msocket.h:1335)
+ *   gysk_export_tdigest() new capability: response-time quantile sketch; the reference's only t-digest user is the
+ *   gysk_query_quantiles  Postgres extension with compression 100 (common/gy_query_common.cc:1805-1858)
+ *   gysk_merge_*          additive roll-up  MS_CLUSTER_STATE::STATE_ONE::add_stats common/gy_comm_proto.h:3199-3214 /
+ *                         SHCONN_HANDLER::aggregate_cluster_state server/gy_shconnhdlr.cc:4583
+ *
+ * Conventions: plain pointers and sizes, no exceptions cross the boundary, 0 = ok, negative = -errno style
+ * (mirrors the reference handlers' bool/int returns wrapped in GY_CATCH_EXCEPTION, gy_mconnhdlr.cc:4763-4774).
+ * CUDA errors are sticky: once a call fails with GYSK_ERR_CUDA every later call fails too; gysk_last_error()
+ * returns the text. There is NO CPU fallback: gysk_create() fails when no sm_100 device is usable.
+ */
+#ifndef GYSKETCH_H
+#define GYSKETCH_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GYSK_ABI_VERSION		1
+
+/* ---- error codes ---- */
+#define GYSK_OK				0
+#define GYSK_ERR_INVAL			(-22)	/* EINVAL  : bad argument / failed wire validation */
+#define GYSK_ERR_NOMEM			(-12)	/* ENOMEM  */
+#define GYSK_ERR_NOENT			(-2)	/* ENOENT  : unknown service / task id */
+#define GYSK_ERR_NOSPC			(-28)	/* ENOSPC  : service table full */
+#define GYSK_ERR_NODEV			(-19)	/* ENODEV  : no usable CUDA device (no CPU fallback exists) */
+#define GYSK_ERR_CUDA			(-5)	/* EIO     : CUDA runtime error (sticky) */
+#define GYSK_ERR_NOTSUP			(-95)	/* EOPNOTSUPP */
+
+/* ---- canonical 32-byte event record ---- */
+enum {
+	GYSK_EV_CONNECT		= 1,	/* TCP_EVENT_TYPE_CONNECT    common/gy_ebpf_kernel.h:24 */
+	GYSK_EV_ACCEPT		= 2,	/* TCP_EVENT_TYPE_ACCEPT */
+	GYSK_EV_CLOSE_CLI	= 3,	/* TCP_EVENT_TYPE_CLOSE_CLI */
+	GYSK_EV_CLOSE_SER	= 4,	/* TCP_EVENT_TYPE_CLOSE_SER */
+	GYSK_EV_RESP		= 5,	/* service response-time sample (tcp_ipv4_resp_event_t / API_TRAN) */
+	GYSK_EV_TASK		= 6,	/* per-process 5-s sample (AGGR_TASK_STATE_NOTIFY) */
+};
+
+typedef struct gysk_event
+{
+	uint64_t	svc_id;		/* ser_glob_id_ ; for GYSK_EV_TASK: aggr_task_id_. 0 is invalid (dropped) */
+	uint64_t	flow_key;	/* TCP/RESP: cli_task_aggr_id_ or a 64-bit fold of the 5-tuple.
+					   TASK: low 32 = cpu_delay_msec_, high 32 = blkio_delay_msec_ */
+	uint32_t	value;		/* RESP: response time in usec; TCP: bytes; TASK: (int)total_cpu_pct_ */
+	uint32_t	host_idx;	/* dense index of the sending partha (shard key: host_idx % world) */
+	uint32_t	tsec;		/* event time, seconds */
+	uint16_t	type;		/* GYSK_EV_* */
+	uint16_t	flags;		/* reserved, 0 */
+} gysk_event;
+
+/* ---- histogram classes (bucket thresholds of common/gy_statistics.h:1674-2063) ---- */
+enum {
+	GYSK_CLS_RESP_TIME	= 0,	/* RESP_TIME_HASH	:1674  (msec) */
+	GYSK_CLS_SEMI_LOG	= 1,	/* SEMI_LOG_HASH	:1729 */
+	GYSK_CLS_SEMI_LOG_LO	= 2,	/* SEMI_LOG_HASH_LO	:1782 */
+	GYSK_CLS_DURATION	= 3,	/* DURATION_HASH	:1835 */
+	GYSK_CLS_HASH_10_5000	= 4,	/* HASH_10_5000		:1908 */
+	GYSK_CLS_HASH_5_250	= 5,	/* HASH_5_250		:1960 */
+	GYSK_CLS_HASH_1_3000	= 6,	/* HASH_1_3000		:2013 */
+	GYSK_CLS_PERCENT	= 7,	/* PERCENT_HASH		:1624 */
+};
+
+#define GYSK_HIST_MAX_BUCKETS		15	/* largest max_buckets among the classes above */
+
+/* byte-compatible with HIST_SERIAL, common/gy_statistics.h:458-468 */
+typedef struct gysk_hist_serial
+{
+	uint64_t	count;
+	int64_t		sum;
+} gysk_hist_serial;
+
+/* which histogram of an id */
+enum {
+	GYSK_HIST_RESP_CUR	= 0,	/* service: response msec, window being filled		(RESP_TIME_HASH, T=int64) */
+	GYSK_HIST_RESP_LAST	= 1,	/* service: last closed 5-s window */
+	GYSK_HIST_RESP_ALL	= 2,	/* service: since start ("Since Process start" level, gy_statistics.h:1548) */
+	GYSK_HIST_TASK_CPU_PCT	= 3,	/* task: MTASK_HIST::cpu_pct_histogram_		(HASH_1_3000, T=int)  server/gy_msocket.h:707 */
+	GYSK_HIST_TASK_CPU_DELAY= 4,	/* task: cpu_delay_histogram_			(DURATION_HASH, T=int) */
+	GYSK_HIST_TASK_BLKIO_DELAY = 5,	/* task: blkio_delay_histogram_			(DURATION_HASH, T=int) */
+};
+
+/* ---- raw record kinds for gysk_ingest_raw ---- */
+enum {
+	GYSK_RAW_EVENT32	= 0,	/* gysk_event[] */
+	GYSK_RAW_TCP_IPV4_EVENT	= 1,	/* tcp_ipv4_event_t[]      72 B  common/gy_ebpf_kernel.h:37  */
+	GYSK_RAW_TCP_IPV4_RESP	= 2,	/* tcp_ipv4_resp_event_t[] 24 B  common/gy_ebpf_kernel.h:106 */
+};
+
+/* ---- wire subtypes accepted by gysk_ingest (NOTIFY_TYPE_E, common/gy_comm_proto.h:155-200) ---- */
+#define GYSK_NOTIFY_LISTENER_STATE	0x309u
+#define GYSK_NOTIFY_TCP_CONN		0x30Cu
+#define GYSK_NOTIFY_AGGR_TASK_STATE	0x310u
+
+/* ---- configuration ---- */
+#define GYSK_FLAG_AUTO_REGISTER		0x1u	/* unknown svc/task ids are inserted on first sight (device side);
+						   without it unknown ids are skipped like a failed
+						   listen_tbl_.lookup_single_elem_locked, gy_mconnhdlr.cc:11183 */
+
+typedef struct gysk_config
+{
+	uint32_t	struct_size;		/* sizeof(gysk_config) */
+	int32_t		device;			/* CUDA device ordinal */
+	uint32_t	max_svcs;		/* service (listener) capacity */
+	uint32_t	max_tasks;		/* aggregated-process capacity */
+	uint32_t	cms_depth;		/* rows, 1..8 (default 4) */
+	uint32_t	cms_log2_width;		/* columns = 1 << this (default 20) */
+	uint32_t	hll_p;			/* registers per service = 1 << p, 4..16 (default 12) */
+	uint32_t	td_compression;		/* t-digest delta (default 100 = public.tdigest(x, 100), gy_query_common.cc:1855) */
+	uint32_t	max_batch;		/* max events per device batch (default 1 << 24) */
+	uint32_t	flags;			/* GYSK_FLAG_* */
+	uint32_t	rank, world;		/* this engine owns events with host_idx % world == rank; world 0/1 = all */
+	uint32_t	reserved[4];
+} gysk_config;
+
+typedef struct gysk_engine gysk_engine;
+
+/* ---- per-service summary: the fields SvcStateFields exposes + the new sketch answers ---- */
+typedef struct gysk_svc_summary
+{
+	uint64_t	glob_id;
+	int32_t		found;			/* 0 if the id is unknown */
+	uint32_t	nqrys_5s;		/* LISTENER_STATE_NOTIFY::nqrys_5s_       (last closed window) */
+	uint64_t	total_resp_5sec;	/* ::total_resp_5sec_ (msec sum, last closed window) */
+	int64_t		p95_5s_resp_ms;		/* ::p95_5s_resp_ms_   = get_percentile(95) of the last window */
+	int64_t		p99_5s_resp_ms;
+	int64_t		p25_5s_resp_ms;		/* the three percentiles listener_stats_update reads, gy_socket_stat.h:459 */
+	int64_t		p95_all_resp_ms;
+	int64_t		p99_all_resp_ms;
+	uint64_t	nqrys_all;
+	int64_t		max_resp_ms;		/* max_val_seen_ of the all-time histogram */
+	uint32_t	nconns_5s;		/* TCP events of the last window */
+	uint32_t	kbytes_5s;
+	uint64_t	nconns_all;
+	uint64_t	kbytes_all;
+	double		distinct_clients;	/* HLL estimate */
+	double		td_p50_us, td_p95_us, td_p99_us;	/* t-digest quantiles (usec); NaN when empty */
+	uint64_t	td_count;
+} gysk_svc_summary;
+
+typedef struct gysk_flow_est
+{
+	uint64_t	flow_key;
+	uint32_t	count;			/* min over rows of the count halves */
+	uint32_t	kbytes;			/* min over rows of the kbytes halves */
+} gysk_flow_est;
+
+typedef struct gysk_stats
+{
+	uint64_t	events_in;		/* events handed to the device */
+	uint64_t	events_dropped;		/* svc_id 0, bad type, table full, unknown id without AUTO_REGISTER */
+	uint64_t	events_resp, events_tcp, events_task;
+	uint64_t	nsvcs, ntasks;
+	uint64_t	batches;
+	uint64_t	kernel_launches;	/* launches of this library's own kernels so far */
+	uint64_t	wire_msgs_ok, wire_msgs_bad;
+} gysk_stats;
+
+/* mergeable device buffers (for the multi-GPU merge step) */
+enum { GYSK_RED_SUM_U64 = 0, GYSK_RED_MAX_U8 = 1 };
+typedef struct gysk_buffer_desc
+{
+	const char	*name;
+	void		*dptr;			/* device pointer */
+	uint64_t	nbytes;
+	int32_t		redop;			/* GYSK_RED_* */
+	int32_t		pad;
+} gysk_buffer_desc;
+
+/* ---- lifecycle ---- */
+int		gysk_abi_version(void);
+void		gysk_config_default(gysk_config *cfg);
+int		gysk_create(const gysk_config *cfg, gysk_engine **out);
+void		gysk_destroy(gysk_engine *e);
+const char *	gysk_last_error(gysk_engine *e);		/* e may be NULL: error of the last failed gysk_create */
+int		gysk_get_stats(gysk_engine *e, gysk_stats *out);	/* synchronises the ingest stream */
+
+/* ---- registration (control path; mirrors partha_listener_info registering listeners before state arrives) ---- */
+int		gysk_register_ids(gysk_engine *e, const uint64_t *ids, uint32_t n, int is_task);
+
+/* ---- ingest ---- */
+int		gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, uint32_t subtype,
+				void *recs, uint32_t nevents, const void *endptr);
+int		gysk_ingest_msg(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, void *comm_header_msg, uint32_t msglen);
+int		gysk_ingest_raw(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, uint32_t kind,
+				const void *events, uint32_t nevents);
+int		gysk_ingest_device(gysk_engine *e, const gysk_event *d_events, uint64_t nevents);
+int		gysk_sync(gysk_engine *e);
+int		gysk_flush(gysk_engine *e, uint32_t tsec);
+
+/* ---- queries ---- */
+int		gysk_query_svcs(gysk_engine *e, const uint64_t *glob_ids, uint32_t n, gysk_svc_summary *out);
+int		gysk_query_flows(gysk_engine *e, const uint64_t *flow_keys, uint32_t n, int last_window, gysk_flow_est *out);
+int		gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial out[GYSK_HIST_MAX_BUCKETS],
+				uint64_t *total_count, int64_t *max_val);
+int		gysk_export_hll(gysk_engine *e, uint64_t glob_id, uint8_t *regs /* 1 << hll_p bytes */);
+int		gysk_export_tdigest(gysk_engine *e, uint64_t glob_id, float *means, float *weights, uint32_t cap, uint32_t *n,
+				float *min_val, float *max_val);
+int		gysk_query_quantiles(gysk_engine *e, uint64_t glob_id, const double *qs, uint32_t nq, double *out);
+int		gysk_export_cms(gysk_engine *e, int last_window, uint64_t *cells /* depth << log2_width entries */);
+
+/* ---- pure helpers (host side, no engine): the reference's percentile rule and the sketch estimators ---- */
+int		gysk_hist_nbuckets(int cls);
+int		gysk_hist_bucket(int cls, int64_t value);	/* RESP_TIME_HASH::get_bucket_from_data & siblings */
+int		gysk_hist_percentiles(int cls, int t_is_int, const gysk_hist_serial *stats, uint64_t total_count,
+				const float *pcts, uint32_t npct, int64_t *out);
+double		gysk_hll_estimate(const uint8_t *regs, uint32_t p);
+double		gysk_tdigest_quantile(const float *means, const float *weights, uint32_t n, float min_val, float max_val, double q);
+uint32_t	gysk_uint64_hash(uint64_t key);		/* get_uint64_hash, common/gy_common_inc.h:1120 */
+
+/* ---- multi-GPU merge ---- */
+int		gysk_set_logical_map(gysk_engine *e, const uint64_t *glob_ids, const uint64_t *logical_ids, uint32_t n);
+int		gysk_merge_prepare(gysk_engine *e);		/* fold per-service sketches into per-logical-service arrays */
+int		gysk_merge_buffers(gysk_engine *e, gysk_buffer_desc *out, uint32_t cap, uint32_t *n);
+int		gysk_merge_tdigest_slab(gysk_engine *e, void **dptr, uint64_t *nbytes);	/* fixed slab to all-gather */
+int		gysk_merge_finish(gysk_engine *e, const void *d_gathered_slabs, uint32_t world);
+int		gysk_query_logical(gysk_engine *e, const uint64_t *logical_ids, uint32_t n, gysk_svc_summary *out);
+
+/* CUDA stream the engine launches on (cudaStream_t as void*), for callers timing with events */
+void *		gysk_stream(gysk_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GYSKETCH_H */

@@ -1,0 +1,843 @@
+/*
+ * gysk_oracle.c — TEST INFRASTRUCTURE ONLY (see gysk_oracle.h). Plain-C CPU restatement of the hot path.
+ * Each function cites the reference file:line (relative to the reference tree) whose behaviour it restates.
+ *
+ * PARITY STATUS: histogram/jhash parts are pinned (tests/test_oracle_pinning.py: the asserted values of
+ * test/test_histogram.cc and the outputs of the reference compiled into oracle/_ref). Count-min, HyperLogLog
+ * and t-digest are PARITY UNPINNED: the reference holds no implementation or vector for them.
+ */
+#include "gysk_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
+#include <math.h>
+#include <time.h>
+#include <pthread.h>
+
+/* ------------------------------------------------------------------------------------------------
+ * jhash: Bob Jenkins' lookup2 (public domain, 1996) in the word-oriented form the reference uses.
+ * common/jhash.h:22-35 (mix), :86-113 (jhash2), :121-140 (n-words), :44-84 (bytes)
+ * ------------------------------------------------------------------------------------------------ */
+#define GOLDEN		0x9e3779b9u
+#define GY_SEED		0xceedfeadu	/* common/gy_common_inc.h:1112-1122 */
+
+static inline void mix3(uint32_t *pa, uint32_t *pb, uint32_t *pc)
+{
+	uint32_t a = *pa, b = *pb, c = *pc;
+
+	a -= b; a -= c; a ^= (c >> 13);
+	b -= c; b -= a; b ^= (a << 8);
+	c -= a; c -= b; c ^= (b >> 13);
+	a -= b; a -= c; a ^= (c >> 12);
+	b -= c; b -= a; b ^= (a << 16);
+	c -= a; c -= b; c ^= (b >> 5);
+	a -= b; a -= c; a ^= (c >> 3);
+	b -= c; b -= a; b ^= (a << 10);
+	c -= a; c -= b; c ^= (b >> 15);
+
+	*pa = a; *pb = b; *pc = c;
+}
+
+uint32_t gyo_jhash_3words(uint32_t a, uint32_t b, uint32_t c, uint32_t initval)
+{
+	a += GOLDEN; b += GOLDEN; c += initval;
+	mix3(&a, &b, &c);
+	return c;
+}
+
+uint32_t gyo_jhash_2words(uint32_t a, uint32_t b, uint32_t initval)
+{
+	return gyo_jhash_3words(a, b, 0, initval);
+}
+
+uint32_t gyo_jhash2(const uint32_t *k, uint32_t length, uint32_t initval)
+{
+	uint32_t a = GOLDEN, b = GOLDEN, c = initval, len = length;
+
+	while (len >= 3) {
+		a += k[0]; b += k[1]; c += k[2];
+		mix3(&a, &b, &c);
+		k += 3; len -= 3;
+	}
+	c += length * 4;
+	if (len == 2) { b += k[1]; a += k[0]; }
+	else if (len == 1) { a += k[0]; }
+	mix3(&a, &b, &c);
+	return c;
+}
+
+uint32_t gyo_jhash(const void *key, uint32_t length, uint32_t initval)
+{
+	const uint8_t *k = (const uint8_t *)key;
+	uint32_t a = GOLDEN, b = GOLDEN, c = initval, len = length;
+
+	while (len >= 12) {
+		a += (k[0] + ((uint32_t)k[1] << 8) + ((uint32_t)k[2] << 16) + ((uint32_t)k[3] << 24));
+		b += (k[4] + ((uint32_t)k[5] << 8) + ((uint32_t)k[6] << 16) + ((uint32_t)k[7] << 24));
+		c += (k[8] + ((uint32_t)k[9] << 8) + ((uint32_t)k[10] << 16) + ((uint32_t)k[11] << 24));
+		mix3(&a, &b, &c);
+		k += 12; len -= 12;
+	}
+	c += length;
+	/* tail bytes: byte i of the tail lands in word i/4 (a, b) or, from the 9th on, one byte higher in c */
+	for (uint32_t i = 0; i < len; ++i) {
+		uint32_t v = k[i];
+		if (i < 4) a += v << (8 * i);
+		else if (i < 8) b += v << (8 * (i - 4));
+		else c += v << (8 * (i - 8 + 1));
+	}
+	mix3(&a, &b, &c);
+	return c;
+}
+
+uint32_t gyo_uint64_hash(uint64_t key)
+{
+	return gyo_jhash_2words((uint32_t)(key & 0xFFFFFFFFu), (uint32_t)(key >> 32), GY_SEED);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * bucket hash classes, common/gy_statistics.h:1584-2063
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cls_desc
+{
+	int		nthr;
+	int64_t		thr[16];
+	int64_t		min_value, max_value;
+	int		trunc_int;	/* operator()(int data): the value is narrowed to int before bucketing (:1748,:1801,...) */
+	int		fixed_diff;	/* FIXED_DIFF_HASH: bucket = 1 + (data - min)/diff (:1611-1621) */
+} cls_desc;
+
+static const cls_desc g_cls[GYO_CLS_MAX] = {
+	[GYO_CLS_RESP_TIME]	= { 13, {1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000}, 0, 15001, 0, 0 },		/* :1677 */
+	[GYO_CLS_SEMI_LOG]	= { 12, {1, 10, 100, 500, 1000, 5000, 25000, 50000, 100000, 300000, 1000000, 5000000}, 0, 5000001, 1, 0 },	/* :1732 */
+	[GYO_CLS_SEMI_LOG_LO]	= { 13, {1, 10, 50, 200, 500, 1000, 3000, 6000, 10000, 15000, 25000, 60000, 150000}, 0, 150001, 1, 0 },	/* :1785 */
+	[GYO_CLS_DURATION]	= { 13, {1, 10, 25, 50, 125, 400, 1000, 3000, 6000, 10000, 25000, 40000, 65000}, 0, 65001, 1, 0 },	/* :1838 */
+	[GYO_CLS_HASH_10_5000]	= { 12, {10, 25, 50, 75, 100, 150, 300, 500, 800, 1000, 2000, 5000}, 0, 5001, 1, 0 },			/* :1911 */
+	[GYO_CLS_HASH_5_250]	= { 10, {5, 10, 20, 40, 60, 80, 100, 140, 200, 250}, 0, 251, 1, 0 },					/* :1963 */
+	[GYO_CLS_HASH_1_3000]	= { 12, {1, 5, 10, 25, 50, 75, 100, 150, 300, 500, 1000, 3000}, 0, 3001, 1, 0 },			/* :2016 */
+	/* FIXED_DIFF_HASH<int64_t,0,100,10>: thresholds tmin + (i+1)*diff - 1, last = tmax (:1570-1582) */
+	[GYO_CLS_PERCENT]	= { 11, {9, 19, 29, 39, 49, 59, 69, 79, 89, 99, 100}, 0, 101, 0, 10 },					/* :1624 */
+	[GYO_CLS_FD_I8_9_26_5]	= { 4, {13, 18, 23, 26}, 9, 27, 0, 5 },			/* test/test_histogram.cc:17 */
+	[GYO_CLS_FD_INT_M15_M3_4] = { 4, {-12, -8, -4, -3}, -15, -2, 0, 4 },		/* test/test_histogram.cc:92 */
+};
+
+int gyo_nbuckets(int cls)
+{
+	if (cls < 0 || cls >= GYO_CLS_MAX) return -1;
+	return g_cls[cls].nthr + 2;
+}
+
+int gyo_bucket(int cls, int64_t value)
+{
+	const cls_desc *d = &g_cls[cls];
+	int64_t data = value;
+
+	if (d->trunc_int) data = (int64_t)(int)value;
+
+	if (data < d->min_value) return 0;
+	if (data >= d->max_value) return d->nthr + 1;
+
+	if (d->fixed_diff) return (int)(1 + (data - d->min_value) / d->fixed_diff);
+
+	/* the mid-slot shortcut (:1711-1716) only changes where the scan starts, never its result */
+	for (int nb = 0; nb < d->nthr; ++nb) {
+		if (data <= d->thr[nb]) return nb + 1;
+	}
+	return d->nthr + 1;
+}
+
+/* get_bucket_max_threshold<HashClass, T>, common/gy_statistics.h:500-515 */
+int64_t gyo_bucket_max_threshold(int cls, int tkind, size_t id)
+{
+	const cls_desc *d = &g_cls[cls];
+	size_t maxb = (size_t)d->nthr + 2;
+
+	if (id == 0) return d->min_value - 1;
+
+	if (id >= maxb - 1) {
+		int64_t maxt = (tkind == GYO_T_INT64) ? INT64_MAX : (tkind == GYO_T_INT ? INT_MAX : SCHAR_MAX);
+		int64_t lesst = d->max_value >= INT_MAX ? LONG_MAX : (d->max_value > (SHRT_MAX >> 1) ? INT_MAX : SHRT_MAX);
+
+		return lesst < maxt ? lesst : maxt;
+	}
+	return d->thr[id - 1];
+}
+
+static inline int64_t t_min(int tkind)
+{
+	return tkind == GYO_T_INT64 ? INT64_MIN : (tkind == GYO_T_INT ? INT_MIN : SCHAR_MIN);
+}
+
+static inline int64_t t_cast(int tkind, int64_t v)
+{
+	return tkind == GYO_T_INT64 ? v : (tkind == GYO_T_INT ? (int64_t)(int)v : (int64_t)(int8_t)v);
+}
+
+void gyo_hist_init(gyo_hist *h, int cls, int tkind)
+{
+	memset(h, 0, sizeof(*h));
+	h->cls = cls; h->tkind = tkind;
+	h->max_val = t_min(tkind);		/* max_val_seen_{numeric_limits<T>::min()} :560 */
+}
+
+/* GY_HISTOGRAM::add_data :596-623 — `T data` narrows first, then hash_(data), sum += data, count++, total++, max */
+int gyo_hist_add(gyo_hist *h, int64_t value)
+{
+	int64_t data = t_cast(h->tkind, value);
+	int b = gyo_bucket(h->cls, data);
+
+	h->stats[b].sum += data;
+	h->stats[b].count++;
+	h->total_count++;
+	if (h->max_val < data) h->max_val = data;
+	return b;
+}
+
+/* update_from_serialized :625-650 (clock fields not modelled) */
+void gyo_hist_merge(gyo_hist *dst, const gyo_hist *src)
+{
+	int nb = gyo_nbuckets(dst->cls);
+
+	for (int i = 0; i < nb; ++i) {
+		dst->stats[i].count += src->stats[i].count;
+		dst->stats[i].sum += src->stats[i].sum;
+	}
+	dst->total_count += src->total_count;
+	if (dst->max_val < src->max_val) dst->max_val = src->max_val;
+}
+
+/* get_percentiles :707-791. Note the float multiplier and the size_t * float product (:753-754) */
+void gyo_hist_percentiles(const gyo_hist *h, const float *pcts, size_t npct, int64_t *out, float *avg)
+{
+	const size_t	nb = (size_t)gyo_nbuckets(h->cls);
+	const size_t	total_count = h->total_count;
+
+	if (avg) {
+		int64_t total_sum = 0, cnt = total_count ? (int64_t)total_count : 1;
+
+		for (size_t i = 0; i < nb; ++i) total_sum += h->stats[i].sum;
+		*avg = (total_sum * 1.0f) / cnt;
+	}
+
+	for (size_t n = 0; n < npct; ++n) {
+		float		multiplier = pcts[n] / 100.0;
+		const size_t	ncutoff = total_count * multiplier;
+		size_t		i, total = 0;
+
+		for (i = 0; i < nb; ++i) {
+			total += h->stats[i].count;
+			if (total >= ncutoff) {
+				out[n] = t_cast(h->tkind, gyo_bucket_max_threshold(h->cls, h->tkind, i));
+				break;
+			}
+		}
+		if (i < nb) continue;
+
+		if (total_count > 0) out[n] = t_cast(h->tkind, gyo_bucket_max_threshold(h->cls, h->tkind, nb));
+		else out[n] = t_cast(h->tkind, gyo_bucket_max_threshold(h->cls, h->tkind, 0));
+	}
+}
+
+int gyo_hist_run(int cls, int tkind, const int64_t *vals, size_t n, const float *pcts, size_t npct,
+		gyo_serial *out_stats, uint64_t *out_total, int64_t *out_max, int64_t *out_pct, int64_t *out_bucket_ids, float *out_avg)
+{
+	gyo_hist h;
+	int nb = gyo_nbuckets(cls);
+
+	if (nb < 0) return -1;
+	gyo_hist_init(&h, cls, tkind);
+	for (size_t i = 0; i < n; ++i) {
+		int b = gyo_hist_add(&h, vals[i]);
+		if (out_bucket_ids) out_bucket_ids[i] = b;
+	}
+	if (out_stats) memcpy(out_stats, h.stats, sizeof(gyo_serial) * (size_t)nb);
+	if (out_total) *out_total = h.total_count;
+	if (out_max) *out_max = h.max_val;
+	if (npct) gyo_hist_percentiles(&h, pcts, npct, out_pct, out_avg);
+	return nb;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * count-min and HyperLogLog definitions (ours; PARITY UNPINNED — no reference implementation exists)
+ * hash family: the reference's jhash_2words over the two halves of the key with row-salted initval
+ * ------------------------------------------------------------------------------------------------ */
+#define HLL_SEED_A	(GY_SEED ^ 0xa5a5a5a5u)
+#define HLL_SEED_B	(GY_SEED ^ 0x5a5a5a5au)
+
+uint32_t gyo_cms_index(uint64_t flow_key, uint32_t row, uint32_t log2_width)
+{
+	uint32_t h = gyo_jhash_2words((uint32_t)flow_key, (uint32_t)(flow_key >> 32), GY_SEED + GOLDEN * (row + 1));
+
+	return h & ((1u << log2_width) - 1);
+}
+
+/* one 64-bit cell = {count: low 32, kbytes: high 32}; a single 64-bit add updates both. The count half
+ * would have to exceed 2^32 events on one cell inside one window before it could carry into kbytes. */
+uint64_t gyo_cms_increment(uint32_t bytes)
+{
+	return 1ull | ((uint64_t)(bytes >> 10) << 32);
+}
+
+uint64_t gyo_hll_hash(uint64_t flow_key)
+{
+	uint32_t lo = (uint32_t)flow_key, hi = (uint32_t)(flow_key >> 32);
+
+	return ((uint64_t)gyo_jhash_2words(lo, hi, HLL_SEED_A) << 32) | gyo_jhash_2words(lo, hi, HLL_SEED_B);
+}
+
+void gyo_hll_idx_rank(uint64_t flow_key, uint32_t p, uint32_t *idx, uint8_t *rank)
+{
+	uint64_t h = gyo_hll_hash(flow_key);
+	uint64_t w = h << p;
+
+	*idx = (uint32_t)(h >> (64 - p));
+	*rank = (uint8_t)(w ? (uint32_t)(__builtin_clzll(w) + 1) : (64u - p + 1u));
+}
+
+/* Flajolet et al. 2007 raw estimator + linear counting for the small range; 64-bit hash => no large-range
+ * correction. Computed from the register-value histogram in a fixed order so that every implementation
+ * (this file, the host side of libgysketch.so) produces the identical double. */
+double gyo_hll_estimate(const uint8_t *regs, uint32_t p)
+{
+	const uint32_t	m = 1u << p;
+	uint32_t	hist[66] = {0};
+	double		sum = 0, alpha, e;
+
+	for (uint32_t i = 0; i < m; ++i) hist[regs[i] > 65 ? 65 : regs[i]]++;
+	for (int r = 65; r >= 0; --r) sum += (double)hist[r] * ldexp(1.0, -r);
+
+	if (m == 16) alpha = 0.673; else if (m == 32) alpha = 0.697; else if (m == 64) alpha = 0.709;
+	else alpha = 0.7213 / (1.0 + 1.079 / (double)m);
+
+	e = alpha * (double)m * (double)m / sum;
+	if (e <= 2.5 * (double)m && hist[0]) e = (double)m * log((double)m / (double)hist[0]);
+	return e;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * t-digest (PARITY UNPINNED). Published algorithm: T. Dunning, "The t-digest: efficient estimates of
+ * distributions" — merging variant, scale function K_1: k(q) = delta/(2 pi) asin(2q - 1).
+ * The reference only fixes delta = 100 (public.tdigest(x, 100), common/gy_query_common.cc:1855).
+ * ------------------------------------------------------------------------------------------------ */
+static inline double td_k(double q, double delta)
+{
+	return delta / (2.0 * M_PI) * asin(2.0 * q - 1.0);
+}
+
+static inline double td_q(double k, double delta)
+{
+	if (k >= delta / 4.0) return 1.0;
+	return (sin(k * 2.0 * M_PI / delta) + 1.0) / 2.0;
+}
+
+void gyo_td_init(gyo_tdigest *t)
+{
+	memset(t, 0, sizeof(*t));
+	t->minv = INFINITY; t->maxv = -INFINITY;
+}
+
+/* greedy pass over centroids sorted by mean. A cluster that starts after weight P absorbs items while the
+ * running total stays <= W * q(k(P/W) + 1); it always takes at least its first item. Cluster mean is
+ * sum(mean*weight)/sum(weight) accumulated in double in input order. */
+uint32_t gyo_td_compress(const gyo_centroid *in, uint32_t n, double delta, gyo_centroid *out, uint32_t cap)
+{
+	uint64_t W = 0, wsofar = 0, cw;
+	uint32_t nout = 0;
+	double csum, wlimit;
+
+	if (!n) return 0;
+	for (uint32_t i = 0; i < n; ++i) W += in[i].weight;
+
+	wlimit = (double)W * td_q(td_k(0.0, delta) + 1.0, delta);
+	cw = in[0].weight; csum = in[0].mean * (double)in[0].weight;
+
+	for (uint32_t i = 1; i < n; ++i) {
+		double projected = (double)(wsofar + cw + in[i].weight);
+
+		if (projected <= wlimit) {
+			cw += in[i].weight;
+			csum += in[i].mean * (double)in[i].weight;
+		}
+		else {
+			if (nout < cap) { out[nout].mean = csum / (double)cw; out[nout].weight = cw; }
+			nout++;
+			wsofar += cw;
+			wlimit = (double)W * td_q(td_k((double)wsofar / (double)W, delta) + 1.0, delta);
+			cw = in[i].weight; csum = in[i].mean * (double)in[i].weight;
+		}
+	}
+	if (nout < cap) { out[nout].mean = csum / (double)cw; out[nout].weight = cw; }
+	nout++;
+	return nout;
+}
+
+static int cmp_u32(const void *a, const void *b)
+{
+	uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+	return x < y ? -1 : (x > y);
+}
+
+/* stable merge of two mean-sorted centroid lists; on equal means the `a` list goes first */
+static uint32_t merge_sorted(const gyo_centroid *a, uint32_t na, const gyo_centroid *b, uint32_t nb, gyo_centroid *out)
+{
+	uint32_t i = 0, j = 0, k = 0;
+
+	while (i < na && j < nb) out[k++] = (b[j].mean < a[i].mean) ? b[j++] : a[i++];
+	while (i < na) out[k++] = a[i++];
+	while (j < nb) out[k++] = b[j++];
+	return k;
+}
+
+/* What the CUDA path does for one device batch: (1) sort the service's new samples, cluster them with the greedy
+ * rule (unit weights; cluster sums are exact integers), (2) merge new clusters with the old centroids and
+ * compress again. */
+void gyo_td_add_batch(gyo_tdigest *t, const uint32_t *vals, uint32_t n, double delta)
+{
+	if (!n) return;
+
+	uint32_t	*sv = (uint32_t *)malloc(sizeof(uint32_t) * n);
+	gyo_centroid	newc[GYO_TD_CAP], merged[2 * GYO_TD_CAP], outc[GYO_TD_CAP];
+	uint32_t	nnew = 0, s = 0;
+
+	memcpy(sv, vals, sizeof(uint32_t) * n);
+	qsort(sv, n, sizeof(uint32_t), cmp_u32);
+
+	/* greedy clustering of n unit weights: cluster [s, e), e = max(s + 1, floor(W q(k(s/W) + 1))) */
+	while (s < n) {
+		double wlimit = (double)n * td_q(td_k((double)s / (double)n, delta) + 1.0, delta);
+		uint64_t e = (uint64_t)floor(wlimit);
+		uint64_t sum = 0;
+
+		if (e > n) e = n;
+		if (e < s + 1) e = s + 1;
+		for (uint64_t i = s; i < e; ++i) sum += sv[i];
+		if (nnew < GYO_TD_CAP) { newc[nnew].mean = (double)sum / (double)(e - s); newc[nnew].weight = e - s; }
+		nnew++;
+		s = (uint32_t)e;
+	}
+	if (nnew > GYO_TD_CAP) nnew = GYO_TD_CAP;	/* cannot happen for delta <= 2*GYO_TD_CAP/... ; asserted in tests */
+
+	if ((double)sv[0] < t->minv) t->minv = (double)sv[0];
+	if ((double)sv[n - 1] > t->maxv) t->maxv = (double)sv[n - 1];
+	free(sv);
+
+	uint32_t nm = merge_sorted(t->c, t->n, newc, nnew, merged);
+	uint32_t no = gyo_td_compress(merged, nm, delta, outc, GYO_TD_CAP);
+
+	if (no > GYO_TD_CAP) no = GYO_TD_CAP;
+	memcpy(t->c, outc, sizeof(gyo_centroid) * no);
+	t->n = no;
+	t->total += n;
+}
+
+/* classic MergingDigest: buffer 5*delta raw points, then sort buffer, merge with centroids, compress */
+void gyo_td_add_classic(gyo_tdigest *t, const uint32_t *vals, uint32_t n, double delta)
+{
+	uint32_t bufcap = (uint32_t)(5 * delta);
+	gyo_centroid *buf = (gyo_centroid *)malloc(sizeof(gyo_centroid) * (bufcap + 2 * GYO_TD_CAP));
+	gyo_centroid *tmp = (gyo_centroid *)malloc(sizeof(gyo_centroid) * (bufcap + 2 * GYO_TD_CAP));
+	uint32_t *chunk = (uint32_t *)malloc(sizeof(uint32_t) * bufcap);
+	gyo_centroid outc[GYO_TD_CAP];
+
+	for (uint32_t off = 0; off < n; off += bufcap) {
+		uint32_t m = n - off < bufcap ? n - off : bufcap;
+
+		memcpy(chunk, vals + off, sizeof(uint32_t) * m);
+		qsort(chunk, m, sizeof(uint32_t), cmp_u32);
+		for (uint32_t i = 0; i < m; ++i) { buf[i].mean = (double)chunk[i]; buf[i].weight = 1; }
+		if ((double)chunk[0] < t->minv) t->minv = (double)chunk[0];
+		if ((double)chunk[m - 1] > t->maxv) t->maxv = (double)chunk[m - 1];
+
+		uint32_t nm = merge_sorted(t->c, t->n, buf, m, tmp);
+		uint32_t no = gyo_td_compress(tmp, nm, delta, outc, GYO_TD_CAP);
+
+		if (no > GYO_TD_CAP) no = GYO_TD_CAP;
+		memcpy(t->c, outc, sizeof(gyo_centroid) * no);
+		t->n = no;
+		t->total += m;
+	}
+	free(buf); free(tmp); free(chunk);
+}
+
+/* quantile by linear interpolation between centroid centres (centre of centroid i sits at cumulative weight
+ * W_{i-1} + w_i/2); the two ends interpolate towards the tracked min / max. */
+double gyo_td_quantile(const gyo_centroid *c, uint32_t n, double minv, double maxv, double q)
+{
+	double total = 0, target, cum = 0, prev_center, prev_mean;
+
+	if (!n) return NAN;
+	for (uint32_t i = 0; i < n; ++i) total += (double)c[i].weight;
+	if (q <= 0) return minv;
+	if (q >= 1) return maxv;
+	target = q * total;
+
+	prev_center = 0; prev_mean = minv;
+	for (uint32_t i = 0; i < n; ++i) {
+		double center = cum + (double)c[i].weight / 2.0;
+
+		if (target < center) {
+			double span = center - prev_center;
+			return span > 0 ? prev_mean + (c[i].mean - prev_mean) * ((target - prev_center) / span) : c[i].mean;
+		}
+		prev_center = center; prev_mean = c[i].mean;
+		cum += (double)c[i].weight;
+	}
+	{
+		double span = total - prev_center;
+		return span > 0 ? prev_mean + (maxv - prev_mean) * ((target - prev_center) / span) : maxv;
+	}
+}
+
+double gyo_td_quantile_f(const float *means, const float *weights, uint32_t n, float minv, float maxv, double q)
+{
+	gyo_centroid c[2 * GYO_TD_CAP];
+
+	if (n > 2 * GYO_TD_CAP) n = 2 * GYO_TD_CAP;
+	for (uint32_t i = 0; i < n; ++i) { c[i].mean = means[i]; c[i].weight = (uint64_t)weights[i]; }
+	return gyo_td_quantile(c, n, minv, maxv, q);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * engine-level oracle: sequential fold of the 32-byte event stream into the same state the CUDA engine keeps.
+ * Semantics per event type are those of include/gysketch.h; each follows the reference code cited there.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct svc_state
+{
+	uint64_t	id;
+	gyo_hist	cur, last, all;		/* RESP_TIME_HASH, T = int64 */
+	uint64_t	conn_cur, conn_last;	/* packed {count, kbytes} like a CMS cell */
+	uint64_t	conn_all_cnt, conn_all_kb;
+	uint8_t		*hll;
+	gyo_tdigest	td;
+	uint32_t	*pend;			/* RESP samples (usec) of the batch being ingested */
+	uint32_t	npend, cappend;
+} svc_state;
+
+typedef struct task_state
+{
+	uint64_t	id;
+	gyo_hist	cpu_pct, cpu_delay, blkio_delay;	/* MTASK_HIST, server/gy_msocket.h:704-718 */
+} task_state;
+
+typedef struct idmap { uint64_t *keys; uint32_t *vals; uint32_t cap, n; } idmap;
+
+struct gyo_engine
+{
+	uint32_t	max_svcs, max_tasks, depth, log2w, hll_p, flags, rank, world;
+	double		delta;
+	idmap		smap, tmap;
+	svc_state	*svcs;
+	task_state	*tasks;
+	uint64_t	*cms_cur, *cms_last;
+	uint64_t	n_in, n_drop, n_resp, n_tcp, n_task, n_foreign;
+};
+
+static uint32_t pow2_at_least(uint32_t v) { uint32_t p = 16; while (p < v) p <<= 1; return p; }
+
+static void idmap_init(idmap *m, uint32_t maxn)
+{
+	m->cap = pow2_at_least(maxn * 2);
+	m->keys = (uint64_t *)calloc(m->cap, sizeof(uint64_t));
+	m->vals = (uint32_t *)calloc(m->cap, sizeof(uint32_t));
+	m->n = 0;
+}
+
+/* open addressing keyed by get_uint64_hash (how the reference keys listen_tbl_, gy_mconnhdlr.cc:11183) */
+static int idmap_find(idmap *m, uint64_t key, int insert, uint32_t maxn)
+{
+	uint32_t pos = gyo_uint64_hash(key) & (m->cap - 1);
+
+	for (;;) {
+		if (m->keys[pos] == key) return (int)m->vals[pos];
+		if (m->keys[pos] == 0) {
+			if (!insert || m->n >= maxn) return -1;
+			m->keys[pos] = key; m->vals[pos] = m->n;
+			return (int)m->n++;
+		}
+		pos = (pos + 1) & (m->cap - 1);
+	}
+}
+
+gyo_engine *gyo_create(uint32_t max_svcs, uint32_t max_tasks, uint32_t cms_depth, uint32_t cms_log2_width, uint32_t hll_p,
+		uint32_t td_compression, uint32_t flags, uint32_t rank, uint32_t world)
+{
+	gyo_engine *e = (gyo_engine *)calloc(1, sizeof(*e));
+
+	e->max_svcs = max_svcs; e->max_tasks = max_tasks; e->depth = cms_depth; e->log2w = cms_log2_width;
+	e->hll_p = hll_p; e->delta = td_compression; e->flags = flags; e->rank = rank; e->world = world ? world : 1;
+	idmap_init(&e->smap, max_svcs);
+	idmap_init(&e->tmap, max_tasks ? max_tasks : 1);
+	e->svcs = (svc_state *)calloc(max_svcs, sizeof(svc_state));
+	e->tasks = (task_state *)calloc(max_tasks ? max_tasks : 1, sizeof(task_state));
+	e->cms_cur = (uint64_t *)calloc((size_t)cms_depth << cms_log2_width, sizeof(uint64_t));
+	e->cms_last = (uint64_t *)calloc((size_t)cms_depth << cms_log2_width, sizeof(uint64_t));
+	return e;
+}
+
+void gyo_destroy(gyo_engine *e)
+{
+	if (!e) return;
+	for (uint32_t i = 0; i < e->smap.n; ++i) { free(e->svcs[i].hll); free(e->svcs[i].pend); }
+	free(e->svcs); free(e->tasks); free(e->cms_cur); free(e->cms_last);
+	free(e->smap.keys); free(e->smap.vals); free(e->tmap.keys); free(e->tmap.vals);
+	free(e);
+}
+
+static svc_state *get_svc(gyo_engine *e, uint64_t id, int insert)
+{
+	uint32_t before = e->smap.n;
+	int slot = idmap_find(&e->smap, id, insert, e->max_svcs);
+
+	if (slot < 0) return NULL;
+	svc_state *s = &e->svcs[slot];
+	if ((uint32_t)slot >= before) {
+		s->id = id;
+		gyo_hist_init(&s->cur, GYO_CLS_RESP_TIME, GYO_T_INT64);
+		gyo_hist_init(&s->last, GYO_CLS_RESP_TIME, GYO_T_INT64);
+		gyo_hist_init(&s->all, GYO_CLS_RESP_TIME, GYO_T_INT64);
+		s->hll = (uint8_t *)calloc(1u << e->hll_p, 1);
+		gyo_td_init(&s->td);
+	}
+	return s;
+}
+
+static task_state *get_task(gyo_engine *e, uint64_t id, int insert)
+{
+	uint32_t before = e->tmap.n;
+	int slot = idmap_find(&e->tmap, id, insert, e->max_tasks);
+
+	if (slot < 0) return NULL;
+	task_state *t = &e->tasks[slot];
+	if ((uint32_t)slot >= before) {
+		t->id = id;
+		gyo_hist_init(&t->cpu_pct, GYO_CLS_HASH_1_3000, GYO_T_INT);
+		gyo_hist_init(&t->cpu_delay, GYO_CLS_DURATION, GYO_T_INT);
+		gyo_hist_init(&t->blkio_delay, GYO_CLS_DURATION, GYO_T_INT);
+	}
+	return t;
+}
+
+int gyo_register_ids(gyo_engine *e, const uint64_t *ids, uint32_t n, int is_task)
+{
+	for (uint32_t i = 0; i < n; ++i) {
+		if (!ids[i]) continue;
+		if (is_task ? !get_task(e, ids[i], 1) : !get_svc(e, ids[i], 1)) return -28;
+	}
+	return 0;
+}
+
+int gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n)
+{
+	const int autoreg = (int)(e->flags & 1u);
+	const uint32_t wmask = (1u << e->log2w) - 1;
+
+	for (uint64_t i = 0; i < n; ++i) {
+		const gyo_event *p = &ev[i];
+
+		if (e->world > 1 && (p->host_idx % e->world) != e->rank) { e->n_foreign++; continue; }
+		e->n_in++;
+		if (p->svc_id == 0) { e->n_drop++; continue; }
+
+		switch (p->type) {
+
+		case 5 : {	/* RESP: SVC_INFO_CAP::upd_stats_on_req gy_proto_parser.cc:2678 (usec/1000 -> resp_cache_.add_cache);
+				   validity rule of handle_ipv4_resp_event gy_socket_stat.cc:1519-1524 (drop > 1 000 000 msec) */
+			uint32_t ms = p->value / 1000u;
+			if (ms > 1000000u) { e->n_drop++; break; }
+			svc_state *s = get_svc(e, p->svc_id, autoreg);
+			if (!s) { e->n_drop++; break; }
+			gyo_hist_add(&s->cur, (int64_t)ms);
+			if (s->npend == s->cappend) {
+				s->cappend = s->cappend ? s->cappend * 2 : 16;
+				s->pend = (uint32_t *)realloc(s->pend, sizeof(uint32_t) * s->cappend);
+			}
+			s->pend[s->npend++] = p->value;
+			e->n_resp++;
+			break;
+		}
+
+		case 1 : case 2 : case 3 : case 4 : {	/* TCP connect/accept/close: group-by of partha_tcp_conn_info gy_mconnhdlr.cc:9245-9311
+							   approximated by CMS(flow) + HLL(svc) + an exact per-service cell */
+			svc_state *s = get_svc(e, p->svc_id, autoreg);
+			if (!s) { e->n_drop++; break; }
+			uint64_t inc = gyo_cms_increment(p->value);
+			for (uint32_t r = 0; r < e->depth; ++r) {
+				e->cms_cur[((size_t)r << e->log2w) + (gyo_cms_index(p->flow_key, r, e->log2w) & wmask)] += inc;
+			}
+			uint32_t idx; uint8_t rank;
+			gyo_hll_idx_rank(p->flow_key, e->hll_p, &idx, &rank);
+			if (s->hll[idx] < rank) s->hll[idx] = rank;
+			s->conn_cur += inc;
+			e->n_tcp++;
+			break;
+		}
+
+		case 6 : {	/* TASK: MAGGR_TASK::set_local_task_state server/gy_msocket.h:1009-1018 */
+			task_state *t = get_task(e, p->svc_id, autoreg);
+			if (!t) { e->n_drop++; break; }
+			gyo_hist_add(&t->cpu_pct, (int64_t)(int)p->value);
+			gyo_hist_add(&t->cpu_delay, (int64_t)(int)(uint32_t)(p->flow_key & 0xFFFFFFFFu));
+			gyo_hist_add(&t->blkio_delay, (int64_t)(int)(uint32_t)(p->flow_key >> 32));
+			e->n_task++;
+			break;
+		}
+
+		default :
+			e->n_drop++;
+			break;
+		}
+	}
+
+	/* end of device batch: batched t-digest update per touched service */
+	for (uint32_t i = 0; i < e->smap.n; ++i) {
+		svc_state *s = &e->svcs[i];
+		if (s->npend) {
+			gyo_td_add_batch(&s->td, s->pend, s->npend, e->delta);
+			s->npend = 0;
+		}
+	}
+	return 0;
+}
+
+/* 5-second roll: listener_stats_update gy_socket_stat.cc:3898 reads the window that just closed, then the
+ * window restarts; the all-time level keeps accumulating (Level_5s_5min_5days_all, gy_statistics.h:1548) */
+void gyo_flush(gyo_engine *e, uint32_t tsec)
+{
+	(void)tsec;
+	for (uint32_t i = 0; i < e->smap.n; ++i) {
+		svc_state *s = &e->svcs[i];
+
+		s->last = s->cur;
+		gyo_hist_merge(&s->all, &s->cur);
+		gyo_hist_init(&s->cur, GYO_CLS_RESP_TIME, GYO_T_INT64);
+		s->conn_last = s->conn_cur;
+		s->conn_all_cnt += (uint32_t)s->conn_cur;
+		s->conn_all_kb += s->conn_cur >> 32;
+		s->conn_cur = 0;
+	}
+	uint64_t *t = e->cms_last; e->cms_last = e->cms_cur; e->cms_cur = t;
+	memset(e->cms_cur, 0, sizeof(uint64_t) * ((size_t)e->depth << e->log2w));
+}
+
+int gyo_export_hist(gyo_engine *e, uint64_t id, int which, gyo_serial *out15, uint64_t *total, int64_t *maxv)
+{
+	const gyo_hist *h = NULL;
+
+	if (which <= 2) {
+		int slot = idmap_find(&e->smap, id, 0, 0);
+		if (slot < 0) return -2;
+		h = which == 0 ? &e->svcs[slot].cur : (which == 1 ? &e->svcs[slot].last : &e->svcs[slot].all);
+	}
+	else {
+		int slot = idmap_find(&e->tmap, id, 0, 0);
+		if (slot < 0) return -2;
+		h = which == 3 ? &e->tasks[slot].cpu_pct : (which == 4 ? &e->tasks[slot].cpu_delay : &e->tasks[slot].blkio_delay);
+	}
+	memset(out15, 0, sizeof(gyo_serial) * 15);
+	memcpy(out15, h->stats, sizeof(gyo_serial) * (size_t)gyo_nbuckets(h->cls));
+	*total = h->total_count; *maxv = h->max_val;
+	return 0;
+}
+
+int gyo_export_hll(gyo_engine *e, uint64_t id, uint8_t *regs)
+{
+	int slot = idmap_find(&e->smap, id, 0, 0);
+	if (slot < 0) return -2;
+	memcpy(regs, e->svcs[slot].hll, 1u << e->hll_p);
+	return 0;
+}
+
+int gyo_export_tdigest(gyo_engine *e, uint64_t id, gyo_tdigest *out)
+{
+	int slot = idmap_find(&e->smap, id, 0, 0);
+	if (slot < 0) return -2;
+	*out = e->svcs[slot].td;
+	return 0;
+}
+
+int gyo_export_conn(gyo_engine *e, uint64_t id, uint64_t *cur, uint64_t *last, uint64_t *all_cnt, uint64_t *all_kb)
+{
+	int slot = idmap_find(&e->smap, id, 0, 0);
+	if (slot < 0) return -2;
+	*cur = e->svcs[slot].conn_cur; *last = e->svcs[slot].conn_last;
+	*all_cnt = e->svcs[slot].conn_all_cnt; *all_kb = e->svcs[slot].conn_all_kb;
+	return 0;
+}
+
+const uint64_t *gyo_cms_table(gyo_engine *e, int last_window)
+{
+	return last_window ? e->cms_last : e->cms_cur;
+}
+
+void gyo_counters(gyo_engine *e, uint64_t out[8])
+{
+	out[0] = e->n_in; out[1] = e->n_drop; out[2] = e->n_resp; out[3] = e->n_tcp; out[4] = e->n_task;
+	out[5] = e->smap.n; out[6] = e->tmap.n; out[7] = e->n_foreign;
+}
+
+/* additive merge of a peer shard: histogram sums (update_from_serialized), CMS sums, HLL max — the CPU statement
+ * of the NCCL merge step; mirrors STATE_ONE::add_stats common/gy_comm_proto.h:3199-3214 */
+void gyo_merge_from(gyo_engine *dst, const gyo_engine *src)
+{
+	size_t ncell = (size_t)dst->depth << dst->log2w;
+
+	for (size_t i = 0; i < ncell; ++i) { dst->cms_cur[i] += src->cms_cur[i]; dst->cms_last[i] += src->cms_last[i]; }
+
+	for (uint32_t i = 0; i < src->smap.n; ++i) {
+		const svc_state *s = &src->svcs[i];
+		svc_state *d = get_svc(dst, s->id, 1);
+		if (!d) continue;
+		gyo_hist_merge(&d->cur, &s->cur); gyo_hist_merge(&d->last, &s->last); gyo_hist_merge(&d->all, &s->all);
+		d->conn_cur += s->conn_cur; d->conn_last += s->conn_last;
+		d->conn_all_cnt += s->conn_all_cnt; d->conn_all_kb += s->conn_all_kb;
+		for (uint32_t r = 0; r < (1u << dst->hll_p); ++r) if (d->hll[r] < s->hll[r]) d->hll[r] = s->hll[r];
+		/* t-digest: rank-ascending merge = concatenate sorted centroid lists, compress */
+		gyo_centroid merged[2 * GYO_TD_CAP], outc[GYO_TD_CAP];
+		uint32_t nm = merge_sorted(d->td.c, d->td.n, s->td.c, s->td.n, merged);
+		uint32_t no = gyo_td_compress(merged, nm, dst->delta, outc, GYO_TD_CAP);
+		if (no > GYO_TD_CAP) no = GYO_TD_CAP;
+		memcpy(d->td.c, outc, sizeof(gyo_centroid) * no);
+		d->td.n = no; d->td.total += s->td.total;
+		if (s->td.minv < d->td.minv) d->td.minv = s->td.minv;
+		if (s->td.maxv > d->td.maxv) d->td.maxv = s->td.maxv;
+	}
+	for (uint32_t i = 0; i < src->tmap.n; ++i) {
+		const task_state *s = &src->tasks[i];
+		task_state *d = get_task(dst, s->id, 1);
+		if (!d) continue;
+		gyo_hist_merge(&d->cpu_pct, &s->cpu_pct); gyo_hist_merge(&d->cpu_delay, &s->cpu_delay);
+		gyo_hist_merge(&d->blkio_delay, &s->blkio_delay);
+	}
+}
+
+/* ---- CPU baseline: one engine + one pre-sharded event array per thread, no shared state ---- */
+typedef struct bench_arg { gyo_engine *e; const gyo_event *ev; uint64_t n, batch; } bench_arg;
+
+static void *bench_thread(void *p)
+{
+	bench_arg *a = (bench_arg *)p;
+
+	for (uint64_t off = 0; off < a->n; off += a->batch) {
+		uint64_t m = a->n - off < a->batch ? a->n - off : a->batch;
+		gyo_ingest(a->e, a->ev + off, m);
+	}
+	return NULL;
+}
+
+double gyo_bench_ingest(gyo_engine **engines, const gyo_event **shards, const uint64_t *counts, int nthreads, uint64_t batch)
+{
+	pthread_t	*th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+	bench_arg	*args = (bench_arg *)malloc(sizeof(bench_arg) * (size_t)nthreads);
+	struct timespec	t0, t1;
+
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int t = 0; t < nthreads; ++t) {
+		args[t].e = engines[t]; args[t].ev = shards[t]; args[t].n = counts[t]; args[t].batch = batch ? batch : counts[t] + 1;
+		pthread_create(&th[t], NULL, bench_thread, &args[t]);
+	}
+	for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	free(th); free(args);
+	return (double)(t1.tv_sec - t0.tv_sec) + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-9;
+}

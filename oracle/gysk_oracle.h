@@ -1,0 +1,126 @@
+/*
+ * gysk_oracle.h — TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C) of the algorithms on the hot path of include/gysketch.h. Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library;
+ * the product (libgysketch.so) never links, loads or calls it.
+ *
+ * Pinning (see oracle/README.md):
+ *   - jhash, bucket hashes, GY_HISTOGRAM add/merge/percentiles: pinned against the reference's own asserted
+ *     fixture test/test_histogram.cc:29-147 and against outputs of the reference compiled here (oracle/_ref).
+ *   - count-min, HyperLogLog, t-digest: the reference has no implementation and no test vector for them
+ *       =>  PARITY UNPINNED for these three; they are definitions, stated here, that the
+ *     CUDA path must reproduce bit-exactly (CMS cells, HLL registers) or within epsilon (t-digest quantiles).
+ */
+#ifndef GYSK_ORACLE_H
+#define GYSK_ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* histogram classes: ids 0..7 equal GYSK_CLS_* of include/gysketch.h; 8,9 are the two FIXED_DIFF_HASH
+ * instantiations asserted in test/test_histogram.cc */
+enum {
+	GYO_CLS_RESP_TIME = 0, GYO_CLS_SEMI_LOG, GYO_CLS_SEMI_LOG_LO, GYO_CLS_DURATION, GYO_CLS_HASH_10_5000,
+	GYO_CLS_HASH_5_250, GYO_CLS_HASH_1_3000, GYO_CLS_PERCENT, GYO_CLS_FD_I8_9_26_5, GYO_CLS_FD_INT_M15_M3_4, GYO_CLS_MAX
+};
+
+/* value type T of GY_HISTOGRAM<T, Hash> */
+enum { GYO_T_INT64 = 0, GYO_T_INT = 1, GYO_T_INT8 = 2 };
+
+#define GYO_MAX_BUCKETS		16
+
+typedef struct gyo_serial { uint64_t count; int64_t sum; } gyo_serial;	/* == HIST_SERIAL */
+
+typedef struct gyo_hist
+{
+	gyo_serial	stats[GYO_MAX_BUCKETS];
+	uint64_t	total_count;
+	int64_t		max_val;
+	int32_t		cls, tkind;
+} gyo_hist;
+
+typedef struct gyo_event		/* == gysk_event */
+{
+	uint64_t	svc_id, flow_key;
+	uint32_t	value, host_idx, tsec;
+	uint16_t	type, flags;
+} gyo_event;
+
+typedef struct gyo_centroid { double mean; uint64_t weight; } gyo_centroid;
+
+#define GYO_TD_CAP		128
+
+typedef struct gyo_tdigest
+{
+	gyo_centroid	c[GYO_TD_CAP];
+	uint32_t	n;
+	uint64_t	total;
+	double		minv, maxv;
+} gyo_tdigest;
+
+/* ---- jhash (Bob Jenkins lookup2 as used by the reference, common/jhash.h:22-140) ---- */
+uint32_t gyo_jhash_3words(uint32_t a, uint32_t b, uint32_t c, uint32_t initval);
+uint32_t gyo_jhash_2words(uint32_t a, uint32_t b, uint32_t initval);
+uint32_t gyo_jhash2(const uint32_t *k, uint32_t length, uint32_t initval);
+uint32_t gyo_jhash(const void *key, uint32_t length, uint32_t initval);
+uint32_t gyo_uint64_hash(uint64_t key);			/* common/gy_common_inc.h:1120 */
+
+/* ---- bucket hashes + GY_HISTOGRAM (common/gy_statistics.h:455-894, 1565-2063) ---- */
+int	gyo_nbuckets(int cls);
+int	gyo_bucket(int cls, int64_t value);		/* HashClass::operator() incl. the (int) truncation of :1748 etc. */
+int64_t	gyo_bucket_max_threshold(int cls, int tkind, size_t id);	/* :500-515 */
+void	gyo_hist_init(gyo_hist *h, int cls, int tkind);
+int	gyo_hist_add(gyo_hist *h, int64_t value);	/* add_data :596-623, returns bucket */
+void	gyo_hist_merge(gyo_hist *dst, const gyo_hist *src);	/* update_from_serialized :625-650 */
+void	gyo_hist_percentiles(const gyo_hist *h, const float *pcts, size_t npct, int64_t *out, float *avg);	/* :707-791 */
+/* convenience: run a fresh histogram over vals */
+int	gyo_hist_run(int cls, int tkind, const int64_t *vals, size_t n, const float *pcts, size_t npct,
+		gyo_serial *out_stats, uint64_t *out_total, int64_t *out_max, int64_t *out_pct, int64_t *out_bucket_ids, float *out_avg);
+
+/* ---- sketch definitions (ours; parity unpinned) ---- */
+uint32_t gyo_cms_index(uint64_t flow_key, uint32_t row, uint32_t log2_width);
+uint64_t gyo_cms_increment(uint32_t bytes);		/* 1 | (bytes >> 10) << 32 */
+uint64_t gyo_hll_hash(uint64_t flow_key);
+void	gyo_hll_idx_rank(uint64_t flow_key, uint32_t p, uint32_t *idx, uint8_t *rank);
+double	gyo_hll_estimate(const uint8_t *regs, uint32_t p);
+
+void	gyo_td_init(gyo_tdigest *t);
+/* Dunning's merging t-digest, K_1 scale k(q) = delta/(2 pi) asin(2q-1): greedy single pass over sorted centroids */
+uint32_t gyo_td_compress(const gyo_centroid *sorted_in, uint32_t n, double delta, gyo_centroid *out, uint32_t cap);
+/* batched update = what the CUDA path does per device batch: cluster the batch's sorted samples, then merge
+ * the new clusters with the old centroids */
+void	gyo_td_add_batch(gyo_tdigest *t, const uint32_t *vals, uint32_t n, double delta);
+/* classic buffered MergingDigest (buffer of 5*delta points) — the "reference CPU path" for epsilon parity */
+void	gyo_td_add_classic(gyo_tdigest *t, const uint32_t *vals, uint32_t n, double delta);
+double	gyo_td_quantile(const gyo_centroid *c, uint32_t n, double minv, double maxv, double q);
+double	gyo_td_quantile_f(const float *means, const float *weights, uint32_t n, float minv, float maxv, double q);
+
+/* ---- engine-level oracle over the 32-byte event stream ---- */
+typedef struct gyo_engine gyo_engine;
+
+gyo_engine *gyo_create(uint32_t max_svcs, uint32_t max_tasks, uint32_t cms_depth, uint32_t cms_log2_width, uint32_t hll_p,
+		uint32_t td_compression, uint32_t flags, uint32_t rank, uint32_t world);
+void	gyo_destroy(gyo_engine *e);
+int	gyo_register_ids(gyo_engine *e, const uint64_t *ids, uint32_t n, int is_task);
+int	gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n);	/* one device batch */
+void	gyo_flush(gyo_engine *e, uint32_t tsec);
+int	gyo_export_hist(gyo_engine *e, uint64_t id, int which, gyo_serial *out15, uint64_t *total, int64_t *maxv);
+int	gyo_export_hll(gyo_engine *e, uint64_t id, uint8_t *regs);
+int	gyo_export_tdigest(gyo_engine *e, uint64_t id, gyo_tdigest *out);
+int	gyo_export_conn(gyo_engine *e, uint64_t id, uint64_t *cur, uint64_t *last, uint64_t *all_cnt, uint64_t *all_kb);
+const uint64_t *gyo_cms_table(gyo_engine *e, int last_window);
+void	gyo_counters(gyo_engine *e, uint64_t out[8]);	/* in, dropped, resp, tcp, task, nsvcs, ntasks, foreign */
+void	gyo_merge_from(gyo_engine *dst, const gyo_engine *src);	/* additive roll-up of a peer shard (hist sum, cms sum, hll max) */
+
+/* CPU baseline: nthreads engines each ingest their own pre-sharded event array; returns wall seconds */
+double	gyo_bench_ingest(gyo_engine **engines, const gyo_event **shards, const uint64_t *counts, int nthreads, uint64_t batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
