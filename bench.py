@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — events/sec aggregated by the B200 streaming-sketch engine (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # product arm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on this box's host cores
+
+One STEP = one pass of the hot path over one batch of synthetic events (ingest kernel + radix sort + t-digest update,
+plus the sketch-merge collective when N > 1). Workload = BASELINE.json configs[2] ("100 M mixed TCP/syscall events,
+100 K services, t-digest p50/p95/p99 on 1xB200"), the largest single-GPU configuration: per rank EVENTS_PER_STEP
+events of the 70/20/10 RESP/TCP/TASK mix over 100 K services (weak scaling: each rank ingests its own host shard).
+
+`value`  : whole-job events/s with the batch already resident in HBM (device timed, CUDA events, max over ranks).
+`e2e`    : same metric through the C-ABI call a user makes with HOST (page-locked) buffers: H2D inside the timed region,
+           plus a device->host read of per-service summaries.
+`roofline`: dominant kernel, algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle port (all host cores, events pre-sharded by host) on a bounded sample of the same stream.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NSVC = 100_000
+NTASK = 25_000
+NHOSTS = 4096
+NCLIENTS = 1_000_000
+ZIPF_S = 1.05
+# algorithmic bytes per event, SURVEY.md §8(d): RESP 98 = 32 + 32 + 16 + 18(t-digest), TCP 98, TASK 128.
+# split per kernel: the ingest kernel carries everything but the t-digest share.
+BYTES_INGEST = 0.7 * (32 + 32 + 16) + 0.2 * 98 + 0.1 * 128          # 88.4 B / event
+BYTES_TDIGEST = 0.7 * 18                                              # 12.6 B / event
+BYTES_EVENT = BYTES_INGEST + BYTES_TDIGEST                            # 101.0 B / event
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gysketch", choices=["gysketch", "reference"])
+    ap.add_argument("--events", type=int, default=100_000_000, help="events per rank per step")
+    ap.add_argument("--max-batch", type=int, default=1 << 24)
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic stream on the GPU (same formulas as gyeeta_b200/synth.py::gen_mixed)
+# ---------------------------------------------------------------------------------------------------------------
+def gen_events_gpu(torch, n, seed, rank, world, dev):
+    from gyeeta_b200 import synth
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    svc_ids = torch.from_numpy(synth.service_ids(NSVC).view(np.int64)).to(dev)
+    task_ids = torch.from_numpy(synth.task_ids(NTASK).view(np.int64)).to(dev)
+    cdf_s = torch.from_numpy(synth.zipf_cdf(NSVC, ZIPF_S)).to(dev)
+    cdf_t = torch.from_numpy(synth.zipf_cdf(NTASK, ZIPF_S)).to(dev)
+    out = torch.empty((n, 4), dtype=torch.int64, device=dev)
+    chunk = 1 << 23
+    for off in range(0, n, chunk):
+        m = min(chunk, n - off)
+        u = torch.rand(m, generator=g, device=dev, dtype=torch.float64)
+        srank = torch.searchsorted(cdf_s, u).clamp_(max=NSVC - 1)
+        kind = torch.rand(m, generator=g, device=dev)
+        is_resp = kind < 0.70
+        is_task = kind >= 0.90
+        tu = torch.rand(m, generator=g, device=dev)
+        ttype = torch.where(tu < 0.45, 2, torch.where(tu < 0.90, 4, 1))
+        etype = torch.where(is_resp, 5, torch.where(is_task, 6, ttype)).to(torch.int64)
+        trank = torch.searchsorted(cdf_t, torch.rand(m, generator=g, device=dev, dtype=torch.float64)).clamp_(max=NTASK - 1)
+        w0 = torch.where(is_task, task_ids[trank], svc_ids[srank])
+        # client key bound to (service rank % 8) groups; 64-bit mix done with int64 wraparound arithmetic
+        cli = torch.randint(0, NCLIENTS // 8, (m,), generator=g, device=dev, dtype=torch.int64) * 8 + (srank % 8)
+        z = cli + (1 << 48) + (-7046029254386353131)           # 0x9E3779B97F4A7C15 as int64
+        z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * (-4658895280553007687)
+        z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * (-7723592293110705685)
+        flow = z ^ ((z >> 31) & ((1 << 33) - 1))
+        resp_us = torch.exp(torch.randn(m, generator=g, device=dev) * 1.5 + float(np.log(2000.0))).clamp_(max=9.0e8)
+        tcp_b = torch.exp(torch.randn(m, generator=g, device=dev) * 2.0 + float(np.log(4096.0))).clamp_(max=4.0e9)
+        cpu_pct = (torch.rand(m, generator=g, device=dev) * 400.0)
+        value = torch.where(is_resp, resp_us, torch.where(is_task, cpu_pct, tcp_b)).to(torch.int64)
+        cpu_delay = torch.exp(torch.randn(m, generator=g, device=dev) * 2.0 + float(np.log(30.0))).clamp_(max=1.0e5).to(torch.int64)
+        blkio = torch.exp(torch.randn(m, generator=g, device=dev) * 2.5 + float(np.log(5.0))).clamp_(max=1.0e5).to(torch.int64)
+        w1 = torch.where(is_task, cpu_delay | (blkio << 32), flow)
+        # hosts of this rank's shard: host_idx % world == rank
+        host = (srank % (NHOSTS // max(world, 1))) * world + rank
+        out[off: off + m, 0] = w0
+        out[off: off + m, 1] = w1
+        out[off: off + m, 2] = value | (host << 32)
+        out[off: off + m, 3] = 1 | (etype << 32)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_port_rate(ev_np, nthreads, repeat=1):
+    from oracle import pyoracle as po
+    L = po.lib()
+    shards = [np.ascontiguousarray(ev_np[(ev_np["host_idx"] // 1) % nthreads == t]) for t in range(nthreads)]
+    engines = [po.OracleEngine(max_svcs=NSVC + 16, max_tasks=NTASK + 16) for _ in range(nthreads)]
+    eh = (C.c_void_p * nthreads)(*[e.h for e in engines])
+    sp = (C.c_void_p * nthreads)(*[s.ctypes.data for s in shards])
+    cn = (C.c_uint64 * nthreads)(*[len(s) for s in shards])
+    L.gyo_bench_ingest(eh, sp, cn, nthreads, 1 << 22)          # untimed pass: registers every id, faults the state in
+    best = None
+    for _ in range(repeat):
+        sec = L.gyo_bench_ingest(eh, sp, cn, nthreads, 1 << 22)
+        best = sec if best is None else min(best, sec)
+    for e in engines:
+        e.close()
+    return len(ev_np) / best, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gyeeta_b200 import synth
+    from oracle import pyoracle as po
+    po.lib()
+    ncores = os.cpu_count() or 1
+    n = int(min(args.cpu_sample, args.events))
+    rng = np.random.default_rng(3)
+    ev = synth.gen_mixed(rng, n, NSVC, ntask=NTASK, zipf_s=ZIPF_S, nhosts=NHOSTS, nclients=NCLIENTS)
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, sec = cpu_port_rate(ev, ncores)
+        if i >= args.warmup:
+            rates.append((r, sec))
+    rate = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([s for _, s in rates])) * 1e3
+    extra = {}
+    R = po.ref()
+    if R is not None:       # the REFERENCE's own GY_HISTOGRAM::add_data loop (hist part of the path only), for context
+        resp = ev[ev["type"] == 5]
+        _, slots = np.unique(resp["svc_id"], return_inverse=True)
+        slots = slots.astype(np.uint32)
+        vals = (resp["value"] // 1000).astype(np.int64)
+        tot = C.c_uint64()
+        sec = R.gyref_bench_resp_hist(po._p(slots), po._p(vals), len(vals), int(slots.max()) + 1, ncores, C.byref(tot))
+        extra["ref_gy_histogram_add_data_only_events_per_s"] = len(vals) / sec
+    print(json.dumps({
+        "impl": "reference", "metric": "events/sec aggregated", "value": rate, "unit": "events/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[2]: mixed RESP/TCP/TASK 70/20/10, 100K services, bounded sample", "events_per_step": n},
+        "cpu_baseline": {"value": rate, "unit": "events/s", "cores": ncores, "kind": "port",
+                         "sample": f"{n} events of the same stream, pre-sharded by host over {ncores} threads", **extra},
+        "e2e": {"value": rate, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# product arm
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from gyeeta_b200 import engine as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n = args.events
+
+    eng = ge.Engine(device=local, max_svcs=1 << 17, max_tasks=1 << 15, max_batch=args.max_batch, rank=rank, world=world)
+    ev_dev = gen_events_gpu(torch, n, 1234 + rank, rank, world, dev)
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def merge_step():
+        if world > 1:
+            from gyeeta_b200 import dist as gd
+            gd.merge_global(eng, torch, dist)
+
+    def step_device():
+        eng.ingest_device_ptr(ev_dev.data_ptr(), n)
+        merge_step()
+
+    for _ in range(args.warmup):
+        step_device()
+    eng.sync()
+    launches0 = eng.stats()["kernel_launches"]
+    eng.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        t0.record()
+    for _ in range(args.steps):
+        step_device()
+    with torch.cuda.stream(stream):
+        t1.record()
+    eng.sync()
+    barrier()
+    dev_ms = t0.elapsed_time(t1)
+    ms_ing, ms_td, nb = eng.profile_read()
+    eng.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.stats()["kernel_launches"] - launches0
+
+    tms = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    max_ms = float(tms.item())
+    value = world * n * args.steps / (max_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, H2D in the timed region + D2H of summaries --------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
+        host.copy_(ev_dev)
+        torch.cuda.synchronize()
+        qids = ev_dev[:4096, 0].cpu().numpy().view(np.uint64)[:256].copy()
+
+        def step_e2e():
+            eng.ingest_pinned_ptr(host.data_ptr(), n)
+            merge_step()
+            return eng.query_svcs(qids)         # syncs, copies the summaries device -> host
+
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        eng.sync()
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        te = torch.tensor([w1 - w0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * args.steps / float(te.item()), "unit": "events/s",
+               "h2d_bytes_per_step": int(n * 32 + len(qids) * 8), "d2h_bytes_per_step": int(len(qids) * 3400),
+               "timed_with": "host wall clock around the C-ABI calls incl. final sync (max over ranks)"}
+        del host
+
+    # ---- accuracy: t-digest p99 vs exact on the hottest services --------------------------------------------------
+    acc = None
+    if rank == 0:
+        w0col = ev_dev[:, 0]
+        is_resp = ((ev_dev[:, 3] >> 32) & 0xFFFF) == 5
+        hot = torch.unique(w0col[:200_000][is_resp[:200_000]])[:8]
+        errs = []
+        for sid in hot.tolist():
+            vals = (ev_dev[:, 2][(w0col == sid) & is_resp] & 0xFFFFFFFF).double()
+            if vals.numel() < 10_000:
+                continue
+            # each step re-ingested the same batch: the digest holds (warmup+steps+e2e) copies, quantiles are unchanged
+            ex = torch.quantile(vals[: 16_000_000], torch.tensor([0.5, 0.95, 0.99], device=dev, dtype=torch.float64),
+                                interpolation="lower").cpu().numpy()
+            got = eng.quantiles(np.uint64(sid & 0xFFFFFFFFFFFFFFFF), [0.5, 0.95, 0.99])
+            errs.append(np.abs(got - ex) / ex)
+        if errs:
+            e = np.max(np.array(errs), axis=0)
+            acc = {"services_checked": len(errs), "max_rel_err_p50": float(e[0]), "max_rel_err_p95": float(e[1]),
+                   "max_rel_err_p99": float(e[2]), "against": "exact sorted quantile of the same samples"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    nev_total = n * args.steps
+    roof = []
+    for name, ms, bpe in (("ingest_kernel", ms_ing, BYTES_INGEST), ("sort+tdigest chain (rs_hist/scan/rs_scatter/td_*)", ms_td, BYTES_TDIGEST)):
+        if ms > 0:
+            ach = nev_total * bpe / (ms * 1e-3) / 1e9
+            roof.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "ms_total": ms, "launch_groups": nb, "algorithmic_bytes_per_event": bpe, "peak_source": peak_src})
+    roof.sort(key=lambda r: -r["ms_total"])
+    whole = nev_total * BYTES_EVENT / (max_ms * 1e-3) / 1e9
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        ncores = os.cpu_count() or 1
+        ns = int(min(args.cpu_sample, n))
+        ev_np = ev_dev[:ns].cpu().numpy().view(np.uint8).reshape(-1).view(ge.EVENT_DTYPE)
+        r, sec = cpu_port_rate(ev_np, ncores)
+        cpu = {"value": r, "unit": "events/s", "cores": ncores, "kind": "port",
+               "sample": f"first {ns} events of rank 0's stream, pre-sharded by host over {ncores} threads ({sec:.1f} s)"}
+
+    out = {
+        "metric": "events/sec aggregated", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[2]: 100M mixed RESP/TCP/TASK (70/20/10) events, 100K services, count-min + HLL + "
+                               "fixed-bucket histograms + t-digest(100)", "events_per_step_per_gpu": n, "services": NSVC,
+                   "zipf_s": ZIPF_S, "max_batch": args.max_batch, "parallelism": f"host-shard x{world}",
+                   "l2": "inputs (3.2 GB/step) larger than L2, no flush needed"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roof[0] if roof else None, "roofline_other": roof[1:] or None,
+        "roofline_whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
+                                "algorithmic_bytes_per_event": BYTES_EVENT},
+        "cpu_baseline": cpu, "accuracy": acc,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+// gysk_device.cuh — device-side building blocks shared by the kernels of libgysketch.so (sm_100a only).
+//
+// Everything here is a from-scratch CUDA formulation of behaviour defined by the reference (citations are
+// relative to the reference tree) or by the sketch definitions stated in DESIGN.md.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gysk {
+
+// ---------------------------------------------------------------------------------------------------
+// HBM layout
+// ---------------------------------------------------------------------------------------------------
+// One histogram = 16 cells of {count u64, sum i64} = 256 B (two 128-B lines). Cells 0..14 are the buckets,
+// byte-identical to HIST_SERIAL (common/gy_statistics.h:458); cell 15 holds {unused, max_val_seen_}.
+struct HistCell { unsigned long long count; long long sum; };
+static constexpr int HIST_CELLS = 16;
+static constexpr int HIST_MAX_CELL = 15;
+
+// service-id table entry: open addressing, 16 B so one 128-bit load fetches key and slot together
+struct alignas(16) TblEntry { unsigned long long key; uint32_t slot1; uint32_t pad; };	// slot1 = slot + 1, 0 = not yet published
+static constexpr uint32_t SLOT_INVALID = 0xFFFFFFFFu;
+
+struct Centroid { double mean; unsigned long long weight; };
+static constexpr int TD_CAP = 128;
+
+// per-service t-digest header
+struct TdHead { unsigned long long total; double minv, maxv; uint32_t n; uint32_t pad; };
+
+struct IdTable
+{
+	TblEntry	*ent;
+	uint32_t	mask;		// capacity - 1
+	uint32_t	max_slots;
+	uint32_t	*count;		// slots handed out so far
+};
+
+// device counters (index into Engine::d_counters)
+enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_NTOUCHED, CTR_MAX = 16 };
+
+// ---------------------------------------------------------------------------------------------------
+// jhash: Bob Jenkins lookup2 in the form the reference uses (common/jhash.h:22-35,121-134); seed 0xceedfead
+// (get_uint64_hash, common/gy_common_inc.h:1120)
+// ---------------------------------------------------------------------------------------------------
+static constexpr uint32_t JHASH_GOLDEN = 0x9e3779b9u;
+static constexpr uint32_t GY_SEED = 0xceedfeadu;
+static constexpr uint32_t HLL_SEED_A = GY_SEED ^ 0xa5a5a5a5u;
+static constexpr uint32_t HLL_SEED_B = GY_SEED ^ 0x5a5a5a5au;
+
+__host__ __device__ __forceinline__ uint32_t jhash_2words(uint32_t a, uint32_t b, uint32_t initval)
+{
+	uint32_t c = initval;
+
+	a += JHASH_GOLDEN; b += JHASH_GOLDEN;
+	a -= b; a -= c; a ^= (c >> 13);
+	b -= c; b -= a; b ^= (a << 8);
+	c -= a; c -= b; c ^= (b >> 13);
+	a -= b; a -= c; a ^= (c >> 12);
+	b -= c; b -= a; b ^= (a << 16);
+	c -= a; c -= b; c ^= (b >> 5);
+	a -= b; a -= c; a ^= (c >> 3);
+	b -= c; b -= a; b ^= (a << 10);
+	c -= a; c -= b; c ^= (b >> 15);
+	return c;
+}
+
+__host__ __device__ __forceinline__ uint32_t uint64_hash(unsigned long long key)
+{
+	return jhash_2words((uint32_t)(key & 0xFFFFFFFFu), (uint32_t)(key >> 32), GY_SEED);
+}
+
+__host__ __device__ __forceinline__ uint32_t cms_index(unsigned long long key, uint32_t row, uint32_t wmask)
+{
+	return jhash_2words((uint32_t)key, (uint32_t)(key >> 32), GY_SEED + JHASH_GOLDEN * (row + 1)) & wmask;
+}
+
+__host__ __device__ __forceinline__ unsigned long long cms_increment(uint32_t bytes)
+{
+	return 1ull | ((unsigned long long)(bytes >> 10) << 32);
+}
+
+__device__ __forceinline__ void hll_idx_rank(unsigned long long key, uint32_t p, uint32_t &idx, uint32_t &rank)
+{
+	const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+	const unsigned long long h = ((unsigned long long)jhash_2words(lo, hi, HLL_SEED_A) << 32) | jhash_2words(lo, hi, HLL_SEED_B);
+	const unsigned long long w = h << p;
+
+	idx = (uint32_t)(h >> (64 - p));
+	rank = w ? (uint32_t)__clzll((long long)w) + 1u : (64u - p + 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bucket hashes (common/gy_statistics.h:1674-2063): bucket = 0 below min, nthr+1 at/after max_value,
+// otherwise 1 + #thresholds strictly below the value (the reference's linear scan, mid-slot shortcut included,
+// returns exactly that). Classes whose operator() takes `int` narrow the value first (:1748,:1801,:1854,:2032).
+// ---------------------------------------------------------------------------------------------------
+template <int N> struct Thr { int v[N]; };
+
+__device__ __forceinline__ int bucket_resp_time(long long ms)			// RESP_TIME_HASH :1677, operator()(int64_t)
+{
+	constexpr int thr[13] = {1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000};
+	if (ms < 0) return 0;
+	if (ms >= 15001) return 14;
+	int b = 1;
+#pragma unroll
+	for (int i = 0; i < 13; ++i) b += (ms > thr[i]);
+	return b;
+}
+
+__device__ __forceinline__ int bucket_hash_1_3000(int data)			// HASH_1_3000 :2016, operator()(int)
+{
+	constexpr int thr[12] = {1, 5, 10, 25, 50, 75, 100, 150, 300, 500, 1000, 3000};
+	if (data < 0) return 0;
+	if (data >= 3001) return 13;
+	int b = 1;
+#pragma unroll
+	for (int i = 0; i < 12; ++i) b += (data > thr[i]);
+	return b;
+}
+
+__device__ __forceinline__ int bucket_duration(int data)				// DURATION_HASH :1838, operator()(int)
+{
+	constexpr int thr[13] = {1, 10, 25, 50, 125, 400, 1000, 3000, 6000, 10000, 25000, 40000, 65000};
+	if (data < 0) return 0;
+	if (data >= 65001) return 14;
+	int b = 1;
+#pragma unroll
+	for (int i = 0; i < 13; ++i) b += (data > thr[i]);
+	return b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// memory helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
+{
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// fire-and-forget 64-bit add: compiles to RED.E.ADD.64 (no return value travels back from L2)
+__device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// id -> dense slot. With `insert`, an unknown id claims an empty entry with a CAS on the key, takes the next slot
+// number and publishes it; racing readers of the same key wait for the publish. Returns -1 when absent / full.
+// Replaces RCU_HASH_TABLE::lookup_single_elem_locked(glob_id, get_uint64_hash(glob_id)) (gy_mconnhdlr.cc:11183).
+__device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long key, bool insert)
+{
+	uint32_t pos = uint64_hash(key) & t.mask;
+
+	for (uint32_t probe = 0; probe <= t.mask; ++probe, pos = (pos + 1) & t.mask) {
+		TblEntry *e = &t.ent[pos];
+		unsigned long long k = ld_volatile_u64(&e->key);
+
+		if (k == 0) {
+			if (!insert) return -1;
+			k = atomicCAS(&e->key, 0ull, key);
+			if (k == 0) {
+				const uint32_t s = atomicAdd(t.count, 1u);
+				if (s >= t.max_slots) {
+					atomicSub(t.count, 1u);
+					st_release_u32(&e->slot1, SLOT_INVALID);
+					return -1;
+				}
+				st_release_u32(&e->slot1, s + 1);
+				return (int)s;
+			}
+		}
+		if (k == key) {
+			uint32_t s1;
+			while ((s1 = ld_acquire_u32(&e->slot1)) == 0) { __nanosleep(20); }
+			return s1 == SLOT_INVALID ? -1 : (int)(s1 - 1);
+		}
+	}
+	return -1;
+}
+
+} // namespace gysk

@@ -1,0 +1,963 @@
+// gysk_engine.cu — host runtime of libgysketch.so and the C ABI declared in include/gysketch.h.
+//
+// One engine = one GPU. Ingest calls are serialised by a mutex, copy their input into page-locked staging (the
+// reference's handlers never retain caller buffers: DB_WRITE_ARR frees them when the L2 loop iteration ends,
+// server/gy_mconnhdlr.h:424-431) and hand full batches to the device: H2D on a copy stream, kernels on the compute
+// stream, two device event buffers so the copy of batch k+1 overlaps the kernels of batch k.
+#include "gysk_kernels.cuh"
+#include "gysk_wire.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace gysk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int NBUF = 2;
+constexpr uint32_t QCHUNK = 1024;		// ids per query kernel launch
+
+struct LogicalState;
+
+} // namespace
+
+struct gysk_engine
+{
+	gysk_config		cfg {};
+	int			dev {0};
+	cudaStream_t		stream {nullptr}, copy_stream {nullptr};
+	DevState		st {};
+	SortTemp		tmp {};
+	std::vector<void *>	dallocs;
+	std::vector<void *>	hallocs;
+
+	// staging
+	gysk_event		*h_stage[NBUF] {};
+	gysk_event		*d_events[NBUF] {};
+	cudaEvent_t		ev_copied[NBUF] {}, ev_done[NBUF] {};
+	uint32_t		stage_fill {0};
+	int			stage_cur {0};
+
+	// query scratch
+	unsigned long long	*d_qids {nullptr}, *h_qids {nullptr};
+	SvcRaw			*d_svcraw {nullptr}, *h_svcraw {nullptr};
+	TaskRaw			*d_taskraw {nullptr}, *h_taskraw {nullptr};
+	uint8_t			*d_hllout {nullptr}, *h_hllout {nullptr};
+	int32_t			*d_found {nullptr}, *h_found {nullptr};
+	gysk_flow_est		*d_flowout {nullptr}, *h_flowout {nullptr};
+	unsigned long long	*h_counters {nullptr};
+
+	// optional per-kernel timing
+	bool			profiling {false};
+	std::vector<cudaEvent_t> prof_events;		// triples: before ingest, after ingest, after t-digest chain
+	size_t			prof_used {0};
+
+	std::mutex		mtx;
+	std::string		err;
+	bool			sticky {false};
+	uint64_t		kernel_launches {0}, batches {0}, wire_ok {0}, wire_bad {0};
+};
+
+namespace {
+
+int fail(gysk_engine *e, int code, const char *what, cudaError_t ce = cudaSuccess)
+{
+	char buf[512];
+
+	if (ce != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(ce));
+	else snprintf(buf, sizeof(buf), "%s", what);
+	if (e) {
+		e->err = buf;
+		if (code == GYSK_ERR_CUDA) e->sticky = true;
+	}
+	else g_create_error = buf;
+	return code;
+}
+
+#define CU(e, call) do { cudaError_t ce__ = (call); if (ce__ != cudaSuccess) return fail((e), GYSK_ERR_CUDA, #call, ce__); } while (0)
+#define CHECK_ENGINE(e) do { if (!(e)) return GYSK_ERR_INVAL; if ((e)->sticky) return GYSK_ERR_CUDA; } while (0)
+
+template <typename T>
+int dalloc(gysk_engine *e, T **p, size_t n, bool zero = true)
+{
+	void *q = nullptr;
+	cudaError_t ce = cudaMalloc(&q, n * sizeof(T));
+
+	if (ce != cudaSuccess) return fail(e, GYSK_ERR_NOMEM, "cudaMalloc", ce);
+	e->dallocs.push_back(q);
+	if (zero) {
+		ce = cudaMemsetAsync(q, 0, n * sizeof(T), e->stream);
+		if (ce != cudaSuccess) return fail(e, GYSK_ERR_CUDA, "cudaMemsetAsync", ce);
+	}
+	*p = static_cast<T *>(q);
+	return 0;
+}
+
+template <typename T>
+int halloc(gysk_engine *e, T **p, size_t n)
+{
+	void *q = nullptr;
+	cudaError_t ce = cudaHostAlloc(&q, n * sizeof(T), cudaHostAllocDefault);
+
+	if (ce != cudaSuccess) return fail(e, GYSK_ERR_NOMEM, "cudaHostAlloc", ce);
+	e->hallocs.push_back(q);
+	*p = static_cast<T *>(q);
+	return 0;
+}
+
+uint32_t pow2_at_least(uint64_t v) { uint32_t p = 16; while (p < v) p <<= 1; return p; }
+
+int post_launch(gysk_engine *e, const char *what)
+{
+	cudaError_t ce = cudaGetLastError();
+	if (ce != cudaSuccess) return fail(e, GYSK_ERR_CUDA, what, ce);
+	return 0;
+}
+
+// one device batch: ingest kernel, then the sort + t-digest chain over the keys it emitted
+int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
+{
+	if (!n) return 0;
+	cudaEvent_t *pe = nullptr;
+	if (e->profiling) {
+		if (e->prof_used + 3 > e->prof_events.size()) {
+			for (int i = 0; i < 3; ++i) {
+				cudaEvent_t ev;
+				CU(e, cudaEventCreate(&ev));
+				e->prof_events.push_back(ev);
+			}
+		}
+		pe = &e->prof_events[e->prof_used];
+		e->prof_used += 3;
+		CU(e, cudaEventRecord(pe[0], e->stream));
+	}
+	e->kernel_launches += launch_ingest(e->st, d_ev, n, e->tmp.keys_a, e->stream);
+	if (pe) CU(e, cudaEventRecord(pe[1], e->stream));
+	e->kernel_launches += launch_tdigest_update(e->st, e->tmp, n, e->cfg.max_svcs, e->stream);
+	if (pe) CU(e, cudaEventRecord(pe[2], e->stream));
+	e->batches++;
+	return post_launch(e, "ingest batch");
+}
+
+// hand the filled part of the current staging buffer to the device
+int submit_stage(gysk_engine *e)
+{
+	const int k = e->stage_cur;
+	const uint32_t n = e->stage_fill;
+
+	if (!n) return 0;
+	CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_done[k], 0));		// device buffer k no longer read by kernels
+	CU(e, cudaMemcpyAsync(e->d_events[k], e->h_stage[k], (size_t)n * sizeof(gysk_event), cudaMemcpyHostToDevice, e->copy_stream));
+	CU(e, cudaEventRecord(e->ev_copied[k], e->copy_stream));
+	CU(e, cudaStreamWaitEvent(e->stream, e->ev_copied[k], 0));
+	int rc = process_device_batch(e, e->d_events[k], n);
+	if (rc) return rc;
+	CU(e, cudaEventRecord(e->ev_done[k], e->stream));
+
+	e->stage_cur = (k + 1) % NBUF;
+	e->stage_fill = 0;
+	CU(e, cudaEventSynchronize(e->ev_copied[e->stage_cur]));		// host may overwrite the next staging buffer
+	return 0;
+}
+
+int stage_events(gysk_engine *e, const gysk_event *ev, uint64_t n)
+{
+	while (n) {
+		const uint32_t room = e->cfg.max_batch - e->stage_fill;
+		const uint32_t m = (uint32_t)std::min<uint64_t>(room, n);
+
+		memcpy(e->h_stage[e->stage_cur] + e->stage_fill, ev, (size_t)m * sizeof(gysk_event));
+		e->stage_fill += m; ev += m; n -= m;
+		if (e->stage_fill == e->cfg.max_batch) { int rc = submit_stage(e); if (rc) return rc; }
+	}
+	return 0;
+}
+
+inline gysk_event *stage_slot(gysk_engine *e, int *rc)
+{
+	if (e->stage_fill == e->cfg.max_batch) { *rc = submit_stage(e); if (*rc) return nullptr; }
+	return e->h_stage[e->stage_cur] + e->stage_fill++;
+}
+
+int sync_locked(gysk_engine *e)
+{
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	CU(e, cudaStreamSynchronize(e->copy_stream));
+	CU(e, cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+// ---- pure host helpers: the reference's percentile rule and the estimators -------------------------------
+
+struct ClsDesc { int nthr; int64_t thr[16]; int64_t minv, maxv; bool trunc_int; int fixed_diff; };
+
+const ClsDesc g_cls[8] = {
+	{13, {1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000}, 0, 15001, false, 0},		// RESP_TIME_HASH    gy_statistics.h:1677
+	{12, {1, 10, 100, 500, 1000, 5000, 25000, 50000, 100000, 300000, 1000000, 5000000}, 0, 5000001, true, 0},	// SEMI_LOG_HASH     :1732
+	{13, {1, 10, 50, 200, 500, 1000, 3000, 6000, 10000, 15000, 25000, 60000, 150000}, 0, 150001, true, 0},	// SEMI_LOG_HASH_LO  :1785
+	{13, {1, 10, 25, 50, 125, 400, 1000, 3000, 6000, 10000, 25000, 40000, 65000}, 0, 65001, true, 0},	// DURATION_HASH     :1838
+	{12, {10, 25, 50, 75, 100, 150, 300, 500, 800, 1000, 2000, 5000}, 0, 5001, true, 0},			// HASH_10_5000      :1911
+	{10, {5, 10, 20, 40, 60, 80, 100, 140, 200, 250}, 0, 251, true, 0},					// HASH_5_250        :1963
+	{12, {1, 5, 10, 25, 50, 75, 100, 150, 300, 500, 1000, 3000}, 0, 3001, true, 0},				// HASH_1_3000       :2016
+	{11, {9, 19, 29, 39, 49, 59, 69, 79, 89, 99, 100}, 0, 101, false, 10},					// PERCENT_HASH      :1624
+};
+
+// get_bucket_max_threshold<HashClass, T>, gy_statistics.h:500-515
+int64_t bucket_max_threshold(const ClsDesc &d, bool t_is_int, size_t id)
+{
+	const size_t maxb = (size_t)d.nthr + 2;
+
+	if (id == 0) return d.minv - 1;
+	if (id >= maxb - 1) {
+		const int64_t maxt = t_is_int ? INT32_MAX : INT64_MAX;
+		const int64_t lesst = d.maxv >= INT32_MAX ? INT64_MAX : (d.maxv > (INT16_MAX >> 1) ? INT32_MAX : INT16_MAX);
+		return std::min(lesst, maxt);
+	}
+	return d.thr[id - 1];
+}
+
+void hist_from_cells(const HistCell *cells, int nb, gysk_hist_serial *out, uint64_t *total, int64_t *maxv, bool t_is_int)
+{
+	uint64_t t = 0;
+
+	for (int i = 0; i < GYSK_HIST_MAX_BUCKETS; ++i) {
+		if (i < nb) { out[i].count = cells[i].count; out[i].sum = cells[i].sum; t += cells[i].count; }
+		else { out[i].count = 0; out[i].sum = 0; }
+	}
+	*total = t;			// total_count_ always equals the sum of the bucket counts (add_data bumps both)
+	int64_t m = cells[HIST_MAX_CELL].sum;
+	if (t_is_int && m == INT64_MIN) m = INT32_MIN;		// numeric_limits<int>::min() for GY_HISTOGRAM<int, ...>
+	*maxv = m;
+}
+
+double td_quantile(const double *means, const uint64_t *weights, uint32_t n, double minv, double maxv, double q)
+{
+	if (!n) return NAN;
+	double total = 0;
+	for (uint32_t i = 0; i < n; ++i) total += (double)weights[i];
+	if (q <= 0) return minv;
+	if (q >= 1) return maxv;
+
+	const double target = q * total;
+	double cum = 0, prev_center = 0, prev_mean = minv;
+
+	for (uint32_t i = 0; i < n; ++i) {
+		const double center = cum + (double)weights[i] / 2.0;
+		if (target < center) {
+			const double span = center - prev_center;
+			return span > 0 ? prev_mean + (means[i] - prev_mean) * ((target - prev_center) / span) : means[i];
+		}
+		prev_center = center; prev_mean = means[i];
+		cum += (double)weights[i];
+	}
+	const double span = total - prev_center;
+	return span > 0 ? prev_mean + (maxv - prev_mean) * ((target - prev_center) / span) : maxv;
+}
+
+double hll_estimate_from_hist(const uint32_t *hist64, uint32_t p)
+{
+	const uint32_t m = 1u << p;
+	double sum = 0, alpha, est;
+
+	for (int r = 63; r >= 0; --r) sum += (double)hist64[r] * ldexp(1.0, -r);
+	if (m == 16) alpha = 0.673; else if (m == 32) alpha = 0.697; else if (m == 64) alpha = 0.709;
+	else alpha = 0.7213 / (1.0 + 1.079 / (double)m);
+	est = alpha * (double)m * (double)m / sum;
+	if (est <= 2.5 * (double)m && hist64[0]) est = (double)m * log((double)m / (double)hist64[0]);
+	return est;
+}
+
+int gather_svcs(gysk_engine *e, const uint64_t *ids, uint32_t n)		// n <= QCHUNK; results in e->h_svcraw
+{
+	memcpy(e->h_qids, ids, (size_t)n * sizeof(uint64_t));
+	CU(e, cudaMemcpyAsync(e->d_qids, e->h_qids, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+	e->kernel_launches += launch_gather_svcs(e->st, e->d_qids, n, e->d_svcraw, e->stream);
+	CU(e, cudaMemcpyAsync(e->h_svcraw, e->d_svcraw, (size_t)n * sizeof(SvcRaw), cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaStreamSynchronize(e->stream));
+	return post_launch(e, "gather_svcs");
+}
+
+} // namespace
+
+// ============================================================================================================
+// C ABI
+// ============================================================================================================
+extern "C" {
+
+int gysk_abi_version(void) { return GYSK_ABI_VERSION; }
+
+void gysk_config_default(gysk_config *cfg)
+{
+	if (!cfg) return;
+	memset(cfg, 0, sizeof(*cfg));
+	cfg->struct_size = sizeof(*cfg);
+	cfg->device = 0;
+	cfg->max_svcs = 1u << 17;
+	cfg->max_tasks = 1u << 16;
+	cfg->cms_depth = 4;
+	cfg->cms_log2_width = 20;
+	cfg->hll_p = 12;
+	cfg->td_compression = 100;
+	cfg->max_batch = 1u << 22;
+	cfg->flags = GYSK_FLAG_AUTO_REGISTER;
+	cfg->rank = 0; cfg->world = 1;
+}
+
+const char *gysk_last_error(gysk_engine *e)
+{
+	return e ? e->err.c_str() : g_create_error.c_str();
+}
+
+void gysk_destroy(gysk_engine *e)
+{
+	if (!e) return;
+	cudaSetDevice(e->dev);
+	if (e->stream) cudaStreamSynchronize(e->stream);
+	if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+	for (int k = 0; k < NBUF; ++k) {
+		if (e->ev_copied[k]) cudaEventDestroy(e->ev_copied[k]);
+		if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
+	}
+	for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+	for (void *p : e->dallocs) cudaFree(p);
+	for (void *p : e->hallocs) cudaFreeHost(p);
+	if (e->stream) cudaStreamDestroy(e->stream);
+	if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+	delete e;
+}
+
+int gysk_create(const gysk_config *ucfg, gysk_engine **out)
+{
+	if (!out) return GYSK_ERR_INVAL;
+	*out = nullptr;
+
+	gysk_config cfg;
+	gysk_config_default(&cfg);
+	if (ucfg) {
+		if (ucfg->struct_size != sizeof(gysk_config)) return fail(nullptr, GYSK_ERR_INVAL, "gysk_config.struct_size mismatch");
+		cfg = *ucfg;
+	}
+	if (!cfg.world) cfg.world = 1;
+	if (cfg.max_svcs < 1 || cfg.max_svcs > (1u << 24) || cfg.max_tasks < 1 || cfg.max_tasks > (1u << 24) || cfg.cms_depth < 1 ||
+			cfg.cms_depth > 8 || cfg.cms_log2_width < 4 || cfg.cms_log2_width > 28 || cfg.hll_p < 4 || cfg.hll_p > 16 ||
+			cfg.td_compression < 10 || cfg.td_compression > 120 || cfg.max_batch < 1024 || cfg.max_batch > (1u << 28) ||
+			cfg.rank >= cfg.world)
+		return fail(nullptr, GYSK_ERR_INVAL, "gysk_config out of range");
+
+	int ndev = 0;
+	cudaError_t ce = cudaGetDeviceCount(&ndev);
+	if (ce != cudaSuccess || ndev <= 0 || cfg.device < 0 || cfg.device >= ndev)
+		return fail(nullptr, GYSK_ERR_NODEV, "no usable CUDA device (libgysketch has no CPU fallback)", ce);
+
+	cudaDeviceProp prop;
+	if ((ce = cudaGetDeviceProperties(&prop, cfg.device)) != cudaSuccess) return fail(nullptr, GYSK_ERR_NODEV, "cudaGetDeviceProperties", ce);
+	if (prop.major != 10) return fail(nullptr, GYSK_ERR_NODEV, "device is not sm_100 (kernels are built for sm_100a only)");
+
+	gysk_engine *e = new (std::nothrow) gysk_engine;
+	if (!e) return fail(nullptr, GYSK_ERR_NOMEM, "new gysk_engine");
+	e->cfg = cfg; e->dev = cfg.device;
+
+	int rc = 0;
+	auto bail = [&](int code) { g_create_error = e->err; gysk_destroy(e); return code; };
+
+	if ((ce = cudaSetDevice(e->dev)) != cudaSuccess) { fail(e, GYSK_ERR_CUDA, "cudaSetDevice", ce); return bail(GYSK_ERR_CUDA); }
+	if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+			(ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+		fail(e, GYSK_ERR_CUDA, "cudaStreamCreate", ce); return bail(GYSK_ERR_CUDA);
+	}
+
+	DevState &st = e->st;
+	const size_t ns = cfg.max_svcs, nt = cfg.max_tasks;
+	const uint32_t scap = pow2_at_least((uint64_t)ns * 2), tcap = pow2_at_least((uint64_t)nt * 2);
+
+#define A(call) do { if ((rc = (call)) != 0) return bail(rc); } while (0)
+	A(dalloc(e, &st.svc_tbl.ent, scap)); st.svc_tbl.mask = scap - 1; st.svc_tbl.max_slots = cfg.max_svcs;
+	A(dalloc(e, &st.svc_tbl.count, 1));
+	A(dalloc(e, &st.task_tbl.ent, tcap)); st.task_tbl.mask = tcap - 1; st.task_tbl.max_slots = cfg.max_tasks;
+	A(dalloc(e, &st.task_tbl.count, 1));
+	A(dalloc(e, &st.hist_cur, ns * HIST_CELLS)); A(dalloc(e, &st.hist_last, ns * HIST_CELLS)); A(dalloc(e, &st.hist_all, ns * HIST_CELLS));
+	A(dalloc(e, &st.conn_cur, ns)); A(dalloc(e, &st.conn_last, ns)); A(dalloc(e, &st.conn_all_cnt, ns)); A(dalloc(e, &st.conn_all_kb, ns));
+	A(dalloc(e, &st.hll, ns << cfg.hll_p));
+	A(dalloc(e, &st.td_cent, ns * TD_CAP)); A(dalloc(e, &st.td_head, ns));
+	A(dalloc(e, &st.task_hist, nt * 3 * HIST_CELLS));
+	A(dalloc(e, &st.cms_cur, (size_t)cfg.cms_depth << cfg.cms_log2_width)); A(dalloc(e, &st.cms_last, (size_t)cfg.cms_depth << cfg.cms_log2_width));
+	A(dalloc(e, &st.counters, (size_t)CTR_MAX));
+	st.cms_depth = cfg.cms_depth; st.cms_log2w = cfg.cms_log2_width; st.cms_wmask = (1u << cfg.cms_log2_width) - 1; st.hll_p = cfg.hll_p;
+	st.rank = cfg.rank; st.world = cfg.world; st.auto_register = (cfg.flags & GYSK_FLAG_AUTO_REGISTER) ? 1 : 0;
+	st.td_delta = (double)cfg.td_compression;
+
+	SortTemp &tmp = e->tmp;
+	tmp.max_tiles = (cfg.max_batch + SORT_TILE - 1) / SORT_TILE;
+	A(dalloc(e, &tmp.keys_a, (size_t)cfg.max_batch, false)); A(dalloc(e, &tmp.keys_b, (size_t)cfg.max_batch, false));
+	A(dalloc(e, &tmp.tile_hist, (size_t)256 * tmp.max_tiles));
+	A(dalloc(e, &tmp.scan_tmp, (size_t)256 * tmp.max_tiles / 2048 + 64));
+	A(dalloc(e, &tmp.seg_start, ns)); A(dalloc(e, &tmp.seg_end, ns)); A(dalloc(e, &tmp.touched, ns));
+
+	for (int k = 0; k < NBUF; ++k) {
+		A(halloc(e, &e->h_stage[k], (size_t)cfg.max_batch));
+		A(dalloc(e, &e->d_events[k], (size_t)cfg.max_batch, false));
+		if ((ce = cudaEventCreateWithFlags(&e->ev_copied[k], cudaEventDisableTiming)) != cudaSuccess ||
+				(ce = cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming)) != cudaSuccess) {
+			fail(e, GYSK_ERR_CUDA, "cudaEventCreate", ce); return bail(GYSK_ERR_CUDA);
+		}
+	}
+	A(dalloc(e, &e->d_qids, (size_t)QCHUNK)); A(halloc(e, &e->h_qids, (size_t)QCHUNK));
+	A(dalloc(e, &e->d_svcraw, (size_t)QCHUNK)); A(halloc(e, &e->h_svcraw, (size_t)QCHUNK));
+	A(dalloc(e, &e->d_taskraw, (size_t)QCHUNK)); A(halloc(e, &e->h_taskraw, (size_t)QCHUNK));
+	A(dalloc(e, &e->d_hllout, (size_t)1 << cfg.hll_p)); A(halloc(e, &e->h_hllout, (size_t)1 << cfg.hll_p));
+	A(dalloc(e, &e->d_found, (size_t)1)); A(halloc(e, &e->h_found, (size_t)1));
+	A(dalloc(e, &e->d_flowout, (size_t)QCHUNK)); A(halloc(e, &e->h_flowout, (size_t)QCHUNK));
+	A(halloc(e, &e->h_counters, (size_t)CTR_MAX + 2));
+#undef A
+
+	e->kernel_launches += launch_init_state(st, cfg.max_svcs, cfg.max_tasks, e->stream);
+	if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess || (ce = cudaGetLastError()) != cudaSuccess) {
+		fail(e, GYSK_ERR_CUDA, "engine init", ce); return bail(GYSK_ERR_CUDA);
+	}
+	*out = e;
+	return GYSK_OK;
+}
+
+void *gysk_stream(gysk_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+int gysk_profile_enable(gysk_engine *e, int on)
+{
+	CHECK_ENGINE(e);
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = sync_locked(e);
+	if (rc) return rc;
+	e->profiling = !!on;
+	e->prof_used = 0;
+	return GYSK_OK;
+}
+
+int gysk_profile_read(gysk_engine *e, double *ms_ingest, double *ms_tdigest, uint64_t *nbatches)
+{
+	CHECK_ENGINE(e);
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = sync_locked(e);
+	if (rc) return rc;
+	double a = 0, b = 0;
+	for (size_t i = 0; i + 3 <= e->prof_used; i += 3) {
+		float t1 = 0, t2 = 0;
+		CU(e, cudaEventElapsedTime(&t1, e->prof_events[i], e->prof_events[i + 1]));
+		CU(e, cudaEventElapsedTime(&t2, e->prof_events[i + 1], e->prof_events[i + 2]));
+		a += t1; b += t2;
+	}
+	if (ms_ingest) *ms_ingest = a;
+	if (ms_tdigest) *ms_tdigest = b;
+	if (nbatches) *nbatches = e->prof_used / 3;
+	e->prof_used = 0;
+	return GYSK_OK;
+}
+
+int gysk_get_stats(gysk_engine *e, gysk_stats *out)
+{
+	CHECK_ENGINE(e);
+	if (!out) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = sync_locked(e);
+	if (rc) return rc;
+	CU(e, cudaMemcpyAsync(e->h_counters, e->st.counters, sizeof(unsigned long long) * CTR_MAX, cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaMemcpyAsync(e->h_counters + CTR_MAX, e->st.svc_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaMemcpyAsync(e->h_counters + CTR_MAX + 1, e->st.task_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaStreamSynchronize(e->stream));
+	memset(out, 0, sizeof(*out));
+	out->events_in = e->h_counters[CTR_IN]; out->events_dropped = e->h_counters[CTR_DROPPED];
+	out->events_resp = e->h_counters[CTR_RESP]; out->events_tcp = e->h_counters[CTR_TCP]; out->events_task = e->h_counters[CTR_TASK];
+	out->nsvcs = std::min<uint64_t>((uint32_t)e->h_counters[CTR_MAX], e->cfg.max_svcs);
+	out->ntasks = std::min<uint64_t>((uint32_t)e->h_counters[CTR_MAX + 1], e->cfg.max_tasks);
+	out->batches = e->batches; out->kernel_launches = e->kernel_launches;
+	out->wire_msgs_ok = e->wire_ok; out->wire_msgs_bad = e->wire_bad;
+	return GYSK_OK;
+}
+
+int gysk_register_ids(gysk_engine *e, const uint64_t *ids, uint32_t n, int is_task)
+{
+	CHECK_ENGINE(e);
+	if (!ids && n) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	for (uint32_t off = 0; off < n; off += QCHUNK) {
+		const uint32_t m = std::min(QCHUNK, n - off);
+		memcpy(e->h_qids, ids + off, (size_t)m * sizeof(uint64_t));
+		CU(e, cudaMemcpyAsync(e->d_qids, e->h_qids, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+		e->kernel_launches += launch_register(e->st, e->d_qids, m, is_task, e->stream);
+		CU(e, cudaStreamSynchronize(e->stream));
+	}
+	return post_launch(e, "register");
+}
+
+// ---- ingest -----------------------------------------------------------------------------------------------
+
+int gysk_ingest_device(gysk_engine *e, const gysk_event *d_events, uint64_t n)
+{
+	CHECK_ENGINE(e);
+	if (!d_events && n) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);					// keep arrival order
+	if (rc) return rc;
+	for (uint64_t off = 0; off < n; off += e->cfg.max_batch) {
+		const uint64_t m = std::min<uint64_t>(e->cfg.max_batch, n - off);
+		if ((rc = process_device_batch(e, d_events + off, m))) return rc;
+	}
+	return GYSK_OK;
+}
+
+int gysk_ingest_pinned(gysk_engine *e, const gysk_event *pinned, uint64_t n)
+{
+	CHECK_ENGINE(e);
+	if (!pinned && n) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	for (uint64_t off = 0; off < n; off += e->cfg.max_batch) {
+		const uint64_t m = std::min<uint64_t>(e->cfg.max_batch, n - off);
+		const int k = e->stage_cur;
+		CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_done[k], 0));
+		CU(e, cudaMemcpyAsync(e->d_events[k], pinned + off, (size_t)m * sizeof(gysk_event), cudaMemcpyHostToDevice, e->copy_stream));
+		CU(e, cudaEventRecord(e->ev_copied[k], e->copy_stream));
+		CU(e, cudaStreamWaitEvent(e->stream, e->ev_copied[k], 0));
+		if ((rc = process_device_batch(e, e->d_events[k], m))) return rc;
+		CU(e, cudaEventRecord(e->ev_done[k], e->stream));
+		e->stage_cur = (k + 1) % NBUF;
+	}
+	return GYSK_OK;
+}
+
+int gysk_ingest_raw(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, uint32_t kind, const void *events, uint32_t n)
+{
+	CHECK_ENGINE(e);
+	(void)host_id;
+	if (!events && n) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = 0;
+
+	switch (kind) {
+
+	case GYSK_RAW_EVENT32 :
+		return stage_events(e, static_cast<const gysk_event *>(events), n);
+
+	case GYSK_RAW_TCP_IPV4_RESP : {
+		// TCP_SOCK_HANDLER::handle_ipv4_resp_event, common/gy_socket_stat.cc:1517-1552: tresp = lsndtime - lrcvtime (msec),
+		// dropped when (uint32_t)tresp > 1 000 000. The listener key is (netns, server ip, server port); the client port keys CONN_BITMAP.
+		const wire::tcp_ipv4_resp_event_t *p = static_cast<const wire::tcp_ipv4_resp_event_t *>(events);
+		for (uint32_t i = 0; i < n; ++i) {
+			const uint32_t tresp = p[i].lsndtime - p[i].lrcvtime;
+			if (tresp > 1000000u) continue;
+			gysk_event *o = stage_slot(e, &rc);
+			if (!o) return rc;
+			const uint32_t words[3] = { p[i].saddr, p[i].netns, p[i].sport };
+			o->svc_id = ((uint64_t)jhash_2words(words[0], words[1], GY_SEED) << 32) | jhash_2words(words[2], words[1], GY_SEED ^ words[0]);
+			if (!o->svc_id) o->svc_id = 1;
+			o->flow_key = ((uint64_t)p[i].daddr << 32) | p[i].dport;
+			o->value = tresp * 1000u; o->host_idx = host_idx; o->tsec = 0; o->type = GYSK_EV_RESP; o->flags = 0;
+		}
+		return GYSK_OK;
+	}
+
+	case GYSK_RAW_TCP_IPV4_EVENT : {
+		// TCP_SOCK_HANDLER::handle_ipv4_conn_event, common/gy_socket_stat.cc:241-294: type 1..4; on close the byte counters
+		// are added to the listener totals (handle_bpf_close_ser :850)
+		const wire::tcp_ipv4_event_t *p = static_cast<const wire::tcp_ipv4_event_t *>(events);
+		for (uint32_t i = 0; i < n; ++i) {
+			if (p[i].type < GYSK_EV_CONNECT || p[i].type > GYSK_EV_CLOSE_SER) continue;
+			gysk_event *o = stage_slot(e, &rc);
+			if (!o) return rc;
+			const bool ser_side = (p[i].type == GYSK_EV_ACCEPT || p[i].type == GYSK_EV_CLOSE_SER);
+			const uint32_t sip = ser_side ? p[i].saddr : p[i].daddr, sport = ser_side ? p[i].sport : p[i].dport;
+			const uint32_t cip = ser_side ? p[i].daddr : p[i].saddr, cport = ser_side ? p[i].dport : p[i].sport;
+			o->svc_id = ((uint64_t)jhash_2words(sip, p[i].netns, GY_SEED) << 32) | jhash_2words(sport, p[i].netns, GY_SEED ^ sip);
+			if (!o->svc_id) o->svc_id = 1;
+			o->flow_key = ((uint64_t)cip << 32) | cport;
+			const uint64_t bytes = p[i].bytes_received + p[i].bytes_acked;
+			o->value = bytes > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bytes;
+			o->host_idx = host_idx; o->tsec = (uint32_t)(p[i].ts_ns / 1000000000ull); o->type = p[i].type; o->flags = 0;
+		}
+		return GYSK_OK;
+	}
+
+	default :
+		return fail(e, GYSK_ERR_INVAL, "gysk_ingest_raw: unknown kind");
+	}
+}
+
+// One wire message body, exactly the arguments handle_l2_misc hands to partha_<kind>() (gy_mconnhdlr.cc:4745-4800).
+int gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, uint32_t subtype, void *recs, uint32_t nevents, const void *endptr)
+{
+	CHECK_ENGINE(e);
+	(void)host_id;
+	if (!recs || !endptr || (const uint8_t *)endptr < (const uint8_t *)recs) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	const uint8_t *pend = static_cast<const uint8_t *>(endptr);
+	int rc = 0;
+
+	switch (subtype) {
+
+	case GYSK_NOTIFY_TCP_CONN : {
+		using T = wire::TCP_CONN_NOTIFY;
+		T *pone = static_cast<T *>(recs);
+		if (!wire::validate_batch<T>(pone, nevents, pend, T::MAX_NUM_CONNS, [](const T & t) -> size_t { return t.cli_cmdline_len_; })) {
+			e->wire_bad++;
+			return fail(e, GYSK_ERR_INVAL, "TCP_CONN_NOTIFY::validate failed");
+		}
+		// record walk of partha_tcp_conn_info (gy_mconnhdlr.cc:9130): i < nconns && ptr < pendptr, stride get_elem_size()
+		for (uint32_t i = 0; i < nevents && (const uint8_t *)pone < pend; ++i, pone = (T *)((uint8_t *)pone + pone->get_elem_size())) {
+			if (!pone->ser_glob_id_ || !pone->cli_task_aggr_id_) continue;		// :9143 guard of the group-by
+			const bool closed = !!pone->tusec_close_;
+			uint16_t type;
+			if (pone->is_tcp_accept_event_) type = closed ? GYSK_EV_CLOSE_SER : GYSK_EV_ACCEPT;
+			else if (pone->is_tcp_connect_event_) type = closed ? GYSK_EV_CLOSE_CLI : GYSK_EV_CONNECT;
+			else continue;
+			gysk_event *o = stage_slot(e, &rc);
+			if (!o) return rc;
+			const uint64_t bytes = closed ? pone->bytes_sent_ + pone->bytes_rcvd_ : 0;
+			o->svc_id = pone->ser_glob_id_; o->flow_key = pone->cli_task_aggr_id_;
+			o->value = bytes > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bytes;
+			o->host_idx = host_idx; o->tsec = (uint32_t)((closed ? pone->tusec_close_ : pone->tusec_start_) / 1000000ull);
+			o->type = type; o->flags = 0;
+		}
+		e->wire_ok++;
+		return GYSK_OK;
+	}
+
+	case GYSK_NOTIFY_AGGR_TASK_STATE : {
+		using T = wire::AGGR_TASK_STATE_NOTIFY;
+		T *pone = static_cast<T *>(recs);
+		if (!wire::validate_batch<T>(pone, nevents, pend, T::MAX_NUM_TASKS, [](const T & t) -> size_t { return t.issue_string_len_; })) {
+			e->wire_bad++;
+			return fail(e, GYSK_ERR_INVAL, "AGGR_TASK_STATE_NOTIFY::validate failed");
+		}
+		// partha_aggr_task_state (gy_mconnhdlr.cc:9959) -> MAGGR_TASK::set_local_task_state (gy_msocket.h:1009)
+		for (uint32_t i = 0; i < nevents && (const uint8_t *)pone < pend; ++i, pone = (T *)((uint8_t *)pone + pone->get_elem_size())) {
+			if (!pone->aggr_task_id_) continue;
+			gysk_event *o = stage_slot(e, &rc);
+			if (!o) return rc;
+			o->svc_id = pone->aggr_task_id_;
+			o->flow_key = (uint64_t)pone->cpu_delay_msec_ | ((uint64_t)pone->blkio_delay_msec_ << 32);
+			o->value = (uint32_t)(int)pone->total_cpu_pct_;				// (int)ptask->total_cpu_pct_ , gy_msocket.h:1014
+			o->host_idx = host_idx; o->tsec = 0; o->type = GYSK_EV_TASK; o->flags = 0;
+		}
+		e->wire_ok++;
+		return GYSK_OK;
+	}
+
+	case GYSK_NOTIFY_LISTENER_STATE : {
+		using T = wire::LISTENER_STATE_NOTIFY;
+		T *pone = static_cast<T *>(recs);
+		if (!wire::validate_batch<T>(pone, nevents, pend, T::MAX_NUM_LISTENERS, [](const T & t) -> size_t { return t.issue_string_len_; })) {
+			e->wire_bad++;
+			return fail(e, GYSK_ERR_INVAL, "LISTENER_STATE_NOTIFY::validate failed");
+		}
+		// Pre-aggregated 5-s listener state: with the per-sample reduction lifted onto the GPU these records carry
+		// nothing the engine does not already derive itself; they are validated and counted, not folded.
+		e->wire_ok++;
+		return GYSK_OK;
+	}
+
+	default :
+		return fail(e, GYSK_ERR_NOTSUP, "gysk_ingest: subtype not on the hot path");
+	}
+}
+
+// Whole message: COMM_HEADER + EVENT_NOTIFY + records, the pointer arithmetic of handle_l2_misc (gy_mconnhdlr.cc:4745-4760)
+int gysk_ingest_msg(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, void *msg, uint32_t msglen)
+{
+	CHECK_ENGINE(e);
+	if (!msg || msglen < sizeof(wire::COMM_HEADER) + sizeof(wire::EVENT_NOTIFY)) return GYSK_ERR_INVAL;
+	wire::COMM_HEADER *phdr = static_cast<wire::COMM_HEADER *>(msg);
+
+	if (phdr->magic_ != wire::PM_HDR_MAGIC || phdr->data_type_ != wire::COMM_EVENT_NOTIFY || phdr->total_sz_ > msglen ||
+			phdr->total_sz_ >= wire::MAX_COMM_DATA_SZ || phdr->padding_sz_ > phdr->total_sz_ ||
+			phdr->get_act_len() < sizeof(wire::COMM_HEADER) + sizeof(wire::EVENT_NOTIFY)) {
+		std::lock_guard<std::mutex> lk(e->mtx);
+		e->wire_bad++;
+		return fail(e, GYSK_ERR_INVAL, "COMM_HEADER::validate failed");
+	}
+	uint8_t *pendptr = static_cast<uint8_t *>(msg) + phdr->get_act_len();
+	wire::EVENT_NOTIFY *pevtnot = reinterpret_cast<wire::EVENT_NOTIFY *>(phdr + 1);
+
+	return gysk_ingest(e, host_id, host_idx, pevtnot->subtype_, pevtnot + 1, pevtnot->nevents_, pendptr);
+}
+
+int gysk_sync(gysk_engine *e)
+{
+	CHECK_ENGINE(e);
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	return sync_locked(e);
+}
+
+int gysk_flush(gysk_engine *e, uint32_t tsec)
+{
+	CHECK_ENGINE(e);
+	(void)tsec;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	e->kernel_launches += launch_flush(e->st, e->cfg.max_svcs, e->stream);
+	std::swap(e->st.cms_cur, e->st.cms_last);
+	CU(e, cudaMemsetAsync(e->st.cms_cur, 0, sizeof(unsigned long long) * ((size_t)e->cfg.cms_depth << e->cfg.cms_log2_width), e->stream));
+	return post_launch(e, "flush");
+}
+
+// ---- queries ------------------------------------------------------------------------------------------------
+
+int gysk_query_svcs(gysk_engine *e, const uint64_t *ids, uint32_t n, gysk_svc_summary *out)
+{
+	CHECK_ENGINE(e);
+	if ((!ids || !out) && n) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);
+	if (rc) return rc;
+
+	const float pcts[3] = {95.0f, 99.0f, 25.0f};		// the percentiles listener_stats_update reads, gy_socket_stat.h:459
+
+	for (uint32_t off = 0; off < n; off += QCHUNK) {
+		const uint32_t m = std::min(QCHUNK, n - off);
+		if ((rc = gather_svcs(e, ids + off, m))) return rc;
+
+		for (uint32_t i = 0; i < m; ++i) {
+			const SvcRaw &r = e->h_svcraw[i];
+			gysk_svc_summary &o = out[off + i];
+
+			memset(&o, 0, sizeof(o));
+			o.glob_id = ids[off + i];
+			o.found = r.found;
+			o.td_p50_us = o.td_p95_us = o.td_p99_us = NAN;
+			if (!r.found) continue;
+
+			gysk_hist_serial ser[GYSK_HIST_MAX_BUCKETS];
+			uint64_t total; int64_t maxv, p[3];
+
+			hist_from_cells(r.last, 15, ser, &total, &maxv, false);
+			gysk_hist_percentiles(GYSK_CLS_RESP_TIME, 0, ser, total, pcts, 3, p);
+			o.nqrys_5s = (uint32_t)total;
+			for (int b = 0; b < 15; ++b) o.total_resp_5sec += (uint64_t)ser[b].sum;
+			o.p95_5s_resp_ms = p[0]; o.p99_5s_resp_ms = p[1]; o.p25_5s_resp_ms = p[2];
+
+			hist_from_cells(r.all, 15, ser, &total, &maxv, false);
+			gysk_hist_percentiles(GYSK_CLS_RESP_TIME, 0, ser, total, pcts, 2, p);
+			o.p95_all_resp_ms = p[0]; o.p99_all_resp_ms = p[1]; o.nqrys_all = total; o.max_resp_ms = maxv;
+
+			o.nconns_5s = (uint32_t)r.conn_last; o.kbytes_5s = (uint32_t)(r.conn_last >> 32);
+			o.nconns_all = r.conn_all_cnt; o.kbytes_all = r.conn_all_kb;
+			o.distinct_clients = hll_estimate_from_hist(r.hll_hist, e->cfg.hll_p);
+
+			double means[TD_CAP]; uint64_t w[TD_CAP];
+			const uint32_t nc = std::min<uint32_t>(r.td.n, TD_CAP);
+			for (uint32_t c = 0; c < nc; ++c) { means[c] = r.cent[c].mean; w[c] = r.cent[c].weight; }
+			o.td_count = r.td.total;
+			if (nc) {
+				o.td_p50_us = td_quantile(means, w, nc, r.td.minv, r.td.maxv, 0.50);
+				o.td_p95_us = td_quantile(means, w, nc, r.td.minv, r.td.maxv, 0.95);
+				o.td_p99_us = td_quantile(means, w, nc, r.td.minv, r.td.maxv, 0.99);
+			}
+		}
+	}
+	return GYSK_OK;
+}
+
+int gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial out[GYSK_HIST_MAX_BUCKETS], uint64_t *total, int64_t *maxv)
+{
+	CHECK_ENGINE(e);
+	if (!out || !total || !maxv) return GYSK_ERR_INVAL;
+	if (which >= GYSK_HIST_TASK_CPU_PCT) return gysk_export_task_hist(e, id, which, out, total, maxv);
+	if (which < 0) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	if ((rc = gather_svcs(e, &id, 1))) return rc;
+	const SvcRaw &r = e->h_svcraw[0];
+	if (!r.found) return GYSK_ERR_NOENT;
+	hist_from_cells(which == GYSK_HIST_RESP_CUR ? r.cur : (which == GYSK_HIST_RESP_LAST ? r.last : r.all), 15, out, total, maxv, false);
+	return GYSK_OK;
+}
+
+int gysk_export_task_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial out[GYSK_HIST_MAX_BUCKETS], uint64_t *total, int64_t *maxv)
+{
+	CHECK_ENGINE(e);
+	if (!out || !total || !maxv || which < GYSK_HIST_TASK_CPU_PCT || which > GYSK_HIST_TASK_BLKIO_DELAY) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	e->h_qids[0] = id;
+	CU(e, cudaMemcpyAsync(e->d_qids, e->h_qids, sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+	e->kernel_launches += launch_gather_tasks(e->st, e->d_qids, 1, e->d_taskraw, e->stream);
+	CU(e, cudaMemcpyAsync(e->h_taskraw, e->d_taskraw, sizeof(TaskRaw), cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaStreamSynchronize(e->stream));
+	if ((rc = post_launch(e, "gather_tasks"))) return rc;
+	if (!e->h_taskraw[0].found) return GYSK_ERR_NOENT;
+	const int h = which - GYSK_HIST_TASK_CPU_PCT;
+	hist_from_cells(e->h_taskraw[0].h[h], h == 0 ? 14 : 15, out, total, maxv, true);
+	return GYSK_OK;
+}
+
+int gysk_export_hll(gysk_engine *e, uint64_t id, uint8_t *regs)
+{
+	CHECK_ENGINE(e);
+	if (!regs) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	e->kernel_launches += launch_gather_hll(e->st, id, e->d_hllout, e->d_found, e->stream);
+	CU(e, cudaMemcpyAsync(e->h_hllout, e->d_hllout, (size_t)1 << e->cfg.hll_p, cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaMemcpyAsync(e->h_found, e->d_found, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaStreamSynchronize(e->stream));
+	if ((rc = post_launch(e, "gather_hll"))) return rc;
+	if (!*e->h_found) return GYSK_ERR_NOENT;
+	memcpy(regs, e->h_hllout, (size_t)1 << e->cfg.hll_p);
+	return GYSK_OK;
+}
+
+int gysk_export_tdigest(gysk_engine *e, uint64_t id, double *means, uint64_t *weights, uint32_t cap, uint32_t *n, double *minv, double *maxv)
+{
+	CHECK_ENGINE(e);
+	if (!means || !weights || !n) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	if ((rc = gather_svcs(e, &id, 1))) return rc;
+	const SvcRaw &r = e->h_svcraw[0];
+	if (!r.found) return GYSK_ERR_NOENT;
+	const uint32_t nc = std::min<uint32_t>(std::min<uint32_t>(r.td.n, TD_CAP), cap);
+	for (uint32_t c = 0; c < nc; ++c) { means[c] = r.cent[c].mean; weights[c] = r.cent[c].weight; }
+	*n = nc;
+	if (minv) *minv = r.td.minv;
+	if (maxv) *maxv = r.td.maxv;
+	return r.td.n > cap ? GYSK_ERR_NOSPC : GYSK_OK;
+}
+
+int gysk_query_quantiles(gysk_engine *e, uint64_t id, const double *qs, uint32_t nq, double *out)
+{
+	double means[TD_CAP], minv = 0, maxv = 0;
+	uint64_t w[TD_CAP];
+	uint32_t n = 0;
+	int rc = gysk_export_tdigest(e, id, means, w, TD_CAP, &n, &minv, &maxv);
+
+	if (rc) return rc;
+	if ((!qs || !out) && nq) return GYSK_ERR_INVAL;
+	for (uint32_t i = 0; i < nq; ++i) out[i] = td_quantile(means, w, n, minv, maxv, qs[i]);
+	return GYSK_OK;
+}
+
+int gysk_query_flows(gysk_engine *e, const uint64_t *keys, uint32_t n, int last_window, gysk_flow_est *out)
+{
+	CHECK_ENGINE(e);
+	if ((!keys || !out) && n) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	for (uint32_t off = 0; off < n; off += QCHUNK) {
+		const uint32_t m = std::min(QCHUNK, n - off);
+		memcpy(e->h_qids, keys + off, (size_t)m * sizeof(uint64_t));
+		CU(e, cudaMemcpyAsync(e->d_qids, e->h_qids, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+		e->kernel_launches += launch_query_flows(e->st, e->d_qids, m, last_window, e->d_flowout, e->stream);
+		CU(e, cudaMemcpyAsync(e->h_flowout, e->d_flowout, (size_t)m * sizeof(gysk_flow_est), cudaMemcpyDeviceToHost, e->stream));
+		CU(e, cudaStreamSynchronize(e->stream));
+		memcpy(out + off, e->h_flowout, (size_t)m * sizeof(gysk_flow_est));
+	}
+	return post_launch(e, "query_flows");
+}
+
+int gysk_export_cms(gysk_engine *e, int last_window, uint64_t *cells)
+{
+	CHECK_ENGINE(e);
+	if (!cells) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = sync_locked(e);
+	if (rc) return rc;
+	CU(e, cudaMemcpy(cells, last_window ? e->st.cms_last : e->st.cms_cur, sizeof(uint64_t) * ((size_t)e->cfg.cms_depth << e->cfg.cms_log2_width),
+			cudaMemcpyDeviceToHost));
+	return GYSK_OK;
+}
+
+// ---- pure helpers ------------------------------------------------------------------------------------------------
+
+int gysk_hist_nbuckets(int cls)
+{
+	if (cls < 0 || cls > GYSK_CLS_PERCENT) return GYSK_ERR_INVAL;
+	return g_cls[cls].nthr + 2;
+}
+
+int gysk_hist_bucket(int cls, int64_t value)
+{
+	if (cls < 0 || cls > GYSK_CLS_PERCENT) return GYSK_ERR_INVAL;
+	const ClsDesc &d = g_cls[cls];
+	int64_t data = d.trunc_int ? (int64_t)(int32_t)value : value;
+
+	if (data < d.minv) return 0;
+	if (data >= d.maxv) return d.nthr + 1;
+	if (d.fixed_diff) return (int)(1 + (data - d.minv) / d.fixed_diff);
+	int b = 1;
+	for (int i = 0; i < d.nthr; ++i) b += (data > d.thr[i]);
+	return b;
+}
+
+// GY_HISTOGRAM::get_percentiles, common/gy_statistics.h:707-791: float multiplier, size_t * float cut-off,
+// first bucket whose cumulative count reaches it, answer = that bucket's upper threshold cast to T
+int gysk_hist_percentiles(int cls, int t_is_int, const gysk_hist_serial *stats, uint64_t total_count, const float *pcts, uint32_t npct, int64_t *out)
+{
+	if (cls < 0 || cls > GYSK_CLS_PERCENT || !stats || (!pcts && npct) || (!out && npct)) return GYSK_ERR_INVAL;
+	const ClsDesc &d = g_cls[cls];
+	const size_t nb = (size_t)d.nthr + 2;
+
+	for (uint32_t n = 0; n < npct; ++n) {
+		const float multiplier = (float)(pcts[n] / 100.0);
+		const size_t ncutoff = (size_t)((float)total_count * multiplier);
+		size_t i, total = 0;
+
+		for (i = 0; i < nb; ++i) {
+			total += stats[i].count;
+			if (total >= ncutoff) break;
+		}
+		int64_t v = bucket_max_threshold(d, !!t_is_int, i < nb ? i : (total_count > 0 ? nb : 0));
+		out[n] = t_is_int ? (int64_t)(int32_t)v : v;
+	}
+	return GYSK_OK;
+}
+
+double gysk_hll_estimate(const uint8_t *regs, uint32_t p)
+{
+	if (!regs || p < 4 || p > 16) return NAN;
+	uint32_t hist[64] = {0};
+	for (uint32_t i = 0; i < (1u << p); ++i) hist[regs[i] > 63 ? 63 : regs[i]]++;
+	return hll_estimate_from_hist(hist, p);
+}
+
+double gysk_tdigest_quantile(const double *means, const uint64_t *weights, uint32_t n, double minv, double maxv, double q)
+{
+	if ((!means || !weights) && n) return NAN;
+	return td_quantile(means, weights, n, minv, maxv, q);
+}
+
+uint32_t gysk_uint64_hash(uint64_t key) { return uint64_hash(key); }
+
+// ---- multi-GPU merge: implemented in gysk_merge.cu ------------------------------------------------------------
+
+} // extern "C"

@@ -1,0 +1,727 @@
+// gysk_kernels.cu — hand-written sm_100a kernels of the streaming-sketch engine.
+//
+//   ingest_kernel        one pass over a batch of 32-byte events: id -> slot, then per event type
+//                          RESP : GY_HISTOGRAM::add_data (RESP_TIME_HASH)            common/gy_statistics.h:596-623, :1698
+//                                 + emit (slot, usec) sort key for the t-digest chain
+//                          TCP  : count-min cell adds, HLL register max, per-service exact cell
+//                          TASK : MAGGR_TASK::set_local_task_state (3 histograms)     server/gy_msocket.h:1009-1018
+//   rs_* / scan_*        stable LSD radix sort of the (slot, usec) keys (8-bit digits)
+//   td_segments/update   batched merging t-digest (K_1 scale, delta = 100)           DESIGN.md §t-digest
+//   flush_kernel         5-s window roll                                               common/gy_socket_stat.cc:3898
+//   gather_* / query_*   read side
+#include "gysk_kernels.cuh"
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+
+namespace gysk {
+
+static constexpr unsigned long long KEY_SENTINEL = ~0ull;
+static constexpr unsigned long long VALUE_MASK = (1ull << VALUE_BITS) - 1;
+
+// ---------------------------------------------------------------------------------------------------
+// state init / registration
+// ---------------------------------------------------------------------------------------------------
+__global__ void init_state_kernel(DevState st, uint32_t max_svcs, uint32_t max_tasks)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i < max_svcs) {
+		st.hist_cur[(size_t)i * HIST_CELLS + HIST_MAX_CELL].sum = LLONG_MIN;	// max_val_seen_{numeric_limits<T>::min()} gy_statistics.h:560
+		st.hist_last[(size_t)i * HIST_CELLS + HIST_MAX_CELL].sum = LLONG_MIN;
+		st.hist_all[(size_t)i * HIST_CELLS + HIST_MAX_CELL].sum = LLONG_MIN;
+		st.td_head[i].minv = INFINITY;
+		st.td_head[i].maxv = -INFINITY;
+	}
+	if (i < max_tasks) {
+		for (int h = 0; h < 3; ++h) st.task_hist[((size_t)i * 3 + h) * HIST_CELLS + HIST_MAX_CELL].sum = LLONG_MIN;
+	}
+}
+
+__global__ void register_kernel(DevState st, const unsigned long long *ids, uint32_t n, int is_task)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i < n && ids[i]) table_lookup(is_task ? st.task_tbl : st.svc_tbl, ids[i], true);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ingest
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hist_add(HistCell *h, int bucket, long long data)
+{
+	red_add_u64(&h[bucket].count, 1ull);
+	red_add_u64((unsigned long long *)&h[bucket].sum, (unsigned long long)data);
+	// max_val_seen_: read first, the atomic is needed only while the maximum still grows
+	if (data > *((volatile long long *)&h[HIST_MAX_CELL].sum)) atomicMax(&h[HIST_MAX_CELL].sum, data);
+}
+
+__device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t rank)
+{
+	uint32_t *wp = reinterpret_cast<uint32_t *>(regs) + (idx >> 2);
+	const uint32_t sh = (idx & 3u) * 8u;
+	uint32_t w = *((volatile uint32_t *)wp);
+
+	while (((w >> sh) & 0xFFu) < rank) {
+		const uint32_t nw = (w & ~(0xFFu << sh)) | (rank << sh);
+		const uint32_t old = atomicCAS(wp, w, nw);
+		if (old == w) break;
+		w = old;
+	}
+}
+
+__global__ void __launch_bounds__(256) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n, unsigned long long *__restrict__ keys)
+{
+	unsigned long long c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const uint4 a = __ldg(reinterpret_cast<const uint4 *>(ev + i));
+		const uint4 b = __ldg(reinterpret_cast<const uint4 *>(ev + i) + 1);
+		const unsigned long long svc_id = ((unsigned long long)a.y << 32) | a.x;
+		const unsigned long long flow_key = ((unsigned long long)a.w << 32) | a.z;
+		const uint32_t value = b.x, host_idx = b.y;
+		const uint32_t type = b.w & 0xFFFFu;
+		unsigned long long key = KEY_SENTINEL;
+
+		if (st.world > 1 && (host_idx % st.world) != st.rank) {
+			c_foreign++;
+		}
+		else {
+			c_in++;
+			if (svc_id == 0) {
+				c_drop++;
+			}
+			else if (type == GYSK_EV_RESP) {
+				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule
+				// of handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
+				const uint32_t ms = value / 1000u;
+				int slot = -1;
+				if (ms <= 1000000u) slot = table_lookup(st.svc_tbl, svc_id, st.auto_register);
+				if (slot < 0) c_drop++;
+				else {
+					hist_add(st.hist_cur + (size_t)slot * HIST_CELLS, bucket_resp_time((long long)ms), (long long)ms);
+					key = ((unsigned long long)(uint32_t)slot << VALUE_BITS) | value;
+					c_resp++;
+				}
+			}
+			else if (type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER) {
+				const int slot = table_lookup(st.svc_tbl, svc_id, st.auto_register);
+				if (slot < 0) c_drop++;
+				else {
+					const unsigned long long inc = cms_increment(value);
+					for (uint32_t r = 0; r < st.cms_depth; ++r) {
+						red_add_u64(st.cms_cur + ((size_t)r << st.cms_log2w) + cms_index(flow_key, r, st.cms_wmask), inc);
+					}
+					uint32_t idx, rank;
+					hll_idx_rank(flow_key, st.hll_p, idx, rank);
+					hll_update(st.hll + ((size_t)slot << st.hll_p), idx, rank);
+					red_add_u64(st.conn_cur + slot, inc);
+					c_tcp++;
+				}
+			}
+			else if (type == GYSK_EV_TASK) {
+				const int slot = table_lookup(st.task_tbl, svc_id, st.auto_register);
+				if (slot < 0) c_drop++;
+				else {
+					// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
+					HistCell *h = st.task_hist + (size_t)slot * 3 * HIST_CELLS;
+					const int cpu_pct = (int)value, cpu_delay = (int)(uint32_t)flow_key, blkio_delay = (int)(uint32_t)(flow_key >> 32);
+					hist_add(h, bucket_hash_1_3000(cpu_pct), (long long)cpu_pct);
+					hist_add(h + HIST_CELLS, bucket_duration(cpu_delay), (long long)cpu_delay);
+					hist_add(h + 2 * HIST_CELLS, bucket_duration(blkio_delay), (long long)blkio_delay);
+					c_task++;
+				}
+			}
+			else c_drop++;
+		}
+		keys[i] = key;
+	}
+
+	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) {
+		c_in += __shfl_down_sync(0xffffffffu, c_in, off);
+		c_drop += __shfl_down_sync(0xffffffffu, c_drop, off);
+		c_resp += __shfl_down_sync(0xffffffffu, c_resp, off);
+		c_tcp += __shfl_down_sync(0xffffffffu, c_tcp, off);
+		c_task += __shfl_down_sync(0xffffffffu, c_task, off);
+		c_foreign += __shfl_down_sync(0xffffffffu, c_foreign, off);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (c_in) atomicAdd(st.counters + CTR_IN, c_in);
+		if (c_drop) atomicAdd(st.counters + CTR_DROPPED, c_drop);
+		if (c_resp) atomicAdd(st.counters + CTR_RESP, c_resp);
+		if (c_tcp) atomicAdd(st.counters + CTR_TCP, c_tcp);
+		if (c_task) atomicAdd(st.counters + CTR_TASK, c_task);
+		if (c_foreign) atomicAdd(st.counters + CTR_FOREIGN, c_foreign);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stable LSD radix sort, 8-bit digits, tile = SORT_TILE keys per CTA of 256 threads
+// ---------------------------------------------------------------------------------------------------
+static constexpr int RS_THREADS = 256;
+static constexpr int RS_WARPS = RS_THREADS / 32;
+static constexpr int RS_ROUNDS = SORT_TILE / RS_THREADS;	// 16 keys per thread
+static constexpr int RADIX = 256;
+
+// per-tile digit histogram -> tile_hist[digit * ntiles + tile]
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long *__restrict__ keys, uint64_t n_host,
+		const unsigned long long *__restrict__ d_n, int shift, uint32_t *__restrict__ tile_hist, uint32_t ntiles)
+{
+	__shared__ uint32_t hist[RADIX];
+	const uint64_t n = d_n ? *d_n : n_host;
+	const uint32_t tile = blockIdx.x;
+
+	hist[threadIdx.x] = 0;
+	__syncthreads();
+
+	const uint64_t base = (uint64_t)tile * SORT_TILE;
+#pragma unroll 4
+	for (int r = 0; r < RS_ROUNDS; ++r) {
+		const uint64_t i = base + (uint64_t)r * RS_THREADS + threadIdx.x;
+		if (i < n) {
+			const unsigned long long k = keys[i];
+			if (k != KEY_SENTINEL) atomicAdd(&hist[(uint32_t)(k >> shift) & 0xFFu], 1u);
+		}
+	}
+	__syncthreads();
+	tile_hist[(size_t)threadIdx.x * ntiles + tile] = hist[threadIdx.x];
+}
+
+// exclusive scan of a u32 array of length len: reduce / scan block sums / apply
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_ITEMS = 8;
+static constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total_out, uint32_t *smem /* >= 32 */)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t incl = v;
+
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane >= off) incl += t;
+	}
+	if (lane == 31) smem[wid] = incl;
+	__syncthreads();
+	if (wid == 0) {
+		const int nw = blockDim.x >> 5;
+		uint32_t w = lane < nw ? smem[lane] : 0, wi = w;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, wi, off);
+			if (lane >= off) wi += t;
+		}
+		smem[lane] = wi - w;			// exclusive warp offsets
+		if (lane == nw - 1 && total_out) *total_out = wi;
+	}
+	__syncthreads();
+	const uint32_t res = smem[wid] + incl - v;
+	__syncthreads();
+	return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t *__restrict__ in, uint32_t len, uint32_t *__restrict__ block_sums)
+{
+	__shared__ uint32_t smem[32];
+	__shared__ uint32_t total;
+	const uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+	uint32_t s = 0;
+
+#pragma unroll
+	for (int j = 0; j < SCAN_ITEMS; ++j) if (base + j < len) s += in[base + j];
+	block_exclusive_scan(s, &total, smem);
+	if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of block_sums[nblocks] in place; grand total -> *total_out (u64 counter)
+__global__ void __launch_bounds__(1024) scan_blocksums_kernel(uint32_t *block_sums, uint32_t nblocks, unsigned long long *total_out)
+{
+	__shared__ uint32_t smem[32];
+	__shared__ uint32_t chunk_total;
+	uint32_t carry = 0;
+
+	for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = i < nblocks ? block_sums[i] : 0;
+		const uint32_t ex = block_exclusive_scan(v, &chunk_total, smem);
+		if (i < nblocks) block_sums[i] = carry + ex;
+		carry += chunk_total;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t *__restrict__ data, uint32_t len, const uint32_t *__restrict__ block_sums)
+{
+	__shared__ uint32_t smem[32];
+	const uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS], s = 0;
+
+#pragma unroll
+	for (int j = 0; j < SCAN_ITEMS; ++j) { v[j] = base + j < len ? data[base + j] : 0; s += v[j]; }
+	uint32_t ex = block_exclusive_scan(s, nullptr, smem) + block_sums[blockIdx.x];
+#pragma unroll
+	for (int j = 0; j < SCAN_ITEMS; ++j) { if (base + j < len) data[base + j] = ex; ex += v[j]; }
+}
+
+// scatter one tile to its stable positions. Thread t of warp w holds keys w*512 + r*32 + lane (r = 0..15), i.e.
+// ascending input order is (warp, round, lane); ranks come from match_any groups so equal digits keep that order.
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
+		uint64_t n_host, const unsigned long long *__restrict__ d_n, int shift, const uint32_t *__restrict__ tile_offs, uint32_t ntiles)
+{
+	__shared__ uint32_t whist[RS_WARPS][RADIX];
+	const uint64_t n = d_n ? *d_n : n_host;
+	const uint32_t tile = blockIdx.x;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+
+	if ((uint64_t)tile * SORT_TILE >= n) return;
+
+	for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&whist[0][0])[i] = 0;
+	__syncthreads();
+
+	unsigned long long k[RS_ROUNDS];
+	uint32_t grp[RS_ROUNDS];
+	const uint64_t wbase = (uint64_t)tile * SORT_TILE + (uint64_t)wid * (RS_ROUNDS * 32);
+
+#pragma unroll
+	for (int r = 0; r < RS_ROUNDS; ++r) {
+		const uint64_t i = wbase + (uint64_t)r * 32 + lane;
+		k[r] = i < n ? in[i] : KEY_SENTINEL;
+	}
+
+	// phase A: per-warp digit counts
+#pragma unroll
+	for (int r = 0; r < RS_ROUNDS; ++r) {
+		const bool valid = k[r] != KEY_SENTINEL;
+		const uint32_t d = valid ? ((uint32_t)(k[r] >> shift) & 0xFFu) : (0x100u + lane);
+		const uint32_t m = __match_any_sync(0xffffffffu, d);
+		grp[r] = m;
+		if (valid && (m & lt_mask) == 0) whist[wid][d] += __popc(m);
+		__syncwarp();
+	}
+	__syncthreads();
+
+	// exclusive prefix over warps per digit, seeded with this tile's global offset for the digit
+	{
+		const uint32_t d = threadIdx.x;
+		uint32_t run = tile_offs[(size_t)d * ntiles + tile];
+#pragma unroll
+		for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = whist[w][d]; whist[w][d] = run; run += t; }
+	}
+	__syncthreads();
+
+	// phase B: positions
+#pragma unroll
+	for (int r = 0; r < RS_ROUNDS; ++r) {
+		const bool valid = k[r] != KEY_SENTINEL;
+		if (valid) {
+			const uint32_t d = (uint32_t)(k[r] >> shift) & 0xFFu;
+			const uint32_t m = grp[r];
+			const uint32_t pos = whist[wid][d] + __popc(m & lt_mask);
+			out[pos] = k[r];
+		}
+		__syncwarp();
+		if (valid && (grp[r] & lt_mask) == 0) whist[wid][(uint32_t)(k[r] >> shift) & 0xFFu] += __popc(grp[r]);
+		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// batched merging t-digest
+// ---------------------------------------------------------------------------------------------------
+__global__ void td_segments_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
+		uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_end, uint32_t *__restrict__ touched, unsigned long long *ntouched)
+{
+	const uint64_t n = *d_n;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i >= n) return;
+	const uint32_t slot = (uint32_t)(keys[i] >> VALUE_BITS);
+	const uint32_t prev = i ? (uint32_t)(keys[i - 1] >> VALUE_BITS) : 0xFFFFFFFFu;
+	const uint32_t next = i + 1 < n ? (uint32_t)(keys[i + 1] >> VALUE_BITS) : 0xFFFFFFFFu;
+
+	if (slot != prev) {
+		seg_start[slot] = (uint32_t)i;
+		touched[atomicAdd(ntouched, 1ull)] = slot;
+	}
+	if (slot != next) seg_end[slot] = (uint32_t)(i + 1);
+}
+
+// K_1 scale function of the merging t-digest (Dunning), k spanning [-delta/2, delta/2]: k(q) = delta/pi asin(2q - 1)
+__device__ __forceinline__ double td_k(double q, double delta)
+{
+	return __dmul_rn(__ddiv_rn(delta, M_PI), asin(__dsub_rn(__dmul_rn(2.0, q), 1.0)));
+}
+
+__device__ __forceinline__ double td_q(double k, double delta)
+{
+	if (k >= __ddiv_rn(delta, 2.0)) return 1.0;
+	return __ddiv_rn(__dadd_rn(sin(__ddiv_rn(__dmul_rn(k, M_PI), delta)), 1.0), 2.0);
+}
+
+__device__ __forceinline__ double td_wlimit(unsigned long long wsofar, unsigned long long W, double delta)
+{
+	const double q0 = wsofar ? __ddiv_rn((double)wsofar, (double)W) : 0.0;
+	return __dmul_rn((double)W, td_q(__dadd_rn(td_k(q0, delta), 1.0), delta));
+}
+
+static constexpr int TD_WARPS = 4;
+
+struct TdScratch
+{
+	Centroid		newc[TD_CAP];
+	Centroid		merged[2 * TD_CAP];
+	unsigned long long	prefix[2 * TD_CAP + 1];
+	uint32_t		bounds[2 * TD_CAP + 1];
+};
+
+// one warp per touched service
+__global__ void __launch_bounds__(TD_WARPS * 32) td_update_kernel(DevState st, const unsigned long long *__restrict__ keys,
+		const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end, const uint32_t *__restrict__ touched,
+		const unsigned long long *__restrict__ ntouched_p)
+{
+	__shared__ TdScratch scratch[TD_WARPS];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	TdScratch &S = scratch[wid];
+	const uint32_t ntouched = (uint32_t)*ntouched_p;
+	const uint32_t nwarps = gridDim.x * TD_WARPS;
+	const double delta = st.td_delta;
+
+	for (uint32_t t = blockIdx.x * TD_WARPS + wid; t < ntouched; t += nwarps) {
+		const uint32_t slot = touched[t];
+		const uint32_t s0 = seg_start[slot];
+		const uint32_t n = seg_end[slot] - s0;
+		const unsigned long long *seg = keys + s0;
+
+		// ---- phase 1: greedy clustering of n sorted unit-weight samples; cluster [s, e), e = max(s+1, floor(wlimit))
+		uint32_t nnew = 0, s = 0;
+		while (s < n) {
+			uint32_t e = 0;
+			if (lane == 0) {
+				const double wl = td_wlimit(s, n, delta);
+				unsigned long long ee = (unsigned long long)floor(wl);
+				if (ee > n) ee = n;
+				if (ee < (unsigned long long)s + 1) ee = s + 1;
+				if (nnew == TD_CAP - 1) ee = n;
+				e = (uint32_t)ee;
+			}
+			e = __shfl_sync(0xffffffffu, e, 0);
+			unsigned long long sum = 0;
+			for (uint32_t i = s + lane; i < e; i += 32) sum += seg[i] & VALUE_MASK;
+#pragma unroll
+			for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
+			if (lane == 0) {
+				S.newc[nnew].mean = __ddiv_rn((double)sum, (double)(e - s));
+				S.newc[nnew].weight = e - s;
+			}
+			nnew++;
+			s = e;
+		}
+		const double bmin = (double)(seg[0] & VALUE_MASK), bmax = (double)(seg[n - 1] & VALUE_MASK);
+		__syncwarp();
+
+		// ---- phase 2: stable merge of old centroids (first on ties) and new clusters by mean
+		TdHead head = st.td_head[slot];
+		const uint32_t nold = head.n;
+		const Centroid *old = st.td_cent + (size_t)slot * TD_CAP;
+		const uint32_t nm = nold + nnew;
+
+		for (uint32_t j = lane; j < nold; j += 32) {
+			const Centroid c = old[j];
+			uint32_t lo = 0, hi = nnew;			// # new with mean < c.mean
+			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.newc[mid].mean < c.mean) lo = mid + 1; else hi = mid; }
+			S.merged[j + lo] = c;
+		}
+		for (uint32_t j = lane; j < nnew; j += 32) {
+			const Centroid c = S.newc[j];
+			uint32_t lo = 0, hi = nold;			// # old with mean <= c.mean
+			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (old[mid].mean <= c.mean) lo = mid + 1; else hi = mid; }
+			S.merged[j + lo] = c;
+		}
+		__syncwarp();
+
+		// exclusive prefix of weights: lane owns 8 consecutive items
+		{
+			unsigned long long w[8], tot = 0;
+#pragma unroll
+			for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; w[j] = i < nm ? S.merged[i].weight : 0; tot += w[j]; }
+			unsigned long long incl = tot;
+#pragma unroll
+			for (int off = 1; off < 32; off <<= 1) {
+				const unsigned long long tt = __shfl_up_sync(0xffffffffu, incl, off);
+				if (lane >= off) incl += tt;
+			}
+			unsigned long long ex = incl - tot;
+#pragma unroll
+			for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; if (i <= nm) S.prefix[i] = ex; ex += w[j]; }
+			if (lane == 31 && nm == 2 * TD_CAP) S.prefix[nm] = incl;
+		}
+		__syncwarp();
+
+		// greedy chain over the merged list (sequential, <= ~delta steps)
+		uint32_t nout = 0;
+		if (lane == 0) {
+			const unsigned long long W = S.prefix[nm];
+			uint32_t cs = 0;
+			while (cs < nm) {
+				const double wl = td_wlimit(S.prefix[cs], W, delta);
+				uint32_t lo = cs + 1, hi = nm;			// largest e in [cs+1, nm] with prefix[e] <= wl
+				while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if ((double)S.prefix[mid] <= wl) lo = mid; else hi = mid - 1; }
+				uint32_t e = lo;
+				if (nout == TD_CAP - 1) e = nm;
+				S.bounds[nout++] = cs;
+				cs = e;
+			}
+			S.bounds[nout] = nm;
+		}
+		nout = __shfl_sync(0xffffffffu, nout, 0);
+		__syncwarp();
+
+		Centroid *outc = st.td_cent + (size_t)slot * TD_CAP;
+		for (uint32_t c = lane; c < nout; c += 32) {
+			double csum = 0.0;
+			unsigned long long cw = 0;
+			for (uint32_t i = S.bounds[c]; i < S.bounds[c + 1]; ++i) {
+				csum = __dadd_rn(csum, __dmul_rn(S.merged[i].mean, (double)S.merged[i].weight));
+				cw += S.merged[i].weight;
+			}
+			Centroid o; o.mean = __ddiv_rn(csum, (double)cw); o.weight = cw;
+			outc[c] = o;
+		}
+		if (lane == 0) {
+			head.n = nout;
+			head.total += n;
+			if (bmin < head.minv) head.minv = bmin;
+			if (bmax > head.maxv) head.maxv = bmax;
+			st.td_head[slot] = head;
+		}
+		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 5-second window roll: last = cur; all += cur; cur = 0  (one thread per histogram cell)
+// ---------------------------------------------------------------------------------------------------
+__global__ void flush_kernel(DevState st, uint32_t nslots)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i >= (uint64_t)nslots * HIST_CELLS) return;
+	const int cell = (int)(i & (HIST_CELLS - 1));
+	const HistCell c = st.hist_cur[i];
+
+	st.hist_last[i] = c;
+	if (cell == HIST_MAX_CELL) {
+		if (c.sum > st.hist_all[i].sum) st.hist_all[i].sum = c.sum;
+		st.hist_cur[i].count = 0; st.hist_cur[i].sum = LLONG_MIN;
+		const uint32_t slot = (uint32_t)(i >> 4);
+		const unsigned long long cc = st.conn_cur[slot];
+		st.conn_last[slot] = cc;
+		st.conn_all_cnt[slot] += (uint32_t)cc;
+		st.conn_all_kb[slot] += cc >> 32;
+		st.conn_cur[slot] = 0;
+	}
+	else {
+		st.hist_all[i].count += c.count;
+		st.hist_all[i].sum += c.sum;
+		st.hist_cur[i].count = 0; st.hist_cur[i].sum = 0;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// read side: one warp per queried id
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gather_svcs_kernel(DevState st, const unsigned long long *__restrict__ ids, uint32_t n, SvcRaw *__restrict__ out)
+{
+	__shared__ uint32_t hh[4][64];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t q = blockIdx.x * 4 + wid;
+
+	if (q >= n) return;
+	SvcRaw &o = out[q];
+	const unsigned long long id = ids[q];
+	int slot = -1;
+	if (lane == 0 && id) slot = table_lookup(st.svc_tbl, id, false);
+	slot = __shfl_sync(0xffffffffu, slot, 0);
+	if (lane == 0) { o.id = id; o.found = slot >= 0; o.slot = (uint32_t)slot; }
+	if (slot < 0) return;
+
+	if (lane < HIST_CELLS) {
+		o.cur[lane] = st.hist_cur[(size_t)slot * HIST_CELLS + lane];
+		o.last[lane] = st.hist_last[(size_t)slot * HIST_CELLS + lane];
+		o.all[lane] = st.hist_all[(size_t)slot * HIST_CELLS + lane];
+	}
+	if (lane == 0) {
+		o.conn_cur = st.conn_cur[slot]; o.conn_last = st.conn_last[slot];
+		o.conn_all_cnt = st.conn_all_cnt[slot]; o.conn_all_kb = st.conn_all_kb[slot];
+		o.td = st.td_head[slot];
+	}
+	for (int i = lane; i < TD_CAP; i += 32) o.cent[i] = st.td_cent[(size_t)slot * TD_CAP + i];
+
+	hh[wid][lane] = 0; hh[wid][lane + 32] = 0;
+	__syncwarp();
+	const uint8_t *regs = st.hll + ((size_t)slot << st.hll_p);
+	for (uint32_t i = lane; i < (1u << st.hll_p); i += 32) atomicAdd(&hh[wid][regs[i] > 63 ? 63 : regs[i]], 1u);
+	__syncwarp();
+	o.hll_hist[lane] = hh[wid][lane]; o.hll_hist[lane + 32] = hh[wid][lane + 32];
+}
+
+__global__ void gather_tasks_kernel(DevState st, const unsigned long long *__restrict__ ids, uint32_t n, TaskRaw *__restrict__ out)
+{
+	const uint32_t q = blockIdx.x;
+	if (q >= n) return;
+	__shared__ int sslot;
+	if (threadIdx.x == 0) {
+		const unsigned long long id = ids[q];
+		sslot = id ? table_lookup(st.task_tbl, id, false) : -1;
+		out[q].id = id; out[q].found = sslot >= 0; out[q].slot = (uint32_t)sslot;
+	}
+	__syncthreads();
+	if (sslot < 0) return;
+	if (threadIdx.x < 3 * HIST_CELLS) (&out[q].h[0][0])[threadIdx.x] = st.task_hist[(size_t)sslot * 3 * HIST_CELLS + threadIdx.x];
+}
+
+__global__ void gather_hll_kernel(DevState st, unsigned long long id, uint8_t *__restrict__ out, int32_t *found)
+{
+	__shared__ int sslot;
+	if (threadIdx.x == 0) { sslot = id ? table_lookup(st.svc_tbl, id, false) : -1; *found = sslot >= 0; }
+	__syncthreads();
+	if (sslot < 0) return;
+	const uint8_t *regs = st.hll + ((size_t)sslot << st.hll_p);
+	for (uint32_t i = threadIdx.x; i < (1u << st.hll_p); i += blockDim.x) out[i] = regs[i];
+}
+
+__global__ void query_flows_kernel(DevState st, const unsigned long long *__restrict__ keys, uint32_t n, int last_window, gysk_flow_est *__restrict__ out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const unsigned long long *tbl = last_window ? st.cms_last : st.cms_cur;
+	const unsigned long long key = keys[i];
+	uint32_t cnt = 0xFFFFFFFFu, kb = 0xFFFFFFFFu;
+
+	for (uint32_t r = 0; r < st.cms_depth; ++r) {
+		const unsigned long long c = tbl[((size_t)r << st.cms_log2w) + cms_index(key, r, st.cms_wmask)];
+		cnt = min(cnt, (uint32_t)c);
+		kb = min(kb, (uint32_t)(c >> 32));
+	}
+	out[i].flow_key = key; out[i].count = cnt; out[i].kbytes = kb;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+static inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks, cudaStream_t s)
+{
+	const uint32_t m = max_svcs > max_tasks ? max_svcs : max_tasks;
+	init_state_kernel<<<div_up(m, 256), 256, 0, s>>>(st, max_svcs, max_tasks);
+	return 1;
+}
+
+int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_t n, int is_task, cudaStream_t s)
+{
+	if (!n) return 0;
+	register_kernel<<<div_up(n, 256), 256, 0, s>>>(st, d_ids, n, is_task);
+	return 1;
+}
+
+int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s)
+{
+	if (!n) return 0;
+	int dev = 0, nsm = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+	const uint64_t want = (n + 255) / 256;
+	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * 8 ? want : (uint64_t)nsm * 8);
+	ingest_kernel<<<grid, 256, 0, s>>>(st, d_ev, n, d_keys);
+	return 1;
+}
+
+static int launch_exclusive_scan(uint32_t *d_data, uint32_t len, uint32_t *d_block_sums, unsigned long long *d_total, cudaStream_t s)
+{
+	const uint32_t nblocks = div_up(len, SCAN_CHUNK);
+	scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(d_data, len, d_block_sums);
+	scan_blocksums_kernel<<<1, 1024, 0, s>>>(d_block_sums, nblocks, d_total);
+	scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(d_data, len, d_block_sums);
+	return 3;
+}
+
+// sort the (slot, usec) keys produced by ingest, then fold every touched service's new samples into its digest
+int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t max_svcs, cudaStream_t s)
+{
+	if (!n) return 0;
+	int launches = 0;
+	const uint32_t ntiles = div_up(n, SORT_TILE);
+	unsigned long long *d_nkeys = st.counters + CTR_NKEYS, *d_ntouched = st.counters + CTR_NTOUCHED;
+
+	uint32_t slot_bits = 1;
+	while (slot_bits < 32 && (1ull << slot_bits) < max_svcs) slot_bits++;
+	const int total_bits = VALUE_BITS + (int)slot_bits;
+
+	const unsigned long long *src = tmp.keys_a;
+	unsigned long long *dst = tmp.keys_b;
+	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
+	int which = 0;
+
+	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
+
+	for (int shift = 0, pass = 0; shift < total_bits; shift += 8, ++pass) {
+		const unsigned long long *dn = pass ? d_nkeys : nullptr;
+		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(src, n, dn, shift, tmp.tile_hist, ntiles);
+		launches += 1 + launch_exclusive_scan(tmp.tile_hist, RADIX * ntiles, tmp.scan_tmp, pass ? nullptr : d_nkeys, s);
+		rs_scatter_kernel<<<ntiles, RS_THREADS, 0, s>>>(src, dst, n, dn, shift, tmp.tile_hist, ntiles);
+		launches++;
+		which ^= 1;
+		src = bufs[which]; dst = bufs[which ^ 1];
+	}
+
+	td_segments_kernel<<<div_up(n, 256), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
+	int dev = 0, nsm = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+	td_update_kernel<<<nsm * 4, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
+	return launches + 2;
+}
+
+int launch_flush(const DevState &st, uint32_t nslots, cudaStream_t s)
+{
+	if (!nslots) return 0;
+	flush_kernel<<<div_up((uint64_t)nslots * HIST_CELLS, 256), 256, 0, s>>>(st, nslots);
+	return 1;
+}
+
+int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, SvcRaw *d_out, cudaStream_t s)
+{
+	if (!n) return 0;
+	gather_svcs_kernel<<<div_up(n, 4), 128, 0, s>>>(st, d_ids, n, d_out);
+	return 1;
+}
+
+int launch_gather_tasks(const DevState &st, const unsigned long long *d_ids, uint32_t n, TaskRaw *d_out, cudaStream_t s)
+{
+	if (!n) return 0;
+	gather_tasks_kernel<<<n, 64, 0, s>>>(st, d_ids, n, d_out);
+	return 1;
+}
+
+int launch_gather_hll(const DevState &st, unsigned long long id, uint8_t *d_out, int32_t *d_found, cudaStream_t s)
+{
+	gather_hll_kernel<<<1, 256, 0, s>>>(st, id, d_out, d_found);
+	return 1;
+}
+
+int launch_query_flows(const DevState &st, const unsigned long long *d_keys, uint32_t n, int last_window, gysk_flow_est *d_out, cudaStream_t s)
+{
+	if (!n) return 0;
+	query_flows_kernel<<<div_up(n, 256), 256, 0, s>>>(st, d_keys, n, last_window, d_out);
+	return 1;
+}
+
+} // namespace gysk

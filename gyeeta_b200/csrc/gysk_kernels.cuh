@@ -1,0 +1,75 @@
+// gysk_kernels.cuh — launch interface between the engine runtime (gysk_engine.cu) and the kernels.
+#pragma once
+
+#include "gysk_device.cuh"
+#include "../../include/gysketch.h"
+
+namespace gysk {
+
+struct DevState
+{
+	// id tables
+	IdTable			svc_tbl, task_tbl;
+	// per-service state, indexed by slot
+	HistCell		*hist_cur, *hist_last, *hist_all;	// [max_svcs][16]
+	unsigned long long	*conn_cur, *conn_last;			// packed {count:32, kbytes:32}
+	unsigned long long	*conn_all_cnt, *conn_all_kb;
+	uint8_t			*hll;					// [max_svcs][1 << hll_p]
+	Centroid		*td_cent;				// [max_svcs][TD_CAP]
+	TdHead			*td_head;				// [max_svcs]
+	// per-task state
+	HistCell		*task_hist;				// [max_tasks][3][16]
+	// flow sketch
+	unsigned long long	*cms_cur, *cms_last;			// [depth][1 << log2w]
+	uint32_t		cms_depth, cms_wmask, cms_log2w, hll_p;
+	uint32_t		rank, world, auto_register;
+	double			td_delta;
+	unsigned long long	*counters;				// [CTR_MAX]
+};
+
+struct SortTemp
+{
+	unsigned long long	*keys_a, *keys_b;	// [max_batch]
+	uint32_t		*tile_hist;		// [256 * max_tiles]
+	uint32_t		*scan_tmp;		// block sums for the scan
+	uint32_t		*seg_start, *seg_end;	// [max_svcs]
+	uint32_t		*touched;		// [max_svcs]
+	uint32_t		max_tiles;
+};
+
+// raw per-id record gathered for queries / exports
+struct SvcRaw
+{
+	unsigned long long	id;
+	int32_t			found;
+	uint32_t		slot;
+	HistCell		cur[HIST_CELLS], last[HIST_CELLS], all[HIST_CELLS];
+	unsigned long long	conn_cur, conn_last, conn_all_cnt, conn_all_kb;
+	uint32_t		hll_hist[64];
+	TdHead			td;
+	Centroid		cent[TD_CAP];
+};
+
+struct TaskRaw
+{
+	unsigned long long	id;
+	int32_t			found;
+	uint32_t		slot;
+	HistCell		h[3][HIST_CELLS];
+};
+
+static constexpr int SORT_TILE = 4096;		// keys per CTA tile in the radix passes
+static constexpr int VALUE_BITS = 30;		// RESP usec < 2^30 (msec <= 1e6 is enforced at ingest)
+
+// every launcher returns the number of kernel launches it issued
+int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks, cudaStream_t s);
+int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_t n, int is_task, cudaStream_t s);
+int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s);
+int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t max_svcs, cudaStream_t s);
+int launch_flush(const DevState &st, uint32_t max_svcs, cudaStream_t s);
+int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, SvcRaw *d_out, cudaStream_t s);
+int launch_gather_tasks(const DevState &st, const unsigned long long *d_ids, uint32_t n, TaskRaw *d_out, cudaStream_t s);
+int launch_gather_hll(const DevState &st, unsigned long long id, uint8_t *d_out, int32_t *d_found, cudaStream_t s);
+int launch_query_flows(const DevState &st, const unsigned long long *d_keys, uint32_t n, int last_window, gysk_flow_est *d_out, cudaStream_t s);
+
+} // namespace gysk

@@ -1,0 +1,263 @@
+"""ctypes binding of libgysketch.so (the C ABI of include/gysketch.h). Fails loudly when the CUDA library is missing."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgysketch.so")
+
+EVENT_DTYPE = np.dtype([("svc_id", "<u8"), ("flow_key", "<u8"), ("value", "<u4"), ("host_idx", "<u4"),
+                        ("tsec", "<u4"), ("type", "<u2"), ("flags", "<u2")], align=True)
+assert EVENT_DTYPE.itemsize == 32
+SERIAL_DTYPE = np.dtype([("count", "<u8"), ("sum", "<i8")])
+FLOW_EST_DTYPE = np.dtype([("flow_key", "<u8"), ("count", "<u4"), ("kbytes", "<u4")])
+
+EV_CONNECT, EV_ACCEPT, EV_CLOSE_CLI, EV_CLOSE_SER, EV_RESP, EV_TASK = 1, 2, 3, 4, 5, 6
+HIST_RESP_CUR, HIST_RESP_LAST, HIST_RESP_ALL, HIST_TASK_CPU_PCT, HIST_TASK_CPU_DELAY, HIST_TASK_BLKIO_DELAY = range(6)
+RAW_EVENT32, RAW_TCP_IPV4_EVENT, RAW_TCP_IPV4_RESP = 0, 1, 2
+NOTIFY_LISTENER_STATE, NOTIFY_TCP_CONN, NOTIFY_AGGR_TASK_STATE = 0x309, 0x30C, 0x310
+FLAG_AUTO_REGISTER = 1
+TD_CAP = 128
+
+
+class GyskError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gysketch error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("max_svcs", C.c_uint32), ("max_tasks", C.c_uint32),
+                ("cms_depth", C.c_uint32), ("cms_log2_width", C.c_uint32), ("hll_p", C.c_uint32),
+                ("td_compression", C.c_uint32), ("max_batch", C.c_uint32), ("flags", C.c_uint32), ("rank", C.c_uint32),
+                ("world", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+
+
+class SvcSummary(C.Structure):
+    _fields_ = [("glob_id", C.c_uint64), ("found", C.c_int32), ("nqrys_5s", C.c_uint32), ("total_resp_5sec", C.c_uint64),
+                ("p95_5s_resp_ms", C.c_int64), ("p99_5s_resp_ms", C.c_int64), ("p25_5s_resp_ms", C.c_int64),
+                ("p95_all_resp_ms", C.c_int64), ("p99_all_resp_ms", C.c_int64), ("nqrys_all", C.c_uint64),
+                ("max_resp_ms", C.c_int64), ("nconns_5s", C.c_uint32), ("kbytes_5s", C.c_uint32), ("nconns_all", C.c_uint64),
+                ("kbytes_all", C.c_uint64), ("distinct_clients", C.c_double), ("td_p50_us", C.c_double),
+                ("td_p95_us", C.c_double), ("td_p99_us", C.c_double), ("td_count", C.c_uint64)]
+
+    def asdict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("events_in", "events_dropped", "events_resp", "events_tcp", "events_task", "nsvcs",
+                                          "ntasks", "batches", "kernel_launches", "wire_msgs_ok", "wire_msgs_bad")]
+
+    def asdict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class BufferDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("dptr", C.c_void_p), ("nbytes", C.c_uint64), ("redop", C.c_int32), ("pad", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libgysketch.so. Raises when it has not been built: there is no fallback implementation."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise GyskError(-19, f"{path} is missing: build it with `python -m gyeeta_b200.build` "
+                             "(CUDA library is the product; no CPU fallback exists)")
+    L = C.CDLL(path)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    sig = {
+        "gysk_abi_version": (i32, []),
+        "gysk_config_default": (None, [vp]),
+        "gysk_create": (i32, [vp, vp]),
+        "gysk_destroy": (None, [vp]),
+        "gysk_last_error": (C.c_char_p, [vp]),
+        "gysk_get_stats": (i32, [vp, vp]),
+        "gysk_register_ids": (i32, [vp, vp, u32, i32]),
+        "gysk_ingest": (i32, [vp, vp, u32, u32, vp, u32, vp]),
+        "gysk_ingest_msg": (i32, [vp, vp, u32, vp, u32]),
+        "gysk_ingest_raw": (i32, [vp, vp, u32, u32, vp, u32]),
+        "gysk_ingest_pinned": (i32, [vp, vp, u64]),
+        "gysk_ingest_device": (i32, [vp, vp, u64]),
+        "gysk_sync": (i32, [vp]),
+        "gysk_flush": (i32, [vp, u32]),
+        "gysk_query_svcs": (i32, [vp, vp, u32, vp]),
+        "gysk_query_flows": (i32, [vp, vp, u32, i32, vp]),
+        "gysk_export_hist": (i32, [vp, u64, i32, vp, vp, vp]),
+        "gysk_export_task_hist": (i32, [vp, u64, i32, vp, vp, vp]),
+        "gysk_export_hll": (i32, [vp, u64, vp]),
+        "gysk_export_tdigest": (i32, [vp, u64, vp, vp, u32, vp, vp, vp]),
+        "gysk_query_quantiles": (i32, [vp, u64, vp, u32, vp]),
+        "gysk_export_cms": (i32, [vp, i32, vp]),
+        "gysk_hist_nbuckets": (i32, [i32]),
+        "gysk_hist_bucket": (i32, [i32, C.c_int64]),
+        "gysk_hist_percentiles": (i32, [i32, i32, vp, u64, vp, u32, vp]),
+        "gysk_hll_estimate": (C.c_double, [vp, u32]),
+        "gysk_tdigest_quantile": (C.c_double, [vp, vp, u32, C.c_double, C.c_double, C.c_double]),
+        "gysk_uint64_hash": (u32, [u64]),
+        "gysk_set_logical_map": (i32, [vp, vp, vp, u32]),
+        "gysk_merge_prepare": (i32, [vp]),
+        "gysk_merge_buffers": (i32, [vp, vp, u32, vp]),
+        "gysk_merge_tdigest_slab": (i32, [vp, vp, vp]),
+        "gysk_merge_finish": (i32, [vp, vp, u32]),
+        "gysk_query_logical": (i32, [vp, vp, u32, vp]),
+        "gysk_stream": (vp, [vp]),
+        "gysk_profile_enable": (i32, [vp, i32]),
+        "gysk_profile_read": (i32, [vp, vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)          # AttributeError here = the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    if path == LIB_PATH:
+        _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One engine = one GPU. Mirrors the C ABI one to one."""
+
+    def __init__(self, device=0, max_svcs=1 << 14, max_tasks=1 << 12, cms_depth=4, cms_log2_width=20, hll_p=12,
+                 td_compression=100, max_batch=1 << 20, auto_register=True, rank=0, world=1):
+        self.L = load_library()
+        cfg = Config()
+        self.L.gysk_config_default(C.byref(cfg))
+        cfg.device, cfg.max_svcs, cfg.max_tasks = device, max_svcs, max_tasks
+        cfg.cms_depth, cfg.cms_log2_width, cfg.hll_p, cfg.td_compression = cms_depth, cms_log2_width, hll_p, td_compression
+        cfg.max_batch = max_batch
+        cfg.flags = FLAG_AUTO_REGISTER if auto_register else 0
+        cfg.rank, cfg.world = rank, world
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.L.gysk_create(C.byref(cfg), C.byref(self.h))
+        if rc:
+            raise GyskError(rc, (self.L.gysk_last_error(None) or b"").decode())
+        self._host_id = (C.c_uint8 * 16)()
+
+    def _chk(self, rc):
+        if rc:
+            raise GyskError(rc, (self.L.gysk_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gysk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- ingest ----
+    def register_ids(self, ids, is_task=False):
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        self._chk(self.L.gysk_register_ids(self.h, _p(ids), len(ids), int(is_task)))
+
+    def ingest_events(self, ev, host_idx=0):
+        assert ev.dtype == EVENT_DTYPE
+        ev = np.ascontiguousarray(ev)
+        self._chk(self.L.gysk_ingest_raw(self.h, self._host_id, host_idx, RAW_EVENT32, _p(ev), len(ev)))
+
+    def ingest_raw(self, kind, buf, n, host_idx=0):
+        self._chk(self.L.gysk_ingest_raw(self.h, self._host_id, host_idx, kind, _p(buf), n))
+
+    def ingest_pinned_ptr(self, ptr, n):
+        self._chk(self.L.gysk_ingest_pinned(self.h, C.c_void_p(ptr), n))
+
+    def ingest_device_ptr(self, dptr, n):
+        self._chk(self.L.gysk_ingest_device(self.h, C.c_void_p(dptr), n))
+
+    def ingest_msg(self, msg, host_idx=0):
+        """msg: writable bytes-like holding COMM_HEADER + EVENT_NOTIFY + records"""
+        buf = np.frombuffer(msg, dtype=np.uint8)
+        return self.L.gysk_ingest_msg(self.h, self._host_id, host_idx, _p(buf), len(buf))
+
+    def sync(self):
+        self._chk(self.L.gysk_sync(self.h))
+
+    def flush(self, tsec=0):
+        self._chk(self.L.gysk_flush(self.h, tsec))
+
+    def stream(self):
+        return self.L.gysk_stream(self.h)
+
+    def profile_enable(self, on=True):
+        self._chk(self.L.gysk_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        a, b, n = C.c_double(), C.c_double(), C.c_uint64()
+        self._chk(self.L.gysk_profile_read(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    # ---- queries ----
+    def stats(self):
+        s = Stats()
+        self._chk(self.L.gysk_get_stats(self.h, C.byref(s)))
+        return s.asdict()
+
+    def query_svcs(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = (SvcSummary * len(ids))()
+        self._chk(self.L.gysk_query_svcs(self.h, _p(ids), len(ids), out))
+        return [o.asdict() for o in out]
+
+    def query_flows(self, keys, last_window=False):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.zeros(len(keys), dtype=FLOW_EST_DTYPE)
+        self._chk(self.L.gysk_query_flows(self.h, _p(keys), len(keys), int(last_window), _p(out)))
+        return out
+
+    def export_hist(self, id_, which):
+        out = np.zeros(15, dtype=SERIAL_DTYPE)
+        total, mx = C.c_uint64(), C.c_int64()
+        rc = self.L.gysk_export_hist(self.h, int(id_), which, _p(out), C.byref(total), C.byref(mx))
+        if rc == -2:
+            return None
+        self._chk(rc)
+        return out, total.value, mx.value
+
+    def export_hll(self, id_):
+        regs = np.zeros(1 << self.cfg.hll_p, dtype=np.uint8)
+        rc = self.L.gysk_export_hll(self.h, int(id_), _p(regs))
+        if rc == -2:
+            return None
+        self._chk(rc)
+        return regs
+
+    def export_tdigest(self, id_):
+        means = np.zeros(TD_CAP, dtype=np.float64)
+        weights = np.zeros(TD_CAP, dtype=np.uint64)
+        n, mn, mx = C.c_uint32(), C.c_double(), C.c_double()
+        rc = self.L.gysk_export_tdigest(self.h, int(id_), _p(means), _p(weights), TD_CAP, C.byref(n), C.byref(mn), C.byref(mx))
+        if rc == -2:
+            return None
+        self._chk(rc)
+        return means[: n.value].copy(), weights[: n.value].copy(), mn.value, mx.value
+
+    def quantiles(self, id_, qs):
+        qs = np.ascontiguousarray(qs, dtype=np.float64)
+        out = np.zeros(len(qs), dtype=np.float64)
+        self._chk(self.L.gysk_query_quantiles(self.h, int(id_), _p(qs), len(qs), _p(out)))
+        return out
+
+    def export_cms(self, last_window=False):
+        out = np.zeros(self.cfg.cms_depth << self.cfg.cms_log2_width, dtype=np.uint64)
+        self._chk(self.L.gysk_export_cms(self.h, int(last_window), _p(out)))
+        return out

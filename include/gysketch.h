@@ -211,7 +211,12 @@ int		gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, u
 int		gysk_ingest_msg(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, void *comm_header_msg, uint32_t msglen);
 int		gysk_ingest_raw(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, uint32_t kind,
 				const void *events, uint32_t nevents);
+/* zero-copy variant for GYSK_RAW_EVENT32 in page-locked host memory: the buffer is read asynchronously and must stay
+ * valid and unmodified until the next gysk_sync() returns */
+int		gysk_ingest_pinned(gysk_engine *e, const gysk_event *pinned_events, uint64_t nevents);
 int		gysk_ingest_device(gysk_engine *e, const gysk_event *d_events, uint64_t nevents);
+int		gysk_export_task_hist(gysk_engine *e, uint64_t aggr_task_id, int which, gysk_hist_serial out[GYSK_HIST_MAX_BUCKETS],
+				uint64_t *total_count, int64_t *max_val);
 int		gysk_sync(gysk_engine *e);
 int		gysk_flush(gysk_engine *e, uint32_t tsec);
 
@@ -221,8 +226,8 @@ int		gysk_query_flows(gysk_engine *e, const uint64_t *flow_keys, uint32_t n, int
 int		gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial out[GYSK_HIST_MAX_BUCKETS],
 				uint64_t *total_count, int64_t *max_val);
 int		gysk_export_hll(gysk_engine *e, uint64_t glob_id, uint8_t *regs /* 1 << hll_p bytes */);
-int		gysk_export_tdigest(gysk_engine *e, uint64_t glob_id, float *means, float *weights, uint32_t cap, uint32_t *n,
-				float *min_val, float *max_val);
+int		gysk_export_tdigest(gysk_engine *e, uint64_t glob_id, double *means, uint64_t *weights, uint32_t cap, uint32_t *n,
+				double *min_val, double *max_val);
 int		gysk_query_quantiles(gysk_engine *e, uint64_t glob_id, const double *qs, uint32_t nq, double *out);
 int		gysk_export_cms(gysk_engine *e, int last_window, uint64_t *cells /* depth << log2_width entries */);
 
@@ -232,7 +237,7 @@ int		gysk_hist_bucket(int cls, int64_t value);	/* RESP_TIME_HASH::get_bucket_fro
 int		gysk_hist_percentiles(int cls, int t_is_int, const gysk_hist_serial *stats, uint64_t total_count,
 				const float *pcts, uint32_t npct, int64_t *out);
 double		gysk_hll_estimate(const uint8_t *regs, uint32_t p);
-double		gysk_tdigest_quantile(const float *means, const float *weights, uint32_t n, float min_val, float max_val, double q);
+double		gysk_tdigest_quantile(const double *means, const uint64_t *weights, uint32_t n, double min_val, double max_val, double q);
 uint32_t	gysk_uint64_hash(uint64_t key);		/* get_uint64_hash, common/gy_common_inc.h:1120 */
 
 /* ---- multi-GPU merge ---- */
@@ -242,6 +247,11 @@ int		gysk_merge_buffers(gysk_engine *e, gysk_buffer_desc *out, uint32_t cap, uin
 int		gysk_merge_tdigest_slab(gysk_engine *e, void **dptr, uint64_t *nbytes);	/* fixed slab to all-gather */
 int		gysk_merge_finish(gysk_engine *e, const void *d_gathered_slabs, uint32_t world);
 int		gysk_query_logical(gysk_engine *e, const uint64_t *logical_ids, uint32_t n, gysk_svc_summary *out);
+
+/* per-kernel device timing (CUDA events on the launching stream around the ingest kernel and around the sort +
+ * t-digest chain of every device batch). read() synchronises, returns the sums since the last read and resets. */
+int		gysk_profile_enable(gysk_engine *e, int on);
+int		gysk_profile_read(gysk_engine *e, double *ms_ingest, double *ms_tdigest, uint64_t *nbatches);
 
 /* CUDA stream the engine launches on (cudaStream_t as void*), for callers timing with events */
 void *		gysk_stream(gysk_engine *e);

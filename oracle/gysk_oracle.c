@@ -317,18 +317,20 @@ double gyo_hll_estimate(const uint8_t *regs, uint32_t p)
 
 /* ------------------------------------------------------------------------------------------------
  * t-digest (PARITY UNPINNED). Published algorithm: T. Dunning, "The t-digest: efficient estimates of
- * distributions" — merging variant, scale function K_1: k(q) = delta/(2 pi) asin(2q - 1).
- * The reference only fixes delta = 100 (public.tdigest(x, 100), common/gy_query_common.cc:1855).
+ * distributions" — merging variant, scale function K_1 normalised so that k spans [-delta/2, delta/2]:
+ * k(q) = delta/pi asin(2q - 1), i.e. about delta centroids — the meaning "100" has for both t-digest users of the
+ * reference (Postgres public.tdigest(x, 100), common/gy_query_common.cc:1855; folly::TDigest(100) behind
+ * SlidingWindowQuantileEstimator, test/test_quantiles.cc:32).
  * ------------------------------------------------------------------------------------------------ */
 static inline double td_k(double q, double delta)
 {
-	return delta / (2.0 * M_PI) * asin(2.0 * q - 1.0);
+	return delta / M_PI * asin(2.0 * q - 1.0);
 }
 
 static inline double td_q(double k, double delta)
 {
-	if (k >= delta / 4.0) return 1.0;
-	return (sin(k * 2.0 * M_PI / delta) + 1.0) / 2.0;
+	if (k >= delta / 2.0) return 1.0;
+	return (sin(k * M_PI / delta) + 1.0) / 2.0;
 }
 
 void gyo_td_init(gyo_tdigest *t)
@@ -355,7 +357,7 @@ uint32_t gyo_td_compress(const gyo_centroid *in, uint32_t n, double delta, gyo_c
 	for (uint32_t i = 1; i < n; ++i) {
 		double projected = (double)(wsofar + cw + in[i].weight);
 
-		if (projected <= wlimit) {
+		if (projected <= wlimit || nout + 1 == cap) {		/* the last slot absorbs whatever is left */
 			cw += in[i].weight;
 			csum += in[i].mean * (double)in[i].weight;
 		}
@@ -411,12 +413,12 @@ void gyo_td_add_batch(gyo_tdigest *t, const uint32_t *vals, uint32_t n, double d
 
 		if (e > n) e = n;
 		if (e < s + 1) e = s + 1;
+		if (nnew == GYO_TD_CAP - 1) e = n;			/* the last slot absorbs whatever is left */
 		for (uint64_t i = s; i < e; ++i) sum += sv[i];
 		if (nnew < GYO_TD_CAP) { newc[nnew].mean = (double)sum / (double)(e - s); newc[nnew].weight = e - s; }
 		nnew++;
 		s = (uint32_t)e;
 	}
-	if (nnew > GYO_TD_CAP) nnew = GYO_TD_CAP;	/* cannot happen for delta <= 2*GYO_TD_CAP/... ; asserted in tests */
 
 	if ((double)sv[0] < t->minv) t->minv = (double)sv[0];
 	if ((double)sv[n - 1] > t->maxv) t->maxv = (double)sv[n - 1];
@@ -531,6 +533,8 @@ struct gyo_engine
 	task_state	*tasks;
 	uint64_t	*cms_cur, *cms_last;
 	uint64_t	n_in, n_drop, n_resp, n_tcp, n_task, n_foreign;
+	uint32_t	*touched;		/* slots with pending RESP samples in the batch being ingested */
+	uint32_t	ntouched;
 };
 
 static uint32_t pow2_at_least(uint32_t v) { uint32_t p = 16; while (p < v) p <<= 1; return p; }
@@ -572,6 +576,7 @@ gyo_engine *gyo_create(uint32_t max_svcs, uint32_t max_tasks, uint32_t cms_depth
 	e->tasks = (task_state *)calloc(max_tasks ? max_tasks : 1, sizeof(task_state));
 	e->cms_cur = (uint64_t *)calloc((size_t)cms_depth << cms_log2_width, sizeof(uint64_t));
 	e->cms_last = (uint64_t *)calloc((size_t)cms_depth << cms_log2_width, sizeof(uint64_t));
+	e->touched = (uint32_t *)malloc(sizeof(uint32_t) * max_svcs);
 	return e;
 }
 
@@ -579,7 +584,7 @@ void gyo_destroy(gyo_engine *e)
 {
 	if (!e) return;
 	for (uint32_t i = 0; i < e->smap.n; ++i) { free(e->svcs[i].hll); free(e->svcs[i].pend); }
-	free(e->svcs); free(e->tasks); free(e->cms_cur); free(e->cms_last);
+	free(e->svcs); free(e->tasks); free(e->cms_cur); free(e->cms_last); free(e->touched);
 	free(e->smap.keys); free(e->smap.vals); free(e->tmap.keys); free(e->tmap.vals);
 	free(e);
 }
@@ -648,6 +653,7 @@ int gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n)
 			svc_state *s = get_svc(e, p->svc_id, autoreg);
 			if (!s) { e->n_drop++; break; }
 			gyo_hist_add(&s->cur, (int64_t)ms);
+			if (s->npend == 0) e->touched[e->ntouched++] = (uint32_t)(s - e->svcs);
 			if (s->npend == s->cappend) {
 				s->cappend = s->cappend ? s->cappend * 2 : 16;
 				s->pend = (uint32_t *)realloc(s->pend, sizeof(uint32_t) * s->cappend);
@@ -690,13 +696,13 @@ int gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n)
 	}
 
 	/* end of device batch: batched t-digest update per touched service */
-	for (uint32_t i = 0; i < e->smap.n; ++i) {
-		svc_state *s = &e->svcs[i];
-		if (s->npend) {
-			gyo_td_add_batch(&s->td, s->pend, s->npend, e->delta);
-			s->npend = 0;
-		}
+	for (uint32_t i = 0; i < e->ntouched; ++i) {
+		svc_state *s = &e->svcs[e->touched[i]];
+
+		gyo_td_add_batch(&s->td, s->pend, s->npend, e->delta);
+		s->npend = 0;
 	}
+	e->ntouched = 0;
 	return 0;
 }
 

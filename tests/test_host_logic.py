@@ -1,0 +1,126 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol include/gysketch.h declares; the pure host
+helpers of the library (percentile rule, bucket ids, estimators) agree with the oracle; the t-digest oracle variants agree
+within epsilon and obey the sketch's rank-error bound; creating an engine without a GPU fails loudly."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gyeeta_b200 import engine as ge
+from gyeeta_b200 import synth
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gysketch.h")).read()
+    names = set(re.findall(r"\b(gysk_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"gysk_svc_summary", "gysk_flow_est"}
+    assert len(names) >= 35
+    L = C.CDLL(ge.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert ge.load_library().gysk_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ge.GyskError) as ei:
+        ge.Engine()
+    assert ei.value.code == -19 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_touches_the_oracle():
+    """the product tree may not import / link / dlopen anything under oracle/"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gyeeta_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in src and "libgyoracle" not in src and "gyo_" not in src and "gyref" not in src, f
+    out = os.popen(f"ldd {ge.LIB_PATH}").read()
+    assert "gyoracle" not in out and "gyref" not in out
+
+
+def test_host_helpers_match_oracle():
+    L, O = ge.load_library(), po.lib()
+    rng = np.random.default_rng(2)
+    assert L.gysk_uint64_hash(42) == 4033382092
+    vals = np.concatenate([rng.integers(-100, 200000, 3000), rng.integers(-2 ** 40, 2 ** 40, 500), [2 ** 31, 2 ** 32 + 5, -1, 0]])
+    for cls in range(8):
+        assert L.gysk_hist_nbuckets(cls) == O.gyo_nbuckets(cls)
+        for v in vals:
+            assert L.gysk_hist_bucket(cls, int(v)) == O.gyo_bucket(cls, int(v)), (cls, v)
+    pcts = np.array([25, 50, 95, 99, 99.999, 0.001, 100], dtype=np.float32)
+    for cls in range(8):
+        for tk in (0, 1):
+            for scale in (10, 2 ** 25, 2 ** 40):
+                r = po.hist_run(O, "gyo_hist_run", cls, tk, rng.integers(-5, 70000, 2000), pcts)
+                stats = np.zeros(15, dtype=ge.SERIAL_DTYPE)
+                stats[: r["nb"]] = r["stats"]
+                stats["count"] *= scale          # exercise the float cut-off far beyond 2^24
+                total = int(stats["count"].sum())
+                h = np.zeros(1, dtype=np.dtype([("stats", po.SERIAL_DTYPE, 16), ("total", "<u8"), ("max", "<i8"), ("cls", "<i4"), ("tk", "<i4")]))
+                h["stats"][0][:15] = stats
+                h["total"], h["cls"], h["tk"] = total, cls, tk
+                want = np.zeros(len(pcts), dtype=np.int64)
+                O.gyo_hist_percentiles(po._p(h), po._p(pcts), C.c_size_t(len(pcts)), po._p(want), None)
+                got = np.zeros(len(pcts), dtype=np.int64)
+                assert L.gysk_hist_percentiles(cls, tk, ge._p(stats), total, ge._p(pcts), len(pcts), ge._p(got)) == 0
+                assert np.array_equal(got, want), (cls, tk, scale)
+    for p in (4, 8, 12, 16):
+        regs = rng.integers(0, 40, 1 << p).astype(np.uint8) * (rng.random(1 << p) < 0.6)
+        regs = regs.astype(np.uint8)
+        assert L.gysk_hll_estimate(ge._p(regs), p) == O.gyo_hll_estimate(po._p(regs), p)
+    td = po.td_add(po.td_new(), rng.integers(0, 10 ** 8, 50000).astype(np.uint32))
+    means, weights = td.centroids()
+    for q in (0.0, 0.001, 0.5, 0.95, 0.99, 0.9999, 1.0):
+        assert L.gysk_tdigest_quantile(ge._p(means), ge._p(weights), len(means), td.minv, td.maxv, q) == po.td_quantile(td, q)
+
+
+def test_tdigest_oracle_properties():
+    rng = np.random.default_rng(4)
+    for sigma, n in ((1.2, 200_000), (1.5, 50_000), (0.5, 10_000)):
+        x = np.minimum(np.exp(rng.normal(np.log(2000.0), sigma, n)), 9e8).astype(np.uint32)
+        tb = po.td_new()
+        for ch in np.array_split(x, 5):
+            po.td_add(tb, ch)
+        tc = po.td_add(po.td_new(), x, classic=True)
+        mb, wb = tb.centroids()
+        assert int(wb.sum()) == n == tb.total and tb.n <= po.TD_CAP and tc.n <= po.TD_CAP
+        assert np.all(np.diff(mb) >= 0) and tb.minv == x.min() and tb.maxv == x.max()
+        xs = np.sort(x)
+        for q in (0.5, 0.95, 0.99):
+            ex = float(xs[int(np.ceil(q * n)) - 1])
+            for td in (tb, tc):
+                g = po.td_quantile(td, q)
+                assert abs(np.searchsorted(xs, g) / n - q) < 0.002, (sigma, n, q)          # rank error: what a t-digest bounds
+                assert abs(g - ex) / ex < (0.01 if q < 0.99 else 0.035), (sigma, n, q, g, ex)
+    # tiny inputs
+    t = po.td_add(po.td_new(), np.array([7], dtype=np.uint32))
+    assert t.n == 1 and po.td_quantile(t, 0.5) == 7.0
+    t = po.td_add(po.td_new(), np.array([5, 5, 5, 5], dtype=np.uint32))
+    assert po.td_quantile(t, 0.99) == 5.0
+
+
+def test_oracle_engine_sharded_merge_equals_single():
+    """world_size-2 statement of the merge step on the CPU oracle: shards merged with gyo_merge_from == one engine"""
+    rng = np.random.default_rng(8)
+    ev = synth.gen_mixed(rng, 60_000, 200, ntask=16, nhosts=32, nclients=3000)
+    one = po.OracleEngine(max_svcs=512, max_tasks=64, cms_log2_width=12)
+    one.ingest(ev)
+    sh = [po.OracleEngine(max_svcs=512, max_tasks=64, cms_log2_width=12, rank=r, world=2) for r in range(2)]
+    for s in sh:
+        s.ingest(ev)
+    assert sh[0].counters()["in"] + sh[1].counters()["in"] == len(ev)
+    merged = po.OracleEngine(max_svcs=512, max_tasks=64, cms_log2_width=12)
+    merged.merge_from(sh[0]); merged.merge_from(sh[1])
+    assert np.array_equal(merged.cms(), one.cms())
+    for id_ in np.unique(ev["svc_id"][ev["type"] == 5])[:40]:
+        a, b = merged.export_hist(int(id_), 0), one.export_hist(int(id_), 0)
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+        assert np.array_equal(merged.export_hll(int(id_)), one.export_hll(int(id_)))
