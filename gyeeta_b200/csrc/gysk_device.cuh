@@ -158,8 +158,29 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long
 	asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
-// id -> dense slot. With `insert`, an unknown id claims an empty entry with a CAS on the key, takes the next slot
-// number and publishes it; racing readers of the same key wait for the publish. Returns -1 when absent / full.
+__device__ __forceinline__ uint4 ld_cg_v4(const void *p)
+{
+	uint4 v;
+	asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v)
+{
+	asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// id -> dense slot. Fast path = ONE 16-byte L2 load (key and published slot together), no fence: the slot number is
+// self-validating (0 = not yet published) and nothing else is published through it — per-slot state is zero-initialised at
+// engine creation, never by the inserter. With `insert`, an unknown id claims an empty entry with a CAS on the key, takes the
+// next slot number and publishes it; racing readers of the same key spin on a volatile load. Returns -1 when absent / full.
 // Replaces RCU_HASH_TABLE::lookup_single_elem_locked(glob_id, get_uint64_hash(glob_id)) (gy_mconnhdlr.cc:11183).
 __device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long key, bool insert)
 {
@@ -167,7 +188,9 @@ __device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long
 
 	for (uint32_t probe = 0; probe <= t.mask; ++probe, pos = (pos + 1) & t.mask) {
 		TblEntry *e = &t.ent[pos];
-		unsigned long long k = ld_volatile_u64(&e->key);
+		const uint4 raw = ld_cg_v4(e);
+		unsigned long long k = ((unsigned long long)raw.y << 32) | raw.x;
+		uint32_t s1 = raw.z;
 
 		if (k == 0) {
 			if (!insert) return -1;
@@ -176,16 +199,16 @@ __device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long
 				const uint32_t s = atomicAdd(t.count, 1u);
 				if (s >= t.max_slots) {
 					atomicSub(t.count, 1u);
-					st_release_u32(&e->slot1, SLOT_INVALID);
+					st_volatile_u32(&e->slot1, SLOT_INVALID);
 					return -1;
 				}
-				st_release_u32(&e->slot1, s + 1);
+				st_volatile_u32(&e->slot1, s + 1);
 				return (int)s;
 			}
+			s1 = 0;
 		}
 		if (k == key) {
-			uint32_t s1;
-			while ((s1 = ld_acquire_u32(&e->slot1)) == 0) { __nanosleep(20); }
+			while (s1 == 0) { __nanosleep(20); s1 = ld_volatile_u32(&e->slot1); }
 			return s1 == SLOT_INVALID ? -1 : (int)(s1 - 1);
 		}
 	}

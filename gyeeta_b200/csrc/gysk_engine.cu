@@ -4,18 +4,8 @@
 // reference's handlers never retain caller buffers: DB_WRITE_ARR frees them when the L2 loop iteration ends,
 // server/gy_mconnhdlr.h:424-431) and hand full batches to the device: H2D on a copy stream, kernels on the compute
 // stream, two device event buffers so the copy of batch k+1 overlaps the kernels of batch k.
-#include "gysk_kernels.cuh"
+#include "gysk_engine.h"
 #include "gysk_wire.h"
-
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <string>
-#include <vector>
 
 using namespace gysk;
 
@@ -23,53 +13,11 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int NBUF = 2;
-constexpr uint32_t QCHUNK = 1024;		// ids per query kernel launch
-
-struct LogicalState;
-
 } // namespace
 
-struct gysk_engine
-{
-	gysk_config		cfg {};
-	int			dev {0};
-	cudaStream_t		stream {nullptr}, copy_stream {nullptr};
-	DevState		st {};
-	SortTemp		tmp {};
-	std::vector<void *>	dallocs;
-	std::vector<void *>	hallocs;
+namespace gysk {
 
-	// staging
-	gysk_event		*h_stage[NBUF] {};
-	gysk_event		*d_events[NBUF] {};
-	cudaEvent_t		ev_copied[NBUF] {}, ev_done[NBUF] {};
-	uint32_t		stage_fill {0};
-	int			stage_cur {0};
-
-	// query scratch
-	unsigned long long	*d_qids {nullptr}, *h_qids {nullptr};
-	SvcRaw			*d_svcraw {nullptr}, *h_svcraw {nullptr};
-	TaskRaw			*d_taskraw {nullptr}, *h_taskraw {nullptr};
-	uint8_t			*d_hllout {nullptr}, *h_hllout {nullptr};
-	int32_t			*d_found {nullptr}, *h_found {nullptr};
-	gysk_flow_est		*d_flowout {nullptr}, *h_flowout {nullptr};
-	unsigned long long	*h_counters {nullptr};
-
-	// optional per-kernel timing
-	bool			profiling {false};
-	std::vector<cudaEvent_t> prof_events;		// triples: before ingest, after ingest, after t-digest chain
-	size_t			prof_used {0};
-
-	std::mutex		mtx;
-	std::string		err;
-	bool			sticky {false};
-	uint64_t		kernel_launches {0}, batches {0}, wire_ok {0}, wire_bad {0};
-};
-
-namespace {
-
-int fail(gysk_engine *e, int code, const char *what, cudaError_t ce = cudaSuccess)
+int fail(gysk_engine *e, int code, const char *what, cudaError_t ce)
 {
 	char buf[512];
 
@@ -83,45 +31,18 @@ int fail(gysk_engine *e, int code, const char *what, cudaError_t ce = cudaSucces
 	return code;
 }
 
-#define CU(e, call) do { cudaError_t ce__ = (call); if (ce__ != cudaSuccess) return fail((e), GYSK_ERR_CUDA, #call, ce__); } while (0)
-#define CHECK_ENGINE(e) do { if (!(e)) return GYSK_ERR_INVAL; if ((e)->sticky) return GYSK_ERR_CUDA; } while (0)
-
-template <typename T>
-int dalloc(gysk_engine *e, T **p, size_t n, bool zero = true)
-{
-	void *q = nullptr;
-	cudaError_t ce = cudaMalloc(&q, n * sizeof(T));
-
-	if (ce != cudaSuccess) return fail(e, GYSK_ERR_NOMEM, "cudaMalloc", ce);
-	e->dallocs.push_back(q);
-	if (zero) {
-		ce = cudaMemsetAsync(q, 0, n * sizeof(T), e->stream);
-		if (ce != cudaSuccess) return fail(e, GYSK_ERR_CUDA, "cudaMemsetAsync", ce);
-	}
-	*p = static_cast<T *>(q);
-	return 0;
-}
-
-template <typename T>
-int halloc(gysk_engine *e, T **p, size_t n)
-{
-	void *q = nullptr;
-	cudaError_t ce = cudaHostAlloc(&q, n * sizeof(T), cudaHostAllocDefault);
-
-	if (ce != cudaSuccess) return fail(e, GYSK_ERR_NOMEM, "cudaHostAlloc", ce);
-	e->hallocs.push_back(q);
-	*p = static_cast<T *>(q);
-	return 0;
-}
-
-uint32_t pow2_at_least(uint64_t v) { uint32_t p = 16; while (p < v) p <<= 1; return p; }
-
 int post_launch(gysk_engine *e, const char *what)
 {
 	cudaError_t ce = cudaGetLastError();
 	if (ce != cudaSuccess) return fail(e, GYSK_ERR_CUDA, what, ce);
 	return 0;
 }
+
+} // namespace gysk
+
+namespace {
+
+uint32_t pow2_at_least(uint64_t v) { uint32_t p = 16; while (p < v) p <<= 1; return p; }
 
 // one device batch: ingest kernel, then the sort + t-digest chain over the keys it emitted
 int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
@@ -148,8 +69,10 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
 	return post_launch(e, "ingest batch");
 }
 
+} // namespace
+
 // hand the filled part of the current staging buffer to the device
-int submit_stage(gysk_engine *e)
+int gysk::submit_stage(gysk_engine *e)
 {
 	const int k = e->stage_cur;
 	const uint32_t n = e->stage_fill;
@@ -169,6 +92,17 @@ int submit_stage(gysk_engine *e)
 	return 0;
 }
 
+int gysk::sync_locked(gysk_engine *e)
+{
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	CU(e, cudaStreamSynchronize(e->copy_stream));
+	CU(e, cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+namespace {
+
 int stage_events(gysk_engine *e, const gysk_event *ev, uint64_t n)
 {
 	while (n) {
@@ -186,15 +120,6 @@ inline gysk_event *stage_slot(gysk_engine *e, int *rc)
 {
 	if (e->stage_fill == e->cfg.max_batch) { *rc = submit_stage(e); if (*rc) return nullptr; }
 	return e->h_stage[e->stage_cur] + e->stage_fill++;
-}
-
-int sync_locked(gysk_engine *e)
-{
-	int rc = submit_stage(e);
-	if (rc) return rc;
-	CU(e, cudaStreamSynchronize(e->copy_stream));
-	CU(e, cudaStreamSynchronize(e->stream));
-	return 0;
 }
 
 // ---- pure host helpers: the reference's percentile rule and the estimators -------------------------------
@@ -288,6 +213,45 @@ int gather_svcs(gysk_engine *e, const uint64_t *ids, uint32_t n)		// n <= QCHUNK
 }
 
 } // namespace
+
+// SvcRaw (device gather) -> the fields SvcStateFields exposes (server/gy_mfields.h:1383-1412) + the sketch answers
+void gysk::summarize_raw(const gysk_engine *e, const SvcRaw &r, uint64_t id, gysk_svc_summary &o)
+{
+	const float pcts[3] = {95.0f, 99.0f, 25.0f};		// the percentiles listener_stats_update reads, gy_socket_stat.h:459
+
+	memset(&o, 0, sizeof(o));
+	o.glob_id = id;
+	o.found = r.found;
+	o.td_p50_us = o.td_p95_us = o.td_p99_us = NAN;
+	if (!r.found) return;
+
+	gysk_hist_serial ser[GYSK_HIST_MAX_BUCKETS];
+	uint64_t total; int64_t maxv, p[3];
+
+	hist_from_cells(r.last, 15, ser, &total, &maxv, false);
+	gysk_hist_percentiles(GYSK_CLS_RESP_TIME, 0, ser, total, pcts, 3, p);
+	o.nqrys_5s = (uint32_t)total;
+	for (int b = 0; b < 15; ++b) o.total_resp_5sec += (uint64_t)ser[b].sum;
+	o.p95_5s_resp_ms = p[0]; o.p99_5s_resp_ms = p[1]; o.p25_5s_resp_ms = p[2];
+
+	hist_from_cells(r.all, 15, ser, &total, &maxv, false);
+	gysk_hist_percentiles(GYSK_CLS_RESP_TIME, 0, ser, total, pcts, 2, p);
+	o.p95_all_resp_ms = p[0]; o.p99_all_resp_ms = p[1]; o.nqrys_all = total; o.max_resp_ms = maxv;
+
+	o.nconns_5s = (uint32_t)r.conn_last; o.kbytes_5s = (uint32_t)(r.conn_last >> 32);
+	o.nconns_all = r.conn_all_cnt; o.kbytes_all = r.conn_all_kb;
+	o.distinct_clients = hll_estimate_from_hist(r.hll_hist, e->cfg.hll_p);
+
+	double means[TD_CAP]; uint64_t w[TD_CAP];
+	const uint32_t nc = std::min<uint32_t>(r.td.n, TD_CAP);
+	for (uint32_t c = 0; c < nc; ++c) { means[c] = r.cent[c].mean; w[c] = r.cent[c].weight; }
+	o.td_count = r.td.total;
+	if (nc) {
+		o.td_p50_us = td_quantile(means, w, nc, r.td.minv, r.td.maxv, 0.50);
+		o.td_p95_us = td_quantile(means, w, nc, r.td.minv, r.td.maxv, 0.95);
+		o.td_p99_us = td_quantile(means, w, nc, r.td.minv, r.td.maxv, 0.99);
+	}
+}
 
 // ============================================================================================================
 // C ABI
@@ -402,6 +366,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(dalloc(e, &tmp.tile_hist, (size_t)256 * tmp.max_tiles));
 	A(dalloc(e, &tmp.scan_tmp, (size_t)256 * tmp.max_tiles / 2048 + 64));
 	A(dalloc(e, &tmp.seg_start, ns)); A(dalloc(e, &tmp.seg_end, ns)); A(dalloc(e, &tmp.touched, ns));
+	A(dalloc(e, &tmp.plan_bounds, ns * (TD_CAP + 1))); A(dalloc(e, &tmp.plan_n, ns)); A(dalloc(e, &tmp.newsum, ns * TD_CAP));
 
 	for (int k = 0; k < NBUF; ++k) {
 		A(halloc(e, &e->h_stage[k], (size_t)cfg.max_batch));
@@ -730,48 +695,12 @@ int gysk_query_svcs(gysk_engine *e, const uint64_t *ids, uint32_t n, gysk_svc_su
 	int rc = submit_stage(e);
 	if (rc) return rc;
 
-	const float pcts[3] = {95.0f, 99.0f, 25.0f};		// the percentiles listener_stats_update reads, gy_socket_stat.h:459
-
 	for (uint32_t off = 0; off < n; off += QCHUNK) {
 		const uint32_t m = std::min(QCHUNK, n - off);
 		if ((rc = gather_svcs(e, ids + off, m))) return rc;
 
 		for (uint32_t i = 0; i < m; ++i) {
-			const SvcRaw &r = e->h_svcraw[i];
-			gysk_svc_summary &o = out[off + i];
-
-			memset(&o, 0, sizeof(o));
-			o.glob_id = ids[off + i];
-			o.found = r.found;
-			o.td_p50_us = o.td_p95_us = o.td_p99_us = NAN;
-			if (!r.found) continue;
-
-			gysk_hist_serial ser[GYSK_HIST_MAX_BUCKETS];
-			uint64_t total; int64_t maxv, p[3];
-
-			hist_from_cells(r.last, 15, ser, &total, &maxv, false);
-			gysk_hist_percentiles(GYSK_CLS_RESP_TIME, 0, ser, total, pcts, 3, p);
-			o.nqrys_5s = (uint32_t)total;
-			for (int b = 0; b < 15; ++b) o.total_resp_5sec += (uint64_t)ser[b].sum;
-			o.p95_5s_resp_ms = p[0]; o.p99_5s_resp_ms = p[1]; o.p25_5s_resp_ms = p[2];
-
-			hist_from_cells(r.all, 15, ser, &total, &maxv, false);
-			gysk_hist_percentiles(GYSK_CLS_RESP_TIME, 0, ser, total, pcts, 2, p);
-			o.p95_all_resp_ms = p[0]; o.p99_all_resp_ms = p[1]; o.nqrys_all = total; o.max_resp_ms = maxv;
-
-			o.nconns_5s = (uint32_t)r.conn_last; o.kbytes_5s = (uint32_t)(r.conn_last >> 32);
-			o.nconns_all = r.conn_all_cnt; o.kbytes_all = r.conn_all_kb;
-			o.distinct_clients = hll_estimate_from_hist(r.hll_hist, e->cfg.hll_p);
-
-			double means[TD_CAP]; uint64_t w[TD_CAP];
-			const uint32_t nc = std::min<uint32_t>(r.td.n, TD_CAP);
-			for (uint32_t c = 0; c < nc; ++c) { means[c] = r.cent[c].mean; w[c] = r.cent[c].weight; }
-			o.td_count = r.td.total;
-			if (nc) {
-				o.td_p50_us = td_quantile(means, w, nc, r.td.minv, r.td.maxv, 0.50);
-				o.td_p95_us = td_quantile(means, w, nc, r.td.minv, r.td.maxv, 0.95);
-				o.td_p99_us = td_quantile(means, w, nc, r.td.minv, r.td.maxv, 0.99);
-			}
+			summarize_raw(e, e->h_svcraw[i], ids[off + i], out[off + i]);
 		}
 	}
 	return GYSK_OK;

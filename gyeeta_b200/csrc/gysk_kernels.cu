@@ -10,6 +10,7 @@
 //   flush_kernel         5-s window roll                                               common/gy_socket_stat.cc:3898
 //   gather_* / query_*   read side
 #include "gysk_kernels.cuh"
+#include "gysk_tdigest.cuh"
 
 #include <cfloat>
 #include <climits>
@@ -353,38 +354,103 @@ __global__ void td_segments_kernel(const unsigned long long *__restrict__ keys, 
 	if (slot != next) seg_end[slot] = (uint32_t)(i + 1);
 }
 
-// K_1 scale function of the merging t-digest (Dunning), k spanning [-delta/2, delta/2]: k(q) = delta/pi asin(2q - 1)
-__device__ __forceinline__ double td_k(double q, double delta)
-{
-	return __dmul_rn(__ddiv_rn(delta, M_PI), asin(__dsub_rn(__dmul_rn(2.0, q), 1.0)));
-}
-
-__device__ __forceinline__ double td_q(double k, double delta)
-{
-	if (k >= __ddiv_rn(delta, 2.0)) return 1.0;
-	return __ddiv_rn(__dadd_rn(sin(__ddiv_rn(__dmul_rn(k, M_PI), delta)), 1.0), 2.0);
-}
-
-__device__ __forceinline__ double td_wlimit(unsigned long long wsofar, unsigned long long W, double delta)
-{
-	const double q0 = wsofar ? __ddiv_rn((double)wsofar, (double)W) : 0.0;
-	return __dmul_rn((double)W, td_q(__dadd_rn(td_k(q0, delta), 1.0), delta));
-}
-
 static constexpr int TD_WARPS = 4;
+static constexpr int PLAN_STRIDE = TD_CAP + 1;
 
-struct TdScratch
+// (1) plan: one thread per touched service runs the greedy chain over n unit-weight samples. Cluster j of the run is
+// [bounds[j], bounds[j+1]) with bounds[j+1] = max(bounds[j] + 1, floor(n q(k(bounds[j]/n) + 1))): the boundaries depend on n
+// only, so they can be fixed before any sample is summed. Also clears the cluster-sum row of the service.
+__global__ void td_plan_kernel(double delta, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end,
+		const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p, uint32_t *__restrict__ plan_bounds,
+		uint32_t *__restrict__ plan_n, unsigned long long *__restrict__ newsum)
 {
-	Centroid		newc[TD_CAP];
-	Centroid		merged[2 * TD_CAP];
-	unsigned long long	prefix[2 * TD_CAP + 1];
-	uint32_t		bounds[2 * TD_CAP + 1];
-};
+	const uint32_t ntouched = (uint32_t)*ntouched_p;
 
-// one warp per touched service
-__global__ void __launch_bounds__(TD_WARPS * 32) td_update_kernel(DevState st, const unsigned long long *__restrict__ keys,
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntouched; t += gridDim.x * blockDim.x) {
+		const uint32_t slot = touched[t];
+		const uint32_t n = seg_end[slot] - seg_start[slot];
+		uint32_t *bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
+		unsigned long long *sums = newsum + (size_t)slot * TD_CAP;
+		uint32_t nnew = 0, s = 0;
+
+		while (s < n) {
+			const double wl = td_wlimit(s, n, delta);
+			unsigned long long ee = (unsigned long long)floor(wl);
+			if (ee > n) ee = n;
+			if (ee < (unsigned long long)s + 1) ee = s + 1;
+			if (nnew == TD_CAP - 1) ee = n;			// the last slot absorbs whatever is left
+			bounds[nnew] = s;
+			sums[nnew] = 0;
+			nnew++;
+			s = (uint32_t)ee;
+		}
+		bounds[nnew] = n;
+		plan_n[slot] = nnew;
+	}
+}
+
+// (2) sums: one thread per sorted sample. cluster id = position of the sample's rank in the service's bounds; runs of equal
+// (service, cluster) are contiguous in the sorted order, so a warp reduces them with match.any groups and issues one
+// 64-bit RED per group. Skew-immune: a hot service's samples are spread over as many warps as it has samples / 32.
+__global__ void __launch_bounds__(256) td_sums_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
+		const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ plan_bounds, const uint32_t *__restrict__ plan_n,
+		unsigned long long *__restrict__ newsum)
+{
+	const uint64_t n = *d_n;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	const int lane = threadIdx.x & 31;
+
+	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
+		const uint64_t i = base + lane;
+		const bool valid = i < n;
+		uint32_t slot = 0xFFFFFFFFu, v = 0, j = 0;
+
+		if (valid) {
+			const unsigned long long key = keys[i];
+			slot = (uint32_t)(key >> VALUE_BITS);
+			v = (uint32_t)(key & VALUE_MASK);
+		}
+		// the whole warp usually sits inside one cluster of one hot service: lane 0 searches, the others verify
+		const uint32_t slot0 = __shfl_sync(0xffffffffu, slot, 0);
+		uint32_t r = 0, lo0 = 0, hi0 = 0, j0 = 0;
+		const uint32_t *bounds = nullptr;
+		uint32_t nn = 0;
+		if (valid) {
+			r = (uint32_t)(i - seg_start[slot]);
+			bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
+			nn = plan_n[slot];
+		}
+		if (lane == 0 && valid) {
+			uint32_t lo = 0, hi = nn - 1;			// largest j with bounds[j] <= r
+			while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (bounds[mid] <= r) lo = mid; else hi = mid - 1; }
+			j0 = lo; lo0 = bounds[lo]; hi0 = bounds[lo + 1];
+		}
+		j0 = __shfl_sync(0xffffffffu, j0, 0); lo0 = __shfl_sync(0xffffffffu, lo0, 0); hi0 = __shfl_sync(0xffffffffu, hi0, 0);
+		if (valid) {
+			if (slot == slot0 && r >= lo0 && r < hi0) j = j0;
+			else {
+				uint32_t lo = 0, hi = nn - 1;
+				while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (bounds[mid] <= r) lo = mid; else hi = mid - 1; }
+				j = lo;
+			}
+		}
+		const uint32_t gid = valid ? (slot * (uint32_t)TD_CAP + j) : (0xFFFFFF00u + lane);
+		const uint32_t m = __match_any_sync(0xffffffffu, gid);
+		// group sum in two 32-bit halves (values < 2^30: 32 of them fit the split sums)
+		const uint32_t slo = __reduce_add_sync(m, v & 0xFFFFu);
+		const uint32_t shi = __reduce_add_sync(m, v >> 16);
+		if (valid && (m & ((1u << lane) - 1u)) == 0) {
+			red_add_u64(newsum + (size_t)slot * TD_CAP + j, (unsigned long long)slo + ((unsigned long long)shi << 16));
+		}
+	}
+}
+
+// (3) merge: one warp per touched service turns (sums, bounds) into the new clusters, merges them with the old centroids
+// (old first on ties) and runs the greedy pass again
+__global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, const unsigned long long *__restrict__ keys,
 		const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end, const uint32_t *__restrict__ touched,
-		const unsigned long long *__restrict__ ntouched_p)
+		const unsigned long long *__restrict__ ntouched_p, const uint32_t *__restrict__ plan_bounds, const uint32_t *__restrict__ plan_n,
+		const unsigned long long *__restrict__ newsum)
 {
 	__shared__ TdScratch scratch[TD_WARPS];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -397,103 +463,21 @@ __global__ void __launch_bounds__(TD_WARPS * 32) td_update_kernel(DevState st, c
 		const uint32_t slot = touched[t];
 		const uint32_t s0 = seg_start[slot];
 		const uint32_t n = seg_end[slot] - s0;
-		const unsigned long long *seg = keys + s0;
+		const uint32_t nnew = plan_n[slot];
+		const uint32_t *bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
+		const unsigned long long *sums = newsum + (size_t)slot * TD_CAP;
 
-		// ---- phase 1: greedy clustering of n sorted unit-weight samples; cluster [s, e), e = max(s+1, floor(wlimit))
-		uint32_t nnew = 0, s = 0;
-		while (s < n) {
-			uint32_t e = 0;
-			if (lane == 0) {
-				const double wl = td_wlimit(s, n, delta);
-				unsigned long long ee = (unsigned long long)floor(wl);
-				if (ee > n) ee = n;
-				if (ee < (unsigned long long)s + 1) ee = s + 1;
-				if (nnew == TD_CAP - 1) ee = n;
-				e = (uint32_t)ee;
-			}
-			e = __shfl_sync(0xffffffffu, e, 0);
-			unsigned long long sum = 0;
-			for (uint32_t i = s + lane; i < e; i += 32) sum += seg[i] & VALUE_MASK;
-#pragma unroll
-			for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
-			if (lane == 0) {
-				S.newc[nnew].mean = __ddiv_rn((double)sum, (double)(e - s));
-				S.newc[nnew].weight = e - s;
-			}
-			nnew++;
-			s = e;
-		}
-		const double bmin = (double)(seg[0] & VALUE_MASK), bmax = (double)(seg[n - 1] & VALUE_MASK);
-		__syncwarp();
-
-		// ---- phase 2: stable merge of old centroids (first on ties) and new clusters by mean
-		TdHead head = st.td_head[slot];
-		const uint32_t nold = head.n;
-		const Centroid *old = st.td_cent + (size_t)slot * TD_CAP;
-		const uint32_t nm = nold + nnew;
-
-		for (uint32_t j = lane; j < nold; j += 32) {
-			const Centroid c = old[j];
-			uint32_t lo = 0, hi = nnew;			// # new with mean < c.mean
-			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.newc[mid].mean < c.mean) lo = mid + 1; else hi = mid; }
-			S.merged[j + lo] = c;
-		}
 		for (uint32_t j = lane; j < nnew; j += 32) {
-			const Centroid c = S.newc[j];
-			uint32_t lo = 0, hi = nold;			// # old with mean <= c.mean
-			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (old[mid].mean <= c.mean) lo = mid + 1; else hi = mid; }
-			S.merged[j + lo] = c;
+			const uint32_t w = bounds[j + 1] - bounds[j];
+			S.newc[j].mean = __ddiv_rn((double)sums[j], (double)w);		// cluster sums are exact integers
+			S.newc[j].weight = w;
 		}
+		const double bmin = (double)(keys[s0] & VALUE_MASK), bmax = (double)(keys[s0 + n - 1] & VALUE_MASK);
 		__syncwarp();
 
-		// exclusive prefix of weights: lane owns 8 consecutive items
-		{
-			unsigned long long w[8], tot = 0;
-#pragma unroll
-			for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; w[j] = i < nm ? S.merged[i].weight : 0; tot += w[j]; }
-			unsigned long long incl = tot;
-#pragma unroll
-			for (int off = 1; off < 32; off <<= 1) {
-				const unsigned long long tt = __shfl_up_sync(0xffffffffu, incl, off);
-				if (lane >= off) incl += tt;
-			}
-			unsigned long long ex = incl - tot;
-#pragma unroll
-			for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; if (i <= nm) S.prefix[i] = ex; ex += w[j]; }
-			if (lane == 31 && nm == 2 * TD_CAP) S.prefix[nm] = incl;
-		}
-		__syncwarp();
-
-		// greedy chain over the merged list (sequential, <= ~delta steps)
-		uint32_t nout = 0;
-		if (lane == 0) {
-			const unsigned long long W = S.prefix[nm];
-			uint32_t cs = 0;
-			while (cs < nm) {
-				const double wl = td_wlimit(S.prefix[cs], W, delta);
-				uint32_t lo = cs + 1, hi = nm;			// largest e in [cs+1, nm] with prefix[e] <= wl
-				while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if ((double)S.prefix[mid] <= wl) lo = mid; else hi = mid - 1; }
-				uint32_t e = lo;
-				if (nout == TD_CAP - 1) e = nm;
-				S.bounds[nout++] = cs;
-				cs = e;
-			}
-			S.bounds[nout] = nm;
-		}
-		nout = __shfl_sync(0xffffffffu, nout, 0);
-		__syncwarp();
-
-		Centroid *outc = st.td_cent + (size_t)slot * TD_CAP;
-		for (uint32_t c = lane; c < nout; c += 32) {
-			double csum = 0.0;
-			unsigned long long cw = 0;
-			for (uint32_t i = S.bounds[c]; i < S.bounds[c + 1]; ++i) {
-				csum = __dadd_rn(csum, __dmul_rn(S.merged[i].mean, (double)S.merged[i].weight));
-				cw += S.merged[i].weight;
-			}
-			Centroid o; o.mean = __ddiv_rn(csum, (double)cw); o.weight = cw;
-			outc[c] = o;
-		}
+		TdHead head = st.td_head[slot];
+		Centroid *cent = st.td_cent + (size_t)slot * TD_CAP;
+		const uint32_t nout = warp_merge_compress(S, cent, head.n, S.newc, nnew, cent, delta);
 		if (lane == 0) {
 			head.n = nout;
 			head.total += n;
@@ -686,8 +670,10 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, u
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-	td_update_kernel<<<nsm * 4, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
-	return launches + 2;
+	td_plan_kernel<<<nsm * 2, 128, 0, s>>>(st.td_delta, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
+	td_sums_kernel<<<nsm * 8, 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
+	td_merge_kernel<<<nsm * 4, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
+	return launches + 4;
 }
 
 int launch_flush(const DevState &st, uint32_t nslots, cudaStream_t s)

@@ -34,6 +34,8 @@ struct SortTemp
 	uint32_t		*scan_tmp;		// block sums for the scan
 	uint32_t		*seg_start, *seg_end;	// [max_svcs]
 	uint32_t		*touched;		// [max_svcs]
+	uint32_t		*plan_bounds, *plan_n;	// [max_svcs][TD_CAP + 1], [max_svcs]: cluster boundaries of the batch's runs
+	unsigned long long	*newsum;		// [max_svcs][TD_CAP]: exact cluster sums
 	uint32_t		max_tiles;
 };
 

@@ -1,0 +1,111 @@
+// gysk_tdigest.cuh — warp-level building blocks of the batched merging t-digest (shared by the ingest-side update
+// kernel and the multi-GPU merge kernels). Definitions: DESIGN.md §t-digest; CPU statement: oracle/gysk_oracle.c.
+#pragma once
+
+#include "gysk_device.cuh"
+
+namespace gysk {
+
+// K_1 scale function of the merging t-digest (Dunning), k spanning [-delta/2, delta/2]: k(q) = delta/pi asin(2q - 1)
+__device__ __forceinline__ double td_k(double q, double delta)
+{
+	return __dmul_rn(__ddiv_rn(delta, M_PI), asin(__dsub_rn(__dmul_rn(2.0, q), 1.0)));
+}
+
+__device__ __forceinline__ double td_q(double k, double delta)
+{
+	if (k >= __ddiv_rn(delta, 2.0)) return 1.0;
+	return __ddiv_rn(__dadd_rn(sin(__ddiv_rn(__dmul_rn(k, M_PI), delta)), 1.0), 2.0);
+}
+
+__device__ __forceinline__ double td_wlimit(unsigned long long wsofar, unsigned long long W, double delta)
+{
+	const double q0 = wsofar ? __ddiv_rn((double)wsofar, (double)W) : 0.0;
+	return __dmul_rn((double)W, td_q(__dadd_rn(td_k(q0, delta), 1.0), delta));
+}
+
+struct TdScratch
+{
+	Centroid		newc[TD_CAP];
+	Centroid		merged[2 * TD_CAP];
+	unsigned long long	prefix[2 * TD_CAP + 1];
+	uint32_t		bounds[2 * TD_CAP + 1];
+};
+
+
+// Stable merge by mean of two mean-sorted centroid lists (`a` first on ties), then the greedy K_1 pass; one warp.
+// Both inputs are fully consumed into S.merged before `out` is written, so `out` may alias `a` or `b`.
+// Returns the number of centroids written to out (<= TD_CAP).
+__device__ __forceinline__ uint32_t warp_merge_compress(TdScratch &S, const Centroid *a, uint32_t na, const Centroid *b, uint32_t nb,
+		Centroid *out, double delta)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t nm = na + nb;
+
+	for (uint32_t j = lane; j < na; j += 32) {
+		const Centroid c = a[j];
+		uint32_t lo = 0, hi = nb;			// # of b with mean < c.mean
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (b[mid].mean < c.mean) lo = mid + 1; else hi = mid; }
+		S.merged[j + lo] = c;
+	}
+	for (uint32_t j = lane; j < nb; j += 32) {
+		const Centroid c = b[j];
+		uint32_t lo = 0, hi = na;			// # of a with mean <= c.mean
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid].mean <= c.mean) lo = mid + 1; else hi = mid; }
+		S.merged[j + lo] = c;
+	}
+	__syncwarp();
+
+	// exclusive prefix of weights: lane owns 8 consecutive items
+	{
+		unsigned long long w[8], tot = 0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; w[j] = i < nm ? S.merged[i].weight : 0; tot += w[j]; }
+		unsigned long long incl = tot;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) {
+			const unsigned long long tt = __shfl_up_sync(0xffffffffu, incl, off);
+			if (lane >= off) incl += tt;
+		}
+		unsigned long long ex = incl - tot;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; if (i <= nm) S.prefix[i] = ex; ex += w[j]; }
+		if (lane == 31 && nm == 2 * TD_CAP) S.prefix[nm] = incl;
+	}
+	__syncwarp();
+
+	// greedy chain over the merged list (sequential, about delta steps): a cluster that starts after weight P takes items
+	// while the running total stays <= W q(k(P/W) + 1), and at least one item
+	uint32_t nout = 0;
+	if (lane == 0 && nm) {
+		const unsigned long long W = S.prefix[nm];
+		uint32_t cs = 0;
+		while (cs < nm) {
+			const double wl = td_wlimit(S.prefix[cs], W, delta);
+			uint32_t lo = cs + 1, hi = nm;			// largest e in [cs+1, nm] with prefix[e] <= wl
+			while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if ((double)S.prefix[mid] <= wl) lo = mid; else hi = mid - 1; }
+			uint32_t e = lo;
+			if (nout == TD_CAP - 1) e = nm;			// the last slot absorbs whatever is left
+			S.bounds[nout++] = cs;
+			cs = e;
+		}
+		S.bounds[nout] = nm;
+	}
+	nout = __shfl_sync(0xffffffffu, nout, 0);
+	__syncwarp();
+
+	for (uint32_t c = lane; c < nout; c += 32) {
+		double csum = 0.0;
+		unsigned long long cw = 0;
+		for (uint32_t i = S.bounds[c]; i < S.bounds[c + 1]; ++i) {
+			csum = __dadd_rn(csum, __dmul_rn(S.merged[i].mean, (double)S.merged[i].weight));
+			cw += S.merged[i].weight;
+		}
+		Centroid o; o.mean = __ddiv_rn(csum, (double)cw); o.weight = cw;
+		out[c] = o;
+	}
+	__syncwarp();
+	return nout;
+}
+
+} // namespace gysk

@@ -1,0 +1,47 @@
+"""torch.distributed plumbing of the multi-GPU merge step: one all-reduce per reduction kind over the
+engine's merge arena (u64 SUM, i64 MAX, u8 MAX) and one all-gather of the fixed t-digest slab, NCCL over NVLink/NVSwitch.
+The sketches themselves never leave the device; torch only wraps the device pointers."""
+import numpy as np
+
+RED_SUM_U64, RED_MAX_U8, RED_MAX_I64 = 0, 1, 2
+
+
+def shard_of_host(host_idx, world):
+    """the partition rule of the ingest path: a host (partha) belongs to rank host_idx % world"""
+    return np.asarray(host_idx) % world
+
+
+class _DevBuf:
+    """device pointer -> object torch.as_tensor() understands"""
+
+    def __init__(self, ptr, nbytes, typestr, itemsize):
+        self.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def wrap(torch, ptr, nbytes, redop, device):
+    if redop == RED_MAX_U8:
+        return torch.as_tensor(_DevBuf(ptr, nbytes, "|u1", 1), device=device)
+    return torch.as_tensor(_DevBuf(ptr, nbytes, "<i8", 8), device=device)     # u64 sums == i64 sums bit for bit
+
+
+def merge_global(eng, torch, dist, device=None):
+    """fold -> all-reduce / all-gather -> finish. Returns the device time of the collectives in ms (CUDA events)."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    eng.merge_prepare()                                   # synchronises the engine stream
+    if world == 1:
+        eng.merge_finish(None, 1)
+        return 0.0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _name, ptr, nbytes, redop in eng.merge_buffers():
+        t = wrap(torch, ptr, nbytes, redop, device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if redop == RED_SUM_U64 else dist.ReduceOp.MAX)
+    sptr, snbytes = eng.merge_tdigest_slab()
+    slab = torch.as_tensor(_DevBuf(sptr, snbytes, "|u1", 1), device=device)
+    gathered = torch.empty(world * snbytes, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(gathered, slab)
+    t1.record()
+    torch.cuda.current_stream().synchronize()
+    eng.merge_finish(gathered.data_ptr(), world)
+    return t0.elapsed_time(t1)

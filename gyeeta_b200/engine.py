@@ -107,6 +107,7 @@ def load_library(path=None):
         "gysk_merge_tdigest_slab": (i32, [vp, vp, vp]),
         "gysk_merge_finish": (i32, [vp, vp, u32]),
         "gysk_query_logical": (i32, [vp, vp, u32, vp]),
+        "gysk_query_flows_global": (i32, [vp, vp, u32, i32, vp]),
         "gysk_stream": (vp, [vp]),
         "gysk_profile_enable": (i32, [vp, i32]),
         "gysk_profile_read": (i32, [vp, vp, vp, vp]),
@@ -255,6 +256,42 @@ class Engine:
         qs = np.ascontiguousarray(qs, dtype=np.float64)
         out = np.zeros(len(qs), dtype=np.float64)
         self._chk(self.L.gysk_query_quantiles(self.h, int(id_), _p(qs), len(qs), _p(out)))
+        return out
+
+    # ---- multi-GPU merge ----
+    def set_logical_map(self, glob_ids, logical_ids):
+        g = np.ascontiguousarray(glob_ids, dtype=np.uint64)
+        l = np.ascontiguousarray(logical_ids, dtype=np.uint64)
+        assert len(g) == len(l)
+        self._chk(self.L.gysk_set_logical_map(self.h, _p(g), _p(l), len(g)))
+
+    def merge_prepare(self):
+        self._chk(self.L.gysk_merge_prepare(self.h))
+
+    def merge_buffers(self):
+        descs = (BufferDesc * 8)()
+        n = C.c_uint32()
+        self._chk(self.L.gysk_merge_buffers(self.h, descs, 8, C.byref(n)))
+        return [(d.name.decode(), d.dptr, d.nbytes, d.redop) for d in descs[: n.value]]
+
+    def merge_tdigest_slab(self):
+        p, nb = C.c_void_p(), C.c_uint64()
+        self._chk(self.L.gysk_merge_tdigest_slab(self.h, C.byref(p), C.byref(nb)))
+        return p.value, nb.value
+
+    def merge_finish(self, gathered_ptr=None, world=1):
+        self._chk(self.L.gysk_merge_finish(self.h, C.c_void_p(gathered_ptr), world))
+
+    def query_logical(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = (SvcSummary * len(ids))()
+        self._chk(self.L.gysk_query_logical(self.h, _p(ids), len(ids), out))
+        return [o.asdict() for o in out]
+
+    def query_flows_global(self, keys, last_window=False):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.zeros(len(keys), dtype=FLOW_EST_DTYPE)
+        self._chk(self.L.gysk_query_flows_global(self.h, _p(keys), len(keys), int(last_window), _p(out)))
         return out
 
     def export_cms(self, last_window=False):

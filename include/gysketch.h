@@ -184,7 +184,7 @@ typedef struct gysk_stats
 } gysk_stats;
 
 /* mergeable device buffers (for the multi-GPU merge step) */
-enum { GYSK_RED_SUM_U64 = 0, GYSK_RED_MAX_U8 = 1 };
+enum { GYSK_RED_SUM_U64 = 0, GYSK_RED_MAX_U8 = 1, GYSK_RED_MAX_I64 = 2 };
 typedef struct gysk_buffer_desc
 {
 	const char	*name;
@@ -247,6 +247,7 @@ int		gysk_merge_buffers(gysk_engine *e, gysk_buffer_desc *out, uint32_t cap, uin
 int		gysk_merge_tdigest_slab(gysk_engine *e, void **dptr, uint64_t *nbytes);	/* fixed slab to all-gather */
 int		gysk_merge_finish(gysk_engine *e, const void *d_gathered_slabs, uint32_t world);
 int		gysk_query_logical(gysk_engine *e, const uint64_t *logical_ids, uint32_t n, gysk_svc_summary *out);
+int		gysk_query_flows_global(gysk_engine *e, const uint64_t *flow_keys, uint32_t n, int last_window, gysk_flow_est *out);
 
 /* per-kernel device timing (CUDA events on the launching stream around the ingest kernel and around the sort +
  * t-digest chain of every device batch). read() synchronises, returns the sums since the last read and resets. */
