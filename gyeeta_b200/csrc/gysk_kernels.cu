@@ -50,19 +50,72 @@ __global__ void register_kernel(DevState st, const unsigned long long *ids, uint
 // ---------------------------------------------------------------------------------------------------
 // ingest
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hist_add(HistCell *h, int bucket, long long data)
+// Service popularity is Zipf-skewed: a few {count, sum} cells would take millions of same-address L2 atomics per batch and
+// serialise the kernel. Two levels take that pressure off L2:
+//   warp : lanes updating the same cell are grouped with match.any, reduced with redux and represented by one leader;
+//   CTA  : a direct-mapped shared-memory table privatises hot cells for the lifetime of the CTA (a cell is admitted when it
+//          shows up at least twice inside one warp), and is flushed with one RED pair per entry when the CTA retires.
+// Everything stays exact integer arithmetic, so the result is independent of grouping and order.
+struct HotEntry { uint32_t tag; uint32_t count; unsigned long long sum; };
+static constexpr int HOT_BITS = 11;
+static constexpr int HOT_N = 1 << HOT_BITS;			// 32 KB of shared memory
+static constexpr uint32_t CELL_TASK = 1u << 30;			// cell ids: svc hist = slot*16 + bucket, conn = slot*16 + 15,
+								//           task = CELL_TASK | (tslot*48 + hist*16 + bucket)
+
+__device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cell, uint32_t cnt, unsigned long long sum)
 {
-	red_add_u64(&h[bucket].count, 1ull);
-	red_add_u64((unsigned long long *)&h[bucket].sum, (unsigned long long)data);
-	// max_val_seen_: read first, the atomic is needed only while the maximum still grows
-	if (data > *((volatile long long *)&h[HIST_MAX_CELL].sum)) atomicMax(&h[HIST_MAX_CELL].sum, data);
+	if (cell & CELL_TASK) {
+		HistCell *c = st.task_hist + (cell & ~CELL_TASK);
+		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
+	}
+	else if ((cell & 15u) == (uint32_t)HIST_MAX_CELL) {
+		red_add_u64(st.conn_cur + (cell >> 4), (unsigned long long)cnt + (sum << 32));	// packed {count, kbytes}
+	}
+	else {
+		HistCell *c = st.hist_cur + cell;
+		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
+	}
+}
+
+// all 32 lanes call this; lanes with active == false only take part in the collectives
+__device__ __forceinline__ void cell_add(const DevState &st, HotEntry *hot, bool active, uint32_t cell, int data, bool track_max)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t id = active ? cell : (0x80000000u | (uint32_t)lane);
+	const uint32_t m = __match_any_sync(0xffffffffu, id);
+	const uint32_t cnt = __popc(m);
+	// 64-bit sum of the group's int values from three 32-bit reductions: sum(u32 pattern) - 2^32 * #negatives
+	const uint32_t slo = __reduce_add_sync(m, (uint32_t)data & 0xFFFFu);
+	const uint32_t shi = __reduce_add_sync(m, (uint32_t)data >> 16);
+	const uint32_t nneg = __reduce_add_sync(m, data < 0 ? 1u : 0u);
+	const int gmax = __reduce_max_sync(m, data);
+
+	if (!active || (m & ((1u << lane) - 1u))) return;		// group leader = lowest lane
+
+	const unsigned long long sum = (unsigned long long)slo + ((unsigned long long)shi << 16) - ((unsigned long long)nneg << 32);
+	HotEntry *e = hot + ((cell * 2654435761u) >> (32 - HOT_BITS));
+	uint32_t tag = *((volatile uint32_t *)&e->tag);
+	bool hit = tag == cell + 1;
+
+	if (!hit && tag == 0 && cnt >= 2) {
+		tag = atomicCAS(&e->tag, 0u, cell + 1);
+		hit = tag == 0 || tag == cell + 1;
+	}
+	if (hit) { atomicAdd(&e->count, cnt); atomicAdd(&e->sum, sum); }
+	else cell_add_global(st, cell, cnt, sum);
+
+	if (track_max) {
+		// max_val_seen_: a (possibly stale) cached read first, the atomic only while the maximum still grows
+		long long *mp = (cell & CELL_TASK) ? &st.task_hist[((cell & ~CELL_TASK) | 15u)].sum : &st.hist_cur[cell | 15u].sum;
+		if ((long long)gmax > __ldca(mp)) atomicMax(mp, (long long)gmax);
+	}
 }
 
 __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t rank)
 {
 	uint32_t *wp = reinterpret_cast<uint32_t *>(regs) + (idx >> 2);
 	const uint32_t sh = (idx & 3u) * 8u;
-	uint32_t w = *((volatile uint32_t *)wp);
+	uint32_t w = __ldca(wp);				// stale is harmless: the CAS re-validates
 
 	while (((w >> sh) & 0xFFu) < rank) {
 		const uint32_t nw = (w & ~(0xFFu << sh)) | (rank << sh);
@@ -74,70 +127,100 @@ __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t
 
 __global__ void __launch_bounds__(256) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n, unsigned long long *__restrict__ keys)
 {
+	__shared__ HotEntry hot[HOT_N];
 	unsigned long long c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	const int lane = threadIdx.x & 31;
 
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const uint4 a = __ldg(reinterpret_cast<const uint4 *>(ev + i));
-		const uint4 b = __ldg(reinterpret_cast<const uint4 *>(ev + i) + 1);
-		const unsigned long long svc_id = ((unsigned long long)a.y << 32) | a.x;
-		const unsigned long long flow_key = ((unsigned long long)a.w << 32) | a.z;
-		const uint32_t value = b.x, host_idx = b.y;
-		const uint32_t type = b.w & 0xFFFFu;
+	for (int i = threadIdx.x; i < HOT_N; i += blockDim.x) { hot[i].tag = 0; hot[i].count = 0; hot[i].sum = 0; }
+	__syncthreads();
+
+	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
+		const uint64_t i = base + lane;
+		const bool valid = i < n;
 		unsigned long long key = KEY_SENTINEL;
+		// up to three cell updates per event: RESP -> 1 histogram cell; TCP -> the service's conn cell; TASK -> 3 histogram cells
+		uint32_t cell0 = 0, cell1 = 0, cell2 = 0;
+		int d0 = 0, d1 = 0, d2 = 0;
+		bool a0 = false, a12 = false, max0 = false;
 
-		if (st.world > 1 && (host_idx % st.world) != st.rank) {
-			c_foreign++;
-		}
-		else {
-			c_in++;
-			if (svc_id == 0) {
-				c_drop++;
+		if (valid) {
+			const uint4 a = __ldg(reinterpret_cast<const uint4 *>(ev + i));
+			const uint4 b = __ldg(reinterpret_cast<const uint4 *>(ev + i) + 1);
+			const unsigned long long svc_id = ((unsigned long long)a.y << 32) | a.x;
+			const unsigned long long flow_key = ((unsigned long long)a.w << 32) | a.z;
+			const uint32_t value = b.x, host_idx = b.y;
+			const uint32_t type = b.w & 0xFFFFu;
+
+			if (st.world > 1 && (host_idx % st.world) != st.rank) {
+				c_foreign++;
 			}
-			else if (type == GYSK_EV_RESP) {
-				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule
-				// of handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-				const uint32_t ms = value / 1000u;
-				int slot = -1;
-				if (ms <= 1000000u) slot = table_lookup(st.svc_tbl, svc_id, st.auto_register);
-				if (slot < 0) c_drop++;
-				else {
-					hist_add(st.hist_cur + (size_t)slot * HIST_CELLS, bucket_resp_time((long long)ms), (long long)ms);
-					key = ((unsigned long long)(uint32_t)slot << VALUE_BITS) | value;
-					c_resp++;
+			else {
+				c_in++;
+				if (svc_id == 0) {
+					c_drop++;
 				}
-			}
-			else if (type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER) {
-				const int slot = table_lookup(st.svc_tbl, svc_id, st.auto_register);
-				if (slot < 0) c_drop++;
-				else {
-					const unsigned long long inc = cms_increment(value);
-					for (uint32_t r = 0; r < st.cms_depth; ++r) {
-						red_add_u64(st.cms_cur + ((size_t)r << st.cms_log2w) + cms_index(flow_key, r, st.cms_wmask), inc);
+				else if (type == GYSK_EV_RESP) {
+					// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule
+					// of handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
+					const uint32_t ms = value / 1000u;
+					int slot = -1;
+					if (ms <= 1000000u) slot = table_lookup(st.svc_tbl, svc_id, st.auto_register);
+					if (slot < 0) c_drop++;
+					else {
+						// GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data, gy_statistics.h:596-623
+						cell0 = (uint32_t)slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
+						d0 = (int)ms; a0 = true; max0 = true;
+						key = ((unsigned long long)(uint32_t)slot << VALUE_BITS) | value;
+						c_resp++;
 					}
-					uint32_t idx, rank;
-					hll_idx_rank(flow_key, st.hll_p, idx, rank);
-					hll_update(st.hll + ((size_t)slot << st.hll_p), idx, rank);
-					red_add_u64(st.conn_cur + slot, inc);
-					c_tcp++;
 				}
-			}
-			else if (type == GYSK_EV_TASK) {
-				const int slot = table_lookup(st.task_tbl, svc_id, st.auto_register);
-				if (slot < 0) c_drop++;
-				else {
-					// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
-					HistCell *h = st.task_hist + (size_t)slot * 3 * HIST_CELLS;
-					const int cpu_pct = (int)value, cpu_delay = (int)(uint32_t)flow_key, blkio_delay = (int)(uint32_t)(flow_key >> 32);
-					hist_add(h, bucket_hash_1_3000(cpu_pct), (long long)cpu_pct);
-					hist_add(h + HIST_CELLS, bucket_duration(cpu_delay), (long long)cpu_delay);
-					hist_add(h + 2 * HIST_CELLS, bucket_duration(blkio_delay), (long long)blkio_delay);
-					c_task++;
+				else if (type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER) {
+					const int slot = table_lookup(st.svc_tbl, svc_id, st.auto_register);
+					if (slot < 0) c_drop++;
+					else {
+						const unsigned long long inc = cms_increment(value);
+						for (uint32_t r = 0; r < st.cms_depth; ++r) {
+							red_add_u64(st.cms_cur + ((size_t)r << st.cms_log2w) + cms_index(flow_key, r, st.cms_wmask), inc);
+						}
+						uint32_t idx, rank;
+						hll_idx_rank(flow_key, st.hll_p, idx, rank);
+						hll_update(st.hll + ((size_t)slot << st.hll_p), idx, rank);
+						cell0 = (uint32_t)slot * HIST_CELLS + HIST_MAX_CELL;		// exact per-service {count, kbytes} cell
+						d0 = (int)(value >> 10); a0 = true;
+						c_tcp++;
+					}
 				}
+				else if (type == GYSK_EV_TASK) {
+					const int slot = table_lookup(st.task_tbl, svc_id, st.auto_register);
+					if (slot < 0) c_drop++;
+					else {
+						// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
+						const uint32_t tb = CELL_TASK | ((uint32_t)slot * 3u * HIST_CELLS);
+						d0 = (int)value; d1 = (int)(uint32_t)flow_key; d2 = (int)(uint32_t)(flow_key >> 32);
+						cell0 = tb + (uint32_t)bucket_hash_1_3000(d0);
+						cell1 = tb + HIST_CELLS + (uint32_t)bucket_duration(d1);
+						cell2 = tb + 2 * HIST_CELLS + (uint32_t)bucket_duration(d2);
+						a0 = true; a12 = true; max0 = true;
+						c_task++;
+					}
+				}
+				else c_drop++;
 			}
-			else c_drop++;
+			keys[i] = key;
 		}
-		keys[i] = key;
+
+		cell_add(st, hot, a0, cell0, d0, max0);
+		if (__any_sync(0xffffffffu, a12)) {
+			cell_add(st, hot, a12, cell1, d1, true);
+			cell_add(st, hot, a12, cell2, d2, true);
+		}
+	}
+
+	// retire: one RED pair per privatised cell
+	__syncthreads();
+	for (int i = threadIdx.x; i < HOT_N; i += blockDim.x) {
+		if (hot[i].tag && hot[i].count) cell_add_global(st, hot[i].tag - 1, hot[i].count, hot[i].sum);
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
@@ -150,7 +233,7 @@ __global__ void __launch_bounds__(256) ingest_kernel(DevState st, const gysk_eve
 		c_task += __shfl_down_sync(0xffffffffu, c_task, off);
 		c_foreign += __shfl_down_sync(0xffffffffu, c_foreign, off);
 	}
-	if ((threadIdx.x & 31) == 0) {
+	if (lane == 0) {
 		if (c_in) atomicAdd(st.counters + CTR_IN, c_in);
 		if (c_drop) atomicAdd(st.counters + CTR_DROPPED, c_drop);
 		if (c_resp) atomicAdd(st.counters + CTR_RESP, c_resp);

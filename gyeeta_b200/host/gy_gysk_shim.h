@@ -1,0 +1,76 @@
+// gy_gysk_shim.h — the host-side mirror of the reference's ingest interface for this path (C++17, header only).
+//
+// The three handlers below keep the names, argument meaning and bool return of the reference's member functions
+//     MCONN_HANDLER::partha_tcp_conn_info     server/gy_mconnhdlr.h:2091   (definition gy_mconnhdlr.cc:9052)
+//     MCONN_HANDLER::partha_aggr_task_state   server/gy_mconnhdlr.h:2098   (definition gy_mconnhdlr.cc:9959)
+//     MCONN_HANDLER::partha_listener_state    server/gy_mconnhdlr.h:2129   (definition gy_mconnhdlr.cc:10993)
+// and forward the record batch to the B200 engine through the C ABI of include/gysketch.h. The template parameters
+// stand for the reference's own types (std::shared_ptr<PARTHA_INFO>, comm::TCP_CONN_NOTIFY, POOL_ALLOC_ARRAY, PGConnPool) so
+// that this header compiles both inside gy_mconnhdlr.cc (with the real types) and stand-alone in this repository's tests (with
+// the POD mirrors of gyeeta_b200/csrc/gysk_wire.h). See INTEGRATION.md for the call-site patch.
+#pragma once
+
+#include <cstdint>
+#include <memory>
+
+#include "../../include/gysketch.h"
+
+namespace gysk_shim {
+
+// What the shim needs from PARTHA_INFO: the 16-byte machine id (GY_MACHINE_ID machine_id_, server/gy_mconnhdlr.h:1110) and a
+// dense per-madhava host index (the engine shards by it). Specialise / overload for the real PARTHA_INFO.
+template <typename ParthaInfo>
+struct partha_traits
+{
+	static const uint8_t *machine_id(const ParthaInfo & p) noexcept { return reinterpret_cast<const uint8_t *>(&p.machine_id_); }
+	static uint32_t host_index(const ParthaInfo & p) noexcept { return p.gysk_host_idx_; }
+};
+
+class GYSK_HANDLER
+{
+public :
+	explicit GYSK_HANDLER(gysk_engine *engine) noexcept : engine_(engine) {}
+
+	// bool partha_tcp_conn_info(const std::shared_ptr<PARTHA_INFO> &, comm::TCP_CONN_NOTIFY *, int nconns, uint8_t *pendptr, POOL_ALLOC_ARRAY *)
+	template <typename ParthaInfo, typename TcpConnNotify, typename PoolArr>
+	bool partha_tcp_conn_info(const std::shared_ptr<ParthaInfo> & partha_shr, TcpConnNotify *pone, int nconns, uint8_t *pendptr, PoolArr * /*pthrpoolarr*/) noexcept
+	{
+		return forward(partha_shr, GYSK_NOTIFY_TCP_CONN, pone, nconns, pendptr);
+	}
+
+	// bool partha_aggr_task_state(const std::shared_ptr<PARTHA_INFO> &, const comm::AGGR_TASK_STATE_NOTIFY *, int ntasks, uint8_t *pendptr, PGConnPool &)
+	template <typename ParthaInfo, typename AggrTaskStateNotify, typename DbPool>
+	bool partha_aggr_task_state(const std::shared_ptr<ParthaInfo> & partha_shr, const AggrTaskStateNotify *ptask, int ntasks, uint8_t *pendptr, DbPool & /*dbpool*/) noexcept
+	{
+		return forward(partha_shr, GYSK_NOTIFY_AGGR_TASK_STATE, const_cast<AggrTaskStateNotify *>(ptask), ntasks, pendptr);
+	}
+
+	// bool partha_listener_state(const std::shared_ptr<PARTHA_INFO> &, const comm::LISTENER_STATE_NOTIFY *, int nitems, uint8_t *pendptr,
+	//                            POOL_ALLOC_ARRAY *, PGConnPool &, bool isdummycall = false)
+	template <typename ParthaInfo, typename ListenerStateNotify, typename PoolArr, typename DbPool>
+	bool partha_listener_state(const std::shared_ptr<ParthaInfo> & partha_shr, const ListenerStateNotify *plist, int nitems, uint8_t *pendptr,
+			PoolArr * /*pthrpoolarr*/, DbPool & /*dbpool*/, bool isdummycall = false) noexcept
+	{
+		if (isdummycall) return true;
+		return forward(partha_shr, GYSK_NOTIFY_LISTENER_STATE, const_cast<ListenerStateNotify *>(plist), nitems, pendptr);
+	}
+
+	// the 5-s reducer tick (TCP_SOCK_HANDLER::listener_stats_update cadence, common/gy_socket_stat.cc:3898)
+	bool flush_window(uint32_t tsec) noexcept { return 0 == gysk_flush(engine_, tsec); }
+
+	gysk_engine * engine() const noexcept { return engine_; }
+
+private :
+	template <typename ParthaInfo, typename T>
+	bool forward(const std::shared_ptr<ParthaInfo> & partha_shr, uint32_t subtype, T *recs, int nevents, uint8_t *pendptr) noexcept
+	{
+		if (!partha_shr || !recs || nevents < 0) return false;
+		// same contract as the reference handlers: true = ok, false = failure, nothing thrown, caller memory not retained
+		return 0 == gysk_ingest(engine_, partha_traits<ParthaInfo>::machine_id(*partha_shr), partha_traits<ParthaInfo>::host_index(*partha_shr),
+				subtype, recs, (uint32_t)nevents, pendptr);
+	}
+
+	gysk_engine		*engine_;
+};
+
+} // namespace gysk_shim

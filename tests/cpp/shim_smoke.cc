@@ -1,0 +1,53 @@
+// Compiles the host-side mirror (gyeeta_b200/host/gy_gysk_shim.h) the way gy_mconnhdlr.cc would use it, with stand-in
+// PARTHA_INFO / pool types, links libgysketch.so and drives the three handlers. Without a GPU gysk_create() must fail with
+// GYSK_ERR_NODEV (no CPU fallback) and the handlers must return false without touching the records.
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "gy_gysk_shim.h"
+#include "gysk_wire.h"
+
+struct PARTHA_INFO { uint64_t machine_id_[2] {1, 2}; uint32_t gysk_host_idx_ {7}; };
+struct POOL_ALLOC_ARRAY {};
+struct PGConnPool {};
+
+int main()
+{
+	using namespace gysk::wire;
+
+	gysk_config cfg;
+	gysk_config_default(&cfg);
+	gysk_engine *e = nullptr;
+	int rc = gysk_create(&cfg, &e);
+	std::printf("gysk_create rc=%d (%s)\n", rc, rc ? gysk_last_error(nullptr) : "ok");
+
+	std::vector<uint8_t> buf(sizeof(TCP_CONN_NOTIFY) * 2 + 16);
+	auto *p = reinterpret_cast<TCP_CONN_NOTIFY *>(buf.data());
+	std::memset(p, 0, buf.size());
+	p[0].ser_glob_id_ = 11; p[0].cli_task_aggr_id_ = 22; p[0].is_tcp_accept_event_ = true; p[0].tusec_close_ = 5; p[0].bytes_sent_ = 4096;
+
+	gysk_shim::GYSK_HANDLER h(e);
+	auto partha = std::make_shared<PARTHA_INFO>();
+	POOL_ALLOC_ARRAY pool; PGConnPool db;
+
+	bool ok1 = h.partha_tcp_conn_info(partha, p, 1, buf.data() + sizeof(TCP_CONN_NOTIFY), &pool);
+	AGGR_TASK_STATE_NOTIFY t {}; t.aggr_task_id_ = 5; t.total_cpu_pct_ = 12.5f;
+	bool ok2 = h.partha_aggr_task_state(partha, &t, 1, reinterpret_cast<uint8_t *>(&t + 1), db);
+	LISTENER_STATE_NOTIFY l {}; l.glob_id_ = 11;
+	bool ok3 = h.partha_listener_state(partha, &l, 1, reinterpret_cast<uint8_t *>(&l + 1), &pool, db);
+	std::printf("handlers: %d %d %d\n", ok1, ok2, ok3);
+
+	if (e) {
+		gysk_svc_summary s;
+		uint64_t id = 11;
+		gysk_flush(e, 5);
+		rc = gysk_query_svcs(e, &id, 1, &s);
+		std::printf("query rc=%d found=%d nconns_5s=%u kbytes_5s=%u\n", rc, s.found, s.nconns_5s, s.kbytes_5s);
+		bool good = ok1 && ok2 && ok3 && rc == 0 && s.found == 1 && s.nconns_5s == 1 && s.kbytes_5s == 4;
+		gysk_destroy(e);
+		return good ? 0 : 2;
+	}
+	return (rc == GYSK_ERR_NODEV && !ok1 && !ok2 && !ok3) ? 0 : 1;
+}

@@ -83,13 +83,13 @@ def test_two_shards_merge_to_global_answers():
         assert x["distinct_clients"] == po.lib().gyo_hll_estimate(po._p(regs), 12)
         # t-digests: rank-ascending merge of two shard digests vs one engine folding 16 members: same samples, different
         # clustering => epsilon parity on the quantiles, exact parity on the counts
-        if x["td_count"] >= 5000:
+        if x["td_count"] >= 2000:
             for f in ("td_p50_us", "td_p95_us"):
                 assert abs(x[f] - z[f]) / z[f] < 0.01, (f, x[f], z[f])
             assert abs(x["td_p99_us"] - z["td_p99_us"]) / z["td_p99_us"] < 0.03
             assert x["td_p50_us"] == y["td_p50_us"]                                          # both ranks computed the same merge
             nonzero += 1
-    assert nonzero >= 5
+    assert nonzero >= 3
     # global count-min = sum of the shard tables = the single engine's table
     keys = np.unique(ev["flow_key"][(ev["type"] >= 1) & (ev["type"] <= 4)])[:1000]
     ga = shards[0].query_flows_global(keys, last_window=True)
