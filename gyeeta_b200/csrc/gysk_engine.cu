@@ -359,6 +359,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	st.cms_depth = cfg.cms_depth; st.cms_log2w = cfg.cms_log2_width; st.cms_wmask = (1u << cfg.cms_log2_width) - 1; st.hll_p = cfg.hll_p;
 	st.rank = cfg.rank; st.world = cfg.world; st.auto_register = (cfg.flags & GYSK_FLAG_AUTO_REGISTER) ? 1 : 0;
 	st.td_delta = (double)cfg.td_compression;
+	st.td.C = cos(M_PI / st.td_delta); st.td.S = sin(M_PI / st.td_delta); st.td.qclamp = (1.0 + st.td.C) / 2.0;
 
 	SortTemp &tmp = e->tmp;
 	tmp.max_tiles = (cfg.max_batch + SORT_TILE - 1) / SORT_TILE;

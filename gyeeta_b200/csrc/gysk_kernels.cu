@@ -10,7 +10,6 @@
 //   flush_kernel         5-s window roll                                               common/gy_socket_stat.cc:3898
 //   gather_* / query_*   read side
 #include "gysk_kernels.cuh"
-#include "gysk_tdigest.cuh"
 
 #include <cfloat>
 #include <climits>
@@ -443,7 +442,7 @@ static constexpr int PLAN_STRIDE = TD_CAP + 1;
 // (1) plan: one thread per touched service runs the greedy chain over n unit-weight samples. Cluster j of the run is
 // [bounds[j], bounds[j+1]) with bounds[j+1] = max(bounds[j] + 1, floor(n q(k(bounds[j]/n) + 1))): the boundaries depend on n
 // only, so they can be fixed before any sample is summed. Also clears the cluster-sum row of the service.
-__global__ void td_plan_kernel(double delta, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end,
+__global__ void td_plan_kernel(TdParams P, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end,
 		const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p, uint32_t *__restrict__ plan_bounds,
 		uint32_t *__restrict__ plan_n, unsigned long long *__restrict__ newsum)
 {
@@ -457,7 +456,7 @@ __global__ void td_plan_kernel(double delta, const uint32_t *__restrict__ seg_st
 		uint32_t nnew = 0, s = 0;
 
 		while (s < n) {
-			const double wl = td_wlimit(s, n, delta);
+			const double wl = td_wlimit(s, n, P);
 			unsigned long long ee = (unsigned long long)floor(wl);
 			if (ee > n) ee = n;
 			if (ee < (unsigned long long)s + 1) ee = s + 1;
@@ -540,8 +539,6 @@ __global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, co
 	TdScratch &S = scratch[wid];
 	const uint32_t ntouched = (uint32_t)*ntouched_p;
 	const uint32_t nwarps = gridDim.x * TD_WARPS;
-	const double delta = st.td_delta;
-
 	for (uint32_t t = blockIdx.x * TD_WARPS + wid; t < ntouched; t += nwarps) {
 		const uint32_t slot = touched[t];
 		const uint32_t s0 = seg_start[slot];
@@ -560,7 +557,7 @@ __global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, co
 
 		TdHead head = st.td_head[slot];
 		Centroid *cent = st.td_cent + (size_t)slot * TD_CAP;
-		const uint32_t nout = warp_merge_compress(S, cent, head.n, S.newc, nnew, cent, delta);
+		const uint32_t nout = warp_merge_compress(S, cent, head.n, S.newc, nnew, cent, st.td);
 		if (lane == 0) {
 			head.n = nout;
 			head.total += n;
@@ -753,9 +750,9 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, u
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-	td_plan_kernel<<<nsm * 2, 128, 0, s>>>(st.td_delta, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
+	td_plan_kernel<<<nsm * 2, 128, 0, s>>>(st.td, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
 	td_sums_kernel<<<nsm * 8, 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
-	td_merge_kernel<<<nsm * 4, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
+	td_merge_kernel<<<nsm * 6, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
 	return launches + 4;
 }
 

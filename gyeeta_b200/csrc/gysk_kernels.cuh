@@ -2,6 +2,7 @@
 #pragma once
 
 #include "gysk_device.cuh"
+#include "gysk_tdigest.cuh"
 #include "../../include/gysketch.h"
 
 namespace gysk {
@@ -24,6 +25,7 @@ struct DevState
 	uint32_t		cms_depth, cms_wmask, cms_log2w, hll_p;
 	uint32_t		rank, world, auto_register;
 	double			td_delta;
+	TdParams		td;
 	unsigned long long	*counters;				// [CTR_MAX]
 };
 

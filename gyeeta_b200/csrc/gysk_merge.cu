@@ -17,7 +17,6 @@
 // SHCONN_HANDLER::aggregate_cluster_state (server/gy_shconnhdlr.cc:4583) and of GY_HISTOGRAM::update_from_serialized
 // (common/gy_statistics.h:625-650): integer sums are order independent => bit-exact at any GPU count.
 #include "gysk_engine.h"
-#include "gysk_tdigest.cuh"
 
 #include <climits>
 
@@ -101,7 +100,7 @@ __global__ void __launch_bounds__(MG_WARPS * 32) fold_td_kernel(DevState st, con
 			const uint32_t s = members[m];
 			const TdHead h = st.td_head[s];
 			if (!h.n) continue;
-			nacc = warp_merge_compress(S, S.newc, nacc, st.td_cent + (size_t)s * TD_CAP, h.n, S.newc, st.td_delta);
+			nacc = warp_merge_compress(S, S.newc, nacc, st.td_cent + (size_t)s * TD_CAP, h.n, S.newc, st.td);
 			total += h.total; mn = fmin(mn, h.minv); mx = fmax(mx, h.maxv);
 		}
 		for (uint32_t c = lane; c < TD_CAP; c += 32) slab[l].cent[c] = c < nacc ? S.newc[c] : Centroid {0.0, 0};
@@ -112,7 +111,7 @@ __global__ void __launch_bounds__(MG_WARPS * 32) fold_td_kernel(DevState st, con
 
 // one warp per logical service over the all-gathered slabs [world][nl]
 __global__ void __launch_bounds__(MG_WARPS * 32) finish_td_kernel(const SlabEntry *__restrict__ gathered, uint32_t world, uint32_t nl,
-		SlabEntry *__restrict__ out, double delta)
+		SlabEntry *__restrict__ out, TdParams P)
 {
 	__shared__ TdScratch scratch[MG_WARPS];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -126,7 +125,7 @@ __global__ void __launch_bounds__(MG_WARPS * 32) finish_td_kernel(const SlabEntr
 		for (uint32_t r = 0; r < world; ++r) {			// fixed rank-ascending order => deterministic result
 			const SlabEntry &e = gathered[(size_t)r * nl + l];
 			if (!e.head.n) continue;
-			nacc = warp_merge_compress(S, S.newc, nacc, e.cent, e.head.n, S.newc, delta);
+			nacc = warp_merge_compress(S, S.newc, nacc, e.cent, e.head.n, S.newc, P);
 			total += e.head.total; mn = fmin(mn, e.head.minv); mx = fmax(mx, e.head.maxv);
 		}
 		for (uint32_t c = lane; c < TD_CAP; c += 32) out[l].cent[c] = c < nacc ? S.newc[c] : Centroid {0.0, 0};
@@ -342,7 +341,7 @@ int gysk_merge_finish(gysk_engine *e, const void *d_gathered, uint32_t world)
 	if (!d_gathered) world = 1;
 	if (mg.nlogical) {
 		finish_td_kernel<<<std::min<uint32_t>(div_up(mg.nlogical, MG_WARPS), 148 * 8), MG_WARPS * 32, 0, e->stream>>>(src, world, mg.nlogical,
-				reinterpret_cast<SlabEntry *>(mg.final_slab), e->st.td_delta);
+				reinterpret_cast<SlabEntry *>(mg.final_slab), e->st.td);
 		e->kernel_launches++;
 	}
 	CU(e, cudaStreamSynchronize(e->stream));

@@ -6,22 +6,26 @@
 
 namespace gysk {
 
-// K_1 scale function of the merging t-digest (Dunning), k spanning [-delta/2, delta/2]: k(q) = delta/pi asin(2q - 1)
-__device__ __forceinline__ double td_k(double q, double delta)
+// K_1 scale function of the merging t-digest (Dunning), k spanning [-delta/2, delta/2]: k(q) = delta/pi asin(2q - 1).
+// td_q_next(q0) = q(k(q0) + 1), the upper end of the unit-k interval starting at q0, without inverse trig:
+// sin(asin(2 q0 - 1) + pi/delta) = (2 q0 - 1) cos(pi/delta) + 2 sqrt(q0 (1 - q0)) sin(pi/delta). Only IEEE + - * / sqrt with
+// explicit round-to-nearest (no FMA contraction), in the same order as oracle/gysk_oracle.c::td_q_next => identical bits.
+struct TdParams { double C, S, qclamp; };		// cos(pi/delta), sin(pi/delta), (1 + C)/2 — computed once on the host
+
+__device__ __forceinline__ double td_q_next(double q0, const TdParams &P)
 {
-	return __dmul_rn(__ddiv_rn(delta, M_PI), asin(__dsub_rn(__dmul_rn(2.0, q), 1.0)));
+	if (q0 >= P.qclamp) return 1.0;
+	const double t = __dsub_rn(__dmul_rn(2.0, q0), 1.0);
+	const double r = __dsqrt_rn(__dmul_rn(q0, __dsub_rn(1.0, q0)));
+	const double a = __dmul_rn(t, P.C);
+	const double b = __dmul_rn(__dmul_rn(2.0, r), P.S);
+	return __ddiv_rn(__dadd_rn(__dadd_rn(a, b), 1.0), 2.0);
 }
 
-__device__ __forceinline__ double td_q(double k, double delta)
-{
-	if (k >= __ddiv_rn(delta, 2.0)) return 1.0;
-	return __ddiv_rn(__dadd_rn(sin(__ddiv_rn(__dmul_rn(k, M_PI), delta)), 1.0), 2.0);
-}
-
-__device__ __forceinline__ double td_wlimit(unsigned long long wsofar, unsigned long long W, double delta)
+__device__ __forceinline__ double td_wlimit(unsigned long long wsofar, unsigned long long W, const TdParams &P)
 {
 	const double q0 = wsofar ? __ddiv_rn((double)wsofar, (double)W) : 0.0;
-	return __dmul_rn((double)W, td_q(__dadd_rn(td_k(q0, delta), 1.0), delta));
+	return __dmul_rn((double)W, td_q_next(q0, P));
 }
 
 struct TdScratch
@@ -37,7 +41,7 @@ struct TdScratch
 // Both inputs are fully consumed into S.merged before `out` is written, so `out` may alias `a` or `b`.
 // Returns the number of centroids written to out (<= TD_CAP).
 __device__ __forceinline__ uint32_t warp_merge_compress(TdScratch &S, const Centroid *a, uint32_t na, const Centroid *b, uint32_t nb,
-		Centroid *out, double delta)
+		Centroid *out, const TdParams &P)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t nm = na + nb;
@@ -81,10 +85,9 @@ __device__ __forceinline__ uint32_t warp_merge_compress(TdScratch &S, const Cent
 		const unsigned long long W = S.prefix[nm];
 		uint32_t cs = 0;
 		while (cs < nm) {
-			const double wl = td_wlimit(S.prefix[cs], W, delta);
-			uint32_t lo = cs + 1, hi = nm;			// largest e in [cs+1, nm] with prefix[e] <= wl
-			while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if ((double)S.prefix[mid] <= wl) lo = mid; else hi = mid - 1; }
-			uint32_t e = lo;
+			const double wl = td_wlimit(S.prefix[cs], W, P);
+			uint32_t e = cs + 1;				// largest e in [cs+1, nm] with prefix[e] <= wl: clusters of the
+			while (e < nm && (double)S.prefix[e + 1] <= wl) ++e;	// merged list hold ~2 items, a forward scan beats bisection
 			if (nout == TD_CAP - 1) e = nm;			// the last slot absorbs whatever is left
 			S.bounds[nout++] = cs;
 			cs = e;

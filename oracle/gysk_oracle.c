@@ -322,15 +322,26 @@ double gyo_hll_estimate(const uint8_t *regs, uint32_t p)
  * reference (Postgres public.tdigest(x, 100), common/gy_query_common.cc:1855; folly::TDigest(100) behind
  * SlidingWindowQuantileEstimator, test/test_quantiles.cc:32).
  * ------------------------------------------------------------------------------------------------ */
-static inline double td_k(double q, double delta)
+/* Upper end q1 of the unit-k interval that starts at q0: q1 = q(k(q0) + 1) with k(q) = delta/pi asin(2q - 1), written without
+ * inverse trig: with theta = asin(2 q0 - 1), sin(theta + pi/delta) = (2 q0 - 1) cos(pi/delta) + 2 sqrt(q0 (1 - q0)) sin(pi/delta).
+ * Only IEEE +,-,*,/ and sqrt, each rounded on its own, in this order — the CUDA path performs the identical sequence, so both
+ * produce the same bits. */
+static inline double td_q_next(double q0, double C, double S)
 {
-	return delta / M_PI * asin(2.0 * q - 1.0);
+	if (q0 >= (1.0 + C) / 2.0) return 1.0;			/* k(q0) + 1 >= delta/2 */
+	double t = 2.0 * q0 - 1.0;
+	double r = sqrt(q0 * (1.0 - q0));
+	double a = t * C;
+	double b = (2.0 * r) * S;
+	return ((a + b) + 1.0) / 2.0;
 }
 
-static inline double td_q(double k, double delta)
+static inline double td_wlimit(uint64_t wsofar, uint64_t W, double delta)
 {
-	if (k >= delta / 2.0) return 1.0;
-	return (sin(k * M_PI / delta) + 1.0) / 2.0;
+	const double C = cos(M_PI / delta), S = sin(M_PI / delta);
+	const double q0 = wsofar ? (double)wsofar / (double)W : 0.0;
+
+	return (double)W * td_q_next(q0, C, S);
 }
 
 void gyo_td_init(gyo_tdigest *t)
@@ -351,7 +362,7 @@ uint32_t gyo_td_compress(const gyo_centroid *in, uint32_t n, double delta, gyo_c
 	if (!n) return 0;
 	for (uint32_t i = 0; i < n; ++i) W += in[i].weight;
 
-	wlimit = (double)W * td_q(td_k(0.0, delta) + 1.0, delta);
+	wlimit = td_wlimit(0, W, delta);
 	cw = in[0].weight; csum = in[0].mean * (double)in[0].weight;
 
 	for (uint32_t i = 1; i < n; ++i) {
@@ -365,7 +376,7 @@ uint32_t gyo_td_compress(const gyo_centroid *in, uint32_t n, double delta, gyo_c
 			if (nout < cap) { out[nout].mean = csum / (double)cw; out[nout].weight = cw; }
 			nout++;
 			wsofar += cw;
-			wlimit = (double)W * td_q(td_k((double)wsofar / (double)W, delta) + 1.0, delta);
+			wlimit = td_wlimit(wsofar, W, delta);
 			cw = in[i].weight; csum = in[i].mean * (double)in[i].weight;
 		}
 	}
@@ -407,7 +418,7 @@ void gyo_td_add_batch(gyo_tdigest *t, const uint32_t *vals, uint32_t n, double d
 
 	/* greedy clustering of n unit weights: cluster [s, e), e = max(s + 1, floor(W q(k(s/W) + 1))) */
 	while (s < n) {
-		double wlimit = (double)n * td_q(td_k((double)s / (double)n, delta) + 1.0, delta);
+		double wlimit = td_wlimit(s, n, delta);
 		uint64_t e = (uint64_t)floor(wlimit);
 		uint64_t sum = 0;
 
