@@ -76,22 +76,28 @@ __device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cel
 	}
 }
 
-// all 32 lanes call this; lanes with active == false only take part in the collectives
+// all 32 lanes call this; lanes with active == false only take part in the collectives.
+// Group sums use a shuffle loop bounded by the largest group of the warp (typically 1-4): redux with per-lane masks would
+// make the compiler iterate over every distinct group.
 __device__ __forceinline__ void cell_add(const DevState &st, HotEntry *hot, bool active, uint32_t cell, int data, bool track_max)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t id = active ? cell : (0x80000000u | (uint32_t)lane);
 	const uint32_t m = __match_any_sync(0xffffffffu, id);
 	const uint32_t cnt = __popc(m);
-	// 64-bit sum of the group's int values from three 32-bit reductions: sum(u32 pattern) - 2^32 * #negatives
-	const uint32_t slo = __reduce_add_sync(m, (uint32_t)data & 0xFFFFu);
-	const uint32_t shi = __reduce_add_sync(m, (uint32_t)data >> 16);
-	const uint32_t nneg = __reduce_add_sync(m, data < 0 ? 1u : 0u);
-	const int gmax = __reduce_max_sync(m, data);
+	const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+	long long sum = data;
+	int gmax = data;
+	uint32_t rest = m & ~(1u << lane);
+
+	for (uint32_t t = 1; t < maxcnt; ++t) {
+		const int src = rest ? (__ffs(rest) - 1) : lane;
+		const int other = __shfl_sync(0xffffffffu, data, src);
+		if (rest) { sum += other; gmax = max(gmax, other); rest &= rest - 1; }
+	}
 
 	if (!active || (m & ((1u << lane) - 1u))) return;		// group leader = lowest lane
 
-	const unsigned long long sum = (unsigned long long)slo + ((unsigned long long)shi << 16) - ((unsigned long long)nneg << 32);
 	HotEntry *e = hot + ((cell * 2654435761u) >> (32 - HOT_BITS));
 	uint32_t tag = *((volatile uint32_t *)&e->tag);
 	bool hit = tag == cell + 1;
@@ -100,8 +106,8 @@ __device__ __forceinline__ void cell_add(const DevState &st, HotEntry *hot, bool
 		tag = atomicCAS(&e->tag, 0u, cell + 1);
 		hit = tag == 0 || tag == cell + 1;
 	}
-	if (hit) { atomicAdd(&e->count, cnt); atomicAdd(&e->sum, sum); }
-	else cell_add_global(st, cell, cnt, sum);
+	if (hit) { atomicAdd(&e->count, cnt); atomicAdd(&e->sum, (unsigned long long)sum); }
+	else cell_add_global(st, cell, cnt, (unsigned long long)sum);
 
 	if (track_max) {
 		// max_val_seen_: a (possibly stale) cached read first, the atomic only while the maximum still grows
@@ -156,55 +162,48 @@ __global__ void __launch_bounds__(256) ingest_kernel(DevState st, const gysk_eve
 			}
 			else {
 				c_in++;
-				if (svc_id == 0) {
+				const bool is_resp = type == GYSK_EV_RESP, is_task = type == GYSK_EV_TASK;
+				const bool is_tcp = type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER;
+				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
+				// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
+				const uint32_t ms = value / 1000u;
+				int slot = -1;
+				// one id lookup for all three event kinds (services and tasks live in separate tables)
+				if (svc_id != 0 && (is_tcp || is_task || (is_resp && ms <= 1000000u)))
+					slot = table_lookup(is_task ? st.task_tbl : st.svc_tbl, svc_id, st.auto_register);
+
+				if (slot < 0) {
 					c_drop++;
 				}
-				else if (type == GYSK_EV_RESP) {
-					// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule
-					// of handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-					const uint32_t ms = value / 1000u;
-					int slot = -1;
-					if (ms <= 1000000u) slot = table_lookup(st.svc_tbl, svc_id, st.auto_register);
-					if (slot < 0) c_drop++;
-					else {
-						// GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data, gy_statistics.h:596-623
-						cell0 = (uint32_t)slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
-						d0 = (int)ms; a0 = true; max0 = true;
-						key = ((unsigned long long)(uint32_t)slot << VALUE_BITS) | value;
-						c_resp++;
-					}
+				else if (is_resp) {
+					// GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data, gy_statistics.h:596-623
+					cell0 = (uint32_t)slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
+					d0 = (int)ms; a0 = true; max0 = true;
+					key = ((unsigned long long)(uint32_t)slot << VALUE_BITS) | value;
+					c_resp++;
 				}
-				else if (type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER) {
-					const int slot = table_lookup(st.svc_tbl, svc_id, st.auto_register);
-					if (slot < 0) c_drop++;
-					else {
-						const unsigned long long inc = cms_increment(value);
-						for (uint32_t r = 0; r < st.cms_depth; ++r) {
-							red_add_u64(st.cms_cur + ((size_t)r << st.cms_log2w) + cms_index(flow_key, r, st.cms_wmask), inc);
-						}
-						uint32_t idx, rank;
-						hll_idx_rank(flow_key, st.hll_p, idx, rank);
-						hll_update(st.hll + ((size_t)slot << st.hll_p), idx, rank);
-						cell0 = (uint32_t)slot * HIST_CELLS + HIST_MAX_CELL;		// exact per-service {count, kbytes} cell
-						d0 = (int)(value >> 10); a0 = true;
-						c_tcp++;
+				else if (is_tcp) {
+					const unsigned long long inc = cms_increment(value);
+					for (uint32_t r = 0; r < st.cms_depth; ++r) {
+						red_add_u64(st.cms_cur + ((size_t)r << st.cms_log2w) + cms_index(flow_key, r, st.cms_wmask), inc);
 					}
+					uint32_t idx, rank;
+					hll_idx_rank(flow_key, st.hll_p, idx, rank);
+					hll_update(st.hll + ((size_t)slot << st.hll_p), idx, rank);
+					cell0 = (uint32_t)slot * HIST_CELLS + HIST_MAX_CELL;		// exact per-service {count, kbytes} cell
+					d0 = (int)(value >> 10); a0 = true;
+					c_tcp++;
 				}
-				else if (type == GYSK_EV_TASK) {
-					const int slot = table_lookup(st.task_tbl, svc_id, st.auto_register);
-					if (slot < 0) c_drop++;
-					else {
-						// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
-						const uint32_t tb = CELL_TASK | ((uint32_t)slot * 3u * HIST_CELLS);
-						d0 = (int)value; d1 = (int)(uint32_t)flow_key; d2 = (int)(uint32_t)(flow_key >> 32);
-						cell0 = tb + (uint32_t)bucket_hash_1_3000(d0);
-						cell1 = tb + HIST_CELLS + (uint32_t)bucket_duration(d1);
-						cell2 = tb + 2 * HIST_CELLS + (uint32_t)bucket_duration(d2);
-						a0 = true; a12 = true; max0 = true;
-						c_task++;
-					}
+				else {
+					// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
+					const uint32_t tb = CELL_TASK | ((uint32_t)slot * 3u * HIST_CELLS);
+					d0 = (int)value; d1 = (int)(uint32_t)flow_key; d2 = (int)(uint32_t)(flow_key >> 32);
+					cell0 = tb + (uint32_t)bucket_hash_1_3000(d0);
+					cell1 = tb + HIST_CELLS + (uint32_t)bucket_duration(d1);
+					cell2 = tb + 2 * HIST_CELLS + (uint32_t)bucket_duration(d2);
+					a0 = true; a12 = true; max0 = true;
+					c_task++;
 				}
-				else c_drop++;
 			}
 			keys[i] = key;
 		}
@@ -518,11 +517,23 @@ __global__ void __launch_bounds__(256) td_sums_kernel(const unsigned long long *
 		}
 		const uint32_t gid = valid ? (slot * (uint32_t)TD_CAP + j) : (0xFFFFFF00u + lane);
 		const uint32_t m = __match_any_sync(0xffffffffu, gid);
-		// group sum in two 32-bit halves (values < 2^30: 32 of them fit the split sums)
-		const uint32_t slo = __reduce_add_sync(m, v & 0xFFFFu);
-		const uint32_t shi = __reduce_add_sync(m, v >> 16);
+		// group sum by a shuffle loop bounded by the warp's largest group (redux with per-lane masks would iterate over
+		// every distinct group); a warp inside one hot cluster takes the single-group fast path
+		unsigned long long gsum = v;
+		if (m == 0xffffffffu) {
+			gsum = (unsigned long long)__reduce_add_sync(0xffffffffu, v & 0xFFFFu) + ((unsigned long long)__reduce_add_sync(0xffffffffu, v >> 16) << 16);
+		}
+		else {
+			const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(m));
+			uint32_t rest = m & ~(1u << lane);
+			for (uint32_t t = 1; t < maxcnt; ++t) {
+				const int src = rest ? (__ffs(rest) - 1) : lane;
+				const uint32_t other = __shfl_sync(0xffffffffu, v, src);
+				if (rest) { gsum += other; rest &= rest - 1; }
+			}
+		}
 		if (valid && (m & ((1u << lane) - 1u)) == 0) {
-			red_add_u64(newsum + (size_t)slot * TD_CAP + j, (unsigned long long)slo + ((unsigned long long)shi << 16));
+			red_add_u64(newsum + (size_t)slot * TD_CAP + j, gsum);
 		}
 	}
 }
