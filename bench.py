@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gysketch", choices=["gysketch", "reference"])
     ap.add_argument("--events", type=int, default=100_000_000, help="events per rank per step")
-    ap.add_argument("--max-batch", type=int, default=1 << 24)
+    ap.add_argument("--max-batch", type=int, default=1 << 27, help="events per device batch (value path: one batch per step)")
+    ap.add_argument("--stage-batch", type=int, default=1 << 23, help="events per H2D chunk on the host-buffer path")
     ap.add_argument("--cpu-sample", type=int, default=20_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -244,7 +245,7 @@ def main():
     dev = torch.device("cuda", local)
     n = args.events
 
-    eng = ge.Engine(device=local, max_svcs=1 << 17, max_tasks=1 << 15, max_batch=args.max_batch, rank=rank, world=world)
+    eng = ge.Engine(device=local, max_svcs=1 << 17, max_tasks=1 << 15, max_batch=args.max_batch, stage_batch=args.stage_batch, rank=rank, world=world)
     ev_dev = gen_events_gpu(torch, n, 1234 + rank, rank, world, dev)
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
@@ -377,7 +378,7 @@ def main():
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "configs[2]: 100M mixed RESP/TCP/TASK (70/20/10) events, 100K services, count-min + HLL + "
                                "fixed-bucket histograms + t-digest(100)", "events_per_step_per_gpu": n, "services": NSVC,
-                   "zipf_s": ZIPF_S, "max_batch": args.max_batch, "parallelism": f"host-shard x{world}",
+                   "zipf_s": ZIPF_S, "max_batch": args.max_batch, "stage_batch": args.stage_batch, "parallelism": f"host-shard x{world}",
                    "l2": "inputs (3.2 GB/step) larger than L2, no flush needed"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof[0] if roof else None, "roofline_other": roof[1:] or None,

@@ -106,19 +106,19 @@ namespace {
 int stage_events(gysk_engine *e, const gysk_event *ev, uint64_t n)
 {
 	while (n) {
-		const uint32_t room = e->cfg.max_batch - e->stage_fill;
+		const uint32_t room = e->cfg.stage_batch - e->stage_fill;
 		const uint32_t m = (uint32_t)std::min<uint64_t>(room, n);
 
 		memcpy(e->h_stage[e->stage_cur] + e->stage_fill, ev, (size_t)m * sizeof(gysk_event));
 		e->stage_fill += m; ev += m; n -= m;
-		if (e->stage_fill == e->cfg.max_batch) { int rc = submit_stage(e); if (rc) return rc; }
+		if (e->stage_fill == e->cfg.stage_batch) { int rc = submit_stage(e); if (rc) return rc; }
 	}
 	return 0;
 }
 
 inline gysk_event *stage_slot(gysk_engine *e, int *rc)
 {
-	if (e->stage_fill == e->cfg.max_batch) { *rc = submit_stage(e); if (*rc) return nullptr; }
+	if (e->stage_fill == e->cfg.stage_batch) { *rc = submit_stage(e); if (*rc) return nullptr; }
 	return e->h_stage[e->stage_cur] + e->stage_fill++;
 }
 
@@ -202,11 +202,26 @@ double hll_estimate_from_hist(const uint32_t *hist64, uint32_t p)
 	return est;
 }
 
+// width of one ring slot per level: Level_5s_5min_5days_all durations {300 s, 432000 s} / 10 slots (gy_statistics.h:1548, :1105)
+const uint32_t g_level_width[NLEVELS] = { 30, 43200 };
+
+uint32_t live_mask(const gysk_engine *e, int l)
+{
+	const uint64_t now_epoch = e->last_flush_tsec / g_level_width[l];
+	uint32_t m = 0;
+
+	for (int k = 0; k < NSLOTS; ++k) {
+		const uint64_t ep = e->ring_epoch[l][k];
+		if (ep != ~0ull && ep + NSLOTS > now_epoch && ep <= now_epoch) m |= 1u << k;
+	}
+	return m;
+}
+
 int gather_svcs(gysk_engine *e, const uint64_t *ids, uint32_t n)		// n <= QCHUNK; results in e->h_svcraw
 {
 	memcpy(e->h_qids, ids, (size_t)n * sizeof(uint64_t));
 	CU(e, cudaMemcpyAsync(e->d_qids, e->h_qids, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
-	e->kernel_launches += launch_gather_svcs(e->st, e->d_qids, n, e->d_svcraw, e->stream);
+	e->kernel_launches += launch_gather_svcs(e->st, e->d_qids, n, e->cfg.max_svcs, live_mask(e, 0), live_mask(e, 1), e->d_svcraw, e->stream);
 	CU(e, cudaMemcpyAsync(e->h_svcraw, e->d_svcraw, (size_t)n * sizeof(SvcRaw), cudaMemcpyDeviceToHost, e->stream));
 	CU(e, cudaStreamSynchronize(e->stream));
 	return post_launch(e, "gather_svcs");
@@ -233,6 +248,13 @@ void gysk::summarize_raw(const gysk_engine *e, const SvcRaw &r, uint64_t id, gys
 	o.nqrys_5s = (uint32_t)total;
 	for (int b = 0; b < 15; ++b) o.total_resp_5sec += (uint64_t)ser[b].sum;
 	o.p95_5s_resp_ms = p[0]; o.p99_5s_resp_ms = p[1]; o.p25_5s_resp_ms = p[2];
+
+	hist_from_cells(r.lvl[0], 15, ser, &total, &maxv, false);
+	gysk_hist_percentiles(GYSK_CLS_RESP_TIME, 0, ser, total, pcts, 2, p);
+	o.p95_5min_resp_ms = p[0]; o.p99_5min_resp_ms = p[1]; o.nqrys_5min = total;
+	hist_from_cells(r.lvl[1], 15, ser, &total, &maxv, false);
+	gysk_hist_percentiles(GYSK_CLS_RESP_TIME, 0, ser, total, pcts, 1, p);
+	o.p95_5day_resp_ms = p[0]; o.nqrys_5day = total;
 
 	hist_from_cells(r.all, 15, ser, &total, &maxv, false);
 	gysk_hist_percentiles(GYSK_CLS_RESP_TIME, 0, ser, total, pcts, 2, p);
@@ -273,6 +295,7 @@ void gysk_config_default(gysk_config *cfg)
 	cfg->hll_p = 12;
 	cfg->td_compression = 100;
 	cfg->max_batch = 1u << 22;
+	cfg->stage_batch = 0;
 	cfg->flags = GYSK_FLAG_AUTO_REGISTER;
 	cfg->rank = 0; cfg->world = 1;
 }
@@ -312,6 +335,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 		cfg = *ucfg;
 	}
 	if (!cfg.world) cfg.world = 1;
+	if (!cfg.stage_batch || cfg.stage_batch > cfg.max_batch) cfg.stage_batch = std::min<uint32_t>(cfg.max_batch, 1u << 22);
 	if (cfg.max_svcs < 1 || cfg.max_svcs > (1u << 24) || cfg.max_tasks < 1 || cfg.max_tasks > (1u << 24) || cfg.cms_depth < 1 ||
 			cfg.cms_depth > 8 || cfg.cms_log2_width < 4 || cfg.cms_log2_width > 28 || cfg.hll_p < 4 || cfg.hll_p > 16 ||
 			cfg.td_compression < 10 || cfg.td_compression > 120 || cfg.max_batch < 1024 || cfg.max_batch > (1u << 28) ||
@@ -330,6 +354,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	gysk_engine *e = new (std::nothrow) gysk_engine;
 	if (!e) return fail(nullptr, GYSK_ERR_NOMEM, "new gysk_engine");
 	e->cfg = cfg; e->dev = cfg.device;
+	memset(e->ring_epoch, 0xFF, sizeof(e->ring_epoch));
 
 	int rc = 0;
 	auto bail = [&](int code) { g_create_error = e->err; gysk_destroy(e); return code; };
@@ -350,6 +375,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(dalloc(e, &st.task_tbl.ent, tcap)); st.task_tbl.mask = tcap - 1; st.task_tbl.max_slots = cfg.max_tasks;
 	A(dalloc(e, &st.task_tbl.count, 1));
 	A(dalloc(e, &st.hist_cur, ns * HIST_CELLS)); A(dalloc(e, &st.hist_last, ns * HIST_CELLS)); A(dalloc(e, &st.hist_all, ns * HIST_CELLS));
+	A(dalloc(e, &st.hist_ring, (size_t)NLEVELS * NSLOTS * ns * HIST_CELLS));
 	A(dalloc(e, &st.conn_cur, ns)); A(dalloc(e, &st.conn_last, ns)); A(dalloc(e, &st.conn_all_cnt, ns)); A(dalloc(e, &st.conn_all_kb, ns));
 	A(dalloc(e, &st.hll, ns << cfg.hll_p));
 	A(dalloc(e, &st.td_cent, ns * TD_CAP)); A(dalloc(e, &st.td_head, ns));
@@ -370,8 +396,8 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(dalloc(e, &tmp.plan_bounds, ns * (TD_CAP + 1))); A(dalloc(e, &tmp.plan_n, ns)); A(dalloc(e, &tmp.newsum, ns * TD_CAP));
 
 	for (int k = 0; k < NBUF; ++k) {
-		A(halloc(e, &e->h_stage[k], (size_t)cfg.max_batch));
-		A(dalloc(e, &e->d_events[k], (size_t)cfg.max_batch, false));
+		A(halloc(e, &e->h_stage[k], (size_t)cfg.stage_batch));
+		A(dalloc(e, &e->d_events[k], (size_t)cfg.stage_batch, false));
 		if ((ce = cudaEventCreateWithFlags(&e->ev_copied[k], cudaEventDisableTiming)) != cudaSuccess ||
 				(ce = cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming)) != cudaSuccess) {
 			fail(e, GYSK_ERR_CUDA, "cudaEventCreate", ce); return bail(GYSK_ERR_CUDA);
@@ -492,8 +518,8 @@ int gysk_ingest_pinned(gysk_engine *e, const gysk_event *pinned, uint64_t n)
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
-	for (uint64_t off = 0; off < n; off += e->cfg.max_batch) {
-		const uint64_t m = std::min<uint64_t>(e->cfg.max_batch, n - off);
+	for (uint64_t off = 0; off < n; off += e->cfg.stage_batch) {
+		const uint64_t m = std::min<uint64_t>(e->cfg.stage_batch, n - off);
 		const int k = e->stage_cur;
 		CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_done[k], 0));
 		CU(e, cudaMemcpyAsync(e->d_events[k], pinned + off, (size_t)m * sizeof(gysk_event), cudaMemcpyHostToDevice, e->copy_stream));
@@ -674,12 +700,26 @@ int gysk_sync(gysk_engine *e)
 int gysk_flush(gysk_engine *e, uint32_t tsec)
 {
 	CHECK_ENGINE(e);
-	(void)tsec;
 	std::lock_guard<std::mutex> lk(e->mtx);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
-	e->kernel_launches += launch_flush(e->st, e->cfg.max_svcs, e->stream);
+
+	// rolling levels: the closing window goes to slot (tsec / width) % 10; a slot still holding an older epoch is cleared first
+	const size_t plane = (size_t)e->cfg.max_svcs * HIST_CELLS;
+	HistCell *planes[NLEVELS];
+	for (int l = 0; l < NLEVELS; ++l) {
+		const uint64_t epoch = tsec / g_level_width[l];
+		const int k = (int)(epoch % NSLOTS);
+		planes[l] = e->st.hist_ring + ((size_t)l * NSLOTS + k) * plane;
+		if (e->ring_epoch[l][k] != epoch) {
+			CU(e, cudaMemsetAsync(planes[l], 0, plane * sizeof(HistCell), e->stream));
+			e->ring_epoch[l][k] = epoch;
+		}
+	}
+	e->last_flush_tsec = tsec;
+
+	e->kernel_launches += launch_flush(e->st, e->cfg.max_svcs, planes[0], planes[1], e->stream);
 	std::swap(e->st.cms_cur, e->st.cms_last);
 	CU(e, cudaMemsetAsync(e->st.cms_cur, 0, sizeof(unsigned long long) * ((size_t)e->cfg.cms_depth << e->cfg.cms_log2_width), e->stream));
 	return post_launch(e, "flush");
@@ -711,7 +751,8 @@ int gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial ou
 {
 	CHECK_ENGINE(e);
 	if (!out || !total || !maxv) return GYSK_ERR_INVAL;
-	if (which >= GYSK_HIST_TASK_CPU_PCT) return gysk_export_task_hist(e, id, which, out, total, maxv);
+	if (which >= GYSK_HIST_TASK_CPU_PCT && which <= GYSK_HIST_TASK_BLKIO_DELAY) return gysk_export_task_hist(e, id, which, out, total, maxv);
+	if (which > GYSK_HIST_RESP_5DAY) return GYSK_ERR_INVAL;
 	if (which < 0) return GYSK_ERR_INVAL;
 	std::lock_guard<std::mutex> lk(e->mtx);
 	CU(e, cudaSetDevice(e->dev));
@@ -720,6 +761,11 @@ int gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial ou
 	if ((rc = gather_svcs(e, &id, 1))) return rc;
 	const SvcRaw &r = e->h_svcraw[0];
 	if (!r.found) return GYSK_ERR_NOENT;
+	if (which == GYSK_HIST_RESP_5MIN || which == GYSK_HIST_RESP_5DAY) {
+		hist_from_cells(r.lvl[which - GYSK_HIST_RESP_5MIN], 15, out, total, maxv, false);
+		if (*total == 0) *maxv = INT64_MIN;
+		return GYSK_OK;
+	}
 	hist_from_cells(which == GYSK_HIST_RESP_CUR ? r.cur : (which == GYSK_HIST_RESP_LAST ? r.last : r.all), 15, out, total, maxv, false);
 	return GYSK_OK;
 }

@@ -77,6 +77,10 @@ struct gysk_engine
 	std::vector<cudaEvent_t> prof_events;		// triples: before ingest, after ingest, after t-digest chain
 	size_t			prof_used {0};
 
+	// rolling levels: epoch held by each ring slot (~0 = never written) and the time of the last flush
+	uint64_t		ring_epoch[gysk::NLEVELS][gysk::NSLOTS];
+	uint32_t		last_flush_tsec {0};
+
 	gysk::MergeState	mg;
 
 	std::mutex		mtx;

@@ -14,6 +14,7 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 
 namespace gysk {
 
@@ -55,17 +56,27 @@ __global__ void register_kernel(DevState st, const unsigned long long *ids, uint
 //   CTA  : a direct-mapped shared-memory table privatises hot cells for the lifetime of the CTA (a cell is admitted when it
 //          shows up at least twice inside one warp), and is flushed with one RED pair per entry when the CTA retires.
 // Everything stays exact integer arithmetic, so the result is independent of grouping and order.
-struct HotEntry { uint32_t tag; uint32_t count; unsigned long long sum; };
-static constexpr int HOT_BITS = 11;
-static constexpr int HOT_N = 1 << HOT_BITS;			// 32 KB of shared memory
+struct HotTable					// structure of arrays, 20 B per entry
+{
+	static constexpr int BITS = 10;
+	static constexpr int N = 1 << BITS;
+	uint32_t		tag[N];			// cell id + 1, 0 = free
+	uint32_t		count[N];
+	unsigned long long	sum[N];
+	int			vmax[N];
+};
 static constexpr uint32_t CELL_TASK = 1u << 30;			// cell ids: svc hist = slot*16 + bucket, conn = slot*16 + 15,
 								//           task = CELL_TASK | (tslot*48 + hist*16 + bucket)
 
-__device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cell, uint32_t cnt, unsigned long long sum)
+__device__ __forceinline__ bool cell_is_conn(uint32_t cell) { return !(cell & CELL_TASK) && (cell & 15u) == (uint32_t)HIST_MAX_CELL; }
+
+// one RED per field, nothing is read back: {count, sum} (+ max_val_seen_ for histogram cells)
+__device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cell, uint32_t cnt, unsigned long long sum, int vmax)
 {
 	if (cell & CELL_TASK) {
 		HistCell *c = st.task_hist + (cell & ~CELL_TASK);
 		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
+		atomicMax(&st.task_hist[(cell & ~CELL_TASK) | 15u].sum, (long long)vmax);
 	}
 	else if ((cell & 15u) == (uint32_t)HIST_MAX_CELL) {
 		red_add_u64(st.conn_cur + (cell >> 4), (unsigned long long)cnt + (sum << 32));	// packed {count, kbytes}
@@ -73,13 +84,14 @@ __device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cel
 	else {
 		HistCell *c = st.hist_cur + cell;
 		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
+		atomicMax(&st.hist_cur[cell | 15u].sum, (long long)vmax);
 	}
 }
 
 // all 32 lanes call this; lanes with active == false only take part in the collectives.
 // Group sums use a shuffle loop bounded by the largest group of the warp (typically 1-4): redux with per-lane masks would
-// make the compiler iterate over every distinct group.
-__device__ __forceinline__ void cell_add(const DevState &st, HotEntry *hot, bool active, uint32_t cell, int data, bool track_max)
+// make the compiler iterate over every distinct group. No global load anywhere: the updates are fire-and-forget REDs.
+__device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool active, uint32_t cell, int data)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t id = active ? cell : (0x80000000u | (uint32_t)lane);
@@ -98,22 +110,18 @@ __device__ __forceinline__ void cell_add(const DevState &st, HotEntry *hot, bool
 
 	if (!active || (m & ((1u << lane) - 1u))) return;		// group leader = lowest lane
 
-	HotEntry *e = hot + ((cell * 2654435761u) >> (32 - HOT_BITS));
-	uint32_t tag = *((volatile uint32_t *)&e->tag);
+	const uint32_t h = (cell * 2654435761u) >> (32 - HotTable::BITS);
+	uint32_t tag = *((volatile uint32_t *)&hot.tag[h]);
 	bool hit = tag == cell + 1;
 
 	if (!hit && tag == 0 && cnt >= 2) {
-		tag = atomicCAS(&e->tag, 0u, cell + 1);
+		tag = atomicCAS(&hot.tag[h], 0u, cell + 1);
 		hit = tag == 0 || tag == cell + 1;
 	}
-	if (hit) { atomicAdd(&e->count, cnt); atomicAdd(&e->sum, (unsigned long long)sum); }
-	else cell_add_global(st, cell, cnt, (unsigned long long)sum);
-
-	if (track_max) {
-		// max_val_seen_: a (possibly stale) cached read first, the atomic only while the maximum still grows
-		long long *mp = (cell & CELL_TASK) ? &st.task_hist[((cell & ~CELL_TASK) | 15u)].sum : &st.hist_cur[cell | 15u].sum;
-		if ((long long)gmax > __ldca(mp)) atomicMax(mp, (long long)gmax);
+	if (hit) {
+		atomicAdd(&hot.count[h], cnt); atomicAdd(&hot.sum[h], (unsigned long long)sum); atomicMax(&hot.vmax[h], gmax);
 	}
+	else cell_add_global(st, cell, cnt, (unsigned long long)sum, gmax);
 }
 
 __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t rank)
@@ -130,14 +138,15 @@ __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t
 	}
 }
 
-__global__ void __launch_bounds__(256) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n, unsigned long long *__restrict__ keys)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n, unsigned long long *__restrict__ keys)
 {
-	__shared__ HotEntry hot[HOT_N];
+	__shared__ HotTable hot;
 	unsigned long long c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	const int lane = threadIdx.x & 31;
 
-	for (int i = threadIdx.x; i < HOT_N; i += blockDim.x) { hot[i].tag = 0; hot[i].count = 0; hot[i].sum = 0; }
+	for (int i = threadIdx.x; i < HotTable::N; i += blockDim.x) { hot.tag[i] = 0; hot.count[i] = 0; hot.sum[i] = 0; hot.vmax[i] = INT_MIN; }
 	__syncthreads();
 
 	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(256) ingest_kernel(DevState st, const gysk_eve
 		// up to three cell updates per event: RESP -> 1 histogram cell; TCP -> the service's conn cell; TASK -> 3 histogram cells
 		uint32_t cell0 = 0, cell1 = 0, cell2 = 0;
 		int d0 = 0, d1 = 0, d2 = 0;
-		bool a0 = false, a12 = false, max0 = false;
+		bool a0 = false, a12 = false;
 
 		if (valid) {
 			const uint4 a = __ldg(reinterpret_cast<const uint4 *>(ev + i));
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(256) ingest_kernel(DevState st, const gysk_eve
 				else if (is_resp) {
 					// GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data, gy_statistics.h:596-623
 					cell0 = (uint32_t)slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
-					d0 = (int)ms; a0 = true; max0 = true;
+					d0 = (int)ms; a0 = true;
 					key = ((unsigned long long)(uint32_t)slot << VALUE_BITS) | value;
 					c_resp++;
 				}
@@ -201,24 +210,24 @@ __global__ void __launch_bounds__(256) ingest_kernel(DevState st, const gysk_eve
 					cell0 = tb + (uint32_t)bucket_hash_1_3000(d0);
 					cell1 = tb + HIST_CELLS + (uint32_t)bucket_duration(d1);
 					cell2 = tb + 2 * HIST_CELLS + (uint32_t)bucket_duration(d2);
-					a0 = true; a12 = true; max0 = true;
+					a0 = true; a12 = true;
 					c_task++;
 				}
 			}
 			keys[i] = key;
 		}
 
-		cell_add(st, hot, a0, cell0, d0, max0);
+		cell_add(st, hot, a0, cell0, d0);
 		if (__any_sync(0xffffffffu, a12)) {
-			cell_add(st, hot, a12, cell1, d1, true);
-			cell_add(st, hot, a12, cell2, d2, true);
+			cell_add(st, hot, a12, cell1, d1);
+			cell_add(st, hot, a12, cell2, d2);
 		}
 	}
 
 	// retire: one RED pair per privatised cell
 	__syncthreads();
-	for (int i = threadIdx.x; i < HOT_N; i += blockDim.x) {
-		if (hot[i].tag && hot[i].count) cell_add_global(st, hot[i].tag - 1, hot[i].count, hot[i].sum);
+	for (int i = threadIdx.x; i < HotTable::N; i += blockDim.x) {
+		if (hot.tag[i] && hot.count[i]) cell_add_global(st, hot.tag[i] - 1, hot.count[i], hot.sum[i], hot.vmax[i]);
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
@@ -583,7 +592,7 @@ __global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, co
 // ---------------------------------------------------------------------------------------------------
 // 5-second window roll: last = cur; all += cur; cur = 0  (one thread per histogram cell)
 // ---------------------------------------------------------------------------------------------------
-__global__ void flush_kernel(DevState st, uint32_t nslots)
+__global__ void flush_kernel(DevState st, uint32_t nslots, HistCell *__restrict__ ring0, HistCell *__restrict__ ring1)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 
@@ -592,6 +601,16 @@ __global__ void flush_kernel(DevState st, uint32_t nslots)
 	const HistCell c = st.hist_cur[i];
 
 	st.hist_last[i] = c;
+	// rolling levels: the window is added to the current slot of each level (cleared by the host when its epoch changed).
+	// A cleared slot's max cell reads 0, which is below any recorded response time or equal to it: harmless for max().
+	if (cell == HIST_MAX_CELL) {
+		if (c.sum > ring0[i].sum) ring0[i].sum = c.sum;
+		if (c.sum > ring1[i].sum) ring1[i].sum = c.sum;
+	}
+	else {
+		ring0[i].count += c.count; ring0[i].sum += c.sum;
+		ring1[i].count += c.count; ring1[i].sum += c.sum;
+	}
 	if (cell == HIST_MAX_CELL) {
 		if (c.sum > st.hist_all[i].sum) st.hist_all[i].sum = c.sum;
 		st.hist_cur[i].count = 0; st.hist_cur[i].sum = LLONG_MIN;
@@ -612,7 +631,8 @@ __global__ void flush_kernel(DevState st, uint32_t nslots)
 // ---------------------------------------------------------------------------------------------------
 // read side: one warp per queried id
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gather_svcs_kernel(DevState st, const unsigned long long *__restrict__ ids, uint32_t n, SvcRaw *__restrict__ out)
+__global__ void __launch_bounds__(128) gather_svcs_kernel(DevState st, const unsigned long long *__restrict__ ids, uint32_t n, uint32_t max_svcs,
+		uint32_t live0, uint32_t live1, SvcRaw *__restrict__ out)
 {
 	__shared__ uint32_t hh[4][64];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -631,6 +651,19 @@ __global__ void __launch_bounds__(128) gather_svcs_kernel(DevState st, const uns
 		o.cur[lane] = st.hist_cur[(size_t)slot * HIST_CELLS + lane];
 		o.last[lane] = st.hist_last[(size_t)slot * HIST_CELLS + lane];
 		o.all[lane] = st.hist_all[(size_t)slot * HIST_CELLS + lane];
+		// rolling levels: sum of the slots still inside the level's span
+		for (int l = 0; l < NLEVELS; ++l) {
+			const uint32_t live = l ? live1 : live0;
+			HistCell a {0, 0};
+			if (lane == HIST_MAX_CELL) a.sum = LLONG_MIN;
+			for (int k = 0; k < NSLOTS; ++k) {
+				if (!((live >> k) & 1u)) continue;
+				const HistCell x = st.hist_ring[(((size_t)l * NSLOTS + k) * max_svcs + slot) * HIST_CELLS + lane];
+				if (lane == HIST_MAX_CELL) a.sum = max(a.sum, x.sum);
+				else { a.count += x.count; a.sum += x.sum; }
+			}
+			o.lvl[l][lane] = a;
+		}
 	}
 	if (lane == 0) {
 		o.conn_cur = st.conn_cur[slot]; o.conn_last = st.conn_last[slot];
@@ -713,9 +746,14 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+	// occupancy variant: 8 CTAs/SM (32 registers, a few spilled bytes) hides the id-table / HLL load latency best;
+	// GYSK_INGEST_CTAS=6 selects the spill-free 40-register build for A/B runs
+	static const int variant = []{ const char *v = getenv("GYSK_INGEST_CTAS"); return v ? atoi(v) : 8; }();
+	const int per_sm = variant == 6 ? 6 : 8;
 	const uint64_t want = (n + 255) / 256;
-	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * 8 ? want : (uint64_t)nsm * 8);
-	ingest_kernel<<<grid, 256, 0, s>>>(st, d_ev, n, d_keys);
+	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * per_sm ? want : (uint64_t)nsm * per_sm);
+	if (per_sm == 6) ingest_kernel<6><<<grid, 256, 0, s>>>(st, d_ev, n, d_keys);
+	else ingest_kernel<8><<<grid, 256, 0, s>>>(st, d_ev, n, d_keys);
 	return 1;
 }
 
@@ -767,17 +805,18 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, u
 	return launches + 4;
 }
 
-int launch_flush(const DevState &st, uint32_t nslots, cudaStream_t s)
+int launch_flush(const DevState &st, uint32_t nslots, HistCell *ring_plane0, HistCell *ring_plane1, cudaStream_t s)
 {
 	if (!nslots) return 0;
-	flush_kernel<<<div_up((uint64_t)nslots * HIST_CELLS, 256), 256, 0, s>>>(st, nslots);
+	flush_kernel<<<div_up((uint64_t)nslots * HIST_CELLS, 256), 256, 0, s>>>(st, nslots, ring_plane0, ring_plane1);
 	return 1;
 }
 
-int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, SvcRaw *d_out, cudaStream_t s)
+int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, uint32_t max_svcs, uint32_t live_mask0, uint32_t live_mask1,
+		SvcRaw *d_out, cudaStream_t s)
 {
 	if (!n) return 0;
-	gather_svcs_kernel<<<div_up(n, 4), 128, 0, s>>>(st, d_ids, n, d_out);
+	gather_svcs_kernel<<<div_up(n, 4), 128, 0, s>>>(st, d_ids, n, max_svcs, live_mask0, live_mask1, d_out);
 	return 1;
 }
 

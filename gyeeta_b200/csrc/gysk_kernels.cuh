@@ -13,6 +13,7 @@ struct DevState
 	IdTable			svc_tbl, task_tbl;
 	// per-service state, indexed by slot
 	HistCell		*hist_cur, *hist_last, *hist_all;	// [max_svcs][16]
+	HistCell		*hist_ring;				// [NLEVELS][NSLOTS][max_svcs][16] rolling 300-s / 5-day levels
 	unsigned long long	*conn_cur, *conn_last;			// packed {count:32, kbytes:32}
 	unsigned long long	*conn_all_cnt, *conn_all_kb;
 	uint8_t			*hll;					// [max_svcs][1 << hll_p]
@@ -48,6 +49,7 @@ struct SvcRaw
 	int32_t			found;
 	uint32_t		slot;
 	HistCell		cur[HIST_CELLS], last[HIST_CELLS], all[HIST_CELLS];
+	HistCell		lvl[2][HIST_CELLS];			// sums of the live slots of the rolling levels
 	unsigned long long	conn_cur, conn_last, conn_all_cnt, conn_all_kb;
 	uint32_t		hll_hist[64];
 	TdHead			td;
@@ -62,6 +64,8 @@ struct TaskRaw
 	HistCell		h[3][HIST_CELLS];
 };
 
+static constexpr int NLEVELS = 2;			// rolling levels beyond the 5-s window: 300 s, 432000 s (gy_statistics.h:1548)
+static constexpr int NSLOTS = 10;			// slots per level (gy_statistics.h:1105)
 static constexpr int SORT_TILE = 4096;		// keys per CTA tile in the radix passes
 static constexpr int VALUE_BITS = 30;		// RESP usec < 2^30 (msec <= 1e6 is enforced at ingest)
 
@@ -70,8 +74,9 @@ int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks,
 int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_t n, int is_task, cudaStream_t s);
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s);
 int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t max_svcs, cudaStream_t s);
-int launch_flush(const DevState &st, uint32_t max_svcs, cudaStream_t s);
-int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, SvcRaw *d_out, cudaStream_t s);
+int launch_flush(const DevState &st, uint32_t max_svcs, HistCell *ring_plane0, HistCell *ring_plane1, cudaStream_t s);
+int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, uint32_t max_svcs, uint32_t live_mask0, uint32_t live_mask1,
+		SvcRaw *d_out, cudaStream_t s);
 int launch_gather_tasks(const DevState &st, const unsigned long long *d_ids, uint32_t n, TaskRaw *d_out, cudaStream_t s);
 int launch_gather_hll(const DevState &st, unsigned long long id, uint8_t *d_out, int32_t *d_found, cudaStream_t s);
 int launch_query_flows(const DevState &st, const unsigned long long *d_keys, uint32_t n, int last_window, gysk_flow_est *d_out, cudaStream_t s);

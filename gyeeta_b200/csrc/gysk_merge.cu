@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(128) gather_logical_kernel(const int32_t *__re
 		HistCell a = l_last[(size_t)l * HIST_CELLS + lane], b = l_all[(size_t)l * HIST_CELLS + lane];
 		if (lane == HIST_MAX_CELL) { a.sum = l_hmax[2 * l]; b.sum = l_hmax[2 * l + 1]; }
 		o.last[lane] = a; o.all[lane] = b; o.cur[lane] = HistCell {0, 0};
+		o.lvl[0][lane] = HistCell {0, 0}; o.lvl[1][lane] = HistCell {0, 0};
 	}
 	if (lane == 0) {
 		o.conn_cur = 0;

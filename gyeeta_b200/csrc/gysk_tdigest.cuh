@@ -34,6 +34,7 @@ struct TdScratch
 	Centroid		merged[2 * TD_CAP];
 	unsigned long long	prefix[2 * TD_CAP + 1];
 	uint32_t		bounds[2 * TD_CAP + 1];
+	uint16_t		nxt[2 * TD_CAP];
 };
 
 
@@ -78,16 +79,24 @@ __device__ __forceinline__ uint32_t warp_merge_compress(TdScratch &S, const Cent
 	}
 	__syncwarp();
 
-	// greedy chain over the merged list (sequential, about delta steps): a cluster that starts after weight P takes items
-	// while the running total stays <= W q(k(P/W) + 1), and at least one item
-	uint32_t nout = 0;
-	if (lane == 0 && nm) {
+	// greedy chain over the merged list: a cluster that starts at item i (after weight P = prefix[i]) takes items while the
+	// running total stays <= W q(k(P/W) + 1), and at least one item. The successor nxt[i] of EVERY possible start is
+	// evaluated in parallel (8 per lane, the expensive double sqrt/div part); the chain itself is then a pointer walk.
+	if (nm) {
 		const unsigned long long W = S.prefix[nm];
+		for (uint32_t i = lane; i < nm; i += 32) {
+			const double wl = td_wlimit(S.prefix[i], W, P);
+			uint32_t e = i + 1;				// largest e in [i+1, nm] with prefix[e] <= wl
+			while (e < nm && (double)S.prefix[e + 1] <= wl) ++e;
+			S.nxt[i] = (uint16_t)e;
+		}
+	}
+	__syncwarp();
+	uint32_t nout = 0;
+	if (lane == 0) {
 		uint32_t cs = 0;
 		while (cs < nm) {
-			const double wl = td_wlimit(S.prefix[cs], W, P);
-			uint32_t e = cs + 1;				// largest e in [cs+1, nm] with prefix[e] <= wl: clusters of the
-			while (e < nm && (double)S.prefix[e + 1] <= wl) ++e;	// merged list hold ~2 items, a forward scan beats bisection
+			uint32_t e = S.nxt[cs];
 			if (nout == TD_CAP - 1) e = nm;			// the last slot absorbs whatever is left
 			S.bounds[nout++] = cs;
 			cs = e;

@@ -14,7 +14,7 @@ SERIAL_DTYPE = np.dtype([("count", "<u8"), ("sum", "<i8")])
 FLOW_EST_DTYPE = np.dtype([("flow_key", "<u8"), ("count", "<u4"), ("kbytes", "<u4")])
 
 EV_CONNECT, EV_ACCEPT, EV_CLOSE_CLI, EV_CLOSE_SER, EV_RESP, EV_TASK = 1, 2, 3, 4, 5, 6
-HIST_RESP_CUR, HIST_RESP_LAST, HIST_RESP_ALL, HIST_TASK_CPU_PCT, HIST_TASK_CPU_DELAY, HIST_TASK_BLKIO_DELAY = range(6)
+HIST_RESP_CUR, HIST_RESP_LAST, HIST_RESP_ALL, HIST_TASK_CPU_PCT, HIST_TASK_CPU_DELAY, HIST_TASK_BLKIO_DELAY, HIST_RESP_5MIN, HIST_RESP_5DAY = range(8)
 RAW_EVENT32, RAW_TCP_IPV4_EVENT, RAW_TCP_IPV4_RESP = 0, 1, 2
 NOTIFY_LISTENER_STATE, NOTIFY_TCP_CONN, NOTIFY_AGGR_TASK_STATE = 0x309, 0x30C, 0x310
 FLAG_AUTO_REGISTER = 1
@@ -31,12 +31,14 @@ class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("max_svcs", C.c_uint32), ("max_tasks", C.c_uint32),
                 ("cms_depth", C.c_uint32), ("cms_log2_width", C.c_uint32), ("hll_p", C.c_uint32),
                 ("td_compression", C.c_uint32), ("max_batch", C.c_uint32), ("flags", C.c_uint32), ("rank", C.c_uint32),
-                ("world", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("world", C.c_uint32), ("stage_batch", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class SvcSummary(C.Structure):
     _fields_ = [("glob_id", C.c_uint64), ("found", C.c_int32), ("nqrys_5s", C.c_uint32), ("total_resp_5sec", C.c_uint64),
                 ("p95_5s_resp_ms", C.c_int64), ("p99_5s_resp_ms", C.c_int64), ("p25_5s_resp_ms", C.c_int64),
+                ("p95_5min_resp_ms", C.c_int64), ("p99_5min_resp_ms", C.c_int64), ("nqrys_5min", C.c_uint64),
+                ("p95_5day_resp_ms", C.c_int64), ("nqrys_5day", C.c_uint64),
                 ("p95_all_resp_ms", C.c_int64), ("p99_all_resp_ms", C.c_int64), ("nqrys_all", C.c_uint64),
                 ("max_resp_ms", C.c_int64), ("nconns_5s", C.c_uint32), ("kbytes_5s", C.c_uint32), ("nconns_all", C.c_uint64),
                 ("kbytes_all", C.c_uint64), ("distinct_clients", C.c_double), ("td_p50_us", C.c_double),
@@ -129,13 +131,14 @@ class Engine:
     """One engine = one GPU. Mirrors the C ABI one to one."""
 
     def __init__(self, device=0, max_svcs=1 << 14, max_tasks=1 << 12, cms_depth=4, cms_log2_width=20, hll_p=12,
-                 td_compression=100, max_batch=1 << 20, auto_register=True, rank=0, world=1):
+                 td_compression=100, max_batch=1 << 20, auto_register=True, rank=0, world=1, stage_batch=0):
         self.L = load_library()
         cfg = Config()
         self.L.gysk_config_default(C.byref(cfg))
         cfg.device, cfg.max_svcs, cfg.max_tasks = device, max_svcs, max_tasks
         cfg.cms_depth, cfg.cms_log2_width, cfg.hll_p, cfg.td_compression = cms_depth, cms_log2_width, hll_p, td_compression
         cfg.max_batch = max_batch
+        cfg.stage_batch = stage_batch
         cfg.flags = FLAG_AUTO_REGISTER if auto_register else 0
         cfg.rank, cfg.world = rank, world
         self.cfg = cfg

@@ -105,6 +105,8 @@ enum {
 	GYSK_HIST_TASK_CPU_PCT	= 3,	/* task: MTASK_HIST::cpu_pct_histogram_		(HASH_1_3000, T=int)  server/gy_msocket.h:707 */
 	GYSK_HIST_TASK_CPU_DELAY= 4,	/* task: cpu_delay_histogram_			(DURATION_HASH, T=int) */
 	GYSK_HIST_TASK_BLKIO_DELAY = 5,	/* task: blkio_delay_histogram_			(DURATION_HASH, T=int) */
+	GYSK_HIST_RESP_5MIN	= 6,	/* service: 300-s level    (Level_5s_5min_5days_all, gy_statistics.h:1545-1551; 10 slots, :1105) */
+	GYSK_HIST_RESP_5DAY	= 7,	/* service: 432000-s level */
 };
 
 /* ---- raw record kinds for gysk_ingest_raw ---- */
@@ -134,10 +136,11 @@ typedef struct gysk_config
 	uint32_t	cms_log2_width;		/* columns = 1 << this (default 20) */
 	uint32_t	hll_p;			/* registers per service = 1 << p, 4..16 (default 12) */
 	uint32_t	td_compression;		/* t-digest delta (default 100 = public.tdigest(x, 100), gy_query_common.cc:1855) */
-	uint32_t	max_batch;		/* max events per device batch (default 1 << 24) */
+	uint32_t	max_batch;		/* max events per device batch = one ingest + sort + t-digest pass (default 1 << 22) */
 	uint32_t	flags;			/* GYSK_FLAG_* */
 	uint32_t	rank, world;		/* this engine owns events with host_idx % world == rank; world 0/1 = all */
-	uint32_t	reserved[4];
+	uint32_t	stage_batch;		/* events per host staging buffer / H2D chunk; 0 = min(max_batch, 1 << 22) */
+	uint32_t	reserved[3];
 } gysk_config;
 
 typedef struct gysk_engine gysk_engine;
@@ -152,6 +155,11 @@ typedef struct gysk_svc_summary
 	int64_t		p95_5s_resp_ms;		/* ::p95_5s_resp_ms_   = get_percentile(95) of the last window */
 	int64_t		p99_5s_resp_ms;
 	int64_t		p25_5s_resp_ms;		/* the three percentiles listener_stats_update reads, gy_socket_stat.h:459 */
+	int64_t		p95_5min_resp_ms;	/* ::p95_5min_resp_ms_ = get_percentile(95) of the 300-s level */
+	int64_t		p99_5min_resp_ms;
+	uint64_t	nqrys_5min;
+	int64_t		p95_5day_resp_ms;
+	uint64_t	nqrys_5day;
 	int64_t		p95_all_resp_ms;
 	int64_t		p99_all_resp_ms;
 	uint64_t	nqrys_all;

@@ -519,6 +519,7 @@ typedef struct svc_state
 {
 	uint64_t	id;
 	gyo_hist	cur, last, all;		/* RESP_TIME_HASH, T = int64 */
+	gyo_hist	ring[GYO_NLEVELS][GYO_NSLOTS];	/* 300 s and 432000 s levels, 10 slots each */
 	uint64_t	conn_cur, conn_last;	/* packed {count, kbytes} like a CMS cell */
 	uint64_t	conn_all_cnt, conn_all_kb;
 	uint8_t		*hll;
@@ -544,6 +545,8 @@ struct gyo_engine
 	task_state	*tasks;
 	uint64_t	*cms_cur, *cms_last;
 	uint64_t	n_in, n_drop, n_resp, n_tcp, n_task, n_foreign;
+	uint64_t	ring_epoch[GYO_NLEVELS][GYO_NSLOTS];
+	uint32_t	last_flush_tsec;
 	uint32_t	*touched;		/* slots with pending RESP samples in the batch being ingested */
 	uint32_t	ntouched;
 };
@@ -588,6 +591,7 @@ gyo_engine *gyo_create(uint32_t max_svcs, uint32_t max_tasks, uint32_t cms_depth
 	e->cms_cur = (uint64_t *)calloc((size_t)cms_depth << cms_log2_width, sizeof(uint64_t));
 	e->cms_last = (uint64_t *)calloc((size_t)cms_depth << cms_log2_width, sizeof(uint64_t));
 	e->touched = (uint32_t *)malloc(sizeof(uint32_t) * max_svcs);
+	memset(e->ring_epoch, 0xFF, sizeof(e->ring_epoch));
 	return e;
 }
 
@@ -612,6 +616,7 @@ static svc_state *get_svc(gyo_engine *e, uint64_t id, int insert)
 		gyo_hist_init(&s->cur, GYO_CLS_RESP_TIME, GYO_T_INT64);
 		gyo_hist_init(&s->last, GYO_CLS_RESP_TIME, GYO_T_INT64);
 		gyo_hist_init(&s->all, GYO_CLS_RESP_TIME, GYO_T_INT64);
+		for (int l = 0; l < GYO_NLEVELS; ++l) for (int k = 0; k < GYO_NSLOTS; ++k) gyo_hist_init(&s->ring[l][k], GYO_CLS_RESP_TIME, GYO_T_INT64);
 		s->hll = (uint8_t *)calloc(1u << e->hll_p, 1);
 		gyo_td_init(&s->td);
 	}
@@ -717,16 +722,34 @@ int gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n)
 	return 0;
 }
 
-/* 5-second roll: listener_stats_update gy_socket_stat.cc:3898 reads the window that just closed, then the
- * window restarts; the all-time level keeps accumulating (Level_5s_5min_5days_all, gy_statistics.h:1548) */
+/* 5-second roll: listener_stats_update gy_socket_stat.cc:3898 reads the window that just closed, then the window restarts.
+ * Levels follow Level_5s_5min_5days_all (gy_statistics.h:1545-1551) with 10 slots per level (:1105). folly's
+ * MultiLevelTimeSeries is un-vendored, so the slot rule is OUR definition: level with duration D has 10 slots of width D/10;
+ * a window closing at tsec is added to slot (tsec / width) % 10 after that slot is cleared if it still holds an older epoch;
+ * a level's answer = sum of the slots whose epoch lies within the last 10 epochs. The 5-s level is the window itself. */
+static const uint32_t g_level_width[GYO_NLEVELS] = { 30, 43200 };
+
 void gyo_flush(gyo_engine *e, uint32_t tsec)
 {
-	(void)tsec;
+	int clear[GYO_NLEVELS], slot[GYO_NLEVELS];
+
+	for (int l = 0; l < GYO_NLEVELS; ++l) {
+		uint64_t epoch = tsec / g_level_width[l];
+		slot[l] = (int)(epoch % GYO_NSLOTS);
+		clear[l] = e->ring_epoch[l][slot[l]] != epoch;
+		e->ring_epoch[l][slot[l]] = epoch;
+	}
+	e->last_flush_tsec = tsec;
+
 	for (uint32_t i = 0; i < e->smap.n; ++i) {
 		svc_state *s = &e->svcs[i];
 
 		s->last = s->cur;
 		gyo_hist_merge(&s->all, &s->cur);
+		for (int l = 0; l < GYO_NLEVELS; ++l) {
+			if (clear[l]) gyo_hist_init(&s->ring[l][slot[l]], GYO_CLS_RESP_TIME, GYO_T_INT64);
+			gyo_hist_merge(&s->ring[l][slot[l]], &s->cur);
+		}
 		gyo_hist_init(&s->cur, GYO_CLS_RESP_TIME, GYO_T_INT64);
 		s->conn_last = s->conn_cur;
 		s->conn_all_cnt += (uint32_t)s->conn_cur;
@@ -737,14 +760,33 @@ void gyo_flush(gyo_engine *e, uint32_t tsec)
 	memset(e->cms_cur, 0, sizeof(uint64_t) * ((size_t)e->depth << e->log2w));
 }
 
+static void level_sum(const gyo_engine *e, const svc_state *s, int l, gyo_hist *out)
+{
+	const uint64_t now_epoch = e->last_flush_tsec / g_level_width[l];
+
+	gyo_hist_init(out, GYO_CLS_RESP_TIME, GYO_T_INT64);
+	for (int k = 0; k < GYO_NSLOTS; ++k) {
+		const uint64_t ep = e->ring_epoch[l][k];
+		if (ep != UINT64_MAX && ep + GYO_NSLOTS > now_epoch && ep <= now_epoch) gyo_hist_merge(out, &s->ring[l][k]);
+	}
+}
+
 int gyo_export_hist(gyo_engine *e, uint64_t id, int which, gyo_serial *out15, uint64_t *total, int64_t *maxv)
 {
 	const gyo_hist *h = NULL;
+
+	gyo_hist lvl;
 
 	if (which <= 2) {
 		int slot = idmap_find(&e->smap, id, 0, 0);
 		if (slot < 0) return -2;
 		h = which == 0 ? &e->svcs[slot].cur : (which == 1 ? &e->svcs[slot].last : &e->svcs[slot].all);
+	}
+	else if (which == 6 || which == 7) {
+		int slot = idmap_find(&e->smap, id, 0, 0);
+		if (slot < 0) return -2;
+		level_sum(e, &e->svcs[slot], which - 6, &lvl);
+		h = &lvl;
 	}
 	else {
 		int slot = idmap_find(&e->tmap, id, 0, 0);

@@ -33,6 +33,8 @@ enum {
 enum { GYO_T_INT64 = 0, GYO_T_INT = 1, GYO_T_INT8 = 2 };
 
 #define GYO_MAX_BUCKETS		16
+#define GYO_NLEVELS		2	/* rolling levels beyond the 5-s window: 300 s and 432000 s */
+#define GYO_NSLOTS		10	/* slots per level, common/gy_statistics.h:1105 */
 
 typedef struct gyo_serial { uint64_t count; int64_t sum; } gyo_serial;	/* == HIST_SERIAL */
 

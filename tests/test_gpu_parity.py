@@ -250,3 +250,34 @@ def test_sharded_engines_merge_to_single_engine_integers():
         full = one.export_hist(int(id_), ge.HIST_RESP_CUR)
         got = [o for o in owners if o is not None]
         assert sum(int(o[1]) for o in got) == full[1]
+
+
+def test_rolling_levels_300s_and_5days():
+    """multi-level windows (Level_5s_5min_5days_all, gy_statistics.h:1545-1551; 10 slots per level :1105): the 300-s and
+    432000-s levels after a sequence of 5-s flushes with time jumps (the scenario of test/test_timeseries_hist.cc:29-72,
+    which jumps +3600 s) — bit-exact against the oracle's slot rule, and expiry actually drops old windows."""
+    rng = np.random.default_rng(77)
+    eng, orc = make_pair(max_svcs=128, max_tasks=8, max_batch=1 << 14, cms_log2_width=10)
+    times = [5, 10, 15, 35, 65, 300, 305, 310, 3905, 3910, 50_000, 50_005, 500_000, 500_005]
+    ids = None
+    for t in times:
+        ev = synth.gen_mixed(rng, 8000, 40, ntask=4, nhosts=4, nclients=500)
+        ev["tsec"] = t
+        ids = np.unique(ev["svc_id"][ev["type"] == ge.EV_RESP])[:25] if ids is None else ids
+        feed_both(eng, orc, ev, 1 << 14)
+        eng.flush(t); orc.flush(t)
+        for id_ in ids[:10]:
+            for which in (ge.HIST_RESP_LAST, ge.HIST_RESP_5MIN, ge.HIST_RESP_5DAY, ge.HIST_RESP_ALL):
+                assert_hist_equal(eng, orc, int(id_), which)
+    # after the jump to t = 500 005 the 300-s level only holds the last two windows, the 5-day level (span 432 000 s) has
+    # dropped everything recorded before t = 68 005 and "all" still has everything
+    sm = eng.query_svcs(ids[:10])
+    for s_, id_ in zip(sm, ids[:10]):
+        h5m = orc.export_hist(int(id_), 6); h5d = orc.export_hist(int(id_), 7); hall = orc.export_hist(int(id_), 2)
+        assert s_["nqrys_5min"] == h5m[1] and s_["nqrys_5day"] == h5d[1] and s_["nqrys_all"] == hall[1]
+        assert s_["nqrys_5min"] <= s_["nqrys_5day"] < s_["nqrys_all"]
+        pc = np.zeros(1, dtype=np.int64)
+        p95 = np.array([95], dtype=np.float32)
+        ser = np.zeros(15, dtype=ge.SERIAL_DTYPE); ser[:] = h5m[0]
+        eng.L.gysk_hist_percentiles(0, 0, ser.ctypes.data_as(C.c_void_p), h5m[1], p95.ctypes.data_as(C.c_void_p), 1, pc.ctypes.data_as(C.c_void_p))
+        assert s_["p95_5min_resp_ms"] == pc[0]
