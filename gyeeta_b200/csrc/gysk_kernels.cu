@@ -138,96 +138,171 @@ __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t
 	}
 }
 
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n, unsigned long long *__restrict__ keys)
-{
-	__shared__ HotTable hot;
-	unsigned long long c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	const int lane = threadIdx.x & 31;
+// The kernel runs as a persistent tile pipeline. A CTA takes a tile of INGEST_TILE events and
+//   phase 1 (one event per thread and round, fully converged): 2 x 128-bit load, shard filter, id -> slot lookup, then the
+//           decoded record {slot, value, flow_key} goes to shared memory and its index to the queue of its kind
+//           (RESP / TCP / TASK; ballot + one shared-memory atomic per warp and kind);
+//   phase 2 (converged per kind): every warp strides over one queue at a time, so the RESP histogram code, the count-min
+//           rows (one (event, row) pair per lane), the HLL updates and the three task histograms (one (event, histogram)
+//           pair per lane) each run with all lanes doing the same thing instead of serialising 70/20/10-divergent branches.
+// RESP sort keys are written compacted (one global cursor bump per tile), so the radix sort never sees a non-RESP slot.
+static constexpr int INGEST_THREADS = 256;
+static constexpr int INGEST_EPT = 4;
+static constexpr int INGEST_TILE = INGEST_THREADS * INGEST_EPT;
 
-	for (int i = threadIdx.x; i < HotTable::N; i += blockDim.x) { hot.tag[i] = 0; hot.count[i] = 0; hot.sum[i] = 0; hot.vmax[i] = INT_MIN; }
+struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
+
+struct IngestShared
+{
+	HotTable	hot;
+	IngestRec	rec[INGEST_TILE];
+	uint16_t	q_resp[INGEST_TILE], q_tcp[INGEST_TILE], q_task[INGEST_TILE];
+	uint32_t	n_resp, n_tcp, n_task;
+	unsigned long long key_base;
+};
+
+__device__ __forceinline__ void queue_push(bool pred, uint16_t *q, uint32_t *qn, uint16_t item)
+{
+	const uint32_t m = __ballot_sync(0xffffffffu, pred);
+	if (!m) return;
+	const int lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == __ffs(m) - 1) base = atomicAdd(qn, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+	if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = item;
+}
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
+		unsigned long long *__restrict__ keys)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	IngestShared &S = *reinterpret_cast<IngestShared *>(smem_raw);
+	unsigned long long c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint64_t ntiles = (n + INGEST_TILE - 1) / INGEST_TILE;
+
+	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
+	if (threadIdx.x == 0) { S.n_resp = 0; S.n_tcp = 0; S.n_task = 0; }
 	__syncthreads();
 
-	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
-		const uint64_t i = base + lane;
-		const bool valid = i < n;
-		unsigned long long key = KEY_SENTINEL;
-		// up to three cell updates per event: RESP -> 1 histogram cell; TCP -> the service's conn cell; TASK -> 3 histogram cells
-		uint32_t cell0 = 0, cell1 = 0, cell2 = 0;
-		int d0 = 0, d1 = 0, d2 = 0;
-		bool a0 = false, a12 = false;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const uint64_t tbase = tile * INGEST_TILE;
 
-		if (valid) {
-			const uint4 a = __ldg(reinterpret_cast<const uint4 *>(ev + i));
-			const uint4 b = __ldg(reinterpret_cast<const uint4 *>(ev + i) + 1);
-			const unsigned long long svc_id = ((unsigned long long)a.y << 32) | a.x;
-			const unsigned long long flow_key = ((unsigned long long)a.w << 32) | a.z;
-			const uint32_t value = b.x, host_idx = b.y;
-			const uint32_t type = b.w & 0xFFFFu;
-
-			if (st.world > 1 && (host_idx % st.world) != st.rank) {
-				c_foreign++;
+		// ---------------- phase 1: decode + lookup + enqueue ----------------
+		uint4 ra[INGEST_EPT], rb[INGEST_EPT];
+#pragma unroll
+		for (int k = 0; k < INGEST_EPT; ++k) {
+			const uint64_t i = tbase + (uint64_t)k * INGEST_THREADS + threadIdx.x;
+			if (i < n) {
+				ra[k] = __ldg(reinterpret_cast<const uint4 *>(ev + i));
+				rb[k] = __ldg(reinterpret_cast<const uint4 *>(ev + i) + 1);
 			}
-			else {
+			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }	// type 0xFFFF: padding, not counted
+		}
+#pragma unroll
+		for (int k = 0; k < INGEST_EPT; ++k) {
+			const unsigned long long svc_id = ((unsigned long long)ra[k].y << 32) | ra[k].x;
+			const unsigned long long flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
+			const uint32_t value = rb[k].x, host_idx = rb[k].y;
+			const uint32_t type = rb[k].w & 0xFFFFu;
+			const bool pad = tbase + (uint64_t)k * INGEST_THREADS + threadIdx.x >= n;
+			const bool is_resp = type == GYSK_EV_RESP, is_task = type == GYSK_EV_TASK;
+			const bool is_tcp = type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER;
+			// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
+			// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
+			const uint32_t ms = value / 1000u;
+			int slot = -1;
+			bool mine = !pad;
+
+			if (mine && st.world > 1 && (host_idx % st.world) != st.rank) { c_foreign++; mine = false; }
+			if (mine) {
 				c_in++;
-				const bool is_resp = type == GYSK_EV_RESP, is_task = type == GYSK_EV_TASK;
-				const bool is_tcp = type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER;
-				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
-				// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-				const uint32_t ms = value / 1000u;
-				int slot = -1;
 				// one id lookup for all three event kinds (services and tasks live in separate tables)
 				if (svc_id != 0 && (is_tcp || is_task || (is_resp && ms <= 1000000u)))
 					slot = table_lookup(is_task ? st.task_tbl : st.svc_tbl, svc_id, st.auto_register);
-
-				if (slot < 0) {
-					c_drop++;
-				}
-				else if (is_resp) {
-					// GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data, gy_statistics.h:596-623
-					cell0 = (uint32_t)slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
-					d0 = (int)ms; a0 = true;
-					key = ((unsigned long long)(uint32_t)slot << VALUE_BITS) | value;
-					c_resp++;
-				}
-				else if (is_tcp) {
-					const unsigned long long inc = cms_increment(value);
-					for (uint32_t r = 0; r < st.cms_depth; ++r) {
-						red_add_u64(st.cms_cur + ((size_t)r << st.cms_log2w) + cms_index(flow_key, r, st.cms_wmask), inc);
-					}
-					uint32_t idx, rank;
-					hll_idx_rank(flow_key, st.hll_p, idx, rank);
-					hll_update(st.hll + ((size_t)slot << st.hll_p), idx, rank);
-					cell0 = (uint32_t)slot * HIST_CELLS + HIST_MAX_CELL;		// exact per-service {count, kbytes} cell
-					d0 = (int)(value >> 10); a0 = true;
-					c_tcp++;
-				}
-				else {
-					// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
-					const uint32_t tb = CELL_TASK | ((uint32_t)slot * 3u * HIST_CELLS);
-					d0 = (int)value; d1 = (int)(uint32_t)flow_key; d2 = (int)(uint32_t)(flow_key >> 32);
-					cell0 = tb + (uint32_t)bucket_hash_1_3000(d0);
-					cell1 = tb + HIST_CELLS + (uint32_t)bucket_duration(d1);
-					cell2 = tb + 2 * HIST_CELLS + (uint32_t)bucket_duration(d2);
-					a0 = true; a12 = true;
-					c_task++;
-				}
+				if (slot < 0) c_drop++;
+				else if (is_resp) c_resp++;
+				else if (is_tcp) c_tcp++;
+				else c_task++;
 			}
-			keys[i] = key;
+			const uint16_t pos = (uint16_t)(k * INGEST_THREADS + threadIdx.x);
+			if (slot >= 0) { IngestRec r; r.slot = (uint32_t)slot; r.value = value; r.flow_key = flow_key; S.rec[pos] = r; }
+			queue_push(slot >= 0 && is_resp, S.q_resp, &S.n_resp, pos);
+			queue_push(slot >= 0 && is_tcp, S.q_tcp, &S.n_tcp, pos);
+			queue_push(slot >= 0 && is_task, S.q_task, &S.n_task, pos);
 		}
+		__syncthreads();
+		const uint32_t n_resp = S.n_resp, n_tcp = S.n_tcp, n_task = S.n_task;
+		if (threadIdx.x == 0) S.key_base = n_resp ? atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)n_resp) : 0ull;
+		__syncthreads();
 
-		cell_add(st, hot, a0, cell0, d0);
-		if (__any_sync(0xffffffffu, a12)) {
-			cell_add(st, hot, a12, cell1, d1);
-			cell_add(st, hot, a12, cell2, d2);
+		// ---------------- phase 2a: RESP — GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data, gy_statistics.h:596-623 ----------------
+		{
+			const unsigned long long kb = S.key_base;
+			for (uint32_t base = wid * 32; base < n_resp; base += INGEST_THREADS) {
+				const uint32_t q = base + lane;
+				const bool act = q < n_resp;
+				uint32_t cell = 0; int ms = 0;
+				if (act) {
+					const IngestRec r = S.rec[S.q_resp[q]];
+					ms = (int)(r.value / 1000u);
+					cell = r.slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
+					keys[kb + q] = ((unsigned long long)r.slot << VALUE_BITS) | r.value;
+				}
+				cell_add(st, S.hot, act, cell, ms);
+			}
 		}
+		// ---------------- phase 2b: TCP — count-min rows, one (event, row) pair per lane ----------------
+		{
+			const uint32_t npairs = n_tcp * st.cms_depth;
+			for (uint32_t p = threadIdx.x; p < npairs; p += INGEST_THREADS) {
+				const uint32_t e = p / st.cms_depth, row = p - e * st.cms_depth;
+				const IngestRec r = S.rec[S.q_tcp[e]];
+				red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index(r.flow_key, row, st.cms_wmask), cms_increment(r.value));
+			}
+			// HLL register + the service's exact {count, kbytes} cell
+			for (uint32_t base = wid * 32; base < n_tcp; base += INGEST_THREADS) {
+				const uint32_t q = base + lane;
+				const bool act = q < n_tcp;
+				uint32_t cell = 0; int kb = 0;
+				if (act) {
+					const IngestRec r = S.rec[S.q_tcp[q]];
+					uint32_t idx, rank;
+					hll_idx_rank(r.flow_key, st.hll_p, idx, rank);
+					hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
+					cell = r.slot * HIST_CELLS + HIST_MAX_CELL;
+					kb = (int)(r.value >> 10);
+				}
+				cell_add(st, S.hot, act, cell, kb);
+			}
+		}
+		// ---------------- phase 2c: TASK — MAGGR_TASK::set_local_task_state, one (event, histogram) pair per lane ----------------
+		{
+			const uint32_t ntrip = n_task * 3u;
+			for (uint32_t base = wid * 32; base < ntrip; base += INGEST_THREADS) {
+				const uint32_t p = base + lane;
+				const bool act = p < ntrip;
+				uint32_t cell = 0; int d = 0;
+				if (act) {
+					const uint32_t e = p / 3u, h = p - e * 3u;
+					const IngestRec r = S.rec[S.q_task[e]];
+					// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
+					d = h == 0 ? (int)r.value : (h == 1 ? (int)(uint32_t)r.flow_key : (int)(uint32_t)(r.flow_key >> 32));
+					const uint32_t b = h == 0 ? (uint32_t)bucket_hash_1_3000(d) : (uint32_t)bucket_duration(d);
+					cell = CELL_TASK | (r.slot * 3u * HIST_CELLS + h * HIST_CELLS + b);
+				}
+				cell_add(st, S.hot, act, cell, d);
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) { S.n_resp = 0; S.n_tcp = 0; S.n_task = 0; }
+		__syncthreads();
 	}
 
-	// retire: one RED pair per privatised cell
-	__syncthreads();
-	for (int i = threadIdx.x; i < HotTable::N; i += blockDim.x) {
-		if (hot.tag[i] && hot.count[i]) cell_add_global(st, hot.tag[i] - 1, hot.count[i], hot.sum[i], hot.vmax[i]);
+	// retire: one RED group per privatised cell
+	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) {
+		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i]);
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
@@ -746,14 +821,19 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-	// occupancy variant: 8 CTAs/SM (32 registers, a few spilled bytes) hides the id-table / HLL load latency best;
-	// GYSK_INGEST_CTAS=6 selects the spill-free 40-register build for A/B runs
-	static const int variant = []{ const char *v = getenv("GYSK_INGEST_CTAS"); return v ? atoi(v) : 8; }();
-	const int per_sm = variant == 6 ? 6 : 8;
-	const uint64_t want = (n + 255) / 256;
+	static const int per_sm = []{ const char *v = getenv("GYSK_INGEST_CTAS"); const int c = v ? atoi(v) : 4; return c >= 1 && c <= 8 ? c : 4; }();
+	static bool attr_set = false;
+	const size_t smem = sizeof(IngestShared);
+	if (!attr_set) {
+		cudaFuncSetAttribute(ingest_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaFuncSetAttribute(ingest_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		attr_set = true;
+	}
+	const uint64_t want = (n + INGEST_TILE - 1) / INGEST_TILE;
 	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * per_sm ? want : (uint64_t)nsm * per_sm);
-	if (per_sm == 6) ingest_kernel<6><<<grid, 256, 0, s>>>(st, d_ev, n, d_keys);
-	else ingest_kernel<8><<<grid, 256, 0, s>>>(st, d_ev, n, d_keys);
+	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, sizeof(unsigned long long), s);	// the key cursor of this batch
+	if (per_sm >= 5) ingest_kernel<5><<<grid, INGEST_THREADS, smem, s>>>(st, d_ev, n, d_keys);
+	else ingest_kernel<4><<<grid, INGEST_THREADS, smem, s>>>(st, d_ev, n, d_keys);
 	return 1;
 }
 
@@ -786,9 +866,9 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, u
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
 
 	for (int shift = 0, pass = 0; shift < total_bits; shift += 8, ++pass) {
-		const unsigned long long *dn = pass ? d_nkeys : nullptr;
+		const unsigned long long *dn = d_nkeys;		// ingest left the number of (compacted) RESP keys there
 		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(src, n, dn, shift, tmp.tile_hist, ntiles);
-		launches += 1 + launch_exclusive_scan(tmp.tile_hist, RADIX * ntiles, tmp.scan_tmp, pass ? nullptr : d_nkeys, s);
+		launches += 1 + launch_exclusive_scan(tmp.tile_hist, RADIX * ntiles, tmp.scan_tmp, nullptr, s);
 		rs_scatter_kernel<<<ntiles, RS_THREADS, 0, s>>>(src, dst, n, dn, shift, tmp.tile_hist, ntiles);
 		launches++;
 		which ^= 1;
