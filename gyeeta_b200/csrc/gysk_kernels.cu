@@ -157,7 +157,7 @@ struct IngestShared
 	HotTable	hot;
 	IngestRec	rec[INGEST_TILE];
 	uint16_t	q_resp[INGEST_TILE], q_tcp[INGEST_TILE], q_task[INGEST_TILE];
-	uint32_t	n_resp, n_tcp, n_task;
+	uint32_t	qn[2][4];		// per tile parity: n_resp, n_tcp, n_task (double-buffered: no barrier to reset them)
 	unsigned long long key_base;
 };
 
@@ -183,11 +183,13 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	const uint64_t ntiles = (n + INGEST_TILE - 1) / INGEST_TILE;
 
 	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
-	if (threadIdx.x == 0) { S.n_resp = 0; S.n_tcp = 0; S.n_task = 0; }
+	if (threadIdx.x < 8) (&S.qn[0][0])[threadIdx.x] = 0;
 	__syncthreads();
 
-	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+	int par = 0;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1) {
 		const uint64_t tbase = tile * INGEST_TILE;
+		uint32_t *qn = S.qn[par];
 
 		// ---------------- phase 1: decode + lookup + enqueue ----------------
 		uint4 ra[INGEST_EPT], rb[INGEST_EPT];
@@ -195,8 +197,8 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 		for (int k = 0; k < INGEST_EPT; ++k) {
 			const uint64_t i = tbase + (uint64_t)k * INGEST_THREADS + threadIdx.x;
 			if (i < n) {
-				ra[k] = __ldg(reinterpret_cast<const uint4 *>(ev + i));
-				rb[k] = __ldg(reinterpret_cast<const uint4 *>(ev + i) + 1);
+				ra[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i));		// streamed once: evict-first, keep L2 for
+				rb[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i) + 1);	// the id table / histogram / count-min lines
 			}
 			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }	// type 0xFFFF: padding, not counted
 		}
@@ -228,31 +230,18 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			}
 			const uint16_t pos = (uint16_t)(k * INGEST_THREADS + threadIdx.x);
 			if (slot >= 0) { IngestRec r; r.slot = (uint32_t)slot; r.value = value; r.flow_key = flow_key; S.rec[pos] = r; }
-			queue_push(slot >= 0 && is_resp, S.q_resp, &S.n_resp, pos);
-			queue_push(slot >= 0 && is_tcp, S.q_tcp, &S.n_tcp, pos);
-			queue_push(slot >= 0 && is_task, S.q_task, &S.n_task, pos);
+			queue_push(slot >= 0 && is_resp, S.q_resp, &qn[0], pos);
+			queue_push(slot >= 0 && is_tcp, S.q_tcp, &qn[1], pos);
+			queue_push(slot >= 0 && is_task, S.q_task, &qn[2], pos);
 		}
 		__syncthreads();
-		const uint32_t n_resp = S.n_resp, n_tcp = S.n_tcp, n_task = S.n_task;
-		if (threadIdx.x == 0) S.key_base = n_resp ? atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)n_resp) : 0ull;
-		__syncthreads();
+		const uint32_t n_resp = qn[0], n_tcp = qn[1], n_task = qn[2];
+		// thread 0 bumps the global key cursor now; its round trip to L2 hides behind the TCP and TASK phases
+		if (threadIdx.x == 0) {
+			S.qn[par ^ 1][0] = 0; S.qn[par ^ 1][1] = 0; S.qn[par ^ 1][2] = 0;
+			S.key_base = n_resp ? atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)n_resp) : 0ull;
+		}
 
-		// ---------------- phase 2a: RESP — GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data, gy_statistics.h:596-623 ----------------
-		{
-			const unsigned long long kb = S.key_base;
-			for (uint32_t base = wid * 32; base < n_resp; base += INGEST_THREADS) {
-				const uint32_t q = base + lane;
-				const bool act = q < n_resp;
-				uint32_t cell = 0; int ms = 0;
-				if (act) {
-					const IngestRec r = S.rec[S.q_resp[q]];
-					ms = (int)(r.value / 1000u);
-					cell = r.slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
-					keys[kb + q] = ((unsigned long long)r.slot << VALUE_BITS) | r.value;
-				}
-				cell_add(st, S.hot, act, cell, ms);
-			}
-		}
 		// ---------------- phase 2b: TCP — count-min rows, one (event, row) pair per lane ----------------
 		{
 			const uint32_t npairs = n_tcp * st.cms_depth;
@@ -295,9 +284,24 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				cell_add(st, S.hot, act, cell, d);
 			}
 		}
-		__syncthreads();
-		if (threadIdx.x == 0) { S.n_resp = 0; S.n_tcp = 0; S.n_task = 0; }
-		__syncthreads();
+		__syncthreads();			// key_base is visible
+		// ---------------- phase 2d: RESP — GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data, gy_statistics.h:596-623 ----------------
+		{
+			const unsigned long long kb = S.key_base;
+			for (uint32_t base = wid * 32; base < n_resp; base += INGEST_THREADS) {
+				const uint32_t q = base + lane;
+				const bool act = q < n_resp;
+				uint32_t cell = 0; int ms = 0;
+				if (act) {
+					const IngestRec r = S.rec[S.q_resp[q]];
+					ms = (int)(r.value / 1000u);
+					cell = r.slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
+					__stcs(keys + kb + q, ((unsigned long long)r.slot << VALUE_BITS) | r.value);
+				}
+				cell_add(st, S.hot, act, cell, ms);
+			}
+		}
+		__syncthreads();			// rec / queues may be overwritten by the next tile
 	}
 
 	// retire: one RED group per privatised cell
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 // ---------------------------------------------------------------------------------------------------
 // stable LSD radix sort, 8-bit digits, tile = SORT_TILE keys per CTA of 256 threads
 // ---------------------------------------------------------------------------------------------------
-static constexpr int RS_THREADS = 256;
+static constexpr int RS_THREADS = 512;
 static constexpr int RS_WARPS = RS_THREADS / 32;
 static constexpr int RS_ROUNDS = SORT_TILE / RS_THREADS;	// 16 keys per thread
 static constexpr int RADIX = 256;
@@ -341,11 +345,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long
 	const uint64_t n = d_n ? *d_n : n_host;
 	const uint32_t tile = blockIdx.x;
 
-	hist[threadIdx.x] = 0;
+	if (threadIdx.x < RADIX) hist[threadIdx.x] = 0;
 	__syncthreads();
 
 	const uint64_t base = (uint64_t)tile * SORT_TILE;
-#pragma unroll 4
+#pragma unroll
 	for (int r = 0; r < RS_ROUNDS; ++r) {
 		const uint64_t i = base + (uint64_t)r * RS_THREADS + threadIdx.x;
 		if (i < n) {
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long
 		}
 	}
 	__syncthreads();
-	tile_hist[(size_t)threadIdx.x * ntiles + tile] = hist[threadIdx.x];
+	if (threadIdx.x < RADIX) tile_hist[(size_t)threadIdx.x * ntiles + tile] = hist[threadIdx.x];
 }
 
 // exclusive scan of a u32 array of length len: reduce / scan block sums / apply
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
 	__syncthreads();
 
 	unsigned long long k[RS_ROUNDS];
-	uint32_t grp[RS_ROUNDS];
+	uint32_t rank[RS_ROUNDS];
 	const uint64_t wbase = (uint64_t)tile * SORT_TILE + (uint64_t)wid * (RS_ROUNDS * 32);
 
 #pragma unroll
@@ -461,20 +465,25 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
 		k[r] = i < n ? in[i] : KEY_SENTINEL;
 	}
 
-	// phase A: per-warp digit counts
+	// phase A: rank of every key among the keys of its digit inside this warp's chunk (rounds in order, lanes in order),
+	// leaving the per-warp digit counts in whist. One match.any per round; the group leader bumps the warp counter and
+	// hands the previous value to its group.
 #pragma unroll
 	for (int r = 0; r < RS_ROUNDS; ++r) {
 		const bool valid = k[r] != KEY_SENTINEL;
 		const uint32_t d = valid ? ((uint32_t)(k[r] >> shift) & 0xFFu) : (0x100u + lane);
 		const uint32_t m = __match_any_sync(0xffffffffu, d);
-		grp[r] = m;
-		if (valid && (m & lt_mask) == 0) whist[wid][d] += __popc(m);
+		const int leader = __ffs(m) - 1;
+		uint32_t old = 0;
+		if (valid && lane == leader) { old = whist[wid][d]; whist[wid][d] = old + __popc(m); }
 		__syncwarp();
+		old = __shfl_sync(0xffffffffu, old, leader);
+		rank[r] = old + __popc(m & lt_mask);
 	}
 	__syncthreads();
 
 	// exclusive prefix over warps per digit, seeded with this tile's global offset for the digit
-	{
+	if (threadIdx.x < RADIX) {
 		const uint32_t d = threadIdx.x;
 		uint32_t run = tile_offs[(size_t)d * ntiles + tile];
 #pragma unroll
@@ -482,19 +491,10 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
 	}
 	__syncthreads();
 
-	// phase B: positions
+	// phase B: position = warp base of the digit + rank
 #pragma unroll
 	for (int r = 0; r < RS_ROUNDS; ++r) {
-		const bool valid = k[r] != KEY_SENTINEL;
-		if (valid) {
-			const uint32_t d = (uint32_t)(k[r] >> shift) & 0xFFu;
-			const uint32_t m = grp[r];
-			const uint32_t pos = whist[wid][d] + __popc(m & lt_mask);
-			out[pos] = k[r];
-		}
-		__syncwarp();
-		if (valid && (grp[r] & lt_mask) == 0) whist[wid][(uint32_t)(k[r] >> shift) & 0xFFu] += __popc(grp[r]);
-		__syncwarp();
+		if (k[r] != KEY_SENTINEL) out[whist[wid][(uint32_t)(k[r] >> shift) & 0xFFu] + rank[r]] = k[r];
 	}
 }
 
@@ -550,7 +550,7 @@ __global__ void td_plan_kernel(TdParams P, const uint32_t *__restrict__ seg_star
 			s = (uint32_t)ee;
 		}
 		bounds[nnew] = n;
-		plan_n[slot] = nnew;
+		plan_n[slot] = nnew | (nnew == n ? 0x80000000u : 0u);	// flag: every cluster is a single sample, cluster id == rank
 	}
 }
 
@@ -585,14 +585,17 @@ __global__ void __launch_bounds__(256) td_sums_kernel(const unsigned long long *
 			bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
 			nn = plan_n[slot];
 		}
-		if (lane == 0 && valid) {
+		const bool single = (nn & 0x80000000u) != 0;
+		nn &= 0x7FFFFFFFu;
+		if (lane == 0 && valid && !single) {
 			uint32_t lo = 0, hi = nn - 1;			// largest j with bounds[j] <= r
 			while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (bounds[mid] <= r) lo = mid; else hi = mid - 1; }
 			j0 = lo; lo0 = bounds[lo]; hi0 = bounds[lo + 1];
 		}
 		j0 = __shfl_sync(0xffffffffu, j0, 0); lo0 = __shfl_sync(0xffffffffu, lo0, 0); hi0 = __shfl_sync(0xffffffffu, hi0, 0);
 		if (valid) {
-			if (slot == slot0 && r >= lo0 && r < hi0) j = j0;
+			if (single) j = r;
+			else if (slot == slot0 && r >= lo0 && r < hi0) j = j0;
 			else {
 				uint32_t lo = 0, hi = nn - 1;
 				while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (bounds[mid] <= r) lo = mid; else hi = mid - 1; }
@@ -638,7 +641,7 @@ __global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, co
 		const uint32_t slot = touched[t];
 		const uint32_t s0 = seg_start[slot];
 		const uint32_t n = seg_end[slot] - s0;
-		const uint32_t nnew = plan_n[slot];
+		const uint32_t nnew = plan_n[slot] & 0x7FFFFFFFu;
 		const uint32_t *bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
 		const unsigned long long *sums = newsum + (size_t)slot * TD_CAP;
 
