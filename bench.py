@@ -44,7 +44,7 @@ BYTES_EVENT = BYTES_INGEST + BYTES_TDIGEST                            # 101.0 B 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gysketch", choices=["gysketch", "reference"])
     ap.add_argument("--events", type=int, default=100_000_000, help="events per rank per step")
@@ -56,6 +56,13 @@ def parse():
     return ap.parse_args()
 
 
+def rank_service_ids(rank):
+    from gyeeta_b200 import synth
+    ids = synth.splitmix64(np.arange(1, NSVC + 1, dtype=np.uint64) + np.uint64(rank * NSVC))
+    ids[ids == 0] = 1
+    return ids
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # synthetic stream on the GPU (same formulas as gyeeta_b200/synth.py::gen_mixed)
 # ---------------------------------------------------------------------------------------------------------------
@@ -63,8 +70,9 @@ def gen_events_gpu(torch, n, seed, rank, world, dev):
     from gyeeta_b200 import synth
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    svc_ids = torch.from_numpy(synth.service_ids(NSVC).view(np.int64)).to(dev)
-    task_ids = torch.from_numpy(synth.task_ids(NTASK).view(np.int64)).to(dev)
+    # a service id is unique per host (CityHash of host + netns + ip + port in the reference): every rank owns its own ids
+    svc_ids = torch.from_numpy(rank_service_ids(rank).view(np.int64)).to(dev)
+    task_ids = torch.from_numpy(synth.splitmix64(np.arange(1, NTASK + 1, dtype=np.uint64) + np.uint64((1 << 40) + rank * NTASK)).view(np.int64)).to(dev)
     cdf_s = torch.from_numpy(synth.zipf_cdf(NSVC, ZIPF_S)).to(dev)
     cdf_t = torch.from_numpy(synth.zipf_cdf(NTASK, ZIPF_S)).to(dev)
     out = torch.empty((n, 4), dtype=torch.int64, device=dev)
@@ -118,7 +126,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
@@ -152,6 +160,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic_per_event():
+    """DRAM bytes per event of each kernel group from the committed `ncu --set full` captures (profiles/ncu_traffic.json)"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -168,7 +185,11 @@ def measured_peak_gbs():
 def cpu_port_rate(ev_np, nthreads, repeat=1):
     from oracle import pyoracle as po
     L = po.lib()
-    shards = [np.ascontiguousarray(ev_np[(ev_np["host_idx"] // 1) % nthreads == t]) for t in range(nthreads)]
+    # pre-shard by host (mirrors l1_thr_num % maxthr, gy_mconnhdlr.cc:16252): one stable sort, then split
+    owner = (ev_np["host_idx"] % nthreads).astype(np.int32)
+    order = np.argsort(owner, kind="stable")
+    cuts = np.searchsorted(owner[order], np.arange(1, nthreads))
+    shards = [np.ascontiguousarray(a) for a in np.split(ev_np[order], cuts)]
     engines = [po.OracleEngine(max_svcs=NSVC + 16, max_tasks=NTASK + 16) for _ in range(nthreads)]
     eh = (C.c_void_p * nthreads)(*[e.h for e in engines])
     sp = (C.c_void_p * nthreads)(*[s.ctypes.data for s in shards])
@@ -255,15 +276,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    merge_ms = []
+
     def merge_step():
         if world > 1:
             from gyeeta_b200 import dist as gd
-            gd.merge_global(eng, torch, dist)
+            merge_ms.append(gd.merge_global(eng, torch, dist, dev))
+
+    def setup_logical_map():
+        # BASELINE configs[3]: global per-logical-service stats, 16 hosts' instances per logical service; every rank passes the
+        # same (glob_id, logical_id) list so the dense logical index is identical everywhere
+        ids_all = np.concatenate([rank_service_ids(r) for r in range(world)])
+        logical_all = np.tile(np.arange(NSVC, dtype=np.uint64) // np.uint64(16) + np.uint64(1), world)
+        eng.set_logical_map(ids_all, logical_all)
 
     def step_device():
         eng.ingest_device_ptr(ev_dev.data_ptr(), n)
         merge_step()
 
+    eng.ingest_device_ptr(ev_dev.data_ptr(), n)       # registers this rank's services
+    eng.sync()
+    if world > 1:
+        setup_logical_map()
     for _ in range(args.warmup):
         step_device()
     eng.sync()
@@ -355,11 +389,16 @@ def main():
     peak, peak_src = measured_peak_gbs()
     nev_total = n * args.steps
     roof = []
-    for name, ms, bpe in (("ingest_kernel", ms_ing, BYTES_INGEST), ("sort+tdigest chain (rs_hist/scan/rs_scatter/td_*)", ms_td, BYTES_TDIGEST)):
+    traffic = ncu_traffic_per_event()
+    for name, key, ms, bpe in (("ingest_kernel", "ingest_kernel", ms_ing, BYTES_INGEST),
+                               ("sort+tdigest chain (rs_hist/scan/rs_scatter/td_*)", "chain", ms_td, BYTES_TDIGEST)):
         if ms > 0:
             ach = nev_total * bpe / (ms * 1e-3) / 1e9
+            tr = traffic.get(key, {}).get("dram_bytes_per_event")
             roof.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "ms_total": ms, "launch_groups": nb, "algorithmic_bytes_per_event": bpe, "peak_source": peak_src})
+                         "traffic": (tr * n if tr else None), "traffic_note": traffic.get(key, {}).get("source"),
+                         "algorithmic_bytes_per_launch": bpe * n, "ms_per_launch": ms / max(nb, 1),
+                         "ms_total": ms, "launch_groups": nb, "algorithmic_bytes_per_event": bpe, "peak_source": peak_src})
     roof.sort(key=lambda r: -r["ms_total"])
     whole = nev_total * BYTES_EVENT / (max_ms * 1e-3) / 1e9
 
@@ -385,6 +424,9 @@ def main():
         "roofline_whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
                                 "algorithmic_bytes_per_event": BYTES_EVENT},
         "cpu_baseline": cpu, "accuracy": acc,
+        "merge": ({"collective_ms_per_step_rank0": float(np.mean(merge_ms)) if merge_ms else None, "logical_services": NSVC // 16,
+                   "what": "one all-reduce per reduction kind (u64 sum / i64 max / u8 max) + one all-gather of t-digest slabs, NCCL"}
+                  if world > 1 else None),
     }
     print(json.dumps(out))
     if world > 1:

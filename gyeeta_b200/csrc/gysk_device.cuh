@@ -34,6 +34,8 @@ struct IdTable
 	uint32_t	mask;		// capacity - 1
 	uint32_t	max_slots;
 	uint32_t	*count;		// slots handed out so far
+	unsigned long long *slot_id;	// optional: slot -> id
+	uint32_t	*slot_host;	// optional: slot -> host index of the inserting event
 };
 
 // device counters (index into Engine::d_counters)
@@ -182,7 +184,7 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v)
 // engine creation, never by the inserter. With `insert`, an unknown id claims an empty entry with a CAS on the key, takes the
 // next slot number and publishes it; racing readers of the same key spin on a volatile load. Returns -1 when absent / full.
 // Replaces RCU_HASH_TABLE::lookup_single_elem_locked(glob_id, get_uint64_hash(glob_id)) (gy_mconnhdlr.cc:11183).
-__device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long key, bool insert)
+__device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long key, bool insert, uint32_t host_idx = 0)
 {
 	uint32_t pos = uint64_hash(key) & t.mask;
 
@@ -202,6 +204,7 @@ __device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long
 					st_volatile_u32(&e->slot1, SLOT_INVALID);
 					return -1;
 				}
+				if (t.slot_id) { t.slot_id[s] = key; t.slot_host[s] = host_idx; }
 				st_volatile_u32(&e->slot1, s + 1);
 				return (int)s;
 			}

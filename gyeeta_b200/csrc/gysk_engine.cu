@@ -372,6 +372,8 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 #define A(call) do { if ((rc = (call)) != 0) return bail(rc); } while (0)
 	A(dalloc(e, &st.svc_tbl.ent, scap)); st.svc_tbl.mask = scap - 1; st.svc_tbl.max_slots = cfg.max_svcs;
 	A(dalloc(e, &st.svc_tbl.count, 1));
+	A(dalloc(e, &st.slot_id, ns)); A(dalloc(e, &st.slot_host, ns));
+	st.svc_tbl.slot_id = st.slot_id; st.svc_tbl.slot_host = st.slot_host;
 	A(dalloc(e, &st.task_tbl.ent, tcap)); st.task_tbl.mask = tcap - 1; st.task_tbl.max_slots = cfg.max_tasks;
 	A(dalloc(e, &st.task_tbl.count, 1));
 	A(dalloc(e, &st.hist_cur, ns * HIST_CELLS)); A(dalloc(e, &st.hist_last, ns * HIST_CELLS)); A(dalloc(e, &st.hist_all, ns * HIST_CELLS));
@@ -658,8 +660,23 @@ int gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, ui
 			e->wire_bad++;
 			return fail(e, GYSK_ERR_INVAL, "LISTENER_STATE_NOTIFY::validate failed");
 		}
-		// Pre-aggregated 5-s listener state: with the per-sample reduction lifted onto the GPU these records carry
-		// nothing the engine does not already derive itself; they are validated and counted, not folded.
+		// Pre-aggregated 5-s listener state. With the per-sample reduction lifted onto the GPU the per-listener fields are
+		// derived by the engine itself; what these records still feed is the per-host roll-up of partha_listener_state
+		// (gy_mconnhdlr.cc:11175-11251): summstats.update(*pone) per record == LISTEN_SUMM_STATS::update, gy_msocket.h:854-866.
+		// <= 512 records per host per 5 s: host-side integer adds, nothing for a GPU to do.
+		gysk_host_summary hs;
+		memset(&hs, 0, sizeof(hs));
+		for (uint32_t i = 0; i < nevents && (const uint8_t *)pone < pend; ++i, pone = (T *)((uint8_t *)pone + pone->get_elem_size())) {
+			if (pone->curr_state_ < 8) hs.nstates[pone->curr_state_]++;
+			hs.tot_qps += (int32_t)(pone->nqrys_5s_ / 5);
+			hs.tot_act_conn += (int32_t)pone->nconns_active_;
+			hs.tot_kb_inbound += (int32_t)pone->curr_kbytes_inbound_;
+			hs.tot_kb_outbound += (int32_t)pone->curr_kbytes_outbound_;
+			hs.tot_ser_errors += (int32_t)pone->ser_errors_;
+			hs.nlisteners++;
+			hs.nactive += !!pone->nqrys_5s_;
+		}
+		e->host_summ[host_idx] = hs;
 		e->wire_ok++;
 		return GYSK_OK;
 	}
@@ -858,6 +875,40 @@ int gysk_query_flows(gysk_engine *e, const uint64_t *keys, uint32_t n, int last_
 		memcpy(out + off, e->h_flowout, (size_t)m * sizeof(gysk_flow_est));
 	}
 	return post_launch(e, "query_flows");
+}
+
+int gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gysk_topn_entry *out, uint32_t *nout)
+{
+	CHECK_ENGINE(e);
+	if (!out || !nout || n == 0 || n > 64 || metric < GYSK_TOPN_QPS || metric > GYSK_TOPN_NET) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = sync_locked(e);
+	if (rc) return rc;
+	uint32_t nslots = 0;
+	CU(e, cudaMemcpy(&nslots, e->st.svc_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	nslots = std::min(nslots, std::min(e->cfg.max_svcs, e->cfg.max_batch));
+	gysk_topn_entry *d_out = reinterpret_cast<gysk_topn_entry *>(e->d_flowout);		// QCHUNK * 16 B >= 64 * 24 B
+	e->kernel_launches += launch_topn(e->st, e->tmp, nslots, metric, host_idx, n, d_out, e->stream);
+	gysk_topn_entry *h_out = reinterpret_cast<gysk_topn_entry *>(e->h_flowout);
+	CU(e, cudaMemcpyAsync(h_out, d_out, sizeof(gysk_topn_entry) * n, cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaStreamSynchronize(e->stream));
+	if ((rc = post_launch(e, "topn"))) return rc;
+	uint32_t k = 0;
+	for (uint32_t i = 0; i < n; ++i) if (h_out[i].glob_id && h_out[i].score) out[k++] = h_out[i];
+	*nout = k;
+	return GYSK_OK;
+}
+
+int gysk_query_host_summary(gysk_engine *e, uint32_t host_idx, gysk_host_summary *out)
+{
+	CHECK_ENGINE(e);
+	if (!out) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	auto it = e->host_summ.find(host_idx);
+	if (it == e->host_summ.end()) return GYSK_ERR_NOENT;
+	*out = it->second;
+	return GYSK_OK;
 }
 
 int gysk_export_cms(gysk_engine *e, int last_window, uint64_t *cells)

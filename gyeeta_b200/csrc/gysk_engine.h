@@ -81,6 +81,8 @@ struct gysk_engine
 	uint64_t		ring_epoch[gysk::NLEVELS][gysk::NSLOTS];
 	uint32_t		last_flush_tsec {0};
 
+	std::unordered_map<uint32_t, gysk_host_summary> host_summ;	// last LISTEN_SUMM_STATS per host (control-plane sized: <= 512 hosts)
+
 	gysk::MergeState	mg;
 
 	std::mutex		mtx;

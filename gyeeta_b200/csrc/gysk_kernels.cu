@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				c_in++;
 				// one id lookup for all three event kinds (services and tasks live in separate tables)
 				if (svc_id != 0 && (is_tcp || is_task || (is_resp && ms <= 1000000u)))
-					slot = table_lookup(is_task ? st.task_tbl : st.svc_tbl, svc_id, st.auto_register);
+					slot = table_lookup(is_task ? st.task_tbl : st.svc_tbl, svc_id, st.auto_register, host_idx);
 				if (slot < 0) c_drop++;
 				else if (is_resp) c_resp++;
 				else if (is_tcp) c_tcp++;
@@ -849,6 +849,25 @@ static int launch_exclusive_scan(uint32_t *d_data, uint32_t len, uint32_t *d_blo
 	return 3;
 }
 
+// stable LSD radix sort of tmp.keys_a (n_upper >= *d_n keys) on key bits [bit_lo, bit_hi); result in bufs[*which]
+int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s)
+{
+	int launches = 0;
+	const uint32_t ntiles = div_up(n_upper, SORT_TILE);
+	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
+	int w = 0;
+
+	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
+		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], n_upper, d_n, shift, tmp.tile_hist, ntiles);
+		launches += 1 + launch_exclusive_scan(tmp.tile_hist, RADIX * ntiles, tmp.scan_tmp, nullptr, s);
+		rs_scatter_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], bufs[w ^ 1], n_upper, d_n, shift, tmp.tile_hist, ntiles);
+		launches++;
+		w ^= 1;
+	}
+	*which = w;
+	return launches;
+}
+
 // sort the (slot, usec) keys produced by ingest, then fold every touched service's new samples into its digest
 int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t max_svcs, cudaStream_t s)
 {
@@ -862,21 +881,13 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, u
 	const int total_bits = VALUE_BITS + (int)slot_bits;
 
 	const unsigned long long *src = tmp.keys_a;
-	unsigned long long *dst = tmp.keys_b;
 	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
 	int which = 0;
 
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
 
-	for (int shift = 0, pass = 0; shift < total_bits; shift += 8, ++pass) {
-		const unsigned long long *dn = d_nkeys;		// ingest left the number of (compacted) RESP keys there
-		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(src, n, dn, shift, tmp.tile_hist, ntiles);
-		launches += 1 + launch_exclusive_scan(tmp.tile_hist, RADIX * ntiles, tmp.scan_tmp, nullptr, s);
-		rs_scatter_kernel<<<ntiles, RS_THREADS, 0, s>>>(src, dst, n, dn, shift, tmp.tile_hist, ntiles);
-		launches++;
-		which ^= 1;
-		src = bufs[which]; dst = bufs[which ^ 1];
-	}
+	launches += launch_radix_sort(tmp, n, d_nkeys, 0, total_bits, &which, s);
+	src = bufs[which];
 
 	td_segments_kernel<<<div_up(n, 256), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
 	int dev = 0, nsm = 148;
@@ -886,6 +897,53 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, u
 	td_sums_kernel<<<nsm * 8, 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
 	td_merge_kernel<<<nsm * 6, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
 	return launches + 4;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// top-N services of the last closed window (BOUNDED_PRIO_QUEUE uses of partha_listener_state, gy_mconnhdlr.cc:11262-11304:
+// top listeners by qps / active conns / network): score every service, radix-sort (score, slot) keys, read the tail
+// ---------------------------------------------------------------------------------------------------
+__global__ void topn_score_kernel(DevState st, uint32_t nslots, int metric, int host_filter, unsigned long long *__restrict__ keys,
+		unsigned long long *d_n)
+{
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot == 0) *d_n = nslots;
+	if (slot >= nslots) return;
+	unsigned long long score = 0;
+
+	if (host_filter < 0 || st.slot_host[slot] == (uint32_t)host_filter) {
+		if (metric == GYSK_TOPN_QPS) {
+			for (int b = 0; b < HIST_MAX_CELL; ++b) score += st.hist_last[(size_t)slot * HIST_CELLS + b].count;
+		}
+		else if (metric == GYSK_TOPN_CONNS) score = (uint32_t)st.conn_last[slot];
+		else score = st.conn_last[slot] >> 32;
+	}
+	if (score > 0xFFFFFFFFull) score = 0xFFFFFFFFull;
+	keys[slot] = (score << 32) | slot;
+}
+
+__global__ void topn_pick_kernel(DevState st, const unsigned long long *__restrict__ sorted, uint32_t nslots, uint32_t want, gysk_topn_entry *__restrict__ out)
+{
+	const uint32_t i = threadIdx.x;
+	if (i >= want) return;
+	gysk_topn_entry o; o.glob_id = 0; o.score = 0; o.host_idx = 0; o.pad = 0;
+	if (i < nslots) {
+		const unsigned long long k = sorted[nslots - 1 - i];		// descending
+		const uint32_t slot = (uint32_t)k;
+		o.glob_id = st.slot_id[slot]; o.score = k >> 32; o.host_idx = st.slot_host[slot];
+	}
+	out[i] = o;
+}
+
+int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int metric, int host_filter, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s)
+{
+	if (!nslots) return 0;
+	unsigned long long *d_n = st.counters + CTR_NKEYS;
+	int which = 0, launches = 2;
+	topn_score_kernel<<<div_up(nslots, 256), 256, 0, s>>>(st, nslots, metric, host_filter, tmp.keys_a, d_n);
+	launches += launch_radix_sort(tmp, nslots, d_n, 32, 64, &which, s);
+	topn_pick_kernel<<<1, 64, 0, s>>>(st, which ? tmp.keys_b : tmp.keys_a, nslots, want, d_out);
+	return launches;
 }
 
 int launch_flush(const DevState &st, uint32_t nslots, HistCell *ring_plane0, HistCell *ring_plane1, cudaStream_t s)

@@ -15,6 +15,8 @@ struct DevState
 	HistCell		*hist_cur, *hist_last, *hist_all;	// [max_svcs][16]
 	HistCell		*hist_ring;				// [NLEVELS][NSLOTS][max_svcs][16] rolling 300-s / 5-day levels
 	unsigned long long	*conn_cur, *conn_last;			// packed {count:32, kbytes:32}
+	unsigned long long	*slot_id;				// [max_svcs] slot -> glob_id (written by the inserter)
+	uint32_t		*slot_host;				// [max_svcs] slot -> host_idx of the first event seen
 	unsigned long long	*conn_all_cnt, *conn_all_kb;
 	uint8_t			*hll;					// [max_svcs][1 << hll_p]
 	Centroid		*td_cent;				// [max_svcs][TD_CAP]
@@ -74,6 +76,8 @@ int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks,
 int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_t n, int is_task, cudaStream_t s);
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s);
 int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t max_svcs, cudaStream_t s);
+int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s);
+int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int metric, int host_filter, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
 int launch_flush(const DevState &st, uint32_t max_svcs, HistCell *ring_plane0, HistCell *ring_plane1, cudaStream_t s);
 int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, uint32_t max_svcs, uint32_t live_mask0, uint32_t live_mask1,
 		SvcRaw *d_out, cudaStream_t s);

@@ -48,6 +48,15 @@ class SvcSummary(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class HostSummary(C.Structure):
+    _fields_ = [("nstates", C.c_int32 * 8)] + [(n, C.c_int32) for n in ("tot_qps", "tot_act_conn", "tot_kb_inbound", "tot_kb_outbound",
+                                                                         "tot_ser_errors", "nlisteners", "nactive", "pad")]
+
+
+class TopnEntry(C.Structure):
+    _fields_ = [("glob_id", C.c_uint64), ("score", C.c_uint64), ("host_idx", C.c_uint32), ("pad", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("events_in", "events_dropped", "events_resp", "events_tcp", "events_task", "nsvcs",
                                           "ntasks", "batches", "kernel_launches", "wire_msgs_ok", "wire_msgs_bad")]
@@ -91,6 +100,8 @@ def load_library(path=None):
         "gysk_flush": (i32, [vp, u32]),
         "gysk_query_svcs": (i32, [vp, vp, u32, vp]),
         "gysk_query_flows": (i32, [vp, vp, u32, i32, vp]),
+        "gysk_query_host_summary": (i32, [vp, u32, vp]),
+        "gysk_topn_svcs": (i32, [vp, i32, C.c_int32, u32, vp, vp]),
         "gysk_export_hist": (i32, [vp, u64, i32, vp, vp, vp]),
         "gysk_export_task_hist": (i32, [vp, u64, i32, vp, vp, vp]),
         "gysk_export_hll": (i32, [vp, u64, vp]),
@@ -227,6 +238,22 @@ class Engine:
         out = np.zeros(len(keys), dtype=FLOW_EST_DTYPE)
         self._chk(self.L.gysk_query_flows(self.h, _p(keys), len(keys), int(last_window), _p(out)))
         return out
+
+    def topn(self, metric, n=10, host_idx=-1):
+        out = (TopnEntry * n)()
+        k = C.c_uint32()
+        self._chk(self.L.gysk_topn_svcs(self.h, metric, host_idx, n, out, C.byref(k)))
+        return [(o.glob_id, o.score, o.host_idx) for o in out[: k.value]]
+
+    def host_summary(self, host_idx):
+        hs = HostSummary()
+        rc = self.L.gysk_query_host_summary(self.h, host_idx, C.byref(hs))
+        if rc == -2:
+            return None
+        self._chk(rc)
+        d = {f: getattr(hs, f) for f, _ in hs._fields_ if f not in ("nstates", "pad")}
+        d["nstates"] = list(hs.nstates)
+        return d
 
     def export_hist(self, id_, which):
         out = np.zeros(15, dtype=SERIAL_DTYPE)

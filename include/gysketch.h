@@ -173,6 +173,30 @@ typedef struct gysk_svc_summary
 	uint64_t	td_count;
 } gysk_svc_summary;
 
+/* per-host roll-up of the listener states of one 5-s tick: LISTEN_SUMM_STATS<int>, server/gy_msocket.h:840-866 */
+typedef struct gysk_host_summary
+{
+	int32_t		nstates[8];		/* per OBJ_STATE_E value (STATE_IDLE .. STATE_DOWN) */
+	int32_t		tot_qps;		/* += nqrys_5s_ / 5 */
+	int32_t		tot_act_conn;		/* += nconns_active_ */
+	int32_t		tot_kb_inbound;
+	int32_t		tot_kb_outbound;
+	int32_t		tot_ser_errors;
+	int32_t		nlisteners;
+	int32_t		nactive;		/* += !!nqrys_5s_ */
+	int32_t		pad;
+} gysk_host_summary;
+
+/* top-N services of the last closed window (BOUNDED_PRIO_QUEUE users of partha_listener_state, gy_mconnhdlr.cc:11262-11304) */
+enum { GYSK_TOPN_QPS = 0, GYSK_TOPN_CONNS = 1, GYSK_TOPN_NET = 2 };
+typedef struct gysk_topn_entry
+{
+	uint64_t	glob_id;
+	uint64_t	score;			/* nqrys_5s / conn events / kbytes of the last window */
+	uint32_t	host_idx;
+	uint32_t	pad;
+} gysk_topn_entry;
+
 typedef struct gysk_flow_est
 {
 	uint64_t	flow_key;
@@ -231,6 +255,10 @@ int		gysk_flush(gysk_engine *e, uint32_t tsec);
 /* ---- queries ---- */
 int		gysk_query_svcs(gysk_engine *e, const uint64_t *glob_ids, uint32_t n, gysk_svc_summary *out);
 int		gysk_query_flows(gysk_engine *e, const uint64_t *flow_keys, uint32_t n, int last_window, gysk_flow_est *out);
+/* LISTEN_SUMM_STATS of the last NOTIFY_LISTENER_STATE message of a host (partha_listener_state, gy_mconnhdlr.cc:11251) */
+/* host_idx < 0: over all hosts of this engine; n <= 64 */
+int		gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gysk_topn_entry *out, uint32_t *nout);
+int		gysk_query_host_summary(gysk_engine *e, uint32_t host_idx, gysk_host_summary *out);
 int		gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial out[GYSK_HIST_MAX_BUCKETS],
 				uint64_t *total_count, int64_t *max_val);
 int		gysk_export_hll(gysk_engine *e, uint64_t glob_id, uint8_t *regs /* 1 << hll_p bytes */);

@@ -281,3 +281,26 @@ def test_rolling_levels_300s_and_5days():
         ser = np.zeros(15, dtype=ge.SERIAL_DTYPE); ser[:] = h5m[0]
         eng.L.gysk_hist_percentiles(0, 0, ser.ctypes.data_as(C.c_void_p), h5m[1], p95.ctypes.data_as(C.c_void_p), 1, pc.ctypes.data_as(C.c_void_p))
         assert s_["p95_5min_resp_ms"] == pc[0]
+
+
+def test_topn_services_last_window():
+    """device top-N (score + radix sort) against numpy over the oracle's last-window state; per-host filter included"""
+    rng = np.random.default_rng(15)
+    eng, orc = make_pair(max_svcs=2048, max_tasks=16, max_batch=1 << 16, cms_log2_width=12)
+    ev = synth.gen_mixed(rng, 120_000, 700, ntask=8, nhosts=16, nclients=3000)
+    feed_both(eng, orc, ev, 1 << 16)
+    eng.flush(5); orc.flush(5)
+    ids = np.unique(ev["svc_id"][ev["type"] != ge.EV_TASK])
+    host_of = {int(i): int(ev["host_idx"][np.argmax(ev["svc_id"] == i)]) for i in ids}
+    qps = {int(i): (orc.export_hist(int(i), 1) or (None, 0, 0))[1] for i in ids}
+    conn = {int(i): orc.export_conn(int(i))[1] for i in ids}
+    for metric, score in ((0, qps), (1, {k: v & 0xFFFFFFFF for k, v in conn.items()}), (2, {k: v >> 32 for k, v in conn.items()})):
+        got = eng.topn(metric, 10)
+        want = sorted(score.values(), reverse=True)[:10]
+        assert [s for _, s, _ in got] == [w for w in want if w > 0]
+        for gid, s, h in got:
+            assert score[gid] == s and host_of[gid] == h
+    h = host_of[int(ids[0])]
+    got = eng.topn(0, 5, host_idx=h)
+    want = sorted([v for k, v in qps.items() if host_of[k] == h], reverse=True)[:5]
+    assert [s for _, s, _ in got] == [w for w in want if w > 0] and all(hh == h for _, _, hh in got)

@@ -156,3 +156,33 @@ def test_raw_ebpf_records():
     assert st["nsvcs"] == 1 and st["events_tcp"] == 10      # same (netns, ip, port) -> same service id as the resp events
     assert int(eng.export_cms().sum() & 0xFFFFFFFF) == 40   # 10 events x 4 rows, count halves
     assert want["total"] == kept
+
+
+def test_listener_state_host_summary():
+    """NOTIFY_LISTENER_STATE: validated like LISTENER_STATE_NOTIFY::validate and rolled up per host exactly as
+    LISTEN_SUMM_STATS::update (server/gy_msocket.h:854-866) does inside partha_listener_state (gy_mconnhdlr.cc:11251)."""
+    LSN = np.dtype([("glob_id", "<u8"), ("nqrys_5s", "<u4"), ("total_resp_5sec", "<u4"), ("nconns", "<u4"), ("nconns_active", "<u4"),
+                    ("ntasks", "<u4"), ("p95_5s", "<u4"), ("p95_5min", "<u4"), ("kb_in", "<u4"), ("kb_out", "<u4"), ("ser_errors", "<u4"),
+                    ("cli_errors", "<u4"), ("t1", "<u4"), ("t2", "<u4"), ("t3", "<u4"), ("t4", "<u4"), ("t5", "<u4"), ("t6", "<u4"),
+                    ("ntasks_issue", "<u2"), ("is_http", "u1"), ("curr_state", "u1"), ("curr_issue", "u1"), ("issue_bit_hist", "u1"),
+                    ("high_resp_bit_hist", "u1"), ("last_issue_subsrc", "u1"), ("query_flags", "u1"), ("issue_string_len", "u1"),
+                    ("padding_len", "u1"), ("pad", "u1")])
+    assert LSN.itemsize == 88
+    rng = np.random.default_rng(4)
+    eng = ge.Engine(max_svcs=64, max_tasks=16, max_batch=2048, cms_log2_width=10)
+    recs, want = [], dict(nstates=[0] * 8, tot_qps=0, tot_act_conn=0, tot_kb_inbound=0, tot_kb_outbound=0, tot_ser_errors=0, nlisteners=0, nactive=0)
+    for i in range(200):
+        r = np.zeros(1, dtype=LSN)
+        r["glob_id"] = 100 + i
+        r["nqrys_5s"] = int(rng.integers(0, 5000)) if i % 4 else 0
+        r["nconns_active"], r["kb_in"], r["kb_out"], r["ser_errors"] = rng.integers(0, 1000, 4)
+        r["curr_state"] = int(rng.integers(0, 7))
+        recs.append((r, b"some issue" if i % 5 == 0 else b""))
+        want["nstates"][int(r["curr_state"][0])] += 1
+        want["tot_qps"] += int(r["nqrys_5s"][0]) // 5
+        want["tot_act_conn"] += int(r["nconns_active"][0]); want["tot_kb_inbound"] += int(r["kb_in"][0])
+        want["tot_kb_outbound"] += int(r["kb_out"][0]); want["tot_ser_errors"] += int(r["ser_errors"][0])
+        want["nlisteners"] += 1; want["nactive"] += int(r["nqrys_5s"][0] != 0)
+    assert eng.ingest_msg(build_msg(ge.NOTIFY_LISTENER_STATE, recs), host_idx=9) == 0
+    assert eng.host_summary(9) == want
+    assert eng.host_summary(10) is None
