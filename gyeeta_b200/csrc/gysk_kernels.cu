@@ -56,9 +56,10 @@ __global__ void register_kernel(DevState st, const unsigned long long *ids, uint
 //   CTA  : a direct-mapped shared-memory table privatises hot cells for the lifetime of the CTA (a cell is admitted when it
 //          shows up at least twice inside one warp), and is flushed with one RED pair per entry when the CTA retires.
 // Everything stays exact integer arithmetic, so the result is independent of grouping and order.
-struct HotTable					// structure of arrays, 20 B per entry
+template <int BITS_>
+struct HotTableT				// structure of arrays, 20 B per entry
 {
-	static constexpr int BITS = 10;
+	static constexpr int BITS = BITS_;
 	static constexpr int N = 1 << BITS;
 	uint32_t		tag[N];			// cell id + 1, 0 = free
 	uint32_t		count[N];
@@ -91,6 +92,7 @@ __device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cel
 // all 32 lanes call this; lanes with active == false only take part in the collectives.
 // Group sums use a shuffle loop bounded by the largest group of the warp (typically 1-4): redux with per-lane masks would
 // make the compiler iterate over every distinct group. No global load anywhere: the updates are fire-and-forget REDs.
+template <typename HotTable>
 __device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool active, uint32_t cell, int data)
 {
 	const int lane = threadIdx.x & 31;
@@ -146,14 +148,15 @@ __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t
 //           rows (one (event, row) pair per lane), the HLL updates and the three task histograms (one (event, histogram)
 //           pair per lane) each run with all lanes doing the same thing instead of serialising 70/20/10-divergent branches.
 // RESP sort keys are written compacted (one global cursor bump per tile), so the radix sort never sees a non-RESP slot.
-static constexpr int INGEST_THREADS = 256;
 static constexpr int INGEST_EPT = 4;
-static constexpr int INGEST_TILE = INGEST_THREADS * INGEST_EPT;
 
 struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
 
-struct IngestShared
+template <int INGEST_THREADS>
+struct IngestSharedT
 {
+	static constexpr int INGEST_TILE = INGEST_THREADS * INGEST_EPT;
+	using HotTable = HotTableT<(INGEST_THREADS >= 256 ? 10 : 9)>;
 	HotTable	hot;
 	IngestRec	rec[INGEST_TILE];
 	uint16_t	q_resp[INGEST_TILE], q_tcp[INGEST_TILE], q_task[INGEST_TILE];
@@ -172,10 +175,13 @@ __device__ __forceinline__ void queue_push(bool pred, uint16_t *q, uint32_t *qn,
 	if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = item;
 }
 
-template <int MIN_CTAS>
+template <int INGEST_THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
 		unsigned long long *__restrict__ keys)
 {
+	using IngestShared = IngestSharedT<INGEST_THREADS>;
+	using HotTable = typename IngestShared::HotTable;
+	constexpr int INGEST_TILE = IngestShared::INGEST_TILE;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	IngestShared &S = *reinterpret_cast<IngestShared *>(smem_raw);
 	unsigned long long c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;
@@ -818,25 +824,29 @@ int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_
 	return 1;
 }
 
+template <int THREADS, int MIN_CTAS>
+static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, int nsm, cudaStream_t s)
+{
+	using Shared = IngestSharedT<THREADS>;
+	static bool attr_set = false;
+	if (!attr_set) { cudaFuncSetAttribute(ingest_kernel<THREADS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)); attr_set = true; }
+	const uint64_t want = (n + Shared::INGEST_TILE - 1) / Shared::INGEST_TILE;
+	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * MIN_CTAS ? want : (uint64_t)nsm * MIN_CTAS);
+	ingest_kernel<THREADS, MIN_CTAS><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys);
+}
+
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s)
 {
 	if (!n) return 0;
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-	static const int per_sm = []{ const char *v = getenv("GYSK_INGEST_CTAS"); const int c = v ? atoi(v) : 4; return c >= 1 && c <= 8 ? c : 4; }();
-	static bool attr_set = false;
-	const size_t smem = sizeof(IngestShared);
-	if (!attr_set) {
-		cudaFuncSetAttribute(ingest_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		cudaFuncSetAttribute(ingest_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		attr_set = true;
-	}
-	const uint64_t want = (n + INGEST_TILE - 1) / INGEST_TILE;
-	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * per_sm ? want : (uint64_t)nsm * per_sm);
+	// CTA shape: 128 threads x 8 CTAs/SM keeps more independent barrier groups per SM than 256 x 4 (the tile pipeline has three
+	// block barriers per tile); GYSK_INGEST_VARIANT=256 selects the wide shape for A/B runs
+	static const int variant = []{ const char *v = getenv("GYSK_INGEST_VARIANT"); return v ? atoi(v) : 128; }();
 	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, sizeof(unsigned long long), s);	// the key cursor of this batch
-	if (per_sm >= 5) ingest_kernel<5><<<grid, INGEST_THREADS, smem, s>>>(st, d_ev, n, d_keys);
-	else ingest_kernel<4><<<grid, INGEST_THREADS, smem, s>>>(st, d_ev, n, d_keys);
+	if (variant == 256) launch_ingest_variant<256, 4>(st, d_ev, n, d_keys, nsm, s);
+	else launch_ingest_variant<128, 8>(st, d_ev, n, d_keys, nsm, s);
 	return 1;
 }
 
