@@ -39,7 +39,7 @@ struct IdTable
 };
 
 // device counters (index into Engine::d_counters)
-enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_NTOUCHED, CTR_MAX = 16 };
+enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_MAXVAL, CTR_NTOUCHED, CTR_MAX = 16 };	// NKEYS, MAXVAL adjacent: reset / read together
 
 // ---------------------------------------------------------------------------------------------------
 // jhash: Bob Jenkins lookup2 in the form the reference uses (common/jhash.h:22-35,121-134); seed 0xceedfead

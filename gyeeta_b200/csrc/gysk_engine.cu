@@ -63,7 +63,19 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
 	}
 	e->kernel_launches += launch_ingest(e->st, d_ev, n, e->tmp.keys_a, e->stream);
 	if (pe) CU(e, cudaEventRecord(pe[1], e->stream));
-	e->kernel_launches += launch_tdigest_update(e->st, e->tmp, n, e->cfg.max_svcs, e->stream);
+	// the sort is sized by what the batch actually holds: number of RESP keys, bits of the largest response time, slots in
+	// use — three words read back here (one stream sync per device batch; the kernels of the batch stay back to back)
+	CU(e, cudaMemcpyAsync(e->h_counters, e->st.counters + CTR_NKEYS, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaMemcpyAsync(e->h_counters + 2, e->st.svc_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaStreamSynchronize(e->stream));
+	{
+		const uint64_t nkeys = e->h_counters[0];
+		const uint64_t max_us = std::min<uint64_t>(e->h_counters[1] * 1000ull + 999ull, (1ull << VALUE_BITS) - 1);	// msec maximum -> usec bound
+		const uint32_t nslots = std::min<uint32_t>((uint32_t)e->h_counters[2], e->cfg.max_svcs);
+		int value_bits = 1;
+		while (value_bits < VALUE_BITS && (1ull << value_bits) <= max_us) value_bits++;
+		e->kernel_launches += launch_tdigest_update(e->st, e->tmp, nkeys, nslots, value_bits, e->stream);
+	}
 	if (pe) CU(e, cudaEventRecord(pe[2], e->stream));
 	e->batches++;
 	return post_launch(e, "ingest batch");
@@ -379,6 +391,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(dalloc(e, &st.hist_cur, ns * HIST_CELLS)); A(dalloc(e, &st.hist_last, ns * HIST_CELLS)); A(dalloc(e, &st.hist_all, ns * HIST_CELLS));
 	A(dalloc(e, &st.hist_ring, (size_t)NLEVELS * NSLOTS * ns * HIST_CELLS));
 	A(dalloc(e, &st.conn_cur, ns)); A(dalloc(e, &st.conn_last, ns)); A(dalloc(e, &st.conn_all_cnt, ns)); A(dalloc(e, &st.conn_all_kb, ns));
+	A(dalloc(e, &st.bm_cur, ns * HIST_CELLS)); A(dalloc(e, &st.bm_last, ns * HIST_CELLS));
 	A(dalloc(e, &st.hll, ns << cfg.hll_p));
 	A(dalloc(e, &st.td_cent, ns * TD_CAP)); A(dalloc(e, &st.td_head, ns));
 	A(dalloc(e, &st.task_hist, nt * 3 * HIST_CELLS));
@@ -804,6 +817,23 @@ int gysk_export_task_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_seri
 	if (!e->h_taskraw[0].found) return GYSK_ERR_NOENT;
 	const int h = which - GYSK_HIST_TASK_CPU_PCT;
 	hist_from_cells(e->h_taskraw[0].h[h], h == 0 ? 14 : 15, out, total, maxv, true);
+	return GYSK_OK;
+}
+
+// CONN_BITMAP::get_conn_breakup (common/gy_socket_stat.h:412-433): per response bucket the number of (client port & 31) slots seen
+int gysk_export_conn_bitmap(gysk_engine *e, uint64_t id, int last_window, uint32_t masks[GYSK_HIST_MAX_BUCKETS], uint8_t nconn_arr[GYSK_HIST_MAX_BUCKETS])
+{
+	CHECK_ENGINE(e);
+	if (!masks || !nconn_arr) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = submit_stage(e);
+	if (rc) return rc;
+	if ((rc = gather_svcs(e, &id, 1))) return rc;
+	const SvcRaw &r = e->h_svcraw[0];
+	if (!r.found) return GYSK_ERR_NOENT;
+	const uint32_t *bm = last_window ? r.bm_last : r.bm_cur;
+	for (int j = 0; j < GYSK_HIST_MAX_BUCKETS; ++j) { masks[j] = bm[j]; nconn_arr[j] = (uint8_t)__builtin_popcount(bm[j]); }
 	return GYSK_OK;
 }
 

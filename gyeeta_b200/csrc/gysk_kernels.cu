@@ -65,6 +65,7 @@ struct HotTableT				// structure of arrays, 20 B per entry
 	uint32_t		count[N];
 	unsigned long long	sum[N];
 	int			vmax[N];
+	uint32_t		bits[N];		// CONN_BITMAP bits of a RESP cell
 };
 static constexpr uint32_t CELL_TASK = 1u << 30;			// cell ids: svc hist = slot*16 + bucket, conn = slot*16 + 15,
 								//           task = CELL_TASK | (tslot*48 + hist*16 + bucket)
@@ -72,7 +73,7 @@ static constexpr uint32_t CELL_TASK = 1u << 30;			// cell ids: svc hist = slot*1
 __device__ __forceinline__ bool cell_is_conn(uint32_t cell) { return !(cell & CELL_TASK) && (cell & 15u) == (uint32_t)HIST_MAX_CELL; }
 
 // one RED per field, nothing is read back: {count, sum} (+ max_val_seen_ for histogram cells)
-__device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cell, uint32_t cnt, unsigned long long sum, int vmax)
+__device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cell, uint32_t cnt, unsigned long long sum, int vmax, uint32_t bits)
 {
 	if (cell & CELL_TASK) {
 		HistCell *c = st.task_hist + (cell & ~CELL_TASK);
@@ -86,6 +87,8 @@ __device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cel
 		HistCell *c = st.hist_cur + cell;
 		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
 		atomicMax(&st.hist_cur[cell | 15u].sum, (long long)vmax);
+		// TCP_LISTENER::CONN_BITMAP::add_response (common/gy_socket_stat.h:403-410), transposed: the cell index is the same
+		if (bits) atomicOr(st.bm_cur + cell, bits);
 	}
 }
 
@@ -93,7 +96,7 @@ __device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cel
 // Group sums use a shuffle loop bounded by the largest group of the warp (typically 1-4): redux with per-lane masks would
 // make the compiler iterate over every distinct group. No global load anywhere: the updates are fire-and-forget REDs.
 template <typename HotTable>
-__device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool active, uint32_t cell, int data)
+__device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool active, uint32_t cell, int data, uint32_t bits = 0)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t id = active ? cell : (0x80000000u | (uint32_t)lane);
@@ -107,7 +110,8 @@ __device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool
 	for (uint32_t t = 1; t < maxcnt; ++t) {
 		const int src = rest ? (__ffs(rest) - 1) : lane;
 		const int other = __shfl_sync(0xffffffffu, data, src);
-		if (rest) { sum += other; gmax = max(gmax, other); rest &= rest - 1; }
+		const uint32_t obits = __shfl_sync(0xffffffffu, bits, src);
+		if (rest) { sum += other; gmax = max(gmax, other); bits |= obits; rest &= rest - 1; }
 	}
 
 	if (!active || (m & ((1u << lane) - 1u))) return;		// group leader = lowest lane
@@ -122,8 +126,9 @@ __device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool
 	}
 	if (hit) {
 		atomicAdd(&hot.count[h], cnt); atomicAdd(&hot.sum[h], (unsigned long long)sum); atomicMax(&hot.vmax[h], gmax);
+		if (bits) atomicOr(&hot.bits[h], bits);
 	}
-	else cell_add_global(st, cell, cnt, (unsigned long long)sum, gmax);
+	else cell_add_global(st, cell, cnt, (unsigned long long)sum, gmax, bits);
 }
 
 __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t rank)
@@ -152,16 +157,42 @@ static constexpr int INGEST_EPT = 4;
 
 struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
 
-template <int INGEST_THREADS>
+// ---- TMA (bulk async copy) staging of the next event tile into shared memory, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");		// make the init visible to the async proxy
+}
+
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");		// earlier generic-proxy reads of dst are done (after bar.sync)
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			:: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}"
+			:: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int INGEST_THREADS, bool STAGE>
 struct IngestSharedT
 {
 	static constexpr int INGEST_TILE = INGEST_THREADS * INGEST_EPT;
 	using HotTable = HotTableT<(INGEST_THREADS >= 256 ? 10 : 9)>;
+	alignas(128) uint4	evbuf[STAGE ? INGEST_TILE * 2 : 1];	// next tile of 32-byte events, filled by cp.async.bulk
+	unsigned long long	mbar;
 	HotTable	hot;
 	IngestRec	rec[INGEST_TILE];
 	uint16_t	q_resp[INGEST_TILE], q_tcp[INGEST_TILE], q_task[INGEST_TILE];
 	uint32_t	qn[2][4];		// per tile parity: n_resp, n_tcp, n_task (double-buffered: no barrier to reset them)
 	unsigned long long key_base;
+	uint32_t	max_value;		// largest RESP usec seen by this CTA (sizes the radix sort)
 };
 
 __device__ __forceinline__ void queue_push(bool pred, uint16_t *q, uint32_t *qn, uint16_t item)
@@ -175,11 +206,11 @@ __device__ __forceinline__ void queue_push(bool pred, uint16_t *q, uint32_t *qn,
 	if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = item;
 }
 
-template <int INGEST_THREADS, int MIN_CTAS>
+template <int INGEST_THREADS, int MIN_CTAS, bool STAGE>
 __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
 		unsigned long long *__restrict__ keys)
 {
-	using IngestShared = IngestSharedT<INGEST_THREADS>;
+	using IngestShared = IngestSharedT<INGEST_THREADS, STAGE>;
 	using HotTable = typename IngestShared::HotTable;
 	constexpr int INGEST_TILE = IngestShared::INGEST_TILE;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -188,14 +219,23 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint64_t ntiles = (n + INGEST_TILE - 1) / INGEST_TILE;
 
-	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
+	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; S.hot.bits[i] = 0; }
 	if (threadIdx.x < 8) (&S.qn[0][0])[threadIdx.x] = 0;
+	if (threadIdx.x == 0) S.max_value = 0;
+	if (STAGE && threadIdx.x == 0) mbar_init(&S.mbar, 1);
 	__syncthreads();
+	// prologue: the first tile of this CTA starts flying into shared memory
+	if (STAGE && threadIdx.x == 0 && blockIdx.x < ntiles) {
+		const uint64_t b0 = (uint64_t)blockIdx.x * INGEST_TILE;
+		const uint64_t cnt = n - b0 < (uint64_t)INGEST_TILE ? n - b0 : (uint64_t)INGEST_TILE;
+		tma_load_1d(S.evbuf, ev + b0, (uint32_t)cnt * 32u, &S.mbar);
+	}
 
 	int par = 0;
 	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1) {
 		const uint64_t tbase = tile * INGEST_TILE;
 		uint32_t *qn = S.qn[par];
+		if (STAGE) mbar_wait(&S.mbar, (uint32_t)par);		// this tile's events have landed (one completion per tile)
 
 		// ---------------- phase 1: decode + lookup + enqueue ----------------
 		uint4 ra[INGEST_EPT], rb[INGEST_EPT];
@@ -203,8 +243,14 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 		for (int k = 0; k < INGEST_EPT; ++k) {
 			const uint64_t i = tbase + (uint64_t)k * INGEST_THREADS + threadIdx.x;
 			if (i < n) {
-				ra[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i));		// streamed once: evict-first, keep L2 for
-				rb[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i) + 1);	// the id table / histogram / count-min lines
+				if (STAGE) {
+					ra[k] = S.evbuf[2 * (k * INGEST_THREADS + threadIdx.x)];
+					rb[k] = S.evbuf[2 * (k * INGEST_THREADS + threadIdx.x) + 1];
+				}
+				else {
+					ra[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i));		// streamed once: evict-first, keep L2 for
+					rb[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i) + 1);	// the id table / histogram / count-min lines
+				}
 			}
 			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }	// type 0xFFFF: padding, not counted
 		}
@@ -246,6 +292,12 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 		if (threadIdx.x == 0) {
 			S.qn[par ^ 1][0] = 0; S.qn[par ^ 1][1] = 0; S.qn[par ^ 1][2] = 0;
 			S.key_base = n_resp ? atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)n_resp) : 0ull;
+			// every thread has consumed evbuf (barrier above): stage the next tile of this CTA while phase 2 runs
+			if (STAGE && tile + gridDim.x < ntiles) {
+				const uint64_t b1 = (tile + gridDim.x) * INGEST_TILE;
+				const uint64_t cnt = n - b1 < (uint64_t)INGEST_TILE ? n - b1 : (uint64_t)INGEST_TILE;
+				tma_load_1d(S.evbuf, ev + b1, (uint32_t)cnt * 32u, &S.mbar);
+			}
 		}
 
 		// ---------------- phase 2b: TCP — count-min rows, one (event, row) pair per lane ----------------
@@ -297,22 +349,26 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			for (uint32_t base = wid * 32; base < n_resp; base += INGEST_THREADS) {
 				const uint32_t q = base + lane;
 				const bool act = q < n_resp;
-				uint32_t cell = 0; int ms = 0;
+				uint32_t cell = 0, bit = 0; int ms = 0;
 				if (act) {
 					const IngestRec r = S.rec[S.q_resp[q]];
+					bit = 1u << ((uint32_t)r.flow_key & 0x1Fu);		// CONN_BITMAP: client port & 0x1F
 					ms = (int)(r.value / 1000u);
 					cell = r.slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
 					__stcs(keys + kb + q, ((unsigned long long)r.slot << VALUE_BITS) | r.value);
 				}
-				cell_add(st, S.hot, act, cell, ms);
+				const uint32_t wmax = __reduce_max_sync(0xffffffffu, act ? (uint32_t)ms : 0u);	// msec is enough: bits(usec) <= bits(msec) + 10
+				if (lane == 0 && wmax > S.max_value) atomicMax(&S.max_value, wmax);
+				cell_add(st, S.hot, act, cell, ms, bit);
 			}
 		}
 		__syncthreads();			// rec / queues may be overwritten by the next tile
 	}
 
+	if (threadIdx.x == 0 && S.max_value) atomicMax(st.counters + CTR_MAXVAL, (unsigned long long)S.max_value);
 	// retire: one RED group per privatised cell
 	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) {
-		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i]);
+		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i], S.hot.bits[i]);
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
@@ -684,6 +740,7 @@ __global__ void flush_kernel(DevState st, uint32_t nslots, HistCell *__restrict_
 	const int cell = (int)(i & (HIST_CELLS - 1));
 	const HistCell c = st.hist_cur[i];
 
+	st.bm_last[i] = st.bm_cur[i]; st.bm_cur[i] = 0;		// CONN_BITMAP::clear every 5 s (gy_socket_stat.h:436)
 	st.hist_last[i] = c;
 	// rolling levels: the window is added to the current slot of each level (cleared by the host when its epoch changed).
 	// A cleared slot's max cell reads 0, which is below any recorded response time or equal to it: harmless for max().
@@ -735,6 +792,7 @@ __global__ void __launch_bounds__(128) gather_svcs_kernel(DevState st, const uns
 		o.cur[lane] = st.hist_cur[(size_t)slot * HIST_CELLS + lane];
 		o.last[lane] = st.hist_last[(size_t)slot * HIST_CELLS + lane];
 		o.all[lane] = st.hist_all[(size_t)slot * HIST_CELLS + lane];
+		o.bm_cur[lane] = st.bm_cur[(size_t)slot * HIST_CELLS + lane]; o.bm_last[lane] = st.bm_last[(size_t)slot * HIST_CELLS + lane];
 		// rolling levels: sum of the slots still inside the level's span
 		for (int l = 0; l < NLEVELS; ++l) {
 			const uint32_t live = l ? live1 : live0;
@@ -824,15 +882,15 @@ int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_
 	return 1;
 }
 
-template <int THREADS, int MIN_CTAS>
+template <int THREADS, int MIN_CTAS, bool STAGE>
 static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, int nsm, cudaStream_t s)
 {
-	using Shared = IngestSharedT<THREADS>;
+	using Shared = IngestSharedT<THREADS, STAGE>;
 	static bool attr_set = false;
-	if (!attr_set) { cudaFuncSetAttribute(ingest_kernel<THREADS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)); attr_set = true; }
+	if (!attr_set) { cudaFuncSetAttribute(ingest_kernel<THREADS, MIN_CTAS, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)); attr_set = true; }
 	const uint64_t want = (n + Shared::INGEST_TILE - 1) / Shared::INGEST_TILE;
 	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * MIN_CTAS ? want : (uint64_t)nsm * MIN_CTAS);
-	ingest_kernel<THREADS, MIN_CTAS><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys);
+	ingest_kernel<THREADS, MIN_CTAS, STAGE><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys);
 }
 
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s)
@@ -841,12 +899,13 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-	// CTA shape: 128 threads x 8 CTAs/SM keeps more independent barrier groups per SM than 256 x 4 (the tile pipeline has three
-	// block barriers per tile); GYSK_INGEST_VARIANT=256 selects the wide shape for A/B runs
-	static const int variant = []{ const char *v = getenv("GYSK_INGEST_VARIANT"); return v ? atoi(v) : 128; }();
-	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, sizeof(unsigned long long), s);	// the key cursor of this batch
-	if (variant == 256) launch_ingest_variant<256, 4>(st, d_ev, n, d_keys, nsm, s);
-	else launch_ingest_variant<128, 8>(st, d_ev, n, d_keys, nsm, s);
+	// variants for A/B runs (GYSK_INGEST_VARIANT): 256 = 256 thr x 4 CTAs/SM, events by direct streaming loads (measured best so
+	// far); 2563 = same shape, next tile staged by TMA bulk copy (3 CTAs/SM: +32 KB smem); 128 = 128 thr x 8 CTAs/SM
+	static const int variant = []{ const char *v = getenv("GYSK_INGEST_VARIANT"); return v ? atoi(v) : 256; }();
+	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, 2 * sizeof(unsigned long long), s);	// key cursor + max RESP msec of this batch
+	if (variant == 2563) launch_ingest_variant<256, 3, true>(st, d_ev, n, d_keys, nsm, s);
+	else if (variant == 128) launch_ingest_variant<128, 8, false>(st, d_ev, n, d_keys, nsm, s);
+	else launch_ingest_variant<256, 4, false>(st, d_ev, n, d_keys, nsm, s);
 	return 1;
 }
 
@@ -860,12 +919,12 @@ static int launch_exclusive_scan(uint32_t *d_data, uint32_t len, uint32_t *d_blo
 }
 
 // stable LSD radix sort of tmp.keys_a (n_upper >= *d_n keys) on key bits [bit_lo, bit_hi); result in bufs[*which]
-int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s)
+int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s)
 {
 	int launches = 0;
 	const uint32_t ntiles = div_up(n_upper, SORT_TILE);
 	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
-	int w = 0;
+	int w = start;
 
 	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
 		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], n_upper, d_n, shift, tmp.tile_hist, ntiles);
@@ -878,17 +937,22 @@ int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long
 	return launches;
 }
 
-// sort the (slot, usec) keys produced by ingest, then fold every touched service's new samples into its digest
-int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t max_svcs, cudaStream_t s)
+int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s)
 {
-	if (!n) return 0;
+	return launch_radix_sort_from(tmp, 0, n_upper, d_n, bit_lo, bit_hi, which, s);
+}
+
+// sort the (slot, usec) keys produced by ingest, then fold every touched service's new samples into its digest
+int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t nslots, int value_bits, cudaStream_t s)
+{
+	if (!n) return 0;		// n = number of RESP keys of this batch (read back by the host), nslots = services registered so far
 	int launches = 0;
 	const uint32_t ntiles = div_up(n, SORT_TILE);
 	unsigned long long *d_nkeys = st.counters + CTR_NKEYS, *d_ntouched = st.counters + CTR_NTOUCHED;
 
+	// radix passes cover only the bits that can differ: usec bits of the batch maximum, then the slot bits in use
 	uint32_t slot_bits = 1;
-	while (slot_bits < 32 && (1ull << slot_bits) < max_svcs) slot_bits++;
-	const int total_bits = VALUE_BITS + (int)slot_bits;
+	while (slot_bits < 32 && (1ull << slot_bits) < nslots) slot_bits++;
 
 	const unsigned long long *src = tmp.keys_a;
 	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
@@ -896,7 +960,8 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, u
 
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
 
-	launches += launch_radix_sort(tmp, n, d_nkeys, 0, total_bits, &which, s);
+	launches += launch_radix_sort_from(tmp, 0, n, d_nkeys, 0, value_bits, &which, s);
+	launches += launch_radix_sort_from(tmp, which, n, d_nkeys, VALUE_BITS, VALUE_BITS + (int)slot_bits, &which, s);
 	src = bufs[which];
 
 	td_segments_kernel<<<div_up(n, 256), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);

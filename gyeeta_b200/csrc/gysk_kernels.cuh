@@ -18,6 +18,7 @@ struct DevState
 	unsigned long long	*slot_id;				// [max_svcs] slot -> glob_id (written by the inserter)
 	uint32_t		*slot_host;				// [max_svcs] slot -> host_idx of the first event seen
 	unsigned long long	*conn_all_cnt, *conn_all_kb;
+	uint32_t		*bm_cur, *bm_last;			// [max_svcs][16] CONN_BITMAP transposed: per bucket a mask over (client port & 31)
 	uint8_t			*hll;					// [max_svcs][1 << hll_p]
 	Centroid		*td_cent;				// [max_svcs][TD_CAP]
 	TdHead			*td_head;				// [max_svcs]
@@ -53,6 +54,7 @@ struct SvcRaw
 	HistCell		cur[HIST_CELLS], last[HIST_CELLS], all[HIST_CELLS];
 	HistCell		lvl[2][HIST_CELLS];			// sums of the live slots of the rolling levels
 	unsigned long long	conn_cur, conn_last, conn_all_cnt, conn_all_kb;
+	uint32_t		bm_cur[HIST_CELLS], bm_last[HIST_CELLS];
 	uint32_t		hll_hist[64];
 	TdHead			td;
 	Centroid		cent[TD_CAP];
@@ -75,7 +77,7 @@ static constexpr int VALUE_BITS = 30;		// RESP usec < 2^30 (msec <= 1e6 is enfor
 int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks, cudaStream_t s);
 int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_t n, int is_task, cudaStream_t s);
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s);
-int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t max_svcs, cudaStream_t s);
+int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t nkeys, uint32_t nslots, int value_bits, cudaStream_t s);
 int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s);
 int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int metric, int host_filter, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
 int launch_flush(const DevState &st, uint32_t max_svcs, HistCell *ring_plane0, HistCell *ring_plane1, cudaStream_t s);

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(128) gather_logical_kernel(const int32_t *__re
 		if (lane == HIST_MAX_CELL) { a.sum = l_hmax[2 * l]; b.sum = l_hmax[2 * l + 1]; }
 		o.last[lane] = a; o.all[lane] = b; o.cur[lane] = HistCell {0, 0};
 		o.lvl[0][lane] = HistCell {0, 0}; o.lvl[1][lane] = HistCell {0, 0};
+		o.bm_cur[lane] = 0; o.bm_last[lane] = 0;
 	}
 	if (lane == 0) {
 		o.conn_cur = 0;

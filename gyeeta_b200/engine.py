@@ -105,6 +105,7 @@ def load_library(path=None):
         "gysk_export_hist": (i32, [vp, u64, i32, vp, vp, vp]),
         "gysk_export_task_hist": (i32, [vp, u64, i32, vp, vp, vp]),
         "gysk_export_hll": (i32, [vp, u64, vp]),
+        "gysk_export_conn_bitmap": (i32, [vp, u64, i32, vp, vp]),
         "gysk_export_tdigest": (i32, [vp, u64, vp, vp, u32, vp, vp, vp]),
         "gysk_query_quantiles": (i32, [vp, u64, vp, u32, vp]),
         "gysk_export_cms": (i32, [vp, i32, vp]),
@@ -271,6 +272,15 @@ class Engine:
             return None
         self._chk(rc)
         return regs
+
+    def export_conn_bitmap(self, id_, last_window=False):
+        masks = np.zeros(15, dtype=np.uint32)
+        cnt = np.zeros(15, dtype=np.uint8)
+        rc = self.L.gysk_export_conn_bitmap(self.h, int(id_), int(last_window), _p(masks), _p(cnt))
+        if rc == -2:
+            return None
+        self._chk(rc)
+        return masks, cnt
 
     def export_tdigest(self, id_):
         means = np.zeros(TD_CAP, dtype=np.float64)

@@ -262,6 +262,10 @@ int		gysk_query_host_summary(gysk_engine *e, uint32_t host_idx, gysk_host_summar
 int		gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial out[GYSK_HIST_MAX_BUCKETS],
 				uint64_t *total_count, int64_t *max_val);
 int		gysk_export_hll(gysk_engine *e, uint64_t glob_id, uint8_t *regs /* 1 << hll_p bytes */);
+/* TCP_LISTENER::CONN_BITMAP (common/gy_socket_stat.h:390-455): per response bucket a 32-bit mask over (client port & 0x1F) and its
+ * popcount = get_conn_breakup(); bit index = flow_key & 0x1F */
+int		gysk_export_conn_bitmap(gysk_engine *e, uint64_t glob_id, int last_window, uint32_t masks[GYSK_HIST_MAX_BUCKETS],
+				uint8_t nconn_arr[GYSK_HIST_MAX_BUCKETS]);
 int		gysk_export_tdigest(gysk_engine *e, uint64_t glob_id, double *means, uint64_t *weights, uint32_t cap, uint32_t *n,
 				double *min_val, double *max_val);
 int		gysk_query_quantiles(gysk_engine *e, uint64_t glob_id, const double *qs, uint32_t nq, double *out);

@@ -521,6 +521,7 @@ typedef struct svc_state
 	gyo_hist	cur, last, all;		/* RESP_TIME_HASH, T = int64 */
 	gyo_hist	ring[GYO_NLEVELS][GYO_NSLOTS];	/* 300 s and 432000 s levels, 10 slots each */
 	uint64_t	conn_cur, conn_last;	/* packed {count, kbytes} like a CMS cell */
+	uint32_t	bm_cur[16], bm_last[16];	/* CONN_BITMAP transposed: per response bucket a mask over (client port & 31) */
 	uint64_t	conn_all_cnt, conn_all_kb;
 	uint8_t		*hll;
 	gyo_tdigest	td;
@@ -668,7 +669,11 @@ int gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n)
 			if (ms > 1000000u) { e->n_drop++; break; }
 			svc_state *s = get_svc(e, p->svc_id, autoreg);
 			if (!s) { e->n_drop++; break; }
-			gyo_hist_add(&s->cur, (int64_t)ms);
+			{
+				/* TCP_LISTENER::CONN_BITMAP::add_response, common/gy_socket_stat.h:403-410: respmap_[cli_port & 0x1F].set(bucket) */
+				int b = gyo_hist_add(&s->cur, (int64_t)ms);
+				s->bm_cur[b] |= 1u << (uint32_t)(p->flow_key & 0x1F);
+			}
 			if (s->npend == 0) e->touched[e->ntouched++] = (uint32_t)(s - e->svcs);
 			if (s->npend == s->cappend) {
 				s->cappend = s->cappend ? s->cappend * 2 : 16;
@@ -751,6 +756,7 @@ void gyo_flush(gyo_engine *e, uint32_t tsec)
 			gyo_hist_merge(&s->ring[l][slot[l]], &s->cur);
 		}
 		gyo_hist_init(&s->cur, GYO_CLS_RESP_TIME, GYO_T_INT64);
+		memcpy(s->bm_last, s->bm_cur, sizeof(s->bm_cur)); memset(s->bm_cur, 0, sizeof(s->bm_cur));	/* CONN_BITMAP::clear every 5 s, :436 */
 		s->conn_last = s->conn_cur;
 		s->conn_all_cnt += (uint32_t)s->conn_cur;
 		s->conn_all_kb += s->conn_cur >> 32;
@@ -821,6 +827,16 @@ int gyo_export_conn(gyo_engine *e, uint64_t id, uint64_t *cur, uint64_t *last, u
 	if (slot < 0) return -2;
 	*cur = e->svcs[slot].conn_cur; *last = e->svcs[slot].conn_last;
 	*all_cnt = e->svcs[slot].conn_all_cnt; *all_kb = e->svcs[slot].conn_all_kb;
+	return 0;
+}
+
+/* CONN_BITMAP::get_conn_breakup, common/gy_socket_stat.h:412-433: per bucket the number of port-hash slots that saw it */
+int gyo_export_conn_bitmap(gyo_engine *e, uint64_t id, int last_window, uint32_t *masks15, uint8_t *nconn15)
+{
+	int slot = idmap_find(&e->smap, id, 0, 0);
+	if (slot < 0) return -2;
+	const uint32_t *bm = last_window ? e->svcs[slot].bm_last : e->svcs[slot].bm_cur;
+	for (int j = 0; j < 15; ++j) { masks15[j] = bm[j]; nconn15[j] = (uint8_t)__builtin_popcount(bm[j]); }
 	return 0;
 }
 

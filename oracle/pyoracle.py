@@ -93,6 +93,7 @@ def lib():
         L.gyo_export_hll.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.gyo_export_tdigest.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.gyo_export_conn.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
+        L.gyo_export_conn_bitmap.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         L.gyo_cms_table.restype = C.c_void_p
         L.gyo_cms_table.argtypes = [C.c_void_p, C.c_int]
         L.gyo_counters.argtypes = [C.c_void_p, C.c_void_p]
@@ -197,6 +198,12 @@ class OracleEngine:
         v = [C.c_uint64() for _ in range(4)]
         rc = self.L.gyo_export_conn(self.h, int(id_), *[C.byref(x) for x in v])
         return None if rc else tuple(x.value for x in v)
+
+    def export_conn_bitmap(self, id_, last_window=False):
+        masks = np.zeros(15, dtype=np.uint32)
+        cnt = np.zeros(15, dtype=np.uint8)
+        rc = self.L.gyo_export_conn_bitmap(self.h, int(id_), int(last_window), _p(masks), _p(cnt))
+        return None if rc else (masks, cnt)
 
     def cms(self, last_window=False):
         n = self.cfg["cms_depth"] << self.cfg["cms_log2_width"]

@@ -93,6 +93,9 @@ def test_mixed_stream_bit_exact(nsvc, n, batch):
         nresp += assert_hist_equal(eng, orc, int(id_), ge.HIST_RESP_CUR)
         a, b = eng.export_hll(int(id_)), orc.export_hll(int(id_))
         assert np.array_equal(a, b), hex(int(id_))
+        # CONN_BITMAP (gy_socket_stat.h:390-455): masks and get_conn_breakup() counts
+        bm_g, bm_o = eng.export_conn_bitmap(int(id_)), orc.export_conn_bitmap(int(id_))
+        assert np.array_equal(bm_g[0], bm_o[0]) and np.array_equal(bm_g[1], bm_o[1]), hex(int(id_))
         assert eng.L.gysk_hll_estimate(a.ctypes.data_as(C.c_void_p), 12) == po.lib().gyo_hll_estimate(po._p(b), 12)
     assert nresp > 0
     for id_ in tasks[:100]:
@@ -123,6 +126,10 @@ def test_flush_window_roll_and_summary():
         for id_ in ids[:40]:
             for which in (ge.HIST_RESP_CUR, ge.HIST_RESP_LAST, ge.HIST_RESP_ALL):
                 assert_hist_equal(eng, orc, int(id_), which)
+            for lw in (False, True):
+                g, o = eng.export_conn_bitmap(int(id_), lw), orc.export_conn_bitmap(int(id_), lw)
+                assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1])
+            assert not eng.export_conn_bitmap(int(id_))[0].any()          # cleared with the window
     R = po.ref()
     summ = eng.query_svcs(ids[:40])
     pcts = np.array([95, 99, 25], dtype=np.float32)
