@@ -399,9 +399,17 @@ static constexpr int RS_WARPS = RS_THREADS / 32;
 static constexpr int RS_ROUNDS = SORT_TILE / RS_THREADS;	// 16 keys per thread
 static constexpr int RADIX = 256;
 
+// one radix pass sorts on an 8-bit digit made of up to two bit fields of the key, so that the unused bits between the usec field
+// and the slot field of a key never cost a pass: digit = ((k >> s1) & m1) | (((k >> s2) & m2) << b1)
+struct DigitSpec { int s1, b1, s2, b2; };
+__device__ __forceinline__ uint32_t key_digit(unsigned long long k, const DigitSpec &D)
+{
+	return ((uint32_t)(k >> D.s1) & ((1u << D.b1) - 1u)) | (((uint32_t)(k >> D.s2) & ((1u << D.b2) - 1u)) << D.b1);
+}
+
 // per-tile digit histogram -> tile_hist[digit * ntiles + tile]
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long *__restrict__ keys, uint64_t n_host,
-		const unsigned long long *__restrict__ d_n, int shift, uint32_t *__restrict__ tile_hist, uint32_t ntiles)
+		const unsigned long long *__restrict__ d_n, DigitSpec D, uint32_t *__restrict__ tile_hist, uint32_t ntiles)
 {
 	__shared__ uint32_t hist[RADIX];
 	const uint64_t n = d_n ? *d_n : n_host;
@@ -416,7 +424,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long
 		const uint64_t i = base + (uint64_t)r * RS_THREADS + threadIdx.x;
 		if (i < n) {
 			const unsigned long long k = keys[i];
-			if (k != KEY_SENTINEL) atomicAdd(&hist[(uint32_t)(k >> shift) & 0xFFu], 1u);
+			if (k != KEY_SENTINEL) atomicAdd(&hist[key_digit(k, D)], 1u);
 		}
 	}
 	__syncthreads();
@@ -504,7 +512,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t *__re
 // scatter one tile to its stable positions. Thread t of warp w holds keys w*512 + r*32 + lane (r = 0..15), i.e.
 // ascending input order is (warp, round, lane); ranks come from match_any groups so equal digits keep that order.
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
-		uint64_t n_host, const unsigned long long *__restrict__ d_n, int shift, const uint32_t *__restrict__ tile_offs, uint32_t ntiles)
+		uint64_t n_host, const unsigned long long *__restrict__ d_n, DigitSpec D, const uint32_t *__restrict__ tile_offs, uint32_t ntiles)
 {
 	__shared__ uint32_t whist[RS_WARPS][RADIX];
 	const uint64_t n = d_n ? *d_n : n_host;
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
 #pragma unroll
 	for (int r = 0; r < RS_ROUNDS; ++r) {
 		const bool valid = k[r] != KEY_SENTINEL;
-		const uint32_t d = valid ? ((uint32_t)(k[r] >> shift) & 0xFFu) : (0x100u + lane);
+		const uint32_t d = valid ? key_digit(k[r], D) : (0x100u + lane);
 		const uint32_t m = __match_any_sync(0xffffffffu, d);
 		const int leader = __ffs(m) - 1;
 		uint32_t old = 0;
@@ -556,7 +564,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
 	// phase B: position = warp base of the digit + rank
 #pragma unroll
 	for (int r = 0; r < RS_ROUNDS; ++r) {
-		if (k[r] != KEY_SENTINEL) out[whist[wid][(uint32_t)(k[r] >> shift) & 0xFFu] + rank[r]] = k[r];
+		if (k[r] != KEY_SENTINEL) out[whist[wid][key_digit(k[r], D)] + rank[r]] = k[r];
 	}
 }
 
@@ -918,18 +926,31 @@ static int launch_exclusive_scan(uint32_t *d_data, uint32_t len, uint32_t *d_blo
 	return 3;
 }
 
-// stable LSD radix sort of tmp.keys_a (n_upper >= *d_n keys) on key bits [bit_lo, bit_hi); result in bufs[*which]
-int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s)
+// stable LSD radix sort of bufs[start] (n_upper >= *d_n keys) on the significant key bits [lo1, hi1) then [lo2, hi2) (lo2 >= hi1;
+// pass hi2 <= lo2 for a single range): the significant bits are cut into 8-bit digits in order, a digit may straddle the gap.
+// Result in bufs[*which].
+int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_upper, const unsigned long long *d_n, int lo1, int hi1, int lo2, int hi2,
+		int *which, cudaStream_t s)
 {
 	int launches = 0;
 	const uint32_t ntiles = div_up(n_upper, SORT_TILE);
 	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
 	int w = start;
+	int p1 = lo1, p2 = lo2;			// next unsorted bit of each range
 
-	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
-		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], n_upper, d_n, shift, tmp.tile_hist, ntiles);
+	if (hi2 < lo2) hi2 = lo2;
+	while (p1 < hi1 || p2 < hi2) {
+		DigitSpec D {0, 0, 0, 0};
+		int need = 8;
+		if (p1 < hi1) { D.s1 = p1; D.b1 = hi1 - p1 < need ? hi1 - p1 : need; p1 += D.b1; need -= D.b1; }
+		if (need && p1 >= hi1 && p2 < hi2) {
+			const int take = hi2 - p2 < need ? hi2 - p2 : need;
+			if (D.b1) { D.s2 = p2; D.b2 = take; } else { D.s1 = p2; D.b1 = take; }
+			p2 += take;
+		}
+		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], n_upper, d_n, D, tmp.tile_hist, ntiles);
 		launches += 1 + launch_exclusive_scan(tmp.tile_hist, RADIX * ntiles, tmp.scan_tmp, nullptr, s);
-		rs_scatter_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], bufs[w ^ 1], n_upper, d_n, shift, tmp.tile_hist, ntiles);
+		rs_scatter_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], bufs[w ^ 1], n_upper, d_n, D, tmp.tile_hist, ntiles);
 		launches++;
 		w ^= 1;
 	}
@@ -939,7 +960,7 @@ int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_upper, con
 
 int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s)
 {
-	return launch_radix_sort_from(tmp, 0, n_upper, d_n, bit_lo, bit_hi, which, s);
+	return launch_radix_sort_from(tmp, 0, n_upper, d_n, bit_lo, bit_hi, bit_hi, bit_hi, which, s);
 }
 
 // sort the (slot, usec) keys produced by ingest, then fold every touched service's new samples into its digest
@@ -960,8 +981,7 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, u
 
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
 
-	launches += launch_radix_sort_from(tmp, 0, n, d_nkeys, 0, value_bits, &which, s);
-	launches += launch_radix_sort_from(tmp, which, n, d_nkeys, VALUE_BITS, VALUE_BITS + (int)slot_bits, &which, s);
+	launches += launch_radix_sort_from(tmp, 0, n, d_nkeys, 0, value_bits, VALUE_BITS, VALUE_BITS + (int)slot_bits, &which, s);
 	src = bufs[which];
 
 	td_segments_kernel<<<div_up(n, 256), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
