@@ -74,7 +74,7 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
 		const uint32_t nslots = std::min<uint32_t>((uint32_t)e->h_counters[2], e->cfg.max_svcs);
 		int value_bits = 1;
 		while (value_bits < VALUE_BITS && (1ull << value_bits) <= max_us) value_bits++;
-		e->kernel_launches += launch_tdigest_update(e->st, e->tmp, nkeys, nslots, value_bits, e->stream);
+		e->kernel_launches += launch_tdigest_update(e->st, e->tmp, n, nkeys, nslots, value_bits, e->stream);
 	}
 	if (pe) CU(e, cudaEventRecord(pe[2], e->stream));
 	e->batches++;

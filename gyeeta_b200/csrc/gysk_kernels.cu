@@ -890,6 +890,192 @@ int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_
 	return 1;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// warp-autonomous variant of the tile pipeline: every warp owns a 128-event tile, its records and its three queues, so
+// the two phases need only __syncwarp — no block barrier, no global key cursor. A warp writes its RESP sort keys to the 128
+// key slots that belong to its events (keys first, sentinels behind); the first radix pass compacts the sentinels away.
+// The hot-cell table stays shared by the CTA (shared-memory atomics).
+// ---------------------------------------------------------------------------------------------------
+static constexpr int WI_WARPS = 8;
+static constexpr int WI_EPT = 4;
+static constexpr int WI_TILE = 32 * WI_EPT;		// events per warp tile
+
+struct WarpIngestShared
+{
+	using HotTable = HotTableT<10>;
+	HotTable	hot;
+	IngestRec	rec[WI_WARPS][WI_TILE];
+	uint8_t		q_resp[WI_WARPS][WI_TILE], q_tcp[WI_WARPS][WI_TILE], q_task[WI_WARPS][WI_TILE];
+};
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(WI_WARPS * 32, MIN_CTAS) ingest_warp_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
+		unsigned long long *__restrict__ keys)
+{
+	__shared__ WarpIngestShared S;
+	unsigned long long c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	const uint64_t ntiles = (n + WI_TILE - 1) / WI_TILE;
+	uint32_t max_ms = 0;
+
+	for (int i = threadIdx.x; i < WarpIngestShared::HotTable::N; i += WI_WARPS * 32) {
+		S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; S.hot.bits[i] = 0;
+	}
+	__syncthreads();
+
+	IngestRec *rec = S.rec[wid];
+	uint8_t *q_resp = S.q_resp[wid], *q_tcp = S.q_tcp[wid], *q_task = S.q_task[wid];
+
+	for (uint64_t tile = (uint64_t)blockIdx.x * WI_WARPS + wid; tile < ntiles; tile += (uint64_t)gridDim.x * WI_WARPS) {
+		const uint64_t tbase = tile * WI_TILE;
+		uint32_t n_resp = 0, n_tcp = 0, n_task = 0;		// warp-uniform queue lengths
+
+		// ---------------- phase 1: decode + lookup + enqueue (all lanes converged) ----------------
+		uint4 ra[WI_EPT], rb[WI_EPT];
+#pragma unroll
+		for (int k = 0; k < WI_EPT; ++k) {
+			const uint64_t i = tbase + (uint64_t)k * 32 + lane;
+			if (i < n) {
+				ra[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i));		// streamed once: evict-first
+				rb[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i) + 1);
+			}
+			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }
+		}
+#pragma unroll
+		for (int k = 0; k < WI_EPT; ++k) {
+			const unsigned long long svc_id = ((unsigned long long)ra[k].y << 32) | ra[k].x;
+			const unsigned long long flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
+			const uint32_t value = rb[k].x, host_idx = rb[k].y;
+			const uint32_t type = rb[k].w & 0xFFFFu;
+			const bool pad = tbase + (uint64_t)k * 32 + lane >= n;
+			const bool is_resp = type == GYSK_EV_RESP, is_task = type == GYSK_EV_TASK;
+			const bool is_tcp = type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER;
+			// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
+			// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
+			const uint32_t ms = value / 1000u;
+			int slot = -1;
+			bool mine = !pad;
+
+			if (mine && st.world > 1 && (host_idx % st.world) != st.rank) { c_foreign++; mine = false; }
+			if (mine) {
+				c_in++;
+				if (svc_id != 0 && (is_tcp || is_task || (is_resp && ms <= 1000000u)))
+					slot = table_lookup(is_task ? st.task_tbl : st.svc_tbl, svc_id, st.auto_register, host_idx);
+				if (slot < 0) c_drop++;
+				else if (is_resp) c_resp++;
+				else if (is_tcp) c_tcp++;
+				else c_task++;
+			}
+			const uint8_t pos = (uint8_t)(k * 32 + lane);
+			if (slot >= 0) { IngestRec r; r.slot = (uint32_t)slot; r.value = value; r.flow_key = flow_key; rec[pos] = r; }
+			const uint32_t m_resp = __ballot_sync(0xffffffffu, slot >= 0 && is_resp);
+			const uint32_t m_tcp = __ballot_sync(0xffffffffu, slot >= 0 && is_tcp);
+			const uint32_t m_task = __ballot_sync(0xffffffffu, slot >= 0 && is_task);
+			if (slot >= 0) {
+				if (is_resp) q_resp[n_resp + __popc(m_resp & lt_mask)] = pos;
+				else if (is_tcp) q_tcp[n_tcp + __popc(m_tcp & lt_mask)] = pos;
+				else q_task[n_task + __popc(m_task & lt_mask)] = pos;
+			}
+			n_resp += __popc(m_resp); n_tcp += __popc(m_tcp); n_task += __popc(m_task);
+		}
+		__syncwarp();
+
+		// ---------------- phase 2a: TCP — count-min rows, one (event, row) pair per lane ----------------
+		{
+			const uint32_t npairs = n_tcp * st.cms_depth;
+			for (uint32_t p = lane; p < npairs; p += 32) {
+				const uint32_t e = p / st.cms_depth, row = p - e * st.cms_depth;
+				const IngestRec r = rec[q_tcp[e]];
+				red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index(r.flow_key, row, st.cms_wmask), cms_increment(r.value));
+			}
+			for (uint32_t base = 0; base < n_tcp; base += 32) {
+				const uint32_t q = base + lane;
+				const bool act = q < n_tcp;
+				uint32_t cell = 0; int kb = 0;
+				if (act) {
+					const IngestRec r = rec[q_tcp[q]];
+					uint32_t idx, rank;
+					hll_idx_rank(r.flow_key, st.hll_p, idx, rank);
+					hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
+					cell = r.slot * HIST_CELLS + HIST_MAX_CELL;
+					kb = (int)(r.value >> 10);
+				}
+				cell_add(st, S.hot, act, cell, kb);
+			}
+		}
+		// ---------------- phase 2b: TASK — one (event, histogram) pair per lane ----------------
+		{
+			const uint32_t ntrip = n_task * 3u;
+			for (uint32_t base = 0; base < ntrip; base += 32) {
+				const uint32_t p = base + lane;
+				const bool act = p < ntrip;
+				uint32_t cell = 0; int d = 0;
+				if (act) {
+					const uint32_t e = p / 3u, h = p - e * 3u;
+					const IngestRec r = rec[q_task[e]];
+					d = h == 0 ? (int)r.value : (h == 1 ? (int)(uint32_t)r.flow_key : (int)(uint32_t)(r.flow_key >> 32));
+					const uint32_t b = h == 0 ? (uint32_t)bucket_hash_1_3000(d) : (uint32_t)bucket_duration(d);
+					cell = CELL_TASK | (r.slot * 3u * HIST_CELLS + h * HIST_CELLS + b);
+				}
+				cell_add(st, S.hot, act, cell, d);
+			}
+		}
+		// ---------------- phase 2c: RESP — histogram cell + CONN_BITMAP bit + sort key ----------------
+		for (uint32_t base = 0; base < WI_TILE; base += 32) {
+			const uint32_t q = base + lane;
+			const bool act = q < n_resp;
+			uint32_t cell = 0, bit = 0; int ms = 0;
+			unsigned long long key = KEY_SENTINEL;
+			if (act) {
+				const IngestRec r = rec[q_resp[q]];
+				bit = 1u << ((uint32_t)r.flow_key & 0x1Fu);
+				ms = (int)(r.value / 1000u);
+				cell = r.slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
+				key = ((unsigned long long)r.slot << VALUE_BITS) | r.value;
+				max_ms = max(max_ms, (uint32_t)ms);
+			}
+			if (tbase + q < n) __stcs(keys + tbase + q, key);		// the tile's key slots: RESP keys, then sentinels
+			if (base < n_resp) cell_add(st, S.hot, act, cell, ms, bit);
+		}
+		__syncwarp();		// rec / queues are rewritten by the next tile
+	}
+
+	__syncthreads();
+	for (int i = threadIdx.x; i < WarpIngestShared::HotTable::N; i += WI_WARPS * 32) {
+		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i], S.hot.bits[i]);
+	}
+
+	max_ms = __reduce_max_sync(0xffffffffu, max_ms);
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) {
+		c_in += __shfl_down_sync(0xffffffffu, c_in, off);
+		c_drop += __shfl_down_sync(0xffffffffu, c_drop, off);
+		c_resp += __shfl_down_sync(0xffffffffu, c_resp, off);
+		c_tcp += __shfl_down_sync(0xffffffffu, c_tcp, off);
+		c_task += __shfl_down_sync(0xffffffffu, c_task, off);
+		c_foreign += __shfl_down_sync(0xffffffffu, c_foreign, off);
+	}
+	if (lane == 0) {
+		if (c_in) atomicAdd(st.counters + CTR_IN, c_in);
+		if (c_drop) atomicAdd(st.counters + CTR_DROPPED, c_drop);
+		if (c_resp) { atomicAdd(st.counters + CTR_RESP, c_resp); atomicAdd(st.counters + CTR_NKEYS, c_resp); }
+		if (c_tcp) atomicAdd(st.counters + CTR_TCP, c_tcp);
+		if (c_task) atomicAdd(st.counters + CTR_TASK, c_task);
+		if (c_foreign) atomicAdd(st.counters + CTR_FOREIGN, c_foreign);
+		if (max_ms) atomicMax(st.counters + CTR_MAXVAL, (unsigned long long)max_ms);
+	}
+}
+
+// 0 (default) = warp-autonomous tiles (keys left in event order with sentinels); 256 / 128 / 2563 = CTA tile pipeline shapes
+static int ingest_variant()
+{
+	static const int v = []{ const char *e = getenv("GYSK_INGEST_VARIANT"); return e ? atoi(e) : 0; }();
+	return v;
+}
+
+bool ingest_keys_compact() { return ingest_variant() != 0 && ingest_variant() != 4; }
+
 template <int THREADS, int MIN_CTAS, bool STAGE>
 static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, int nsm, cudaStream_t s)
 {
@@ -909,11 +1095,18 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 	// variants for A/B runs (GYSK_INGEST_VARIANT): 256 = 256 thr x 4 CTAs/SM, events by direct streaming loads (measured best so
 	// far); 2563 = same shape, next tile staged by TMA bulk copy (3 CTAs/SM: +32 KB smem); 128 = 128 thr x 8 CTAs/SM
-	static const int variant = []{ const char *v = getenv("GYSK_INGEST_VARIANT"); return v ? atoi(v) : 256; }();
+	static const int variant = ingest_variant();
 	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, 2 * sizeof(unsigned long long), s);	// key cursor + max RESP msec of this batch
 	if (variant == 2563) launch_ingest_variant<256, 3, true>(st, d_ev, n, d_keys, nsm, s);
 	else if (variant == 128) launch_ingest_variant<128, 8, false>(st, d_ev, n, d_keys, nsm, s);
-	else launch_ingest_variant<256, 4, false>(st, d_ev, n, d_keys, nsm, s);
+	else if (variant == 256) launch_ingest_variant<256, 4, false>(st, d_ev, n, d_keys, nsm, s);
+	else {
+		const uint64_t want = (n + (uint64_t)WI_TILE * WI_WARPS - 1) / ((uint64_t)WI_TILE * WI_WARPS);
+		const int per_sm = variant == 4 ? 4 : 5;			// 4: 64 registers, no spills; 5: 48 registers, small spills
+		const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * per_sm ? want : (uint64_t)nsm * per_sm);
+		if (per_sm == 4) ingest_warp_kernel<4><<<grid, WI_WARPS * 32, 0, s>>>(st, d_ev, n, d_keys);
+		else ingest_warp_kernel<5><<<grid, WI_WARPS * 32, 0, s>>>(st, d_ev, n, d_keys);
+	}
 	return 1;
 }
 
@@ -929,11 +1122,11 @@ static int launch_exclusive_scan(uint32_t *d_data, uint32_t len, uint32_t *d_blo
 // stable LSD radix sort of bufs[start] (n_upper >= *d_n keys) on the significant key bits [lo1, hi1) then [lo2, hi2) (lo2 >= hi1;
 // pass hi2 <= lo2 for a single range): the significant bits are cut into 8-bit digits in order, a digit may straddle the gap.
 // Result in bufs[*which].
-int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_upper, const unsigned long long *d_n, int lo1, int hi1, int lo2, int hi2,
+int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_first, uint64_t n_upper, const unsigned long long *d_n, int lo1, int hi1, int lo2, int hi2,
 		int *which, cudaStream_t s)
 {
 	int launches = 0;
-	const uint32_t ntiles = div_up(n_upper, SORT_TILE);
+	bool first = true;
 	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
 	int w = start;
 	int p1 = lo1, p2 = lo2;			// next unsorted bit of each range
@@ -948,11 +1141,15 @@ int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_upper, con
 			if (D.b1) { D.s2 = p2; D.b2 = take; } else { D.s1 = p2; D.b1 = take; }
 			p2 += take;
 		}
-		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], n_upper, d_n, D, tmp.tile_hist, ntiles);
+		// the first pass may run over n_first >= n_upper slots holding sentinels (skipped, so its output is compact)
+		const uint64_t nn = first ? n_first : n_upper;
+		const unsigned long long *dn = (first && n_first != n_upper) ? nullptr : d_n;
+		const uint32_t ntiles = div_up(nn, SORT_TILE);
+		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], nn, dn, D, tmp.tile_hist, ntiles);
 		launches += 1 + launch_exclusive_scan(tmp.tile_hist, RADIX * ntiles, tmp.scan_tmp, nullptr, s);
-		rs_scatter_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], bufs[w ^ 1], n_upper, d_n, D, tmp.tile_hist, ntiles);
+		rs_scatter_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], bufs[w ^ 1], nn, dn, D, tmp.tile_hist, ntiles);
 		launches++;
-		w ^= 1;
+		w ^= 1; first = false;
 	}
 	*which = w;
 	return launches;
@@ -960,11 +1157,11 @@ int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_upper, con
 
 int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s)
 {
-	return launch_radix_sort_from(tmp, 0, n_upper, d_n, bit_lo, bit_hi, bit_hi, bit_hi, which, s);
+	return launch_radix_sort_from(tmp, 0, n_upper, n_upper, d_n, bit_lo, bit_hi, bit_hi, bit_hi, which, s);
 }
 
 // sort the (slot, usec) keys produced by ingest, then fold every touched service's new samples into its digest
-int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t nslots, int value_bits, cudaStream_t s)
+int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_events, uint64_t n, uint32_t nslots, int value_bits, cudaStream_t s)
 {
 	if (!n) return 0;		// n = number of RESP keys of this batch (read back by the host), nslots = services registered so far
 	int launches = 0;
@@ -981,7 +1178,9 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, u
 
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
 
-	launches += launch_radix_sort_from(tmp, 0, n, d_nkeys, 0, value_bits, VALUE_BITS, VALUE_BITS + (int)slot_bits, &which, s);
+	// with the warp-autonomous ingest the keys sit at their events' positions with sentinels in between: the first pass reads
+	// n_events slots and compacts, the later passes run over the n keys
+	launches += launch_radix_sort_from(tmp, 0, ingest_keys_compact() ? n : n_events, n, d_nkeys, 0, value_bits, VALUE_BITS, VALUE_BITS + (int)slot_bits, &which, s);
 	src = bufs[which];
 
 	td_segments_kernel<<<div_up(n, 256), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);

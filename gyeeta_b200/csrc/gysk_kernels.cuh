@@ -77,7 +77,7 @@ static constexpr int VALUE_BITS = 30;		// RESP usec < 2^30 (msec <= 1e6 is enfor
 int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks, cudaStream_t s);
 int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_t n, int is_task, cudaStream_t s);
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s);
-int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t nkeys, uint32_t nslots, int value_bits, cudaStream_t s);
+int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_events, uint64_t nkeys, uint32_t nslots, int value_bits, cudaStream_t s);
 int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s);
 int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int metric, int host_filter, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
 int launch_flush(const DevState &st, uint32_t max_svcs, HistCell *ring_plane0, HistCell *ring_plane1, cudaStream_t s);
