@@ -627,70 +627,91 @@ __global__ void td_plan_kernel(TdParams P, const uint32_t *__restrict__ seg_star
 // (2) sums: one thread per sorted sample. cluster id = position of the sample's rank in the service's bounds; runs of equal
 // (service, cluster) are contiguous in the sorted order, so a warp reduces them with match.any groups and issues one
 // 64-bit RED per group. Skew-immune: a hot service's samples are spread over as many warps as it has samples / 32.
+__device__ __forceinline__ uint32_t td_cluster_of(const uint32_t *__restrict__ bounds, uint32_t nn, uint32_t r, uint32_t &lo_out, uint32_t &hi_out)
+{
+	uint32_t lo = 0, hi = nn - 1;			// largest j with bounds[j] <= r
+	while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (bounds[mid] <= r) lo = mid; else hi = mid - 1; }
+	lo_out = bounds[lo]; hi_out = bounds[lo + 1];
+	return lo;
+}
+
+static constexpr int TDS_V = 4;			// consecutive sorted samples per lane
+
 __global__ void __launch_bounds__(256) td_sums_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
 		const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ plan_bounds, const uint32_t *__restrict__ plan_n,
 		unsigned long long *__restrict__ newsum)
 {
 	const uint64_t n = *d_n;
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * TDS_V;
 	const int lane = threadIdx.x & 31;
 
-	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
-		const uint64_t i = base + lane;
-		const bool valid = i < n;
-		uint32_t slot = 0xFFFFFFFFu, v = 0, j = 0;
-
-		if (valid) {
-			const unsigned long long key = keys[i];
-			slot = (uint32_t)(key >> VALUE_BITS);
-			v = (uint32_t)(key & VALUE_MASK);
-		}
-		// the whole warp usually sits inside one cluster of one hot service: lane 0 searches, the others verify
-		const uint32_t slot0 = __shfl_sync(0xffffffffu, slot, 0);
-		uint32_t r = 0, lo0 = 0, hi0 = 0, j0 = 0;
-		const uint32_t *bounds = nullptr;
-		uint32_t nn = 0;
-		if (valid) {
-			r = (uint32_t)(i - seg_start[slot]);
-			bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
-			nn = plan_n[slot];
-		}
-		const bool single = (nn & 0x80000000u) != 0;
-		nn &= 0x7FFFFFFFu;
-		if (lane == 0 && valid && !single) {
-			uint32_t lo = 0, hi = nn - 1;			// largest j with bounds[j] <= r
-			while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (bounds[mid] <= r) lo = mid; else hi = mid - 1; }
-			j0 = lo; lo0 = bounds[lo]; hi0 = bounds[lo + 1];
-		}
-		j0 = __shfl_sync(0xffffffffu, j0, 0); lo0 = __shfl_sync(0xffffffffu, lo0, 0); hi0 = __shfl_sync(0xffffffffu, hi0, 0);
-		if (valid) {
-			if (single) j = r;
-			else if (slot == slot0 && r >= lo0 && r < hi0) j = j0;
-			else {
-				uint32_t lo = 0, hi = nn - 1;
-				while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (bounds[mid] <= r) lo = mid; else hi = mid - 1; }
-				j = lo;
-			}
-		}
-		const uint32_t gid = valid ? (slot * (uint32_t)TD_CAP + j) : (0xFFFFFF00u + lane);
-		const uint32_t m = __match_any_sync(0xffffffffu, gid);
-		// group sum by a shuffle loop bounded by the warp's largest group (redux with per-lane masks would iterate over
-		// every distinct group); a warp inside one hot cluster takes the single-group fast path
-		unsigned long long gsum = v;
-		if (m == 0xffffffffu) {
-			gsum = (unsigned long long)__reduce_add_sync(0xffffffffu, v & 0xFFFFu) + ((unsigned long long)__reduce_add_sync(0xffffffffu, v >> 16) << 16);
+	for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane) * TDS_V; base < n; base += stride) {
+		const uint64_t i0 = base + (uint64_t)lane * TDS_V;
+		unsigned long long kk[TDS_V];
+		if (i0 + TDS_V <= n) {
+			const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0), c = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
+			kk[0] = a.x; kk[1] = a.y; kk[2] = c.x; kk[3] = c.y;
 		}
 		else {
-			const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(m));
-			uint32_t rest = m & ~(1u << lane);
-			for (uint32_t t = 1; t < maxcnt; ++t) {
-				const int src = rest ? (__ffs(rest) - 1) : lane;
-				const uint32_t other = __shfl_sync(0xffffffffu, v, src);
-				if (rest) { gsum += other; rest &= rest - 1; }
-			}
+#pragma unroll
+			for (int t = 0; t < TDS_V; ++t) kk[t] = i0 + t < n ? keys[i0 + t] : KEY_SENTINEL;
 		}
-		if (valid && (m & ((1u << lane) - 1u)) == 0) {
-			red_add_u64(newsum + (size_t)slot * TD_CAP + j, gsum);
+
+		// the whole warp (128 consecutive samples) usually sits inside one cluster of one hot service: lane 0 looks its first
+		// sample up, every sample first checks that range
+		uint32_t slot0 = 0xFFFFFFFFu, j0 = 0, lo0 = 1, hi0 = 0;
+		if (lane == 0 && kk[0] != KEY_SENTINEL) {
+			slot0 = (uint32_t)(kk[0] >> VALUE_BITS);
+			const uint32_t nn = plan_n[slot0], r = (uint32_t)(i0 - seg_start[slot0]);
+			if (nn & 0x80000000u) { j0 = r; lo0 = r; hi0 = r + 1; }
+			else j0 = td_cluster_of(plan_bounds + (size_t)slot0 * PLAN_STRIDE, nn, r, lo0, hi0);
+		}
+		slot0 = __shfl_sync(0xffffffffu, slot0, 0); j0 = __shfl_sync(0xffffffffu, j0, 0);
+		lo0 = __shfl_sync(0xffffffffu, lo0, 0); hi0 = __shfl_sync(0xffffffffu, hi0, 0);
+
+		// own samples -> runs of equal (service, cluster); sorted input keeps them contiguous
+		uint32_t pg[TDS_V];
+		unsigned long long ps[TDS_V];
+		int np = 0;
+		uint32_t cslot = 0xFFFFFFFFu, cstart = 0, cnn = 0, clo = 1, chi = 0, cj = 0;	// cached lookup of the previous sample
+#pragma unroll
+		for (int t = 0; t < TDS_V; ++t) {
+			if (kk[t] == KEY_SENTINEL) continue;
+			const uint32_t slot = (uint32_t)(kk[t] >> VALUE_BITS), v = (uint32_t)(kk[t] & VALUE_MASK);
+			if (slot != cslot) { cslot = slot; cstart = seg_start[slot]; cnn = plan_n[slot]; clo = 1; chi = 0; }
+			const uint32_t r = (uint32_t)(i0 + t - cstart);
+			uint32_t j;
+			if (cnn & 0x80000000u) j = r;
+			else if (slot == slot0 && r >= lo0 && r < hi0) j = j0;
+			else if (r >= clo && r < chi) j = cj;
+			else { cj = td_cluster_of(plan_bounds + (size_t)slot * PLAN_STRIDE, cnn, r, clo, chi); j = cj; }
+			const uint32_t gid = slot * (uint32_t)TD_CAP + j;
+			if (np && pg[np - 1] == gid) ps[np - 1] += v;
+			else { pg[np] = gid; ps[np] = v; np++; }
+		}
+
+		// emit the runs: round t handles every lane's t-th run; usually one round, one group for the whole warp
+		const int maxp = (int)__reduce_max_sync(0xffffffffu, (uint32_t)np);
+		for (int t = 0; t < maxp; ++t) {
+			const bool act = t < np;
+			const uint32_t gid = act ? pg[t] : (0xFFFFFF00u + lane);
+			const unsigned long long v = act ? ps[t] : 0ull;		// < 2^33
+			const uint32_t m = __match_any_sync(0xffffffffu, gid);
+			unsigned long long gsum = v;
+			if (m == 0xffffffffu) {
+				gsum = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)v & 0xFFFFu) +
+						((unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)(v >> 16)) << 16);
+			}
+			else {
+				const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(m));
+				uint32_t rest = m & ~(1u << lane);
+				for (uint32_t u = 1; u < maxcnt; ++u) {
+					const int src = rest ? (__ffs(rest) - 1) : lane;
+					const unsigned long long other = __shfl_sync(0xffffffffu, v, src);
+					if (rest) { gsum += other; rest &= rest - 1; }
+				}
+			}
+			if (act && (m & ((1u << lane) - 1u)) == 0) red_add_u64(newsum + gid, gsum);	// gid == slot * TD_CAP + j
 		}
 	}
 }
