@@ -184,13 +184,18 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v)
 // engine creation, never by the inserter. With `insert`, an unknown id claims an empty entry with a CAS on the key, takes the
 // next slot number and publishes it; racing readers of the same key spin on a volatile load. Returns -1 when absent / full.
 // Replaces RCU_HASH_TABLE::lookup_single_elem_locked(glob_id, get_uint64_hash(glob_id)) (gy_mconnhdlr.cc:11183).
-__device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long key, bool insert, uint32_t host_idx = 0)
+// The lookup is split so that a thread can put the first-probe loads of several ids in flight before resolving any of them
+// (the 16-byte entry load is the latency that matters; hash collisions and inserts are the rare continuation).
+__device__ __forceinline__ uint4 table_probe_first(const IdTable &t, unsigned long long key, uint32_t &pos)
 {
-	uint32_t pos = uint64_hash(key) & t.mask;
+	pos = uint64_hash(key) & t.mask;
+	return ld_cg_v4(&t.ent[pos]);
+}
 
-	for (uint32_t probe = 0; probe <= t.mask; ++probe, pos = (pos + 1) & t.mask) {
+__device__ __forceinline__ int table_resolve(const IdTable &t, unsigned long long key, bool insert, uint32_t host_idx, uint32_t pos, uint4 raw)
+{
+	for (uint32_t probe = 0; probe <= t.mask; ++probe) {
 		TblEntry *e = &t.ent[pos];
-		const uint4 raw = ld_cg_v4(e);
 		unsigned long long k = ((unsigned long long)raw.y << 32) | raw.x;
 		uint32_t s1 = raw.z;
 
@@ -214,8 +219,17 @@ __device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long
 			while (s1 == 0) { __nanosleep(20); s1 = ld_volatile_u32(&e->slot1); }
 			return s1 == SLOT_INVALID ? -1 : (int)(s1 - 1);
 		}
+		pos = (pos + 1) & t.mask;
+		raw = ld_cg_v4(&t.ent[pos]);
 	}
 	return -1;
+}
+
+__device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long key, bool insert, uint32_t host_idx = 0)
+{
+	uint32_t pos;
+	const uint4 raw = table_probe_first(t, key, pos);
+	return table_resolve(t, key, insert, host_idx, pos, raw);
 }
 
 } // namespace gysk

@@ -254,34 +254,51 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			}
 			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }	// type 0xFFFF: padding, not counted
 		}
+		// decode; put the first id-table probe of all EPT events in flight before any of them is resolved
+		unsigned long long svc[INGEST_EPT];
+		uint4 praw[INGEST_EPT];
+		uint32_t ppos[INGEST_EPT];
+		uint32_t kind[INGEST_EPT];		// 0 none, GYSK_EV_RESP, 1 tcp (stored as GYSK_EV_ACCEPT), GYSK_EV_TASK
 #pragma unroll
 		for (int k = 0; k < INGEST_EPT; ++k) {
-			const unsigned long long svc_id = ((unsigned long long)ra[k].y << 32) | ra[k].x;
-			const unsigned long long flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
+			svc[k] = ((unsigned long long)ra[k].y << 32) | ra[k].x;
 			const uint32_t value = rb[k].x, host_idx = rb[k].y;
 			const uint32_t type = rb[k].w & 0xFFFFu;
 			const bool pad = tbase + (uint64_t)k * INGEST_THREADS + threadIdx.x >= n;
 			const bool is_resp = type == GYSK_EV_RESP, is_task = type == GYSK_EV_TASK;
 			const bool is_tcp = type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER;
-			// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
-			// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-			const uint32_t ms = value / 1000u;
-			int slot = -1;
 			bool mine = !pad;
 
+			kind[k] = 0; ppos[k] = 0; praw[k] = make_uint4(0, 0, 0, 0);
 			if (mine && st.world > 1 && (host_idx % st.world) != st.rank) { c_foreign++; mine = false; }
 			if (mine) {
 				c_in++;
+				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
+				// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
+				if (svc[k] != 0 && (is_tcp || is_task || (is_resp && value / 1000u <= 1000000u))) {
+					kind[k] = is_resp ? (uint32_t)GYSK_EV_RESP : (is_task ? (uint32_t)GYSK_EV_TASK : (uint32_t)GYSK_EV_ACCEPT);
+					praw[k] = table_probe_first(is_task ? st.task_tbl : st.svc_tbl, svc[k], ppos[k]);
+				}
+				else c_drop++;
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < INGEST_EPT; ++k) {
+			const bool is_resp = kind[k] == GYSK_EV_RESP, is_task = kind[k] == GYSK_EV_TASK, is_tcp = kind[k] == GYSK_EV_ACCEPT;
+			int slot = -1;
+			if (kind[k]) {
 				// one id lookup for all three event kinds (services and tasks live in separate tables)
-				if (svc_id != 0 && (is_tcp || is_task || (is_resp && ms <= 1000000u)))
-					slot = table_lookup(is_task ? st.task_tbl : st.svc_tbl, svc_id, st.auto_register, host_idx);
+				slot = table_resolve(is_task ? st.task_tbl : st.svc_tbl, svc[k], st.auto_register, rb[k].y, ppos[k], praw[k]);
 				if (slot < 0) c_drop++;
 				else if (is_resp) c_resp++;
 				else if (is_tcp) c_tcp++;
 				else c_task++;
 			}
 			const uint16_t pos = (uint16_t)(k * INGEST_THREADS + threadIdx.x);
-			if (slot >= 0) { IngestRec r; r.slot = (uint32_t)slot; r.value = value; r.flow_key = flow_key; S.rec[pos] = r; }
+			if (slot >= 0) {
+				IngestRec r; r.slot = (uint32_t)slot; r.value = rb[k].x; r.flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
+				S.rec[pos] = r;
+			}
 			queue_push(slot >= 0 && is_resp, S.q_resp, &qn[0], pos);
 			queue_push(slot >= 0 && is_tcp, S.q_tcp, &qn[1], pos);
 			queue_push(slot >= 0 && is_task, S.q_task, &qn[2], pos);
@@ -1088,14 +1105,15 @@ __global__ void __launch_bounds__(WI_WARPS * 32, MIN_CTAS) ingest_warp_kernel(De
 	}
 }
 
-// 0 (default) = warp-autonomous tiles (keys left in event order with sentinels); 256 / 128 / 2563 = CTA tile pipeline shapes
+// 256 (default, measured best) / 128 / 2563 (TMA-staged) = CTA tile pipeline shapes; 4 / 40 = warp-autonomous tiles (keys left in
+// event order with sentinels) with 4 / 5 CTAs per SM
 static int ingest_variant()
 {
-	static const int v = []{ const char *e = getenv("GYSK_INGEST_VARIANT"); return e ? atoi(e) : 0; }();
+	static const int v = []{ const char *e = getenv("GYSK_INGEST_VARIANT"); return e ? atoi(e) : 256; }();
 	return v;
 }
 
-bool ingest_keys_compact() { return ingest_variant() != 0 && ingest_variant() != 4; }
+bool ingest_keys_compact() { return ingest_variant() != 40 && ingest_variant() != 4; }
 
 template <int THREADS, int MIN_CTAS, bool STAGE>
 static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, int nsm, cudaStream_t s)
