@@ -318,6 +318,12 @@ def main():
     barrier()
     dev_ms = t0.elapsed_time(t1)
     ms_ing, ms_td, nb = eng.profile_read()
+    # diagnostic (outside the timed region): per-step spread of the two kernel groups
+    spread = {"ingest_ms": [], "chain_ms": []}
+    for _ in range(min(args.steps, 8)):
+        eng.ingest_device_ptr(ev_dev.data_ptr(), n)
+        a, b, _nb = eng.profile_read()
+        spread["ingest_ms"].append(round(a, 3)); spread["chain_ms"].append(round(b, 3))
     eng.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.stats()["kernel_launches"] - launches0
@@ -425,7 +431,7 @@ def main():
         "roofline": roof[0] if roof else None, "roofline_other": roof[1:] or None,
         "roofline_whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
                                 "algorithmic_bytes_per_event": BYTES_EVENT},
-        "cpu_baseline": cpu, "accuracy": acc,
+        "cpu_baseline": cpu, "accuracy": acc, "per_step_spread_ms": spread,
         "merge": ({"collective_ms_per_step_rank0": float(np.mean(merge_ms)) if merge_ms else None, "logical_services": NSVC // 16,
                    "what": "one all-reduce per reduction kind (u64 sum / i64 max / u8 max) + one all-gather of t-digest slabs, NCCL"}
                   if world > 1 else None),

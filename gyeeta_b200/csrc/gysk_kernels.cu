@@ -116,13 +116,22 @@ __device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool
 
 	if (!active || (m & ((1u << lane) - 1u))) return;		// group leader = lowest lane
 
-	const uint32_t h = (cell * 2654435761u) >> (32 - HotTable::BITS);
+	// two candidate entries per cell, hashed with a per-CTA seed: which hot cells collide differs from CTA to CTA, so no cell
+	// loses its privatisation everywhere at once (slot numbers, hence cell ids, depend on registration order)
+	const uint32_t seed = blockIdx.x * 0x9E3779B9u;
+	uint32_t h = ((cell ^ seed) * 2654435761u) >> (32 - HotTable::BITS);
 	uint32_t tag = *((volatile uint32_t *)&hot.tag[h]);
 	bool hit = tag == cell + 1;
 
-	if (!hit && tag == 0 && cnt >= 2) {
-		tag = atomicCAS(&hot.tag[h], 0u, cell + 1);
-		hit = tag == 0 || tag == cell + 1;
+	if (!hit) {
+		const uint32_t h2 = ((cell ^ ~seed) * 0x85EBCA6Bu) >> (32 - HotTable::BITS);
+		const uint32_t tag2 = *((volatile uint32_t *)&hot.tag[h2]);
+		if (tag2 == cell + 1) { hit = true; h = h2; }
+		else if (cnt >= 2) {
+			// admission: a cell that shows up twice in one warp takes a free candidate entry
+			if (tag == 0) { tag = atomicCAS(&hot.tag[h], 0u, cell + 1); hit = tag == 0 || tag == cell + 1; }
+			if (!hit && tag2 == 0) { const uint32_t t2 = atomicCAS(&hot.tag[h2], 0u, cell + 1); if (t2 == 0 || t2 == cell + 1) { hit = true; h = h2; } }
+		}
 	}
 	if (hit) {
 		atomicAdd(&hot.count[h], cnt); atomicAdd(&hot.sum[h], (unsigned long long)sum); atomicMax(&hot.vmax[h], gmax);
