@@ -301,7 +301,7 @@ int gysk_merge_prepare(gysk_engine *e)
 				reinterpret_cast<SlabEntry *>(mg.slab));
 		e->kernel_launches += 3;
 	}
-	CU(e, cudaStreamSynchronize(e->stream));		// the collectives run on the caller's stream
+	// no host sync: the caller enqueues the collectives on gysk_stream(e) (stream order) or calls gysk_sync() first
 	mg.prepared = true; mg.finished = false;
 	return post_launch(e, "merge_prepare");
 }
@@ -346,8 +346,7 @@ int gysk_merge_finish(gysk_engine *e, const void *d_gathered, uint32_t world)
 				reinterpret_cast<SlabEntry *>(mg.final_slab), e->st.td);
 		e->kernel_launches++;
 	}
-	CU(e, cudaStreamSynchronize(e->stream));
-	mg.finished = true;
+	mg.finished = true;			// stream-ordered; the query calls synchronise
 	return post_launch(e, "merge_finish");
 }
 

@@ -282,7 +282,8 @@ uint32_t	gysk_uint64_hash(uint64_t key);		/* get_uint64_hash, common/gy_common_i
 
 /* ---- multi-GPU merge ---- */
 int		gysk_set_logical_map(gysk_engine *e, const uint64_t *glob_ids, const uint64_t *logical_ids, uint32_t n);
-int		gysk_merge_prepare(gysk_engine *e);		/* fold per-service sketches into per-logical-service arrays */
+int		gysk_merge_prepare(gysk_engine *e);		/* fold per-service sketches into per-logical-service arrays; asynchronous on
+							   gysk_stream(e): enqueue the collectives on that stream, or gysk_sync() first */
 int		gysk_merge_buffers(gysk_engine *e, gysk_buffer_desc *out, uint32_t cap, uint32_t *n);
 int		gysk_merge_tdigest_slab(gysk_engine *e, void **dptr, uint64_t *nbytes);	/* fixed slab to all-gather */
 int		gysk_merge_finish(gysk_engine *e, const void *d_gathered_slabs, uint32_t world);

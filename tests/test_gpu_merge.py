@@ -16,6 +16,7 @@ def _emulate_collectives(torch, engines):
     dev = torch.device("cuda", 0)
     for e in engines:
         e.merge_prepare()
+        e.sync()                     # merge_prepare is stream-ordered; the emulation below runs on torch's stream
     bufs = [e.merge_buffers() for e in engines]
     for k in range(len(bufs[0])):
         ts = [gd.wrap(torch, b[k][1], b[k][2], b[k][3], dev) for b in bufs]
