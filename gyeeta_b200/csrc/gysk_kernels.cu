@@ -162,7 +162,6 @@ __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t
 //           rows (one (event, row) pair per lane), the HLL updates and the three task histograms (one (event, histogram)
 //           pair per lane) each run with all lanes doing the same thing instead of serialising 70/20/10-divergent branches.
 // RESP sort keys are written compacted (one global cursor bump per tile), so the radix sort never sees a non-RESP slot.
-static constexpr int INGEST_EPT = 4;
 
 struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
 
@@ -189,7 +188,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 			:: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-template <int INGEST_THREADS, bool STAGE>
+template <int INGEST_THREADS, bool STAGE, int INGEST_EPT = 4>
 struct IngestSharedT
 {
 	static constexpr int INGEST_TILE = INGEST_THREADS * INGEST_EPT;
@@ -215,11 +214,11 @@ __device__ __forceinline__ void queue_push(bool pred, uint16_t *q, uint32_t *qn,
 	if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = item;
 }
 
-template <int INGEST_THREADS, int MIN_CTAS, bool STAGE>
+template <int INGEST_THREADS, int MIN_CTAS, bool STAGE, int INGEST_EPT>
 __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
 		unsigned long long *__restrict__ keys)
 {
-	using IngestShared = IngestSharedT<INGEST_THREADS, STAGE>;
+	using IngestShared = IngestSharedT<INGEST_THREADS, STAGE, INGEST_EPT>;
 	using HotTable = typename IngestShared::HotTable;
 	constexpr int INGEST_TILE = IngestShared::INGEST_TILE;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1124,15 +1123,15 @@ static int ingest_variant()
 
 bool ingest_keys_compact() { return ingest_variant() != 40 && ingest_variant() != 4; }
 
-template <int THREADS, int MIN_CTAS, bool STAGE>
+template <int THREADS, int MIN_CTAS, bool STAGE, int EPT = 4>
 static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, int nsm, cudaStream_t s)
 {
-	using Shared = IngestSharedT<THREADS, STAGE>;
+	using Shared = IngestSharedT<THREADS, STAGE, EPT>;
 	static bool attr_set = false;
-	if (!attr_set) { cudaFuncSetAttribute(ingest_kernel<THREADS, MIN_CTAS, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)); attr_set = true; }
+	if (!attr_set) { cudaFuncSetAttribute(ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)); attr_set = true; }
 	const uint64_t want = (n + Shared::INGEST_TILE - 1) / Shared::INGEST_TILE;
 	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * MIN_CTAS ? want : (uint64_t)nsm * MIN_CTAS);
-	ingest_kernel<THREADS, MIN_CTAS, STAGE><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys);
+	ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys);
 }
 
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s)
@@ -1148,6 +1147,8 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 	if (variant == 2563) launch_ingest_variant<256, 3, true>(st, d_ev, n, d_keys, nsm, s);
 	else if (variant == 128) launch_ingest_variant<128, 8, false>(st, d_ev, n, d_keys, nsm, s);
 	else if (variant == 256) launch_ingest_variant<256, 4, false>(st, d_ev, n, d_keys, nsm, s);
+	else if (variant == 2562) launch_ingest_variant<256, 5, false, 2>(st, d_ev, n, d_keys, nsm, s);	// 2 events per thread: fewer live registers, 5 CTAs/SM
+	else if (variant == 2568) launch_ingest_variant<256, 3, false, 8>(st, d_ev, n, d_keys, nsm, s);	// 8 events per thread: fewer barriers per event
 	else {
 		const uint64_t want = (n + (uint64_t)WI_TILE * WI_WARPS - 1) / ((uint64_t)WI_TILE * WI_WARPS);
 		const int per_sm = variant == 4 ? 4 : 5;			// 4: 64 registers, no spills; 5: 48 registers, small spills
