@@ -45,7 +45,8 @@ namespace {
 uint32_t pow2_at_least(uint64_t v) { uint32_t p = 16; while (p < v) p <<= 1; return p; }
 
 // one device batch: ingest kernel, then the sort + t-digest chain over the keys it emitted
-int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
+template <typename AfterIngest>
+int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n, AfterIngest after_ingest)
 {
 	if (!n) return 0;
 	cudaEvent_t *pe = nullptr;
@@ -63,6 +64,9 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
 	}
 	e->kernel_launches += launch_ingest(e->st, d_ev, n, e->tmp.keys_a, e->stream);
 	if (pe) CU(e, cudaEventRecord(pe[1], e->stream));
+	// the events of this batch are consumed once the ingest kernel has run: callers release / refill the event buffer here,
+	// so that the next H2D copy overlaps the readback below and the whole sort + t-digest chain
+	{ int rc_ai = after_ingest(); if (rc_ai) return rc_ai; }
 	// the sort is sized by what the batch actually holds: number of RESP keys, bits of the largest response time, slots in
 	// use — three words read back here (one stream sync per device batch; the kernels of the batch stay back to back)
 	CU(e, cudaMemcpyAsync(e->h_counters, e->st.counters + CTR_NKEYS, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
@@ -81,6 +85,11 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
 	return post_launch(e, "ingest batch");
 }
 
+int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
+{
+	return process_device_batch(e, d_ev, n, []() { return 0; });
+}
+
 } // namespace
 
 // hand the filled part of the current staging buffer to the device
@@ -94,9 +103,8 @@ int gysk::submit_stage(gysk_engine *e)
 	CU(e, cudaMemcpyAsync(e->d_events[k], e->h_stage[k], (size_t)n * sizeof(gysk_event), cudaMemcpyHostToDevice, e->copy_stream));
 	CU(e, cudaEventRecord(e->ev_copied[k], e->copy_stream));
 	CU(e, cudaStreamWaitEvent(e->stream, e->ev_copied[k], 0));
-	int rc = process_device_batch(e, e->d_events[k], n);
+	int rc = process_device_batch(e, e->d_events[k], n, [&]() -> int { CU(e, cudaEventRecord(e->ev_done[k], e->stream)); return 0; });
 	if (rc) return rc;
-	CU(e, cudaEventRecord(e->ev_done[k], e->stream));
 
 	e->stage_cur = (k + 1) % NBUF;
 	e->stage_fill = 0;
@@ -533,16 +541,27 @@ int gysk_ingest_pinned(gysk_engine *e, const gysk_event *pinned, uint64_t n)
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
-	for (uint64_t off = 0; off < n; off += e->cfg.stage_batch) {
-		const uint64_t m = std::min<uint64_t>(e->cfg.stage_batch, n - off);
-		const int k = e->stage_cur;
-		CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_done[k], 0));
+	// software pipeline over stage_batch chunks: the H2D copy of chunk c+1 is enqueued as soon as the ingest kernel of chunk c is
+	// launched, so the PCIe link never waits for the host readback or the sort + t-digest chain of chunk c
+	const uint64_t sb = e->cfg.stage_batch;
+	auto issue_copy = [&](uint64_t off, int k) -> int {
+		const uint64_t m = std::min<uint64_t>(sb, n - off);
+		CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_done[k], 0));		// ingest kernel that last read buffer k has run
 		CU(e, cudaMemcpyAsync(e->d_events[k], pinned + off, (size_t)m * sizeof(gysk_event), cudaMemcpyHostToDevice, e->copy_stream));
 		CU(e, cudaEventRecord(e->ev_copied[k], e->copy_stream));
+		return 0;
+	};
+	if (n && (rc = issue_copy(0, e->stage_cur))) return rc;
+	for (uint64_t off = 0; off < n; off += sb) {
+		const uint64_t m = std::min<uint64_t>(sb, n - off);
+		const int k = e->stage_cur, knext = (k + 1) % NBUF;
 		CU(e, cudaStreamWaitEvent(e->stream, e->ev_copied[k], 0));
-		if ((rc = process_device_batch(e, e->d_events[k], m))) return rc;
-		CU(e, cudaEventRecord(e->ev_done[k], e->stream));
-		e->stage_cur = (k + 1) % NBUF;
+		rc = process_device_batch(e, e->d_events[k], m, [&]() -> int {
+			CU(e, cudaEventRecord(e->ev_done[k], e->stream));
+			return off + sb < n ? issue_copy(off + sb, knext) : 0;
+		});
+		if (rc) return rc;
+		e->stage_cur = knext;
 	}
 	return GYSK_OK;
 }
