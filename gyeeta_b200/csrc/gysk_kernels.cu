@@ -534,12 +534,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t *__re
 	for (int j = 0; j < SCAN_ITEMS; ++j) { if (base + j < len) data[base + j] = ex; ex += v[j]; }
 }
 
-// scatter one tile to its stable positions. Thread t of warp w holds keys w*512 + r*32 + lane (r = 0..15), i.e.
-// ascending input order is (warp, round, lane); ranks come from match_any groups so equal digits keep that order.
+// scatter one tile to its stable positions. Thread t of warp w holds keys w*256 + r*32 + lane (r = 0..7), i.e. ascending input
+// order is (warp, round, lane); ranks come from match.any groups so equal digits keep that order. The tile is first reordered by
+// digit in shared memory, then written out by consecutive threads: every digit's keys leave as one contiguous run (full 32-byte
+// sectors) instead of 4096 scattered 8-byte stores.
+struct ScatterShared
+{
+	unsigned long long	keys[SORT_TILE];		// tile reordered by digit
+	uint32_t		whist[RS_WARPS][RADIX];		// per-warp digit counts, then local start of (warp, digit)
+	uint32_t		dstart[RADIX];			// tile-local start of each digit
+	uint32_t		goff[RADIX];			// global position of the tile's first key of each digit
+	uint32_t		wsum[RS_WARPS];
+	uint32_t		nvalid;				// keys of the tile that are not sentinels
+};
+
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
 		uint64_t n_host, const unsigned long long *__restrict__ d_n, DigitSpec D, const uint32_t *__restrict__ tile_offs, uint32_t ntiles)
 {
-	__shared__ uint32_t whist[RS_WARPS][RADIX];
+	extern __shared__ __align__(16) unsigned char rs_smem[];
+	ScatterShared &S = *reinterpret_cast<ScatterShared *>(rs_smem);
 	const uint64_t n = d_n ? *d_n : n_host;
 	const uint32_t tile = blockIdx.x;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -547,7 +560,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
 
 	if ((uint64_t)tile * SORT_TILE >= n) return;
 
-	for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&whist[0][0])[i] = 0;
+	for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&S.whist[0][0])[i] = 0;
 	__syncthreads();
 
 	unsigned long long k[RS_ROUNDS];
@@ -570,26 +583,54 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
 		const uint32_t m = __match_any_sync(0xffffffffu, d);
 		const int leader = __ffs(m) - 1;
 		uint32_t old = 0;
-		if (valid && lane == leader) { old = whist[wid][d]; whist[wid][d] = old + __popc(m); }
+		if (valid && lane == leader) { old = S.whist[wid][d]; S.whist[wid][d] = old + __popc(m); }
 		__syncwarp();
 		old = __shfl_sync(0xffffffffu, old, leader);
 		rank[r] = old + __popc(m & lt_mask);
 	}
 	__syncthreads();
 
-	// exclusive prefix over warps per digit, seeded with this tile's global offset for the digit
+	// per digit: exclusive prefix over warps, total, and (block scan over the 256 digit totals) the tile-local digit start
+	uint32_t dtotal = 0;
 	if (threadIdx.x < RADIX) {
 		const uint32_t d = threadIdx.x;
-		uint32_t run = tile_offs[(size_t)d * ntiles + tile];
+		uint32_t run = 0;
 #pragma unroll
-		for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = whist[w][d]; whist[w][d] = run; run += t; }
+		for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
+		dtotal = run;
+		S.goff[d] = tile_offs[(size_t)d * ntiles + tile];
+	}
+	{
+		uint32_t incl = dtotal;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+		if (lane == 31) S.wsum[wid] = incl;
+		__syncthreads();
+		if (threadIdx.x < RADIX) {
+			uint32_t woff = 0;
+			for (int w = 0; w < wid; ++w) woff += S.wsum[w];		// wid < 8 here
+			S.dstart[threadIdx.x] = woff + incl - dtotal;
+			if (threadIdx.x == RADIX - 1) S.nvalid = woff + incl;
+		}
 	}
 	__syncthreads();
 
-	// phase B: position = warp base of the digit + rank
+	// phase B1: reorder the tile by digit in shared memory
 #pragma unroll
 	for (int r = 0; r < RS_ROUNDS; ++r) {
-		if (k[r] != KEY_SENTINEL) out[whist[wid][key_digit(k[r], D)] + rank[r]] = k[r];
+		if (k[r] != KEY_SENTINEL) {
+			const uint32_t d = key_digit(k[r], D);
+			S.keys[S.dstart[d] + S.whist[wid][d] + rank[r]] = k[r];
+		}
+	}
+	__syncthreads();
+
+	// phase B2: consecutive threads write consecutive keys; a digit's run goes to goff[d] onwards
+	const uint32_t nvalid = S.nvalid;
+	for (uint32_t i = threadIdx.x; i < nvalid; i += RS_THREADS) {
+		const unsigned long long key = S.keys[i];
+		const uint32_t d = key_digit(key, D);
+		out[S.goff[d] + (i - S.dstart[d])] = key;
 	}
 }
 
@@ -1175,6 +1216,8 @@ int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_first, uin
 		int *which, cudaStream_t s)
 {
 	int launches = 0;
+	static bool attr_set = false;
+	if (!attr_set) { cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared)); attr_set = true; }
 	bool first = true;
 	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
 	int w = start;
@@ -1196,7 +1239,7 @@ int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_first, uin
 		const uint32_t ntiles = div_up(nn, SORT_TILE);
 		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], nn, dn, D, tmp.tile_hist, ntiles);
 		launches += 1 + launch_exclusive_scan(tmp.tile_hist, RADIX * ntiles, tmp.scan_tmp, nullptr, s);
-		rs_scatter_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], bufs[w ^ 1], nn, dn, D, tmp.tile_hist, ntiles);
+		rs_scatter_kernel<<<ntiles, RS_THREADS, sizeof(ScatterShared), s>>>(bufs[w], bufs[w ^ 1], nn, dn, D, tmp.tile_hist, ntiles);
 		launches++;
 		w ^= 1; first = false;
 	}
