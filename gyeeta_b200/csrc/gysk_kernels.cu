@@ -642,17 +642,26 @@ __global__ void td_segments_kernel(const unsigned long long *__restrict__ keys, 
 {
 	const uint64_t n = *d_n;
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const bool valid = i < n;
+	uint32_t slot = 0xFFFFFFFFu, prev = 0xFFFFFFFFu, next = 0xFFFFFFFFu;
 
-	if (i >= n) return;
-	const uint32_t slot = (uint32_t)(keys[i] >> VALUE_BITS);
-	const uint32_t prev = i ? (uint32_t)(keys[i - 1] >> VALUE_BITS) : 0xFFFFFFFFu;
-	const uint32_t next = i + 1 < n ? (uint32_t)(keys[i + 1] >> VALUE_BITS) : 0xFFFFFFFFu;
-
-	if (slot != prev) {
-		seg_start[slot] = (uint32_t)i;
-		touched[atomicAdd(ntouched, 1ull)] = slot;
+	if (valid) {
+		slot = (uint32_t)(keys[i] >> VALUE_BITS);
+		prev = i ? (uint32_t)(keys[i - 1] >> VALUE_BITS) : 0xFFFFFFFFu;
+		next = i + 1 < n ? (uint32_t)(keys[i + 1] >> VALUE_BITS) : 0xFFFFFFFFu;
 	}
-	if (slot != next) seg_end[slot] = (uint32_t)(i + 1);
+	const bool is_start = valid && slot != prev;
+	// one cursor bump per warp for all the runs that start in it (the cold tail has a new service almost every sample)
+	const uint32_t m = __ballot_sync(0xffffffffu, is_start);
+	unsigned long long base = 0;
+	if (m && lane == __ffs(m) - 1) base = atomicAdd(ntouched, (unsigned long long)__popc(m));
+	if (m) base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+	if (is_start) {
+		seg_start[slot] = (uint32_t)i;
+		touched[base + __popc(m & ((1u << lane) - 1u))] = slot;
+	}
+	if (valid && slot != next) seg_end[slot] = (uint32_t)(i + 1);
 }
 
 static constexpr int TD_WARPS = 4;
@@ -1281,7 +1290,7 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_ev
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 	td_plan_kernel<<<nsm * 2, 128, 0, s>>>(st.td, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
 	td_sums_kernel<<<nsm * 8, 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
-	td_merge_kernel<<<nsm * 6, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
+	td_merge_kernel<<<nsm * 7, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
 	return launches + 4;
 }
 

@@ -28,18 +28,17 @@ __device__ __forceinline__ double td_wlimit(unsigned long long wsofar, unsigned 
 	return __dmul_rn((double)W, td_q_next(q0, P));
 }
 
-struct TdScratch
+struct TdScratch			// 7.1 KB per warp
 {
-	Centroid		newc[TD_CAP];
-	Centroid		merged[2 * TD_CAP];
-	unsigned long long	prefix[2 * TD_CAP + 1];
-	uint32_t		bounds[2 * TD_CAP + 1];
+	Centroid		newc[TD_CAP];			// list b / accumulator of the callers
+	double			mean[2 * TD_CAP];		// merged list: means ...
+	unsigned long long	pref[2 * TD_CAP + 1];		// ... and exclusive weight prefix: weight of item i = pref[i+1] - pref[i]
+	uint16_t		bounds[2 * TD_CAP + 1];
 	uint16_t		nxt[2 * TD_CAP];
 };
 
-
 // Stable merge by mean of two mean-sorted centroid lists (`a` first on ties), then the greedy K_1 pass; one warp.
-// Both inputs are fully consumed into S.merged before `out` is written, so `out` may alias `a` or `b`.
+// Both inputs are fully consumed into S.mean / S.pref before `out` is written, so `out` may alias `a` or `b`.
 // Returns the number of centroids written to out (<= TD_CAP).
 __device__ __forceinline__ uint32_t warp_merge_compress(TdScratch &S, const Centroid *a, uint32_t na, const Centroid *b, uint32_t nb,
 		Centroid *out, const TdParams &P)
@@ -51,43 +50,43 @@ __device__ __forceinline__ uint32_t warp_merge_compress(TdScratch &S, const Cent
 		const Centroid c = a[j];
 		uint32_t lo = 0, hi = nb;			// # of b with mean < c.mean
 		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (b[mid].mean < c.mean) lo = mid + 1; else hi = mid; }
-		S.merged[j + lo] = c;
+		S.mean[j + lo] = c.mean; S.pref[j + lo + 1] = c.weight;
 	}
 	for (uint32_t j = lane; j < nb; j += 32) {
 		const Centroid c = b[j];
 		uint32_t lo = 0, hi = na;			// # of a with mean <= c.mean
 		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid].mean <= c.mean) lo = mid + 1; else hi = mid; }
-		S.merged[j + lo] = c;
+		S.mean[j + lo] = c.mean; S.pref[j + lo + 1] = c.weight;
 	}
 	__syncwarp();
 
-	// exclusive prefix of weights: lane owns 8 consecutive items
+	// in-place weight prefix: pref[i+1] holds w_i on entry and sum(w_0..w_i) on exit; lane owns 8 consecutive items
 	{
 		unsigned long long w[8], tot = 0;
 #pragma unroll
-		for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; w[j] = i < nm ? S.merged[i].weight : 0; tot += w[j]; }
+		for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; w[j] = i < nm ? S.pref[i + 1] : 0; tot += w[j]; }
 		unsigned long long incl = tot;
 #pragma unroll
 		for (int off = 1; off < 32; off <<= 1) {
 			const unsigned long long tt = __shfl_up_sync(0xffffffffu, incl, off);
 			if (lane >= off) incl += tt;
 		}
-		unsigned long long ex = incl - tot;
+		unsigned long long run = incl - tot;
 #pragma unroll
-		for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; if (i <= nm) S.prefix[i] = ex; ex += w[j]; }
-		if (lane == 31 && nm == 2 * TD_CAP) S.prefix[nm] = incl;
+		for (int j = 0; j < 8; ++j) { const uint32_t i = lane * 8 + j; run += w[j]; if (i < nm) S.pref[i + 1] = run; }
+		if (lane == 0) S.pref[0] = 0;
 	}
 	__syncwarp();
 
-	// greedy chain over the merged list: a cluster that starts at item i (after weight P = prefix[i]) takes items while the
+	// greedy chain over the merged list: a cluster that starts at item i (after weight P = pref[i]) takes items while the
 	// running total stays <= W q(k(P/W) + 1), and at least one item. The successor nxt[i] of EVERY possible start is
 	// evaluated in parallel (8 per lane, the expensive double sqrt/div part); the chain itself is then a pointer walk.
 	if (nm) {
-		const unsigned long long W = S.prefix[nm];
+		const unsigned long long W = S.pref[nm];
 		for (uint32_t i = lane; i < nm; i += 32) {
-			const double wl = td_wlimit(S.prefix[i], W, P);
-			uint32_t e = i + 1;				// largest e in [i+1, nm] with prefix[e] <= wl
-			while (e < nm && (double)S.prefix[e + 1] <= wl) ++e;
+			const double wl = td_wlimit(S.pref[i], W, P);
+			uint32_t e = i + 1;				// largest e in [i+1, nm] with pref[e] <= wl
+			while (e < nm && (double)S.pref[e + 1] <= wl) ++e;
 			S.nxt[i] = (uint16_t)e;
 		}
 	}
@@ -98,21 +97,21 @@ __device__ __forceinline__ uint32_t warp_merge_compress(TdScratch &S, const Cent
 		while (cs < nm) {
 			uint32_t e = S.nxt[cs];
 			if (nout == TD_CAP - 1) e = nm;			// the last slot absorbs whatever is left
-			S.bounds[nout++] = cs;
+			S.bounds[nout++] = (uint16_t)cs;
 			cs = e;
 		}
-		S.bounds[nout] = nm;
+		S.bounds[nout] = (uint16_t)nm;
 	}
 	nout = __shfl_sync(0xffffffffu, nout, 0);
 	__syncwarp();
 
 	for (uint32_t c = lane; c < nout; c += 32) {
 		double csum = 0.0;
-		unsigned long long cw = 0;
-		for (uint32_t i = S.bounds[c]; i < S.bounds[c + 1]; ++i) {
-			csum = __dadd_rn(csum, __dmul_rn(S.merged[i].mean, (double)S.merged[i].weight));
-			cw += S.merged[i].weight;
+		const uint32_t lo = S.bounds[c], hi = S.bounds[c + 1];
+		for (uint32_t i = lo; i < hi; ++i) {
+			csum = __dadd_rn(csum, __dmul_rn(S.mean[i], (double)(S.pref[i + 1] - S.pref[i])));
 		}
+		const unsigned long long cw = S.pref[hi] - S.pref[lo];
 		Centroid o; o.mean = __ddiv_rn(csum, (double)cw); o.weight = cw;
 		out[c] = o;
 	}
