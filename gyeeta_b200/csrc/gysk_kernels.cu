@@ -637,31 +637,52 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
 // ---------------------------------------------------------------------------------------------------
 // batched merging t-digest
 // ---------------------------------------------------------------------------------------------------
-__global__ void td_segments_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
+static constexpr int TSEG_V = 4;			// consecutive keys per thread
+
+__global__ void __launch_bounds__(256) td_segments_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
 		uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_end, uint32_t *__restrict__ touched, unsigned long long *ntouched)
 {
 	const uint64_t n = *d_n;
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * TSEG_V;
 	const int lane = threadIdx.x & 31;
-	const bool valid = i < n;
-	uint32_t slot = 0xFFFFFFFFu, prev = 0xFFFFFFFFu, next = 0xFFFFFFFFu;
+	uint32_t sl[TSEG_V + 2];			// slots of key i0-1, i0 .. i0+3, i0+4 (0xFFFFFFFF outside the array)
 
-	if (valid) {
-		slot = (uint32_t)(keys[i] >> VALUE_BITS);
-		prev = i ? (uint32_t)(keys[i - 1] >> VALUE_BITS) : 0xFFFFFFFFu;
-		next = i + 1 < n ? (uint32_t)(keys[i + 1] >> VALUE_BITS) : 0xFFFFFFFFu;
+#pragma unroll
+	for (int t = 0; t < TSEG_V + 2; ++t) sl[t] = 0xFFFFFFFFu;
+	if (i0 + TSEG_V <= n) {
+		const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0), c = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
+		sl[1] = (uint32_t)(a.x >> VALUE_BITS); sl[2] = (uint32_t)(a.y >> VALUE_BITS);
+		sl[3] = (uint32_t)(c.x >> VALUE_BITS); sl[4] = (uint32_t)(c.y >> VALUE_BITS);
 	}
-	const bool is_start = valid && slot != prev;
+	else {
+#pragma unroll
+		for (int t = 0; t < TSEG_V; ++t) if (i0 + t < n) sl[1 + t] = (uint32_t)(keys[i0 + t] >> VALUE_BITS);
+	}
+	// neighbours: from the adjacent lanes, the warp's edge lanes load them
+	const uint32_t up = __shfl_up_sync(0xffffffffu, sl[TSEG_V], 1), down = __shfl_down_sync(0xffffffffu, sl[1], 1);
+	sl[0] = lane ? up : ((i0 && i0 - 1 < n) ? (uint32_t)(keys[i0 - 1] >> VALUE_BITS) : 0xFFFFFFFFu);
+	sl[TSEG_V + 1] = lane < 31 ? down : (i0 + TSEG_V < n ? (uint32_t)(keys[i0 + TSEG_V] >> VALUE_BITS) : 0xFFFFFFFFu);
+
+	uint32_t nstart = 0;
+#pragma unroll
+	for (int t = 1; t <= TSEG_V; ++t) nstart += (i0 + t - 1 < n && sl[t] != sl[t - 1]) ? 1u : 0u;
+
 	// one cursor bump per warp for all the runs that start in it (the cold tail has a new service almost every sample)
-	const uint32_t m = __ballot_sync(0xffffffffu, is_start);
+	uint32_t incl = nstart;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+	const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
 	unsigned long long base = 0;
-	if (m && lane == __ffs(m) - 1) base = atomicAdd(ntouched, (unsigned long long)__popc(m));
-	if (m) base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-	if (is_start) {
-		seg_start[slot] = (uint32_t)i;
-		touched[base + __popc(m & ((1u << lane) - 1u))] = slot;
+	if (wtotal && lane == 0) base = atomicAdd(ntouched, (unsigned long long)wtotal);
+	base = __shfl_sync(0xffffffffu, base, 0) + (incl - nstart);
+
+#pragma unroll
+	for (int t = 1; t <= TSEG_V; ++t) {
+		const uint64_t i = i0 + t - 1;
+		if (i >= n) break;
+		if (sl[t] != sl[t - 1]) { seg_start[sl[t]] = (uint32_t)i; touched[base++] = sl[t]; }
+		if (sl[t] != sl[t + 1]) seg_end[sl[t]] = (uint32_t)(i + 1);
 	}
-	if (valid && slot != next) seg_end[slot] = (uint32_t)(i + 1);
 }
 
 static constexpr int TD_WARPS = 4;
@@ -1284,7 +1305,7 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_ev
 	launches += launch_radix_sort_from(tmp, 0, ingest_keys_compact() ? n : n_events, n, d_nkeys, 0, value_bits, VALUE_BITS, VALUE_BITS + (int)slot_bits, &which, s);
 	src = bufs[which];
 
-	td_segments_kernel<<<div_up(n, 256), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
+	td_segments_kernel<<<div_up(n, 256 * TSEG_V), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
