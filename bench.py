@@ -35,9 +35,11 @@ NHOSTS = 4096
 NCLIENTS = 1_000_000
 ZIPF_S = 1.05
 # algorithmic bytes per event, SURVEY.md §8(d): RESP 98 = 32 + 32 + 16 + 18(t-digest), TCP 98, TASK 128.
-# split per kernel: the ingest kernel carries everything but the t-digest share.
-BYTES_INGEST = 0.7 * (32 + 32 + 16) + 0.2 * 98 + 0.1 * 128          # 88.4 B / event
-BYTES_TDIGEST = 0.7 * 18                                              # 12.6 B / event
+# split per kernel group: the ingest kernel reads every record (32 B) and carries the TCP (count-min + HLL) and TASK state; the
+# RESP histogram cell (32 B), per-service counter (16 B) and t-digest share (18 B) are produced from the sorted keys by the
+# sort + t-digest chain.
+BYTES_INGEST = 0.7 * 32 + 0.2 * 98 + 0.1 * 128                      # 54.8 B / event
+BYTES_TDIGEST = 0.7 * (32 + 16 + 18)                                  # 46.2 B / event
 BYTES_EVENT = BYTES_INGEST + BYTES_TDIGEST                            # 101.0 B / event
 
 
@@ -398,7 +400,7 @@ def main():
     roof = []
     traffic = ncu_traffic_per_event()
     for name, key, ms, bpe in (("ingest_kernel", "ingest_kernel", ms_ing, BYTES_INGEST),
-                               ("sort+tdigest chain (rs_hist/scan/rs_scatter/td_*)", "chain", ms_td, BYTES_TDIGEST)):
+                               ("sort + histogram/t-digest chain (os_hist/os_pass/td_*)", "chain", ms_td, BYTES_TDIGEST)):
         if ms > 0:
             ach = nev_total * bpe / (ms * 1e-3) / 1e9
             tr = traffic.get(key, {}).get("dram_bytes_per_event")
@@ -407,7 +409,7 @@ def main():
                          "algorithmic_bytes_per_launch": bpe * n, "ms_per_launch": ms / max(nb, 1),
                          "ms_total": ms, "launch_groups": nb, "algorithmic_bytes_per_event": bpe, "peak_source": peak_src})
     # `roofline` = the dominant SINGLE kernel: ingest_kernel is one launch per device batch and holds the largest share of any
-    # individual kernel (profiles/r01_launches_*.csv); the sort + t-digest chain is 12+ launches of 9 small kernels
+    # individual kernel (profiles/r01_launches_*.csv); the sort + t-digest chain is 10 launches of 6 kernels
     roof.sort(key=lambda r: 0 if r["kernel"] == "ingest_kernel" else 1)
     whole = nev_total * BYTES_EVENT / (max_ms * 1e-3) / 1e9
 

@@ -14,12 +14,16 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace gysk {
 
 static constexpr unsigned long long KEY_SENTINEL = ~0ull;
 static constexpr unsigned long long VALUE_MASK = (1ull << VALUE_BITS) - 1;
+__device__ __forceinline__ uint32_t key_slot(unsigned long long k) { return (uint32_t)(k >> KEY_SLOT_SHIFT); }
+__device__ __forceinline__ uint32_t key_usec(unsigned long long k) { return (uint32_t)(k >> KEY_VALUE_SHIFT) & (uint32_t)VALUE_MASK; }
 
 // ---------------------------------------------------------------------------------------------------
 // state init / registration
@@ -65,38 +69,25 @@ struct HotTableT				// structure of arrays, 20 B per entry
 	uint32_t		count[N];
 	unsigned long long	sum[N];
 	int			vmax[N];
-	uint32_t		bits[N];		// CONN_BITMAP bits of a RESP cell
 };
-static constexpr uint32_t CELL_TASK = 1u << 30;			// cell ids: svc hist = slot*16 + bucket, conn = slot*16 + 15,
-								//           task = CELL_TASK | (tslot*48 + hist*16 + bucket)
-
-__device__ __forceinline__ bool cell_is_conn(uint32_t cell) { return !(cell & CELL_TASK) && (cell & 15u) == (uint32_t)HIST_MAX_CELL; }
+static constexpr uint32_t CELL_TASK = 1u << 30;			// cell ids: conn = slot, task = CELL_TASK | (tslot*48 + hist*16 + bucket)
 
 // one RED per field, nothing is read back: {count, sum} (+ max_val_seen_ for histogram cells)
-__device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cell, uint32_t cnt, unsigned long long sum, int vmax, uint32_t bits)
+__device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cell, uint32_t cnt, unsigned long long sum, int vmax)
 {
 	if (cell & CELL_TASK) {
 		HistCell *c = st.task_hist + (cell & ~CELL_TASK);
 		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
 		atomicMax(&st.task_hist[(cell & ~CELL_TASK) | 15u].sum, (long long)vmax);
 	}
-	else if ((cell & 15u) == (uint32_t)HIST_MAX_CELL) {
-		red_add_u64(st.conn_cur + (cell >> 4), (unsigned long long)cnt + (sum << 32));	// packed {count, kbytes}
-	}
-	else {
-		HistCell *c = st.hist_cur + cell;
-		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
-		atomicMax(&st.hist_cur[cell | 15u].sum, (long long)vmax);
-		// TCP_LISTENER::CONN_BITMAP::add_response (common/gy_socket_stat.h:403-410), transposed: the cell index is the same
-		if (bits) atomicOr(st.bm_cur + cell, bits);
-	}
+	else red_add_u64(st.conn_cur + cell, (unsigned long long)cnt + (sum << 32));	// packed {count, kbytes}
 }
 
 // all 32 lanes call this; lanes with active == false only take part in the collectives.
 // Group sums use a shuffle loop bounded by the largest group of the warp (typically 1-4): redux with per-lane masks would
 // make the compiler iterate over every distinct group. No global load anywhere: the updates are fire-and-forget REDs.
 template <typename HotTable>
-__device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool active, uint32_t cell, int data, uint32_t bits = 0)
+__device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool active, uint32_t cell, int data)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t id = active ? cell : (0x80000000u | (uint32_t)lane);
@@ -110,8 +101,7 @@ __device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool
 	for (uint32_t t = 1; t < maxcnt; ++t) {
 		const int src = rest ? (__ffs(rest) - 1) : lane;
 		const int other = __shfl_sync(0xffffffffu, data, src);
-		const uint32_t obits = __shfl_sync(0xffffffffu, bits, src);
-		if (rest) { sum += other; gmax = max(gmax, other); bits |= obits; rest &= rest - 1; }
+		if (rest) { sum += other; gmax = max(gmax, other); rest &= rest - 1; }
 	}
 
 	if (!active || (m & ((1u << lane) - 1u))) return;		// group leader = lowest lane
@@ -133,11 +123,8 @@ __device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool
 			if (!hit && tag2 == 0) { const uint32_t t2 = atomicCAS(&hot.tag[h2], 0u, cell + 1); if (t2 == 0 || t2 == cell + 1) { hit = true; h = h2; } }
 		}
 	}
-	if (hit) {
-		atomicAdd(&hot.count[h], cnt); atomicAdd(&hot.sum[h], (unsigned long long)sum); atomicMax(&hot.vmax[h], gmax);
-		if (bits) atomicOr(&hot.bits[h], bits);
-	}
-	else cell_add_global(st, cell, cnt, (unsigned long long)sum, gmax, bits);
+	if (hit) { atomicAdd(&hot.count[h], cnt); atomicAdd(&hot.sum[h], (unsigned long long)sum); atomicMax(&hot.vmax[h], gmax); }
+	else cell_add_global(st, cell, cnt, (unsigned long long)sum, gmax);
 }
 
 __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t rank)
@@ -155,13 +142,15 @@ __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t
 }
 
 // The kernel runs as a persistent tile pipeline. A CTA takes a tile of INGEST_TILE events and
-//   phase 1 (one event per thread and round, fully converged): 2 x 128-bit load, shard filter, id -> slot lookup, then the
-//           decoded record {slot, value, flow_key} goes to shared memory and its index to the queue of its kind
-//           (RESP / TCP / TASK; ballot + one shared-memory atomic per warp and kind);
-//   phase 2 (converged per kind): every warp strides over one queue at a time, so the RESP histogram code, the count-min
-//           rows (one (event, row) pair per lane), the HLL updates and the three task histograms (one (event, histogram)
-//           pair per lane) each run with all lanes doing the same thing instead of serialising 70/20/10-divergent branches.
-// RESP sort keys are written compacted (one global cursor bump per tile), so the radix sort never sees a non-RESP slot.
+//   phase 1 (one event per thread and round, fully converged): 2 x 128-bit load, shard filter, id -> slot lookup. A RESP
+//           sample becomes its sort key {slot, usec, client port & 31} in the tile's key queue — its histogram cell, CONN_BITMAP
+//           bit and t-digest share are all produced later from the SORTED keys, where equal cells are contiguous runs
+//           (td_sums_kernel). TCP / TASK events leave their decoded record in shared memory and their index in the queue of
+//           their kind (ballot + one shared-memory atomic per warp and kind);
+//   phase 2 (converged per kind): every warp strides over one queue at a time, so the count-min rows (one (event, row) pair
+//           per lane), the HLL updates and the three task histograms (one (event, histogram) pair per lane) each run with all
+//           lanes doing the same thing instead of serialising 70/20/10-divergent branches;
+//   phase 3: the tile's RESP keys go out as one contiguous, coalesced run (one global cursor bump per tile).
 
 struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
 
@@ -192,18 +181,20 @@ template <int INGEST_THREADS, bool STAGE, int INGEST_EPT = 4>
 struct IngestSharedT
 {
 	static constexpr int INGEST_TILE = INGEST_THREADS * INGEST_EPT;
-	using HotTable = HotTableT<(INGEST_THREADS >= 256 ? 10 : 9)>;
+	using HotTable = HotTableT<(INGEST_TILE >= 1024 ? 10 : 9)>;
 	alignas(128) uint4	evbuf[STAGE ? INGEST_TILE * 2 : 1];	// next tile of 32-byte events, filled by cp.async.bulk
 	unsigned long long	mbar;
 	HotTable	hot;
-	IngestRec	rec[INGEST_TILE];
-	uint16_t	q_resp[INGEST_TILE], q_tcp[INGEST_TILE], q_task[INGEST_TILE];
+	unsigned long long kq[INGEST_TILE];		// RESP sort keys of the tile, compacted
+	IngestRec	rec[INGEST_TILE];		// decoded TCP / TASK events, by tile position
+	uint16_t	q_tcp[INGEST_TILE], q_task[INGEST_TILE];
 	uint32_t	qn[2][4];		// per tile parity: n_resp, n_tcp, n_task (double-buffered: no barrier to reset them)
 	unsigned long long key_base;
-	uint32_t	max_value;		// largest RESP usec seen by this CTA (sizes the radix sort)
+	uint32_t	max_value;		// largest RESP msec seen by this CTA (sizes the radix sort)
 };
 
-__device__ __forceinline__ void queue_push(bool pred, uint16_t *q, uint32_t *qn, uint16_t item)
+template <typename T>
+__device__ __forceinline__ void queue_push(bool pred, T *q, uint32_t *qn, T item)
 {
 	const uint32_t m = __ballot_sync(0xffffffffu, pred);
 	if (!m) return;
@@ -223,11 +214,12 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	constexpr int INGEST_TILE = IngestShared::INGEST_TILE;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	IngestShared &S = *reinterpret_cast<IngestShared *>(smem_raw);
-	unsigned long long c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;
+	uint32_t c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;	// per thread: < 2^32 events per launch
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint64_t ntiles = (n + INGEST_TILE - 1) / INGEST_TILE;
+	uint32_t max_ms = 0;
 
-	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; S.hot.bits[i] = 0; }
+	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
 	if (threadIdx.x < 8) (&S.qn[0][0])[threadIdx.x] = 0;
 	if (threadIdx.x == 0) S.max_value = 0;
 	if (STAGE && threadIdx.x == 0) mbar_init(&S.mbar, 1);
@@ -263,13 +255,12 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }	// type 0xFFFF: padding, not counted
 		}
 		// decode; put the first id-table probe of all EPT events in flight before any of them is resolved
-		unsigned long long svc[INGEST_EPT];
 		uint4 praw[INGEST_EPT];
 		uint32_t ppos[INGEST_EPT];
 		uint32_t kind[INGEST_EPT];		// 0 none, GYSK_EV_RESP, 1 tcp (stored as GYSK_EV_ACCEPT), GYSK_EV_TASK
 #pragma unroll
 		for (int k = 0; k < INGEST_EPT; ++k) {
-			svc[k] = ((unsigned long long)ra[k].y << 32) | ra[k].x;
+			const unsigned long long svc = ((unsigned long long)ra[k].y << 32) | ra[k].x;
 			const uint32_t value = rb[k].x, host_idx = rb[k].y;
 			const uint32_t type = rb[k].w & 0xFFFFu;
 			const bool pad = tbase + (uint64_t)k * INGEST_THREADS + threadIdx.x >= n;
@@ -283,9 +274,9 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				c_in++;
 				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
 				// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-				if (svc[k] != 0 && (is_tcp || is_task || (is_resp && value / 1000u <= 1000000u))) {
+				if (svc != 0 && (is_tcp || is_task || (is_resp && value / 1000u <= 1000000u))) {
 					kind[k] = is_resp ? (uint32_t)GYSK_EV_RESP : (is_task ? (uint32_t)GYSK_EV_TASK : (uint32_t)GYSK_EV_ACCEPT);
-					praw[k] = table_probe_first(is_task ? st.task_tbl : st.svc_tbl, svc[k], ppos[k]);
+					praw[k] = table_probe_first(is_task ? st.task_tbl : st.svc_tbl, svc, ppos[k]);
 				}
 				else c_drop++;
 			}
@@ -296,20 +287,24 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			int slot = -1;
 			if (kind[k]) {
 				// one id lookup for all three event kinds (services and tasks live in separate tables)
-				slot = table_resolve(is_task ? st.task_tbl : st.svc_tbl, svc[k], st.auto_register, rb[k].y, ppos[k], praw[k]);
+				slot = table_resolve(is_task ? st.task_tbl : st.svc_tbl, ((unsigned long long)ra[k].y << 32) | ra[k].x, st.auto_register, rb[k].y, ppos[k], praw[k]);
 				if (slot < 0) c_drop++;
 				else if (is_resp) c_resp++;
 				else if (is_tcp) c_tcp++;
 				else c_task++;
 			}
 			const uint16_t pos = (uint16_t)(k * INGEST_THREADS + threadIdx.x);
-			if (slot >= 0) {
+			const bool ok = slot >= 0;
+			if (ok && !is_resp) {
 				IngestRec r; r.slot = (uint32_t)slot; r.value = rb[k].x; r.flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
 				S.rec[pos] = r;
 			}
-			queue_push(slot >= 0 && is_resp, S.q_resp, &qn[0], pos);
-			queue_push(slot >= 0 && is_tcp, S.q_tcp, &qn[1], pos);
-			queue_push(slot >= 0 && is_task, S.q_task, &qn[2], pos);
+			// RESP: {slot, usec, client port & 31 (CONN_BITMAP index, common/gy_socket_stat.h:403-410)}
+			const unsigned long long key = ((unsigned long long)(uint32_t)slot << KEY_SLOT_SHIFT) | ((unsigned long long)rb[k].x << KEY_VALUE_SHIFT) | (ra[k].z & 0x1Fu);
+			if (ok && is_resp) max_ms = max(max_ms, rb[k].x / 1000u);	// msec is enough: bits(usec) <= bits(msec) + 10
+			queue_push(ok && is_resp, S.kq, &qn[0], key);
+			queue_push(ok && is_tcp, S.q_tcp, &qn[1], pos);
+			queue_push(ok && is_task, S.q_task, &qn[2], pos);
 		}
 		__syncthreads();
 		const uint32_t n_resp = qn[0], n_tcp = qn[1], n_task = qn[2];
@@ -325,7 +320,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			}
 		}
 
-		// ---------------- phase 2b: TCP — count-min rows, one (event, row) pair per lane ----------------
+		// ---------------- phase 2a: TCP — count-min rows, one (event, row) pair per lane ----------------
 		{
 			const uint32_t npairs = n_tcp * st.cms_depth;
 			for (uint32_t p = threadIdx.x; p < npairs; p += INGEST_THREADS) {
@@ -343,13 +338,13 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 					uint32_t idx, rank;
 					hll_idx_rank(r.flow_key, st.hll_p, idx, rank);
 					hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
-					cell = r.slot * HIST_CELLS + HIST_MAX_CELL;
+					cell = r.slot;
 					kb = (int)(r.value >> 10);
 				}
 				cell_add(st, S.hot, act, cell, kb);
 			}
 		}
-		// ---------------- phase 2c: TASK — MAGGR_TASK::set_local_task_state, one (event, histogram) pair per lane ----------------
+		// ---------------- phase 2b: TASK — MAGGR_TASK::set_local_task_state, one (event, histogram) pair per lane ----------------
 		{
 			const uint32_t ntrip = n_task * 3u;
 			for (uint32_t base = wid * 32; base < ntrip; base += INGEST_THREADS) {
@@ -368,32 +363,21 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			}
 		}
 		__syncthreads();			// key_base is visible
-		// ---------------- phase 2d: RESP — GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data, gy_statistics.h:596-623 ----------------
+		// ---------------- phase 3: the tile's RESP keys leave as one coalesced run ----------------
 		{
-			const unsigned long long kb = S.key_base;
-			for (uint32_t base = wid * 32; base < n_resp; base += INGEST_THREADS) {
-				const uint32_t q = base + lane;
-				const bool act = q < n_resp;
-				uint32_t cell = 0, bit = 0; int ms = 0;
-				if (act) {
-					const IngestRec r = S.rec[S.q_resp[q]];
-					bit = 1u << ((uint32_t)r.flow_key & 0x1Fu);		// CONN_BITMAP: client port & 0x1F
-					ms = (int)(r.value / 1000u);
-					cell = r.slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
-					__stcs(keys + kb + q, ((unsigned long long)r.slot << VALUE_BITS) | r.value);
-				}
-				const uint32_t wmax = __reduce_max_sync(0xffffffffu, act ? (uint32_t)ms : 0u);	// msec is enough: bits(usec) <= bits(msec) + 10
-				if (lane == 0 && wmax > S.max_value) atomicMax(&S.max_value, wmax);
-				cell_add(st, S.hot, act, cell, ms, bit);
-			}
+			unsigned long long *dst = keys + S.key_base;
+			for (uint32_t q = threadIdx.x; q < n_resp; q += INGEST_THREADS) __stcs(dst + q, S.kq[q]);
 		}
-		__syncthreads();			// rec / queues may be overwritten by the next tile
+		__syncthreads();			// kq / rec / queues may be overwritten by the next tile
 	}
 
+	max_ms = __reduce_max_sync(0xffffffffu, max_ms);
+	if (lane == 0 && max_ms) atomicMax(&S.max_value, max_ms);
+	__syncthreads();
 	if (threadIdx.x == 0 && S.max_value) atomicMax(st.counters + CTR_MAXVAL, (unsigned long long)S.max_value);
 	// retire: one RED group per privatised cell
 	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) {
-		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i], S.hot.bits[i]);
+		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i]);
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
@@ -407,21 +391,18 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 		c_foreign += __shfl_down_sync(0xffffffffu, c_foreign, off);
 	}
 	if (lane == 0) {
-		if (c_in) atomicAdd(st.counters + CTR_IN, c_in);
-		if (c_drop) atomicAdd(st.counters + CTR_DROPPED, c_drop);
-		if (c_resp) atomicAdd(st.counters + CTR_RESP, c_resp);
-		if (c_tcp) atomicAdd(st.counters + CTR_TCP, c_tcp);
-		if (c_task) atomicAdd(st.counters + CTR_TASK, c_task);
-		if (c_foreign) atomicAdd(st.counters + CTR_FOREIGN, c_foreign);
+		if (c_in) atomicAdd(st.counters + CTR_IN, (unsigned long long)c_in);
+		if (c_drop) atomicAdd(st.counters + CTR_DROPPED, (unsigned long long)c_drop);
+		if (c_resp) atomicAdd(st.counters + CTR_RESP, (unsigned long long)c_resp);
+		if (c_tcp) atomicAdd(st.counters + CTR_TCP, (unsigned long long)c_tcp);
+		if (c_task) atomicAdd(st.counters + CTR_TASK, (unsigned long long)c_task);
+		if (c_foreign) atomicAdd(st.counters + CTR_FOREIGN, (unsigned long long)c_foreign);
 	}
 }
 
 // ---------------------------------------------------------------------------------------------------
 // stable LSD radix sort, 8-bit digits, tile = SORT_TILE keys per CTA of 256 threads
 // ---------------------------------------------------------------------------------------------------
-static constexpr int RS_THREADS = 512;
-static constexpr int RS_WARPS = RS_THREADS / 32;
-static constexpr int RS_ROUNDS = SORT_TILE / RS_THREADS;	// 16 keys per thread
 static constexpr int RADIX = 256;
 
 // one radix pass sorts on an 8-bit digit made of up to two bit fields of the key, so that the unused bits between the usec field
@@ -432,205 +413,211 @@ __device__ __forceinline__ uint32_t key_digit(unsigned long long k, const DigitS
 	return ((uint32_t)(k >> D.s1) & ((1u << D.b1) - 1u)) | (((uint32_t)(k >> D.s2) & ((1u << D.b2) - 1u)) << D.b1);
 }
 
-// per-tile digit histogram -> tile_hist[digit * ntiles + tile]
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long *__restrict__ keys, uint64_t n_host,
-		const unsigned long long *__restrict__ d_n, DigitSpec D, uint32_t *__restrict__ tile_hist, uint32_t ntiles)
-{
-	__shared__ uint32_t hist[RADIX];
-	const uint64_t n = d_n ? *d_n : n_host;
-	const uint32_t tile = blockIdx.x;
+// ---------------------------------------------------------------------------------------------------
+// one-sweep radix pass: 16 B of HBM traffic per key and pass (read once, write once)
+//
+//   os_hist_kernel   one read of the keys fills the GLOBAL digit histograms of every pass (digits are fixed before the first
+//                    pass, and a stable pass does not change how many keys carry a digit value);
+//   os_pass_kernel   a CTA takes the next tile (ticket from an atomic counter, so every predecessor tile is already running),
+//                    ranks its keys per digit, publishes the tile's digit counts and obtains the number of keys with the same
+//                    digit in all earlier tiles by decoupled look-back over the status words of its predecessors
+//                    (status word = 2-bit state | 30-bit count: 1 = this tile's count, 2 = inclusive prefix up to this tile),
+//                    reorders the tile by digit in shared memory and writes every digit's run to its final place.
+// Stability: tiles are ordered by ticket = tile index, ranks inside a tile follow the input order (warp, round, lane).
+// ---------------------------------------------------------------------------------------------------
+static constexpr int OS_THREADS = 256;			// == RADIX: thread d owns digit d in the per-digit steps
+static constexpr int OS_WARPS = OS_THREADS / 32;
+static constexpr int OS_KPT = SORT_TILE / OS_THREADS;	// 16 keys per thread
+static constexpr int OS_MAX_PASSES = 8;
+static constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_COUNT_MASK = (1u << 30) - 1u;
+static_assert(OS_THREADS == RADIX, "one thread per digit");
 
-	if (threadIdx.x < RADIX) hist[threadIdx.x] = 0;
+struct DigitSpecs { DigitSpec d[OS_MAX_PASSES]; int np; };
+
+static constexpr int OSH_COPIES = 8;			// lane-privatised histogram copies (lane & 7), skewed by one bank each
+static constexpr int OSH_STRIDE = RADIX + 1;
+
+__global__ void __launch_bounds__(512) os_hist_kernel(const unsigned long long *__restrict__ keys, uint64_t n, DigitSpecs P,
+		uint32_t *__restrict__ ghist /* [np][256] */)
+{
+	extern __shared__ __align__(16) unsigned char osh_smem[];
+	uint32_t (*h)[OSH_COPIES][OSH_STRIDE] = reinterpret_cast<uint32_t (*)[OSH_COPIES][OSH_STRIDE]>(osh_smem);	// [np][copies][257]
+	const int copy = threadIdx.x & (OSH_COPIES - 1);
+
+	for (int i = threadIdx.x; i < P.np * OSH_COPIES * OSH_STRIDE; i += blockDim.x) (&h[0][0][0])[i] = 0;
 	__syncthreads();
 
-	const uint64_t base = (uint64_t)tile * SORT_TILE;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 2;
+	for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+		unsigned long long k0, k1 = 0;
+		const bool two = i + 1 < n;
+		if (two) { const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2 *>(keys + i)); k0 = v.x; k1 = v.y; }
+		else k0 = keys[i];
 #pragma unroll
-	for (int r = 0; r < RS_ROUNDS; ++r) {
-		const uint64_t i = base + (uint64_t)r * RS_THREADS + threadIdx.x;
-		if (i < n) {
-			const unsigned long long k = keys[i];
-			if (k != KEY_SENTINEL) atomicAdd(&hist[key_digit(k, D)], 1u);
+		for (int p = 0; p < OS_MAX_PASSES; ++p) {
+			if (p < P.np) {
+				atomicAdd(&h[p][copy][key_digit(k0, P.d[p])], 1u);
+				if (two) atomicAdd(&h[p][copy][key_digit(k1, P.d[p])], 1u);
+			}
 		}
 	}
 	__syncthreads();
-	if (threadIdx.x < RADIX) tile_hist[(size_t)threadIdx.x * ntiles + tile] = hist[threadIdx.x];
+	for (int j = threadIdx.x; j < P.np * RADIX; j += blockDim.x) {
+		const int p = j >> 8, d = j & (RADIX - 1);
+		uint32_t s = 0;
+#pragma unroll
+		for (int c = 0; c < OSH_COPIES; ++c) s += h[p][c][d];
+		if (s) atomicAdd(&ghist[j], s);
+	}
 }
 
-// exclusive scan of a u32 array of length len: reduce / scan block sums / apply
-static constexpr int SCAN_THREADS = 256;
-static constexpr int SCAN_ITEMS = 8;
-static constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
-
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total_out, uint32_t *smem /* >= 32 */)
+// exclusive scan over the 256 threads of the CTA of a packed pair {hi: < 2^32, lo: < 2^16 summed}; smem >= 8 u64
+__device__ __forceinline__ unsigned long long os_block_exclusive_scan(unsigned long long v, unsigned long long *smem)
 {
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	uint32_t incl = v;
+	unsigned long long incl = v;
 
 #pragma unroll
 	for (int off = 1; off < 32; off <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+		const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, off);
 		if (lane >= off) incl += t;
 	}
 	if (lane == 31) smem[wid] = incl;
 	__syncthreads();
-	if (wid == 0) {
-		const int nw = blockDim.x >> 5;
-		uint32_t w = lane < nw ? smem[lane] : 0, wi = w;
+	unsigned long long woff = 0;
 #pragma unroll
-		for (int off = 1; off < 32; off <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xffffffffu, wi, off);
-			if (lane >= off) wi += t;
-		}
-		smem[lane] = wi - w;			// exclusive warp offsets
-		if (lane == nw - 1 && total_out) *total_out = wi;
-	}
-	__syncthreads();
-	const uint32_t res = smem[wid] + incl - v;
-	__syncthreads();
-	return res;
+	for (int w = 0; w < OS_WARPS; ++w) if (w < wid) woff += smem[w];
+	return woff + incl - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t *__restrict__ in, uint32_t len, uint32_t *__restrict__ block_sums)
-{
-	__shared__ uint32_t smem[32];
-	__shared__ uint32_t total;
-	const uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
-	uint32_t s = 0;
-
-#pragma unroll
-	for (int j = 0; j < SCAN_ITEMS; ++j) if (base + j < len) s += in[base + j];
-	block_exclusive_scan(s, &total, smem);
-	if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-// single CTA: exclusive scan of block_sums[nblocks] in place; grand total -> *total_out (u64 counter)
-__global__ void __launch_bounds__(1024) scan_blocksums_kernel(uint32_t *block_sums, uint32_t nblocks, unsigned long long *total_out)
-{
-	__shared__ uint32_t smem[32];
-	__shared__ uint32_t chunk_total;
-	uint32_t carry = 0;
-
-	for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
-		const uint32_t i = base + threadIdx.x;
-		const uint32_t v = i < nblocks ? block_sums[i] : 0;
-		const uint32_t ex = block_exclusive_scan(v, &chunk_total, smem);
-		if (i < nblocks) block_sums[i] = carry + ex;
-		carry += chunk_total;
-		__syncthreads();
-	}
-	if (threadIdx.x == 0 && total_out) *total_out = carry;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t *__restrict__ data, uint32_t len, const uint32_t *__restrict__ block_sums)
-{
-	__shared__ uint32_t smem[32];
-	const uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
-	uint32_t v[SCAN_ITEMS], s = 0;
-
-#pragma unroll
-	for (int j = 0; j < SCAN_ITEMS; ++j) { v[j] = base + j < len ? data[base + j] : 0; s += v[j]; }
-	uint32_t ex = block_exclusive_scan(s, nullptr, smem) + block_sums[blockIdx.x];
-#pragma unroll
-	for (int j = 0; j < SCAN_ITEMS; ++j) { if (base + j < len) data[base + j] = ex; ex += v[j]; }
-}
-
-// scatter one tile to its stable positions. Thread t of warp w holds keys w*256 + r*32 + lane (r = 0..7), i.e. ascending input
-// order is (warp, round, lane); ranks come from match.any groups so equal digits keep that order. The tile is first reordered by
-// digit in shared memory, then written out by consecutive threads: every digit's keys leave as one contiguous run (full 32-byte
-// sectors) instead of 4096 scattered 8-byte stores.
-struct ScatterShared
+struct OneSweepShared
 {
 	unsigned long long	keys[SORT_TILE];		// tile reordered by digit
-	uint32_t		whist[RS_WARPS][RADIX];		// per-warp digit counts, then local start of (warp, digit)
+	uint32_t		whist[OS_WARPS][RADIX];		// per-warp digit counts, then exclusive prefix over the warps
 	uint32_t		dstart[RADIX];			// tile-local start of each digit
-	uint32_t		goff[RADIX];			// global position of the tile's first key of each digit
-	uint32_t		wsum[RS_WARPS];
-	uint32_t		nvalid;				// keys of the tile that are not sentinels
+	uint32_t		goff[RADIX];			// output index of tile-local position 0 of each digit's run (mod 2^32)
+	unsigned long long	scan[OS_WARPS];
+	float			fscan[OS_WARPS];
+	uint32_t		tile;
 };
 
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
-		uint64_t n_host, const unsigned long long *__restrict__ d_n, DigitSpec D, const uint32_t *__restrict__ tile_offs, uint32_t ntiles)
+__global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
+		uint32_t n, DigitSpec D, const uint32_t *__restrict__ ghist /* [256] of this pass */, uint32_t *__restrict__ status /* [ntiles][256] */,
+		uint32_t *__restrict__ ticket, int rank_mode /* 0 auto, 1 match.any, 2 ballots */)
 {
-	extern __shared__ __align__(16) unsigned char rs_smem[];
-	ScatterShared &S = *reinterpret_cast<ScatterShared *>(rs_smem);
-	const uint64_t n = d_n ? *d_n : n_host;
-	const uint32_t tile = blockIdx.x;
+	extern __shared__ __align__(16) unsigned char os_smem[];
+	OneSweepShared &S = *reinterpret_cast<OneSweepShared *>(os_smem);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 
-	if ((uint64_t)tile * SORT_TILE >= n) return;
-
-	for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&S.whist[0][0])[i] = 0;
+	if (threadIdx.x == 0) S.tile = atomicAdd(ticket, 1u);
+	for (int i = threadIdx.x; i < OS_WARPS * RADIX; i += OS_THREADS) (&S.whist[0][0])[i] = 0;
 	__syncthreads();
+	const uint32_t tile = S.tile;
+	const uint32_t wbase = tile * (uint32_t)SORT_TILE + (uint32_t)wid * (OS_KPT * 32);
 
-	unsigned long long k[RS_ROUNDS];
-	uint32_t rank[RS_ROUNDS];
-	const uint64_t wbase = (uint64_t)tile * SORT_TILE + (uint64_t)wid * (RS_ROUNDS * 32);
-
+	unsigned long long k[OS_KPT];
+	uint32_t rk[OS_KPT / 2];			// two 16-bit ranks per word
 #pragma unroll
-	for (int r = 0; r < RS_ROUNDS; ++r) {
-		const uint64_t i = wbase + (uint64_t)r * 32 + lane;
-		k[r] = i < n ? in[i] : KEY_SENTINEL;
+	for (int r = 0; r < OS_KPT; ++r) {
+		const uint32_t i = wbase + (uint32_t)r * 32 + lane;
+		k[r] = i < n ? __ldcs(in + i) : 0ull;
 	}
 
-	// phase A: rank of every key among the keys of its digit inside this warp's chunk (rounds in order, lanes in order),
-	// leaving the per-warp digit counts in whist. One match.any per round; the group leader bumps the warp counter and
-	// hands the previous value to its group.
+	// Lanes holding the same digit form a group. match.any finds the groups in one instruction, but the hardware walks the
+	// distinct values of the warp one by one (ADU pipe: 73 % busy on a pass whose digits are uniform, ncu r01); eight ballots —
+	// one per digit bit — cost the same whatever the data. The CTA picks per pass: expected number of distinct digits among 32
+	// keys, from the global histogram of the pass.
+	bool use_ballot;
+	{
+		const float pd = (float)ghist[threadIdx.x] / (float)n;
+		float q = 1.f - pd; q *= q; q *= q; q *= q; q *= q; q *= q;		// (1 - p)^32
+		float distinct = 1.f - q;
 #pragma unroll
-	for (int r = 0; r < RS_ROUNDS; ++r) {
-		const bool valid = k[r] != KEY_SENTINEL;
+		for (int off = 16; off > 0; off >>= 1) distinct += __shfl_xor_sync(0xffffffffu, distinct, off);
+		if (lane == 0) S.fscan[wid] = distinct;
+		__syncthreads();
+		float tot = 0.f;
+#pragma unroll
+		for (int w = 0; w < OS_WARPS; ++w) tot += S.fscan[w];
+		use_ballot = rank_mode == 2 || (rank_mode == 0 && tot > 10.f);
+	}
+	const bool partial = (tile + 1) * (uint32_t)SORT_TILE > n;
+
+	// rank of every key among the keys of its digit inside this warp's chunk (rounds in order, lanes in order); the group
+	// leader bumps the warp's digit counter and hands the previous value to its group
+#pragma unroll
+	for (int r = 0; r < OS_KPT; ++r) {
+		const bool valid = wbase + (uint32_t)r * 32 + lane < n;
 		const uint32_t d = valid ? key_digit(k[r], D) : (0x100u + lane);
-		const uint32_t m = __match_any_sync(0xffffffffu, d);
+		uint32_t m;
+		if (use_ballot) {
+			m = 0xffffffffu;
+#pragma unroll
+			for (int b = 0; b < 8; ++b) {
+				const bool bit = (d >> b) & 1u;
+				const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+				m &= bit ? bal : ~bal;
+			}
+			if (partial) m &= __ballot_sync(0xffffffffu, valid);
+		}
+		else m = __match_any_sync(0xffffffffu, d);
 		const int leader = __ffs(m) - 1;
 		uint32_t old = 0;
 		if (valid && lane == leader) { old = S.whist[wid][d]; S.whist[wid][d] = old + __popc(m); }
 		__syncwarp();
-		old = __shfl_sync(0xffffffffu, old, leader);
-		rank[r] = old + __popc(m & lt_mask);
+		old = __shfl_sync(0xffffffffu, old, leader & 31);
+		const uint32_t rank = old + __popc(m & lt_mask);
+		if (r & 1) rk[r >> 1] |= rank << 16; else rk[r >> 1] = rank;
 	}
 	__syncthreads();
 
-	// per digit: exclusive prefix over warps, total, and (block scan over the 256 digit totals) the tile-local digit start
+	// thread d: prefix over the warps, the tile's count of digit d -> published at once, so successors can look back through it
+	const uint32_t d = threadIdx.x;
 	uint32_t dtotal = 0;
-	if (threadIdx.x < RADIX) {
-		const uint32_t d = threadIdx.x;
-		uint32_t run = 0;
 #pragma unroll
-		for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
-		dtotal = run;
-		S.goff[d] = tile_offs[(size_t)d * ntiles + tile];
+	for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = dtotal; dtotal += t; }
+	st_volatile_u32(status + (size_t)tile * RADIX + d, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | dtotal);
+
+	// {global count of digit d, tile count of digit d} -> exclusive scans over the digits in one go
+	const unsigned long long sc = os_block_exclusive_scan(((unsigned long long)ghist[d] << 16) | dtotal, S.scan);
+	const uint32_t gexcl = (uint32_t)(sc >> 16), dstart = (uint32_t)(sc & 0xFFFFu);
+
+	// decoupled look-back: keys with digit d in the tiles before this one
+	uint32_t excl = 0;
+	if (tile > 0) {
+		uint32_t p = tile - 1;
+		for (;;) {
+			const uint32_t v = ld_volatile_u32(status + (size_t)p * RADIX + d);
+			if (!(v >> 30)) continue;				// predecessor has its ticket, so it is running: its count will come
+			excl += v & OS_COUNT_MASK;
+			if (v & OS_FLAG_PREFIX) break;
+			--p;
+		}
+		st_volatile_u32(status + (size_t)tile * RADIX + d, OS_FLAG_PREFIX | (excl + dtotal));
 	}
-	{
-		uint32_t incl = dtotal;
+	S.dstart[d] = dstart;
+	S.goff[d] = gexcl + excl - dstart;
+	__syncthreads();
+
+	// reorder the tile by digit in shared memory
 #pragma unroll
-		for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
-		if (lane == 31) S.wsum[wid] = incl;
-		__syncthreads();
-		if (threadIdx.x < RADIX) {
-			uint32_t woff = 0;
-			for (int w = 0; w < wid; ++w) woff += S.wsum[w];		// wid < 8 here
-			S.dstart[threadIdx.x] = woff + incl - dtotal;
-			if (threadIdx.x == RADIX - 1) S.nvalid = woff + incl;
+	for (int r = 0; r < OS_KPT; ++r) {
+		if (wbase + (uint32_t)r * 32 + lane < n) {
+			const uint32_t dd = key_digit(k[r], D);
+			const uint32_t rank = (r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xFFFFu);
+			S.keys[S.dstart[dd] + S.whist[wid][dd] + rank] = k[r];
 		}
 	}
 	__syncthreads();
 
-	// phase B1: reorder the tile by digit in shared memory
-#pragma unroll
-	for (int r = 0; r < RS_ROUNDS; ++r) {
-		if (k[r] != KEY_SENTINEL) {
-			const uint32_t d = key_digit(k[r], D);
-			S.keys[S.dstart[d] + S.whist[wid][d] + rank[r]] = k[r];
-		}
-	}
-	__syncthreads();
-
-	// phase B2: consecutive threads write consecutive keys; a digit's run goes to goff[d] onwards
-	const uint32_t nvalid = S.nvalid;
-	for (uint32_t i = threadIdx.x; i < nvalid; i += RS_THREADS) {
+	// consecutive threads write consecutive keys: every digit's run leaves as full sectors
+	const uint32_t tbase = tile * (uint32_t)SORT_TILE;
+	const uint32_t nvalid = n - tbase < (uint32_t)SORT_TILE ? n - tbase : (uint32_t)SORT_TILE;
+#pragma unroll 4
+	for (uint32_t i = threadIdx.x; i < nvalid; i += OS_THREADS) {
 		const unsigned long long key = S.keys[i];
-		const uint32_t d = key_digit(key, D);
-		out[S.goff[d] + (i - S.dstart[d])] = key;
+		out[S.goff[key_digit(key, D)] + i] = key;
 	}
 }
 
@@ -651,17 +638,17 @@ __global__ void __launch_bounds__(256) td_segments_kernel(const unsigned long lo
 	for (int t = 0; t < TSEG_V + 2; ++t) sl[t] = 0xFFFFFFFFu;
 	if (i0 + TSEG_V <= n) {
 		const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0), c = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
-		sl[1] = (uint32_t)(a.x >> VALUE_BITS); sl[2] = (uint32_t)(a.y >> VALUE_BITS);
-		sl[3] = (uint32_t)(c.x >> VALUE_BITS); sl[4] = (uint32_t)(c.y >> VALUE_BITS);
+		sl[1] = key_slot(a.x); sl[2] = key_slot(a.y);
+		sl[3] = key_slot(c.x); sl[4] = key_slot(c.y);
 	}
 	else {
 #pragma unroll
-		for (int t = 0; t < TSEG_V; ++t) if (i0 + t < n) sl[1 + t] = (uint32_t)(keys[i0 + t] >> VALUE_BITS);
+		for (int t = 0; t < TSEG_V; ++t) if (i0 + t < n) sl[1 + t] = key_slot(keys[i0 + t]);
 	}
 	// neighbours: from the adjacent lanes, the warp's edge lanes load them
 	const uint32_t up = __shfl_up_sync(0xffffffffu, sl[TSEG_V], 1), down = __shfl_down_sync(0xffffffffu, sl[1], 1);
-	sl[0] = lane ? up : ((i0 && i0 - 1 < n) ? (uint32_t)(keys[i0 - 1] >> VALUE_BITS) : 0xFFFFFFFFu);
-	sl[TSEG_V + 1] = lane < 31 ? down : (i0 + TSEG_V < n ? (uint32_t)(keys[i0 + TSEG_V] >> VALUE_BITS) : 0xFFFFFFFFu);
+	sl[0] = lane ? up : ((i0 && i0 - 1 < n) ? key_slot(keys[i0 - 1]) : 0xFFFFFFFFu);
+	sl[TSEG_V + 1] = lane < 31 ? down : (i0 + TSEG_V < n ? key_slot(keys[i0 + TSEG_V]) : 0xFFFFFFFFu);
 
 	uint32_t nstart = 0;
 #pragma unroll
@@ -720,9 +707,16 @@ __global__ void td_plan_kernel(TdParams P, const uint32_t *__restrict__ seg_star
 	}
 }
 
-// (2) sums: one thread per sorted sample. cluster id = position of the sample's rank in the service's bounds; runs of equal
-// (service, cluster) are contiguous in the sorted order, so a warp reduces them with match.any groups and issues one
-// 64-bit RED per group. Skew-immune: a hot service's samples are spread over as many warps as it has samples / 32.
+// (2) sums: one thread per sorted sample. cluster id = position of the sample's rank in the service's bounds; histogram bucket
+// = RESP_TIME_HASH of its msec value. Both are monotone in the rank, so runs of equal (service, cluster, bucket) are contiguous
+// in the sorted order: a lane combines its own consecutive samples, the warp groups the runs with match.any (one group for the
+// whole warp inside a hot service) and the group leader issues
+//   one 64-bit RED with the exact usec sum of the run into the cluster sum (t-digest), and
+//   GY_HISTOGRAM::add_data for the whole run (common/gy_statistics.h:596-623): count and msec sum of the bucket cell, plus the
+//   run's CONN_BITMAP bits (TCP_LISTENER::CONN_BITMAP::add_response, common/gy_socket_stat.h:403-410, transposed: one mask over
+//   (client port & 31) per bucket).
+// max_val_seen_ is the service's last sorted sample: td_merge_kernel records it. Skew-immune: a hot service's samples are spread
+// over as many warps as it has samples / 128, and no cell sees more than one RED per warp.
 __device__ __forceinline__ uint32_t td_cluster_of(const uint32_t *__restrict__ bounds, uint32_t nn, uint32_t r, uint32_t &lo_out, uint32_t &hi_out)
 {
 	uint32_t lo = 0, hi = nn - 1;			// largest j with bounds[j] <= r
@@ -733,7 +727,7 @@ __device__ __forceinline__ uint32_t td_cluster_of(const uint32_t *__restrict__ b
 
 static constexpr int TDS_V = 4;			// consecutive sorted samples per lane
 
-__global__ void __launch_bounds__(256) td_sums_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
+__global__ void __launch_bounds__(256) td_sums_kernel(DevState st, const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
 		const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ plan_bounds, const uint32_t *__restrict__ plan_n,
 		unsigned long long *__restrict__ newsum)
 {
@@ -757,7 +751,7 @@ __global__ void __launch_bounds__(256) td_sums_kernel(const unsigned long long *
 		// sample up, every sample first checks that range
 		uint32_t slot0 = 0xFFFFFFFFu, j0 = 0, lo0 = 1, hi0 = 0;
 		if (lane == 0 && kk[0] != KEY_SENTINEL) {
-			slot0 = (uint32_t)(kk[0] >> VALUE_BITS);
+			slot0 = key_slot(kk[0]);
 			const uint32_t nn = plan_n[slot0], r = (uint32_t)(i0 - seg_start[slot0]);
 			if (nn & 0x80000000u) { j0 = r; lo0 = r; hi0 = r + 1; }
 			else j0 = td_cluster_of(plan_bounds + (size_t)slot0 * PLAN_STRIDE, nn, r, lo0, hi0);
@@ -765,15 +759,20 @@ __global__ void __launch_bounds__(256) td_sums_kernel(const unsigned long long *
 		slot0 = __shfl_sync(0xffffffffu, slot0, 0); j0 = __shfl_sync(0xffffffffu, j0, 0);
 		lo0 = __shfl_sync(0xffffffffu, lo0, 0); hi0 = __shfl_sync(0xffffffffu, hi0, 0);
 
-		// own samples -> runs of equal (service, cluster); sorted input keeps them contiguous
-		uint32_t pg[TDS_V];
-		unsigned long long ps[TDS_V];
-		int np = 0;
+		// own samples -> runs of equal (service, cluster, bucket); sorted input keeps them contiguous. Sample t carries the totals
+		// of its run so far; only the last sample of a run (its tail) is emitted. Everything is indexed statically (registers).
+		unsigned long long pg[TDS_V];		// (slot * TD_CAP + cluster) << 4 | bucket
+		unsigned long long ps[TDS_V];		// usec sum
+		uint32_t pc[TDS_V], pm[TDS_V], pb[TDS_V];	// samples, msec sum, CONN_BITMAP bits
+		bool tail[TDS_V];
 		uint32_t cslot = 0xFFFFFFFFu, cstart = 0, cnn = 0, clo = 1, chi = 0, cj = 0;	// cached lookup of the previous sample
 #pragma unroll
 		for (int t = 0; t < TDS_V; ++t) {
-			if (kk[t] == KEY_SENTINEL) continue;
-			const uint32_t slot = (uint32_t)(kk[t] >> VALUE_BITS), v = (uint32_t)(kk[t] & VALUE_MASK);
+			const bool valid = kk[t] != KEY_SENTINEL;
+			tail[t] = valid;
+			pg[t] = 0xFFFFFFFFFFFFFF00ull + lane; ps[t] = 0; pc[t] = 0; pm[t] = 0; pb[t] = 0;
+			if (!valid) continue;
+			const uint32_t slot = key_slot(kk[t]), v = key_usec(kk[t]), bit = 1u << ((uint32_t)kk[t] & 0x1Fu);
 			if (slot != cslot) { cslot = slot; cstart = seg_start[slot]; cnn = plan_n[slot]; clo = 1; chi = 0; }
 			const uint32_t r = (uint32_t)(i0 + t - cstart);
 			uint32_t j;
@@ -781,33 +780,52 @@ __global__ void __launch_bounds__(256) td_sums_kernel(const unsigned long long *
 			else if (slot == slot0 && r >= lo0 && r < hi0) j = j0;
 			else if (r >= clo && r < chi) j = cj;
 			else { cj = td_cluster_of(plan_bounds + (size_t)slot * PLAN_STRIDE, cnn, r, clo, chi); j = cj; }
-			const uint32_t gid = slot * (uint32_t)TD_CAP + j;
-			if (np && pg[np - 1] == gid) ps[np - 1] += v;
-			else { pg[np] = gid; ps[np] = v; np++; }
+			const uint32_t ms = v / 1000u;			// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678)
+			pg[t] = ((unsigned long long)(slot * (uint32_t)TD_CAP + j) << 4) | (uint32_t)bucket_resp_time((long long)ms);
+			ps[t] = v; pc[t] = 1; pm[t] = ms; pb[t] = bit;
+			if (t > 0 && pg[t] == pg[t - 1]) {		// continues the previous sample's run (an invalid predecessor never matches)
+				ps[t] += ps[t - 1]; pc[t] += pc[t - 1]; pm[t] += pm[t - 1]; pb[t] |= pb[t - 1];
+				tail[t - 1] = false;
+			}
 		}
 
-		// emit the runs: round t handles every lane's t-th run; usually one round, one group for the whole warp
-		const int maxp = (int)__reduce_max_sync(0xffffffffu, (uint32_t)np);
-		for (int t = 0; t < maxp; ++t) {
-			const bool act = t < np;
-			const uint32_t gid = act ? pg[t] : (0xFFFFFF00u + lane);
-			const unsigned long long v = act ? ps[t] : 0ull;		// < 2^33
+		// emit the run tails: round t handles every lane's run ending at its sample t; inside a hot service the only tail of a
+		// lane is its last sample and the whole warp forms one group
+#pragma unroll
+		for (int t = 0; t < TDS_V; ++t) {
+			const bool act = tail[t];
+			if (!__any_sync(0xffffffffu, act)) continue;
+			const unsigned long long gid = act ? pg[t] : (0xFFFFFFFFFFFFFF00ull + lane);
+			const unsigned long long v = act ? ps[t] : 0ull;		// < 2^32
+			uint32_t cnt = act ? pc[t] : 0u, msum = act ? pm[t] : 0u, bits = act ? pb[t] : 0u;	// msum <= 4e6 per lane
 			const uint32_t m = __match_any_sync(0xffffffffu, gid);
 			unsigned long long gsum = v;
 			if (m == 0xffffffffu) {
 				gsum = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)v & 0xFFFFu) +
 						((unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)(v >> 16)) << 16);
+				cnt = __reduce_add_sync(0xffffffffu, cnt);
+				msum = __reduce_add_sync(0xffffffffu, msum);
+				bits = __reduce_or_sync(0xffffffffu, bits);
 			}
 			else {
 				const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(m));
 				uint32_t rest = m & ~(1u << lane);
+				const uint32_t cnt0 = cnt, msum0 = msum, bits0 = bits;
 				for (uint32_t u = 1; u < maxcnt; ++u) {
 					const int src = rest ? (__ffs(rest) - 1) : lane;
-					const unsigned long long other = __shfl_sync(0xffffffffu, v, src);
-					if (rest) { gsum += other; rest &= rest - 1; }
+					const unsigned long long ov = __shfl_sync(0xffffffffu, v, src);
+					const uint32_t oc = __shfl_sync(0xffffffffu, cnt0, src), om = __shfl_sync(0xffffffffu, msum0, src), ob = __shfl_sync(0xffffffffu, bits0, src);
+					if (rest) { gsum += ov; cnt += oc; msum += om; bits |= ob; rest &= rest - 1; }
 				}
 			}
-			if (act && (m & ((1u << lane) - 1u)) == 0) red_add_u64(newsum + gid, gsum);	// gid == slot * TD_CAP + j
+			if (act && (m & ((1u << lane) - 1u)) == 0) {
+				const uint32_t cj2 = (uint32_t)(gid >> 4);			// slot * TD_CAP + cluster
+				const uint32_t cell = (cj2 / (uint32_t)TD_CAP) * HIST_CELLS + ((uint32_t)gid & 15u);
+				red_add_u64(newsum + cj2, gsum);
+				red_add_u64(&st.hist_cur[cell].count, cnt);
+				red_add_u64((unsigned long long *)&st.hist_cur[cell].sum, msum);
+				atomicOr(st.bm_cur + cell, bits);
+			}
 		}
 	}
 }
@@ -837,7 +855,10 @@ __global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, co
 			S.newc[j].mean = __ddiv_rn((double)sums[j], (double)w);		// cluster sums are exact integers
 			S.newc[j].weight = w;
 		}
-		const double bmin = (double)(keys[s0] & VALUE_MASK), bmax = (double)(keys[s0 + n - 1] & VALUE_MASK);
+		const uint32_t us_max = key_usec(keys[s0 + n - 1]);
+		const double bmin = (double)key_usec(keys[s0]), bmax = (double)us_max;
+		// max_val_seen_ of GY_HISTOGRAM::add_data (gy_statistics.h:609-611): the batch maximum is the last sorted sample
+		if (lane == 0) atomicMax(&st.hist_cur[(size_t)slot * HIST_CELLS + HIST_MAX_CELL].sum, (long long)(us_max / 1000u));
 		__syncwarp();
 
 		TdHead head = st.td_head[slot];
@@ -1007,192 +1028,13 @@ int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_
 	return 1;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// warp-autonomous variant of the tile pipeline: every warp owns a 128-event tile, its records and its three queues, so
-// the two phases need only __syncwarp — no block barrier, no global key cursor. A warp writes its RESP sort keys to the 128
-// key slots that belong to its events (keys first, sentinels behind); the first radix pass compacts the sentinels away.
-// The hot-cell table stays shared by the CTA (shared-memory atomics).
-// ---------------------------------------------------------------------------------------------------
-static constexpr int WI_WARPS = 8;
-static constexpr int WI_EPT = 4;
-static constexpr int WI_TILE = 32 * WI_EPT;		// events per warp tile
-
-struct WarpIngestShared
-{
-	using HotTable = HotTableT<10>;
-	HotTable	hot;
-	IngestRec	rec[WI_WARPS][WI_TILE];
-	uint8_t		q_resp[WI_WARPS][WI_TILE], q_tcp[WI_WARPS][WI_TILE], q_task[WI_WARPS][WI_TILE];
-};
-
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(WI_WARPS * 32, MIN_CTAS) ingest_warp_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
-		unsigned long long *__restrict__ keys)
-{
-	__shared__ WarpIngestShared S;
-	unsigned long long c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const uint32_t lt_mask = (1u << lane) - 1u;
-	const uint64_t ntiles = (n + WI_TILE - 1) / WI_TILE;
-	uint32_t max_ms = 0;
-
-	for (int i = threadIdx.x; i < WarpIngestShared::HotTable::N; i += WI_WARPS * 32) {
-		S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; S.hot.bits[i] = 0;
-	}
-	__syncthreads();
-
-	IngestRec *rec = S.rec[wid];
-	uint8_t *q_resp = S.q_resp[wid], *q_tcp = S.q_tcp[wid], *q_task = S.q_task[wid];
-
-	for (uint64_t tile = (uint64_t)blockIdx.x * WI_WARPS + wid; tile < ntiles; tile += (uint64_t)gridDim.x * WI_WARPS) {
-		const uint64_t tbase = tile * WI_TILE;
-		uint32_t n_resp = 0, n_tcp = 0, n_task = 0;		// warp-uniform queue lengths
-
-		// ---------------- phase 1: decode + lookup + enqueue (all lanes converged) ----------------
-		uint4 ra[WI_EPT], rb[WI_EPT];
-#pragma unroll
-		for (int k = 0; k < WI_EPT; ++k) {
-			const uint64_t i = tbase + (uint64_t)k * 32 + lane;
-			if (i < n) {
-				ra[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i));		// streamed once: evict-first
-				rb[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i) + 1);
-			}
-			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }
-		}
-#pragma unroll
-		for (int k = 0; k < WI_EPT; ++k) {
-			const unsigned long long svc_id = ((unsigned long long)ra[k].y << 32) | ra[k].x;
-			const unsigned long long flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
-			const uint32_t value = rb[k].x, host_idx = rb[k].y;
-			const uint32_t type = rb[k].w & 0xFFFFu;
-			const bool pad = tbase + (uint64_t)k * 32 + lane >= n;
-			const bool is_resp = type == GYSK_EV_RESP, is_task = type == GYSK_EV_TASK;
-			const bool is_tcp = type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER;
-			// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
-			// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-			const uint32_t ms = value / 1000u;
-			int slot = -1;
-			bool mine = !pad;
-
-			if (mine && st.world > 1 && (host_idx % st.world) != st.rank) { c_foreign++; mine = false; }
-			if (mine) {
-				c_in++;
-				if (svc_id != 0 && (is_tcp || is_task || (is_resp && ms <= 1000000u)))
-					slot = table_lookup(is_task ? st.task_tbl : st.svc_tbl, svc_id, st.auto_register, host_idx);
-				if (slot < 0) c_drop++;
-				else if (is_resp) c_resp++;
-				else if (is_tcp) c_tcp++;
-				else c_task++;
-			}
-			const uint8_t pos = (uint8_t)(k * 32 + lane);
-			if (slot >= 0) { IngestRec r; r.slot = (uint32_t)slot; r.value = value; r.flow_key = flow_key; rec[pos] = r; }
-			const uint32_t m_resp = __ballot_sync(0xffffffffu, slot >= 0 && is_resp);
-			const uint32_t m_tcp = __ballot_sync(0xffffffffu, slot >= 0 && is_tcp);
-			const uint32_t m_task = __ballot_sync(0xffffffffu, slot >= 0 && is_task);
-			if (slot >= 0) {
-				if (is_resp) q_resp[n_resp + __popc(m_resp & lt_mask)] = pos;
-				else if (is_tcp) q_tcp[n_tcp + __popc(m_tcp & lt_mask)] = pos;
-				else q_task[n_task + __popc(m_task & lt_mask)] = pos;
-			}
-			n_resp += __popc(m_resp); n_tcp += __popc(m_tcp); n_task += __popc(m_task);
-		}
-		__syncwarp();
-
-		// ---------------- phase 2a: TCP — count-min rows, one (event, row) pair per lane ----------------
-		{
-			const uint32_t npairs = n_tcp * st.cms_depth;
-			for (uint32_t p = lane; p < npairs; p += 32) {
-				const uint32_t e = p / st.cms_depth, row = p - e * st.cms_depth;
-				const IngestRec r = rec[q_tcp[e]];
-				red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index(r.flow_key, row, st.cms_wmask), cms_increment(r.value));
-			}
-			for (uint32_t base = 0; base < n_tcp; base += 32) {
-				const uint32_t q = base + lane;
-				const bool act = q < n_tcp;
-				uint32_t cell = 0; int kb = 0;
-				if (act) {
-					const IngestRec r = rec[q_tcp[q]];
-					uint32_t idx, rank;
-					hll_idx_rank(r.flow_key, st.hll_p, idx, rank);
-					hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
-					cell = r.slot * HIST_CELLS + HIST_MAX_CELL;
-					kb = (int)(r.value >> 10);
-				}
-				cell_add(st, S.hot, act, cell, kb);
-			}
-		}
-		// ---------------- phase 2b: TASK — one (event, histogram) pair per lane ----------------
-		{
-			const uint32_t ntrip = n_task * 3u;
-			for (uint32_t base = 0; base < ntrip; base += 32) {
-				const uint32_t p = base + lane;
-				const bool act = p < ntrip;
-				uint32_t cell = 0; int d = 0;
-				if (act) {
-					const uint32_t e = p / 3u, h = p - e * 3u;
-					const IngestRec r = rec[q_task[e]];
-					d = h == 0 ? (int)r.value : (h == 1 ? (int)(uint32_t)r.flow_key : (int)(uint32_t)(r.flow_key >> 32));
-					const uint32_t b = h == 0 ? (uint32_t)bucket_hash_1_3000(d) : (uint32_t)bucket_duration(d);
-					cell = CELL_TASK | (r.slot * 3u * HIST_CELLS + h * HIST_CELLS + b);
-				}
-				cell_add(st, S.hot, act, cell, d);
-			}
-		}
-		// ---------------- phase 2c: RESP — histogram cell + CONN_BITMAP bit + sort key ----------------
-		for (uint32_t base = 0; base < WI_TILE; base += 32) {
-			const uint32_t q = base + lane;
-			const bool act = q < n_resp;
-			uint32_t cell = 0, bit = 0; int ms = 0;
-			unsigned long long key = KEY_SENTINEL;
-			if (act) {
-				const IngestRec r = rec[q_resp[q]];
-				bit = 1u << ((uint32_t)r.flow_key & 0x1Fu);
-				ms = (int)(r.value / 1000u);
-				cell = r.slot * HIST_CELLS + (uint32_t)bucket_resp_time((long long)ms);
-				key = ((unsigned long long)r.slot << VALUE_BITS) | r.value;
-				max_ms = max(max_ms, (uint32_t)ms);
-			}
-			if (tbase + q < n) __stcs(keys + tbase + q, key);		// the tile's key slots: RESP keys, then sentinels
-			if (base < n_resp) cell_add(st, S.hot, act, cell, ms, bit);
-		}
-		__syncwarp();		// rec / queues are rewritten by the next tile
-	}
-
-	__syncthreads();
-	for (int i = threadIdx.x; i < WarpIngestShared::HotTable::N; i += WI_WARPS * 32) {
-		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i], S.hot.bits[i]);
-	}
-
-	max_ms = __reduce_max_sync(0xffffffffu, max_ms);
-#pragma unroll
-	for (int off = 16; off > 0; off >>= 1) {
-		c_in += __shfl_down_sync(0xffffffffu, c_in, off);
-		c_drop += __shfl_down_sync(0xffffffffu, c_drop, off);
-		c_resp += __shfl_down_sync(0xffffffffu, c_resp, off);
-		c_tcp += __shfl_down_sync(0xffffffffu, c_tcp, off);
-		c_task += __shfl_down_sync(0xffffffffu, c_task, off);
-		c_foreign += __shfl_down_sync(0xffffffffu, c_foreign, off);
-	}
-	if (lane == 0) {
-		if (c_in) atomicAdd(st.counters + CTR_IN, c_in);
-		if (c_drop) atomicAdd(st.counters + CTR_DROPPED, c_drop);
-		if (c_resp) { atomicAdd(st.counters + CTR_RESP, c_resp); atomicAdd(st.counters + CTR_NKEYS, c_resp); }
-		if (c_tcp) atomicAdd(st.counters + CTR_TCP, c_tcp);
-		if (c_task) atomicAdd(st.counters + CTR_TASK, c_task);
-		if (c_foreign) atomicAdd(st.counters + CTR_FOREIGN, c_foreign);
-		if (max_ms) atomicMax(st.counters + CTR_MAXVAL, (unsigned long long)max_ms);
-	}
-}
-
-// 256 (default, measured best) / 128 / 2563 (TMA-staged) = CTA tile pipeline shapes; 4 / 40 = warp-autonomous tiles (keys left in
-// event order with sentinels) with 4 / 5 CTAs per SM
+// GYSK_INGEST_VARIANT selects a CTA shape of the tile pipeline for A/B runs: 256 (default, measured best) / 128 / 2563 (TMA-staged
+// tiles) / 2562 / 2568 (2 / 8 events per thread)
 static int ingest_variant()
 {
-	static const int v = []{ const char *e = getenv("GYSK_INGEST_VARIANT"); return e ? atoi(e) : 256; }();
+	static const int v = []{ const char *e = getenv("GYSK_INGEST_VARIANT"); return e ? atoi(e) : 2562; }();
 	return v;
 }
-
-bool ingest_keys_compact() { return ingest_variant() != 40 && ingest_variant() != 4; }
 
 template <int THREADS, int MIN_CTAS, bool STAGE, int EPT = 4>
 static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, int nsm, cudaStream_t s)
@@ -1217,44 +1059,27 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, 2 * sizeof(unsigned long long), s);	// key cursor + max RESP msec of this batch
 	if (variant == 2563) launch_ingest_variant<256, 3, true>(st, d_ev, n, d_keys, nsm, s);
 	else if (variant == 128) launch_ingest_variant<128, 8, false>(st, d_ev, n, d_keys, nsm, s);
-	else if (variant == 256) launch_ingest_variant<256, 4, false>(st, d_ev, n, d_keys, nsm, s);
 	else if (variant == 2562) launch_ingest_variant<256, 5, false, 2>(st, d_ev, n, d_keys, nsm, s);	// 2 events per thread: fewer live registers, 5 CTAs/SM
 	else if (variant == 2568) launch_ingest_variant<256, 3, false, 8>(st, d_ev, n, d_keys, nsm, s);	// 8 events per thread: fewer barriers per event
-	else {
-		const uint64_t want = (n + (uint64_t)WI_TILE * WI_WARPS - 1) / ((uint64_t)WI_TILE * WI_WARPS);
-		const int per_sm = variant == 4 ? 4 : 5;			// 4: 64 registers, no spills; 5: 48 registers, small spills
-		const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * per_sm ? want : (uint64_t)nsm * per_sm);
-		if (per_sm == 4) ingest_warp_kernel<4><<<grid, WI_WARPS * 32, 0, s>>>(st, d_ev, n, d_keys);
-		else ingest_warp_kernel<5><<<grid, WI_WARPS * 32, 0, s>>>(st, d_ev, n, d_keys);
-	}
+	else if (variant == 2662) launch_ingest_variant<256, 6, false, 2>(st, d_ev, n, d_keys, nsm, s);
+	else if (variant == 2581) launch_ingest_variant<256, 8, false, 1>(st, d_ev, n, d_keys, nsm, s);
+	else if (variant == 5122) launch_ingest_variant<512, 2, false, 2>(st, d_ev, n, d_keys, nsm, s);
+	else if (variant == 5123) launch_ingest_variant<512, 3, false, 2>(st, d_ev, n, d_keys, nsm, s);
+	else if (variant == 256) launch_ingest_variant<256, 4, false>(st, d_ev, n, d_keys, nsm, s);
+	else launch_ingest_variant<256, 5, false, 2>(st, d_ev, n, d_keys, nsm, s);
 	return 1;
 }
 
-static int launch_exclusive_scan(uint32_t *d_data, uint32_t len, uint32_t *d_block_sums, unsigned long long *d_total, cudaStream_t s)
-{
-	const uint32_t nblocks = div_up(len, SCAN_CHUNK);
-	scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(d_data, len, d_block_sums);
-	scan_blocksums_kernel<<<1, 1024, 0, s>>>(d_block_sums, nblocks, d_total);
-	scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(d_data, len, d_block_sums);
-	return 3;
-}
-
-// stable LSD radix sort of bufs[start] (n_upper >= *d_n keys) on the significant key bits [lo1, hi1) then [lo2, hi2) (lo2 >= hi1;
-// pass hi2 <= lo2 for a single range): the significant bits are cut into 8-bit digits in order, a digit may straddle the gap.
+// stable LSD radix sort of the n keys in bufs[0] on the significant key bits [lo1, hi1) then [lo2, hi2) (lo2 >= hi1; pass
+// hi2 <= lo2 for a single range): the significant bits are cut into 8-bit digits in order, a digit may straddle the gap.
 // Result in bufs[*which].
-int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_first, uint64_t n_upper, const unsigned long long *d_n, int lo1, int hi1, int lo2, int hi2,
-		int *which, cudaStream_t s)
+static int build_digit_specs(int lo1, int hi1, int lo2, int hi2, DigitSpecs &P)
 {
-	int launches = 0;
-	static bool attr_set = false;
-	if (!attr_set) { cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared)); attr_set = true; }
-	bool first = true;
-	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
-	int w = start;
 	int p1 = lo1, p2 = lo2;			// next unsorted bit of each range
 
+	P.np = 0;
 	if (hi2 < lo2) hi2 = lo2;
-	while (p1 < hi1 || p2 < hi2) {
+	while ((p1 < hi1 || p2 < hi2) && P.np < OS_MAX_PASSES) {
 		DigitSpec D {0, 0, 0, 0};
 		int need = 8;
 		if (p1 < hi1) { D.s1 = p1; D.b1 = hi1 - p1 < need ? hi1 - p1 : need; p1 += D.b1; need -= D.b1; }
@@ -1263,23 +1088,49 @@ int launch_radix_sort_from(const SortTemp &tmp, int start, uint64_t n_first, uin
 			if (D.b1) { D.s2 = p2; D.b2 = take; } else { D.s1 = p2; D.b1 = take; }
 			p2 += take;
 		}
-		// the first pass may run over n_first >= n_upper slots holding sentinels (skipped, so its output is compact)
-		const uint64_t nn = first ? n_first : n_upper;
-		const unsigned long long *dn = (first && n_first != n_upper) ? nullptr : d_n;
-		const uint32_t ntiles = div_up(nn, SORT_TILE);
-		rs_hist_kernel<<<ntiles, RS_THREADS, 0, s>>>(bufs[w], nn, dn, D, tmp.tile_hist, ntiles);
-		launches += 1 + launch_exclusive_scan(tmp.tile_hist, RADIX * ntiles, tmp.scan_tmp, nullptr, s);
-		rs_scatter_kernel<<<ntiles, RS_THREADS, sizeof(ScatterShared), s>>>(bufs[w], bufs[w ^ 1], nn, dn, D, tmp.tile_hist, ntiles);
+		P.d[P.np++] = D;
+	}
+	return (p1 < hi1 || p2 < hi2) ? -1 : 0;		// more than 64 significant bits cannot happen
+}
+
+int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, int lo2, int hi2, int *which, cudaStream_t s)
+{
+	int launches = 0;
+	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
+	int w = 0;
+	DigitSpecs P;
+
+	*which = 0;
+	if (!n_keys) return 0;
+	if (build_digit_specs(lo1, hi1, lo2, hi2, P) || n_keys >= (1ull << 30)) return -1;	// status words carry 30-bit counts
+
+	// one-sweep passes: global digit histograms of all passes from one read, then 16 B per key and pass
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaFuncSetAttribute(os_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepShared));
+		cudaFuncSetAttribute(os_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * OSH_COPIES * OSH_STRIDE * (int)sizeof(uint32_t));
+		attr_set = true;
+	}
+	static const int rank_mode = []{ const char *e = getenv("GYSK_OS_RANK"); return e ? atoi(e) : 0; }();
+	const uint32_t n = (uint32_t)n_keys;
+	const uint32_t ntiles = div_up(n, SORT_TILE);
+	uint32_t *ghist = tmp.os_ghist, *tickets = tmp.os_ghist + OS_MAX_PASSES * RADIX;
+	int dev = 0, nsm = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+
+	cudaMemsetAsync(ghist, 0, (OS_MAX_PASSES * RADIX + OS_MAX_PASSES) * sizeof(uint32_t), s);
+	const uint32_t hgrid = std::min<uint32_t>(div_up(n, 512 * 2 * 4), (uint32_t)nsm * 3);
+	os_hist_kernel<<<hgrid, 512, P.np * OSH_COPIES * OSH_STRIDE * sizeof(uint32_t), s>>>(bufs[w], n, P, ghist);
+	launches++;
+	for (int p = 0; p < P.np; ++p) {
+		cudaMemsetAsync(tmp.tile_status, 0, (size_t)ntiles * RADIX * sizeof(uint32_t), s);
+		os_pass_kernel<<<ntiles, OS_THREADS, sizeof(OneSweepShared), s>>>(bufs[w], bufs[w ^ 1], n, P.d[p], ghist + p * RADIX, tmp.tile_status, tickets + p, rank_mode);
 		launches++;
-		w ^= 1; first = false;
+		w ^= 1;
 	}
 	*which = w;
 	return launches;
-}
-
-int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s)
-{
-	return launch_radix_sort_from(tmp, 0, n_upper, n_upper, d_n, bit_lo, bit_hi, bit_hi, bit_hi, which, s);
 }
 
 // sort the (slot, usec) keys produced by ingest, then fold every touched service's new samples into its digest
@@ -1302,7 +1153,8 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_ev
 
 	// with the warp-autonomous ingest the keys sit at their events' positions with sentinels in between: the first pass reads
 	// n_events slots and compacts, the later passes run over the n keys
-	launches += launch_radix_sort_from(tmp, 0, ingest_keys_compact() ? n : n_events, n, d_nkeys, 0, value_bits, VALUE_BITS, VALUE_BITS + (int)slot_bits, &which, s);
+	(void)n_events;
+	launches += launch_radix_sort(tmp, n, KEY_VALUE_SHIFT, KEY_VALUE_SHIFT + value_bits, KEY_SLOT_SHIFT, KEY_SLOT_SHIFT + (int)slot_bits, &which, s);
 	src = bufs[which];
 
 	td_segments_kernel<<<div_up(n, 256 * TSEG_V), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
@@ -1310,7 +1162,7 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_ev
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 	td_plan_kernel<<<nsm * 2, 128, 0, s>>>(st.td, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
-	td_sums_kernel<<<nsm * 8, 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
+	td_sums_kernel<<<nsm * 8, 256, 0, s>>>(st, src, d_nkeys, tmp.seg_start, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
 	td_merge_kernel<<<nsm * 7, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
 	return launches + 4;
 }
@@ -1357,7 +1209,7 @@ int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int me
 	unsigned long long *d_n = st.counters + CTR_NKEYS;
 	int which = 0, launches = 2;
 	topn_score_kernel<<<div_up(nslots, 256), 256, 0, s>>>(st, nslots, metric, host_filter, tmp.keys_a, d_n);
-	launches += launch_radix_sort(tmp, nslots, d_n, 32, 64, &which, s);
+	launches += launch_radix_sort(tmp, nslots, 32, 64, 64, 64, &which, s);
 	topn_pick_kernel<<<1, 64, 0, s>>>(st, which ? tmp.keys_b : tmp.keys_a, nslots, want, d_out);
 	return launches;
 }

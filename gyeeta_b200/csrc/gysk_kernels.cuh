@@ -36,8 +36,8 @@ struct DevState
 struct SortTemp
 {
 	unsigned long long	*keys_a, *keys_b;	// [max_batch]
-	uint32_t		*tile_hist;		// [256 * max_tiles]
-	uint32_t		*scan_tmp;		// block sums for the scan
+	uint32_t		*tile_status;		// [max_tiles][256] look-back status words of the current radix pass
+	uint32_t		*os_ghist;		// [8][256] global digit histograms of the one-sweep passes + [8] tile tickets
 	uint32_t		*seg_start, *seg_end;	// [max_svcs]
 	uint32_t		*touched;		// [max_svcs]
 	uint32_t		*plan_bounds, *plan_n;	// [max_svcs][TD_CAP + 1], [max_svcs]: cluster boundaries of the batch's runs
@@ -72,13 +72,16 @@ static constexpr int NLEVELS = 2;			// rolling levels beyond the 5-s window: 300
 static constexpr int NSLOTS = 10;			// slots per level (gy_statistics.h:1105)
 static constexpr int SORT_TILE = 4096;		// keys per CTA tile in the radix passes
 static constexpr int VALUE_BITS = 30;		// RESP usec < 2^30 (msec <= 1e6 is enforced at ingest)
+// RESP sort key = {slot : 29 | usec : 30 | client port & 31 : 5}; the radix passes skip the low 5 bits
+static constexpr int KEY_VALUE_SHIFT = 5;
+static constexpr int KEY_SLOT_SHIFT = KEY_VALUE_SHIFT + VALUE_BITS;
 
 // every launcher returns the number of kernel launches it issued
 int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks, cudaStream_t s);
 int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_t n, int is_task, cudaStream_t s);
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s);
 int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_events, uint64_t nkeys, uint32_t nslots, int value_bits, cudaStream_t s);
-int launch_radix_sort(const SortTemp &tmp, uint64_t n_upper, const unsigned long long *d_n, int bit_lo, int bit_hi, int *which, cudaStream_t s);
+int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, int lo2, int hi2, int *which, cudaStream_t s);
 int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int metric, int host_filter, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
 int launch_flush(const DevState &st, uint32_t max_svcs, HistCell *ring_plane0, HistCell *ring_plane1, cudaStream_t s);
 int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, uint32_t max_svcs, uint32_t live_mask0, uint32_t live_mask1,
