@@ -185,24 +185,26 @@ struct IngestSharedT
 	alignas(128) uint4	evbuf[STAGE ? INGEST_TILE * 2 : 1];	// next tile of 32-byte events, filled by cp.async.bulk
 	unsigned long long	mbar;
 	HotTable	hot;
-	unsigned long long kq[INGEST_TILE];		// RESP sort keys of the tile, compacted
-	IngestRec	rec[INGEST_TILE];		// decoded TCP / TASK events, by tile position
-	uint16_t	q_tcp[INGEST_TILE], q_task[INGEST_TILE];
-	uint32_t	qn[2][4];		// per tile parity: n_resp, n_tcp, n_task (double-buffered: no barrier to reset them)
-	unsigned long long key_base;
-	uint32_t	max_value;		// largest RESP msec seen by this CTA (sizes the radix sort)
+	// per-tile state, double-buffered by tile parity: phase 1 of tile t+1 fills one set while stragglers still drain the other
+	unsigned long long kq[2][INGEST_TILE];		// RESP sort keys of the tile, compacted
+	IngestRec	rec[2][INGEST_TILE];		// decoded TCP events from the front, TASK events from the back (together <= tile)
+	uint32_t	qn[3][4];			// n_resp, n_tcp, n_task; three sets in rotation so that a set is cleared a full tile
+							// before its next use (after the barrier of tile t: the set of tile t+2)
+	unsigned long long key_base[2];
+	uint32_t	key_seq[2];			// tile sequence number + 1 once key_base of that parity is valid
+	uint32_t	max_value;			// largest RESP msec seen by this CTA (sizes the radix sort)
 };
 
-template <typename T>
-__device__ __forceinline__ void queue_push(bool pred, T *q, uint32_t *qn, T item)
+// warp-aggregated append: returns this lane's position in the queue (valid where pred)
+__device__ __forceinline__ uint32_t queue_reserve(bool pred, uint32_t *qn)
 {
 	const uint32_t m = __ballot_sync(0xffffffffu, pred);
-	if (!m) return;
+	if (!m) return 0;
 	const int lane = threadIdx.x & 31;
 	uint32_t base = 0;
 	if (lane == __ffs(m) - 1) base = atomicAdd(qn, (uint32_t)__popc(m));
 	base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-	if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = item;
+	return base + __popc(m & ((1u << lane) - 1u));
 }
 
 template <int INGEST_THREADS, int MIN_CTAS, bool STAGE, int INGEST_EPT>
@@ -220,8 +222,8 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	uint32_t max_ms = 0;
 
 	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
-	if (threadIdx.x < 8) (&S.qn[0][0])[threadIdx.x] = 0;
-	if (threadIdx.x == 0) S.max_value = 0;
+	if (threadIdx.x < 12) (&S.qn[0][0])[threadIdx.x] = 0;
+	if (threadIdx.x == 0) { S.max_value = 0; S.key_seq[0] = 0; S.key_seq[1] = 0; }
 	if (STAGE && threadIdx.x == 0) mbar_init(&S.mbar, 1);
 	__syncthreads();
 	// prologue: the first tile of this CTA starts flying into shared memory
@@ -231,10 +233,13 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 		tma_load_1d(S.evbuf, ev + b0, (uint32_t)cnt * 32u, &S.mbar);
 	}
 
-	int par = 0;
-	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1) {
+	int par = 0, qi = 0;
+	uint32_t seq = 1;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1, ++seq, qi = qi == 2 ? 0 : qi + 1) {
 		const uint64_t tbase = tile * INGEST_TILE;
-		uint32_t *qn = S.qn[par];
+		uint32_t *qn = S.qn[qi];
+		unsigned long long *kq = S.kq[par];
+		IngestRec *rec = S.rec[par];
 		if (STAGE) mbar_wait(&S.mbar, (uint32_t)par);		// this tile's events have landed (one completion per tile)
 
 		// ---------------- phase 1: decode + lookup + enqueue ----------------
@@ -293,25 +298,33 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				else if (is_tcp) c_tcp++;
 				else c_task++;
 			}
-			const uint16_t pos = (uint16_t)(k * INGEST_THREADS + threadIdx.x);
 			const bool ok = slot >= 0;
-			if (ok && !is_resp) {
-				IngestRec r; r.slot = (uint32_t)slot; r.value = rb[k].x; r.flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
-				S.rec[pos] = r;
-			}
-			// RESP: {slot, usec, client port & 31 (CONN_BITMAP index, common/gy_socket_stat.h:403-410)}
-			const unsigned long long key = ((unsigned long long)(uint32_t)slot << KEY_SLOT_SHIFT) | ((unsigned long long)rb[k].x << KEY_VALUE_SHIFT) | (ra[k].z & 0x1Fu);
 			if (ok && is_resp) max_ms = max(max_ms, rb[k].x / 1000u);	// msec is enough: bits(usec) <= bits(msec) + 10
-			queue_push(ok && is_resp, S.kq, &qn[0], key);
-			queue_push(ok && is_tcp, S.q_tcp, &qn[1], pos);
-			queue_push(ok && is_task, S.q_task, &qn[2], pos);
+			const uint32_t q_resp = queue_reserve(ok && is_resp, &qn[0]);
+			const uint32_t q_tcp = queue_reserve(ok && is_tcp, &qn[1]);
+			const uint32_t q_task = queue_reserve(ok && is_task, &qn[2]);
+			if (ok) {
+				if (is_resp) {
+					// {slot, usec, client port & 31 (CONN_BITMAP index, common/gy_socket_stat.h:403-410)}
+					kq[q_resp] = ((unsigned long long)(uint32_t)slot << KEY_SLOT_SHIFT) | ((unsigned long long)rb[k].x << KEY_VALUE_SHIFT) | (ra[k].z & 0x1Fu);
+				}
+				else {
+					IngestRec r; r.slot = (uint32_t)slot; r.value = rb[k].x; r.flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
+					rec[is_tcp ? q_tcp : (uint32_t)INGEST_TILE - 1u - q_task] = r;
+				}
+			}
 		}
-		__syncthreads();
+		__syncthreads();			// the only block barrier of the tile: queues of this parity are complete
 		const uint32_t n_resp = qn[0], n_tcp = qn[1], n_task = qn[2];
 		// thread 0 bumps the global key cursor now; its round trip to L2 hides behind the TCP and TASK phases
 		if (threadIdx.x == 0) {
-			S.qn[par ^ 1][0] = 0; S.qn[par ^ 1][1] = 0; S.qn[par ^ 1][2] = 0;
-			S.key_base = n_resp ? atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)n_resp) : 0ull;
+			// the set of tile t+2 (== tile t-1): every warp has read its counts (it passed this barrier), and nobody appends
+			// to it before the next barrier
+			uint32_t *qz = S.qn[qi == 0 ? 2 : qi - 1];
+			qz[0] = 0; qz[1] = 0; qz[2] = 0;
+			S.key_base[par] = n_resp ? atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)n_resp) : 0ull;
+			__threadfence_block();
+			*((volatile uint32_t *)&S.key_seq[par]) = seq;
 			// every thread has consumed evbuf (barrier above): stage the next tile of this CTA while phase 2 runs
 			if (STAGE && tile + gridDim.x < ntiles) {
 				const uint64_t b1 = (tile + gridDim.x) * INGEST_TILE;
@@ -325,7 +338,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			const uint32_t npairs = n_tcp * st.cms_depth;
 			for (uint32_t p = threadIdx.x; p < npairs; p += INGEST_THREADS) {
 				const uint32_t e = p / st.cms_depth, row = p - e * st.cms_depth;
-				const IngestRec r = S.rec[S.q_tcp[e]];
+				const IngestRec r = rec[e];
 				red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index(r.flow_key, row, st.cms_wmask), cms_increment(r.value));
 			}
 			// HLL register + the service's exact {count, kbytes} cell
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				const bool act = q < n_tcp;
 				uint32_t cell = 0; int kb = 0;
 				if (act) {
-					const IngestRec r = S.rec[S.q_tcp[q]];
+					const IngestRec r = rec[q];
 					uint32_t idx, rank;
 					hll_idx_rank(r.flow_key, st.hll_p, idx, rank);
 					hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
@@ -353,7 +366,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				uint32_t cell = 0; int d = 0;
 				if (act) {
 					const uint32_t e = p / 3u, h = p - e * 3u;
-					const IngestRec r = S.rec[S.q_task[e]];
+					const IngestRec r = rec[(uint32_t)INGEST_TILE - 1u - e];
 					// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
 					d = h == 0 ? (int)r.value : (h == 1 ? (int)(uint32_t)r.flow_key : (int)(uint32_t)(r.flow_key >> 32));
 					const uint32_t b = h == 0 ? (uint32_t)bucket_hash_1_3000(d) : (uint32_t)bucket_duration(d);
@@ -362,13 +375,13 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				cell_add(st, S.hot, act, cell, d);
 			}
 		}
-		__syncthreads();			// key_base is visible
 		// ---------------- phase 3: the tile's RESP keys leave as one coalesced run ----------------
-		{
-			unsigned long long *dst = keys + S.key_base;
-			for (uint32_t q = threadIdx.x; q < n_resp; q += INGEST_THREADS) __stcs(dst + q, S.kq[q]);
+		if (n_resp) {
+			while (*((volatile uint32_t *)&S.key_seq[par]) != seq) { }		// thread 0's cursor bump has landed (normally long ago)
+			unsigned long long *dst = keys + *((volatile unsigned long long *)&S.key_base[par]);
+			for (uint32_t q = threadIdx.x; q < n_resp; q += INGEST_THREADS) __stcs(dst + q, kq[q]);
 		}
-		__syncthreads();			// kq / rec / queues may be overwritten by the next tile
+		// no barrier here: the next tile fills the other parity; this parity is reused only after the next tile's barrier
 	}
 
 	max_ms = __reduce_max_sync(0xffffffffu, max_ms);
@@ -1062,6 +1075,7 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 	else if (variant == 2562) launch_ingest_variant<256, 5, false, 2>(st, d_ev, n, d_keys, nsm, s);	// 2 events per thread: fewer live registers, 5 CTAs/SM
 	else if (variant == 2568) launch_ingest_variant<256, 3, false, 8>(st, d_ev, n, d_keys, nsm, s);	// 8 events per thread: fewer barriers per event
 	else if (variant == 2662) launch_ingest_variant<256, 6, false, 2>(st, d_ev, n, d_keys, nsm, s);
+	else if (variant == 1282) launch_ingest_variant<128, 10, false, 2>(st, d_ev, n, d_keys, nsm, s);
 	else if (variant == 2581) launch_ingest_variant<256, 8, false, 1>(st, d_ev, n, d_keys, nsm, s);
 	else if (variant == 5122) launch_ingest_variant<512, 2, false, 2>(st, d_ev, n, d_keys, nsm, s);
 	else if (variant == 5123) launch_ingest_variant<512, 3, false, 2>(st, d_ev, n, d_keys, nsm, s);
