@@ -36,10 +36,13 @@ struct IdTable
 	uint32_t	*count;		// slots handed out so far
 	unsigned long long *slot_id;	// optional: slot -> id
 	uint32_t	*slot_host;	// optional: slot -> host index of the inserting event
+	int32_t		*free_n;	// optional: number of recycled slots on the stack (pushed by the eviction kernel at a flush,
+	uint32_t	*free_slots;	//           popped here; the two never run concurrently: same stream)
 };
+static constexpr unsigned long long KEY_TOMBSTONE = ~0ull;	// table entry of an evicted id: never matches, never ends a probe chain
 
 // device counters (index into Engine::d_counters)
-enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_MAXVAL, CTR_NTOUCHED, CTR_MAX = 16 };	// NKEYS, MAXVAL adjacent: reset / read together
+enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_MAXVAL, CTR_NTOUCHED, CTR_NEVICT, CTR_EVICTED_TOTAL, CTR_MAX = 16 };	// NKEYS, MAXVAL adjacent: reset / read together
 
 // ---------------------------------------------------------------------------------------------------
 // jhash: Bob Jenkins lookup2 in the form the reference uses (common/jhash.h:22-35,121-134); seed 0xceedfead
@@ -203,11 +206,20 @@ __device__ __forceinline__ int table_resolve(const IdTable &t, unsigned long lon
 			if (!insert) return -1;
 			k = atomicCAS(&e->key, 0ull, key);
 			if (k == 0) {
-				const uint32_t s = atomicAdd(t.count, 1u);
-				if (s >= t.max_slots) {
-					atomicSub(t.count, 1u);
-					st_volatile_u32(&e->slot1, SLOT_INVALID);
-					return -1;
+				// a slot recycled by an eviction first, else the next fresh one
+				uint32_t s = SLOT_INVALID;
+				if (t.free_n) {
+					const int32_t f = atomicSub(t.free_n, 1);
+					if (f > 0) s = t.free_slots[f - 1];
+					else atomicAdd(t.free_n, 1);
+				}
+				if (s == SLOT_INVALID) {
+					s = atomicAdd(t.count, 1u);
+					if (s >= t.max_slots) {
+						atomicSub(t.count, 1u);
+						st_volatile_u32(&e->slot1, SLOT_INVALID);
+						return -1;
+					}
 				}
 				if (t.slot_id) { t.slot_id[s] = key; t.slot_host[s] = host_idx; }
 				st_volatile_u32(&e->slot1, s + 1);

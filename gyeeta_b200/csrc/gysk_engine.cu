@@ -92,6 +92,19 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n)
 
 } // namespace
 
+// pick up the eviction list of the last flush once its copy has landed (wait = block until it has)
+int gysk::collect_evicted(gysk_engine *e, bool wait)
+{
+	if (!e->evict_pending) return 0;
+	if (wait) CU(e, cudaEventSynchronize(e->ev_evict));
+	else if (cudaEventQuery(e->ev_evict) != cudaSuccess) { cudaGetLastError(); CU(e, cudaEventSynchronize(e->ev_evict)); }
+	const uint64_t cnt = std::min<uint64_t>(e->h_evict[0], e->cfg.max_svcs);
+	e->evicted_ids.assign(e->h_evict + 1, e->h_evict + 1 + cnt);
+	e->tombstones += cnt; e->evicted_total += cnt;
+	e->evict_pending = false;
+	return 0;
+}
+
 // hand the filled part of the current staging buffer to the device
 int gysk::submit_stage(gysk_engine *e)
 {
@@ -336,6 +349,7 @@ void gysk_destroy(gysk_engine *e)
 		if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
 	}
 	for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+	if (e->ev_evict) cudaEventDestroy(e->ev_evict);
 	for (void *p : e->dallocs) cudaFree(p);
 	for (void *p : e->hallocs) cudaFreeHost(p);
 	if (e->stream) cudaStreamDestroy(e->stream);
@@ -386,7 +400,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	}
 
 	DevState &st = e->st;
-	const size_t ns = cfg.max_svcs, nt = cfg.max_tasks;
+	const size_t ns = (size_t)cfg.max_svcs + 1, nt = cfg.max_tasks;		// slot max_svcs = the null slot: never handed out, always pristine
 	const uint32_t scap = pow2_at_least((uint64_t)ns * 2), tcap = pow2_at_least((uint64_t)nt * 2);
 
 #define A(call) do { if ((rc = (call)) != 0) return bail(rc); } while (0)
@@ -394,15 +408,23 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(dalloc(e, &st.svc_tbl.count, 1));
 	A(dalloc(e, &st.slot_id, ns)); A(dalloc(e, &st.slot_host, ns));
 	st.svc_tbl.slot_id = st.slot_id; st.svc_tbl.slot_host = st.slot_host;
+	A(dalloc(e, &st.slot_first_seen, ns)); A(dalloc(e, &st.slot_last_active, ns));
+	A(dalloc(e, &st.evict_list, ns)); A(dalloc(e, &st.evict_ids, ns));
+	A(dalloc(e, &st.svc_tbl.free_n, 1)); A(dalloc(e, &st.svc_tbl.free_slots, ns));
+	A(halloc(e, &e->h_evict, ns + 1));
+	if ((ce = cudaEventCreateWithFlags(&e->ev_evict, cudaEventDisableTiming)) != cudaSuccess) { fail(e, GYSK_ERR_CUDA, "cudaEventCreate", ce); return bail(GYSK_ERR_CUDA); }
 	A(dalloc(e, &st.task_tbl.ent, tcap)); st.task_tbl.mask = tcap - 1; st.task_tbl.max_slots = cfg.max_tasks;
 	A(dalloc(e, &st.task_tbl.count, 1));
 	A(dalloc(e, &st.hist_cur, ns * HIST_CELLS)); A(dalloc(e, &st.hist_last, ns * HIST_CELLS)); A(dalloc(e, &st.hist_all, ns * HIST_CELLS));
-	A(dalloc(e, &st.hist_ring, (size_t)NLEVELS * NSLOTS * ns * HIST_CELLS));
+	A(dalloc(e, &st.hist_ring, (size_t)NLEVELS * NSLOTS * cfg.max_svcs * HIST_CELLS));
 	A(dalloc(e, &st.conn_cur, ns)); A(dalloc(e, &st.conn_last, ns)); A(dalloc(e, &st.conn_all_cnt, ns)); A(dalloc(e, &st.conn_all_kb, ns));
 	A(dalloc(e, &st.bm_cur, ns * HIST_CELLS)); A(dalloc(e, &st.bm_last, ns * HIST_CELLS));
 	A(dalloc(e, &st.hll, ns << cfg.hll_p));
 	A(dalloc(e, &st.td_cent, ns * TD_CAP)); A(dalloc(e, &st.td_head, ns));
 	A(dalloc(e, &st.task_hist, nt * 3 * HIST_CELLS));
+	A(dalloc(e, &st.task_prev, nt * 3)); A(dalloc(e, &st.task_last, nt * 3));
+	A(dalloc(e, &st.task_slot_id, nt)); A(dalloc(e, &st.task_slot_host, nt));
+	st.task_tbl.slot_id = st.task_slot_id; st.task_tbl.slot_host = st.task_slot_host;
 	A(dalloc(e, &st.cms_cur, (size_t)cfg.cms_depth << cfg.cms_log2_width)); A(dalloc(e, &st.cms_last, (size_t)cfg.cms_depth << cfg.cms_log2_width));
 	A(dalloc(e, &st.counters, (size_t)CTR_MAX));
 	st.cms_depth = cfg.cms_depth; st.cms_log2w = cfg.cms_log2_width; st.cms_wmask = (1u << cfg.cms_log2_width) - 1; st.hll_p = cfg.hll_p;
@@ -435,7 +457,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(halloc(e, &e->h_counters, (size_t)CTR_MAX + 2));
 #undef A
 
-	e->kernel_launches += launch_init_state(st, cfg.max_svcs, cfg.max_tasks, e->stream);
+	e->kernel_launches += launch_init_state(st, cfg.max_svcs + 1, cfg.max_tasks, e->stream);
 	if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess || (ce = cudaGetLastError()) != cudaSuccess) {
 		fail(e, GYSK_ERR_CUDA, "engine init", ce); return bail(GYSK_ERR_CUDA);
 	}
@@ -493,7 +515,11 @@ int gysk_get_stats(gysk_engine *e, gysk_stats *out)
 	memset(out, 0, sizeof(*out));
 	out->events_in = e->h_counters[CTR_IN]; out->events_dropped = e->h_counters[CTR_DROPPED];
 	out->events_resp = e->h_counters[CTR_RESP]; out->events_tcp = e->h_counters[CTR_TCP]; out->events_task = e->h_counters[CTR_TASK];
-	out->nsvcs = std::min<uint64_t>((uint32_t)e->h_counters[CTR_MAX], e->cfg.max_svcs);
+	if ((rc = collect_evicted(e, true))) return rc;
+	int32_t nfree = 0;
+	CU(e, cudaMemcpy(&nfree, e->st.svc_tbl.free_n, sizeof(nfree), cudaMemcpyDeviceToHost));
+	out->nsvcs = std::min<uint64_t>((uint32_t)e->h_counters[CTR_MAX], e->cfg.max_svcs) - (uint64_t)std::max(nfree, 0);
+	out->svcs_evicted = e->evicted_total;
 	out->ntasks = std::min<uint64_t>((uint32_t)e->h_counters[CTR_MAX + 1], e->cfg.max_tasks);
 	out->batches = e->batches; out->kernel_launches = e->kernel_launches;
 	out->wire_msgs_ok = e->wire_ok; out->wire_msgs_bad = e->wire_bad;
@@ -768,10 +794,37 @@ int gysk_flush(gysk_engine *e, uint32_t tsec)
 	}
 	e->last_flush_tsec = tsec;
 
-	e->kernel_launches += launch_flush(e->st, e->cfg.max_svcs, planes[0], planes[1], e->stream);
+	if ((rc = collect_evicted(e, false))) return rc;		// list of the previous flush (normally long complete)
+	// tombstones lengthen probe chains: once they fill an eighth of the table, rebuild it from the live slots
+	if (e->tombstones > ((uint64_t)e->st.svc_tbl.mask + 1) / 8) {
+		e->kernel_launches += launch_rebuild_table(e->st, e->cfg.max_svcs, e->stream);
+		e->tombstones = 0;
+	}
+	e->kernel_launches += launch_flush(e->st, e->cfg.max_svcs, planes[0], planes[1], tsec, e->cfg.idle_evict_secs, e->stream);
+	e->kernel_launches += launch_task_flush(e->st, e->cfg.max_tasks, e->stream);
+	if (e->cfg.idle_evict_secs) {
+		// count + ids travel to the host behind the kernels; nobody waits for them here
+		CU(e, cudaMemcpyAsync(e->h_evict, e->st.counters + CTR_NEVICT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+		CU(e, cudaMemcpyAsync(e->h_evict + 1, e->st.evict_ids, (size_t)e->cfg.max_svcs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+		CU(e, cudaEventRecord(e->ev_evict, e->stream));
+		e->evict_pending = true;
+	}
 	std::swap(e->st.cms_cur, e->st.cms_last);
 	CU(e, cudaMemsetAsync(e->st.cms_cur, 0, sizeof(unsigned long long) * ((size_t)e->cfg.cms_depth << e->cfg.cms_log2_width), e->stream));
 	return post_launch(e, "flush");
+}
+
+int gysk_evicted_ids(gysk_engine *e, uint64_t *out, uint32_t cap, uint32_t *n)
+{
+	CHECK_ENGINE(e);
+	if (!n || (!out && cap)) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = collect_evicted(e, true);
+	if (rc) return rc;
+	*n = (uint32_t)e->evicted_ids.size();
+	for (uint32_t i = 0; i < *n && i < cap; ++i) out[i] = e->evicted_ids[i];
+	return GYSK_OK;
 }
 
 // ---- queries ------------------------------------------------------------------------------------------------
@@ -893,6 +946,38 @@ int gysk_export_tdigest(gysk_engine *e, uint64_t id, double *means, uint64_t *we
 	return r.td.n > cap ? GYSK_ERR_NOSPC : GYSK_OK;
 }
 
+// Text form of the Postgres `tdigest` type (extension tvondra/tdigest, loaded by the reference with `create extension if not
+// exists tdigest`, common/gy_query_common.cc:3385-3387; version unpinned there). tdigest_out prints
+//   "flags %d count %ld compression %d centroids %d" followed by " (%lf, %ld)" per centroid, flags = 1 (TDIGEST_STORES_MEAN),
+// and tdigest_in parses the same with sscanf: a row built from this string answers tdigest_percentile(col, p) like the rows the
+// reference aggregates with public.tdigest(expr, 100) (gy_query_common.cc:1805-1858). Means are printed with 17 significant
+// digits (sscanf %lf reads them back exactly). Returns the string length (without NUL), or GYSK_ERR_NOSPC.
+int gysk_tdigest_to_pgtext(const double *means, const uint64_t *weights, uint32_t n, uint32_t compression, char *buf, uint32_t cap)
+{
+	if ((!means || !weights) && n) return GYSK_ERR_INVAL;
+	if (!buf || !cap) return GYSK_ERR_INVAL;
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n; ++i) total += weights[i];
+	int off = snprintf(buf, cap, "flags 1 count %llu compression %u centroids %u", (unsigned long long)total, compression, n);
+	if (off < 0 || (uint32_t)off >= cap) return GYSK_ERR_NOSPC;
+	for (uint32_t i = 0; i < n; ++i) {
+		const int k = snprintf(buf + off, cap - off, " (%.17g, %llu)", means[i], (unsigned long long)weights[i]);
+		if (k < 0 || (uint32_t)(off + k) >= cap) return GYSK_ERR_NOSPC;
+		off += k;
+	}
+	return off;
+}
+
+int gysk_export_tdigest_pgtext(gysk_engine *e, uint64_t id, char *buf, uint32_t cap)
+{
+	double means[TD_CAP], minv = 0, maxv = 0;
+	uint64_t w[TD_CAP];
+	uint32_t n = 0;
+	int rc = gysk_export_tdigest(e, id, means, w, TD_CAP, &n, &minv, &maxv);
+	if (rc) return rc;
+	return gysk_tdigest_to_pgtext(means, w, n, e->cfg.td_compression, buf, cap);
+}
+
 int gysk_query_quantiles(gysk_engine *e, uint64_t id, const double *qs, uint32_t nq, double *out)
 {
 	double means[TD_CAP], minv = 0, maxv = 0;
@@ -943,6 +1028,30 @@ int gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gys
 	CU(e, cudaMemcpyAsync(h_out, d_out, sizeof(gysk_topn_entry) * n, cudaMemcpyDeviceToHost, e->stream));
 	CU(e, cudaStreamSynchronize(e->stream));
 	if ((rc = post_launch(e, "topn"))) return rc;
+	uint32_t k = 0;
+	for (uint32_t i = 0; i < n; ++i) if (h_out[i].glob_id && h_out[i].score) out[k++] = h_out[i];
+	*nout = k;
+	return GYSK_OK;
+}
+
+int gysk_topn_tasks(gysk_engine *e, int metric, uint32_t n, gysk_topn_entry *out, uint32_t *nout)
+{
+	CHECK_ENGINE(e);
+	if (!out || !nout || n == 0 || n > 64 || metric < GYSK_TOPN_TASK_CPU || metric > GYSK_TOPN_TASK_BLKIO_DELAY) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	int rc = sync_locked(e);
+	if (rc) return rc;
+	uint32_t ntasks = 0;
+	CU(e, cudaMemcpy(&ntasks, e->st.task_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	ntasks = std::min(ntasks, std::min(e->cfg.max_tasks, e->cfg.max_batch));
+	gysk_topn_entry *d_out = reinterpret_cast<gysk_topn_entry *>(e->d_flowout);		// QCHUNK * 16 B >= 64 * 24 B
+	CU(e, cudaMemsetAsync(d_out, 0, sizeof(gysk_topn_entry) * n, e->stream));
+	e->kernel_launches += launch_topn_tasks(e->st, e->tmp, ntasks, metric, n, d_out, e->stream);
+	gysk_topn_entry *h_out = reinterpret_cast<gysk_topn_entry *>(e->h_flowout);
+	CU(e, cudaMemcpyAsync(h_out, d_out, sizeof(gysk_topn_entry) * n, cudaMemcpyDeviceToHost, e->stream));
+	CU(e, cudaStreamSynchronize(e->stream));
+	if ((rc = post_launch(e, "topn_tasks"))) return rc;
 	uint32_t k = 0;
 	for (uint32_t i = 0; i < n; ++i) if (h_out[i].glob_id && h_out[i].score) out[k++] = h_out[i];
 	*nout = k;

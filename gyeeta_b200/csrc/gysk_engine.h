@@ -26,6 +26,8 @@ struct MergeState
 	std::vector<uint64_t>	logical_ids;		// dense index -> logical id
 	std::unordered_map<uint64_t, uint32_t> index;	// logical id -> dense index
 	uint32_t		*d_offsets {nullptr}, *d_members {nullptr};	// CSR: logical -> member slots on this GPU
+	unsigned long long	*d_member_ids {nullptr};			// id each member slot held when the map was set
+	uint32_t		nmembers {0};
 	// one arena so that each reduction kind is a single collective
 	uint8_t			*arena {nullptr};
 	size_t			arena_bytes {0};
@@ -81,6 +83,13 @@ struct gysk_engine
 	uint64_t		ring_epoch[gysk::NLEVELS][gysk::NSLOTS];
 	uint32_t		last_flush_tsec {0};
 
+	// idle-service eviction: ids evicted by the last flush arrive lagged (copied behind the flush kernels, read at the next call)
+	unsigned long long	*h_evict {nullptr};			// [0] = count, [1..] = ids (pinned)
+	cudaEvent_t		ev_evict {nullptr};
+	bool			evict_pending {false};
+	std::vector<uint64_t>	evicted_ids;				// of the last completed flush
+	uint64_t		tombstones {0}, evicted_total {0};
+
 	std::unordered_map<uint32_t, gysk_host_summary> host_summ;	// last LISTEN_SUMM_STATS per host (control-plane sized: <= 512 hosts)
 
 	gysk::MergeState	mg;
@@ -97,6 +106,7 @@ int fail(gysk_engine *e, int code, const char *what, cudaError_t ce = cudaSucces
 int post_launch(gysk_engine *e, const char *what);
 int submit_stage(gysk_engine *e);
 int sync_locked(gysk_engine *e);
+int collect_evicted(gysk_engine *e, bool wait);
 void summarize_raw(const gysk_engine *e, const SvcRaw &r, uint64_t id, gysk_svc_summary &o);
 
 #define CU(e, call) do { cudaError_t ce__ = (call); if (ce__ != cudaSuccess) return gysk::fail((e), GYSK_ERR_CUDA, #call, ce__); } while (0)

@@ -48,7 +48,7 @@ __global__ void register_kernel(DevState st, const unsigned long long *ids, uint
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 
-	if (i < n && ids[i]) table_lookup(is_task ? st.task_tbl : st.svc_tbl, ids[i], true);
+	if (i < n && ids[i] && ids[i] != KEY_TOMBSTONE) table_lookup(is_task ? st.task_tbl : st.svc_tbl, ids[i], true);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				c_in++;
 				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
 				// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-				if (svc != 0 && (is_tcp || is_task || (is_resp && value / 1000u <= 1000000u))) {
+				if (svc != 0 && svc != KEY_TOMBSTONE && (is_tcp || is_task || (is_resp && value / 1000u <= 1000000u))) {
 					kind[k] = is_resp ? (uint32_t)GYSK_EV_RESP : (is_task ? (uint32_t)GYSK_EV_TASK : (uint32_t)GYSK_EV_ACCEPT);
 					praw[k] = table_probe_first(is_task ? st.task_tbl : st.svc_tbl, svc, ppos[k]);
 				}
@@ -891,13 +891,28 @@ __global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, co
 // ---------------------------------------------------------------------------------------------------
 // 5-second window roll: last = cur; all += cur; cur = 0  (one thread per histogram cell)
 // ---------------------------------------------------------------------------------------------------
-__global__ void flush_kernel(DevState st, uint32_t nslots, HistCell *__restrict__ ring0, HistCell *__restrict__ ring1)
+//
+// Idle services: the reference deletes a listener that produced no statistics for TIMEOUT_INET_DIAG_SECS
+// (300 s, common/gy_socket_stat.h:997) once it is older than twice that (common/gy_socket_stat.cc:3968-3982: tclock != 0,
+// tclock + 300 s < now, tstart + 600 s < now) and tells madhava with LISTEN_FLAG_DELETE (:4023-4033). Here the flush records,
+// per slot, the first flush that saw it and the last window that held events, and lists the slots that meet the rule.
+__global__ void flush_kernel(DevState st, uint32_t nslots, HistCell *__restrict__ ring0, HistCell *__restrict__ ring1, uint32_t tsec, uint32_t idle_secs)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-
-	if (i >= (uint64_t)nslots * HIST_CELLS) return;
+	const bool valid = i < (uint64_t)nslots * HIST_CELLS;		// nslots * 16: whole half-warps are valid or not
 	const int cell = (int)(i & (HIST_CELLS - 1));
-	const HistCell c = st.hist_cur[i];
+	HistCell c {0, 0};
+	unsigned long long cc = 0;
+	const uint32_t slot = (uint32_t)(i >> 4);
+
+	if (valid) {
+		c = st.hist_cur[i];
+		if (cell == HIST_MAX_CELL) cc = st.conn_cur[slot];
+	}
+	// did the closing window hold any event of this service? (16 lanes = the 15 buckets + the max / conn cell)
+	const uint32_t bal = __ballot_sync(0xffffffffu, valid && (cell == HIST_MAX_CELL ? cc != 0 : c.count != 0));
+	const bool active = ((bal >> (threadIdx.x & 16)) & 0xFFFFu) != 0;
+	if (!valid) return;
 
 	st.bm_last[i] = st.bm_cur[i]; st.bm_cur[i] = 0;		// CONN_BITMAP::clear every 5 s (gy_socket_stat.h:436)
 	st.hist_last[i] = c;
@@ -914,17 +929,80 @@ __global__ void flush_kernel(DevState st, uint32_t nslots, HistCell *__restrict_
 	if (cell == HIST_MAX_CELL) {
 		if (c.sum > st.hist_all[i].sum) st.hist_all[i].sum = c.sum;
 		st.hist_cur[i].count = 0; st.hist_cur[i].sum = LLONG_MIN;
-		const uint32_t slot = (uint32_t)(i >> 4);
-		const unsigned long long cc = st.conn_cur[slot];
 		st.conn_last[slot] = cc;
 		st.conn_all_cnt[slot] += (uint32_t)cc;
 		st.conn_all_kb[slot] += cc >> 32;
 		st.conn_cur[slot] = 0;
+
+		const unsigned long long id = st.slot_id[slot];
+		if (id) {
+			uint32_t first = st.slot_first_seen[slot], last = st.slot_last_active[slot];
+			if (!first) { first = tsec ? tsec : 1u; st.slot_first_seen[slot] = first; }
+			if (active) { last = tsec ? tsec : 1u; st.slot_last_active[slot] = last; }
+			if (idle_secs && last && (uint64_t)last + idle_secs < tsec && (uint64_t)first + 2ull * idle_secs < tsec) {
+				const unsigned long long k = atomicAdd(st.counters + CTR_NEVICT, 1ull);
+				st.evict_list[k] = slot;
+				st.evict_ids[k] = id;
+			}
+		}
 	}
 	else {
 		st.hist_all[i].count += c.count;
 		st.hist_all[i].sum += c.sum;
 		st.hist_cur[i].count = 0; st.hist_cur[i].sum = 0;
+	}
+}
+
+// one CTA per evicted slot (grid-stride): the id's table entry becomes a tombstone, every per-slot array returns to its
+// just-created state and the slot number goes on the free stack for the next unknown id
+__global__ void __launch_bounds__(256) evict_kernel(DevState st, uint32_t max_svcs)
+{
+	const uint32_t nev = (uint32_t)st.counters[CTR_NEVICT];
+
+	for (uint32_t q = blockIdx.x; q < nev; q += gridDim.x) {
+		const uint32_t slot = st.evict_list[q];
+		const unsigned long long id = st.evict_ids[q];
+
+		if (threadIdx.x == 0) {
+			uint32_t pos = uint64_hash(id) & st.svc_tbl.mask;
+			for (uint32_t probe = 0; probe <= st.svc_tbl.mask; ++probe, pos = (pos + 1) & st.svc_tbl.mask) {
+				TblEntry *e = &st.svc_tbl.ent[pos];
+				if (e->key == id) { e->key = KEY_TOMBSTONE; e->slot1 = 0; break; }
+				if (e->key == 0) break;
+			}
+			st.slot_id[slot] = 0; st.slot_host[slot] = 0; st.slot_first_seen[slot] = 0; st.slot_last_active[slot] = 0;
+			st.conn_cur[slot] = 0; st.conn_last[slot] = 0; st.conn_all_cnt[slot] = 0; st.conn_all_kb[slot] = 0;
+			TdHead h; h.total = 0; h.minv = INFINITY; h.maxv = -INFINITY; h.n = 0; h.pad = 0;
+			st.td_head[slot] = h;
+			const int32_t f = atomicAdd(st.svc_tbl.free_n, 1);
+			st.svc_tbl.free_slots[f] = slot;
+			atomicAdd(st.counters + CTR_EVICTED_TOTAL, 1ull);
+		}
+		if (threadIdx.x < HIST_CELLS) {
+			const size_t c = (size_t)slot * HIST_CELLS + threadIdx.x;
+			const HistCell z {0, threadIdx.x == HIST_MAX_CELL ? LLONG_MIN : 0};
+			st.hist_cur[c] = z; st.hist_last[c] = z; st.hist_all[c] = z;
+			st.bm_cur[c] = 0; st.bm_last[c] = 0;
+			for (int pl = 0; pl < NLEVELS * NSLOTS; ++pl) st.hist_ring[((size_t)pl * max_svcs + slot) * HIST_CELLS + threadIdx.x] = HistCell {0, 0};
+		}
+		uint32_t *hw = reinterpret_cast<uint32_t *>(st.hll + ((size_t)slot << st.hll_p));
+		for (uint32_t w = threadIdx.x; w < (1u << st.hll_p) / 4u; w += blockDim.x) hw[w] = 0;
+		for (uint32_t w = threadIdx.x; w < (uint32_t)TD_CAP; w += blockDim.x) st.td_cent[(size_t)slot * TD_CAP + w] = Centroid {0.0, 0ull};
+	}
+}
+
+// tombstones only go away by rebuilding: clear the table, re-insert the ids of the live slots (slot numbers stay)
+__global__ void rebuild_table_kernel(DevState st, uint32_t max_svcs)
+{
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= max_svcs) return;
+	const unsigned long long id = st.slot_id[slot];
+	if (!id) return;
+	uint32_t pos = uint64_hash(id) & st.svc_tbl.mask;
+	for (;;) {
+		const unsigned long long k = atomicCAS(&st.svc_tbl.ent[pos].key, 0ull, id);
+		if (k == 0) { st.svc_tbl.ent[pos].slot1 = slot + 1; return; }
+		pos = (pos + 1) & st.svc_tbl.mask;
 	}
 }
 
@@ -1228,10 +1306,74 @@ int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int me
 	return launches;
 }
 
-int launch_flush(const DevState &st, uint32_t nslots, HistCell *ring_plane0, HistCell *ring_plane1, cudaStream_t s)
+// per-task window of the three MTASK_HIST histograms: totals now minus totals at the previous flush (nothing on the ingest path)
+__global__ void task_flush_kernel(DevState st, uint32_t max_tasks)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;		// (task, histogram)
+	if (i >= max_tasks * 3u) return;
+	const HistCell *h = st.task_hist + (size_t)i * HIST_CELLS;
+	HistCell tot {0, 0};
+	for (int b = 0; b < HIST_MAX_CELL; ++b) { tot.count += h[b].count; tot.sum += h[b].sum; }
+	const HistCell prev = st.task_prev[i];
+	st.task_last[i] = HistCell {tot.count - prev.count, tot.sum - prev.sum};
+	st.task_prev[i] = tot;
+}
+
+int launch_task_flush(const DevState &st, uint32_t max_tasks, cudaStream_t s)
+{
+	task_flush_kernel<<<div_up((uint64_t)max_tasks * 3, 256), 256, 0, s>>>(st, max_tasks);
+	return 1;
+}
+
+// top-N aggregated processes of the last closed window by cpu / cpu delay / blkio delay: the atask_top_cpu_ / _cpu_delay_ /
+// _io_delay_ queues of partha_aggr_task_state (server/gy_mconnhdlr.cc:10020-10065; entries with a zero metric never enter)
+__global__ void topn_task_score_kernel(DevState st, uint32_t ntasks, int metric, unsigned long long *__restrict__ keys)
+{
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= ntasks) return;
+	unsigned long long score = st.task_slot_id[slot] ? (unsigned long long)st.task_last[(size_t)slot * 3 + metric].sum : 0ull;
+	if ((long long)score < 0) score = 0;
+	if (score > 0xFFFFFFFFull) score = 0xFFFFFFFFull;
+	keys[slot] = (score << 32) | slot;
+}
+
+__global__ void topn_task_pick_kernel(DevState st, const unsigned long long *__restrict__ sorted, uint32_t ntasks, uint32_t want, gysk_topn_entry *__restrict__ out)
+{
+	const uint32_t i = threadIdx.x;
+	if (i >= want) return;
+	gysk_topn_entry o; o.glob_id = 0; o.score = 0; o.host_idx = 0; o.pad = 0;
+	if (i < ntasks) {
+		const unsigned long long k = sorted[ntasks - 1 - i];		// descending
+		const uint32_t slot = (uint32_t)k;
+		o.glob_id = st.task_slot_id[slot]; o.score = k >> 32; o.host_idx = st.task_slot_host[slot];
+	}
+	out[i] = o;
+}
+
+int launch_topn_tasks(const DevState &st, const SortTemp &tmp, uint32_t ntasks, int metric, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s)
+{
+	if (!ntasks) return 0;
+	int which = 0, launches = 2;
+	topn_task_score_kernel<<<div_up(ntasks, 256), 256, 0, s>>>(st, ntasks, metric, tmp.keys_a);
+	launches += launch_radix_sort(tmp, ntasks, 32, 64, 64, 64, &which, s);
+	topn_task_pick_kernel<<<1, 64, 0, s>>>(st, which ? tmp.keys_b : tmp.keys_a, ntasks, want, d_out);
+	return launches;
+}
+
+int launch_flush(const DevState &st, uint32_t nslots, HistCell *ring_plane0, HistCell *ring_plane1, uint32_t tsec, uint32_t idle_secs, cudaStream_t s)
 {
 	if (!nslots) return 0;
-	flush_kernel<<<div_up((uint64_t)nslots * HIST_CELLS, 256), 256, 0, s>>>(st, nslots, ring_plane0, ring_plane1);
+	cudaMemsetAsync(st.counters + CTR_NEVICT, 0, sizeof(unsigned long long), s);
+	flush_kernel<<<div_up((uint64_t)nslots * HIST_CELLS, 256), 256, 0, s>>>(st, nslots, ring_plane0, ring_plane1, tsec, idle_secs);
+	if (!idle_secs) return 1;
+	evict_kernel<<<296, 256, 0, s>>>(st, nslots);		// grid-stride over the (device-side) eviction list
+	return 2;
+}
+
+int launch_rebuild_table(const DevState &st, uint32_t max_svcs, cudaStream_t s)
+{
+	cudaMemsetAsync(st.svc_tbl.ent, 0, ((size_t)st.svc_tbl.mask + 1) * sizeof(TblEntry), s);
+	rebuild_table_kernel<<<div_up(max_svcs, 256), 256, 0, s>>>(st, max_svcs);
 	return 1;
 }
 

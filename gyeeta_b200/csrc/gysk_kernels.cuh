@@ -17,6 +17,9 @@ struct DevState
 	unsigned long long	*conn_cur, *conn_last;			// packed {count:32, kbytes:32}
 	unsigned long long	*slot_id;				// [max_svcs] slot -> glob_id (written by the inserter)
 	uint32_t		*slot_host;				// [max_svcs] slot -> host_idx of the first event seen
+	uint32_t		*slot_first_seen, *slot_last_active;	// [max_svcs] tsec of the first flush that saw the slot / of the last window with events
+	uint32_t		*evict_list;				// [max_svcs] slots evicted by the last flush; evict_ids: their ids
+	unsigned long long	*evict_ids;
 	unsigned long long	*conn_all_cnt, *conn_all_kb;
 	uint32_t		*bm_cur, *bm_last;			// [max_svcs][16] CONN_BITMAP transposed: per bucket a mask over (client port & 31)
 	uint8_t			*hll;					// [max_svcs][1 << hll_p]
@@ -24,6 +27,9 @@ struct DevState
 	TdHead			*td_head;				// [max_svcs]
 	// per-task state
 	HistCell		*task_hist;				// [max_tasks][3][16]
+	HistCell		*task_prev, *task_last;			// [max_tasks][3] {count, sum}: totals at the last flush / of the last closed window
+	unsigned long long	*task_slot_id;				// [max_tasks] slot -> aggr_task_id
+	uint32_t		*task_slot_host;
 	// flow sketch
 	unsigned long long	*cms_cur, *cms_last;			// [depth][1 << log2w]
 	uint32_t		cms_depth, cms_wmask, cms_log2w, hll_p;
@@ -83,7 +89,10 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_events, uint64_t nkeys, uint32_t nslots, int value_bits, cudaStream_t s);
 int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, int lo2, int hi2, int *which, cudaStream_t s);
 int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int metric, int host_filter, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
-int launch_flush(const DevState &st, uint32_t max_svcs, HistCell *ring_plane0, HistCell *ring_plane1, cudaStream_t s);
+int launch_topn_tasks(const DevState &st, const SortTemp &tmp, uint32_t ntasks, int metric, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
+int launch_task_flush(const DevState &st, uint32_t max_tasks, cudaStream_t s);
+int launch_flush(const DevState &st, uint32_t max_svcs, HistCell *ring_plane0, HistCell *ring_plane1, uint32_t tsec, uint32_t idle_secs, cudaStream_t s);
+int launch_rebuild_table(const DevState &st, uint32_t max_svcs, cudaStream_t s);
 int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, uint32_t max_svcs, uint32_t live_mask0, uint32_t live_mask1,
 		SvcRaw *d_out, cudaStream_t s);
 int launch_gather_tasks(const DevState &st, const unsigned long long *d_ids, uint32_t n, TaskRaw *d_out, cudaStream_t s);

@@ -32,6 +32,15 @@ __global__ void resolve_slots_kernel(DevState st, const unsigned long long *__re
 	if (i < n) slots[i] = ids[i] ? table_lookup(st.svc_tbl, ids[i], false) : -1;
 }
 
+// a member whose slot was evicted (or recycled for another id) since the map was set folds the engine's null slot instead
+// (index max_svcs: always in its just-created state)
+__global__ void validate_members_kernel(DevState st, uint32_t *__restrict__ members, const unsigned long long *__restrict__ member_ids, uint32_t n,
+		uint32_t null_slot)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && members[i] != null_slot && st.slot_id[members[i]] != member_ids[i]) members[i] = null_slot;
+}
+
 // one thread per (logical, cell)
 __global__ void fold_hist_kernel(DevState st, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ members, uint32_t nl,
 		HistCell *__restrict__ l_last, HistCell *__restrict__ l_all, unsigned long long *__restrict__ l_conn, long long *__restrict__ l_hmax)
@@ -225,17 +234,18 @@ int gysk_set_logical_map(gysk_engine *e, const uint64_t *glob_ids, const uint64_
 
 	// CSR logical -> member slots present on this GPU
 	std::vector<uint32_t> offs(nl + 1, 0), members;
+	std::vector<uint64_t> member_ids;
 	for (uint32_t i = 0; i < n; ++i) if (slots[i] >= 0) offs[lidx[i] + 1]++;
 	for (uint32_t l = 0; l < nl; ++l) offs[l + 1] += offs[l];
-	members.resize(offs[nl]);
+	members.resize(offs[nl]); member_ids.resize(offs[nl]);
 	{
 		std::vector<uint32_t> cur(offs.begin(), offs.end() - 1);
-		for (uint32_t i = 0; i < n; ++i) if (slots[i] >= 0) members[cur[lidx[i]]++] = (uint32_t)slots[i];
+		for (uint32_t i = 0; i < n; ++i) if (slots[i] >= 0) { member_ids[cur[lidx[i]]] = glob_ids[i]; members[cur[lidx[i]]++] = (uint32_t)slots[i]; }
 	}
 
 	// (re)allocate the arena
 	auto dfree = [&](void *p) { if (p) { cudaFree(p); e->dallocs.erase(std::remove(e->dallocs.begin(), e->dallocs.end(), p), e->dallocs.end()); } };
-	dfree(mg.d_offsets); dfree(mg.d_members); dfree(mg.arena); dfree(mg.slab); dfree(mg.final_slab);
+	dfree(mg.d_offsets); dfree(mg.d_members); dfree(mg.d_member_ids); dfree(mg.arena); dfree(mg.slab); dfree(mg.final_slab);
 	{
 		std::vector<uint64_t> ids_keep(std::move(mg.logical_ids));
 		std::unordered_map<uint64_t, uint32_t> idx_keep(std::move(mg.index));
@@ -271,6 +281,9 @@ int gysk_set_logical_map(gysk_engine *e, const uint64_t *glob_ids, const uint64_
 	if ((rc = dalloc(e, &mg.final_slab, mg.slab_bytes))) return rc;
 	if ((rc = dalloc(e, &mg.d_offsets, (size_t)nl + 1))) return rc;
 	if ((rc = dalloc(e, &mg.d_members, members.size() + 1))) return rc;
+	if ((rc = dalloc(e, &mg.d_member_ids, member_ids.size() + 1))) return rc;
+	mg.nmembers = (uint32_t)members.size();
+	if (!member_ids.empty()) CU(e, cudaMemcpyAsync(mg.d_member_ids, member_ids.data(), member_ids.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
 	CU(e, cudaMemcpyAsync(mg.d_offsets, offs.data(), ((size_t)nl + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
 	if (!members.empty()) CU(e, cudaMemcpyAsync(mg.d_members, members.data(), members.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
 	CU(e, cudaStreamSynchronize(e->stream));
@@ -293,6 +306,10 @@ int gysk_merge_prepare(gysk_engine *e)
 	CU(e, cudaMemcpyAsync(mg.g_cms_cur, e->st.cms_cur, b_cms, cudaMemcpyDeviceToDevice, e->stream));
 	CU(e, cudaMemcpyAsync(mg.g_cms_last, e->st.cms_last, b_cms, cudaMemcpyDeviceToDevice, e->stream));
 	if (nl) {
+		if (mg.nmembers && e->cfg.idle_evict_secs) {
+			validate_members_kernel<<<div_up(mg.nmembers, 256), 256, 0, e->stream>>>(e->st, mg.d_members, mg.d_member_ids, mg.nmembers, e->cfg.max_svcs);
+			e->kernel_launches++;
+		}
 		fold_hist_kernel<<<div_up((uint64_t)nl * HIST_CELLS, 256), 256, 0, e->stream>>>(e->st, mg.d_offsets, mg.d_members, nl,
 				mg.l_hist_last, mg.l_hist_all, mg.l_conn, mg.l_hmax);
 		fold_hll_kernel<<<div_up((uint64_t)nl << (e->cfg.hll_p - 2), 256), 256, 0, e->stream>>>(e->st, mg.d_offsets, mg.d_members, nl,

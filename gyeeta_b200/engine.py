@@ -31,7 +31,7 @@ class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("max_svcs", C.c_uint32), ("max_tasks", C.c_uint32),
                 ("cms_depth", C.c_uint32), ("cms_log2_width", C.c_uint32), ("hll_p", C.c_uint32),
                 ("td_compression", C.c_uint32), ("max_batch", C.c_uint32), ("flags", C.c_uint32), ("rank", C.c_uint32),
-                ("world", C.c_uint32), ("stage_batch", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("world", C.c_uint32), ("stage_batch", C.c_uint32), ("idle_evict_secs", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
 
 class SvcSummary(C.Structure):
@@ -59,7 +59,7 @@ class TopnEntry(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("events_in", "events_dropped", "events_resp", "events_tcp", "events_task", "nsvcs",
-                                          "ntasks", "batches", "kernel_launches", "wire_msgs_ok", "wire_msgs_bad")]
+                                          "ntasks", "batches", "kernel_launches", "wire_msgs_ok", "wire_msgs_bad", "svcs_evicted")]
 
     def asdict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -98,16 +98,20 @@ def load_library(path=None):
         "gysk_ingest_device": (i32, [vp, vp, u64]),
         "gysk_sync": (i32, [vp]),
         "gysk_flush": (i32, [vp, u32]),
+        "gysk_evicted_ids": (i32, [vp, vp, u32, vp]),
         "gysk_query_svcs": (i32, [vp, vp, u32, vp]),
         "gysk_query_flows": (i32, [vp, vp, u32, i32, vp]),
         "gysk_query_host_summary": (i32, [vp, u32, vp]),
         "gysk_topn_svcs": (i32, [vp, i32, C.c_int32, u32, vp, vp]),
+        "gysk_topn_tasks": (i32, [vp, i32, u32, vp, vp]),
         "gysk_export_hist": (i32, [vp, u64, i32, vp, vp, vp]),
         "gysk_export_task_hist": (i32, [vp, u64, i32, vp, vp, vp]),
         "gysk_export_hll": (i32, [vp, u64, vp]),
         "gysk_export_conn_bitmap": (i32, [vp, u64, i32, vp, vp]),
         "gysk_export_tdigest": (i32, [vp, u64, vp, vp, u32, vp, vp, vp]),
         "gysk_query_quantiles": (i32, [vp, u64, vp, u32, vp]),
+        "gysk_tdigest_to_pgtext": (i32, [vp, vp, u32, u32, vp, u32]),
+        "gysk_export_tdigest_pgtext": (i32, [vp, u64, vp, u32]),
         "gysk_export_cms": (i32, [vp, i32, vp]),
         "gysk_hist_nbuckets": (i32, [i32]),
         "gysk_hist_bucket": (i32, [i32, C.c_int64]),
@@ -143,7 +147,7 @@ class Engine:
     """One engine = one GPU. Mirrors the C ABI one to one."""
 
     def __init__(self, device=0, max_svcs=1 << 14, max_tasks=1 << 12, cms_depth=4, cms_log2_width=20, hll_p=12,
-                 td_compression=100, max_batch=1 << 20, auto_register=True, rank=0, world=1, stage_batch=0):
+                 td_compression=100, max_batch=1 << 20, auto_register=True, rank=0, world=1, stage_batch=0, idle_evict_secs=0):
         self.L = load_library()
         cfg = Config()
         self.L.gysk_config_default(C.byref(cfg))
@@ -151,6 +155,7 @@ class Engine:
         cfg.cms_depth, cfg.cms_log2_width, cfg.hll_p, cfg.td_compression = cms_depth, cms_log2_width, hll_p, td_compression
         cfg.max_batch = max_batch
         cfg.stage_batch = stage_batch
+        cfg.idle_evict_secs = idle_evict_secs
         cfg.flags = FLAG_AUTO_REGISTER if auto_register else 0
         cfg.rank, cfg.world = rank, world
         self.cfg = cfg
@@ -211,6 +216,13 @@ class Engine:
     def flush(self, tsec=0):
         self._chk(self.L.gysk_flush(self.h, tsec))
 
+    def evicted_ids(self, cap=1 << 16):
+        """ids evicted by the most recent flush (LISTEN_FLAG_DELETE notifications)"""
+        out = np.zeros(cap, dtype=np.uint64)
+        n = C.c_uint32()
+        self._chk(self.L.gysk_evicted_ids(self.h, _p(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
     def stream(self):
         return self.L.gysk_stream(self.h)
 
@@ -245,6 +257,12 @@ class Engine:
         k = C.c_uint32()
         self._chk(self.L.gysk_topn_svcs(self.h, metric, host_idx, n, out, C.byref(k)))
         return [(o.glob_id, o.score, o.host_idx) for o in out[: k.value]]
+
+    def topn_tasks(self, metric, n=10):
+        out = (TopnEntry * n)()
+        k = C.c_uint32()
+        self._chk(self.L.gysk_topn_tasks(self.h, metric, n, out, C.byref(k)))
+        return [(o.glob_id, o.score) for o in out[: k.value]]
 
     def host_summary(self, host_idx):
         hs = HostSummary()
@@ -291,6 +309,15 @@ class Engine:
             return None
         self._chk(rc)
         return means[: n.value].copy(), weights[: n.value].copy(), mn.value, mx.value
+
+    def export_tdigest_pgtext(self, id_):
+        buf = C.create_string_buffer(8192)
+        rc = self.L.gysk_export_tdigest_pgtext(self.h, int(id_), buf, len(buf))
+        if rc == -2:
+            return None
+        if rc < 0:
+            self._chk(rc)
+        return buf.value.decode()
 
     def quantiles(self, id_, qs):
         qs = np.ascontiguousarray(qs, dtype=np.float64)

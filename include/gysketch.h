@@ -140,7 +140,10 @@ typedef struct gysk_config
 	uint32_t	flags;			/* GYSK_FLAG_* */
 	uint32_t	rank, world;		/* this engine owns events with host_idx % world == rank; world 0/1 = all */
 	uint32_t	stage_batch;		/* events per host staging buffer / H2D chunk; 0 = min(max_batch, 1 << 22) */
-	uint32_t	reserved[3];
+	uint32_t	idle_evict_secs;	/* a service without events for this long (and older than twice that) is evicted at
+						   gysk_flush: TIMEOUT_INET_DIAG_SECS 300, common/gy_socket_stat.h:997, rule of
+						   common/gy_socket_stat.cc:3968-3982. 0 (default) = never */
+	uint32_t	reserved[2];
 } gysk_config;
 
 typedef struct gysk_engine gysk_engine;
@@ -189,6 +192,10 @@ typedef struct gysk_host_summary
 
 /* top-N services of the last closed window (BOUNDED_PRIO_QUEUE users of partha_listener_state, gy_mconnhdlr.cc:11262-11304) */
 enum { GYSK_TOPN_QPS = 0, GYSK_TOPN_CONNS = 1, GYSK_TOPN_NET = 2 };
+/* top-N aggregated processes of the last closed window: atask_top_cpu_ / atask_top_cpu_delay_ / atask_top_io_delay_ of
+ * partha_aggr_task_state (server/gy_mconnhdlr.cc:10020-10065; a task whose metric is zero never enters a queue).
+ * score = the window's sum of cpu_pct / cpu_delay msec / blkio_delay msec samples */
+enum { GYSK_TOPN_TASK_CPU = 0, GYSK_TOPN_TASK_CPU_DELAY = 1, GYSK_TOPN_TASK_BLKIO_DELAY = 2 };
 typedef struct gysk_topn_entry
 {
 	uint64_t	glob_id;
@@ -213,6 +220,7 @@ typedef struct gysk_stats
 	uint64_t	batches;
 	uint64_t	kernel_launches;	/* launches of this library's own kernels so far */
 	uint64_t	wire_msgs_ok, wire_msgs_bad;
+	uint64_t	svcs_evicted;		/* idle services evicted so far (their slots are recycled) */
 } gysk_stats;
 
 /* mergeable device buffers (for the multi-GPU merge step) */
@@ -251,6 +259,9 @@ int		gysk_export_task_hist(gysk_engine *e, uint64_t aggr_task_id, int which, gys
 				uint64_t *total_count, int64_t *max_val);
 int		gysk_sync(gysk_engine *e);
 int		gysk_flush(gysk_engine *e, uint32_t tsec);
+/* ids evicted by the most recent gysk_flush (the LISTEN_FLAG_DELETE notifications of common/gy_socket_stat.cc:4023-4033);
+ * synchronises the ingest stream. *n = number of ids (may exceed cap: then only cap are written) */
+int		gysk_evicted_ids(gysk_engine *e, uint64_t *out, uint32_t cap, uint32_t *n);
 
 /* ---- queries ---- */
 int		gysk_query_svcs(gysk_engine *e, const uint64_t *glob_ids, uint32_t n, gysk_svc_summary *out);
@@ -258,6 +269,7 @@ int		gysk_query_flows(gysk_engine *e, const uint64_t *flow_keys, uint32_t n, int
 /* LISTEN_SUMM_STATS of the last NOTIFY_LISTENER_STATE message of a host (partha_listener_state, gy_mconnhdlr.cc:11251) */
 /* host_idx < 0: over all hosts of this engine; n <= 64 */
 int		gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gysk_topn_entry *out, uint32_t *nout);
+int		gysk_topn_tasks(gysk_engine *e, int metric, uint32_t n, gysk_topn_entry *out, uint32_t *nout);	/* n <= 64; glob_id = aggr_task_id */
 int		gysk_query_host_summary(gysk_engine *e, uint32_t host_idx, gysk_host_summary *out);
 int		gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial out[GYSK_HIST_MAX_BUCKETS],
 				uint64_t *total_count, int64_t *max_val);
@@ -277,6 +289,11 @@ int		gysk_hist_bucket(int cls, int64_t value);	/* RESP_TIME_HASH::get_bucket_fro
 int		gysk_hist_percentiles(int cls, int t_is_int, const gysk_hist_serial *stats, uint64_t total_count,
 				const float *pcts, uint32_t npct, int64_t *out);
 double		gysk_hll_estimate(const uint8_t *regs, uint32_t p);
+/* a digest in the text form of the Postgres `tdigest` type the reference stores and queries (public.tdigest(expr, 100) /
+ * tdigest_percentile, common/gy_query_common.cc:1805-1858): "flags 1 count N compression C centroids K (mean, count) ...".
+ * Both return the string length, or a negative GYSK_ERR_* */
+int		gysk_tdigest_to_pgtext(const double *means, const uint64_t *weights, uint32_t n, uint32_t compression, char *buf, uint32_t cap);
+int		gysk_export_tdigest_pgtext(gysk_engine *e, uint64_t glob_id, char *buf, uint32_t cap);
 double		gysk_tdigest_quantile(const double *means, const uint64_t *weights, uint32_t n, double min_val, double max_val, double q);
 uint32_t	gysk_uint64_hash(uint64_t key);		/* get_uint64_hash, common/gy_common_inc.h:1120 */
 

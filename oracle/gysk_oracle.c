@@ -527,15 +527,18 @@ typedef struct svc_state
 	gyo_tdigest	td;
 	uint32_t	*pend;			/* RESP samples (usec) of the batch being ingested */
 	uint32_t	npend, cappend;
+	uint32_t	first_seen, last_active;	/* tsec of the first flush that saw the service / of the last window with events */
 } svc_state;
 
 typedef struct task_state
 {
 	uint64_t	id;
 	gyo_hist	cpu_pct, cpu_delay, blkio_delay;	/* MTASK_HIST, server/gy_msocket.h:704-718 */
+	uint64_t	prev[3][2], last[3][2];			/* {count, sum} totals at the last flush / of the last closed window */
 } task_state;
 
-typedef struct idmap { uint64_t *keys; uint32_t *vals; uint32_t cap, n; } idmap;
+typedef struct idmap { uint64_t *keys; uint32_t *vals; uint32_t cap, n; uint32_t *freed; uint32_t nfreed; } idmap;
+#define GYO_TOMBSTONE	(~0ull)		/* key of a deleted entry: never matches, never ends a probe chain */
 
 struct gyo_engine
 {
@@ -550,6 +553,10 @@ struct gyo_engine
 	uint32_t	last_flush_tsec;
 	uint32_t	*touched;		/* slots with pending RESP samples in the batch being ingested */
 	uint32_t	ntouched;
+	uint32_t	idle_evict_secs;	/* 0 = never */
+	uint64_t	*evicted;		/* ids evicted by the last flush */
+	uint32_t	nevicted;
+	uint64_t	evicted_total;
 };
 
 static uint32_t pow2_at_least(uint32_t v) { uint32_t p = 16; while (p < v) p <<= 1; return p; }
@@ -559,7 +566,8 @@ static void idmap_init(idmap *m, uint32_t maxn)
 	m->cap = pow2_at_least(maxn * 2);
 	m->keys = (uint64_t *)calloc(m->cap, sizeof(uint64_t));
 	m->vals = (uint32_t *)calloc(m->cap, sizeof(uint32_t));
-	m->n = 0;
+	m->freed = (uint32_t *)calloc(maxn ? maxn : 1, sizeof(uint32_t));
+	m->n = 0; m->nfreed = 0;
 }
 
 /* open addressing keyed by get_uint64_hash (how the reference keys listen_tbl_, gy_mconnhdlr.cc:11183) */
@@ -567,10 +575,13 @@ static int idmap_find(idmap *m, uint64_t key, int insert, uint32_t maxn)
 {
 	uint32_t pos = gyo_uint64_hash(key) & (m->cap - 1);
 
+	if (key == GYO_TOMBSTONE) return -1;
 	for (;;) {
 		if (m->keys[pos] == key) return (int)m->vals[pos];
 		if (m->keys[pos] == 0) {
-			if (!insert || m->n >= maxn) return -1;
+			if (!insert || key == GYO_TOMBSTONE) return -1;
+			if (m->nfreed) { m->keys[pos] = key; m->vals[pos] = m->freed[--m->nfreed]; return (int)m->vals[pos]; }	/* recycled slot */
+			if (m->n >= maxn) return -1;
 			m->keys[pos] = key; m->vals[pos] = m->n;
 			return (int)m->n++;
 		}
@@ -592,6 +603,7 @@ gyo_engine *gyo_create(uint32_t max_svcs, uint32_t max_tasks, uint32_t cms_depth
 	e->cms_cur = (uint64_t *)calloc((size_t)cms_depth << cms_log2_width, sizeof(uint64_t));
 	e->cms_last = (uint64_t *)calloc((size_t)cms_depth << cms_log2_width, sizeof(uint64_t));
 	e->touched = (uint32_t *)malloc(sizeof(uint32_t) * max_svcs);
+	e->evicted = (uint64_t *)malloc(sizeof(uint64_t) * max_svcs);
 	memset(e->ring_epoch, 0xFF, sizeof(e->ring_epoch));
 	return e;
 }
@@ -600,19 +612,20 @@ void gyo_destroy(gyo_engine *e)
 {
 	if (!e) return;
 	for (uint32_t i = 0; i < e->smap.n; ++i) { free(e->svcs[i].hll); free(e->svcs[i].pend); }
-	free(e->svcs); free(e->tasks); free(e->cms_cur); free(e->cms_last); free(e->touched);
-	free(e->smap.keys); free(e->smap.vals); free(e->tmap.keys); free(e->tmap.vals);
+	free(e->svcs); free(e->tasks); free(e->cms_cur); free(e->cms_last); free(e->touched); free(e->evicted);
+	free(e->smap.keys); free(e->smap.vals); free(e->tmap.keys); free(e->tmap.vals); free(e->smap.freed); free(e->tmap.freed);
 	free(e);
 }
 
 static svc_state *get_svc(gyo_engine *e, uint64_t id, int insert)
 {
-	uint32_t before = e->smap.n;
 	int slot = idmap_find(&e->smap, id, insert, e->max_svcs);
 
 	if (slot < 0) return NULL;
 	svc_state *s = &e->svcs[slot];
-	if ((uint32_t)slot >= before) {
+	if (s->id != id) {			/* fresh or recycled slot */
+		free(s->hll); free(s->pend);
+		memset(s, 0, sizeof(*s));
 		s->id = id;
 		gyo_hist_init(&s->cur, GYO_CLS_RESP_TIME, GYO_T_INT64);
 		gyo_hist_init(&s->last, GYO_CLS_RESP_TIME, GYO_T_INT64);
@@ -746,8 +759,18 @@ void gyo_flush(gyo_engine *e, uint32_t tsec)
 	}
 	e->last_flush_tsec = tsec;
 
+	e->nevicted = 0;
 	for (uint32_t i = 0; i < e->smap.n; ++i) {
 		svc_state *s = &e->svcs[i];
+
+		if (!s->id) continue;		/* evicted, slot waiting for reuse */
+		/* idle-service rule (ours, after common/gy_socket_stat.cc:3968-3982: tclock != 0, tclock + 300 s < now, tstart + 600 s < now) */
+		{
+			int active = (uint32_t)s->conn_cur != 0 || (s->conn_cur >> 32) != 0;
+			for (int b = 0; b < 15 && !active; ++b) active = s->cur.stats[b].count != 0;
+			if (!s->first_seen) s->first_seen = tsec ? tsec : 1u;
+			if (active) s->last_active = tsec ? tsec : 1u;
+		}
 
 		s->last = s->cur;
 		gyo_hist_merge(&s->all, &s->cur);
@@ -761,10 +784,53 @@ void gyo_flush(gyo_engine *e, uint32_t tsec)
 		s->conn_all_cnt += (uint32_t)s->conn_cur;
 		s->conn_all_kb += s->conn_cur >> 32;
 		s->conn_cur = 0;
+
+		if (e->idle_evict_secs && s->last_active && (uint64_t)s->last_active + e->idle_evict_secs < tsec &&
+				(uint64_t)s->first_seen + 2ull * e->idle_evict_secs < tsec) {
+			/* delete: table entry -> tombstone, slot number recycled, state gone */
+			uint32_t pos = gyo_uint64_hash(s->id) & (e->smap.cap - 1);
+			while (e->smap.keys[pos] != s->id && e->smap.keys[pos] != 0) pos = (pos + 1) & (e->smap.cap - 1);
+			if (e->smap.keys[pos] == s->id) e->smap.keys[pos] = GYO_TOMBSTONE;
+			e->evicted[e->nevicted++] = s->id; e->evicted_total++;
+			e->smap.freed[e->smap.nfreed++] = i;
+			free(s->hll); free(s->pend);
+			memset(s, 0, sizeof(*s));
+		}
+	}
+	/* per-task window of the three histograms = totals now - totals at the previous flush (feeds the task top-N) */
+	for (uint32_t i = 0; i < e->tmap.n; ++i) {
+		task_state *ts = &e->tasks[i];
+		const gyo_hist *hh[3] = { &ts->cpu_pct, &ts->cpu_delay, &ts->blkio_delay };
+		for (int h = 0; h < 3; ++h) {
+			uint64_t cnt = 0, sum = 0;
+			for (int b = 0; b < 15; ++b) { cnt += hh[h]->stats[b].count; sum += (uint64_t)hh[h]->stats[b].sum; }
+			ts->last[h][0] = cnt - ts->prev[h][0]; ts->last[h][1] = sum - ts->prev[h][1];
+			ts->prev[h][0] = cnt; ts->prev[h][1] = sum;
+		}
 	}
 	uint64_t *t = e->cms_last; e->cms_last = e->cms_cur; e->cms_cur = t;
 	memset(e->cms_cur, 0, sizeof(uint64_t) * ((size_t)e->depth << e->log2w));
 }
+
+/* last closed window of a task: out[h*2] = samples, out[h*2+1] = sum, h = cpu_pct, cpu_delay, blkio_delay */
+int gyo_task_last(gyo_engine *e, uint64_t id, uint64_t out[6])
+{
+	task_state *t = get_task(e, id, 0);
+	if (!t) return -2;
+	for (int h = 0; h < 3; ++h) { out[2 * h] = t->last[h][0]; out[2 * h + 1] = t->last[h][1]; }
+	return 0;
+}
+
+void gyo_set_idle_evict(gyo_engine *e, uint32_t secs) { e->idle_evict_secs = secs; }
+
+uint32_t gyo_evicted(gyo_engine *e, uint64_t *out, uint32_t cap, uint64_t *total)
+{
+	for (uint32_t i = 0; i < e->nevicted && i < cap; ++i) out[i] = e->evicted[i];
+	if (total) *total = e->evicted_total;
+	return e->nevicted;
+}
+
+uint32_t gyo_nsvcs(gyo_engine *e) { return e->smap.n - e->smap.nfreed; }
 
 static void level_sum(const gyo_engine *e, const svc_state *s, int l, gyo_hist *out)
 {
@@ -848,7 +914,7 @@ const uint64_t *gyo_cms_table(gyo_engine *e, int last_window)
 void gyo_counters(gyo_engine *e, uint64_t out[8])
 {
 	out[0] = e->n_in; out[1] = e->n_drop; out[2] = e->n_resp; out[3] = e->n_tcp; out[4] = e->n_task;
-	out[5] = e->smap.n; out[6] = e->tmap.n; out[7] = e->n_foreign;
+	out[5] = e->smap.n - e->smap.nfreed; out[6] = e->tmap.n; out[7] = e->n_foreign;
 }
 
 /* additive merge of a peer shard: histogram sums (update_from_serialized), CMS sums, HLL max — the CPU statement
@@ -861,6 +927,7 @@ void gyo_merge_from(gyo_engine *dst, const gyo_engine *src)
 
 	for (uint32_t i = 0; i < src->smap.n; ++i) {
 		const svc_state *s = &src->svcs[i];
+		if (!s->id) continue;		/* evicted */
 		svc_state *d = get_svc(dst, s->id, 1);
 		if (!d) continue;
 		gyo_hist_merge(&d->cur, &s->cur); gyo_hist_merge(&d->last, &s->last); gyo_hist_merge(&d->all, &s->all);

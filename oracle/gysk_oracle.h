@@ -111,6 +111,11 @@ void	gyo_destroy(gyo_engine *e);
 int	gyo_register_ids(gyo_engine *e, const uint64_t *ids, uint32_t n, int is_task);
 int	gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n);	/* one device batch */
 void	gyo_flush(gyo_engine *e, uint32_t tsec);
+/* idle-service eviction at flush (rule of common/gy_socket_stat.cc:3968-3982); 0 = never */
+int	gyo_task_last(gyo_engine *e, uint64_t id, uint64_t out[6]);
+void	gyo_set_idle_evict(gyo_engine *e, uint32_t secs);
+uint32_t gyo_evicted(gyo_engine *e, uint64_t *out, uint32_t cap, uint64_t *total);	/* ids evicted by the last flush */
+uint32_t gyo_nsvcs(gyo_engine *e);
 int	gyo_export_hist(gyo_engine *e, uint64_t id, int which, gyo_serial *out15, uint64_t *total, int64_t *maxv);
 int	gyo_export_hll(gyo_engine *e, uint64_t id, uint8_t *regs);
 int	gyo_export_tdigest(gyo_engine *e, uint64_t id, gyo_tdigest *out);

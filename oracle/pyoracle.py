@@ -89,6 +89,12 @@ def lib():
         L.gyo_register_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
         L.gyo_ingest.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.gyo_flush.argtypes = [C.c_void_p, C.c_uint32]
+        L.gyo_task_last.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.gyo_set_idle_evict.argtypes = [C.c_void_p, C.c_uint32]
+        L.gyo_evicted.restype = C.c_uint32
+        L.gyo_evicted.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.gyo_nsvcs.restype = C.c_uint32
+        L.gyo_nsvcs.argtypes = [C.c_void_p]
         L.gyo_export_hist.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gyo_export_hll.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.gyo_export_tdigest.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
@@ -175,6 +181,23 @@ class OracleEngine:
 
     def flush(self, tsec=0):
         self.L.gyo_flush(self.h, tsec)
+
+    def task_last(self, id_):
+        out = np.zeros(6, dtype=np.uint64)
+        rc = self.L.gyo_task_last(self.h, int(id_), _p(out))
+        return None if rc else out
+
+    def set_idle_evict(self, secs):
+        self.L.gyo_set_idle_evict(self.h, secs)
+
+    def evicted_ids(self, cap=1 << 20):
+        out = np.zeros(cap, dtype=np.uint64)
+        tot = C.c_uint64()
+        n = self.L.gyo_evicted(self.h, _p(out), cap, C.byref(tot))
+        return out[:n].copy(), tot.value
+
+    def nsvcs(self):
+        return self.L.gyo_nsvcs(self.h)
 
     def export_hist(self, id_, which):
         out = np.zeros(15, dtype=SERIAL_DTYPE)

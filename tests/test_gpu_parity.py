@@ -311,3 +311,95 @@ def test_topn_services_last_window():
     got = eng.topn(0, 5, host_idx=h)
     want = sorted([v for k, v in qps.items() if host_of[k] == h], reverse=True)[:5]
     assert [s for _, s, _ in got] == [w for w in want if w > 0] and all(hh == h for _, _, hh in got)
+
+
+def test_idle_service_eviction_and_slot_reuse():
+    """a service without events for idle_evict_secs (and older than twice that) is evicted at a flush — the
+    listener deletion rule of common/gy_socket_stat.cc:3968-3982 with TIMEOUT_INET_DIAG_SECS (gy_socket_stat.h:997). Same
+    evicted ids as the oracle at every flush, evicted ids answer "unknown", their slots are handed to new ids (capacity is
+    tight on purpose), a returning id starts from scratch, and the survivors' state stays bit-exact."""
+    rng = np.random.default_rng(91)
+    nsvc = 60
+    eng, orc = make_pair(max_svcs=64, max_tasks=8, max_batch=1 << 14, cms_log2_width=10, idle_evict_secs=300)
+    base = synth.gen_mixed(rng, 20_000, nsvc, ntask=4, nhosts=4, nclients=500)
+    all_ids = np.unique(base["svc_id"][base["type"] != ge.EV_TASK])
+    assert len(all_ids) >= 50
+    keep = set(int(i) for i in all_ids[::2])            # these stay busy; the others go silent after t = 10
+
+    def window(t, ids_allowed, n=6000, extra=None):
+        ev = synth.gen_mixed(rng, n, nsvc, ntask=4, nhosts=4, nclients=500)
+        is_task = ev["type"] == ge.EV_TASK
+        ok = is_task | np.isin(ev["svc_id"], np.fromiter(ids_allowed, dtype=np.uint64))
+        ev = ev[ok]
+        if extra is not None:
+            ev = np.concatenate([ev, extra])
+        ev["tsec"] = t
+        feed_both(eng, orc, ev, 1 << 14)
+        eng.flush(t); orc.flush(t)
+        got = np.sort(eng.evicted_ids())
+        want, _tot = orc.evicted_ids()
+        assert np.array_equal(got, np.sort(want)), (t, got, want)
+        return got
+
+    evicted = set()
+    window(5, set(int(i) for i in all_ids))
+    window(10, set(int(i) for i in all_ids))
+    for t in (100, 200, 305, 311, 400, 500, 606, 611, 700):
+        ev_ids = window(t, keep)
+        evicted |= set(int(i) for i in ev_ids)
+    silent = set(int(i) for i in all_ids) - keep
+    assert evicted == silent                              # last active at t = 10, first seen t = 5: gone once t > 610
+    st = eng.stats()
+    assert st["svcs_evicted"] == len(silent) and st["nsvcs"] == orc.nsvcs() == len(keep)
+    sm = eng.query_svcs(np.array(sorted(silent), dtype=np.uint64))
+    assert all(s_["found"] == 0 for s_ in sm)
+    for id_ in sorted(keep)[:12]:
+        for which in (ge.HIST_RESP_LAST, ge.HIST_RESP_5MIN, ge.HIST_RESP_ALL):
+            assert_hist_equal(eng, orc, id_, which)
+        assert np.array_equal(eng.export_hll(id_), orc.export_hll(id_))
+
+    # 30 new ids + one returning id: more than the 64-slot table could hold without recycling (30 live + 31 new > 64 - 30)
+    new_ids = synth.splitmix64(np.arange(1, 31, dtype=np.uint64) + np.uint64(1 << 50))
+    back = sorted(silent)[0]
+    extra = np.zeros(3100, dtype=ge.EVENT_DTYPE)
+    extra["svc_id"] = np.concatenate([np.repeat(new_ids, 100), np.full(100, back, dtype=np.uint64)])
+    extra["type"] = ge.EV_RESP
+    extra["value"] = rng.integers(100, 900_000, len(extra))
+    extra["flow_key"] = rng.integers(1, 1 << 60, len(extra), dtype=np.uint64)
+    window(705, keep, extra=extra)
+    st2 = eng.stats()
+    assert st2["nsvcs"] == orc.nsvcs() == len(keep) + 31
+    for id_ in [back] + [int(i) for i in new_ids[:8]] + sorted(keep)[:6]:
+        for which in (ge.HIST_RESP_LAST, ge.HIST_RESP_ALL):
+            assert_hist_equal(eng, orc, id_, which)
+        (means, weights, mn, mx), td = eng.export_tdigest(id_), orc.export_tdigest(id_)
+        om, ow = td.centroids()
+        assert np.array_equal(means, om) and np.array_equal(weights, ow) and mn == td.minv and mx == td.maxv
+        if id_ == back or id_ in set(int(i) for i in new_ids):
+            assert int(weights.sum()) == 100
+    hb = eng.export_hist(back, ge.HIST_RESP_ALL)
+    assert hb[1] == 100                                   # nothing of its first life is left
+
+
+def test_topn_tasks_last_window():
+    """device task top-N (atask_top_cpu_ / _cpu_delay_ / _io_delay_, server/gy_mconnhdlr.cc:10020-10065) over the last closed
+    window = histogram totals differenced between flushes, against the oracle's task windows; second window differs from the
+    first (the score must be the window's, not the running total)"""
+    rng = np.random.default_rng(23)
+    eng, orc = make_pair(max_svcs=256, max_tasks=512, max_batch=1 << 16, cms_log2_width=10)
+    for t in (5, 10):
+        ev = synth.gen_mixed(rng, 60_000, 50, ntask=300, nhosts=4, nclients=500)
+        ev["tsec"] = t
+        feed_both(eng, orc, ev, 1 << 16)
+        eng.flush(t); orc.flush(t)
+        tids = np.unique(ev["svc_id"][ev["type"] == ge.EV_TASK])
+        for metric in (0, 1, 2):
+            want = {}
+            for i in tids:
+                w = orc.task_last(int(i))
+                if w is not None and w[2 * metric + 1] > 0:
+                    want[int(i)] = min(int(w[2 * metric + 1]), 0xFFFFFFFF)
+            got = eng.topn_tasks(metric, 10)
+            top = sorted(want.values(), reverse=True)[:10]
+            assert [sc for _, sc in got] == top, (t, metric)
+            assert all(want[i] == sc for i, sc in got)

@@ -124,3 +124,53 @@ def test_oracle_engine_sharded_merge_equals_single():
         a, b = merged.export_hist(int(id_), 0), one.export_hist(int(id_), 0)
         assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
         assert np.array_equal(merged.export_hll(int(id_)), one.export_hll(int(id_)))
+
+
+def test_oracle_idle_eviction_rule():
+    """the checker's own statement of the listener deletion rule (common/gy_socket_stat.cc:3968-3982): never-active services
+    stay (tclock == 0), an idle one goes only when last activity + 300 s < now AND first seen + 600 s < now, its slot is
+    recycled and a returning id starts empty"""
+    from gyeeta_b200 import engine as ge
+    from oracle import pyoracle as po
+    orc = po.OracleEngine(max_svcs=4, max_tasks=4, cms_log2_width=8)
+    orc.set_idle_evict(300)
+
+    def resp(ids, t):
+        ev = np.zeros(len(ids), dtype=po.EVENT_DTYPE)
+        ev["svc_id"] = ids; ev["type"] = 5; ev["value"] = 5000; ev["tsec"] = t; ev["flow_key"] = 7
+        orc.ingest(ev)
+
+    orc.register_ids(np.array([11, 22, 33], dtype=np.uint64))
+    resp([11, 22], 100); orc.flush(100)                     # 33 never active
+    resp([11], 350); orc.flush(350)
+    assert len(orc.evicted_ids()[0]) == 0                   # 22: 100 + 300 < 350 fails the age test (100 + 600 < 350 is false)
+    resp([11], 650); orc.flush(650)
+    assert len(orc.evicted_ids()[0]) == 0                   # 100 + 600 < 650 false
+    resp([11], 701); orc.flush(701)
+    ids, tot = orc.evicted_ids()
+    assert list(ids) == [22] and tot == 1 and orc.nsvcs() == 2
+    assert orc.export_hist(22, 2) is None and orc.export_hist(33, 2) is not None
+    resp([22, 44, 55], 705)                                  # 22 returns, 44 takes a fresh slot, 55 finds the table full
+    assert orc.nsvcs() == 4 and orc.export_hist(55, 0) is None
+    assert orc.export_hist(22, 0)[1] == 1 and orc.export_hist(44, 0)[1] == 1
+
+
+def test_tdigest_pgtext_form():
+    """the Postgres `tdigest` text form (tdigest_out / tdigest_in of the extension the reference queries through,
+    common/gy_query_common.cc:1805-1858,3385): header fields, one "(mean, count)" pair per centroid, lossless means"""
+    import ctypes as C
+    import re
+    from gyeeta_b200 import engine as ge
+    L = ge.load_library()
+    means = np.array([1.5, 2.25, 1000.000001, 123456789.123456789], dtype=np.float64)
+    weights = np.array([1, 7, 3, 2], dtype=np.uint64)
+    buf = C.create_string_buffer(512)
+    n = L.gysk_tdigest_to_pgtext(means.ctypes.data_as(C.c_void_p), weights.ctypes.data_as(C.c_void_p), 4, 100, buf, len(buf))
+    txt = buf.value.decode()
+    assert n == len(txt)
+    m = re.fullmatch(r"flags 1 count (\d+) compression (\d+) centroids (\d+)((?: \([^)]*\))*)", txt)
+    assert m and int(m.group(1)) == 13 and int(m.group(2)) == 100 and int(m.group(3)) == 4
+    pairs = re.findall(r"\(([^,]+), (\d+)\)", m.group(4))
+    assert [float(a) for a, _ in pairs] == list(means) and [int(b) for _, b in pairs] == list(weights)
+    small = C.create_string_buffer(40)
+    assert L.gysk_tdigest_to_pgtext(means.ctypes.data_as(C.c_void_p), weights.ctypes.data_as(C.c_void_p), 4, 100, small, len(small)) == -28
