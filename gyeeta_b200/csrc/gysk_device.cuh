@@ -195,7 +195,7 @@ __device__ __forceinline__ uint4 table_probe_first(const IdTable &t, unsigned lo
 	return ld_cg_v4(&t.ent[pos]);
 }
 
-__device__ __forceinline__ int table_resolve(const IdTable &t, unsigned long long key, bool insert, uint32_t host_idx, uint32_t pos, uint4 raw)
+__device__ __forceinline__ int table_resolve_slow(const IdTable &t, unsigned long long key, bool insert, uint32_t host_idx, uint32_t pos, uint4 raw)
 {
 	for (uint32_t probe = 0; probe <= t.mask; ++probe) {
 		TblEntry *e = &t.ent[pos];
@@ -235,6 +235,14 @@ __device__ __forceinline__ int table_resolve(const IdTable &t, unsigned long lon
 		raw = ld_cg_v4(&t.ent[pos]);
 	}
 	return -1;
+}
+
+// the common case — the first probe holds the key with its slot published — costs three compares; collisions, unknown ids and
+// inserts take the branch to the full probe loop
+__device__ __forceinline__ int table_resolve(const IdTable &t, unsigned long long key, bool insert, uint32_t host_idx, uint32_t pos, uint4 raw)
+{
+	if (raw.x == (uint32_t)key && raw.y == (uint32_t)(key >> 32) && raw.z - 1u < SLOT_INVALID - 1u) return (int)(raw.z - 1u);
+	return table_resolve_slow(t, key, insert, host_idx, pos, raw);
 }
 
 __device__ __forceinline__ int table_lookup(const IdTable &t, unsigned long long key, bool insert, uint32_t host_idx = 0)

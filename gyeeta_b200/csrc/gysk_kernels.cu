@@ -188,8 +188,8 @@ struct IngestSharedT
 	// per-tile state, double-buffered by tile parity: phase 1 of tile t+1 fills one set while stragglers still drain the other
 	unsigned long long kq[2][INGEST_TILE];		// RESP sort keys of the tile, compacted
 	IngestRec	rec[2][INGEST_TILE];		// decoded TCP events from the front, TASK events from the back (together <= tile)
-	uint32_t	qn[3][4];			// n_resp, n_tcp, n_task; three sets in rotation so that a set is cleared a full tile
-							// before its next use (after the barrier of tile t: the set of tile t+2)
+	unsigned long long qn[3];			// packed {n_resp : 21 | n_tcp : 21 | n_task : 21}; three sets in rotation so that a set is
+							// cleared a full tile before its next use (after the barrier of tile t: the set of tile t+2)
 	unsigned long long key_base[2];
 	uint32_t	key_seq[2];			// tile sequence number + 1 once key_base of that parity is valid
 	uint32_t	max_value;			// largest RESP msec seen by this CTA (sizes the radix sort)
@@ -216,13 +216,14 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	constexpr int INGEST_TILE = IngestShared::INGEST_TILE;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	IngestShared &S = *reinterpret_cast<IngestShared *>(smem_raw);
-	uint32_t c_in = 0, c_drop = 0, c_resp = 0, c_tcp = 0, c_task = 0, c_foreign = 0;	// per thread: < 2^32 events per launch
+	uint32_t c_in = 0, c_foreign = 0;		// per thread: < 2^32 events per launch
+	unsigned long long t_resp = 0, t_tcp = 0, t_task = 0;	// thread 0: per-tile queue lengths summed
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint64_t ntiles = (n + INGEST_TILE - 1) / INGEST_TILE;
-	uint32_t max_ms = 0;
+	uint32_t max_us = 0;
 
 	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
-	if (threadIdx.x < 12) (&S.qn[0][0])[threadIdx.x] = 0;
+	if (threadIdx.x < 3) S.qn[threadIdx.x] = 0;
 	if (threadIdx.x == 0) { S.max_value = 0; S.key_seq[0] = 0; S.key_seq[1] = 0; }
 	if (STAGE && threadIdx.x == 0) mbar_init(&S.mbar, 1);
 	__syncthreads();
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	uint32_t seq = 1;
 	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1, ++seq, qi = qi == 2 ? 0 : qi + 1) {
 		const uint64_t tbase = tile * INGEST_TILE;
-		uint32_t *qn = S.qn[qi];
+		unsigned long long *qn64 = &S.qn[qi];
 		unsigned long long *kq = S.kq[par];
 		IngestRec *rec = S.rec[par];
 		if (STAGE) mbar_wait(&S.mbar, (uint32_t)par);		// this tile's events have landed (one completion per tile)
@@ -279,11 +280,10 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				c_in++;
 				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
 				// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-				if (svc != 0 && svc != KEY_TOMBSTONE && (is_tcp || is_task || (is_resp && value / 1000u <= 1000000u))) {
+				if (svc != 0 && svc != KEY_TOMBSTONE && (is_tcp || is_task || (is_resp && value < 1000001000u))) {	// msec <= 1 000 000
 					kind[k] = is_resp ? (uint32_t)GYSK_EV_RESP : (is_task ? (uint32_t)GYSK_EV_TASK : (uint32_t)GYSK_EV_ACCEPT);
 					praw[k] = table_probe_first(is_task ? st.task_tbl : st.svc_tbl, svc, ppos[k]);
 				}
-				else c_drop++;
 			}
 		}
 #pragma unroll
@@ -293,16 +293,19 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			if (kind[k]) {
 				// one id lookup for all three event kinds (services and tasks live in separate tables)
 				slot = table_resolve(is_task ? st.task_tbl : st.svc_tbl, ((unsigned long long)ra[k].y << 32) | ra[k].x, st.auto_register, rb[k].y, ppos[k], praw[k]);
-				if (slot < 0) c_drop++;
-				else if (is_resp) c_resp++;
-				else if (is_tcp) c_tcp++;
-				else c_task++;
 			}
 			const bool ok = slot >= 0;
-			if (ok && is_resp) max_ms = max(max_ms, rb[k].x / 1000u);	// msec is enough: bits(usec) <= bits(msec) + 10
-			const uint32_t q_resp = queue_reserve(ok && is_resp, &qn[0]);
-			const uint32_t q_tcp = queue_reserve(ok && is_tcp, &qn[1]);
-			const uint32_t q_task = queue_reserve(ok && is_task, &qn[2]);
+			if (ok && is_resp) max_us = max(max_us, rb[k].x);
+			// one shared-memory atomic per warp reserves queue space for all three kinds: {resp : 21 | tcp : 21 | task : 21}
+			const uint32_t m_resp = __ballot_sync(0xffffffffu, ok && is_resp), m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp),
+					m_task = __ballot_sync(0xffffffffu, ok && is_task);
+			unsigned long long qbase = 0;
+			if (lane == 0 && (m_resp | m_tcp | m_task))
+				qbase = atomicAdd(qn64, (unsigned long long)__popc(m_resp) | ((unsigned long long)__popc(m_tcp) << 21) | ((unsigned long long)__popc(m_task) << 42));
+			qbase = __shfl_sync(0xffffffffu, qbase, 0);
+			const uint32_t lt = (1u << lane) - 1u;
+			const uint32_t q_resp = ((uint32_t)qbase & 0x1FFFFFu) + __popc(m_resp & lt), q_tcp = ((uint32_t)(qbase >> 21) & 0x1FFFFFu) + __popc(m_tcp & lt),
+					q_task = (uint32_t)(qbase >> 42) + __popc(m_task & lt);
 			if (ok) {
 				if (is_resp) {
 					// {slot, usec, client port & 31 (CONN_BITMAP index, common/gy_socket_stat.h:403-410)}
@@ -315,13 +318,14 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			}
 		}
 		__syncthreads();			// the only block barrier of the tile: queues of this parity are complete
-		const uint32_t n_resp = qn[0], n_tcp = qn[1], n_task = qn[2];
+		const unsigned long long qv = *qn64;
+		const uint32_t n_resp = (uint32_t)qv & 0x1FFFFFu, n_tcp = (uint32_t)(qv >> 21) & 0x1FFFFFu, n_task = (uint32_t)(qv >> 42);
 		// thread 0 bumps the global key cursor now; its round trip to L2 hides behind the TCP and TASK phases
 		if (threadIdx.x == 0) {
 			// the set of tile t+2 (== tile t-1): every warp has read its counts (it passed this barrier), and nobody appends
 			// to it before the next barrier
-			uint32_t *qz = S.qn[qi == 0 ? 2 : qi - 1];
-			qz[0] = 0; qz[1] = 0; qz[2] = 0;
+			S.qn[qi == 0 ? 2 : qi - 1] = 0;
+			t_resp += n_resp; t_tcp += n_tcp; t_task += n_task;
 			S.key_base[par] = n_resp ? atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)n_resp) : 0ull;
 			__threadfence_block();
 			*((volatile uint32_t *)&S.key_seq[par]) = seq;
@@ -384,8 +388,8 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 		// no barrier here: the next tile fills the other parity; this parity is reused only after the next tile's barrier
 	}
 
-	max_ms = __reduce_max_sync(0xffffffffu, max_ms);
-	if (lane == 0 && max_ms) atomicMax(&S.max_value, max_ms);
+	max_us = __reduce_max_sync(0xffffffffu, max_us);
+	if (lane == 0 && max_us) atomicMax(&S.max_value, max_us / 1000u);	// msec is enough: bits(usec) <= bits(msec) + 10
 	__syncthreads();
 	if (threadIdx.x == 0 && S.max_value) atomicMax(st.counters + CTR_MAXVAL, (unsigned long long)S.max_value);
 	// retire: one RED group per privatised cell
@@ -394,22 +398,20 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
-#pragma unroll
-	for (int off = 16; off > 0; off >>= 1) {
-		c_in += __shfl_down_sync(0xffffffffu, c_in, off);
-		c_drop += __shfl_down_sync(0xffffffffu, c_drop, off);
-		c_resp += __shfl_down_sync(0xffffffffu, c_resp, off);
-		c_tcp += __shfl_down_sync(0xffffffffu, c_tcp, off);
-		c_task += __shfl_down_sync(0xffffffffu, c_task, off);
-		c_foreign += __shfl_down_sync(0xffffffffu, c_foreign, off);
-	}
+	c_in = __reduce_add_sync(0xffffffffu, c_in);
+	c_foreign = __reduce_add_sync(0xffffffffu, c_foreign);
 	if (lane == 0) {
 		if (c_in) atomicAdd(st.counters + CTR_IN, (unsigned long long)c_in);
-		if (c_drop) atomicAdd(st.counters + CTR_DROPPED, (unsigned long long)c_drop);
-		if (c_resp) atomicAdd(st.counters + CTR_RESP, (unsigned long long)c_resp);
-		if (c_tcp) atomicAdd(st.counters + CTR_TCP, (unsigned long long)c_tcp);
-		if (c_task) atomicAdd(st.counters + CTR_TASK, (unsigned long long)c_task);
 		if (c_foreign) atomicAdd(st.counters + CTR_FOREIGN, (unsigned long long)c_foreign);
+		// dropped = taken in but not queued (svc_id 0, bad type or value, table full, unknown id): derived after all adds landed
+		if (c_in) atomicAdd(st.counters + CTR_DROPPED, (unsigned long long)c_in);
+	}
+	if (threadIdx.x == 0) {
+		if (t_resp) atomicAdd(st.counters + CTR_RESP, t_resp);
+		if (t_tcp) atomicAdd(st.counters + CTR_TCP, t_tcp);
+		if (t_task) atomicAdd(st.counters + CTR_TASK, t_task);
+		const unsigned long long q = t_resp + t_tcp + t_task;
+		if (q) atomicAdd(st.counters + CTR_DROPPED, 0ull - q);	// two's complement: dropped += in - queued
 	}
 }
 
