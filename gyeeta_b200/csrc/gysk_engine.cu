@@ -946,6 +946,41 @@ int gysk_export_tdigest(gysk_engine *e, uint64_t id, double *means, uint64_t *we
 	return r.td.n > cap ? GYSK_ERR_NOSPC : GYSK_OK;
 }
 
+// Summary encoder (output side): per-service summaries -> one NOTIFY_LISTENER_STATE message body, i.e. the records
+// MTCP_LISTENER::set_state / the listener-state DB insert read (LISTENER_STATE_NOTIFY, common/gy_comm_proto.h:2183-2254; consumer
+// partha_listener_state, server/gy_mconnhdlr.cc:11175-11251). Fields the engine computes are filled (nqrys_5s_, total_resp_5sec_,
+// p95_5s_resp_ms_, p95_5min_resp_ms_, nconns_ = TCP events of the window, curr_kbytes_inbound_ = their kbytes); what only the host
+// agent knows (task counters, errors, http flag) is zero; curr_state_ is STATE_IDLE (0) without queries, else STATE_OK (2) — the
+// state classifier is out of scope. No issue string: every record is sizeof(LISTENER_STATE_NOTIFY) = 88 bytes, 8-byte aligned.
+int gysk_encode_listener_state(const gysk_svc_summary *sums, uint32_t n, void *buf, uint32_t cap, uint32_t *nrecs, uint32_t *nbytes)
+{
+	if ((!sums && n) || !buf || !nrecs || !nbytes) return GYSK_ERR_INVAL;
+	auto clamp32 = [](uint64_t v) -> uint32_t { return v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v; };
+	auto clampms = [](int64_t v) -> uint32_t { return v < 0 ? 0u : (v > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)v); };
+	uint8_t *p = static_cast<uint8_t *>(buf);
+	uint32_t k = 0;
+
+	for (uint32_t i = 0; i < n; ++i) {
+		if (!sums[i].found) continue;
+		if (k >= wire::LISTENER_STATE_NOTIFY::MAX_NUM_LISTENERS) break;			// one message holds at most 512 records (:2222)
+		if ((size_t)(k + 1) * sizeof(wire::LISTENER_STATE_NOTIFY) > cap) return GYSK_ERR_NOSPC;
+		wire::LISTENER_STATE_NOTIFY r;
+		memset(&r, 0, sizeof(r));
+		r.glob_id_ = sums[i].glob_id;
+		r.nqrys_5s_ = sums[i].nqrys_5s;
+		r.total_resp_5sec_ = clamp32(sums[i].total_resp_5sec);
+		r.p95_5s_resp_ms_ = clampms(sums[i].p95_5s_resp_ms);
+		r.p95_5min_resp_ms_ = clampms(sums[i].p95_5min_resp_ms);
+		r.nconns_ = sums[i].nconns_5s;
+		r.curr_kbytes_inbound_ = sums[i].kbytes_5s;
+		r.curr_state_ = sums[i].nqrys_5s ? 2 : 0;
+		memcpy(p + (size_t)k * sizeof(r), &r, sizeof(r));
+		k++;
+	}
+	*nrecs = k; *nbytes = k * (uint32_t)sizeof(wire::LISTENER_STATE_NOTIFY);
+	return GYSK_OK;
+}
+
 // Text form of the Postgres `tdigest` type (extension tvondra/tdigest, loaded by the reference with `create extension if not
 // exists tdigest`, common/gy_query_common.cc:3385-3387; version unpinned there). tdigest_out prints
 //   "flags %d count %ld compression %d centroids %d" followed by " (%lf, %ld)" per centroid, flags = 1 (TDIGEST_STORES_MEAN),

@@ -340,8 +340,9 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 		// ---------------- phase 2a: TCP — count-min rows, one (event, row) pair per lane ----------------
 		{
 			const uint32_t npairs = n_tcp * st.cms_depth;
+			const bool d4 = st.cms_depth == 4;		// the default depth: no integer division on the pair index
 			for (uint32_t p = threadIdx.x; p < npairs; p += INGEST_THREADS) {
-				const uint32_t e = p / st.cms_depth, row = p - e * st.cms_depth;
+				const uint32_t e = d4 ? p >> 2 : p / st.cms_depth, row = d4 ? p & 3u : p - e * st.cms_depth;
 				const IngestRec r = rec[e];
 				red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index(r.flow_key, row, st.cms_wmask), cms_increment(r.value));
 			}

@@ -111,6 +111,7 @@ def load_library(path=None):
         "gysk_export_tdigest": (i32, [vp, u64, vp, vp, u32, vp, vp, vp]),
         "gysk_query_quantiles": (i32, [vp, u64, vp, u32, vp]),
         "gysk_tdigest_to_pgtext": (i32, [vp, vp, u32, u32, vp, u32]),
+        "gysk_encode_listener_state": (i32, [vp, u32, vp, u32, vp, vp]),
         "gysk_export_tdigest_pgtext": (i32, [vp, u64, vp, u32]),
         "gysk_export_cms": (i32, [vp, i32, vp]),
         "gysk_hist_nbuckets": (i32, [i32]),
@@ -245,6 +246,16 @@ class Engine:
         out = (SvcSummary * len(ids))()
         self._chk(self.L.gysk_query_svcs(self.h, _p(ids), len(ids), out))
         return [o.asdict() for o in out]
+
+    def listener_state_records(self, ids):
+        """query_svcs + gysk_encode_listener_state: the LISTENER_STATE_NOTIFY records (bytes) of the known ids, <= 512"""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = (SvcSummary * len(ids))()
+        self._chk(self.L.gysk_query_svcs(self.h, _p(ids), len(ids), out))
+        buf = C.create_string_buffer(88 * 512)
+        nrecs, nbytes = C.c_uint32(), C.c_uint32()
+        self._chk(self.L.gysk_encode_listener_state(out, len(ids), buf, len(buf), C.byref(nrecs), C.byref(nbytes)))
+        return nrecs.value, buf.raw[: nbytes.value]
 
     def query_flows(self, keys, last_window=False):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)

@@ -289,6 +289,10 @@ int		gysk_hist_bucket(int cls, int64_t value);	/* RESP_TIME_HASH::get_bucket_fro
 int		gysk_hist_percentiles(int cls, int t_is_int, const gysk_hist_serial *stats, uint64_t total_count,
 				const float *pcts, uint32_t npct, int64_t *out);
 double		gysk_hll_estimate(const uint8_t *regs, uint32_t p);
+/* per-service summaries -> LISTENER_STATE_NOTIFY records (common/gy_comm_proto.h:2183-2254), the body of one
+ * NOTIFY_LISTENER_STATE message (<= 512 records, 88 bytes each) that MTCP_LISTENER::set_state / partha_listener_state consume
+ * (server/gy_mconnhdlr.cc:11175-11251). Entries with found == 0 are skipped. No engine needed. */
+int		gysk_encode_listener_state(const gysk_svc_summary *sums, uint32_t n, void *buf, uint32_t cap, uint32_t *nrecs, uint32_t *nbytes);
 /* a digest in the text form of the Postgres `tdigest` type the reference stores and queries (public.tdigest(expr, 100) /
  * tdigest_percentile, common/gy_query_common.cc:1805-1858): "flags 1 count N compression C centroids K (mean, count) ...".
  * Both return the string length, or a negative GYSK_ERR_* */

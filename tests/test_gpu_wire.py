@@ -186,3 +186,38 @@ def test_listener_state_host_summary():
     assert eng.ingest_msg(build_msg(ge.NOTIFY_LISTENER_STATE, recs), host_idx=9) == 0
     assert eng.host_summary(9) == want
     assert eng.host_summary(10) is None
+
+
+def test_listener_state_encoder_roundtrip():
+    """summary encoder: the engine's per-service rows leave as LISTENER_STATE_NOTIFY records; fed back as a
+    NOTIFY_LISTENER_STATE message they pass LISTENER_STATE_NOTIFY::validate and roll up (LISTEN_SUMM_STATS::update) to the
+    totals of the oracle's last window"""
+    from gyeeta_b200 import synth
+    LSN = np.dtype([("glob_id", "<u8"), ("nqrys_5s", "<u4"), ("total_resp_5sec", "<u4"), ("nconns", "<u4"), ("nconns_active", "<u4"),
+                    ("ntasks", "<u4"), ("p95_5s", "<u4"), ("p95_5min", "<u4"), ("kb_in", "<u4"), ("kb_out", "<u4"), ("rest", "u1", 44)])
+    assert LSN.itemsize == 88
+    rng = np.random.default_rng(8)
+    eng = ge.Engine(max_svcs=512, max_tasks=16, max_batch=1 << 15, cms_log2_width=10)
+    orc = po.OracleEngine(max_svcs=512, max_tasks=16, cms_log2_width=10)
+    ev = synth.gen_mixed(rng, 30_000, 150, ntask=4, nhosts=2, nclients=500)
+    eng.ingest_events(ev); orc.ingest(ev)
+    eng.flush(5); orc.flush(5)
+    ids = np.unique(ev["svc_id"][ev["type"] != ge.EV_TASK])
+    ask = np.concatenate([ids, np.array([0xDEAD], dtype=np.uint64)])           # one unknown id: skipped by the encoder
+    nrecs, raw = eng.listener_state_records(ask)
+    assert nrecs == len(ids) and len(raw) == 88 * nrecs
+    recs = np.frombuffer(raw, dtype=LSN)
+    tot_qps = nact = 0
+    for r in recs:
+        h = orc.export_hist(int(r["glob_id"]), 1)
+        c = orc.export_conn(int(r["glob_id"]))
+        assert r["nqrys_5s"] == h[1] and r["total_resp_5sec"] == int(h[0]["sum"].sum())
+        assert r["nconns"] == (c[1] & 0xFFFFFFFF) and r["kb_in"] == (c[1] >> 32)
+        tot_qps += int(h[1]) // 5; nact += int(h[1] != 0)
+    hdr = np.zeros(1, dtype=HDR)
+    hdr["magic"], hdr["data_type"] = PM_MAGIC, COMM_EVENT_NOTIFY
+    hdr["total_sz"] = HDR.itemsize + len(raw)
+    hdr["subtype"], hdr["nevents"] = ge.NOTIFY_LISTENER_STATE, nrecs
+    assert eng.ingest_msg(bytearray(hdr.tobytes() + raw), host_idx=3) == 0
+    hs = eng.host_summary(3)
+    assert hs["nlisteners"] == nrecs and hs["tot_qps"] == tot_qps and hs["nactive"] == nact
