@@ -435,8 +435,8 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	SortTemp &tmp = e->tmp;
 	tmp.max_tiles = (cfg.max_batch + SORT_TILE - 1) / SORT_TILE;
 	A(dalloc(e, &tmp.keys_a, (size_t)cfg.max_batch, false)); A(dalloc(e, &tmp.keys_b, (size_t)cfg.max_batch, false));
-	A(dalloc(e, &tmp.tile_status, (size_t)256 * tmp.max_tiles));
-	A(dalloc(e, &tmp.os_ghist, (size_t)8 * 256 + 8));
+	A(dalloc(e, &tmp.tile_status, (size_t)512 * tmp.max_tiles));
+	A(dalloc(e, &tmp.os_ghist, (size_t)8 * 512 + 8));
 	A(dalloc(e, &tmp.seg_start, ns)); A(dalloc(e, &tmp.seg_end, ns)); A(dalloc(e, &tmp.touched, ns));
 	A(dalloc(e, &tmp.plan_bounds, ns * (TD_CAP + 1))); A(dalloc(e, &tmp.plan_n, ns)); A(dalloc(e, &tmp.newsum, ns * TD_CAP));
 

@@ -417,11 +417,12 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 }
 
 // ---------------------------------------------------------------------------------------------------
-// stable LSD radix sort, 8-bit digits, tile = SORT_TILE keys per CTA of 256 threads
+// stable LSD radix sort, 8- or 9-bit digits, tile = SORT_TILE keys per CTA of 256 threads
 // ---------------------------------------------------------------------------------------------------
-static constexpr int RADIX = 256;
+static constexpr int RADIX_MAX_BITS = 9;
+static constexpr int RADIX_MAX = 1 << RADIX_MAX_BITS;
 
-// one radix pass sorts on an 8-bit digit made of up to two bit fields of the key, so that the unused bits between the usec field
+// one radix pass sorts on a digit made of up to two bit fields of the key, so that the unused bits between the usec field
 // and the slot field of a key never cost a pass: digit = ((k >> s1) & m1) | (((k >> s2) & m2) << b1)
 struct DigitSpec { int s1, b1, s2, b2; };
 __device__ __forceinline__ uint32_t key_digit(unsigned long long k, const DigitSpec &D)
@@ -440,31 +441,32 @@ __device__ __forceinline__ uint32_t key_digit(unsigned long long k, const DigitS
 //                    (status word = 2-bit state | 30-bit count: 1 = this tile's count, 2 = inclusive prefix up to this tile),
 //                    reorders the tile by digit in shared memory and writes every digit's run to its final place.
 // Stability: tiles are ordered by ticket = tile index, ranks inside a tile follow the input order (warp, round, lane).
+// Digits are 8 bits wide; when the significant bits do not fit ceil(bits / 9) + ... passes of 8 (e.g. 41 bits), some passes take
+// 9 bits (512 digits, two per thread in the per-digit steps) instead of the sort paying a whole extra pass.
 // ---------------------------------------------------------------------------------------------------
-static constexpr int OS_THREADS = 256;			// == RADIX: thread d owns digit d in the per-digit steps
+static constexpr int OS_THREADS = 256;			// thread t owns digits t, t + 256 in the per-digit steps
 static constexpr int OS_WARPS = OS_THREADS / 32;
 static constexpr int OS_KPT = SORT_TILE / OS_THREADS;	// 16 keys per thread
 static constexpr int OS_MAX_PASSES = 8;
 static constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_COUNT_MASK = (1u << 30) - 1u;
-static_assert(OS_THREADS == RADIX, "one thread per digit");
 
 struct DigitSpecs { DigitSpec d[OS_MAX_PASSES]; int np; };
 
-static constexpr int OSH_COPIES = 8;			// lane-privatised histogram copies (lane & 7), skewed by one bank each
-static constexpr int OSH_STRIDE = RADIX + 1;
-
+// lane-privatised histogram copies (lane & (copies - 1)), skewed by one bank each: 8 copies of 257 words per pass for 8-bit
+// digits, 4 copies of 513 words when a pass has 9 bits
 __global__ void __launch_bounds__(512) os_hist_kernel(const unsigned long long *__restrict__ keys, uint64_t n, DigitSpecs P,
-		uint32_t *__restrict__ ghist /* [np][256] */)
+		uint32_t *__restrict__ ghist /* [np][RADIX_MAX] */, int copies, int stride)
 {
 	extern __shared__ __align__(16) unsigned char osh_smem[];
-	uint32_t (*h)[OSH_COPIES][OSH_STRIDE] = reinterpret_cast<uint32_t (*)[OSH_COPIES][OSH_STRIDE]>(osh_smem);	// [np][copies][257]
-	const int copy = threadIdx.x & (OSH_COPIES - 1);
+	uint32_t *h = reinterpret_cast<uint32_t *>(osh_smem);		// [np][copies][stride]
+	const int copy = threadIdx.x & (copies - 1);
+	const int pstride = copies * stride;
 
-	for (int i = threadIdx.x; i < P.np * OSH_COPIES * OSH_STRIDE; i += blockDim.x) (&h[0][0][0])[i] = 0;
+	for (int i = threadIdx.x; i < P.np * pstride; i += blockDim.x) h[i] = 0;
 	__syncthreads();
 
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 2;
-	for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+	const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x * 2;
+	for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += gstride) {
 		unsigned long long k0, k1 = 0;
 		const bool two = i + 1 < n;
 		if (two) { const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2 *>(keys + i)); k0 = v.x; k1 = v.y; }
@@ -472,23 +474,25 @@ __global__ void __launch_bounds__(512) os_hist_kernel(const unsigned long long *
 #pragma unroll
 		for (int p = 0; p < OS_MAX_PASSES; ++p) {
 			if (p < P.np) {
-				atomicAdd(&h[p][copy][key_digit(k0, P.d[p])], 1u);
-				if (two) atomicAdd(&h[p][copy][key_digit(k1, P.d[p])], 1u);
+				uint32_t *hp = h + p * pstride + copy * stride;
+				atomicAdd(hp + key_digit(k0, P.d[p]), 1u);
+				if (two) atomicAdd(hp + key_digit(k1, P.d[p]), 1u);
 			}
 		}
 	}
 	__syncthreads();
-	for (int j = threadIdx.x; j < P.np * RADIX; j += blockDim.x) {
-		const int p = j >> 8, d = j & (RADIX - 1);
+	for (int j = threadIdx.x; j < P.np * RADIX_MAX; j += blockDim.x) {
+		const int p = j >> RADIX_MAX_BITS, d = j & (RADIX_MAX - 1);
+		if (d >= stride - 1) continue;
 		uint32_t s = 0;
-#pragma unroll
-		for (int c = 0; c < OSH_COPIES; ++c) s += h[p][c][d];
+		for (int c = 0; c < copies; ++c) s += h[p * pstride + c * stride + d];
 		if (s) atomicAdd(&ghist[j], s);
 	}
 }
 
-// exclusive scan over the 256 threads of the CTA of a packed pair {hi: < 2^32, lo: < 2^16 summed}; smem >= 8 u64
-__device__ __forceinline__ unsigned long long os_block_exclusive_scan(unsigned long long v, unsigned long long *smem)
+// exclusive scan over the 256 threads of the CTA of a packed pair {hi: < 2^32, lo: < 2^16 summed}; smem >= 8 u64.
+// *total = sum over all threads (same value in every thread)
+__device__ __forceinline__ unsigned long long os_block_exclusive_scan(unsigned long long v, unsigned long long *smem, unsigned long long *total)
 {
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	unsigned long long incl = v;
@@ -500,29 +504,35 @@ __device__ __forceinline__ unsigned long long os_block_exclusive_scan(unsigned l
 	}
 	if (lane == 31) smem[wid] = incl;
 	__syncthreads();
-	unsigned long long woff = 0;
+	unsigned long long woff = 0, tot = 0;
 #pragma unroll
-	for (int w = 0; w < OS_WARPS; ++w) if (w < wid) woff += smem[w];
+	for (int w = 0; w < OS_WARPS; ++w) { const unsigned long long x = smem[w]; if (w < wid) woff += x; if (total) tot += x; }
+	if (total) *total = tot;
 	return woff + incl - v;
 }
 
-struct OneSweepShared
+template <int RBITS>
+struct OneSweepSharedT
 {
+	static constexpr int RADIX = 1 << RBITS;
 	unsigned long long	keys[SORT_TILE];		// tile reordered by digit
 	uint32_t		whist[OS_WARPS][RADIX];		// per-warp digit counts, then exclusive prefix over the warps
 	uint32_t		dstart[RADIX];			// tile-local start of each digit
 	uint32_t		goff[RADIX];			// output index of tile-local position 0 of each digit's run (mod 2^32)
-	unsigned long long	scan[OS_WARPS];
+	unsigned long long	scan[2][OS_WARPS];
 	float			fscan[OS_WARPS];
 	uint32_t		tile;
 };
 
+template <int RBITS>
 __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
-		uint32_t n, DigitSpec D, const uint32_t *__restrict__ ghist /* [256] of this pass */, uint32_t *__restrict__ status /* [ntiles][256] */,
+		uint32_t n, DigitSpec D, const uint32_t *__restrict__ ghist /* [RADIX] of this pass */, uint32_t *__restrict__ status /* [ntiles][RADIX] */,
 		uint32_t *__restrict__ ticket, int rank_mode /* 0 auto, 1 match.any, 2 ballots */)
 {
+	constexpr int RADIX = 1 << RBITS;
+	constexpr int DPT = RADIX / OS_THREADS;		// digits per thread in the per-digit steps
 	extern __shared__ __align__(16) unsigned char os_smem[];
-	OneSweepShared &S = *reinterpret_cast<OneSweepShared *>(os_smem);
+	OneSweepSharedT<RBITS> &S = *reinterpret_cast<OneSweepSharedT<RBITS> *>(os_smem);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 
@@ -541,14 +551,18 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 	}
 
 	// Lanes holding the same digit form a group. match.any finds the groups in one instruction, but the hardware walks the
-	// distinct values of the warp one by one (ADU pipe: 73 % busy on a pass whose digits are uniform, ncu r01); eight ballots —
-	// one per digit bit — cost the same whatever the data. The CTA picks per pass: expected number of distinct digits among 32
-	// keys, from the global histogram of the pass.
+	// distinct values of the warp one by one (ADU pipe: 73 % busy on a pass whose digits are uniform, ncu r01); one ballot per
+	// digit bit costs the same whatever the data. The CTA picks per pass: expected number of distinct digits among 32 keys,
+	// from the global histogram of the pass.
 	bool use_ballot;
 	{
-		const float pd = (float)ghist[threadIdx.x] / (float)n;
-		float q = 1.f - pd; q *= q; q *= q; q *= q; q *= q; q *= q;		// (1 - p)^32
-		float distinct = 1.f - q;
+		float distinct = 0.f;
+#pragma unroll
+		for (int j = 0; j < DPT; ++j) {
+			const float pd = (float)ghist[threadIdx.x + j * OS_THREADS] / (float)n;
+			float q = 1.f - pd; q *= q; q *= q; q *= q; q *= q; q *= q;		// (1 - p)^32
+			distinct += 1.f - q;
+		}
 #pragma unroll
 		for (int off = 16; off > 0; off >>= 1) distinct += __shfl_xor_sync(0xffffffffu, distinct, off);
 		if (lane == 0) S.fscan[wid] = distinct;
@@ -565,12 +579,12 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 #pragma unroll
 	for (int r = 0; r < OS_KPT; ++r) {
 		const bool valid = wbase + (uint32_t)r * 32 + lane < n;
-		const uint32_t d = valid ? key_digit(k[r], D) : (0x100u + lane);
+		const uint32_t d = valid ? key_digit(k[r], D) : ((uint32_t)RADIX + lane);
 		uint32_t m;
 		if (use_ballot) {
 			m = 0xffffffffu;
 #pragma unroll
-			for (int b = 0; b < 8; ++b) {
+			for (int b = 0; b < RBITS; ++b) {
 				const bool bit = (d >> b) & 1u;
 				const uint32_t bal = __ballot_sync(0xffffffffu, bit);
 				m &= bit ? bal : ~bal;
@@ -588,32 +602,50 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 	}
 	__syncthreads();
 
-	// thread d: prefix over the warps, the tile's count of digit d -> published at once, so successors can look back through it
-	const uint32_t d = threadIdx.x;
-	uint32_t dtotal = 0;
+	// per digit (thread t: digits t, t + 256): prefix over the warps, the tile's count -> published at once, so successors can
+	// look back through it
+	uint32_t dtotal[DPT];
 #pragma unroll
-	for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = dtotal; dtotal += t; }
-	st_volatile_u32(status + (size_t)tile * RADIX + d, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | dtotal);
-
-	// {global count of digit d, tile count of digit d} -> exclusive scans over the digits in one go
-	const unsigned long long sc = os_block_exclusive_scan(((unsigned long long)ghist[d] << 16) | dtotal, S.scan);
-	const uint32_t gexcl = (uint32_t)(sc >> 16), dstart = (uint32_t)(sc & 0xFFFFu);
-
-	// decoupled look-back: keys with digit d in the tiles before this one
-	uint32_t excl = 0;
-	if (tile > 0) {
-		uint32_t p = tile - 1;
-		for (;;) {
-			const uint32_t v = ld_volatile_u32(status + (size_t)p * RADIX + d);
-			if (!(v >> 30)) continue;				// predecessor has its ticket, so it is running: its count will come
-			excl += v & OS_COUNT_MASK;
-			if (v & OS_FLAG_PREFIX) break;
-			--p;
-		}
-		st_volatile_u32(status + (size_t)tile * RADIX + d, OS_FLAG_PREFIX | (excl + dtotal));
+	for (int j = 0; j < DPT; ++j) {
+		const uint32_t d = threadIdx.x + j * OS_THREADS;
+		uint32_t run = 0;
+#pragma unroll
+		for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
+		dtotal[j] = run;
+		st_volatile_u32(status + (size_t)tile * RADIX + d, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | run);
 	}
-	S.dstart[d] = dstart;
-	S.goff[d] = gexcl + excl - dstart;
+
+	// {global count of the digit, tile count of the digit} -> exclusive scans over the digits (in digit order) in one go
+	unsigned long long carry = 0;
+	uint32_t gexcl[DPT], dstart[DPT];
+#pragma unroll
+	for (int j = 0; j < DPT; ++j) {
+		unsigned long long tot = 0;
+		const unsigned long long sc = carry + os_block_exclusive_scan(((unsigned long long)ghist[threadIdx.x + j * OS_THREADS] << 16) | dtotal[j], S.scan[j],
+				DPT > 1 ? &tot : nullptr);
+		carry += tot;
+		gexcl[j] = (uint32_t)(sc >> 16); dstart[j] = (uint32_t)(sc & 0xFFFFu);
+	}
+
+	// decoupled look-back: keys with the digit in the tiles before this one
+#pragma unroll
+	for (int j = 0; j < DPT; ++j) {
+		const uint32_t d = threadIdx.x + j * OS_THREADS;
+		uint32_t excl = 0;
+		if (tile > 0) {
+			uint32_t p = tile - 1;
+			for (;;) {
+				const uint32_t v = ld_volatile_u32(status + (size_t)p * RADIX + d);
+				if (!(v >> 30)) continue;				// predecessor has its ticket, so it is running: its count will come
+				excl += v & OS_COUNT_MASK;
+				if (v & OS_FLAG_PREFIX) break;
+				--p;
+			}
+			st_volatile_u32(status + (size_t)tile * RADIX + d, OS_FLAG_PREFIX | (excl + dtotal[j]));
+		}
+		S.dstart[d] = dstart[j];
+		S.goff[d] = gexcl[j] + excl - dstart[j];
+	}
 	__syncthreads();
 
 	// reorder the tile by digit in shared memory
@@ -1166,17 +1198,21 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 }
 
 // stable LSD radix sort of the n keys in bufs[0] on the significant key bits [lo1, hi1) then [lo2, hi2) (lo2 >= hi1; pass
-// hi2 <= lo2 for a single range): the significant bits are cut into 8-bit digits in order, a digit may straddle the gap.
-// Result in bufs[*which].
+// hi2 <= lo2 for a single range): the significant bits are cut into digits in order, a digit may straddle the gap. Digits are
+// 8 bits wide unless 9-bit digits save a whole pass (41-45 significant bits: 5 passes instead of 6). Result in bufs[*which].
 static int build_digit_specs(int lo1, int hi1, int lo2, int hi2, DigitSpecs &P)
 {
 	int p1 = lo1, p2 = lo2;			// next unsorted bit of each range
 
 	P.np = 0;
 	if (hi2 < lo2) hi2 = lo2;
+	const int T = (hi1 - lo1) + (hi2 - lo2);
+	const int p8 = (T + 7) / 8, p9 = (T + 8) / 9;
+	int wide = p9 < p8 ? T - 8 * p9 : 0;	// number of 9-bit passes (the first ones)
 	while ((p1 < hi1 || p2 < hi2) && P.np < OS_MAX_PASSES) {
 		DigitSpec D {0, 0, 0, 0};
-		int need = 8;
+		int need = wide > 0 ? 9 : 8;
+		if (wide > 0) --wide;
 		if (p1 < hi1) { D.s1 = p1; D.b1 = hi1 - p1 < need ? hi1 - p1 : need; p1 += D.b1; need -= D.b1; }
 		if (need && p1 >= hi1 && p2 < hi2) {
 			const int take = hi2 - p2 < need ? hi2 - p2 : need;
@@ -1198,29 +1234,35 @@ int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, in
 	*which = 0;
 	if (!n_keys) return 0;
 	if (build_digit_specs(lo1, hi1, lo2, hi2, P) || n_keys >= (1ull << 30)) return -1;	// status words carry 30-bit counts
+	bool any9 = false;
+	for (int p = 0; p < P.np; ++p) any9 |= P.d[p].b1 + P.d[p].b2 > 8;
+	const int copies = any9 ? 4 : 8, stride = (any9 ? 512 : 256) + 1;
 
 	// one-sweep passes: global digit histograms of all passes from one read, then 16 B per key and pass
 	static bool attr_set = false;
 	if (!attr_set) {
-		cudaFuncSetAttribute(os_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepShared));
-		cudaFuncSetAttribute(os_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * OSH_COPIES * OSH_STRIDE * (int)sizeof(uint32_t));
+		cudaFuncSetAttribute(os_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<8>));
+		cudaFuncSetAttribute(os_pass_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<9>));
+		cudaFuncSetAttribute(os_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 8 * 257 * (int)sizeof(uint32_t));
 		attr_set = true;
 	}
 	static const int rank_mode = []{ const char *e = getenv("GYSK_OS_RANK"); return e ? atoi(e) : 0; }();
 	const uint32_t n = (uint32_t)n_keys;
 	const uint32_t ntiles = div_up(n, SORT_TILE);
-	uint32_t *ghist = tmp.os_ghist, *tickets = tmp.os_ghist + OS_MAX_PASSES * RADIX;
+	uint32_t *ghist = tmp.os_ghist, *tickets = tmp.os_ghist + OS_MAX_PASSES * RADIX_MAX;
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 
-	cudaMemsetAsync(ghist, 0, (OS_MAX_PASSES * RADIX + OS_MAX_PASSES) * sizeof(uint32_t), s);
+	cudaMemsetAsync(ghist, 0, (OS_MAX_PASSES * RADIX_MAX + OS_MAX_PASSES) * sizeof(uint32_t), s);
 	const uint32_t hgrid = std::min<uint32_t>(div_up(n, 512 * 2 * 4), (uint32_t)nsm * 3);
-	os_hist_kernel<<<hgrid, 512, P.np * OSH_COPIES * OSH_STRIDE * sizeof(uint32_t), s>>>(bufs[w], n, P, ghist);
+	os_hist_kernel<<<hgrid, 512, (size_t)P.np * copies * stride * sizeof(uint32_t), s>>>(bufs[w], n, P, ghist, copies, stride);
 	launches++;
 	for (int p = 0; p < P.np; ++p) {
-		cudaMemsetAsync(tmp.tile_status, 0, (size_t)ntiles * RADIX * sizeof(uint32_t), s);
-		os_pass_kernel<<<ntiles, OS_THREADS, sizeof(OneSweepShared), s>>>(bufs[w], bufs[w ^ 1], n, P.d[p], ghist + p * RADIX, tmp.tile_status, tickets + p, rank_mode);
+		const bool nine = P.d[p].b1 + P.d[p].b2 > 8;
+		cudaMemsetAsync(tmp.tile_status, 0, (size_t)ntiles * (nine ? 512 : 256) * sizeof(uint32_t), s);
+		if (nine) os_pass_kernel<9><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, rank_mode);
+		else os_pass_kernel<8><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, rank_mode);
 		launches++;
 		w ^= 1;
 	}

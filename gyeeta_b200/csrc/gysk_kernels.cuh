@@ -42,8 +42,8 @@ struct DevState
 struct SortTemp
 {
 	unsigned long long	*keys_a, *keys_b;	// [max_batch]
-	uint32_t		*tile_status;		// [max_tiles][256] look-back status words of the current radix pass
-	uint32_t		*os_ghist;		// [8][256] global digit histograms of the one-sweep passes + [8] tile tickets
+	uint32_t		*tile_status;		// [max_tiles][256 or 512] look-back status words of the current radix pass
+	uint32_t		*os_ghist;		// [8][512] global digit histograms of the one-sweep passes + [8] tile tickets
 	uint32_t		*seg_start, *seg_end;	// [max_svcs]
 	uint32_t		*touched;		// [max_svcs]
 	uint32_t		*plan_bounds, *plan_n;	// [max_svcs][TD_CAP + 1], [max_svcs]: cluster boundaries of the batch's runs

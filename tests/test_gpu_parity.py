@@ -403,3 +403,29 @@ def test_topn_tasks_last_window():
             top = sorted(want.values(), reverse=True)[:10]
             assert [sc for _, sc in got] == top, (t, metric)
             assert all(want[i] == sc for i, sc in got)
+
+
+def test_wide_keys_take_nine_bit_radix_passes():
+    """30 usec bits + 11 slot bits = 41 significant key bits: the sort takes five passes with one 9-bit digit instead of six 8-bit
+    ones (512-digit look-back rows, two digits per thread). Histograms and t-digest centroids stay bit-exact vs the oracle."""
+    rng = np.random.default_rng(41)
+    nsvc = 1500
+    eng, orc = make_pair(max_svcs=2048, max_tasks=8, max_batch=1 << 18, cms_log2_width=10)
+    ids = synth.service_ids(nsvc)
+    n = 200_000
+    ev = np.zeros(n, dtype=ge.EVENT_DTYPE)
+    ev["svc_id"] = ids[rng.integers(0, nsvc, n)]
+    ev["type"] = ge.EV_RESP
+    ev["value"] = np.minimum(np.exp(rng.normal(np.log(2000.0), 3.0, n)), 1.0e9).astype(np.uint32)
+    ev["value"][:50] = 1_000_000_999                     # the largest value the validity rule lets through (msec 1 000 000)
+    ev["flow_key"] = rng.integers(1, 1 << 60, n, dtype=np.uint64)
+    assert int(ev["value"].max()).bit_length() == 30
+    feed_both(eng, orc, ev, 1 << 18)
+    for id_ in ids[:40]:
+        assert_hist_equal(eng, orc, int(id_), ge.HIST_RESP_CUR)
+        got = eng.export_tdigest(int(id_)); td = orc.export_tdigest(int(id_))
+        if got is None:
+            assert td is None
+            continue
+        om, ow = td.centroids()
+        assert np.array_equal(got[0], om) and np.array_equal(got[1], ow) and got[2] == td.minv and got[3] == td.maxv
