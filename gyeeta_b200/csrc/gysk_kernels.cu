@@ -209,7 +209,7 @@ __device__ __forceinline__ uint32_t queue_reserve(bool pred, uint32_t *qn)
 
 template <int INGEST_THREADS, int MIN_CTAS, bool STAGE, int INGEST_EPT>
 __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
-		unsigned long long *__restrict__ keys)
+		unsigned long long *__restrict__ keys, int prefetch_next)
 {
 	using IngestShared = IngestSharedT<INGEST_THREADS, STAGE, INGEST_EPT>;
 	using HotTable = typename IngestShared::HotTable;
@@ -259,6 +259,17 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				}
 			}
 			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }	// type 0xFFFF: padding, not counted
+		}
+		// this CTA's next tile starts moving from HBM to L2 now (no registers held): its loads one tile later find L2
+		if (!STAGE && prefetch_next) {
+#pragma unroll
+			for (int k = 0; k < INGEST_EPT; ++k) {
+				const uint64_t i = tbase + (uint64_t)gridDim.x * INGEST_TILE + (uint64_t)k * INGEST_THREADS + threadIdx.x;
+				if (i < n) {
+					if (prefetch_next == 2) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(ev + i));
+					else asm volatile("prefetch.global.L2 [%0];" :: "l"(ev + i));
+				}
+			}
 		}
 		// decode; put the first id-table probe of all EPT events in flight before any of them is resolved
 		uint4 praw[INGEST_EPT];
@@ -454,13 +465,14 @@ struct DigitSpecs { DigitSpec d[OS_MAX_PASSES]; int np; };
 
 // lane-privatised histogram copies (lane & (copies - 1)), skewed by one bank each: 8 copies of 257 words per pass for 8-bit
 // digits, 4 copies of 513 words when a pass has 9 bits
+template <int copies, int stride>
 __global__ void __launch_bounds__(512) os_hist_kernel(const unsigned long long *__restrict__ keys, uint64_t n, DigitSpecs P,
-		uint32_t *__restrict__ ghist /* [np][RADIX_MAX] */, int copies, int stride)
+		uint32_t *__restrict__ ghist /* [np][RADIX_MAX] */)
 {
 	extern __shared__ __align__(16) unsigned char osh_smem[];
 	uint32_t *h = reinterpret_cast<uint32_t *>(osh_smem);		// [np][copies][stride]
 	const int copy = threadIdx.x & (copies - 1);
-	const int pstride = copies * stride;
+	constexpr int pstride = copies * stride;
 
 	for (int i = threadIdx.x; i < P.np * pstride; i += blockDim.x) h[i] = 0;
 	__syncthreads();
@@ -602,35 +614,19 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 	}
 	__syncthreads();
 
-	// per digit (thread t: digits t, t + 256): prefix over the warps, the tile's count -> published at once, so successors can
-	// look back through it
-	uint32_t dtotal[DPT];
+	if constexpr (DPT == 1) {
+		// thread d: prefix over the warps, the tile's count of digit d -> published at once, so successors can look back through it
+		const uint32_t d = threadIdx.x;
+		uint32_t dtotal = 0;
 #pragma unroll
-	for (int j = 0; j < DPT; ++j) {
-		const uint32_t d = threadIdx.x + j * OS_THREADS;
-		uint32_t run = 0;
-#pragma unroll
-		for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
-		dtotal[j] = run;
-		st_volatile_u32(status + (size_t)tile * RADIX + d, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | run);
-	}
+		for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = dtotal; dtotal += t; }
+		st_volatile_u32(status + (size_t)tile * RADIX + d, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | dtotal);
 
-	// {global count of the digit, tile count of the digit} -> exclusive scans over the digits (in digit order) in one go
-	unsigned long long carry = 0;
-	uint32_t gexcl[DPT], dstart[DPT];
-#pragma unroll
-	for (int j = 0; j < DPT; ++j) {
-		unsigned long long tot = 0;
-		const unsigned long long sc = carry + os_block_exclusive_scan(((unsigned long long)ghist[threadIdx.x + j * OS_THREADS] << 16) | dtotal[j], S.scan[j],
-				DPT > 1 ? &tot : nullptr);
-		carry += tot;
-		gexcl[j] = (uint32_t)(sc >> 16); dstart[j] = (uint32_t)(sc & 0xFFFFu);
-	}
+		// {global count of digit d, tile count of digit d} -> exclusive scans over the digits in one go
+		const unsigned long long sc = os_block_exclusive_scan(((unsigned long long)ghist[d] << 16) | dtotal, S.scan[0], nullptr);
+		const uint32_t gexcl = (uint32_t)(sc >> 16), dstart = (uint32_t)(sc & 0xFFFFu);
 
-	// decoupled look-back: keys with the digit in the tiles before this one
-#pragma unroll
-	for (int j = 0; j < DPT; ++j) {
-		const uint32_t d = threadIdx.x + j * OS_THREADS;
+		// decoupled look-back: keys with digit d in the tiles before this one
 		uint32_t excl = 0;
 		if (tile > 0) {
 			uint32_t p = tile - 1;
@@ -641,10 +637,46 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 				if (v & OS_FLAG_PREFIX) break;
 				--p;
 			}
-			st_volatile_u32(status + (size_t)tile * RADIX + d, OS_FLAG_PREFIX | (excl + dtotal[j]));
+			st_volatile_u32(status + (size_t)tile * RADIX + d, OS_FLAG_PREFIX | (excl + dtotal));
 		}
-		S.dstart[d] = dstart[j];
-		S.goff[d] = gexcl[j] + excl - dstart[j];
+		S.dstart[d] = dstart;
+		S.goff[d] = gexcl + excl - dstart;
+	}
+	else {
+		// thread t owns digits t and t + 256: same steps, the scan runs in digit order with a carry between the two halves
+		uint32_t dtotal[DPT];
+#pragma unroll
+		for (int j = 0; j < DPT; ++j) {
+			const uint32_t d = threadIdx.x + j * OS_THREADS;
+			uint32_t run = 0;
+#pragma unroll
+			for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
+			dtotal[j] = run;
+			st_volatile_u32(status + (size_t)tile * RADIX + d, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | run);
+		}
+		unsigned long long carry = 0;
+#pragma unroll
+		for (int j = 0; j < DPT; ++j) {
+			const uint32_t d = threadIdx.x + j * OS_THREADS;
+			unsigned long long tot = 0;
+			const unsigned long long sc = carry + os_block_exclusive_scan(((unsigned long long)ghist[d] << 16) | dtotal[j], S.scan[j], &tot);
+			carry += tot;
+			const uint32_t gexcl = (uint32_t)(sc >> 16), dstart = (uint32_t)(sc & 0xFFFFu);
+			uint32_t excl = 0;
+			if (tile > 0) {
+				uint32_t p = tile - 1;
+				for (;;) {
+					const uint32_t v = ld_volatile_u32(status + (size_t)p * RADIX + d);
+					if (!(v >> 30)) continue;
+					excl += v & OS_COUNT_MASK;
+					if (v & OS_FLAG_PREFIX) break;
+					--p;
+				}
+				st_volatile_u32(status + (size_t)tile * RADIX + d, OS_FLAG_PREFIX | (excl + dtotal[j]));
+			}
+			S.dstart[d] = dstart;
+			S.goff[d] = gexcl + excl - dstart;
+		}
 	}
 	__syncthreads();
 
@@ -1170,7 +1202,9 @@ static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, ui
 	if (!attr_set) { cudaFuncSetAttribute(ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)); attr_set = true; }
 	const uint64_t want = (n + Shared::INGEST_TILE - 1) / Shared::INGEST_TILE;
 	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * MIN_CTAS ? want : (uint64_t)nsm * MIN_CTAS);
-	ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys);
+	// A/B switch (measured: L2 prefetch of the CTA's next tile costs more issue slots than the latency it hides: 2.58 -> 2.78 ms)
+	static const int prefetch_next = []{ const char *e = getenv("GYSK_INGEST_PREFETCH"); return e ? atoi(e) : 0; }();
+	ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys, prefetch_next);
 }
 
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s)
@@ -1243,7 +1277,8 @@ int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, in
 	if (!attr_set) {
 		cudaFuncSetAttribute(os_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<8>));
 		cudaFuncSetAttribute(os_pass_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<9>));
-		cudaFuncSetAttribute(os_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 8 * 257 * (int)sizeof(uint32_t));
+		cudaFuncSetAttribute(os_hist_kernel<8, 257>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 8 * 257 * (int)sizeof(uint32_t));
+		cudaFuncSetAttribute(os_hist_kernel<4, 513>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 4 * 513 * (int)sizeof(uint32_t));
 		attr_set = true;
 	}
 	static const int rank_mode = []{ const char *e = getenv("GYSK_OS_RANK"); return e ? atoi(e) : 0; }();
@@ -1256,7 +1291,8 @@ int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, in
 
 	cudaMemsetAsync(ghist, 0, (OS_MAX_PASSES * RADIX_MAX + OS_MAX_PASSES) * sizeof(uint32_t), s);
 	const uint32_t hgrid = std::min<uint32_t>(div_up(n, 512 * 2 * 4), (uint32_t)nsm * 3);
-	os_hist_kernel<<<hgrid, 512, (size_t)P.np * copies * stride * sizeof(uint32_t), s>>>(bufs[w], n, P, ghist, copies, stride);
+	if (any9) os_hist_kernel<4, 513><<<hgrid, 512, (size_t)P.np * copies * stride * sizeof(uint32_t), s>>>(bufs[w], n, P, ghist);
+	else os_hist_kernel<8, 257><<<hgrid, 512, (size_t)P.np * copies * stride * sizeof(uint32_t), s>>>(bufs[w], n, P, ghist);
 	launches++;
 	for (int p = 0; p < P.np; ++p) {
 		const bool nine = P.d[p].b1 + P.d[p].b2 > 8;
