@@ -100,8 +100,6 @@ __device__ __forceinline__ void hll_idx_rank(unsigned long long key, uint32_t p,
 // otherwise 1 + #thresholds strictly below the value (the reference's linear scan, mid-slot shortcut included,
 // returns exactly that). Classes whose operator() takes `int` narrow the value first (:1748,:1801,:1854,:2032).
 // ---------------------------------------------------------------------------------------------------
-template <int N> struct Thr { int v[N]; };
-
 __device__ __forceinline__ int bucket_resp_time(long long ms)			// RESP_TIME_HASH :1677, operator()(int64_t)
 {
 	constexpr int thr[13] = {1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000};
@@ -138,25 +136,6 @@ __device__ __forceinline__ int bucket_duration(int data)				// DURATION_HASH :18
 // ---------------------------------------------------------------------------------------------------
 // memory helpers
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
-{
-	unsigned long long v;
-	asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-	return v;
-}
-
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
-{
-	uint32_t v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
-{
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-
 // fire-and-forget 64-bit add: compiles to RED.E.ADD.64 (no return value travels back from L2)
 __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v)
 {

@@ -78,7 +78,9 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n, Aft
 		const uint32_t nslots = std::min<uint32_t>((uint32_t)e->h_counters[2], e->cfg.max_svcs);
 		int value_bits = 1;
 		while (value_bits < VALUE_BITS && (1ull << value_bits) <= max_us) value_bits++;
-		e->kernel_launches += launch_tdigest_update(e->st, e->tmp, n, nkeys, nslots, value_bits, e->stream);
+		const int nl = launch_tdigest_update(e->st, e->tmp, nkeys, nslots, value_bits, e->stream);
+		if (nl < 0) return fail(e, GYSK_ERR_INVAL, "device batch holds 2^30 or more RESP keys");
+		e->kernel_launches += nl;
 	}
 	if (pe) CU(e, cudaEventRecord(pe[2], e->stream));
 	e->batches++;
@@ -1058,7 +1060,7 @@ int gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gys
 	CU(e, cudaMemcpy(&nslots, e->st.svc_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	nslots = std::min(nslots, std::min(e->cfg.max_svcs, e->cfg.max_batch));
 	gysk_topn_entry *d_out = reinterpret_cast<gysk_topn_entry *>(e->d_flowout);		// QCHUNK * 16 B >= 64 * 24 B
-	e->kernel_launches += launch_topn(e->st, e->tmp, nslots, metric, host_idx, n, d_out, e->stream);
+	{ const int nl = launch_topn(e->st, e->tmp, nslots, metric, host_idx, n, d_out, e->stream); if (nl > 0) e->kernel_launches += nl; }
 	gysk_topn_entry *h_out = reinterpret_cast<gysk_topn_entry *>(e->h_flowout);
 	CU(e, cudaMemcpyAsync(h_out, d_out, sizeof(gysk_topn_entry) * n, cudaMemcpyDeviceToHost, e->stream));
 	CU(e, cudaStreamSynchronize(e->stream));
@@ -1082,7 +1084,7 @@ int gysk_topn_tasks(gysk_engine *e, int metric, uint32_t n, gysk_topn_entry *out
 	ntasks = std::min(ntasks, std::min(e->cfg.max_tasks, e->cfg.max_batch));
 	gysk_topn_entry *d_out = reinterpret_cast<gysk_topn_entry *>(e->d_flowout);		// QCHUNK * 16 B >= 64 * 24 B
 	CU(e, cudaMemsetAsync(d_out, 0, sizeof(gysk_topn_entry) * n, e->stream));
-	e->kernel_launches += launch_topn_tasks(e->st, e->tmp, ntasks, metric, n, d_out, e->stream);
+	{ const int nl = launch_topn_tasks(e->st, e->tmp, ntasks, metric, n, d_out, e->stream); if (nl > 0) e->kernel_launches += nl; }
 	gysk_topn_entry *h_out = reinterpret_cast<gysk_topn_entry *>(e->h_flowout);
 	CU(e, cudaMemcpyAsync(h_out, d_out, sizeof(gysk_topn_entry) * n, cudaMemcpyDeviceToHost, e->stream));
 	CU(e, cudaStreamSynchronize(e->stream));

@@ -1307,7 +1307,7 @@ int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, in
 }
 
 // sort the (slot, usec) keys produced by ingest, then fold every touched service's new samples into its digest
-int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_events, uint64_t n, uint32_t nslots, int value_bits, cudaStream_t s)
+int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t nslots, int value_bits, cudaStream_t s)
 {
 	if (!n) return 0;		// n = number of RESP keys of this batch (read back by the host), nslots = services registered so far
 	int launches = 0;
@@ -1326,8 +1326,9 @@ int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_ev
 
 	// with the warp-autonomous ingest the keys sit at their events' positions with sentinels in between: the first pass reads
 	// n_events slots and compacts, the later passes run over the n keys
-	(void)n_events;
-	launches += launch_radix_sort(tmp, n, KEY_VALUE_SHIFT, KEY_VALUE_SHIFT + value_bits, KEY_SLOT_SHIFT, KEY_SLOT_SHIFT + (int)slot_bits, &which, s);
+	const int sorted = launch_radix_sort(tmp, n, KEY_VALUE_SHIFT, KEY_VALUE_SHIFT + value_bits, KEY_SLOT_SHIFT, KEY_SLOT_SHIFT + (int)slot_bits, &which, s);
+	if (sorted < 0) return sorted;
+	launches += sorted;
 	src = bufs[which];
 
 	td_segments_kernel<<<div_up(n, 256 * TSEG_V), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
@@ -1382,7 +1383,9 @@ int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int me
 	unsigned long long *d_n = st.counters + CTR_NKEYS;
 	int which = 0, launches = 2;
 	topn_score_kernel<<<div_up(nslots, 256), 256, 0, s>>>(st, nslots, metric, host_filter, tmp.keys_a, d_n);
-	launches += launch_radix_sort(tmp, nslots, 32, 64, 64, 64, &which, s);
+	const int sorted = launch_radix_sort(tmp, nslots, 32, 64, 64, 64, &which, s);
+	if (sorted < 0) return sorted;
+	launches += sorted;
 	topn_pick_kernel<<<1, 64, 0, s>>>(st, which ? tmp.keys_b : tmp.keys_a, nslots, want, d_out);
 	return launches;
 }
@@ -1436,7 +1439,9 @@ int launch_topn_tasks(const DevState &st, const SortTemp &tmp, uint32_t ntasks, 
 	if (!ntasks) return 0;
 	int which = 0, launches = 2;
 	topn_task_score_kernel<<<div_up(ntasks, 256), 256, 0, s>>>(st, ntasks, metric, tmp.keys_a);
-	launches += launch_radix_sort(tmp, ntasks, 32, 64, 64, 64, &which, s);
+	const int sorted = launch_radix_sort(tmp, ntasks, 32, 64, 64, 64, &which, s);
+	if (sorted < 0) return sorted;
+	launches += sorted;
 	topn_task_pick_kernel<<<1, 64, 0, s>>>(st, which ? tmp.keys_b : tmp.keys_a, ntasks, want, d_out);
 	return launches;
 }
