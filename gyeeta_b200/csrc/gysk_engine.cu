@@ -1106,6 +1106,30 @@ int gysk_query_host_summary(gysk_engine *e, uint32_t host_idx, gysk_host_summary
 	return GYSK_OK;
 }
 
+int gysk_query_cluster_state(gysk_engine *e, const uint32_t *host_idxs, uint32_t n, gysk_cluster_state *out)
+{
+	CHECK_ENGINE(e);
+	if (!out || (!host_idxs && n)) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->mtx);
+	memset(out, 0, sizeof(*out));
+	auto add = [&](const gysk_host_summary & hs) {
+		const uint32_t issues = (uint32_t)(hs.nstates[3] + hs.nstates[4] + hs.nstates[5]);	// STATE_BAD, STATE_SEVERE, STATE_DOWN
+		out->nhosts++;
+		out->nsvc_issue += issues; out->nsvcissue_hosts += !!issues;
+		out->nsvc += (uint32_t)hs.nlisteners;
+		out->total_qps += (uint32_t)hs.tot_qps;
+		out->svc_net_mb += (uint32_t)((hs.tot_kb_inbound + hs.tot_kb_outbound) / 1024);
+	};
+	if (!host_idxs) { for (const auto & kv : e->host_summ) add(kv.second); }
+	else {
+		for (uint32_t i = 0; i < n; ++i) {
+			auto it = e->host_summ.find(host_idxs[i]);
+			if (it != e->host_summ.end()) add(it->second);
+		}
+	}
+	return GYSK_OK;
+}
+
 int gysk_export_cms(gysk_engine *e, int last_window, uint64_t *cells)
 {
 	CHECK_ENGINE(e);

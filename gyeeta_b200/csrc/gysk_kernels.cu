@@ -207,7 +207,7 @@ __device__ __forceinline__ uint32_t queue_reserve(bool pred, uint32_t *qn)
 	return base + __popc(m & ((1u << lane) - 1u));
 }
 
-template <int INGEST_THREADS, int MIN_CTAS, bool STAGE, int INGEST_EPT>
+template <int INGEST_THREADS, int MIN_CTAS, bool STAGE, int INGEST_EPT, bool PIPE>
 __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
 		unsigned long long *__restrict__ keys, int prefetch_next)
 {
@@ -234,20 +234,11 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 		tma_load_1d(S.evbuf, ev + b0, (uint32_t)cnt * 32u, &S.mbar);
 	}
 
-	int par = 0, qi = 0;
-	uint32_t seq = 1;
-	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1, ++seq, qi = qi == 2 ? 0 : qi + 1) {
-		const uint64_t tbase = tile * INGEST_TILE;
-		unsigned long long *qn64 = &S.qn[qi];
-		unsigned long long *kq = S.kq[par];
-		IngestRec *rec = S.rec[par];
-		if (STAGE) mbar_wait(&S.mbar, (uint32_t)par);		// this tile's events have landed (one completion per tile)
-
-		// ---------------- phase 1: decode + lookup + enqueue ----------------
-		uint4 ra[INGEST_EPT], rb[INGEST_EPT];
+	uint4 ra[INGEST_EPT], rb[INGEST_EPT];
+	auto load_tile = [&](uint64_t tb) {
 #pragma unroll
 		for (int k = 0; k < INGEST_EPT; ++k) {
-			const uint64_t i = tbase + (uint64_t)k * INGEST_THREADS + threadIdx.x;
+			const uint64_t i = tb + (uint64_t)k * INGEST_THREADS + threadIdx.x;
 			if (i < n) {
 				if (STAGE) {
 					ra[k] = S.evbuf[2 * (k * INGEST_THREADS + threadIdx.x)];
@@ -260,6 +251,22 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			}
 			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }	// type 0xFFFF: padding, not counted
 		}
+	};
+	if (PIPE && !STAGE) load_tile((uint64_t)blockIdx.x * INGEST_TILE);
+
+	int par = 0, qi = 0;
+	uint32_t seq = 1;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1, ++seq, qi = qi == 2 ? 0 : qi + 1) {
+		const uint64_t tbase = tile * INGEST_TILE;
+		unsigned long long *qn64 = &S.qn[qi];
+		unsigned long long *kq = S.kq[par];
+		IngestRec *rec = S.rec[par];
+		if (STAGE) mbar_wait(&S.mbar, (uint32_t)par);		// this tile's events have landed (one completion per tile)
+
+		// ---------------- phase 1: decode + lookup + enqueue ----------------
+		// The tile's events are already on their way (or here): their loads were issued before the previous tile's barrier
+		// (PIPE), so the only memory latency left on this phase's critical path is the id-table probe.
+		if (!PIPE || STAGE) load_tile(tbase);
 		// this CTA's next tile starts moving from HBM to L2 now (no registers held): its loads one tile later find L2
 		if (!STAGE && prefetch_next) {
 #pragma unroll
@@ -328,6 +335,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				}
 			}
 		}
+		if (PIPE && !STAGE) load_tile(tbase + (uint64_t)gridDim.x * INGEST_TILE);	// next tile of this CTA (all padding past the end)
 		__syncthreads();			// the only block barrier of the tile: queues of this parity are complete
 		const unsigned long long qv = *qn64;
 		const uint32_t n_resp = (uint32_t)qv & 0x1FFFFFu, n_tcp = (uint32_t)(qv >> 21) & 0x1FFFFFu, n_task = (uint32_t)(qv >> 42);
@@ -1194,17 +1202,17 @@ static int ingest_variant()
 	return v;
 }
 
-template <int THREADS, int MIN_CTAS, bool STAGE, int EPT = 4>
+template <int THREADS, int MIN_CTAS, bool STAGE, int EPT = 4, bool PIPE = false>
 static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, int nsm, cudaStream_t s)
 {
 	using Shared = IngestSharedT<THREADS, STAGE, EPT>;
 	static bool attr_set = false;
-	if (!attr_set) { cudaFuncSetAttribute(ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)); attr_set = true; }
+	if (!attr_set) { cudaFuncSetAttribute(ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)); attr_set = true; }
 	const uint64_t want = (n + Shared::INGEST_TILE - 1) / Shared::INGEST_TILE;
 	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * MIN_CTAS ? want : (uint64_t)nsm * MIN_CTAS);
 	// A/B switch (measured: L2 prefetch of the CTA's next tile costs more issue slots than the latency it hides: 2.58 -> 2.78 ms)
 	static const int prefetch_next = []{ const char *e = getenv("GYSK_INGEST_PREFETCH"); return e ? atoi(e) : 0; }();
-	ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys, prefetch_next);
+	ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT, PIPE><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys, prefetch_next);
 }
 
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s)
@@ -1222,10 +1230,7 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsign
 	else if (variant == 2562) launch_ingest_variant<256, 5, false, 2>(st, d_ev, n, d_keys, nsm, s);	// 2 events per thread: fewer live registers, 5 CTAs/SM
 	else if (variant == 2568) launch_ingest_variant<256, 3, false, 8>(st, d_ev, n, d_keys, nsm, s);	// 8 events per thread: fewer barriers per event
 	else if (variant == 2662) launch_ingest_variant<256, 6, false, 2>(st, d_ev, n, d_keys, nsm, s);
-	else if (variant == 1282) launch_ingest_variant<128, 10, false, 2>(st, d_ev, n, d_keys, nsm, s);
-	else if (variant == 2581) launch_ingest_variant<256, 8, false, 1>(st, d_ev, n, d_keys, nsm, s);
-	else if (variant == 5122) launch_ingest_variant<512, 2, false, 2>(st, d_ev, n, d_keys, nsm, s);
-	else if (variant == 5123) launch_ingest_variant<512, 3, false, 2>(st, d_ev, n, d_keys, nsm, s);
+	else if (variant == 25620) launch_ingest_variant<256, 5, false, 2, true>(st, d_ev, n, d_keys, nsm, s);	// next tile's loads issued before the barrier (measured: 2.74 vs 2.61 ms)
 	else if (variant == 256) launch_ingest_variant<256, 4, false>(st, d_ev, n, d_keys, nsm, s);
 	else launch_ingest_variant<256, 5, false, 2>(st, d_ev, n, d_keys, nsm, s);
 	return 1;

@@ -53,6 +53,10 @@ class HostSummary(C.Structure):
                                                                          "tot_ser_errors", "nlisteners", "nactive", "pad")]
 
 
+class ClusterState(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("nhosts", "nsvc_issue", "nsvcissue_hosts", "nsvc", "total_qps", "svc_net_mb")] + [("pad", C.c_uint32 * 2)]
+
+
 class TopnEntry(C.Structure):
     _fields_ = [("glob_id", C.c_uint64), ("score", C.c_uint64), ("host_idx", C.c_uint32), ("pad", C.c_uint32)]
 
@@ -104,6 +108,7 @@ def load_library(path=None):
         "gysk_query_host_summary": (i32, [vp, u32, vp]),
         "gysk_topn_svcs": (i32, [vp, i32, C.c_int32, u32, vp, vp]),
         "gysk_topn_tasks": (i32, [vp, i32, u32, vp, vp]),
+        "gysk_query_cluster_state": (i32, [vp, vp, u32, vp]),
         "gysk_export_hist": (i32, [vp, u64, i32, vp, vp, vp]),
         "gysk_export_task_hist": (i32, [vp, u64, i32, vp, vp, vp]),
         "gysk_export_hll": (i32, [vp, u64, vp]),
@@ -274,6 +279,15 @@ class Engine:
         k = C.c_uint32()
         self._chk(self.L.gysk_topn_tasks(self.h, metric, n, out, C.byref(k)))
         return [(o.glob_id, o.score) for o in out[: k.value]]
+
+    def cluster_state(self, host_idxs=None):
+        cs = ClusterState()
+        if host_idxs is None:
+            self._chk(self.L.gysk_query_cluster_state(self.h, None, 0, C.byref(cs)))
+        else:
+            h = np.ascontiguousarray(host_idxs, dtype=np.uint32)
+            self._chk(self.L.gysk_query_cluster_state(self.h, _p(h), len(h), C.byref(cs)))
+        return {f: getattr(cs, f) for f, _ in cs._fields_ if f != "pad"}
 
     def host_summary(self, host_idx):
         hs = HostSummary()

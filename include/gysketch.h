@@ -190,6 +190,20 @@ typedef struct gysk_host_summary
 	int32_t		pad;
 } gysk_host_summary;
 
+/* cluster roll-up of the host summaries: the service part of MS_CLUSTER_STATE::STATE_ONE (common/gy_comm_proto.h:3183-3214) as
+ * CLUSTER_STATE_ONE::update_from_state fills it from PARTHA_INFO::summstats_ (server/gy_mconnhdlr.cc:16036-16046). The task / cpu /
+ * memory issue counters come from the host agent's HOST_STATE_NOTIFY and stay zero here. */
+typedef struct gysk_cluster_state
+{
+	uint32_t	nhosts;			/* hosts with a listener-state summary */
+	uint32_t	nsvc_issue;		/* listeners in STATE_BAD / STATE_SEVERE / STATE_DOWN */
+	uint32_t	nsvcissue_hosts;	/* hosts with at least one such listener */
+	uint32_t	nsvc;			/* += nlisteners */
+	uint32_t	total_qps;		/* += tot_qps_ */
+	uint32_t	svc_net_mb;		/* += (tot_kb_inbound_ + tot_kb_outbound_) / 1024 */
+	uint32_t	pad[2];
+} gysk_cluster_state;
+
 /* top-N services of the last closed window (BOUNDED_PRIO_QUEUE users of partha_listener_state, gy_mconnhdlr.cc:11262-11304) */
 enum { GYSK_TOPN_QPS = 0, GYSK_TOPN_CONNS = 1, GYSK_TOPN_NET = 2 };
 /* top-N aggregated processes of the last closed window: atask_top_cpu_ / atask_top_cpu_delay_ / atask_top_io_delay_ of
@@ -269,7 +283,10 @@ int		gysk_query_flows(gysk_engine *e, const uint64_t *flow_keys, uint32_t n, int
 /* LISTEN_SUMM_STATS of the last NOTIFY_LISTENER_STATE message of a host (partha_listener_state, gy_mconnhdlr.cc:11251) */
 /* host_idx < 0: over all hosts of this engine; n <= 64 */
 int		gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gysk_topn_entry *out, uint32_t *nout);
-int		gysk_topn_tasks(gysk_engine *e, int metric, uint32_t n, gysk_topn_entry *out, uint32_t *nout);	/* n <= 64; glob_id = aggr_task_id */
+int		gysk_topn_tasks(gysk_engine *e, int metric, uint32_t n, gysk_topn_entry *out, uint32_t *nout);
+/* roll-up over the given hosts (the hosts of one cluster_name_; host_idxs NULL = every host of this engine): what
+ * MCONN_HANDLER::send_cluster_state (server/gy_mconnhdlr.cc:16052) sends to shyama per cluster */
+int		gysk_query_cluster_state(gysk_engine *e, const uint32_t *host_idxs, uint32_t n, gysk_cluster_state *out);	/* n <= 64; glob_id = aggr_task_id */
 int		gysk_query_host_summary(gysk_engine *e, uint32_t host_idx, gysk_host_summary *out);
 int		gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial out[GYSK_HIST_MAX_BUCKETS],
 				uint64_t *total_count, int64_t *max_val);

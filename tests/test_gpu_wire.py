@@ -186,6 +186,15 @@ def test_listener_state_host_summary():
     assert eng.ingest_msg(build_msg(ge.NOTIFY_LISTENER_STATE, recs), host_idx=9) == 0
     assert eng.host_summary(9) == want
     assert eng.host_summary(10) is None
+    # cluster roll-up of the host summaries (MS_CLUSTER_STATE::STATE_ONE service fields, gy_mconnhdlr.cc:16036-16046)
+    assert eng.ingest_msg(build_msg(ge.NOTIFY_LISTENER_STATE, recs[:50]), host_idx=11) == 0
+    h11 = eng.host_summary(11)
+    issues = lambda h: h["nstates"][3] + h["nstates"][4] + h["nstates"][5]
+    cs = eng.cluster_state()
+    assert cs == dict(nhosts=2, nsvc_issue=issues(want) + issues(h11), nsvcissue_hosts=int(issues(want) > 0) + int(issues(h11) > 0),
+                      nsvc=want["nlisteners"] + 50, total_qps=want["tot_qps"] + h11["tot_qps"],
+                      svc_net_mb=(want["tot_kb_inbound"] + want["tot_kb_outbound"]) // 1024 + (h11["tot_kb_inbound"] + h11["tot_kb_outbound"]) // 1024)
+    assert eng.cluster_state([9, 77])["nhosts"] == 1
 
 
 def test_listener_state_encoder_roundtrip():
