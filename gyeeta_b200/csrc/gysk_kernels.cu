@@ -15,6 +15,7 @@
 #include <climits>
 #include <cmath>
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 
@@ -188,8 +189,12 @@ struct IngestSharedT
 	// per-tile state, double-buffered by tile parity: phase 1 of tile t+1 fills one set while stragglers still drain the other
 	unsigned long long kq[2][INGEST_TILE];		// RESP sort keys of the tile, compacted
 	IngestRec	rec[2][INGEST_TILE];		// decoded TCP events from the front, TASK events from the back (together <= tile)
-	unsigned long long qn[3];			// packed {n_resp : 21 | n_tcp : 21 | n_task : 21}; three sets in rotation so that a set is
-							// cleared a full tile before its next use (after the barrier of tile t: the set of tile t+2)
+	// packed {n_resp | n_tcp | n_task}, QBITS bits each; three sets in rotation so that a set is cleared a full tile before its
+	// next use (after the barrier of tile t: the set of tile t+2). Tiles of up to 512 events fit 3 x 10 bits in ONE 32-bit word
+	// (native shared-memory add; the 64-bit add is a compare-and-swap loop)
+	static constexpr int QBITS = INGEST_TILE <= 512 ? 10 : 21;
+	using QWord = typename std::conditional<INGEST_TILE <= 512, uint32_t, unsigned long long>::type;
+	QWord		qn[3];
 	unsigned long long key_base[2];
 	uint32_t	key_seq[2];			// tile sequence number + 1 once key_base of that parity is valid
 	uint32_t	max_value;			// largest RESP msec seen by this CTA (sizes the radix sort)
@@ -214,6 +219,9 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	using IngestShared = IngestSharedT<INGEST_THREADS, STAGE, INGEST_EPT>;
 	using HotTable = typename IngestShared::HotTable;
 	constexpr int INGEST_TILE = IngestShared::INGEST_TILE;
+	constexpr int QBITS = IngestShared::QBITS;
+	constexpr uint32_t QMASK = (1u << QBITS) - 1u;
+	using QWord = typename IngestShared::QWord;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	IngestShared &S = *reinterpret_cast<IngestShared *>(smem_raw);
 	uint32_t c_in = 0, c_foreign = 0;		// per thread: < 2^32 events per launch
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	uint32_t seq = 1;
 	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1, ++seq, qi = qi == 2 ? 0 : qi + 1) {
 		const uint64_t tbase = tile * INGEST_TILE;
-		unsigned long long *qn64 = &S.qn[qi];
+		QWord *qn64 = &S.qn[qi];
 		unsigned long long *kq = S.kq[par];
 		IngestRec *rec = S.rec[par];
 		if (STAGE) mbar_wait(&S.mbar, (uint32_t)par);		// this tile's events have landed (one completion per tile)
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				c_in++;
 				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
 				// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-				if (svc != 0 && svc != KEY_TOMBSTONE && (is_tcp || is_task || (is_resp && value < 1000001000u))) {	// msec <= 1 000 000
+				if (svc + 1ull > 1ull && (is_tcp || is_task || (is_resp && value < 1000001000u))) {	// id not 0 / ~0 (tombstone); msec <= 1 000 000
 					kind[k] = is_resp ? (uint32_t)GYSK_EV_RESP : (is_task ? (uint32_t)GYSK_EV_TASK : (uint32_t)GYSK_EV_ACCEPT);
 					praw[k] = table_probe_first(is_task ? st.task_tbl : st.svc_tbl, svc, ppos[k]);
 				}
@@ -317,13 +325,13 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			// one shared-memory atomic per warp reserves queue space for all three kinds: {resp : 21 | tcp : 21 | task : 21}
 			const uint32_t m_resp = __ballot_sync(0xffffffffu, ok && is_resp), m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp),
 					m_task = __ballot_sync(0xffffffffu, ok && is_task);
-			unsigned long long qbase = 0;
+			QWord qbase = 0;
 			if (lane == 0 && (m_resp | m_tcp | m_task))
-				qbase = atomicAdd(qn64, (unsigned long long)__popc(m_resp) | ((unsigned long long)__popc(m_tcp) << 21) | ((unsigned long long)__popc(m_task) << 42));
+				qbase = atomicAdd(qn64, (QWord)__popc(m_resp) | ((QWord)__popc(m_tcp) << QBITS) | ((QWord)__popc(m_task) << (2 * QBITS)));
 			qbase = __shfl_sync(0xffffffffu, qbase, 0);
 			const uint32_t lt = (1u << lane) - 1u;
-			const uint32_t q_resp = ((uint32_t)qbase & 0x1FFFFFu) + __popc(m_resp & lt), q_tcp = ((uint32_t)(qbase >> 21) & 0x1FFFFFu) + __popc(m_tcp & lt),
-					q_task = (uint32_t)(qbase >> 42) + __popc(m_task & lt);
+			const uint32_t q_resp = ((uint32_t)qbase & QMASK) + __popc(m_resp & lt), q_tcp = ((uint32_t)(qbase >> QBITS) & QMASK) + __popc(m_tcp & lt),
+					q_task = (uint32_t)(qbase >> (2 * QBITS)) + __popc(m_task & lt);
 			if (ok) {
 				if (is_resp) {
 					// {slot, usec, client port & 31 (CONN_BITMAP index, common/gy_socket_stat.h:403-410)}
@@ -337,8 +345,8 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 		}
 		if (PIPE && !STAGE) load_tile(tbase + (uint64_t)gridDim.x * INGEST_TILE);	// next tile of this CTA (all padding past the end)
 		__syncthreads();			// the only block barrier of the tile: queues of this parity are complete
-		const unsigned long long qv = *qn64;
-		const uint32_t n_resp = (uint32_t)qv & 0x1FFFFFu, n_tcp = (uint32_t)(qv >> 21) & 0x1FFFFFu, n_task = (uint32_t)(qv >> 42);
+		const QWord qv = *qn64;
+		const uint32_t n_resp = (uint32_t)qv & QMASK, n_tcp = (uint32_t)(qv >> QBITS) & QMASK, n_task = (uint32_t)(qv >> (2 * QBITS));
 		// thread 0 bumps the global key cursor now; its round trip to L2 hides behind the TCP and TASK phases
 		if (threadIdx.x == 0) {
 			// the set of tile t+2 (== tile t-1): every warp has read its counts (it passed this barrier), and nobody appends
