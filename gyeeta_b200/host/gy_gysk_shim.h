@@ -12,6 +12,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <vector>
 
 #include "../../include/gysketch.h"
 
@@ -58,6 +59,42 @@ public :
 	// the 5-s reducer tick (TCP_SOCK_HANDLER::listener_stats_update cadence, common/gy_socket_stat.cc:3898)
 	bool flush_window(uint32_t tsec) noexcept { return 0 == gysk_flush(engine_, tsec); }
 
+	// The tick plus what the reference does when a partha reports a deleted listener (LISTENER_STATE_NOTIFY with
+	// query_flags_ == LISTEN_FLAG_DELETE, common/gy_socket_stat.cc:4023-4033): with gysk_config.idle_evict_secs set, the ids the
+	// engine evicted at this flush are handed to `on_delete(glob_id)` — the place to drop the MTCP_LISTENER of that id.
+	template <typename OnDelete>
+	bool flush_window(uint32_t tsec, OnDelete && on_delete) noexcept
+	{
+		if (0 != gysk_flush(engine_, tsec)) return false;
+		try {
+			uint32_t n = 0;
+			evicted_.resize(evicted_.size() < 1024 ? 1024 : evicted_.size());
+			if (0 != gysk_evicted_ids(engine_, evicted_.data(), (uint32_t)evicted_.size(), &n)) return false;
+			if (n > evicted_.size()) {
+				evicted_.resize(n);
+				if (0 != gysk_evicted_ids(engine_, evicted_.data(), (uint32_t)evicted_.size(), &n)) return false;
+			}
+			for (uint32_t i = 0; i < n && i < evicted_.size(); ++i) on_delete(evicted_[i]);
+		}
+		catch (...) { return false; }
+		return true;
+	}
+
+	// Engine output in the reference's own record form: the LISTENER_STATE_NOTIFY batch of the given listeners (<= 512 per call,
+	// common/gy_comm_proto.h:2222), ready for the unchanged partha_listener_state / MTCP_LISTENER::set_state path.
+	// `out` must hold n * 88 bytes. Returns the number of records written, -1 on failure.
+	int listener_state_records(const uint64_t *glob_ids, uint32_t n, void *out, uint32_t cap_bytes) noexcept
+	{
+		try {
+			summ_.resize(n);
+			uint32_t nrecs = 0, nbytes = 0;
+			if (0 != gysk_query_svcs(engine_, glob_ids, n, summ_.data())) return -1;
+			if (0 != gysk_encode_listener_state(summ_.data(), n, out, cap_bytes, &nrecs, &nbytes)) return -1;
+			return (int)nrecs;
+		}
+		catch (...) { return -1; }
+	}
+
 	gysk_engine * engine() const noexcept { return engine_; }
 
 private :
@@ -71,6 +108,8 @@ private :
 	}
 
 	gysk_engine		*engine_;
+	std::vector<uint64_t>	evicted_;
+	std::vector<gysk_svc_summary> summ_;
 };
 
 } // namespace gysk_shim

@@ -49,5 +49,12 @@ int main()
 		gysk_destroy(e);
 		return good ? 0 : 2;
 	}
-	return (rc == GYSK_ERR_NODEV && !ok1 && !ok2 && !ok3) ? 0 : 1;
+	// no engine: the tick helpers and the record encoder report failure instead of touching anything
+	int ndel = 0;
+	const bool tick = h.flush_window(5, [&](uint64_t) { ++ndel; });
+	uint64_t ids[2] = {11, 12};
+	uint8_t recs[2 * sizeof(LISTENER_STATE_NOTIFY)];
+	const int nrec = h.listener_state_records(ids, 2, recs, sizeof(recs));
+	std::printf("tick: %d deletes: %d records: %d\n", tick, ndel, nrec);
+	return (rc == GYSK_ERR_NODEV && !ok1 && !ok2 && !ok3 && !tick && ndel == 0 && nrec == -1) ? 0 : 1;
 }

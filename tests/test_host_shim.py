@@ -28,7 +28,7 @@ def test_shim_compiles_and_fails_loudly_without_gpu():
         pytest.skip("GPU present: covered by the gpu test")
     r = subprocess.run([_build()], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "rc=-19" in r.stdout and "handlers: 0 0 0" in r.stdout
+    assert "rc=-19" in r.stdout and "handlers: 0 0 0" in r.stdout and "tick: 0 deletes: 0 records: -1" in r.stdout
 
 
 @pytest.mark.gpu
