@@ -1130,6 +1130,23 @@ int gysk_query_cluster_state(gysk_engine *e, const uint32_t *host_idxs, uint32_t
 	return GYSK_OK;
 }
 
+// The radix passes the t-digest chain would run for keys with `value_bits` significant usec bits and `nslots` services:
+// out[p] = {shift1, bits1, shift2, bits2}, digit = ((key >> shift1) & mask1) | (((key >> shift2) & mask2) << bits1). No engine, no
+// device: the plan is host logic (tests pin that every significant bit is sorted exactly once, in order, in the fewest passes).
+int gysk_sort_plan(uint32_t value_bits, uint32_t nslots, int32_t out[8][4], uint32_t *npasses)
+{
+	if (!out || !npasses || value_bits < 1 || value_bits > (uint32_t)VALUE_BITS) return GYSK_ERR_INVAL;
+	uint32_t slot_bits = 1;
+	while (slot_bits < 32 && (1ull << slot_bits) < nslots) slot_bits++;
+	if (slot_bits > 64 - (uint32_t)KEY_SLOT_SHIFT) return GYSK_ERR_INVAL;
+	int plan[8][4];
+	const int np = radix_sort_plan(KEY_VALUE_SHIFT, KEY_VALUE_SHIFT + (int)value_bits, KEY_SLOT_SHIFT, KEY_SLOT_SHIFT + (int)slot_bits, plan, 8);
+	if (np < 0) return GYSK_ERR_INVAL;
+	for (int p = 0; p < np && p < 8; ++p) for (int k = 0; k < 4; ++k) out[p][k] = plan[p][k];
+	*npasses = (uint32_t)np;
+	return GYSK_OK;
+}
+
 int gysk_export_cms(gysk_engine *e, int last_window, uint64_t *cells)
 {
 	CHECK_ENGINE(e);

@@ -1271,6 +1271,15 @@ static int build_digit_specs(int lo1, int hi1, int lo2, int hi2, DigitSpecs &P)
 	return (p1 < hi1 || p2 < hi2) ? -1 : 0;		// more than 64 significant bits cannot happen
 }
 
+// host-side view of the pass plan (C ABI: gysk_sort_plan): per pass {shift1, bits1, shift2, bits2}
+int radix_sort_plan(int lo1, int hi1, int lo2, int hi2, int out[][4], int cap)
+{
+	DigitSpecs P;
+	if (build_digit_specs(lo1, hi1, lo2, hi2, P)) return -1;
+	for (int p = 0; p < P.np && p < cap; ++p) { out[p][0] = P.d[p].s1; out[p][1] = P.d[p].b1; out[p][2] = P.d[p].s2; out[p][3] = P.d[p].b2; }
+	return P.np;
+}
+
 int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, int lo2, int hi2, int *which, cudaStream_t s)
 {
 	int launches = 0;

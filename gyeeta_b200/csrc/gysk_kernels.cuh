@@ -88,6 +88,7 @@ int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_
 int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s);
 int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t nkeys, uint32_t nslots, int value_bits, cudaStream_t s);	// < 0: too many keys for one batch
 int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, int lo2, int hi2, int *which, cudaStream_t s);
+int radix_sort_plan(int lo1, int hi1, int lo2, int hi2, int out[][4], int cap);
 int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int metric, int host_filter, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
 int launch_topn_tasks(const DevState &st, const SortTemp &tmp, uint32_t ntasks, int metric, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
 int launch_task_flush(const DevState &st, uint32_t max_tasks, cudaStream_t s);

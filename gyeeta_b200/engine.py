@@ -116,6 +116,7 @@ def load_library(path=None):
         "gysk_export_tdigest": (i32, [vp, u64, vp, vp, u32, vp, vp, vp]),
         "gysk_query_quantiles": (i32, [vp, u64, vp, u32, vp]),
         "gysk_tdigest_to_pgtext": (i32, [vp, vp, u32, u32, vp, u32]),
+        "gysk_sort_plan": (i32, [u32, u32, vp, vp]),
         "gysk_encode_listener_state": (i32, [vp, u32, vp, u32, vp, vp]),
         "gysk_export_tdigest_pgtext": (i32, [vp, u64, vp, u32]),
         "gysk_export_cms": (i32, [vp, i32, vp]),

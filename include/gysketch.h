@@ -310,6 +310,10 @@ double		gysk_hll_estimate(const uint8_t *regs, uint32_t p);
  * NOTIFY_LISTENER_STATE message (<= 512 records, 88 bytes each) that MTCP_LISTENER::set_state / partha_listener_state consume
  * (server/gy_mconnhdlr.cc:11175-11251). Entries with found == 0 are skipped. No engine needed. */
 int		gysk_encode_listener_state(const gysk_svc_summary *sums, uint32_t n, void *buf, uint32_t cap, uint32_t *nrecs, uint32_t *nbytes);
+/* introspection: the stable LSD radix passes over the RESP sort keys {slot | usec | port} for a batch whose largest response
+ * time has value_bits significant usec bits and whose engine has handed out nslots service slots. out[p] = {shift1, bits1,
+ * shift2, bits2}: the pass's digit is ((key >> shift1) & ((1 << bits1) - 1)) | (((key >> shift2) & ((1 << bits2) - 1)) << bits1). */
+int		gysk_sort_plan(uint32_t value_bits, uint32_t nslots, int32_t out[8][4], uint32_t *npasses);
 /* a digest in the text form of the Postgres `tdigest` type the reference stores and queries (public.tdigest(expr, 100) /
  * tdigest_percentile, common/gy_query_common.cc:1805-1858): "flags 1 count N compression C centroids K (mean, count) ...".
  * Both return the string length, or a negative GYSK_ERR_* */

@@ -174,3 +174,34 @@ def test_tdigest_pgtext_form():
     assert [float(a) for a, _ in pairs] == list(means) and [int(b) for _, b in pairs] == list(weights)
     small = C.create_string_buffer(40)
     assert L.gysk_tdigest_to_pgtext(means.ctypes.data_as(C.c_void_p), weights.ctypes.data_as(C.c_void_p), 4, 100, small, len(small)) == -28
+
+
+def test_radix_pass_plan_covers_every_significant_bit_once():
+    """host logic of the one-sweep sort: for every (usec bits, slots) shape the passes sort bits 5.. of the usec field and then
+    the slot field (from bit 35), each significant bit exactly once and in ascending order; the port bits (0-4) and the unused
+    bits in between never cost a pass; digits are 8 bits wide except where 9-bit digits save a whole pass (41-45 bits)."""
+    import ctypes as C
+    from gyeeta_b200 import engine as ge
+    L = ge.load_library()
+    for vb in range(1, 31):
+        for nslots in (1, 2, 100, 1024, 100_000, 1 << 20, 1 << 24):
+            plan = (C.c_int32 * 4 * 8)()
+            npass = C.c_uint32()
+            assert L.gysk_sort_plan(vb, nslots, plan, C.byref(npass)) == 0
+            sb = max(1, int(nslots - 1).bit_length())
+            want = [5 + i for i in range(vb)] + [35 + i for i in range(sb)]
+            got = []
+            for p in range(npass.value):
+                s1, b1, s2, b2 = plan[p]
+                assert 1 <= b1 + b2 <= 9 and b1 >= 1
+                got += [s1 + i for i in range(b1)] + [s2 + i for i in range(b2)]
+            assert got == want, (vb, nslots, got)
+            T = vb + sb
+            assert npass.value == min(-(-T // 8), -(-T // 9) if -(-T // 9) < -(-T // 8) else -(-T // 8))
+            assert npass.value == (-(-T // 9) if -(-T // 9) < -(-T // 8) else -(-T // 8))
+    plan = (C.c_int32 * 4 * 8)(); npass = C.c_uint32()
+    assert L.gysk_sort_plan(24, 100_000, plan, C.byref(npass)) == 0 and npass.value == 5      # 41 bits: one 9-bit digit, not 6 passes
+    assert sorted(plan[p][1] + plan[p][3] for p in range(5)) == [8, 8, 8, 8, 9]
+    assert L.gysk_sort_plan(23, 100_000, plan, C.byref(npass)) == 0 and npass.value == 5      # the bench stream: 40 bits
+    assert all(plan[p][1] + plan[p][3] == 8 for p in range(5))
+    assert L.gysk_sort_plan(0, 10, plan, C.byref(npass)) == -22
