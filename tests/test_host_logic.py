@@ -205,3 +205,43 @@ def test_radix_pass_plan_covers_every_significant_bit_once():
     assert L.gysk_sort_plan(23, 100_000, plan, C.byref(npass)) == 0 and npass.value == 5      # the bench stream: 40 bits
     assert all(plan[p][1] + plan[p][3] == 8 for p in range(5))
     assert L.gysk_sort_plan(0, 10, plan, C.byref(npass)) == -22
+
+
+def test_listener_state_encoder_fields_and_limits():
+    """gysk_encode_listener_state is pure host code: field mapping into LISTENER_STATE_NOTIFY (88-byte records, 8-byte aligned, no
+    issue string), unknown ids skipped, 32-bit clamps, the 512-records-per-message cap (gy_comm_proto.h:2222) and ENOSPC"""
+    import ctypes as C
+    from gyeeta_b200 import engine as ge
+    L = ge.load_library()
+    LSN = np.dtype([("glob_id", "<u8"), ("nqrys_5s", "<u4"), ("total_resp_5sec", "<u4"), ("nconns", "<u4"), ("nconns_active", "<u4"),
+                    ("ntasks", "<u4"), ("p95_5s", "<u4"), ("p95_5min", "<u4"), ("kb_in", "<u4"), ("kb_out", "<u4"), ("ser_errors", "<u4"),
+                    ("cli_errors", "<u4"), ("t", "<u4", 6), ("ntasks_issue", "<u2"), ("is_http", "u1"), ("curr_state", "u1"),
+                    ("curr_issue", "u1"), ("issue_bit_hist", "u1"), ("high_resp_bit_hist", "u1"), ("last_issue_subsrc", "u1"),
+                    ("query_flags", "u1"), ("issue_string_len", "u1"), ("padding_len", "u1"), ("pad", "u1")])
+    assert LSN.itemsize == 88
+    n = 600
+    sums = (ge.SvcSummary * n)()
+    for i in range(n):
+        sums[i].glob_id = 1000 + i
+        sums[i].found = 0 if i % 7 == 3 else 1
+        sums[i].nqrys_5s = 0 if i % 5 == 0 else 10 * i
+        sums[i].total_resp_5sec = (1 << 40) if i == 1 else 3 * i
+        sums[i].p95_5s_resp_ms = -1 if i == 2 else 30
+        sums[i].p95_5min_resp_ms = 60
+        sums[i].nconns_5s = i
+        sums[i].kbytes_5s = 2 * i
+    buf = C.create_string_buffer(88 * 512)
+    nrecs, nbytes = C.c_uint32(), C.c_uint32()
+    assert L.gysk_encode_listener_state(sums, n, buf, len(buf), C.byref(nrecs), C.byref(nbytes)) == 0
+    assert nrecs.value == 512 and nbytes.value == 88 * 512                       # one message holds 512 records
+    recs = np.frombuffer(buf.raw[: nbytes.value], dtype=LSN)
+    found_ids = [1000 + i for i in range(n) if i % 7 != 3][:512]
+    assert list(recs["glob_id"]) == found_ids
+    by = {int(r["glob_id"]): r for r in recs}
+    assert by[1001]["total_resp_5sec"] == 0xFFFFFFFF and by[1002]["p95_5s"] == 0     # clamps
+    r = by[1011]
+    assert (r["nqrys_5s"], r["total_resp_5sec"], r["p95_5s"], r["p95_5min"], r["nconns"], r["kb_in"]) == (110, 33, 30, 60, 11, 22)
+    assert r["curr_state"] == 2 and by[1005]["curr_state"] == 0                 # STATE_OK with queries, STATE_IDLE without
+    assert r["issue_string_len"] == 0 and r["padding_len"] == 0
+    small = C.create_string_buffer(88 * 3)
+    assert L.gysk_encode_listener_state(sums, n, small, len(small), C.byref(nrecs), C.byref(nbytes)) == -28
