@@ -245,3 +245,29 @@ def test_listener_state_encoder_fields_and_limits():
     assert r["issue_string_len"] == 0 and r["padding_len"] == 0
     small = C.create_string_buffer(88 * 3)
     assert L.gysk_encode_listener_state(sums, n, small, len(small), C.byref(nrecs), C.byref(nbytes)) == -28
+
+
+def test_radix_pass_plan_sorts_keys_when_passes_are_stable():
+    """the plan of gysk_sort_plan, executed with numpy's stable argsort as the pass: keys {slot | usec | port} come out ordered by
+    (slot, usec) with ties in input order — for 8-bit plans, the 9-bit plan (41 bits) and a digit that straddles the field gap"""
+    import ctypes as C
+    from gyeeta_b200 import engine as ge
+    L = ge.load_library()
+    rng = np.random.default_rng(5)
+    for vb, nslots in ((23, 100_000), (24, 100_000), (30, 1500), (7, 3), (13, 1 << 20)):
+        plan = (C.c_int32 * 4 * 8)(); npass = C.c_uint32()
+        assert L.gysk_sort_plan(vb, nslots, plan, C.byref(npass)) == 0
+        n = 50_000
+        slot = rng.integers(0, nslots, n, dtype=np.uint64)
+        usec = rng.integers(0, 1 << vb, n, dtype=np.uint64)
+        port = rng.integers(0, 32, n, dtype=np.uint64)
+        keys = (slot << np.uint64(35)) | (usec << np.uint64(5)) | port
+        order = np.arange(n)
+        cur = keys.copy()
+        for p in range(npass.value):
+            s1, b1, s2, b2 = (int(x) for x in plan[p])
+            digit = ((cur >> np.uint64(s1)) & np.uint64((1 << b1) - 1)) | (((cur >> np.uint64(s2)) & np.uint64((1 << b2) - 1)) << np.uint64(b1))
+            perm = np.argsort(digit, kind="stable")
+            cur, order = cur[perm], order[perm]
+        want = np.lexsort((np.arange(n), usec, slot))             # by slot, then usec, then input order
+        assert np.array_equal(order, want), (vb, nslots)
