@@ -23,7 +23,7 @@ struct alignas(16) TblEntry { unsigned long long key; uint32_t slot1; uint32_t p
 static constexpr uint32_t SLOT_INVALID = 0xFFFFFFFFu;
 
 struct Centroid { double mean; unsigned long long weight; };
-static constexpr int TD_CAP = 128;
+static constexpr int TD_CAP = 256;		// delta = 200 yields 200 ... 1.3 x 200 centroids
 
 // per-service t-digest header
 struct TdHead { unsigned long long total; double minv, maxv; uint32_t n; uint32_t pad; };
@@ -38,11 +38,12 @@ struct IdTable
 	uint32_t	*slot_host;	// optional: slot -> host index of the inserting event
 	int32_t		*free_n;	// optional: number of recycled slots on the stack (pushed by the eviction kernel at a flush,
 	uint32_t	*free_slots;	//           popped here; the two never run concurrently: same stream)
+	unsigned long long *insert_fail;	// optional: entries left dead by a lost race for the last slot
 };
 static constexpr unsigned long long KEY_TOMBSTONE = ~0ull;	// table entry of an evicted id: never matches, never ends a probe chain
 
 // device counters (index into Engine::d_counters)
-enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_MAXVAL, CTR_NTOUCHED, CTR_NEVICT, CTR_EVICTED_TOTAL, CTR_MAX = 16 };	// NKEYS, MAXVAL adjacent: reset / read together
+enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_INSERT_FAIL, CTR_NTOUCHED, CTR_NEVICT, CTR_EVICTED_TOTAL, CTR_MAX = 16 };
 
 // ---------------------------------------------------------------------------------------------------
 // jhash: Bob Jenkins lookup2 in the form the reference uses (common/jhash.h:22-35,121-134); seed 0xceedfead
@@ -50,8 +51,8 @@ enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NK
 // ---------------------------------------------------------------------------------------------------
 static constexpr uint32_t JHASH_GOLDEN = 0x9e3779b9u;
 static constexpr uint32_t GY_SEED = 0xceedfeadu;
-static constexpr uint32_t HLL_SEED_A = GY_SEED ^ 0xa5a5a5a5u;
-static constexpr uint32_t HLL_SEED_B = GY_SEED ^ 0x5a5a5a5au;
+static constexpr uint32_t FLOW_SEED_A = GY_SEED;
+static constexpr uint32_t FLOW_SEED_B = GY_SEED ^ 0x5bd1e995u;
 
 __host__ __device__ __forceinline__ uint32_t jhash_2words(uint32_t a, uint32_t b, uint32_t initval)
 {
@@ -75,9 +76,33 @@ __host__ __device__ __forceinline__ uint32_t uint64_hash(unsigned long long key)
 	return jhash_2words((uint32_t)(key & 0xFFFFFFFFu), (uint32_t)(key >> 32), GY_SEED);
 }
 
+// Internal index of the id tables. Which entry an id lands in is not observable in any output (slot numbers follow insertion
+// order, not the hash), so the table does not pay the reference's 36-instruction lookup2 per event: Fibonacci hashing, one
+// 64-bit multiply. The ids themselves are CityHash outputs in the reference (common/gy_socket_stat.cc:1824).
+__host__ __device__ __forceinline__ uint32_t table_hash(unsigned long long key)
+{
+	return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32);
+}
+
+// Two lookup2 words per flow key serve every sketch row (Kirsch-Mitzenmacher double hashing): count-min row r indexes
+// (h1 + r * (h2 | 1)) & wmask, HyperLogLog takes the 64-bit word h2:h1. Definition shared with oracle/gysk_oracle.c.
+__host__ __device__ __forceinline__ void flow_hashes(unsigned long long key, uint32_t &h1, uint32_t &h2)
+{
+	const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+	h1 = jhash_2words(lo, hi, FLOW_SEED_A);
+	h2 = jhash_2words(lo, hi, FLOW_SEED_B);
+}
+
+__host__ __device__ __forceinline__ uint32_t cms_index2(uint32_t h1, uint32_t h2, uint32_t row, uint32_t wmask)
+{
+	return (h1 + row * (h2 | 1u)) & wmask;
+}
+
 __host__ __device__ __forceinline__ uint32_t cms_index(unsigned long long key, uint32_t row, uint32_t wmask)
 {
-	return jhash_2words((uint32_t)key, (uint32_t)(key >> 32), GY_SEED + JHASH_GOLDEN * (row + 1)) & wmask;
+	uint32_t h1, h2;
+	flow_hashes(key, h1, h2);
+	return cms_index2(h1, h2, row, wmask);
 }
 
 __host__ __device__ __forceinline__ unsigned long long cms_increment(uint32_t bytes)
@@ -85,15 +110,32 @@ __host__ __device__ __forceinline__ unsigned long long cms_increment(uint32_t by
 	return 1ull | ((unsigned long long)(bytes >> 10) << 32);
 }
 
-__device__ __forceinline__ void hll_idx_rank(unsigned long long key, uint32_t p, uint32_t &idx, uint32_t &rank)
+__device__ __forceinline__ void hll_idx_rank2(uint32_t h1, uint32_t h2, uint32_t p, uint32_t &idx, uint32_t &rank)
 {
-	const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
-	const unsigned long long h = ((unsigned long long)jhash_2words(lo, hi, HLL_SEED_A) << 32) | jhash_2words(lo, hi, HLL_SEED_B);
+	const unsigned long long h = ((unsigned long long)h2 << 32) | h1;
 	const unsigned long long w = h << p;
 
 	idx = (uint32_t)(h >> (64 - p));
 	rank = w ? (uint32_t)__clzll((long long)w) + 1u : (64u - p + 1u);
 }
+
+// Log-linear value code of a response time: 32 bins per octave, exact below 32, monotone, < 1024 for usec < 2^30. The RESP
+// keys are sorted by (slot, code) only: 10 value bits instead of 30.
+static constexpr int TD_CODE_BITS = 10;
+__host__ __device__ __forceinline__ uint32_t td_code(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+	if (v < 32u) return v;
+	const uint32_t sh = (31u - (uint32_t)__clz((int)v)) - 5u;
+#else
+	if (v < 32u) return v;
+	const uint32_t sh = (31u - (uint32_t)__builtin_clz(v)) - 5u;
+#endif
+	return ((sh + 1u) << 5) | ((v >> sh) & 31u);
+}
+// smallest / largest value carrying a code
+__host__ __device__ __forceinline__ uint32_t td_code_lo(uint32_t c) { return c < 32u ? c : ((32u | (c & 31u)) << ((c >> 5) - 1u)); }
+__host__ __device__ __forceinline__ uint32_t td_code_hi(uint32_t c) { return c < 32u ? c : (((32u | (c & 31u)) + 1u) << ((c >> 5) - 1u)) - 1u; }
 
 // ---------------------------------------------------------------------------------------------------
 // bucket hashes (common/gy_statistics.h:1674-2063): bucket = 0 below min, nthr+1 at/after max_value,
@@ -170,7 +212,7 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v)
 // (the 16-byte entry load is the latency that matters; hash collisions and inserts are the rare continuation).
 __device__ __forceinline__ uint4 table_probe_first(const IdTable &t, unsigned long long key, uint32_t &pos)
 {
-	pos = uint64_hash(key) & t.mask;
+	pos = table_hash(key) & t.mask;
 	return ld_cg_v4(&t.ent[pos]);
 }
 
@@ -183,6 +225,9 @@ __device__ __forceinline__ int table_resolve_slow(const IdTable &t, unsigned lon
 
 		if (k == 0) {
 			if (!insert) return -1;
+			// no slot left (nothing on the free stack, every fresh one handed out): give up BEFORE claiming the entry, so a
+			// full engine does not fill its table with dead keys (unknown ids keep arriving: one per netns/ip/port on the raw path)
+			if ((!t.free_n || *((volatile int32_t *)t.free_n) <= 0) && *((volatile uint32_t *)t.count) >= t.max_slots) return -1;
 			k = atomicCAS(&e->key, 0ull, key);
 			if (k == 0) {
 				// a slot recycled by an eviction first, else the next fresh one
@@ -195,8 +240,11 @@ __device__ __forceinline__ int table_resolve_slow(const IdTable &t, unsigned lon
 				if (s == SLOT_INVALID) {
 					s = atomicAdd(t.count, 1u);
 					if (s >= t.max_slots) {
+						// lost the race for the last slots after the check above: the entry stays dead until the next table
+						// rebuild, which gysk_flush triggers from this counter
 						atomicSub(t.count, 1u);
 						st_volatile_u32(&e->slot1, SLOT_INVALID);
+						if (t.insert_fail) atomicAdd(t.insert_fail, 1ull);
 						return -1;
 					}
 				}

@@ -62,24 +62,17 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n, Aft
 		e->prof_used += 3;
 		CU(e, cudaEventRecord(pe[0], e->stream));
 	}
-	e->kernel_launches += launch_ingest(e->st, d_ev, n, e->tmp.keys_a, e->stream);
+	e->kernel_launches += launch_ingest(e->st, e->tmp, d_ev, n, e->cfg.max_svcs, e->stream);
 	if (pe) CU(e, cudaEventRecord(pe[1], e->stream));
 	// the events of this batch are consumed once the ingest kernel has run: callers release / refill the event buffer here,
-	// so that the next H2D copy overlaps the readback below and the whole sort + t-digest chain
+	// so that the next H2D copy overlaps the whole sort + t-digest chain
 	{ int rc_ai = after_ingest(); if (rc_ai) return rc_ai; }
-	// the sort is sized by what the batch actually holds: number of RESP keys, bits of the largest response time, slots in
-	// use — three words read back here (one stream sync per device batch; the kernels of the batch stay back to back)
-	CU(e, cudaMemcpyAsync(e->h_counters, e->st.counters + CTR_NKEYS, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
-	CU(e, cudaMemcpyAsync(e->h_counters + 2, e->st.svc_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
-	CU(e, cudaStreamSynchronize(e->stream));
+	// No number travels back to the host between ingest and sort: the key count stays in device memory (the passes read it
+	// there, grids are sized for n keys and surplus CTAs leave at once), the digit histograms were counted by the ingest
+	// kernel, the digits cover every slot the engine could hand out. A batch is one uninterrupted run of launches.
 	{
-		const uint64_t nkeys = e->h_counters[0];
-		const uint64_t max_us = std::min<uint64_t>(e->h_counters[1] * 1000ull + 999ull, (1ull << VALUE_BITS) - 1);	// msec maximum -> usec bound
-		const uint32_t nslots = std::min<uint32_t>((uint32_t)e->h_counters[2], e->cfg.max_svcs);
-		int value_bits = 1;
-		while (value_bits < VALUE_BITS && (1ull << value_bits) <= max_us) value_bits++;
-		const int nl = launch_tdigest_update(e->st, e->tmp, nkeys, nslots, value_bits, e->stream);
-		if (nl < 0) return fail(e, GYSK_ERR_INVAL, "device batch holds 2^30 or more RESP keys");
+		const int nl = launch_tdigest_update(e->st, e->tmp, n, e->cfg.max_svcs, e->stream);
+		if (nl < 0) return fail(e, GYSK_ERR_INVAL, "device batch holds 2^30 or more events");
 		e->kernel_launches += nl;
 	}
 	if (pe) CU(e, cudaEventRecord(pe[2], e->stream));
@@ -101,6 +94,7 @@ int gysk::collect_evicted(gysk_engine *e, bool wait)
 	if (wait) CU(e, cudaEventSynchronize(e->ev_evict));
 	else if (cudaEventQuery(e->ev_evict) != cudaSuccess) { cudaGetLastError(); CU(e, cudaEventSynchronize(e->ev_evict)); }
 	const uint64_t cnt = std::min<uint64_t>(e->h_evict[0], e->cfg.max_svcs);
+	e->h_evict_fail = e->h_evict[e->cfg.max_svcs + 1];
 	e->evicted_ids.assign(e->h_evict + 1, e->h_evict + 1 + cnt);
 	e->tombstones += cnt; e->evicted_total += cnt;
 	e->evict_pending = false;
@@ -328,7 +322,7 @@ void gysk_config_default(gysk_config *cfg)
 	cfg->cms_depth = 4;
 	cfg->cms_log2_width = 20;
 	cfg->hll_p = 12;
-	cfg->td_compression = 100;
+	cfg->td_compression = 200;
 	cfg->max_batch = 1u << 22;
 	cfg->stage_batch = 0;
 	cfg->flags = GYSK_FLAG_AUTO_REGISTER;
@@ -374,7 +368,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	if (!cfg.stage_batch || cfg.stage_batch > cfg.max_batch) cfg.stage_batch = std::min<uint32_t>(cfg.max_batch, 1u << 22);
 	if (cfg.max_svcs < 1 || cfg.max_svcs > (1u << 24) || cfg.max_tasks < 1 || cfg.max_tasks > (1u << 24) || cfg.cms_depth < 1 ||
 			cfg.cms_depth > 8 || cfg.cms_log2_width < 4 || cfg.cms_log2_width > 28 || cfg.hll_p < 4 || cfg.hll_p > 16 ||
-			cfg.td_compression < 10 || cfg.td_compression > 120 || cfg.max_batch < 1024 || cfg.max_batch > (1u << 28) ||
+			cfg.td_compression < 10 || cfg.td_compression > 220 || cfg.max_batch < 1024 || cfg.max_batch > (1u << 28) ||
 			cfg.rank >= cfg.world)
 		return fail(nullptr, GYSK_ERR_INVAL, "gysk_config out of range");
 
@@ -406,6 +400,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	const uint32_t scap = pow2_at_least((uint64_t)ns * 2), tcap = pow2_at_least((uint64_t)nt * 2);
 
 #define A(call) do { if ((rc = (call)) != 0) return bail(rc); } while (0)
+	A(dalloc(e, &st.counters, (size_t)CTR_MAX));
 	A(dalloc(e, &st.svc_tbl.ent, scap)); st.svc_tbl.mask = scap - 1; st.svc_tbl.max_slots = cfg.max_svcs;
 	A(dalloc(e, &st.svc_tbl.count, 1));
 	A(dalloc(e, &st.slot_id, ns)); A(dalloc(e, &st.slot_host, ns));
@@ -413,7 +408,8 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(dalloc(e, &st.slot_first_seen, ns)); A(dalloc(e, &st.slot_last_active, ns));
 	A(dalloc(e, &st.evict_list, ns)); A(dalloc(e, &st.evict_ids, ns));
 	A(dalloc(e, &st.svc_tbl.free_n, 1)); A(dalloc(e, &st.svc_tbl.free_slots, ns));
-	A(halloc(e, &e->h_evict, ns + 1));
+	A(halloc(e, &e->h_evict, ns + 2));
+	e->h_evict[0] = 0; e->h_evict[cfg.max_svcs + 1] = 0;
 	if ((ce = cudaEventCreateWithFlags(&e->ev_evict, cudaEventDisableTiming)) != cudaSuccess) { fail(e, GYSK_ERR_CUDA, "cudaEventCreate", ce); return bail(GYSK_ERR_CUDA); }
 	A(dalloc(e, &st.task_tbl.ent, tcap)); st.task_tbl.mask = tcap - 1; st.task_tbl.max_slots = cfg.max_tasks;
 	A(dalloc(e, &st.task_tbl.count, 1));
@@ -428,17 +424,28 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(dalloc(e, &st.task_slot_id, nt)); A(dalloc(e, &st.task_slot_host, nt));
 	st.task_tbl.slot_id = st.task_slot_id; st.task_tbl.slot_host = st.task_slot_host;
 	A(dalloc(e, &st.cms_cur, (size_t)cfg.cms_depth << cfg.cms_log2_width)); A(dalloc(e, &st.cms_last, (size_t)cfg.cms_depth << cfg.cms_log2_width));
-	A(dalloc(e, &st.counters, (size_t)CTR_MAX));
 	st.cms_depth = cfg.cms_depth; st.cms_log2w = cfg.cms_log2_width; st.cms_wmask = (1u << cfg.cms_log2_width) - 1; st.hll_p = cfg.hll_p;
 	st.rank = cfg.rank; st.world = cfg.world; st.auto_register = (cfg.flags & GYSK_FLAG_AUTO_REGISTER) ? 1 : 0;
 	st.td_delta = (double)cfg.td_compression;
-	st.td.C = cos(M_PI / st.td_delta); st.td.S = sin(M_PI / st.td_delta); st.td.qclamp = (1.0 + st.td.C) / 2.0;
+	{
+		// coarser rungs for greedy passes that would not fit TD_CAP clusters (same table in oracle/gysk_oracle.c)
+		static const double ladder[TD_LADDER] = { 1.0, 0.92, 0.85, 0.78, 0.72, 0.66 };
+		for (int k = 0; k < TD_LADDER; ++k) {
+			const double d = st.td_delta * ladder[k];
+			st.td.r[k].C = cos(M_PI / d); st.td.r[k].S = sin(M_PI / d); st.td.r[k].qclamp = (1.0 + st.td.r[k].C) / 2.0;
+		}
+	}
 
 	SortTemp &tmp = e->tmp;
 	tmp.max_tiles = (cfg.max_batch + SORT_TILE - 1) / SORT_TILE;
 	A(dalloc(e, &tmp.keys_a, (size_t)cfg.max_batch, false)); A(dalloc(e, &tmp.keys_b, (size_t)cfg.max_batch, false));
-	A(dalloc(e, &tmp.tile_status, (size_t)512 * tmp.max_tiles));
-	A(dalloc(e, &tmp.os_ghist, (size_t)8 * 512 + 8));
+	A(dalloc(e, &tmp.tile_status, (size_t)RADIX_MAX * tmp.max_tiles));
+	tmp.epoch = &e->sort_epoch;
+	A(dalloc(e, &tmp.os_ghist, (size_t)8 * RADIX_MAX + 8));
+	A(dalloc(e, &tmp.runbits, ((size_t)cfg.max_batch >> 5) + 64)); A(dalloc(e, &tmp.runbits2, ((size_t)cfg.max_batch >> 15) + 2));
+	A(dalloc(e, &tmp.bminmax, ns));
+	A(dalloc(e, &tmp.newc_scratch, (size_t)TD_MERGE_MAX_SMS * TD_MERGE_CTAS_PER_SM * 4 * TD_CAP));
+	st.svc_tbl.insert_fail = st.counters + CTR_INSERT_FAIL; st.task_tbl.insert_fail = nullptr;
 	A(dalloc(e, &tmp.seg_start, ns)); A(dalloc(e, &tmp.seg_end, ns)); A(dalloc(e, &tmp.touched, ns));
 	A(dalloc(e, &tmp.plan_bounds, ns * (TD_CAP + 1))); A(dalloc(e, &tmp.plan_n, ns)); A(dalloc(e, &tmp.newsum, ns * TD_CAP));
 
@@ -617,10 +624,12 @@ int gysk_ingest_raw(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx
 			if (tresp > 1000000u) continue;
 			gysk_event *o = stage_slot(e, &rc);
 			if (!o) return rc;
-			const uint32_t words[3] = { p[i].saddr, p[i].netns, p[i].sport };
+			// inet_sport / skc_dport are in network byte order: ntohs() first, as the reference does (gy_socket_stat.cc:1526-1527)
+			const uint32_t sport = __builtin_bswap16(p[i].sport), dport = __builtin_bswap16(p[i].dport);
+			const uint32_t words[3] = { p[i].saddr, p[i].netns, sport };
 			o->svc_id = ((uint64_t)jhash_2words(words[0], words[1], GY_SEED) << 32) | jhash_2words(words[2], words[1], GY_SEED ^ words[0]);
 			if (!o->svc_id) o->svc_id = 1;
-			o->flow_key = ((uint64_t)p[i].daddr << 32) | p[i].dport;
+			o->flow_key = ((uint64_t)p[i].daddr << 32) | dport;		// CONN_BITMAP index = client port & 0x1F (gy_socket_stat.h:403-410)
 			o->value = tresp * 1000u; o->host_idx = host_idx; o->tsec = 0; o->type = GYSK_EV_RESP; o->flags = 0;
 		}
 		return GYSK_OK;
@@ -635,8 +644,9 @@ int gysk_ingest_raw(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx
 			gysk_event *o = stage_slot(e, &rc);
 			if (!o) return rc;
 			const bool ser_side = (p[i].type == GYSK_EV_ACCEPT || p[i].type == GYSK_EV_CLOSE_SER);
-			const uint32_t sip = ser_side ? p[i].saddr : p[i].daddr, sport = ser_side ? p[i].sport : p[i].dport;
-			const uint32_t cip = ser_side ? p[i].daddr : p[i].saddr, cport = ser_side ? p[i].dport : p[i].sport;
+			const uint32_t hs = __builtin_bswap16(p[i].sport), hd = __builtin_bswap16(p[i].dport);	// ntohs, gy_socket_stat.cc:258-262
+			const uint32_t sip = ser_side ? p[i].saddr : p[i].daddr, sport = ser_side ? hs : hd;
+			const uint32_t cip = ser_side ? p[i].daddr : p[i].saddr, cport = ser_side ? hd : hs;
 			o->svc_id = ((uint64_t)jhash_2words(sip, p[i].netns, GY_SEED) << 32) | jhash_2words(sport, p[i].netns, GY_SEED ^ sip);
 			if (!o->svc_id) o->svc_id = 1;
 			o->flow_key = ((uint64_t)cip << 32) | cport;
@@ -727,7 +737,10 @@ int gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, ui
 		gysk_host_summary hs;
 		memset(&hs, 0, sizeof(hs));
 		for (uint32_t i = 0; i < nevents && (const uint8_t *)pone < pend; ++i, pone = (T *)((uint8_t *)pone + pone->get_elem_size())) {
-			if (pone->curr_state_ < 8) hs.nstates[pone->curr_state_]++;
+			// gy_mconnhdlr.cc:11183-11251: LISTEN_FLAG_DELETE records only delete the listener, records with
+			// curr_state_ > STATE_DOWN count as errors; neither reaches summstats.update()
+			if (pone->query_flags_ == wire::LISTEN_FLAG_DELETE || pone->curr_state_ > wire::STATE_DOWN) continue;
+			hs.nstates[pone->curr_state_]++;
 			hs.tot_qps += (int32_t)(pone->nqrys_5s_ / 5);
 			hs.tot_act_conn += (int32_t)pone->nconns_active_;
 			hs.tot_kb_inbound += (int32_t)pone->curr_kbytes_inbound_;
@@ -798,15 +811,17 @@ int gysk_flush(gysk_engine *e, uint32_t tsec)
 
 	if ((rc = collect_evicted(e, false))) return rc;		// list of the previous flush (normally long complete)
 	// tombstones lengthen probe chains: once they fill an eighth of the table, rebuild it from the live slots
-	if (e->tombstones > ((uint64_t)e->st.svc_tbl.mask + 1) / 8) {
+	const uint64_t dead = e->h_evict_fail > e->insert_fail_seen ? e->h_evict_fail - e->insert_fail_seen : 0;
+	if (e->tombstones + dead > ((uint64_t)e->st.svc_tbl.mask + 1) / 8) {
 		e->kernel_launches += launch_rebuild_table(e->st, e->cfg.max_svcs, e->stream);
-		e->tombstones = 0;
+		e->tombstones = 0; e->insert_fail_seen = e->h_evict_fail;
 	}
 	e->kernel_launches += launch_flush(e->st, e->cfg.max_svcs, planes[0], planes[1], tsec, e->cfg.idle_evict_secs, e->stream);
 	e->kernel_launches += launch_task_flush(e->st, e->cfg.max_tasks, e->stream);
 	if (e->cfg.idle_evict_secs) {
 		// count + ids travel to the host behind the kernels; nobody waits for them here
 		CU(e, cudaMemcpyAsync(e->h_evict, e->st.counters + CTR_NEVICT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+		CU(e, cudaMemcpyAsync(e->h_evict + e->cfg.max_svcs + 1, e->st.counters + CTR_INSERT_FAIL, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
 		CU(e, cudaMemcpyAsync(e->h_evict + 1, e->st.evict_ids, (size_t)e->cfg.max_svcs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
 		CU(e, cudaEventRecord(e->ev_evict, e->stream));
 		e->evict_pending = true;
@@ -1005,14 +1020,44 @@ int gysk_tdigest_to_pgtext(const double *means, const uint64_t *weights, uint32_
 	return off;
 }
 
+// The engine keeps delta = 200 internally; the Postgres side of the reference aggregates with public.tdigest(expr, 100)
+// (common/gy_query_common.cc:1855) and the extension refuses to combine digests of different compression, so the export is one
+// more greedy K_1 pass at compression 100 (host side, same rule as the device: a cluster that starts after weight P takes items
+// while the running total stays <= W q(k(P/W) + 1)).
+static uint32_t host_td_compress(const double *means, const uint64_t *w, uint32_t n, double delta, double *om, uint64_t *ow)
+{
+	if (!n) return 0;
+	const double C = cos(M_PI / delta), S = sin(M_PI / delta), qclamp = (1.0 + C) / 2.0;
+	uint64_t W = 0, wsofar = 0, cw = w[0];
+	for (uint32_t i = 0; i < n; ++i) W += w[i];
+	auto wlimit = [&](uint64_t sofar) {
+		const double q0 = sofar ? (double)sofar / (double)W : 0.0;
+		if (q0 >= qclamp) return (double)W;
+		return (double)W * ((((2.0 * q0 - 1.0) * C + 2.0 * sqrt(q0 * (1.0 - q0)) * S) + 1.0) * 0.5);
+	};
+	double csum = means[0] * (double)w[0], wl = wlimit(0);
+	uint32_t nout = 0;
+	for (uint32_t i = 1; i < n; ++i) {
+		if ((double)(wsofar + cw + w[i]) <= wl) { cw += w[i]; csum += means[i] * (double)w[i]; }
+		else {
+			om[nout] = csum / (double)cw; ow[nout++] = cw;
+			wsofar += cw; wl = wlimit(wsofar);
+			cw = w[i]; csum = means[i] * (double)w[i];
+		}
+	}
+	om[nout] = csum / (double)cw; ow[nout++] = cw;
+	return nout;
+}
+
 int gysk_export_tdigest_pgtext(gysk_engine *e, uint64_t id, char *buf, uint32_t cap)
 {
-	double means[TD_CAP], minv = 0, maxv = 0;
-	uint64_t w[TD_CAP];
+	double means[TD_CAP], minv = 0, maxv = 0, om[TD_CAP];
+	uint64_t w[TD_CAP], ow[TD_CAP];
 	uint32_t n = 0;
 	int rc = gysk_export_tdigest(e, id, means, w, TD_CAP, &n, &minv, &maxv);
 	if (rc) return rc;
-	return gysk_tdigest_to_pgtext(means, w, n, e->cfg.td_compression, buf, cap);
+	const uint32_t no = host_td_compress(means, w, n, 100.0, om, ow);
+	return gysk_tdigest_to_pgtext(om, ow, no, 100, buf, cap);
 }
 
 int gysk_query_quantiles(gysk_engine *e, uint64_t id, const double *qs, uint32_t nq, double *out)
@@ -1060,7 +1105,12 @@ int gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gys
 	CU(e, cudaMemcpy(&nslots, e->st.svc_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	nslots = std::min(nslots, std::min(e->cfg.max_svcs, e->cfg.max_batch));
 	gysk_topn_entry *d_out = reinterpret_cast<gysk_topn_entry *>(e->d_flowout);		// QCHUNK * 16 B >= 64 * 24 B
-	{ const int nl = launch_topn(e->st, e->tmp, nslots, metric, host_idx, n, d_out, e->stream); if (nl > 0) e->kernel_launches += nl; }
+	CU(e, cudaMemsetAsync(d_out, 0, sizeof(gysk_topn_entry) * n, e->stream));
+	{
+		const int nl = launch_topn(e->st, e->tmp, nslots, metric, host_idx, n, d_out, e->stream);
+		if (nl < 0) return fail(e, GYSK_ERR_INVAL, "gysk_topn_svcs: sort failed");
+		e->kernel_launches += nl;
+	}
 	gysk_topn_entry *h_out = reinterpret_cast<gysk_topn_entry *>(e->h_flowout);
 	CU(e, cudaMemcpyAsync(h_out, d_out, sizeof(gysk_topn_entry) * n, cudaMemcpyDeviceToHost, e->stream));
 	CU(e, cudaStreamSynchronize(e->stream));
@@ -1084,7 +1134,11 @@ int gysk_topn_tasks(gysk_engine *e, int metric, uint32_t n, gysk_topn_entry *out
 	ntasks = std::min(ntasks, std::min(e->cfg.max_tasks, e->cfg.max_batch));
 	gysk_topn_entry *d_out = reinterpret_cast<gysk_topn_entry *>(e->d_flowout);		// QCHUNK * 16 B >= 64 * 24 B
 	CU(e, cudaMemsetAsync(d_out, 0, sizeof(gysk_topn_entry) * n, e->stream));
-	{ const int nl = launch_topn_tasks(e->st, e->tmp, ntasks, metric, n, d_out, e->stream); if (nl > 0) e->kernel_launches += nl; }
+	{
+		const int nl = launch_topn_tasks(e->st, e->tmp, ntasks, metric, n, d_out, e->stream);
+		if (nl < 0) return fail(e, GYSK_ERR_INVAL, "gysk_topn_tasks: sort failed");
+		e->kernel_launches += nl;
+	}
 	gysk_topn_entry *h_out = reinterpret_cast<gysk_topn_entry *>(e->h_flowout);
 	CU(e, cudaMemcpyAsync(h_out, d_out, sizeof(gysk_topn_entry) * n, cudaMemcpyDeviceToHost, e->stream));
 	CU(e, cudaStreamSynchronize(e->stream));
@@ -1130,19 +1184,18 @@ int gysk_query_cluster_state(gysk_engine *e, const uint32_t *host_idxs, uint32_t
 	return GYSK_OK;
 }
 
-// The radix passes the t-digest chain would run for keys with `value_bits` significant usec bits and `nslots` services:
-// out[p] = {shift1, bits1, shift2, bits2}, digit = ((key >> shift1) & mask1) | (((key >> shift2) & mask2) << bits1). No engine, no
-// device: the plan is host logic (tests pin that every significant bit is sorted exactly once, in order, in the fewest passes).
-int gysk_sort_plan(uint32_t value_bits, uint32_t nslots, int32_t out[8][4], uint32_t *npasses)
+// The radix passes the t-digest chain runs over the RESP keys of an engine with capacity max_svcs: the sort word is
+// {slot | code(usec)} (TD_CODE_BITS = 10 value bits), out[p] = {shift, bits, 0, 0}, digit = (word >> shift) & ((1 << bits) - 1).
+// No engine, no device: the plan is host logic (tests pin that every significant bit is sorted exactly once, in order, in the
+// fewest passes of at most 9 bits). value_bits is accepted for ABI compatibility and ignored.
+int gysk_sort_plan(uint32_t value_bits, uint32_t max_svcs, int32_t out[8][4], uint32_t *npasses)
 {
-	if (!out || !npasses || value_bits < 1 || value_bits > (uint32_t)VALUE_BITS) return GYSK_ERR_INVAL;
-	uint32_t slot_bits = 1;
-	while (slot_bits < 32 && (1ull << slot_bits) < nslots) slot_bits++;
-	if (slot_bits > 64 - (uint32_t)KEY_SLOT_SHIFT) return GYSK_ERR_INVAL;
-	int plan[8][4];
-	const int np = radix_sort_plan(KEY_VALUE_SHIFT, KEY_VALUE_SHIFT + (int)value_bits, KEY_SLOT_SHIFT, KEY_SLOT_SHIFT + (int)slot_bits, plan, 8);
+	(void)value_bits;
+	if (!out || !npasses || !max_svcs || max_svcs > (1u << 24)) return GYSK_ERR_INVAL;
+	int shift[OS_MAX_PASSES_VK], bits[OS_MAX_PASSES_VK];
+	const int np = vk_sort_plan(max_svcs, shift, bits);
 	if (np < 0) return GYSK_ERR_INVAL;
-	for (int p = 0; p < np && p < 8; ++p) for (int k = 0; k < 4; ++k) out[p][k] = plan[p][k];
+	for (int p = 0; p < np; ++p) { out[p][0] = shift[p]; out[p][1] = bits[p]; out[p][2] = 0; out[p][3] = 0; }
 	*npasses = (uint32_t)np;
 	return GYSK_OK;
 }

@@ -89,6 +89,9 @@ struct gysk_engine
 	bool			evict_pending {false};
 	std::vector<uint64_t>	evicted_ids;				// of the last completed flush
 	uint64_t		tombstones {0}, evicted_total {0};
+	uint64_t		h_evict_fail {0};			// CTR_INSERT_FAIL as of the last collected flush
+	uint64_t		insert_fail_seen {0};			// CTR_INSERT_FAIL at the last table rebuild
+	uint32_t		sort_epoch {0};				// radix passes launched so far (tags the look-back status words)
 
 	std::unordered_map<uint32_t, gysk_host_summary> host_summ;	// last LISTEN_SUMM_STATS per host (control-plane sized: <= 512 hosts)
 

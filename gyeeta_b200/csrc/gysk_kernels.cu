@@ -1,12 +1,13 @@
 // gysk_kernels.cu — hand-written sm_100a kernels of the streaming-sketch engine.
 //
 //   ingest_kernel        one pass over a batch of 32-byte events: id -> slot, then per event type
-//                          RESP : GY_HISTOGRAM::add_data (RESP_TIME_HASH)            common/gy_statistics.h:596-623, :1698
-//                                 + emit (slot, usec) sort key for the t-digest chain
+//                          RESP : emit the (slot, usec, client port) sort key + the digit histograms of the radix passes
 //                          TCP  : count-min cell adds, HLL register max, per-service exact cell
 //                          TASK : MAGGR_TASK::set_local_task_state (3 histograms)     server/gy_msocket.h:1009-1018
-//   rs_* / scan_*        stable LSD radix sort of the (slot, usec) keys (8-bit digits)
-//   td_segments/update   batched merging t-digest (K_1 scale, delta = 100)           DESIGN.md §t-digest
+//   os_pass_kernel       stable one-sweep LSD radix passes over the keys, sorted by (slot, log-linear code of usec)
+//   td_segments/plan/sums/merge
+//                        GY_HISTOGRAM::add_data (RESP_TIME_HASH) common/gy_statistics.h:596-623, :1698, CONN_BITMAP and the
+//                        batched merging t-digest (K_1 scale) from the sorted keys                     DESIGN.md §2
 //   flush_kernel         5-s window roll                                               common/gy_socket_stat.cc:3898
 //   gather_* / query_*   read side
 #include "gysk_kernels.cuh"
@@ -25,6 +26,11 @@ static constexpr unsigned long long KEY_SENTINEL = ~0ull;
 static constexpr unsigned long long VALUE_MASK = (1ull << VALUE_BITS) - 1;
 __device__ __forceinline__ uint32_t key_slot(unsigned long long k) { return (uint32_t)(k >> KEY_SLOT_SHIFT); }
 __device__ __forceinline__ uint32_t key_usec(unsigned long long k) { return (uint32_t)(k >> KEY_VALUE_SHIFT) & (uint32_t)VALUE_MASK; }
+// what the radix passes sort on: {slot | log-linear code of the response time} — 10 value bits instead of 30
+__device__ __forceinline__ unsigned long long key_vk(unsigned long long k)
+{
+	return ((unsigned long long)key_slot(k) << TD_CODE_BITS) | td_code(key_usec(k));
+}
 
 // ---------------------------------------------------------------------------------------------------
 // state init / registration
@@ -57,7 +63,7 @@ __global__ void register_kernel(DevState st, const unsigned long long *ids, uint
 // ---------------------------------------------------------------------------------------------------
 // Service popularity is Zipf-skewed: a few {count, sum} cells would take millions of same-address L2 atomics per batch and
 // serialise the kernel. Two levels take that pressure off L2:
-//   warp : lanes updating the same cell are grouped with match.any, reduced with redux and represented by one leader;
+//   warp : lanes updating the same cell are grouped with match.any, reduced with a shuffle loop and represented by one leader;
 //   CTA  : a direct-mapped shared-memory table privatises hot cells for the lifetime of the CTA (a cell is admitted when it
 //          shows up at least twice inside one warp), and is flushed with one RED pair per entry when the CTA retires.
 // Everything stays exact integer arithmetic, so the result is independent of grouping and order.
@@ -142,31 +148,16 @@ __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t
 	}
 }
 
-// The kernel runs as a persistent tile pipeline. A CTA takes a tile of INGEST_TILE events and
-//   phase 1 (one event per thread and round, fully converged): 2 x 128-bit load, shard filter, id -> slot lookup. A RESP
-//           sample becomes its sort key {slot, usec, client port & 31} in the tile's key queue — its histogram cell, CONN_BITMAP
-//           bit and t-digest share are all produced later from the SORTED keys, where equal cells are contiguous runs
-//           (td_sums_kernel). TCP / TASK events leave their decoded record in shared memory and their index in the queue of
-//           their kind (ballot + one shared-memory atomic per warp and kind);
-//   phase 2 (converged per kind): every warp strides over one queue at a time, so the count-min rows (one (event, row) pair
-//           per lane), the HLL updates and the three task histograms (one (event, histogram) pair per lane) each run with all
-//           lanes doing the same thing instead of serialising 70/20/10-divergent branches;
-//   phase 3: the tile's RESP keys go out as one contiguous, coalesced run (one global cursor bump per tile).
-
-struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
-
-// ---- TMA (bulk async copy) staging of the next event tile into shared memory, completion on an mbarrier ----
+// ---- TMA (bulk async copy) of a warp's next event chunk into shared memory, completion on the warp's own mbarrier ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
 {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");		// make the init visible to the async proxy
 }
 
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
 {
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");		// earlier generic-proxy reads of dst are done (after bar.sync)
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 			:: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -178,80 +169,149 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 			:: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-template <int INGEST_THREADS, bool STAGE, int INGEST_EPT = 4>
+// The kernel is WARP-AUTONOMOUS: no block barrier anywhere in the event loop. A warp takes a chunk of 32 x EPT events and
+//   (1) decodes them fully converged: 2 x 128-bit load per event, shard filter, id -> slot lookup with the first table probe
+//       of all EPT events in flight together. An event then joins one of the warp's three private shared-memory queues
+//       (ballot + popc, no atomics: the queue lengths are warp-uniform registers): RESP -> its 64-bit sort key
+//       {slot, usec, client port & 31}; TCP / TASK -> a 16-byte decoded record;
+//   (2) drains a queue only in whole multiples of 32 entries, so every lane works in every iteration whatever the 70/20/10
+//       mix of the stream is: TCP = two lookup2 hashes per flow key -> four count-min REDs + HLL register + the service's
+//       exact {count, kbytes} cell; TASK = the three histograms of MAGGR_TASK::set_local_task_state with one (event,
+//       histogram) pair per lane; the < 32 left-over entries move to the queue's front;
+//   (3) hands its RESP keys to the global key array in runs of >= KQ_FLUSH (one cursor bump per run, coalesced stores) and
+//       counts, on the way out, each key's digit for every radix pass in the CTA's shared-memory histograms — the one-sweep
+//       passes need the global digit histograms up front, and this way no kernel re-reads the keys to get them.
+// The RESP histogram cell, CONN_BITMAP bit and t-digest share are all produced later from the SORTED keys, where equal cells
+// are contiguous runs (td_sums_kernel).
+struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
+
+struct SortPlan { int np; int shift[OS_MAX_PASSES_VK]; int bits[OS_MAX_PASSES_VK]; };	// digit p = (vk >> shift[p]) & ((1 << bits[p]) - 1)
+
+template <int WARPS, int EPT, bool TMA>
 struct IngestSharedT
 {
-	static constexpr int INGEST_TILE = INGEST_THREADS * INGEST_EPT;
-	using HotTable = HotTableT<(INGEST_TILE >= 1024 ? 10 : 9)>;
-	alignas(128) uint4	evbuf[STAGE ? INGEST_TILE * 2 : 1];	// next tile of 32-byte events, filled by cp.async.bulk
-	unsigned long long	mbar;
+	static constexpr int CHUNK = 32 * EPT;			// events per warp and round
+	static constexpr int KQ_CAP = 256, KQ_FLUSH = KQ_CAP - CHUNK;	// flush leaves room for a whole chunk of RESP events
+	static constexpr int RQ_CAP = 32 + CHUNK;			// < 32 left over + one chunk
+	static_assert(CHUNK <= 128, "key queue sized for chunks of at most 128 events");
+	using HotTable = HotTableT<9>;
+	struct Warp {
+		unsigned long long kq[KQ_CAP];
+		IngestRec	tcp[RQ_CAP], task[RQ_CAP];
+	};
+	alignas(128) uint4	evbuf[TMA ? WARPS * CHUNK * 2 : 1];	// per warp: its next chunk of 32-byte events, filled by cp.async.bulk
+	unsigned long long	mbar[TMA ? WARPS : 1];
+	Warp		w[WARPS];
 	HotTable	hot;
-	// per-tile state, double-buffered by tile parity: phase 1 of tile t+1 fills one set while stragglers still drain the other
-	unsigned long long kq[2][INGEST_TILE];		// RESP sort keys of the tile, compacted
-	IngestRec	rec[2][INGEST_TILE];		// decoded TCP events from the front, TASK events from the back (together <= tile)
-	// packed {n_resp | n_tcp | n_task}, QBITS bits each; three sets in rotation so that a set is cleared a full tile before its
-	// next use (after the barrier of tile t: the set of tile t+2). Tiles of up to 512 events fit 3 x 10 bits in ONE 32-bit word
-	// (native shared-memory add; the 64-bit add is a compare-and-swap loop)
-	static constexpr int QBITS = INGEST_TILE <= 512 ? 10 : 21;
-	using QWord = typename std::conditional<INGEST_TILE <= 512, uint32_t, unsigned long long>::type;
-	QWord		qn[3];
-	unsigned long long key_base[2];
-	uint32_t	key_seq[2];			// tile sequence number + 1 once key_base of that parity is valid
-	uint32_t	max_value;			// largest RESP msec seen by this CTA (sizes the radix sort)
+	uint32_t	dhist[OS_MAX_PASSES_VK][RADIX_MAX];		// digit histograms of this CTA's keys, one per radix pass
 };
 
-// warp-aggregated append: returns this lane's position in the queue (valid where pred)
-__device__ __forceinline__ uint32_t queue_reserve(bool pred, uint32_t *qn)
+template <int WARPS, int MIN_CTAS, int EPT, bool TMA>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
+		unsigned long long *__restrict__ keys, uint32_t *__restrict__ ghist, SortPlan plan)
 {
-	const uint32_t m = __ballot_sync(0xffffffffu, pred);
-	if (!m) return 0;
-	const int lane = threadIdx.x & 31;
-	uint32_t base = 0;
-	if (lane == __ffs(m) - 1) base = atomicAdd(qn, (uint32_t)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-	return base + __popc(m & ((1u << lane) - 1u));
-}
-
-template <int INGEST_THREADS, int MIN_CTAS, bool STAGE, int INGEST_EPT, bool PIPE>
-__global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
-		unsigned long long *__restrict__ keys, int prefetch_next)
-{
-	using IngestShared = IngestSharedT<INGEST_THREADS, STAGE, INGEST_EPT>;
-	using HotTable = typename IngestShared::HotTable;
-	constexpr int INGEST_TILE = IngestShared::INGEST_TILE;
-	constexpr int QBITS = IngestShared::QBITS;
-	constexpr uint32_t QMASK = (1u << QBITS) - 1u;
-	using QWord = typename IngestShared::QWord;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	IngestShared &S = *reinterpret_cast<IngestShared *>(smem_raw);
-	uint32_t c_in = 0, c_foreign = 0;		// per thread: < 2^32 events per launch
-	unsigned long long t_resp = 0, t_tcp = 0, t_task = 0;	// thread 0: per-tile queue lengths summed
+	using Shared = IngestSharedT<WARPS, EPT, TMA>;
+	using HotTable = typename Shared::HotTable;
+	constexpr int CHUNK = Shared::CHUNK;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	Shared &S = *reinterpret_cast<Shared *>(smem_raw);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const uint64_t ntiles = (n + INGEST_TILE - 1) / INGEST_TILE;
-	uint32_t max_us = 0;
+	typename Shared::Warp &W = S.w[wid];
+	const uint32_t lt = (1u << lane) - 1u;
+	uint32_t c_in = 0, c_foreign = 0;				// per thread: < 2^32 events per launch
+	uint32_t nk = 0, ntcp = 0, ntask = 0;				// queue lengths (warp-uniform)
+	unsigned long long t_resp = 0, t_tcp = 0, t_task = 0;	// queued in total (warp-uniform)
 
-	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
-	if (threadIdx.x < 3) S.qn[threadIdx.x] = 0;
-	if (threadIdx.x == 0) { S.max_value = 0; S.key_seq[0] = 0; S.key_seq[1] = 0; }
-	if (STAGE && threadIdx.x == 0) mbar_init(&S.mbar, 1);
-	__syncthreads();
-	// prologue: the first tile of this CTA starts flying into shared memory
-	if (STAGE && threadIdx.x == 0 && blockIdx.x < ntiles) {
-		const uint64_t b0 = (uint64_t)blockIdx.x * INGEST_TILE;
-		const uint64_t cnt = n - b0 < (uint64_t)INGEST_TILE ? n - b0 : (uint64_t)INGEST_TILE;
-		tma_load_1d(S.evbuf, ev + b0, (uint32_t)cnt * 32u, &S.mbar);
-	}
+	for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
+	for (int i = threadIdx.x; i < OS_MAX_PASSES_VK * RADIX_MAX; i += WARPS * 32) (&S.dhist[0][0])[i] = 0;
+	if (TMA && lane == 0) mbar_init(&S.mbar[wid], 1);
+	__syncthreads();						// the only block barriers: here and before the retire step
+	if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");	// mbarrier init visible to the async proxy
 
-	uint4 ra[INGEST_EPT], rb[INGEST_EPT];
-	auto load_tile = [&](uint64_t tb) {
+	const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
+	const uint64_t nwarps = (uint64_t)gridDim.x * WARPS;
+	const uint64_t gwarp = (uint64_t)blockIdx.x * WARPS + wid;
+	uint4 *evw = S.evbuf + (TMA ? wid * CHUNK * 2 : 0);
+	uint32_t tma_phase = 0;
+	auto tma_issue = [&](uint64_t chunk) {
+		const uint64_t b0 = chunk * CHUNK;
+		const uint64_t cnt = n - b0 < (uint64_t)CHUNK ? n - b0 : (uint64_t)CHUNK;
+		// every lane's generic-proxy reads of the buffer happened before the __syncwarp that precedes this call
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		tma_load_1d(evw, ev + b0, (uint32_t)cnt * 32u, &S.mbar[wid]);
+	};
+	if (TMA && lane == 0 && gwarp < nchunks) tma_issue(gwarp);
+
+	// ---- queue drains (all 32 lanes, m = multiple of 32 except in the final drain) ----
+	auto drain_tcp = [&](uint32_t m) {
+		for (uint32_t q = lane; q < ((m + 31u) & ~31u); q += 32) {
+			const bool act = q < m;
+			uint32_t cell = 0; int kb = 0;
+			if (act) {
+				const IngestRec r = W.tcp[q];
+				uint32_t h1, h2, idx, rank;
+				flow_hashes(r.flow_key, h1, h2);
+				const unsigned long long inc = cms_increment(r.value);
+				for (uint32_t row = 0; row < st.cms_depth; ++row)
+					red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index2(h1, h2, row, st.cms_wmask), inc);
+				hll_idx_rank2(h1, h2, st.hll_p, idx, rank);
+				hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
+				cell = r.slot;
+				kb = (int)(r.value >> 10);
+			}
+			cell_add(st, S.hot, act, cell, kb);
+		}
+	};
+	auto drain_task = [&](uint32_t m) {
+		const uint32_t ntrip = m * 3u;
+		for (uint32_t p = lane; p < ((ntrip + 31u) & ~31u); p += 32) {
+			const bool act = p < ntrip;
+			uint32_t cell = 0; int d = 0;
+			if (act) {
+				const uint32_t e = p / 3u, h = p - e * 3u;
+				const IngestRec r = W.task[e];
+				// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
+				d = h == 0 ? (int)r.value : (h == 1 ? (int)(uint32_t)r.flow_key : (int)(uint32_t)(r.flow_key >> 32));
+				const uint32_t b = h == 0 ? (uint32_t)bucket_hash_1_3000(d) : (uint32_t)bucket_duration(d);
+				cell = CELL_TASK | (r.slot * 3u * HIST_CELLS + h * HIST_CELLS + b);
+			}
+			cell_add(st, S.hot, act, cell, d);
+		}
+	};
+	auto keep_rest = [&](IngestRec *q, uint32_t m, uint32_t total) {		// entries [m, total) move to the front (total - m < 32)
+		IngestRec r;
+		const bool mv = m + lane < total;
+		if (mv) r = q[m + lane];
+		__syncwarp();
+		if (mv) q[lane] = r;
+		__syncwarp();
+	};
+	auto flush_keys = [&]() {
+		unsigned long long base = 0;
+		if (lane == 0) base = atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)nk);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		for (uint32_t q = lane; q < nk; q += 32) {
+			const unsigned long long k = W.kq[q];
+			const unsigned long long vk = key_vk(k);
 #pragma unroll
-		for (int k = 0; k < INGEST_EPT; ++k) {
-			const uint64_t i = tb + (uint64_t)k * INGEST_THREADS + threadIdx.x;
+			for (int p = 0; p < OS_MAX_PASSES_VK; ++p)
+				if (p < plan.np) atomicAdd(&S.dhist[p][(uint32_t)(vk >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
+			__stcs(keys + base + q, k);
+		}
+		t_resp += nk;
+		nk = 0;
+		__syncwarp();
+	};
+
+	for (uint64_t chunk = gwarp; chunk < nchunks; chunk += nwarps) {
+		const uint64_t cbase = chunk * CHUNK;
+		uint4 ra[EPT], rb[EPT];
+		if (TMA) mbar_wait(&S.mbar[wid], tma_phase), tma_phase ^= 1u;
+#pragma unroll
+		for (int k = 0; k < EPT; ++k) {
+			const uint64_t i = cbase + (uint64_t)k * 32 + lane;
 			if (i < n) {
-				if (STAGE) {
-					ra[k] = S.evbuf[2 * (k * INGEST_THREADS + threadIdx.x)];
-					rb[k] = S.evbuf[2 * (k * INGEST_THREADS + threadIdx.x) + 1];
-				}
+				if (TMA) { ra[k] = evw[2 * (k * 32 + lane)]; rb[k] = evw[2 * (k * 32 + lane) + 1]; }
 				else {
 					ra[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i));		// streamed once: evict-first, keep L2 for
 					rb[k] = __ldcs(reinterpret_cast<const uint4 *>(ev + i) + 1);	// the id table / histogram / count-min lines
@@ -259,46 +319,23 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			}
 			else { ra[k] = make_uint4(0, 0, 0, 0); rb[k] = make_uint4(0, 0, 0, 0xFFFFu); }	// type 0xFFFF: padding, not counted
 		}
-	};
-	if (PIPE && !STAGE) load_tile((uint64_t)blockIdx.x * INGEST_TILE);
-
-	int par = 0, qi = 0;
-	uint32_t seq = 1;
-	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1, ++seq, qi = qi == 2 ? 0 : qi + 1) {
-		const uint64_t tbase = tile * INGEST_TILE;
-		QWord *qn64 = &S.qn[qi];
-		unsigned long long *kq = S.kq[par];
-		IngestRec *rec = S.rec[par];
-		if (STAGE) mbar_wait(&S.mbar, (uint32_t)par);		// this tile's events have landed (one completion per tile)
-
-		// ---------------- phase 1: decode + lookup + enqueue ----------------
-		// The tile's events are already on their way (or here): their loads were issued before the previous tile's barrier
-		// (PIPE), so the only memory latency left on this phase's critical path is the id-table probe.
-		if (!PIPE || STAGE) load_tile(tbase);
-		// this CTA's next tile starts moving from HBM to L2 now (no registers held): its loads one tile later find L2
-		if (!STAGE && prefetch_next) {
-#pragma unroll
-			for (int k = 0; k < INGEST_EPT; ++k) {
-				const uint64_t i = tbase + (uint64_t)gridDim.x * INGEST_TILE + (uint64_t)k * INGEST_THREADS + threadIdx.x;
-				if (i < n) {
-					if (prefetch_next == 2) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(ev + i));
-					else asm volatile("prefetch.global.L2 [%0];" :: "l"(ev + i));
-				}
-			}
+		if (TMA) {
+			__syncwarp();								// the whole warp has copied its events out of the buffer
+			if (lane == 0 && chunk + nwarps < nchunks) tma_issue(chunk + nwarps);	// next chunk flies in while this one is processed
 		}
+
 		// decode; put the first id-table probe of all EPT events in flight before any of them is resolved
-		uint4 praw[INGEST_EPT];
-		uint32_t ppos[INGEST_EPT];
-		uint32_t kind[INGEST_EPT];		// 0 none, GYSK_EV_RESP, 1 tcp (stored as GYSK_EV_ACCEPT), GYSK_EV_TASK
+		uint4 praw[EPT];
+		uint32_t ppos[EPT];
+		uint32_t kind[EPT];		// 0 none, GYSK_EV_RESP, GYSK_EV_ACCEPT (= any TCP type), GYSK_EV_TASK
 #pragma unroll
-		for (int k = 0; k < INGEST_EPT; ++k) {
+		for (int k = 0; k < EPT; ++k) {
 			const unsigned long long svc = ((unsigned long long)ra[k].y << 32) | ra[k].x;
 			const uint32_t value = rb[k].x, host_idx = rb[k].y;
 			const uint32_t type = rb[k].w & 0xFFFFu;
-			const bool pad = tbase + (uint64_t)k * INGEST_THREADS + threadIdx.x >= n;
 			const bool is_resp = type == GYSK_EV_RESP, is_task = type == GYSK_EV_TASK;
 			const bool is_tcp = type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER;
-			bool mine = !pad;
+			bool mine = type != 0xFFFFu;
 
 			kind[k] = 0; ppos[k] = 0; praw[k] = make_uint4(0, 0, 0, 0);
 			if (mine && st.world > 1 && (host_idx % st.world) != st.rank) { c_foreign++; mine = false; }
@@ -313,7 +350,7 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 			}
 		}
 #pragma unroll
-		for (int k = 0; k < INGEST_EPT; ++k) {
+		for (int k = 0; k < EPT; ++k) {
 			const bool is_resp = kind[k] == GYSK_EV_RESP, is_task = kind[k] == GYSK_EV_TASK, is_tcp = kind[k] == GYSK_EV_ACCEPT;
 			int slot = -1;
 			if (kind[k]) {
@@ -321,108 +358,40 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 				slot = table_resolve(is_task ? st.task_tbl : st.svc_tbl, ((unsigned long long)ra[k].y << 32) | ra[k].x, st.auto_register, rb[k].y, ppos[k], praw[k]);
 			}
 			const bool ok = slot >= 0;
-			if (ok && is_resp) max_us = max(max_us, rb[k].x);
-			// one shared-memory atomic per warp reserves queue space for all three kinds: {resp : 21 | tcp : 21 | task : 21}
 			const uint32_t m_resp = __ballot_sync(0xffffffffu, ok && is_resp), m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp),
 					m_task = __ballot_sync(0xffffffffu, ok && is_task);
-			QWord qbase = 0;
-			if (lane == 0 && (m_resp | m_tcp | m_task))
-				qbase = atomicAdd(qn64, (QWord)__popc(m_resp) | ((QWord)__popc(m_tcp) << QBITS) | ((QWord)__popc(m_task) << (2 * QBITS)));
-			qbase = __shfl_sync(0xffffffffu, qbase, 0);
-			const uint32_t lt = (1u << lane) - 1u;
-			const uint32_t q_resp = ((uint32_t)qbase & QMASK) + __popc(m_resp & lt), q_tcp = ((uint32_t)(qbase >> QBITS) & QMASK) + __popc(m_tcp & lt),
-					q_task = (uint32_t)(qbase >> (2 * QBITS)) + __popc(m_task & lt);
 			if (ok) {
 				if (is_resp) {
 					// {slot, usec, client port & 31 (CONN_BITMAP index, common/gy_socket_stat.h:403-410)}
-					kq[q_resp] = ((unsigned long long)(uint32_t)slot << KEY_SLOT_SHIFT) | ((unsigned long long)rb[k].x << KEY_VALUE_SHIFT) | (ra[k].z & 0x1Fu);
+					W.kq[nk + __popc(m_resp & lt)] = ((unsigned long long)(uint32_t)slot << KEY_SLOT_SHIFT) | ((unsigned long long)rb[k].x << KEY_VALUE_SHIFT) | (ra[k].z & 0x1Fu);
 				}
 				else {
 					IngestRec r; r.slot = (uint32_t)slot; r.value = rb[k].x; r.flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
-					rec[is_tcp ? q_tcp : (uint32_t)INGEST_TILE - 1u - q_task] = r;
+					if (is_tcp) W.tcp[ntcp + __popc(m_tcp & lt)] = r;
+					else W.task[ntask + __popc(m_task & lt)] = r;
 				}
 			}
+			nk += __popc(m_resp); ntcp += __popc(m_tcp); ntask += __popc(m_task);
 		}
-		if (PIPE && !STAGE) load_tile(tbase + (uint64_t)gridDim.x * INGEST_TILE);	// next tile of this CTA (all padding past the end)
-		__syncthreads();			// the only block barrier of the tile: queues of this parity are complete
-		const QWord qv = *qn64;
-		const uint32_t n_resp = (uint32_t)qv & QMASK, n_tcp = (uint32_t)(qv >> QBITS) & QMASK, n_task = (uint32_t)(qv >> (2 * QBITS));
-		// thread 0 bumps the global key cursor now; its round trip to L2 hides behind the TCP and TASK phases
-		if (threadIdx.x == 0) {
-			// the set of tile t+2 (== tile t-1): every warp has read its counts (it passed this barrier), and nobody appends
-			// to it before the next barrier
-			S.qn[qi == 0 ? 2 : qi - 1] = 0;
-			t_resp += n_resp; t_tcp += n_tcp; t_task += n_task;
-			S.key_base[par] = n_resp ? atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)n_resp) : 0ull;
-			__threadfence_block();
-			*((volatile uint32_t *)&S.key_seq[par]) = seq;
-			// every thread has consumed evbuf (barrier above): stage the next tile of this CTA while phase 2 runs
-			if (STAGE && tile + gridDim.x < ntiles) {
-				const uint64_t b1 = (tile + gridDim.x) * INGEST_TILE;
-				const uint64_t cnt = n - b1 < (uint64_t)INGEST_TILE ? n - b1 : (uint64_t)INGEST_TILE;
-				tma_load_1d(S.evbuf, ev + b1, (uint32_t)cnt * 32u, &S.mbar);
-			}
-		}
+		__syncwarp();
 
-		// ---------------- phase 2a: TCP — count-min rows, one (event, row) pair per lane ----------------
-		{
-			const uint32_t npairs = n_tcp * st.cms_depth;
-			const bool d4 = st.cms_depth == 4;		// the default depth: no integer division on the pair index
-			for (uint32_t p = threadIdx.x; p < npairs; p += INGEST_THREADS) {
-				const uint32_t e = d4 ? p >> 2 : p / st.cms_depth, row = d4 ? p & 3u : p - e * st.cms_depth;
-				const IngestRec r = rec[e];
-				red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index(r.flow_key, row, st.cms_wmask), cms_increment(r.value));
-			}
-			// HLL register + the service's exact {count, kbytes} cell
-			for (uint32_t base = wid * 32; base < n_tcp; base += INGEST_THREADS) {
-				const uint32_t q = base + lane;
-				const bool act = q < n_tcp;
-				uint32_t cell = 0; int kb = 0;
-				if (act) {
-					const IngestRec r = rec[q];
-					uint32_t idx, rank;
-					hll_idx_rank(r.flow_key, st.hll_p, idx, rank);
-					hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
-					cell = r.slot;
-					kb = (int)(r.value >> 10);
-				}
-				cell_add(st, S.hot, act, cell, kb);
-			}
-		}
-		// ---------------- phase 2b: TASK — MAGGR_TASK::set_local_task_state, one (event, histogram) pair per lane ----------------
-		{
-			const uint32_t ntrip = n_task * 3u;
-			for (uint32_t base = wid * 32; base < ntrip; base += INGEST_THREADS) {
-				const uint32_t p = base + lane;
-				const bool act = p < ntrip;
-				uint32_t cell = 0; int d = 0;
-				if (act) {
-					const uint32_t e = p / 3u, h = p - e * 3u;
-					const IngestRec r = rec[(uint32_t)INGEST_TILE - 1u - e];
-					// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
-					d = h == 0 ? (int)r.value : (h == 1 ? (int)(uint32_t)r.flow_key : (int)(uint32_t)(r.flow_key >> 32));
-					const uint32_t b = h == 0 ? (uint32_t)bucket_hash_1_3000(d) : (uint32_t)bucket_duration(d);
-					cell = CELL_TASK | (r.slot * 3u * HIST_CELLS + h * HIST_CELLS + b);
-				}
-				cell_add(st, S.hot, act, cell, d);
-			}
-		}
-		// ---------------- phase 3: the tile's RESP keys leave as one coalesced run ----------------
-		if (n_resp) {
-			while (*((volatile uint32_t *)&S.key_seq[par]) != seq) { }		// thread 0's cursor bump has landed (normally long ago)
-			unsigned long long *dst = keys + *((volatile unsigned long long *)&S.key_base[par]);
-			for (uint32_t q = threadIdx.x; q < n_resp; q += INGEST_THREADS) __stcs(dst + q, kq[q]);
-		}
-		// no barrier here: the next tile fills the other parity; this parity is reused only after the next tile's barrier
+		if (ntcp >= 32) { const uint32_t m = ntcp & ~31u; drain_tcp(m); keep_rest(W.tcp, m, ntcp); t_tcp += m; ntcp -= m; }
+		if (ntask >= 32) { const uint32_t m = ntask & ~31u; drain_task(m); keep_rest(W.task, m, ntask); t_task += m; ntask -= m; }
+		if (nk > (uint32_t)Shared::KQ_FLUSH) flush_keys();
 	}
+	// what is left in the queues
+	if (ntcp) { drain_tcp(ntcp); t_tcp += ntcp; }
+	if (ntask) { drain_task(ntask); t_task += ntask; }
+	if (nk) flush_keys();
 
-	max_us = __reduce_max_sync(0xffffffffu, max_us);
-	if (lane == 0 && max_us) atomicMax(&S.max_value, max_us / 1000u);	// msec is enough: bits(usec) <= bits(msec) + 10
 	__syncthreads();
-	if (threadIdx.x == 0 && S.max_value) atomicMax(st.counters + CTR_MAXVAL, (unsigned long long)S.max_value);
-	// retire: one RED group per privatised cell
-	for (int i = threadIdx.x; i < HotTable::N; i += INGEST_THREADS) {
+	// retire: one RED group per privatised cell, one RED per digit this CTA saw
+	for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) {
 		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i]);
+	}
+	for (int i = threadIdx.x; i < plan.np * RADIX_MAX; i += WARPS * 32) {
+		const uint32_t c = (&S.dhist[0][0])[i];
+		if (c) atomicAdd(ghist + i, c);
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
@@ -431,45 +400,43 @@ __global__ void __launch_bounds__(INGEST_THREADS, MIN_CTAS) ingest_kernel(DevSta
 	if (lane == 0) {
 		if (c_in) atomicAdd(st.counters + CTR_IN, (unsigned long long)c_in);
 		if (c_foreign) atomicAdd(st.counters + CTR_FOREIGN, (unsigned long long)c_foreign);
-		// dropped = taken in but not queued (svc_id 0, bad type or value, table full, unknown id): derived after all adds landed
-		if (c_in) atomicAdd(st.counters + CTR_DROPPED, (unsigned long long)c_in);
-	}
-	if (threadIdx.x == 0) {
 		if (t_resp) atomicAdd(st.counters + CTR_RESP, t_resp);
 		if (t_tcp) atomicAdd(st.counters + CTR_TCP, t_tcp);
 		if (t_task) atomicAdd(st.counters + CTR_TASK, t_task);
+		// dropped = taken in but not queued (svc_id 0, bad type or value, table full, unknown id); two's complement arithmetic
 		const unsigned long long q = t_resp + t_tcp + t_task;
-		if (q) atomicAdd(st.counters + CTR_DROPPED, 0ull - q);	// two's complement: dropped += in - queued
+		if (c_in != q) atomicAdd(st.counters + CTR_DROPPED, (unsigned long long)c_in - q);
 	}
 }
 
 // ---------------------------------------------------------------------------------------------------
 // stable LSD radix sort, 8- or 9-bit digits, tile = SORT_TILE keys per CTA of 256 threads
 // ---------------------------------------------------------------------------------------------------
-static constexpr int RADIX_MAX_BITS = 9;
-static constexpr int RADIX_MAX = 1 << RADIX_MAX_BITS;
-
-// one radix pass sorts on a digit made of up to two bit fields of the key, so that the unused bits between the usec field
-// and the slot field of a key never cost a pass: digit = ((k >> s1) & m1) | (((k >> s2) & m2) << b1)
+// A pass sorts on a digit made of up to two bit fields: digit = ((w >> s1) & m1) | (((w >> s2) & m2) << b1), where w is the key
+// itself (plain mode: the top-N sorts) or, in VK mode, the RESP sort word {slot | code(usec)} derived from the key on the fly.
 struct DigitSpec { int s1, b1, s2, b2; };
+template <bool VK>
 __device__ __forceinline__ uint32_t key_digit(unsigned long long k, const DigitSpec &D)
 {
-	return ((uint32_t)(k >> D.s1) & ((1u << D.b1) - 1u)) | (((uint32_t)(k >> D.s2) & ((1u << D.b2) - 1u)) << D.b1);
+	const unsigned long long w = VK ? key_vk(k) : k;
+	return ((uint32_t)(w >> D.s1) & ((1u << D.b1) - 1u)) | (((uint32_t)(w >> D.s2) & ((1u << D.b2) - 1u)) << D.b1);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // one-sweep radix pass: 16 B of HBM traffic per key and pass (read once, write once)
 //
-//   os_hist_kernel   one read of the keys fills the GLOBAL digit histograms of every pass (digits are fixed before the first
-//                    pass, and a stable pass does not change how many keys carry a digit value);
-//   os_pass_kernel   a CTA takes the next tile (ticket from an atomic counter, so every predecessor tile is already running),
-//                    ranks its keys per digit, publishes the tile's digit counts and obtains the number of keys with the same
-//                    digit in all earlier tiles by decoupled look-back over the status words of its predecessors
-//                    (status word = 2-bit state | 30-bit count: 1 = this tile's count, 2 = inclusive prefix up to this tile),
-//                    reorders the tile by digit in shared memory and writes every digit's run to its final place.
+//   digit histograms   the GLOBAL digit histograms of every pass are known before the first pass (a stable pass does not change
+//                      how many keys carry a digit value): for the RESP keys ingest_kernel counts them while it emits the keys,
+//                      for the small top-N sorts os_hist_kernel reads the keys once;
+//   os_pass_kernel     a CTA takes the next tile (ticket from an atomic counter, so every predecessor tile is already running),
+//                      ranks its keys per digit, publishes the tile's digit counts and obtains the number of keys with the same
+//                      digit in all earlier tiles by decoupled look-back over the status words of its predecessors
+//                      (status word = pass epoch : 32 | state : 2 | count : 30; state 1 = this tile's count, 2 = inclusive prefix
+//                      up to this tile; a word of another epoch reads as "not there yet", so the array is never cleared),
+//                      reorders the tile by digit in shared memory and writes every digit's run to its final place.
+// The number of keys comes from DEVICE memory (the key cursor ingest_kernel bumped): the grid is sized for the largest possible
+// count and surplus CTAs leave at once — no host read-back between ingest and sort.
 // Stability: tiles are ordered by ticket = tile index, ranks inside a tile follow the input order (warp, round, lane).
-// Digits are 8 bits wide; when the significant bits do not fit ceil(bits / 9) + ... passes of 8 (e.g. 41 bits), some passes take
-// 9 bits (512 digits, two per thread in the per-digit steps) instead of the sort paying a whole extra pass.
 // ---------------------------------------------------------------------------------------------------
 static constexpr int OS_THREADS = 256;			// thread t owns digits t, t + 256 in the per-digit steps
 static constexpr int OS_WARPS = OS_THREADS / 32;
@@ -479,16 +446,28 @@ static constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_
 
 struct DigitSpecs { DigitSpec d[OS_MAX_PASSES]; int np; };
 
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
 // lane-privatised histogram copies (lane & (copies - 1)), skewed by one bank each: 8 copies of 257 words per pass for 8-bit
 // digits, 4 copies of 513 words when a pass has 9 bits
 template <int copies, int stride>
-__global__ void __launch_bounds__(512) os_hist_kernel(const unsigned long long *__restrict__ keys, uint64_t n, DigitSpecs P,
+__global__ void __launch_bounds__(512) os_hist_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n, DigitSpecs P,
 		uint32_t *__restrict__ ghist /* [np][RADIX_MAX] */)
 {
 	extern __shared__ __align__(16) unsigned char osh_smem[];
 	uint32_t *h = reinterpret_cast<uint32_t *>(osh_smem);		// [np][copies][stride]
 	const int copy = threadIdx.x & (copies - 1);
 	constexpr int pstride = copies * stride;
+	const uint64_t n = *d_n;
 
 	for (int i = threadIdx.x; i < P.np * pstride; i += blockDim.x) h[i] = 0;
 	__syncthreads();
@@ -503,8 +482,8 @@ __global__ void __launch_bounds__(512) os_hist_kernel(const unsigned long long *
 		for (int p = 0; p < OS_MAX_PASSES; ++p) {
 			if (p < P.np) {
 				uint32_t *hp = h + p * pstride + copy * stride;
-				atomicAdd(hp + key_digit(k0, P.d[p]), 1u);
-				if (two) atomicAdd(hp + key_digit(k1, P.d[p]), 1u);
+				atomicAdd(hp + key_digit<false>(k0, P.d[p]), 1u);
+				if (two) atomicAdd(hp + key_digit<false>(k1, P.d[p]), 1u);
 			}
 		}
 	}
@@ -552,10 +531,11 @@ struct OneSweepSharedT
 	uint32_t		tile;
 };
 
-template <int RBITS>
+template <int RBITS, bool VK>
 __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
-		uint32_t n, DigitSpec D, const uint32_t *__restrict__ ghist /* [RADIX] of this pass */, uint32_t *__restrict__ status /* [ntiles][RADIX] */,
-		uint32_t *__restrict__ ticket, int rank_mode /* 0 auto, 1 match.any, 2 ballots */)
+		const unsigned long long *__restrict__ d_n, DigitSpec D, const uint32_t *__restrict__ ghist /* [RADIX] of this pass */,
+		unsigned long long *__restrict__ status /* [ntiles][RADIX] */, uint32_t *__restrict__ ticket, uint32_t epoch,
+		int rank_mode /* 0 auto, 1 match.any, 2 ballots */)
 {
 	constexpr int RADIX = 1 << RBITS;
 	constexpr int DPT = RADIX / OS_THREADS;		// digits per thread in the per-digit steps
@@ -563,11 +543,14 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 	OneSweepSharedT<RBITS> &S = *reinterpret_cast<OneSweepSharedT<RBITS> *>(os_smem);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
+	const uint32_t n = (uint32_t)*d_n;
+	const unsigned long long etag = (unsigned long long)epoch << 32;
 
 	if (threadIdx.x == 0) S.tile = atomicAdd(ticket, 1u);
 	for (int i = threadIdx.x; i < OS_WARPS * RADIX; i += OS_THREADS) (&S.whist[0][0])[i] = 0;
 	__syncthreads();
 	const uint32_t tile = S.tile;
+	if ((uint64_t)tile * SORT_TILE >= n) return;		// surplus CTA of a grid sized for the largest possible key count
 	const uint32_t wbase = tile * (uint32_t)SORT_TILE + (uint32_t)wid * (OS_KPT * 32);
 
 	unsigned long long k[OS_KPT];
@@ -607,7 +590,7 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 #pragma unroll
 	for (int r = 0; r < OS_KPT; ++r) {
 		const bool valid = wbase + (uint32_t)r * 32 + lane < n;
-		const uint32_t d = valid ? key_digit(k[r], D) : ((uint32_t)RADIX + lane);
+		const uint32_t d = valid ? key_digit<VK>(k[r], D) : ((uint32_t)RADIX + lane);
 		uint32_t m;
 		if (use_ballot) {
 			m = 0xffffffffu;
@@ -630,69 +613,42 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 	}
 	__syncthreads();
 
-	if constexpr (DPT == 1) {
-		// thread d: prefix over the warps, the tile's count of digit d -> published at once, so successors can look back through it
-		const uint32_t d = threadIdx.x;
-		uint32_t dtotal = 0;
+	// thread t owns digits t (+ 256): prefix over the warps, the tile's count of the digit -> published at once, so successors
+	// can look back through it; then the scans over the digits, with a carry between the two halves of a 9-bit pass
+	uint32_t dtotal[DPT];
 #pragma unroll
-		for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = dtotal; dtotal += t; }
-		st_volatile_u32(status + (size_t)tile * RADIX + d, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | dtotal);
-
+	for (int j = 0; j < DPT; ++j) {
+		const uint32_t d = threadIdx.x + j * OS_THREADS;
+		uint32_t run = 0;
+#pragma unroll
+		for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
+		dtotal[j] = run;
+		st_volatile_u64(status + (size_t)tile * RADIX + d, etag | (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | run);
+	}
+	unsigned long long carry = 0;
+#pragma unroll
+	for (int j = 0; j < DPT; ++j) {
+		const uint32_t d = threadIdx.x + j * OS_THREADS;
+		unsigned long long tot = 0;
 		// {global count of digit d, tile count of digit d} -> exclusive scans over the digits in one go
-		const unsigned long long sc = os_block_exclusive_scan(((unsigned long long)ghist[d] << 16) | dtotal, S.scan[0], nullptr);
+		const unsigned long long sc = carry + os_block_exclusive_scan(((unsigned long long)ghist[d] << 16) | dtotal[j], S.scan[j], DPT > 1 ? &tot : nullptr);
+		carry += tot;
 		const uint32_t gexcl = (uint32_t)(sc >> 16), dstart = (uint32_t)(sc & 0xFFFFu);
-
 		// decoupled look-back: keys with digit d in the tiles before this one
 		uint32_t excl = 0;
 		if (tile > 0) {
 			uint32_t p = tile - 1;
 			for (;;) {
-				const uint32_t v = ld_volatile_u32(status + (size_t)p * RADIX + d);
-				if (!(v >> 30)) continue;				// predecessor has its ticket, so it is running: its count will come
-				excl += v & OS_COUNT_MASK;
-				if (v & OS_FLAG_PREFIX) break;
+				const unsigned long long v = ld_volatile_u64(status + (size_t)p * RADIX + d);
+				if ((v >> 32) != epoch || !((uint32_t)v >> 30)) continue;	// predecessor has its ticket, so it is running: its count will come
+				excl += (uint32_t)v & OS_COUNT_MASK;
+				if ((uint32_t)v & OS_FLAG_PREFIX) break;
 				--p;
 			}
-			st_volatile_u32(status + (size_t)tile * RADIX + d, OS_FLAG_PREFIX | (excl + dtotal));
+			st_volatile_u64(status + (size_t)tile * RADIX + d, etag | OS_FLAG_PREFIX | (excl + dtotal[j]));
 		}
 		S.dstart[d] = dstart;
 		S.goff[d] = gexcl + excl - dstart;
-	}
-	else {
-		// thread t owns digits t and t + 256: same steps, the scan runs in digit order with a carry between the two halves
-		uint32_t dtotal[DPT];
-#pragma unroll
-		for (int j = 0; j < DPT; ++j) {
-			const uint32_t d = threadIdx.x + j * OS_THREADS;
-			uint32_t run = 0;
-#pragma unroll
-			for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
-			dtotal[j] = run;
-			st_volatile_u32(status + (size_t)tile * RADIX + d, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | run);
-		}
-		unsigned long long carry = 0;
-#pragma unroll
-		for (int j = 0; j < DPT; ++j) {
-			const uint32_t d = threadIdx.x + j * OS_THREADS;
-			unsigned long long tot = 0;
-			const unsigned long long sc = carry + os_block_exclusive_scan(((unsigned long long)ghist[d] << 16) | dtotal[j], S.scan[j], &tot);
-			carry += tot;
-			const uint32_t gexcl = (uint32_t)(sc >> 16), dstart = (uint32_t)(sc & 0xFFFFu);
-			uint32_t excl = 0;
-			if (tile > 0) {
-				uint32_t p = tile - 1;
-				for (;;) {
-					const uint32_t v = ld_volatile_u32(status + (size_t)p * RADIX + d);
-					if (!(v >> 30)) continue;
-					excl += v & OS_COUNT_MASK;
-					if (v & OS_FLAG_PREFIX) break;
-					--p;
-				}
-				st_volatile_u32(status + (size_t)tile * RADIX + d, OS_FLAG_PREFIX | (excl + dtotal[j]));
-			}
-			S.dstart[d] = dstart;
-			S.goff[d] = gexcl + excl - dstart;
-		}
 	}
 	__syncthreads();
 
@@ -700,7 +656,7 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 #pragma unroll
 	for (int r = 0; r < OS_KPT; ++r) {
 		if (wbase + (uint32_t)r * 32 + lane < n) {
-			const uint32_t dd = key_digit(k[r], D);
+			const uint32_t dd = key_digit<VK>(k[r], D);
 			const uint32_t rank = (r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xFFFFu);
 			S.keys[S.dstart[dd] + S.whist[wid][dd] + rank] = k[r];
 		}
@@ -713,44 +669,64 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 #pragma unroll 4
 	for (uint32_t i = threadIdx.x; i < nvalid; i += OS_THREADS) {
 		const unsigned long long key = S.keys[i];
-		out[S.goff[key_digit(key, D)] + i] = key;
+		out[S.goff[key_digit<VK>(key, D)] + i] = key;
 	}
 }
 
 // ---------------------------------------------------------------------------------------------------
-// batched merging t-digest
+// batched merging t-digest + RESP histograms from the sorted keys
 // ---------------------------------------------------------------------------------------------------
-static constexpr int TSEG_V = 4;			// consecutive keys per thread
+// The keys are sorted by (slot, code): a service's samples are one segment, the samples of one log-linear bin one RUN inside
+// it, in no particular order within the run. td_segments_kernel records where segments and runs start:
+//   seg_start / seg_end / touched   per service
+//   runbits   one bit per key position: a run starts here;  runbits2: one bit per 1024 positions: some run starts in there
+// (two levels so that the planner finds the run start before / after a position in a few loads even inside a bin that holds a
+// million equal samples).
+static constexpr int TSEG_V = 4;			// keys per thread: positions wbase + t * 32 + lane
 
 __global__ void __launch_bounds__(256) td_segments_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
-		uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_end, uint32_t *__restrict__ touched, unsigned long long *ntouched)
+		uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_end, uint32_t *__restrict__ touched, unsigned long long *ntouched,
+		uint32_t *__restrict__ runbits, uint32_t *__restrict__ runbits2)
 {
 	const uint64_t n = *d_n;
-	const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * TSEG_V;
 	const int lane = threadIdx.x & 31;
-	uint32_t sl[TSEG_V + 2];			// slots of key i0-1, i0 .. i0+3, i0+4 (0xFFFFFFFF outside the array)
+	const uint64_t wbase = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane) * TSEG_V;		// 128 consecutive keys per warp
+	if (wbase >= n) return;
 
+	unsigned long long g[TSEG_V + 2];		// {slot, code} of key wbase - 1 (lane 0 only), own 4 keys, successor of the last (lane 31 only)
 #pragma unroll
-	for (int t = 0; t < TSEG_V + 2; ++t) sl[t] = 0xFFFFFFFFu;
-	if (i0 + TSEG_V <= n) {
-		const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0), c = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
-		sl[1] = key_slot(a.x); sl[2] = key_slot(a.y);
-		sl[3] = key_slot(c.x); sl[4] = key_slot(c.y);
+	for (int t = 0; t < TSEG_V; ++t) {
+		const uint64_t i = wbase + (uint64_t)t * 32 + lane;
+		g[1 + t] = i < n ? key_vk(keys[i]) : KEY_SENTINEL;
 	}
-	else {
+	g[0] = (lane == 0 && wbase) ? key_vk(keys[wbase - 1]) : KEY_SENTINEL;
+	g[TSEG_V + 1] = (lane == 31 && wbase + 128 < n) ? key_vk(keys[wbase + 128]) : KEY_SENTINEL;
+
+	uint32_t nstart = 0, anyrun = 0;
+	uint32_t isseg = 0, isend = 0;			// bit t: own key t starts / ends a service segment
 #pragma unroll
-		for (int t = 0; t < TSEG_V; ++t) if (i0 + t < n) sl[1 + t] = key_slot(keys[i0 + t]);
+	for (int t = 0; t < TSEG_V; ++t) {
+		const uint64_t i = wbase + (uint64_t)t * 32 + lane;
+		// predecessor: lane - 1 of the same t, lane 31 of t - 1 for lane 0; successor: lane + 1, lane 0 of t + 1 for lane 31
+		unsigned long long prev = __shfl_up_sync(0xffffffffu, g[1 + t], 1);
+		const unsigned long long prev0 = __shfl_sync(0xffffffffu, g[t], 31);		// g[t] of lane 31 = its key t - 1 (t >= 1)
+		if (lane == 0) prev = t == 0 ? g[0] : prev0;
+		unsigned long long next = __shfl_down_sync(0xffffffffu, g[1 + t], 1);
+		const unsigned long long next0 = __shfl_sync(0xffffffffu, g[2 + (t < TSEG_V - 1 ? t : 0)], 0);	// key t + 1 of lane 0
+		if (lane == 31) next = t == TSEG_V - 1 ? g[TSEG_V + 1] : next0;
+		const bool valid = i < n;
+		const bool run = valid && g[1 + t] != prev;			// i == 0: prev is the sentinel
+		const bool seg = valid && (g[1 + t] >> TD_CODE_BITS) != (prev >> TD_CODE_BITS);
+		const bool end = valid && (g[1 + t] >> TD_CODE_BITS) != (next >> TD_CODE_BITS);	// i == n - 1: next is the sentinel
+		const uint32_t word = __ballot_sync(0xffffffffu, run);
+		if (lane == 0) runbits[(wbase >> 5) + t] = word;
+		anyrun |= word;
+		nstart += seg ? 1u : 0u;
+		isseg |= (seg ? 1u : 0u) << t; isend |= (end ? 1u : 0u) << t;
 	}
-	// neighbours: from the adjacent lanes, the warp's edge lanes load them
-	const uint32_t up = __shfl_up_sync(0xffffffffu, sl[TSEG_V], 1), down = __shfl_down_sync(0xffffffffu, sl[1], 1);
-	sl[0] = lane ? up : ((i0 && i0 - 1 < n) ? key_slot(keys[i0 - 1]) : 0xFFFFFFFFu);
-	sl[TSEG_V + 1] = lane < 31 ? down : (i0 + TSEG_V < n ? key_slot(keys[i0 + TSEG_V]) : 0xFFFFFFFFu);
+	if (lane == 0 && anyrun) atomicOr(&runbits2[wbase >> 15], 1u << ((wbase >> 10) & 31u));
 
-	uint32_t nstart = 0;
-#pragma unroll
-	for (int t = 1; t <= TSEG_V; ++t) nstart += (i0 + t - 1 < n && sl[t] != sl[t - 1]) ? 1u : 0u;
-
-	// one cursor bump per warp for all the runs that start in it (the cold tail has a new service almost every sample)
+	// one cursor bump per warp for all the segments that start in it (the cold tail has a new service every few samples)
 	uint32_t incl = nstart;
 #pragma unroll
 	for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
@@ -758,61 +734,122 @@ __global__ void __launch_bounds__(256) td_segments_kernel(const unsigned long lo
 	unsigned long long base = 0;
 	if (wtotal && lane == 0) base = atomicAdd(ntouched, (unsigned long long)wtotal);
 	base = __shfl_sync(0xffffffffu, base, 0) + (incl - nstart);
-
 #pragma unroll
-	for (int t = 1; t <= TSEG_V; ++t) {
-		const uint64_t i = i0 + t - 1;
-		if (i >= n) break;
-		if (sl[t] != sl[t - 1]) { seg_start[sl[t]] = (uint32_t)i; touched[base++] = sl[t]; }
-		if (sl[t] != sl[t + 1]) seg_end[sl[t]] = (uint32_t)(i + 1);
+	for (int t = 0; t < TSEG_V; ++t) {
+		const uint64_t i = wbase + (uint64_t)t * 32 + lane;
+		const uint32_t slot = (uint32_t)(g[1 + t] >> TD_CODE_BITS);
+		if ((isseg >> t) & 1u) { seg_start[slot] = (uint32_t)i; touched[base++] = slot; }
+		if ((isend >> t) & 1u) seg_end[slot] = (uint32_t)(i + 1);
+	}
+}
+
+// largest run start <= pos (a run starts at the segment's first key, so the search never leaves the segment)
+__device__ __forceinline__ uint32_t run_start_at_or_before(const uint32_t *__restrict__ runbits, const uint32_t *__restrict__ runbits2, uint32_t pos)
+{
+	uint32_t w = pos >> 5;
+	uint32_t m = runbits[w] & (0xFFFFFFFFu >> (31u - (pos & 31u)));
+	if (m) return (w << 5) + 31u - (uint32_t)__clz((int)m);
+	const uint32_t blk0 = w & ~31u;				// rest of this 1024-key block, downwards
+	while (w > blk0) { --w; m = runbits[w]; if (m) return (w << 5) + 31u - (uint32_t)__clz((int)m); }
+	uint32_t b = w >> 5;						// earlier blocks through the second level
+	for (;;) {
+		--b;
+		uint32_t m2 = runbits2[b >> 5] & (0xFFFFFFFFu >> (31u - (b & 31u)));
+		while (!m2) { b = (b & ~31u) - 1u; m2 = runbits2[b >> 5]; }
+		b = (b & ~31u) + 31u - (uint32_t)__clz((int)m2);
+		for (w = (b << 5) + 31u; ; --w) { m = runbits[w]; if (m) return (w << 5) + 31u - (uint32_t)__clz((int)m); if (w == (b << 5)) break; }
+	}
+}
+
+// smallest run start > pos and < end, else end
+__device__ __forceinline__ uint32_t run_start_after(const uint32_t *__restrict__ runbits, const uint32_t *__restrict__ runbits2, uint32_t pos, uint32_t end)
+{
+	uint32_t p = pos + 1;
+	if (p >= end) return end;
+	uint32_t w = p >> 5;
+	uint32_t m = runbits[w] & (0xFFFFFFFFu << (p & 31u));
+	const uint32_t wend = (end - 1) >> 5;				// last word that may be looked at
+	for (;;) {
+		if (m) { const uint32_t r = (w << 5) + (uint32_t)__ffs((int)m) - 1u; return r < end ? r : end; }
+		if (w >= wend) return end;
+		++w;
+		if ((w & 31u) == 0) {					// entering a new 1024-key block: skip empty blocks through the second level
+			uint32_t b = w >> 5;
+			const uint32_t bend = wend >> 5;
+			for (;;) {
+				if (b > bend) return end;
+				const uint32_t m2 = runbits2[b >> 5] & (0xFFFFFFFFu << (b & 31u));
+				if (m2) { b = (b & ~31u) + (uint32_t)__ffs((int)m2) - 1u; break; }
+				b = (b & ~31u) + 32u;
+			}
+			if (b > bend) return end;
+			w = b << 5;
+		}
+		m = runbits[w];
 	}
 }
 
 static constexpr int TD_WARPS = 4;
 static constexpr int PLAN_STRIDE = TD_CAP + 1;
 
-// (1) plan: one thread per touched service runs the greedy chain over n unit-weight samples. Cluster j of the run is
-// [bounds[j], bounds[j+1]) with bounds[j+1] = max(bounds[j] + 1, floor(n q(k(bounds[j]/n) + 1))): the boundaries depend on n
-// only, so they can be fixed before any sample is summed. Also clears the cluster-sum row of the service.
+// (1) plan: one thread per touched service cuts its n new samples into clusters with the greedy rule over unit weights —
+// cluster [s, e) with e = the last run start <= floor(n q(k(s/n) + 1)), or the end of the first run when that lies beyond: a
+// cluster never splits a bin, because the samples inside a bin are unordered. The boundaries depend on n and on the run starts
+// only, so they are fixed before any sample is summed. A pass that would need more than TD_CAP clusters is repeated on the next
+// rung of the ladder. Also clears the cluster-sum row and the batch min / max of the service.
 __global__ void td_plan_kernel(TdParams P, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end,
-		const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p, uint32_t *__restrict__ plan_bounds,
-		uint32_t *__restrict__ plan_n, unsigned long long *__restrict__ newsum)
+		const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p, const uint32_t *__restrict__ runbits,
+		const uint32_t *__restrict__ runbits2, uint32_t *__restrict__ plan_bounds, uint32_t *__restrict__ plan_n,
+		unsigned long long *__restrict__ newsum, uint2 *__restrict__ bminmax)
 {
 	const uint32_t ntouched = (uint32_t)*ntouched_p;
 
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntouched; t += gridDim.x * blockDim.x) {
 		const uint32_t slot = touched[t];
-		const uint32_t n = seg_end[slot] - seg_start[slot];
+		const uint32_t s0 = seg_start[slot];
+		const uint32_t n = seg_end[slot] - s0;
 		uint32_t *bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
 		unsigned long long *sums = newsum + (size_t)slot * TD_CAP;
-		uint32_t nnew = 0, s = 0;
+		uint32_t nnew = 0;
 
-		while (s < n) {
-			const double wl = td_wlimit(s, n, P);
-			unsigned long long ee = (unsigned long long)floor(wl);
-			if (ee > n) ee = n;
-			if (ee < (unsigned long long)s + 1) ee = s + 1;
-			if (nnew == TD_CAP - 1) ee = n;			// the last slot absorbs whatever is left
-			bounds[nnew] = s;
-			sums[nnew] = 0;
-			nnew++;
-			s = (uint32_t)ee;
+		bminmax[slot] = make_uint2(0xFFFFFFFFu, 0u);
+		for (int k = 0; k < TD_LADDER; ++k) {
+			const bool final = k == TD_LADDER - 1;
+			bool overflow = false;
+			uint32_t s = 0;
+			nnew = 0;
+			while (s < n) {
+				const double wl = td_wlimit(s, n, P.r[k]);
+				unsigned long long ee = (unsigned long long)floor(wl);
+				uint32_t e;
+				if (ee >= n) e = n;
+				else e = run_start_at_or_before(runbits, runbits2, s0 + (uint32_t)ee) - s0;
+				if (e <= s) e = run_start_after(runbits, runbits2, s0 + s, s0 + n) - s0;	// at least the first bin
+				if (final && nnew == TD_CAP - 1) e = n;			// the last slot absorbs whatever is left
+				if (nnew == TD_CAP) { overflow = true; break; }
+				bounds[nnew] = s;
+				sums[nnew] = 0;
+				nnew++;
+				s = e;
+			}
+			if (!overflow) break;
 		}
 		bounds[nnew] = n;
 		plan_n[slot] = nnew | (nnew == n ? 0x80000000u : 0u);	// flag: every cluster is a single sample, cluster id == rank
 	}
 }
 
-// (2) sums: one thread per sorted sample. cluster id = position of the sample's rank in the service's bounds; histogram bucket
-// = RESP_TIME_HASH of its msec value. Both are monotone in the rank, so runs of equal (service, cluster, bucket) are contiguous
-// in the sorted order: a lane combines its own consecutive samples, the warp groups the runs with match.any (one group for the
-// whole warp inside a hot service) and the group leader issues
-//   one 64-bit RED with the exact usec sum of the run into the cluster sum (t-digest), and
+// (2) sums: cluster id = position of the sample's rank in the service's bounds; histogram bucket = RESP_TIME_HASH of its msec
+// value. Runs of equal (service, cluster, bucket) are contiguous in the sorted order except inside the few bins a bucket
+// threshold cuts through (there a run merely splits into several, which the REDs add up all the same). Per group the leader issues
+//   one 64-bit RED with the exact usec sum into the cluster sum (t-digest), and
 //   GY_HISTOGRAM::add_data for the whole run (common/gy_statistics.h:596-623): count and msec sum of the bucket cell, plus the
 //   run's CONN_BITMAP bits (TCP_LISTENER::CONN_BITMAP::add_response, common/gy_socket_stat.h:403-410, transposed: one mask over
 //   (client port & 31) per bucket).
-// max_val_seen_ is the service's last sorted sample: td_merge_kernel records it. Skew-immune: a hot service's samples are spread
-// over as many warps as it has samples / 128, and no cell sees more than one RED per warp.
+// Batch minimum / maximum of a service (t-digest ends, max_val_seen_): the samples of its first / last bin compete with
+// atomicMin / atomicMax — everything in between cannot be either.
+// FAST PATH: a warp's 128 consecutive samples usually sit inside ONE cluster of ONE hot service and one bucket (checked on the
+// first and last sample only: the order is monotone across bins): three redux + a handful of REDs for the whole warp.
 __device__ __forceinline__ uint32_t td_cluster_of(const uint32_t *__restrict__ bounds, uint32_t nn, uint32_t r, uint32_t &lo_out, uint32_t &hi_out)
 {
 	uint32_t lo = 0, hi = nn - 1;			// largest j with bounds[j] <= r
@@ -824,8 +861,8 @@ __device__ __forceinline__ uint32_t td_cluster_of(const uint32_t *__restrict__ b
 static constexpr int TDS_V = 4;			// consecutive sorted samples per lane
 
 __global__ void __launch_bounds__(256) td_sums_kernel(DevState st, const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
-		const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ plan_bounds, const uint32_t *__restrict__ plan_n,
-		unsigned long long *__restrict__ newsum)
+		const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end, const uint32_t *__restrict__ plan_bounds,
+		const uint32_t *__restrict__ plan_n, unsigned long long *__restrict__ newsum, uint2 *__restrict__ bminmax)
 {
 	const uint64_t n = *d_n;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * TDS_V;
@@ -843,25 +880,74 @@ __global__ void __launch_bounds__(256) td_sums_kernel(DevState st, const unsigne
 			for (int t = 0; t < TDS_V; ++t) kk[t] = i0 + t < n ? keys[i0 + t] : KEY_SENTINEL;
 		}
 
-		// the whole warp (128 consecutive samples) usually sits inside one cluster of one hot service: lane 0 looks its first
-		// sample up, every sample first checks that range
-		uint32_t slot0 = 0xFFFFFFFFu, j0 = 0, lo0 = 1, hi0 = 0;
+		// lane 0 looks up the cluster of the warp's first sample and the ends of its service
+		uint32_t slot0 = 0xFFFFFFFFu, j0 = 0, lo0 = 1, hi0 = 0, sstart0 = 0, cfirst0 = 0, clast0 = 0;
 		if (lane == 0 && kk[0] != KEY_SENTINEL) {
 			slot0 = key_slot(kk[0]);
-			const uint32_t nn = plan_n[slot0], r = (uint32_t)(i0 - seg_start[slot0]);
+			sstart0 = seg_start[slot0];
+			const uint32_t nn = plan_n[slot0], r = (uint32_t)(i0 - sstart0);
 			if (nn & 0x80000000u) { j0 = r; lo0 = r; hi0 = r + 1; }
 			else j0 = td_cluster_of(plan_bounds + (size_t)slot0 * PLAN_STRIDE, nn, r, lo0, hi0);
+			cfirst0 = td_code(key_usec(keys[sstart0]));
+			clast0 = td_code(key_usec(keys[seg_end[slot0] - 1]));
 		}
 		slot0 = __shfl_sync(0xffffffffu, slot0, 0); j0 = __shfl_sync(0xffffffffu, j0, 0);
 		lo0 = __shfl_sync(0xffffffffu, lo0, 0); hi0 = __shfl_sync(0xffffffffu, hi0, 0);
+		sstart0 = __shfl_sync(0xffffffffu, sstart0, 0);
+		cfirst0 = __shfl_sync(0xffffffffu, cfirst0, 0); clast0 = __shfl_sync(0xffffffffu, clast0, 0);
 
-		// own samples -> runs of equal (service, cluster, bucket); sorted input keeps them contiguous. Sample t carries the totals
-		// of its run so far; only the last sample of a run (its tail) is emitted. Everything is indexed statically (registers).
+		// ---- fast path: the whole warp is one (service, cluster, bucket) group ----
+		{
+			const unsigned long long klast = __shfl_sync(0xffffffffu, kk[TDS_V - 1], 31);
+			bool uniform = false;
+			if (klast != KEY_SENTINEL && key_slot(klast) == slot0 && (uint32_t)(base + 127 - sstart0) < hi0) {
+				const unsigned long long kfirst = __shfl_sync(0xffffffffu, kk[0], 0);
+				const uint32_t cF = td_code(key_usec(kfirst)), cL = td_code(key_usec(klast));
+				uniform = bucket_resp_time((long long)(td_code_lo(cF) / 1000u)) == bucket_resp_time((long long)(td_code_hi(cL) / 1000u));
+				if (uniform) {
+					unsigned long long us = 0;
+					uint32_t ms = 0, bits = 0, vmax = 0, vmin = 0xFFFFFFFFu;
+#pragma unroll
+					for (int t = 0; t < TDS_V; ++t) {
+						const uint32_t v = key_usec(kk[t]);
+						us += v; ms += v / 1000u; bits |= 1u << ((uint32_t)kk[t] & 0x1Fu);
+					}
+					// only the warps at the two ends of a service's segment can hold its extreme samples
+					if (cL == clast0) {
+#pragma unroll
+						for (int t = 0; t < TDS_V; ++t) { const uint32_t v = key_usec(kk[t]); if (td_code(v) == clast0) vmax = max(vmax, v); }
+						vmax = __reduce_max_sync(0xffffffffu, vmax);
+					}
+					if (cF == cfirst0) {
+#pragma unroll
+						for (int t = 0; t < TDS_V; ++t) { const uint32_t v = key_usec(kk[t]); if (td_code(v) == cfirst0) vmin = min(vmin, v); }
+						vmin = __reduce_min_sync(0xffffffffu, vmin);
+					}
+					const unsigned long long gsum = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)us & 0xFFFFFu) +
+							((unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)(us >> 20)) << 20);	// us < 2^32: 20 + 12 bits, x 32 lanes fits
+					ms = __reduce_add_sync(0xffffffffu, ms);
+					bits = __reduce_or_sync(0xffffffffu, bits);
+					if (lane == 0) {
+						const uint32_t cell = slot0 * HIST_CELLS + (uint32_t)bucket_resp_time((long long)(key_usec(kfirst) / 1000u));
+						red_add_u64(newsum + (size_t)slot0 * TD_CAP + j0, gsum);
+						red_add_u64(&st.hist_cur[cell].count, 32u * TDS_V);
+						red_add_u64((unsigned long long *)&st.hist_cur[cell].sum, ms);
+						atomicOr(st.bm_cur + cell, bits);
+						if (cL == clast0) atomicMax(&bminmax[slot0].y, vmax);
+						if (cF == cfirst0) atomicMin(&bminmax[slot0].x, vmin);
+					}
+				}
+			}
+			if (uniform) continue;
+		}
+
+		// own samples -> runs of equal (service, cluster, bucket). Sample t carries the totals of its run so far; only the last
+		// sample of a run (its tail) is emitted. Everything is indexed statically (registers).
 		unsigned long long pg[TDS_V];		// (slot * TD_CAP + cluster) << 4 | bucket
 		unsigned long long ps[TDS_V];		// usec sum
 		uint32_t pc[TDS_V], pm[TDS_V], pb[TDS_V];	// samples, msec sum, CONN_BITMAP bits
 		bool tail[TDS_V];
-		uint32_t cslot = 0xFFFFFFFFu, cstart = 0, cnn = 0, clo = 1, chi = 0, cj = 0;	// cached lookup of the previous sample
+		uint32_t cslot = 0xFFFFFFFFu, cstart = 0, cnn = 0, clo = 1, chi = 0, cj = 0, cfirst = 0, clast = 0;	// cached lookup of the previous sample
 #pragma unroll
 		for (int t = 0; t < TDS_V; ++t) {
 			const bool valid = kk[t] != KEY_SENTINEL;
@@ -869,13 +955,21 @@ __global__ void __launch_bounds__(256) td_sums_kernel(DevState st, const unsigne
 			pg[t] = 0xFFFFFFFFFFFFFF00ull + lane; ps[t] = 0; pc[t] = 0; pm[t] = 0; pb[t] = 0;
 			if (!valid) continue;
 			const uint32_t slot = key_slot(kk[t]), v = key_usec(kk[t]), bit = 1u << ((uint32_t)kk[t] & 0x1Fu);
-			if (slot != cslot) { cslot = slot; cstart = seg_start[slot]; cnn = plan_n[slot]; clo = 1; chi = 0; }
+			if (slot != cslot) {
+				cslot = slot; clo = 1; chi = 0;
+				if (slot == slot0) { cstart = sstart0; cfirst = cfirst0; clast = clast0; }
+				else { cstart = seg_start[slot]; cfirst = td_code(key_usec(keys[cstart])); clast = td_code(key_usec(keys[seg_end[slot] - 1])); }
+				cnn = plan_n[slot];
+			}
 			const uint32_t r = (uint32_t)(i0 + t - cstart);
 			uint32_t j;
 			if (cnn & 0x80000000u) j = r;
 			else if (slot == slot0 && r >= lo0 && r < hi0) j = j0;
 			else if (r >= clo && r < chi) j = cj;
 			else { cj = td_cluster_of(plan_bounds + (size_t)slot * PLAN_STRIDE, cnn, r, clo, chi); j = cj; }
+			const uint32_t code = td_code(v);
+			if (code == clast) atomicMax(&bminmax[slot].y, v);
+			if (code == cfirst) atomicMin(&bminmax[slot].x, v);
 			const uint32_t ms = v / 1000u;			// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678)
 			pg[t] = ((unsigned long long)(slot * (uint32_t)TD_CAP + j) << 4) | (uint32_t)bucket_resp_time((long long)ms);
 			ps[t] = v; pc[t] = 1; pm[t] = ms; pb[t] = bit;
@@ -885,34 +979,24 @@ __global__ void __launch_bounds__(256) td_sums_kernel(DevState st, const unsigne
 			}
 		}
 
-		// emit the run tails: round t handles every lane's run ending at its sample t; inside a hot service the only tail of a
-		// lane is its last sample and the whole warp forms one group
+		// emit the run tails: round t handles every lane's run ending at its sample t
 #pragma unroll
 		for (int t = 0; t < TDS_V; ++t) {
 			const bool act = tail[t];
 			if (!__any_sync(0xffffffffu, act)) continue;
 			const unsigned long long gid = act ? pg[t] : (0xFFFFFFFFFFFFFF00ull + lane);
-			const unsigned long long v = act ? ps[t] : 0ull;		// < 2^32
+			const unsigned long long v = act ? ps[t] : 0ull;		// < 2^34
 			uint32_t cnt = act ? pc[t] : 0u, msum = act ? pm[t] : 0u, bits = act ? pb[t] : 0u;	// msum <= 4e6 per lane
 			const uint32_t m = __match_any_sync(0xffffffffu, gid);
 			unsigned long long gsum = v;
-			if (m == 0xffffffffu) {
-				gsum = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)v & 0xFFFFu) +
-						((unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)(v >> 16)) << 16);
-				cnt = __reduce_add_sync(0xffffffffu, cnt);
-				msum = __reduce_add_sync(0xffffffffu, msum);
-				bits = __reduce_or_sync(0xffffffffu, bits);
-			}
-			else {
-				const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(m));
-				uint32_t rest = m & ~(1u << lane);
-				const uint32_t cnt0 = cnt, msum0 = msum, bits0 = bits;
-				for (uint32_t u = 1; u < maxcnt; ++u) {
-					const int src = rest ? (__ffs(rest) - 1) : lane;
-					const unsigned long long ov = __shfl_sync(0xffffffffu, v, src);
-					const uint32_t oc = __shfl_sync(0xffffffffu, cnt0, src), om = __shfl_sync(0xffffffffu, msum0, src), ob = __shfl_sync(0xffffffffu, bits0, src);
-					if (rest) { gsum += ov; cnt += oc; msum += om; bits |= ob; rest &= rest - 1; }
-				}
+			const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(m));
+			uint32_t rest = m & ~(1u << lane);
+			const uint32_t cnt0 = cnt, msum0 = msum, bits0 = bits;
+			for (uint32_t u = 1; u < maxcnt; ++u) {
+				const int src = rest ? (__ffs(rest) - 1) : lane;
+				const unsigned long long ov = __shfl_sync(0xffffffffu, v, src);
+				const uint32_t oc = __shfl_sync(0xffffffffu, cnt0, src), om = __shfl_sync(0xffffffffu, msum0, src), ob = __shfl_sync(0xffffffffu, bits0, src);
+				if (rest) { gsum += ov; cnt += oc; msum += om; bits |= ob; rest &= rest - 1; }
 			}
 			if (act && (m & ((1u << lane) - 1u)) == 0) {
 				const uint32_t cj2 = (uint32_t)(gid >> 4);			// slot * TD_CAP + cluster
@@ -928,38 +1012,38 @@ __global__ void __launch_bounds__(256) td_sums_kernel(DevState st, const unsigne
 
 // (3) merge: one warp per touched service turns (sums, bounds) into the new clusters, merges them with the old centroids
 // (old first on ties) and runs the greedy pass again
-__global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, const unsigned long long *__restrict__ keys,
-		const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end, const uint32_t *__restrict__ touched,
-		const unsigned long long *__restrict__ ntouched_p, const uint32_t *__restrict__ plan_bounds, const uint32_t *__restrict__ plan_n,
-		const unsigned long long *__restrict__ newsum)
+__global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end,
+		const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p, const uint32_t *__restrict__ plan_bounds,
+		const uint32_t *__restrict__ plan_n, const unsigned long long *__restrict__ newsum, const uint2 *__restrict__ bminmax,
+		Centroid *__restrict__ newc_scratch /* [gridDim.x * TD_WARPS][TD_CAP] */)
 {
-	__shared__ TdScratch scratch[TD_WARPS];
+	__shared__ TdWork work[TD_WARPS];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	TdScratch &S = scratch[wid];
+	TdWork &S = work[wid];
+	Centroid *newc = newc_scratch + (size_t)(blockIdx.x * TD_WARPS + wid) * TD_CAP;		// this warp's list of new clusters (L2-resident)
 	const uint32_t ntouched = (uint32_t)*ntouched_p;
 	const uint32_t nwarps = gridDim.x * TD_WARPS;
 	for (uint32_t t = blockIdx.x * TD_WARPS + wid; t < ntouched; t += nwarps) {
 		const uint32_t slot = touched[t];
-		const uint32_t s0 = seg_start[slot];
-		const uint32_t n = seg_end[slot] - s0;
+		const uint32_t n = seg_end[slot] - seg_start[slot];
 		const uint32_t nnew = plan_n[slot] & 0x7FFFFFFFu;
 		const uint32_t *bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
 		const unsigned long long *sums = newsum + (size_t)slot * TD_CAP;
 
 		for (uint32_t j = lane; j < nnew; j += 32) {
 			const uint32_t w = bounds[j + 1] - bounds[j];
-			S.newc[j].mean = __ddiv_rn((double)sums[j], (double)w);		// cluster sums are exact integers
-			S.newc[j].weight = w;
+			Centroid c; c.mean = __ddiv_rn((double)sums[j], (double)w); c.weight = w;	// cluster sums are exact integers
+			newc[j] = c;
 		}
-		const uint32_t us_max = key_usec(keys[s0 + n - 1]);
-		const double bmin = (double)key_usec(keys[s0]), bmax = (double)us_max;
-		// max_val_seen_ of GY_HISTOGRAM::add_data (gy_statistics.h:609-611): the batch maximum is the last sorted sample
-		if (lane == 0) atomicMax(&st.hist_cur[(size_t)slot * HIST_CELLS + HIST_MAX_CELL].sum, (long long)(us_max / 1000u));
+		const uint2 mm = bminmax[slot];
+		const double bmin = (double)mm.x, bmax = (double)mm.y;
+		// max_val_seen_ of GY_HISTOGRAM::add_data (gy_statistics.h:609-611)
+		if (lane == 0) atomicMax(&st.hist_cur[(size_t)slot * HIST_CELLS + HIST_MAX_CELL].sum, (long long)(mm.y / 1000u));
 		__syncwarp();
 
 		TdHead head = st.td_head[slot];
 		Centroid *cent = st.td_cent + (size_t)slot * TD_CAP;
-		const uint32_t nout = warp_merge_compress(S, cent, head.n, S.newc, nnew, cent, st.td);
+		const uint32_t nout = warp_merge_compress(S, cent, head.n, newc, nnew, cent, st.td);
 		if (lane == 0) {
 			head.n = nout;
 			head.total += n;
@@ -1047,7 +1131,7 @@ __global__ void __launch_bounds__(256) evict_kernel(DevState st, uint32_t max_sv
 		const unsigned long long id = st.evict_ids[q];
 
 		if (threadIdx.x == 0) {
-			uint32_t pos = uint64_hash(id) & st.svc_tbl.mask;
+			uint32_t pos = table_hash(id) & st.svc_tbl.mask;
 			for (uint32_t probe = 0; probe <= st.svc_tbl.mask; ++probe, pos = (pos + 1) & st.svc_tbl.mask) {
 				TblEntry *e = &st.svc_tbl.ent[pos];
 				if (e->key == id) { e->key = KEY_TOMBSTONE; e->slot1 = 0; break; }
@@ -1081,7 +1165,7 @@ __global__ void rebuild_table_kernel(DevState st, uint32_t max_svcs)
 	if (slot >= max_svcs) return;
 	const unsigned long long id = st.slot_id[slot];
 	if (!id) return;
-	uint32_t pos = uint64_hash(id) & st.svc_tbl.mask;
+	uint32_t pos = table_hash(id) & st.svc_tbl.mask;
 	for (;;) {
 		const unsigned long long k = atomicCAS(&st.svc_tbl.ent[pos].key, 0ull, id);
 		if (k == 0) { st.svc_tbl.ent[pos].slot1 = slot + 1; return; }
@@ -1188,6 +1272,11 @@ __global__ void query_flows_kernel(DevState st, const unsigned long long *__rest
 // ---------------------------------------------------------------------------------------------------
 static inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute is per DEVICE: one process may own an engine on every GPU of the box
+static constexpr int MAX_DEVICES = 64;
+static int current_device() { int dev = 0; cudaGetDevice(&dev); return dev < 0 || dev >= MAX_DEVICES ? 0 : dev; }
+static int sm_count(int dev) { int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); return nsm; }
+
 int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks, cudaStream_t s)
 {
 	const uint32_t m = max_svcs > max_tasks ? max_svcs : max_tasks;
@@ -1202,51 +1291,65 @@ int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_
 	return 1;
 }
 
-// GYSK_INGEST_VARIANT selects a CTA shape of the tile pipeline for A/B runs: 256 (default, measured best) / 128 / 2563 (TMA-staged
-// tiles) / 2562 / 2568 (2 / 8 events per thread)
+// the radix passes of the RESP keys: sort word = {slot | code}, TD_CODE_BITS + slot bits significant bits cut into the fewest
+// digits of at most 9 bits, widths as even as possible (27 bits -> 9 9 9; 30 bits -> 8 8 7 7)
+int vk_sort_plan(uint32_t max_svcs, int shift[OS_MAX_PASSES_VK], int bits[OS_MAX_PASSES_VK])
+{
+	int slot_bits = 1;
+	while (slot_bits < 29 && (1ull << slot_bits) < max_svcs) slot_bits++;
+	const int T = TD_CODE_BITS + slot_bits;
+	const int np = (T + RADIX_MAX_BITS - 1) / RADIX_MAX_BITS;
+	if (np > OS_MAX_PASSES_VK) return -1;
+	int at = 0;
+	for (int p = 0; p < np; ++p) { bits[p] = T / np + (p < T % np ? 1 : 0); shift[p] = at; at += bits[p]; }
+	return np;
+}
+
+// GYSK_INGEST_VARIANT selects a shape of the warp-autonomous ingest kernel for A/B runs
 static int ingest_variant()
 {
-	static const int v = []{ const char *e = getenv("GYSK_INGEST_VARIANT"); return e ? atoi(e) : 2562; }();
+	static const int v = []{ const char *e = getenv("GYSK_INGEST_VARIANT"); return e ? atoi(e) : 0; }();
 	return v;
 }
 
-template <int THREADS, int MIN_CTAS, bool STAGE, int EPT = 4, bool PIPE = false>
-static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, int nsm, cudaStream_t s)
+template <int WARPS, int MIN_CTAS, int EPT, bool TMA>
+static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, uint32_t *ghist, const SortPlan &plan,
+		int dev, cudaStream_t s)
 {
-	using Shared = IngestSharedT<THREADS, STAGE, EPT>;
-	static bool attr_set = false;
-	if (!attr_set) { cudaFuncSetAttribute(ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)); attr_set = true; }
-	const uint64_t want = (n + Shared::INGEST_TILE - 1) / Shared::INGEST_TILE;
-	const uint32_t grid = (uint32_t)(want < (uint64_t)nsm * MIN_CTAS ? want : (uint64_t)nsm * MIN_CTAS);
-	// A/B switch (measured: L2 prefetch of the CTA's next tile costs more issue slots than the latency it hides: 2.58 -> 2.78 ms)
-	static const int prefetch_next = []{ const char *e = getenv("GYSK_INGEST_PREFETCH"); return e ? atoi(e) : 0; }();
-	ingest_kernel<THREADS, MIN_CTAS, STAGE, EPT, PIPE><<<grid, THREADS, sizeof(Shared), s>>>(st, d_ev, n, d_keys, prefetch_next);
+	using Shared = IngestSharedT<WARPS, EPT, TMA>;
+	static bool attr_set[MAX_DEVICES] = {};
+	if (!attr_set[dev]) {
+		cudaFuncSetAttribute(ingest_kernel<WARPS, MIN_CTAS, EPT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+		attr_set[dev] = true;
+	}
+	const uint64_t want = (n + (uint64_t)Shared::CHUNK * WARPS - 1) / ((uint64_t)Shared::CHUNK * WARPS);
+	const uint64_t full = (uint64_t)sm_count(dev) * MIN_CTAS;
+	ingest_kernel<WARPS, MIN_CTAS, EPT, TMA><<<(uint32_t)(want < full ? want : full), WARPS * 32, sizeof(Shared), s>>>(st, d_ev, n, d_keys, ghist, plan);
 }
 
-int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, cudaStream_t s)
+int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_ev, uint64_t n, uint32_t max_svcs, cudaStream_t s)
 {
 	if (!n) return 0;
-	int dev = 0, nsm = 148;
-	cudaGetDevice(&dev);
-	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-	// variants for A/B runs (GYSK_INGEST_VARIANT): 256 = 256 thr x 4 CTAs/SM, events by direct streaming loads (measured best so
-	// far); 2563 = same shape, next tile staged by TMA bulk copy (3 CTAs/SM: +32 KB smem); 128 = 128 thr x 8 CTAs/SM
-	static const int variant = ingest_variant();
-	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, 2 * sizeof(unsigned long long), s);	// key cursor + max RESP msec of this batch
-	if (variant == 2563) launch_ingest_variant<256, 3, true>(st, d_ev, n, d_keys, nsm, s);
-	else if (variant == 128) launch_ingest_variant<128, 8, false>(st, d_ev, n, d_keys, nsm, s);
-	else if (variant == 2562) launch_ingest_variant<256, 5, false, 2>(st, d_ev, n, d_keys, nsm, s);	// 2 events per thread: fewer live registers, 5 CTAs/SM
-	else if (variant == 2568) launch_ingest_variant<256, 3, false, 8>(st, d_ev, n, d_keys, nsm, s);	// 8 events per thread: fewer barriers per event
-	else if (variant == 2662) launch_ingest_variant<256, 6, false, 2>(st, d_ev, n, d_keys, nsm, s);
-	else if (variant == 25620) launch_ingest_variant<256, 5, false, 2, true>(st, d_ev, n, d_keys, nsm, s);	// next tile's loads issued before the barrier (measured: 2.74 vs 2.61 ms)
-	else if (variant == 256) launch_ingest_variant<256, 4, false>(st, d_ev, n, d_keys, nsm, s);
-	else launch_ingest_variant<256, 5, false, 2>(st, d_ev, n, d_keys, nsm, s);
+	const int dev = current_device();
+	SortPlan plan {};
+	plan.np = vk_sort_plan(max_svcs, plan.shift, plan.bits);
+	// key cursor, digit histograms and tile tickets of this batch's sort
+	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, sizeof(unsigned long long), s);
+	cudaMemsetAsync(tmp.os_ghist, 0, (OS_MAX_PASSES * RADIX_MAX + OS_MAX_PASSES) * sizeof(uint32_t), s);
+	switch (ingest_variant()) {
+	case 842 : launch_ingest_variant<8, 4, 2, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
+	case 834 : launch_ingest_variant<8, 3, 4, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
+	case 832 : launch_ingest_variant<8, 3, 2, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
+	case 442 : launch_ingest_variant<4, 8, 2, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
+	case 1832 : launch_ingest_variant<8, 3, 2, true>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;	// TMA-staged chunks
+	case 1834 : launch_ingest_variant<8, 2, 4, true>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
+	default : launch_ingest_variant<8, 4, 2, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
+	}
 	return 1;
 }
 
-// stable LSD radix sort of the n keys in bufs[0] on the significant key bits [lo1, hi1) then [lo2, hi2) (lo2 >= hi1; pass
-// hi2 <= lo2 for a single range): the significant bits are cut into digits in order, a digit may straddle the gap. Digits are
-// 8 bits wide unless 9-bit digits save a whole pass (41-45 significant bits: 5 passes instead of 6). Result in bufs[*which].
+// plain-key digit plan: the significant bits [lo1, hi1) then [lo2, hi2) (lo2 >= hi1; hi2 <= lo2 for a single range) cut into
+// digits in order, a digit may straddle the gap. Digits are 8 bits wide unless 9-bit digits save a whole pass.
 static int build_digit_specs(int lo1, int hi1, int lo2, int hi2, DigitSpecs &P)
 {
 	int p1 = lo1, p2 = lo2;			// next unsorted bit of each range
@@ -1280,7 +1383,33 @@ int radix_sort_plan(int lo1, int hi1, int lo2, int hi2, int out[][4], int cap)
 	return P.np;
 }
 
-int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, int lo2, int hi2, int *which, cudaStream_t s)
+static void os_set_attrs(int dev)
+{
+	static bool attr_set[MAX_DEVICES] = {};
+	if (attr_set[dev]) return;
+	cudaFuncSetAttribute(os_pass_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<8>));
+	cudaFuncSetAttribute(os_pass_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<9>));
+	cudaFuncSetAttribute(os_pass_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<8>));
+	cudaFuncSetAttribute(os_pass_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<9>));
+	cudaFuncSetAttribute(os_hist_kernel<8, 257>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 8 * 257 * (int)sizeof(uint32_t));
+	cudaFuncSetAttribute(os_hist_kernel<4, 513>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 4 * 513 * (int)sizeof(uint32_t));
+	attr_set[dev] = true;
+}
+
+static uint32_t next_epoch(const SortTemp &tmp, uint32_t max_tiles, cudaStream_t s)
+{
+	uint32_t e = ++*tmp.epoch;
+	if (e == 0) {		// 2^32 passes later: stale words could pass for current ones, start over
+		cudaMemsetAsync(tmp.tile_status, 0, (size_t)max_tiles * RADIX_MAX * sizeof(unsigned long long), s);
+		e = ++*tmp.epoch;
+	}
+	return e;
+}
+
+static const int g_rank_mode = []{ const char *e = getenv("GYSK_OS_RANK"); return e ? atoi(e) : 0; }();
+
+// stable LSD radix sort of the *d_n keys in keys_a on their own bits (plain mode, the top-N sorts): n_max >= *d_n sizes the grids
+int launch_radix_sort(const SortTemp &tmp, const unsigned long long *d_n, uint64_t n_max, int lo1, int hi1, int lo2, int hi2, int *which, cudaStream_t s)
 {
 	int launches = 0;
 	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
@@ -1288,39 +1417,26 @@ int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, in
 	DigitSpecs P;
 
 	*which = 0;
-	if (!n_keys) return 0;
-	if (build_digit_specs(lo1, hi1, lo2, hi2, P) || n_keys >= (1ull << 30)) return -1;	// status words carry 30-bit counts
+	if (!n_max) return 0;
+	if (build_digit_specs(lo1, hi1, lo2, hi2, P) || n_max >= (1ull << 30)) return -1;	// status words carry 30-bit counts
 	bool any9 = false;
 	for (int p = 0; p < P.np; ++p) any9 |= P.d[p].b1 + P.d[p].b2 > 8;
 	const int copies = any9 ? 4 : 8, stride = (any9 ? 512 : 256) + 1;
-
-	// one-sweep passes: global digit histograms of all passes from one read, then 16 B per key and pass
-	static bool attr_set = false;
-	if (!attr_set) {
-		cudaFuncSetAttribute(os_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<8>));
-		cudaFuncSetAttribute(os_pass_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<9>));
-		cudaFuncSetAttribute(os_hist_kernel<8, 257>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 8 * 257 * (int)sizeof(uint32_t));
-		cudaFuncSetAttribute(os_hist_kernel<4, 513>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 4 * 513 * (int)sizeof(uint32_t));
-		attr_set = true;
-	}
-	static const int rank_mode = []{ const char *e = getenv("GYSK_OS_RANK"); return e ? atoi(e) : 0; }();
-	const uint32_t n = (uint32_t)n_keys;
-	const uint32_t ntiles = div_up(n, SORT_TILE);
+	const int dev = current_device();
+	os_set_attrs(dev);
+	const uint32_t ntiles = div_up(n_max, SORT_TILE);
 	uint32_t *ghist = tmp.os_ghist, *tickets = tmp.os_ghist + OS_MAX_PASSES * RADIX_MAX;
-	int dev = 0, nsm = 148;
-	cudaGetDevice(&dev);
-	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 
 	cudaMemsetAsync(ghist, 0, (OS_MAX_PASSES * RADIX_MAX + OS_MAX_PASSES) * sizeof(uint32_t), s);
-	const uint32_t hgrid = std::min<uint32_t>(div_up(n, 512 * 2 * 4), (uint32_t)nsm * 3);
-	if (any9) os_hist_kernel<4, 513><<<hgrid, 512, (size_t)P.np * copies * stride * sizeof(uint32_t), s>>>(bufs[w], n, P, ghist);
-	else os_hist_kernel<8, 257><<<hgrid, 512, (size_t)P.np * copies * stride * sizeof(uint32_t), s>>>(bufs[w], n, P, ghist);
+	const uint32_t hgrid = std::min<uint32_t>(div_up(n_max, 512 * 2 * 4), (uint32_t)sm_count(dev) * 3);
+	if (any9) os_hist_kernel<4, 513><<<hgrid, 512, (size_t)P.np * copies * stride * sizeof(uint32_t), s>>>(bufs[w], d_n, P, ghist);
+	else os_hist_kernel<8, 257><<<hgrid, 512, (size_t)P.np * copies * stride * sizeof(uint32_t), s>>>(bufs[w], d_n, P, ghist);
 	launches++;
 	for (int p = 0; p < P.np; ++p) {
 		const bool nine = P.d[p].b1 + P.d[p].b2 > 8;
-		cudaMemsetAsync(tmp.tile_status, 0, (size_t)ntiles * (nine ? 512 : 256) * sizeof(uint32_t), s);
-		if (nine) os_pass_kernel<9><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, rank_mode);
-		else os_pass_kernel<8><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, rank_mode);
+		const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
+		if (nine) os_pass_kernel<9, false><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], d_n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
+		else os_pass_kernel<8, false><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], d_n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
 		launches++;
 		w ^= 1;
 	}
@@ -1328,38 +1444,45 @@ int launch_radix_sort(const SortTemp &tmp, uint64_t n_keys, int lo1, int hi1, in
 	return launches;
 }
 
-// sort the (slot, usec) keys produced by ingest, then fold every touched service's new samples into its digest
-int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n, uint32_t nslots, int value_bits, cudaStream_t s)
+// sort the keys ingest_kernel emitted by (slot, code), then fold every touched service's new samples into its histogram cells
+// and its digest. Nothing here needs a number from the device on the host: the key count lives in st.counters[CTR_NKEYS], the
+// digit histograms in tmp.os_ghist (both written by ingest_kernel); grids are sized by n_events, the largest possible key count.
+int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_events, uint32_t max_svcs, cudaStream_t s)
 {
-	if (!n) return 0;		// n = number of RESP keys of this batch (read back by the host), nslots = services registered so far
+	if (!n_events) return 0;
+	if (n_events >= (1ull << 30)) return -1;
 	int launches = 0;
-	const uint32_t ntiles = div_up(n, SORT_TILE);
 	unsigned long long *d_nkeys = st.counters + CTR_NKEYS, *d_ntouched = st.counters + CTR_NTOUCHED;
+	const int dev = current_device();
+	const int nsm = sm_count(dev);
+	os_set_attrs(dev);
 
-	// radix passes cover only the bits that can differ: usec bits of the batch maximum, then the slot bits in use
-	uint32_t slot_bits = 1;
-	while (slot_bits < 32 && (1ull << slot_bits) < nslots) slot_bits++;
-
-	const unsigned long long *src = tmp.keys_a;
+	SortPlan plan {};
+	plan.np = vk_sort_plan(max_svcs, plan.shift, plan.bits);
+	if (plan.np < 0) return -1;
+	const uint32_t ntiles = div_up(n_events, SORT_TILE);
 	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
-	int which = 0;
+	uint32_t *ghist = tmp.os_ghist, *tickets = tmp.os_ghist + OS_MAX_PASSES * RADIX_MAX;
+	int w = 0;
+
+	for (int p = 0; p < plan.np; ++p) {
+		const DigitSpec D { plan.shift[p], plan.bits[p], 0, 0 };
+		const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
+		if (plan.bits[p] > 8) os_pass_kernel<9, true><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], d_nkeys, D, ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
+		else os_pass_kernel<8, true><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], d_nkeys, D, ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
+		launches++;
+		w ^= 1;
+	}
+	const unsigned long long *src = bufs[w];
 
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
-
-	// with the warp-autonomous ingest the keys sit at their events' positions with sentinels in between: the first pass reads
-	// n_events slots and compacts, the later passes run over the n keys
-	const int sorted = launch_radix_sort(tmp, n, KEY_VALUE_SHIFT, KEY_VALUE_SHIFT + value_bits, KEY_SLOT_SHIFT, KEY_SLOT_SHIFT + (int)slot_bits, &which, s);
-	if (sorted < 0) return sorted;
-	launches += sorted;
-	src = bufs[which];
-
-	td_segments_kernel<<<div_up(n, 256 * TSEG_V), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched);
-	int dev = 0, nsm = 148;
-	cudaGetDevice(&dev);
-	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-	td_plan_kernel<<<nsm * 2, 128, 0, s>>>(st.td, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
-	td_sums_kernel<<<nsm * 8, 256, 0, s>>>(st, src, d_nkeys, tmp.seg_start, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
-	td_merge_kernel<<<nsm * 7, TD_WARPS * 32, 0, s>>>(st, src, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n, tmp.newsum);
+	cudaMemsetAsync(tmp.runbits2, 0, ((size_t)(n_events >> 15) + 1) * sizeof(uint32_t), s);
+	td_segments_kernel<<<div_up(n_events, 256 * TSEG_V), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.runbits, tmp.runbits2);
+	td_plan_kernel<<<nsm * 2, 128, 0, s>>>(st.td, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.runbits, tmp.runbits2, tmp.plan_bounds, tmp.plan_n,
+			tmp.newsum, tmp.bminmax);
+	td_sums_kernel<<<nsm * 8, 256, 0, s>>>(st, src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.plan_bounds, tmp.plan_n, tmp.newsum, tmp.bminmax);
+	td_merge_kernel<<<nsm * TD_MERGE_CTAS_PER_SM, TD_WARPS * 32, 0, s>>>(st, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n,
+			tmp.newsum, tmp.bminmax, tmp.newc_scratch);
 	return launches + 4;
 }
 
@@ -1405,7 +1528,7 @@ int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int me
 	unsigned long long *d_n = st.counters + CTR_NKEYS;
 	int which = 0, launches = 2;
 	topn_score_kernel<<<div_up(nslots, 256), 256, 0, s>>>(st, nslots, metric, host_filter, tmp.keys_a, d_n);
-	const int sorted = launch_radix_sort(tmp, nslots, 32, 64, 64, 64, &which, s);
+	const int sorted = launch_radix_sort(tmp, d_n, nslots, 32, 64, 64, 64, &which, s);
 	if (sorted < 0) return sorted;
 	launches += sorted;
 	topn_pick_kernel<<<1, 64, 0, s>>>(st, which ? tmp.keys_b : tmp.keys_a, nslots, want, d_out);
@@ -1433,9 +1556,10 @@ int launch_task_flush(const DevState &st, uint32_t max_tasks, cudaStream_t s)
 
 // top-N aggregated processes of the last closed window by cpu / cpu delay / blkio delay: the atask_top_cpu_ / _cpu_delay_ /
 // _io_delay_ queues of partha_aggr_task_state (server/gy_mconnhdlr.cc:10020-10065; entries with a zero metric never enter)
-__global__ void topn_task_score_kernel(DevState st, uint32_t ntasks, int metric, unsigned long long *__restrict__ keys)
+__global__ void topn_task_score_kernel(DevState st, uint32_t ntasks, int metric, unsigned long long *__restrict__ keys, unsigned long long *d_n)
 {
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot == 0) *d_n = ntasks;
 	if (slot >= ntasks) return;
 	unsigned long long score = st.task_slot_id[slot] ? (unsigned long long)st.task_last[(size_t)slot * 3 + metric].sum : 0ull;
 	if ((long long)score < 0) score = 0;
@@ -1460,8 +1584,9 @@ int launch_topn_tasks(const DevState &st, const SortTemp &tmp, uint32_t ntasks, 
 {
 	if (!ntasks) return 0;
 	int which = 0, launches = 2;
-	topn_task_score_kernel<<<div_up(ntasks, 256), 256, 0, s>>>(st, ntasks, metric, tmp.keys_a);
-	const int sorted = launch_radix_sort(tmp, ntasks, 32, 64, 64, 64, &which, s);
+	unsigned long long *d_n = st.counters + CTR_NKEYS;
+	topn_task_score_kernel<<<div_up(ntasks, 256), 256, 0, s>>>(st, ntasks, metric, tmp.keys_a, d_n);
+	const int sorted = launch_radix_sort(tmp, d_n, ntasks, 32, 64, 64, 64, &which, s);
 	if (sorted < 0) return sorted;
 	launches += sorted;
 	topn_task_pick_kernel<<<1, 64, 0, s>>>(st, which ? tmp.keys_b : tmp.keys_a, ntasks, want, d_out);

@@ -106,6 +106,10 @@ struct alignas(8) AGGR_TASK_STATE_NOTIFY				// common/gy_comm_proto.h:2114-2169
 };
 static_assert(sizeof(AGGR_TASK_STATE_NOTIFY) == 72 && offsetof(AGGR_TASK_STATE_NOTIFY, padding_len_) == 69, "AGGR_TASK_STATE_NOTIFY");
 
+static constexpr uint8_t LISTEN_FLAG_DELETE = (1 << 7) | (1 << 6);		// LISTENER_QUERY_FLAGS, common/gy_comm_proto.h:2180
+// OBJ_STATE_E, common/gy_json_field_maps.h:242-251
+enum : uint8_t { STATE_IDLE = 0, STATE_GOOD = 1, STATE_OK = 2, STATE_BAD = 3, STATE_SEVERE = 4, STATE_DOWN = 5 };
+
 struct alignas(8) LISTENER_STATE_NOTIFY					// common/gy_comm_proto.h:2183-2254
 {
 	uint64_t	glob_id_;

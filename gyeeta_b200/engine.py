@@ -18,7 +18,7 @@ HIST_RESP_CUR, HIST_RESP_LAST, HIST_RESP_ALL, HIST_TASK_CPU_PCT, HIST_TASK_CPU_D
 RAW_EVENT32, RAW_TCP_IPV4_EVENT, RAW_TCP_IPV4_RESP = 0, 1, 2
 NOTIFY_LISTENER_STATE, NOTIFY_TCP_CONN, NOTIFY_AGGR_TASK_STATE = 0x309, 0x30C, 0x310
 FLAG_AUTO_REGISTER = 1
-TD_CAP = 128
+TD_CAP = 256
 
 
 class GyskError(RuntimeError):
@@ -154,7 +154,7 @@ class Engine:
     """One engine = one GPU. Mirrors the C ABI one to one."""
 
     def __init__(self, device=0, max_svcs=1 << 14, max_tasks=1 << 12, cms_depth=4, cms_log2_width=20, hll_p=12,
-                 td_compression=100, max_batch=1 << 20, auto_register=True, rank=0, world=1, stage_batch=0, idle_evict_secs=0):
+                 td_compression=200, max_batch=1 << 20, auto_register=True, rank=0, world=1, stage_batch=0, idle_evict_secs=0):
         self.L = load_library()
         cfg = Config()
         self.L.gysk_config_default(C.byref(cfg))

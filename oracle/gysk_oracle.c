@@ -262,14 +262,26 @@ int gyo_hist_run(int cls, int tkind, const int64_t *vals, size_t n, const float 
  * count-min and HyperLogLog definitions (ours; PARITY UNPINNED — no reference implementation exists)
  * hash family: the reference's jhash_2words over the two halves of the key with row-salted initval
  * ------------------------------------------------------------------------------------------------ */
-#define HLL_SEED_A	(GY_SEED ^ 0xa5a5a5a5u)
-#define HLL_SEED_B	(GY_SEED ^ 0x5a5a5a5au)
+#define FLOW_SEED_A	GY_SEED
+#define FLOW_SEED_B	(GY_SEED ^ 0x5bd1e995u)
+
+/* Two lookup2 words per flow key: h1 = jhash_2words(lo, hi, SEED_A), h2 = jhash_2words(lo, hi, SEED_B). Count-min row r indexes
+ * (h1 + r * (h2 | 1)) & (width - 1) (Kirsch & Mitzenmacher double hashing: the d row hashes of a sketch may be linear
+ * combinations of two independent hashes without changing the error bound); HyperLogLog takes the 64-bit word h2:h1. */
+void gyo_flow_hashes(uint64_t flow_key, uint32_t *h1, uint32_t *h2)
+{
+	uint32_t lo = (uint32_t)flow_key, hi = (uint32_t)(flow_key >> 32);
+
+	*h1 = gyo_jhash_2words(lo, hi, FLOW_SEED_A);
+	*h2 = gyo_jhash_2words(lo, hi, FLOW_SEED_B);
+}
 
 uint32_t gyo_cms_index(uint64_t flow_key, uint32_t row, uint32_t log2_width)
 {
-	uint32_t h = gyo_jhash_2words((uint32_t)flow_key, (uint32_t)(flow_key >> 32), GY_SEED + GOLDEN * (row + 1));
+	uint32_t h1, h2;
 
-	return h & ((1u << log2_width) - 1);
+	gyo_flow_hashes(flow_key, &h1, &h2);
+	return (h1 + row * (h2 | 1u)) & ((1u << log2_width) - 1);
 }
 
 /* one 64-bit cell = {count: low 32, kbytes: high 32}; a single 64-bit add updates both. The count half
@@ -281,9 +293,10 @@ uint64_t gyo_cms_increment(uint32_t bytes)
 
 uint64_t gyo_hll_hash(uint64_t flow_key)
 {
-	uint32_t lo = (uint32_t)flow_key, hi = (uint32_t)(flow_key >> 32);
+	uint32_t h1, h2;
 
-	return ((uint64_t)gyo_jhash_2words(lo, hi, HLL_SEED_A) << 32) | gyo_jhash_2words(lo, hi, HLL_SEED_B);
+	gyo_flow_hashes(flow_key, &h1, &h2);
+	return ((uint64_t)h2 << 32) | h1;
 }
 
 void gyo_hll_idx_rank(uint64_t flow_key, uint32_t p, uint32_t *idx, uint8_t *rank)
@@ -318,30 +331,48 @@ double gyo_hll_estimate(const uint8_t *regs, uint32_t p)
 /* ------------------------------------------------------------------------------------------------
  * t-digest (PARITY UNPINNED). Published algorithm: T. Dunning, "The t-digest: efficient estimates of
  * distributions" — merging variant, scale function K_1 normalised so that k spans [-delta/2, delta/2]:
- * k(q) = delta/pi asin(2q - 1), i.e. about delta centroids — the meaning "100" has for both t-digest users of the
- * reference (Postgres public.tdigest(x, 100), common/gy_query_common.cc:1855; folly::TDigest(100) behind
- * SlidingWindowQuantileEstimator, test/test_quantiles.cc:32).
+ * k(q) = delta/pi asin(2q - 1), i.e. delta ... 1.3 delta centroids. The reference's two t-digest users pin "100"
+ * (Postgres public.tdigest(x, 100), common/gy_query_common.cc:1855; folly::TDigest(100) behind
+ * SlidingWindowQuantileEstimator, test/test_quantiles.cc:32); the engine keeps delta = 200 internally (capacity 256)
+ * because SURVEY.md §8c-4 asks for p99 within 1 % of the EXACT quantile on sigma 1.2-1.5 log-normal streams, which a
+ * 100-centroid K_1 digest misses by 1-3 % (interpolation error ~ 1/delta^2), and recompresses to 100 on export.
  * ------------------------------------------------------------------------------------------------ */
 /* Upper end q1 of the unit-k interval that starts at q0: q1 = q(k(q0) + 1) with k(q) = delta/pi asin(2q - 1), written without
  * inverse trig: with theta = asin(2 q0 - 1), sin(theta + pi/delta) = (2 q0 - 1) cos(pi/delta) + 2 sqrt(q0 (1 - q0)) sin(pi/delta).
  * Only IEEE +,-,*,/ and sqrt, each rounded on its own, in this order — the CUDA path performs the identical sequence, so both
  * produce the same bits. */
-static inline double td_q_next(double q0, double C, double S)
+typedef struct td_params { double C, S, qclamp; } td_params;
+
+/* A greedy pass over weighted items that cannot be split yields up to ~1.3 delta clusters. When a pass would need more than
+ * the capacity, it is repeated with the next, coarser rung of this ladder (delta * f): the tail resolution degrades by a few
+ * per cent instead of the last centroid swallowing the whole upper tail. Only the last rung keeps that guard. */
+#define TD_LADDER	6
+static const double g_td_ladder[TD_LADDER] = { 1.0, 0.92, 0.85, 0.78, 0.72, 0.66 };
+
+static void td_make_ladder(double delta, td_params P[TD_LADDER])
 {
-	if (q0 >= (1.0 + C) / 2.0) return 1.0;			/* k(q0) + 1 >= delta/2 */
-	double t = 2.0 * q0 - 1.0;
-	double r = sqrt(q0 * (1.0 - q0));
-	double a = t * C;
-	double b = (2.0 * r) * S;
-	return ((a + b) + 1.0) / 2.0;
+	for (int k = 0; k < TD_LADDER; ++k) {
+		const double d = delta * g_td_ladder[k];
+
+		P[k].C = cos(M_PI / d); P[k].S = sin(M_PI / d); P[k].qclamp = (1.0 + P[k].C) / 2.0;
+	}
 }
 
-static inline double td_wlimit(uint64_t wsofar, uint64_t W, double delta)
+static inline double td_q_next(double q0, const td_params *P)
 {
-	const double C = cos(M_PI / delta), S = sin(M_PI / delta);
+	if (q0 >= P->qclamp) return 1.0;			/* k(q0) + 1 >= delta/2 */
+	double t = 2.0 * q0 - 1.0;
+	double r = sqrt(q0 * (1.0 - q0));
+	double a = t * P->C;
+	double b = (2.0 * r) * P->S;
+	return ((a + b) + 1.0) * 0.5;
+}
+
+static inline double td_wlimit(uint64_t wsofar, uint64_t W, const td_params *P)
+{
 	const double q0 = wsofar ? (double)wsofar / (double)W : 0.0;
 
-	return (double)W * td_q_next(q0, C, S);
+	return (double)W * td_q_next(q0, P);
 }
 
 void gyo_td_init(gyo_tdigest *t)
@@ -350,38 +381,53 @@ void gyo_td_init(gyo_tdigest *t)
 	t->minv = INFINITY; t->maxv = -INFINITY;
 }
 
-/* greedy pass over centroids sorted by mean. A cluster that starts after weight P absorbs items while the
- * running total stays <= W * q(k(P/W) + 1); it always takes at least its first item. Cluster mean is
- * sum(mean*weight)/sum(weight) accumulated in double in input order. */
-uint32_t gyo_td_compress(const gyo_centroid *in, uint32_t n, double delta, gyo_centroid *out, uint32_t cap)
+/* One greedy pass over centroids sorted by mean. A cluster that starts after weight P absorbs items while the running total
+ * stays <= W * q(k(P/W) + 1); it always takes at least its first item. Cluster mean is sum(mean*weight)/sum(weight)
+ * accumulated in double in input order. Returns the number of clusters, or cap + 1 when more than cap would be needed
+ * (final: the last slot absorbs whatever is left instead). */
+static uint32_t td_compress_once(const gyo_centroid *in, uint32_t n, const td_params *P, gyo_centroid *out, uint32_t cap, int final)
 {
 	uint64_t W = 0, wsofar = 0, cw;
 	uint32_t nout = 0;
 	double csum, wlimit;
 
-	if (!n) return 0;
 	for (uint32_t i = 0; i < n; ++i) W += in[i].weight;
 
-	wlimit = td_wlimit(0, W, delta);
+	wlimit = td_wlimit(0, W, P);
 	cw = in[0].weight; csum = in[0].mean * (double)in[0].weight;
 
 	for (uint32_t i = 1; i < n; ++i) {
 		double projected = (double)(wsofar + cw + in[i].weight);
 
-		if (projected <= wlimit || nout + 1 == cap) {		/* the last slot absorbs whatever is left */
+		if (projected <= wlimit || (final && nout + 1 == cap)) {
 			cw += in[i].weight;
 			csum += in[i].mean * (double)in[i].weight;
 		}
 		else {
-			if (nout < cap) { out[nout].mean = csum / (double)cw; out[nout].weight = cw; }
+			if (nout + 1 >= cap && !final) return cap + 1;	/* this cluster is number cap, and another one follows */
+			out[nout].mean = csum / (double)cw; out[nout].weight = cw;
 			nout++;
 			wsofar += cw;
-			wlimit = td_wlimit(wsofar, W, delta);
+			wlimit = td_wlimit(wsofar, W, P);
 			cw = in[i].weight; csum = in[i].mean * (double)in[i].weight;
 		}
 	}
-	if (nout < cap) { out[nout].mean = csum / (double)cw; out[nout].weight = cw; }
+	out[nout].mean = csum / (double)cw; out[nout].weight = cw;
 	nout++;
+	return nout;
+}
+
+uint32_t gyo_td_compress(const gyo_centroid *in, uint32_t n, double delta, gyo_centroid *out, uint32_t cap)
+{
+	td_params P[TD_LADDER];
+	uint32_t nout = 0;
+
+	if (!n) return 0;
+	td_make_ladder(delta, P);
+	for (int k = 0; k < TD_LADDER; ++k) {
+		nout = td_compress_once(in, n, &P[k], out, cap, k == TD_LADDER - 1);
+		if (nout <= cap) break;
+	}
 	return nout;
 }
 
@@ -402,38 +448,73 @@ static uint32_t merge_sorted(const gyo_centroid *a, uint32_t na, const gyo_centr
 	return k;
 }
 
-/* What the CUDA path does for one device batch: (1) sort the service's new samples, cluster them with the greedy
- * rule (unit weights; cluster sums are exact integers), (2) merge new clusters with the old centroids and
- * compress again. */
+/* Log-linear value code: 32 bins per octave (5 mantissa bits), exact below 32. Monotone in v; < 1024 for v < 2^30.
+ * The CUDA path sorts a batch's samples by (service, code) only — 27 instead of 47 significant key bits — so the samples
+ * inside one bin arrive in no particular order and a bin is the unit the batch clustering works with. */
+uint32_t gyo_td_code(uint32_t v)
+{
+	if (v < 32u) return v;
+	uint32_t sh = (31u - (uint32_t)__builtin_clz(v)) - 5u;
+
+	return ((sh + 1u) << 5) | ((v >> sh) & 31u);
+}
+
+/* What the CUDA path does for one device batch and service:
+ * (1) the n new samples, ordered by code, are cut into clusters by the greedy rule over unit weights, except that a cluster
+ *     never splits a bin: a cluster that starts at rank s (a bin boundary) ends at the last bin boundary <= floor(n q(k(s/n) + 1)),
+ *     or at the end of its first bin when that lies beyond. Cluster sums are exact integers, so the result does not depend
+ *     on the order of the samples inside a bin;
+ * (2) the new clusters are merged with the old centroids (old first on equal means) and compressed again. */
 void gyo_td_add_batch(gyo_tdigest *t, const uint32_t *vals, uint32_t n, double delta)
 {
 	if (!n) return;
 
 	uint32_t	*sv = (uint32_t *)malloc(sizeof(uint32_t) * n);
-	gyo_centroid	newc[GYO_TD_CAP], merged[2 * GYO_TD_CAP], outc[GYO_TD_CAP];
-	uint32_t	nnew = 0, s = 0;
+	uint32_t	*rstart = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n + 1));	/* rank -> start of the bin it lies in */
+	uint32_t	bounds[GYO_TD_CAP + 1];
+	gyo_centroid	newc[GYO_TD_CAP], merged[2 * GYO_TD_CAP];
+	gyo_centroid	outc[GYO_TD_CAP + 1];
+	td_params	P[TD_LADDER];
+	uint32_t	nnew = 0;
 
 	memcpy(sv, vals, sizeof(uint32_t) * n);
 	qsort(sv, n, sizeof(uint32_t), cmp_u32);
+	for (uint32_t i = 0; i < n; ++i) rstart[i] = (i && gyo_td_code(sv[i]) == gyo_td_code(sv[i - 1])) ? rstart[i - 1] : i;
+	rstart[n] = n;
 
-	/* greedy clustering of n unit weights: cluster [s, e), e = max(s + 1, floor(W q(k(s/W) + 1))) */
-	while (s < n) {
-		double wlimit = td_wlimit(s, n, delta);
-		uint64_t e = (uint64_t)floor(wlimit);
+	td_make_ladder(delta, P);
+	for (int k = 0; k < TD_LADDER; ++k) {
+		const int final = k == TD_LADDER - 1;
+		uint32_t s = 0;
+		int overflow = 0;
+
+		nnew = 0;
+		while (s < n) {
+			double wlimit = td_wlimit(s, n, &P[k]);
+			uint64_t x = (uint64_t)floor(wlimit);
+			uint32_t e;
+
+			if (x > n) x = n;
+			e = rstart[x];					/* last bin boundary <= x */
+			if (e <= s) { e = s + 1; while (e < n && rstart[e] != e) ++e; }	/* at least the first bin */
+			if (final && nnew == GYO_TD_CAP - 1) e = n;		/* the last slot absorbs whatever is left */
+			if (nnew == GYO_TD_CAP) { overflow = 1; break; }
+			bounds[nnew++] = s;
+			s = e;
+		}
+		if (!overflow) break;
+	}
+	bounds[nnew] = n;
+	for (uint32_t j = 0; j < nnew; ++j) {
 		uint64_t sum = 0;
 
-		if (e > n) e = n;
-		if (e < s + 1) e = s + 1;
-		if (nnew == GYO_TD_CAP - 1) e = n;			/* the last slot absorbs whatever is left */
-		for (uint64_t i = s; i < e; ++i) sum += sv[i];
-		if (nnew < GYO_TD_CAP) { newc[nnew].mean = (double)sum / (double)(e - s); newc[nnew].weight = e - s; }
-		nnew++;
-		s = (uint32_t)e;
+		for (uint32_t i = bounds[j]; i < bounds[j + 1]; ++i) sum += sv[i];
+		newc[j].mean = (double)sum / (double)(bounds[j + 1] - bounds[j]); newc[j].weight = bounds[j + 1] - bounds[j];
 	}
 
 	if ((double)sv[0] < t->minv) t->minv = (double)sv[0];
 	if ((double)sv[n - 1] > t->maxv) t->maxv = (double)sv[n - 1];
-	free(sv);
+	free(sv); free(rstart);
 
 	uint32_t nm = merge_sorted(t->c, t->n, newc, nnew, merged);
 	uint32_t no = gyo_td_compress(merged, nm, delta, outc, GYO_TD_CAP);
@@ -451,7 +532,7 @@ void gyo_td_add_classic(gyo_tdigest *t, const uint32_t *vals, uint32_t n, double
 	gyo_centroid *buf = (gyo_centroid *)malloc(sizeof(gyo_centroid) * (bufcap + 2 * GYO_TD_CAP));
 	gyo_centroid *tmp = (gyo_centroid *)malloc(sizeof(gyo_centroid) * (bufcap + 2 * GYO_TD_CAP));
 	uint32_t *chunk = (uint32_t *)malloc(sizeof(uint32_t) * bufcap);
-	gyo_centroid outc[GYO_TD_CAP];
+	gyo_centroid outc[GYO_TD_CAP + 1];
 
 	for (uint32_t off = 0; off < n; off += bufcap) {
 		uint32_t m = n - off < bufcap ? n - off : bufcap;
@@ -935,7 +1016,7 @@ void gyo_merge_from(gyo_engine *dst, const gyo_engine *src)
 		d->conn_all_cnt += s->conn_all_cnt; d->conn_all_kb += s->conn_all_kb;
 		for (uint32_t r = 0; r < (1u << dst->hll_p); ++r) if (d->hll[r] < s->hll[r]) d->hll[r] = s->hll[r];
 		/* t-digest: rank-ascending merge = concatenate sorted centroid lists, compress */
-		gyo_centroid merged[2 * GYO_TD_CAP], outc[GYO_TD_CAP];
+		gyo_centroid merged[2 * GYO_TD_CAP], outc[GYO_TD_CAP + 1];
 		uint32_t nm = merge_sorted(d->td.c, d->td.n, s->td.c, s->td.n, merged);
 		uint32_t no = gyo_td_compress(merged, nm, dst->delta, outc, GYO_TD_CAP);
 		if (no > GYO_TD_CAP) no = GYO_TD_CAP;

@@ -55,7 +55,7 @@ typedef struct gyo_event		/* == gysk_event */
 
 typedef struct gyo_centroid { double mean; uint64_t weight; } gyo_centroid;
 
-#define GYO_TD_CAP		128
+#define GYO_TD_CAP		256
 
 typedef struct gyo_tdigest
 {
@@ -87,7 +87,9 @@ int	gyo_hist_run(int cls, int tkind, const int64_t *vals, size_t n, const float 
 /* ---- sketch definitions (ours; parity unpinned) ---- */
 uint32_t gyo_cms_index(uint64_t flow_key, uint32_t row, uint32_t log2_width);
 uint64_t gyo_cms_increment(uint32_t bytes);		/* 1 | (bytes >> 10) << 32 */
+void	gyo_flow_hashes(uint64_t flow_key, uint32_t *h1, uint32_t *h2);
 uint64_t gyo_hll_hash(uint64_t flow_key);
+uint32_t gyo_td_code(uint32_t usec);	/* log-linear bin of a response time, 32 bins per octave */
 void	gyo_hll_idx_rank(uint64_t flow_key, uint32_t p, uint32_t *idx, uint8_t *rank);
 double	gyo_hll_estimate(const uint8_t *regs, uint32_t p);
 

@@ -17,7 +17,7 @@ assert EVENT_DTYPE.itemsize == 32
 
 SERIAL_DTYPE = np.dtype([("count", "<u8"), ("sum", "<i8")])
 CENTROID_DTYPE = np.dtype([("mean", "<f8"), ("weight", "<u8")])
-TD_CAP = 128
+TD_CAP = 256
 
 CLS = dict(RESP_TIME=0, SEMI_LOG=1, SEMI_LOG_LO=2, DURATION=3, HASH_10_5000=4, HASH_5_250=5, HASH_1_3000=6,
            PERCENT=7, FD_I8_9_26_5=8, FD_INT_M15_M3_4=9)
@@ -71,6 +71,9 @@ def lib():
         L.gyo_cms_index.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
         L.gyo_cms_increment.restype = C.c_uint64
         L.gyo_cms_increment.argtypes = [C.c_uint32]
+        L.gyo_td_code.restype = C.c_uint32
+        L.gyo_td_code.argtypes = [C.c_uint32]
+        L.gyo_flow_hashes.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p]
         L.gyo_hll_hash.restype = C.c_uint64
         L.gyo_hll_hash.argtypes = [C.c_uint64]
         L.gyo_hll_idx_rank.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -155,7 +158,7 @@ def hist_run(L, fn, cls, tkind, vals, pcts=()):
 
 
 class OracleEngine:
-    def __init__(self, max_svcs=1024, max_tasks=1024, cms_depth=4, cms_log2_width=20, hll_p=12, td_compression=100,
+    def __init__(self, max_svcs=1024, max_tasks=1024, cms_depth=4, cms_log2_width=20, hll_p=12, td_compression=200,
                  flags=1, rank=0, world=1):
         self.L = lib()
         self.cfg = dict(max_svcs=max_svcs, max_tasks=max_tasks, cms_depth=cms_depth, cms_log2_width=cms_log2_width,
@@ -252,7 +255,7 @@ def td_new():
     return td
 
 
-def td_add(td, vals, delta=100.0, classic=False):
+def td_add(td, vals, delta=200.0, classic=False):
     vals = np.ascontiguousarray(vals, dtype=np.uint32)
     fn = lib().gyo_td_add_classic if classic else lib().gyo_td_add_batch
     fn(C.byref(td), _p(vals), len(vals), delta)

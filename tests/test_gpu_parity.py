@@ -14,8 +14,7 @@ pytestmark = pytest.mark.gpu
 
 TD_BATCHED_REL_EPS = 0.0   # GPU vs the CPU t-digest path: same IEEE operation sequence (no libm in the loop) => identical bits
 TD_REL_EPS = 0.01          # north-star epsilon: p50 / p95 within 1 % of the classic buffered CPU t-digest AND of the exact quantile
-TD_P99_EXACT_EPS = 0.03    # value error of ANY t-digest(100) at p99 on these heavy-tailed (sigma 1.2-1.5) streams is 1-3 %:
-                           # the sketch bounds RANK error, checked separately with TD_RANK_EPS
+TD_P99_EXACT_EPS = 0.01    # p99 within 1 % of the exact quantile too (n >= 10 K per service); the engine keeps delta = 200
 TD_RANK_EPS = 0.001        # |F(estimate) - q| on the exact empirical CDF
 
 
@@ -405,9 +404,9 @@ def test_topn_tasks_last_window():
             assert all(want[i] == sc for i, sc in got)
 
 
-def test_wide_keys_take_nine_bit_radix_passes():
-    """30 usec bits + 11 slot bits = 41 significant key bits: the sort takes five passes with one 9-bit digit instead of six 8-bit
-    ones (512-digit look-back rows, two digits per thread). Histograms and t-digest centroids stay bit-exact vs the oracle."""
+def test_full_value_range_keys():
+    """response times over the whole 30-bit usec range incl. the largest value the validity rule lets through (all 832 codes in
+    play), 1500 services: histograms, min / max and t-digest centroids stay bit-exact vs the oracle."""
     rng = np.random.default_rng(41)
     nsvc = 1500
     eng, orc = make_pair(max_svcs=2048, max_tasks=8, max_batch=1 << 18, cms_log2_width=10)

@@ -130,8 +130,10 @@ def test_raw_ebpf_records():
     resp = np.zeros(1000, dtype=np.dtype([("saddr", "<u4"), ("daddr", "<u4"), ("netns", "<u4"), ("sport", "<u2"), ("dport", "<u2"),
                                           ("lsndtime", "<u4"), ("lrcvtime", "<u4")]))
     rng = np.random.default_rng(3)
-    resp["saddr"], resp["netns"], resp["sport"] = 0x0A000001, 4026531840, 8080
-    resp["daddr"] = rng.integers(1, 1 << 31, len(resp)); resp["dport"] = rng.integers(16000, 60000, len(resp))
+    # inet_sport / skc_dport arrive in NETWORK byte order (the reference applies ntohs, gy_socket_stat.cc:1526-1527)
+    cport = rng.integers(16000, 60000, len(resp)).astype(np.uint16)
+    resp["saddr"], resp["netns"], resp["sport"] = 0x0A000001, 4026531840, np.uint16(8080).byteswap()
+    resp["daddr"] = rng.integers(1, 1 << 31, len(resp)); resp["dport"] = cport.byteswap()
     resp["lrcvtime"] = rng.integers(0, 1 << 31, len(resp))
     ms = rng.integers(0, 20000, len(resp)).astype(np.uint32)
     ms[::50] = 2_000_000                                   # beyond the 1 000 000 msec validity rule: dropped on the host
@@ -149,13 +151,26 @@ def test_raw_ebpf_records():
                                         ("comm", "S16"), ("saddr", "<u4"), ("daddr", "<u4"), ("netns", "<u4"), ("sport", "<u2"),
                                         ("dport", "<u2"), ("ipver", "u1"), ("type", "u1")], align=True))
     assert conn.dtype.itemsize == 72
-    conn["saddr"], conn["netns"], conn["sport"], conn["type"], conn["bytes_acked"] = 0x0A000001, 4026531840, 8080, 4, 10240
+    conn["saddr"], conn["netns"], conn["sport"], conn["type"], conn["bytes_acked"] = 0x0A000001, 4026531840, np.uint16(8080).byteswap(), 4, 10240
     conn["daddr"] = np.arange(10) + 100
     eng.ingest_raw(ge.RAW_TCP_IPV4_EVENT, conn, len(conn)); eng.sync()
     st = eng.stats()
     assert st["nsvcs"] == 1 and st["events_tcp"] == 10      # same (netns, ip, port) -> same service id as the resp events
     assert int(eng.export_cms().sum() & 0xFFFFFFFF) == 40   # 10 events x 4 rows, count halves
     assert want["total"] == kept
+    # CONN_BITMAP index = HOST-order client port & 0x1F (gy_socket_stat.h:403-410): per response bucket the set of port slots seen
+    JL = po.lib()
+    seed = 0xceedfead
+    sid = (JL.gyo_jhash_2words(0x0A000001, 4026531840, seed) << 32) | JL.gyo_jhash_2words(8080, 4026531840, seed ^ 0x0A000001)
+    masks, cnts = eng.export_conn_bitmap(sid)
+    ok = ms <= 1_000_000
+    want_masks = np.zeros(15, dtype=np.uint32)
+    for m_, p_ in zip(ms[ok], cport[ok]):
+        want_masks[JL.gyo_bucket(0, int(m_))] |= np.uint32(1 << (int(p_) & 31))
+    assert np.array_equal(masks, want_masks)
+    assert [bin(int(x)).count("1") for x in want_masks] == list(cnts)
+    h = eng.export_hist(sid, ge.HIST_RESP_CUR)
+    assert np.array_equal(h[0]["count"], want["stats"]["count"][:15]) and h[1] == kept
 
 
 def test_listener_state_host_summary():
@@ -176,8 +191,12 @@ def test_listener_state_host_summary():
         r["glob_id"] = 100 + i
         r["nqrys_5s"] = int(rng.integers(0, 5000)) if i % 4 else 0
         r["nconns_active"], r["kb_in"], r["kb_out"], r["ser_errors"] = rng.integers(0, 1000, 4)
-        r["curr_state"] = int(rng.integers(0, 7))
+        r["curr_state"] = int(rng.integers(0, 8))
+        r["query_flags"] = 0xC0 if i % 11 == 0 else (1 if i % 13 == 0 else 0)      # LISTEN_FLAG_DELETE / LISTEN_FLAG_ALERT / none
         recs.append((r, b"some issue" if i % 5 == 0 else b""))
+        # partha_listener_state (gy_mconnhdlr.cc:11183-11251): DELETE records and states beyond STATE_DOWN never reach summstats.update
+        if int(r["query_flags"][0]) == 0xC0 or int(r["curr_state"][0]) > 5:
+            continue
         want["nstates"][int(r["curr_state"][0])] += 1
         want["tot_qps"] += int(r["nqrys_5s"][0]) // 5
         want["tot_act_conn"] += int(r["nconns_active"][0]); want["tot_kb_inbound"] += int(r["kb_in"][0])
@@ -192,7 +211,7 @@ def test_listener_state_host_summary():
     issues = lambda h: h["nstates"][3] + h["nstates"][4] + h["nstates"][5]
     cs = eng.cluster_state()
     assert cs == dict(nhosts=2, nsvc_issue=issues(want) + issues(h11), nsvcissue_hosts=int(issues(want) > 0) + int(issues(h11) > 0),
-                      nsvc=want["nlisteners"] + 50, total_qps=want["tot_qps"] + h11["tot_qps"],
+                      nsvc=want["nlisteners"] + h11["nlisteners"], total_qps=want["tot_qps"] + h11["tot_qps"],
                       svc_net_mb=(want["tot_kb_inbound"] + want["tot_kb_outbound"]) // 1024 + (h11["tot_kb_inbound"] + h11["tot_kb_outbound"]) // 1024)
     assert eng.cluster_state([9, 77])["nhosts"] == 1
 

@@ -88,8 +88,8 @@ def test_tdigest_oracle_properties():
         x = np.minimum(np.exp(rng.normal(np.log(2000.0), sigma, n)), 9e8).astype(np.uint32)
         tb = po.td_new()
         for ch in np.array_split(x, 5):
-            po.td_add(tb, ch)
-        tc = po.td_add(po.td_new(), x, classic=True)
+            po.td_add(tb, ch, delta=200.0)
+        tc = po.td_add(po.td_new(), x, delta=200.0, classic=True)
         mb, wb = tb.centroids()
         assert int(wb.sum()) == n == tb.total and tb.n <= po.TD_CAP and tc.n <= po.TD_CAP
         assert np.all(np.diff(mb) >= 0) and tb.minv == x.min() and tb.maxv == x.max()
@@ -99,7 +99,7 @@ def test_tdigest_oracle_properties():
             for td in (tb, tc):
                 g = po.td_quantile(td, q)
                 assert abs(np.searchsorted(xs, g) / n - q) < 0.002, (sigma, n, q)          # rank error: what a t-digest bounds
-                assert abs(g - ex) / ex < (0.01 if q < 0.99 else 0.035), (sigma, n, q, g, ex)
+                assert abs(g - ex) / ex < 0.01, (sigma, n, q, g, ex)
     # tiny inputs
     t = po.td_add(po.td_new(), np.array([7], dtype=np.uint32))
     assert t.n == 1 and po.td_quantile(t, 0.5) == 7.0
@@ -176,35 +176,59 @@ def test_tdigest_pgtext_form():
     assert L.gysk_tdigest_to_pgtext(means.ctypes.data_as(C.c_void_p), weights.ctypes.data_as(C.c_void_p), 4, 100, small, len(small)) == -28
 
 
+def np_td_code(v):
+    """numpy statement of the log-linear value code (oracle gyo_td_code): 32 bins per octave, exact below 32"""
+    v = np.asarray(v, dtype=np.uint64)
+    e = np.zeros(len(v), dtype=np.uint64)
+    big = v >= 32
+    e[big] = np.floor(np.log2(v[big].astype(np.float64))).astype(np.uint64)
+    e[big] = np.where((np.uint64(1) << e[big]) > v[big], e[big] - np.uint64(1), e[big])        # guard float rounding at powers of two
+    e[big] = np.where((np.uint64(2) << e[big]) <= v[big], e[big] + np.uint64(1), e[big])
+    sh = np.where(big, e - np.uint64(5), np.uint64(0))
+    return np.where(big, ((sh + np.uint64(1)) << np.uint64(5)) | ((v >> sh) & np.uint64(31)), v)
+
+
+def test_td_code_is_monotone_and_matches_the_oracle():
+    from oracle import pyoracle as po
+    L = po.lib()
+    rng = np.random.default_rng(2)
+    v = np.unique(np.concatenate([np.arange(0, 5000), rng.integers(0, 1 << 30, 200_000), (1 << np.arange(5, 30)) - 1, 1 << np.arange(5, 30),
+                                  [(1 << 30) - 1, 1_000_000_999]]).astype(np.uint64))
+    code = np_td_code(v)
+    assert np.array_equal(code, np.array([L.gyo_td_code(int(x)) for x in v], dtype=np.uint64))
+    assert np.all(np.diff(code.astype(np.int64)) >= 0) and code.max() < 1024            # monotone, 10 bits
+    # a bin is at most 1/32 of its lower edge wide: 32 bins per octave
+    for c in np.unique(code)[::7]:
+        inb = v[code == c]
+        assert inb.max() - inb.min() <= max(1, inb.min() // 32)
+
+
 def test_radix_pass_plan_covers_every_significant_bit_once():
-    """host logic of the one-sweep sort: for every (usec bits, slots) shape the passes sort bits 5.. of the usec field and then
-    the slot field (from bit 35), each significant bit exactly once and in ascending order; the port bits (0-4) and the unused
-    bits in between never cost a pass; digits are 8 bits wide except where 9-bit digits save a whole pass (41-45 bits)."""
+    """host logic of the one-sweep sort: the RESP keys are sorted on the word {slot | code(usec)} = 10 value bits + the slot bits
+    of the engine's capacity, each bit exactly once and in ascending order, in the fewest digits of at most 9 bits, widths even"""
     import ctypes as C
     from gyeeta_b200 import engine as ge
     L = ge.load_library()
-    for vb in range(1, 31):
-        for nslots in (1, 2, 100, 1024, 100_000, 1 << 20, 1 << 24):
-            plan = (C.c_int32 * 4 * 8)()
-            npass = C.c_uint32()
-            assert L.gysk_sort_plan(vb, nslots, plan, C.byref(npass)) == 0
-            sb = max(1, int(nslots - 1).bit_length())
-            want = [5 + i for i in range(vb)] + [35 + i for i in range(sb)]
-            got = []
-            for p in range(npass.value):
-                s1, b1, s2, b2 = plan[p]
-                assert 1 <= b1 + b2 <= 9 and b1 >= 1
-                got += [s1 + i for i in range(b1)] + [s2 + i for i in range(b2)]
-            assert got == want, (vb, nslots, got)
-            T = vb + sb
-            assert npass.value == min(-(-T // 8), -(-T // 9) if -(-T // 9) < -(-T // 8) else -(-T // 8))
-            assert npass.value == (-(-T // 9) if -(-T // 9) < -(-T // 8) else -(-T // 8))
+    for max_svcs in (1, 2, 100, 1024, 3000, 100_000, 1 << 17, 1 << 20, 1 << 24):
+        plan = (C.c_int32 * 4 * 8)()
+        npass = C.c_uint32()
+        assert L.gysk_sort_plan(0, max_svcs, plan, C.byref(npass)) == 0
+        sb = max(1, int(max_svcs - 1).bit_length())
+        T = 10 + sb
+        got = []
+        for p in range(npass.value):
+            s1, b1, s2, b2 = plan[p]
+            assert 1 <= b1 <= 9 and b2 == 0
+            got += [s1 + i for i in range(b1)]
+        assert got == list(range(T)), (max_svcs, got)
+        assert npass.value == -(-T // 9)
+        widths = [plan[p][1] for p in range(npass.value)]
+        assert max(widths) - min(widths) <= 1
     plan = (C.c_int32 * 4 * 8)(); npass = C.c_uint32()
-    assert L.gysk_sort_plan(24, 100_000, plan, C.byref(npass)) == 0 and npass.value == 5      # 41 bits: one 9-bit digit, not 6 passes
-    assert sorted(plan[p][1] + plan[p][3] for p in range(5)) == [8, 8, 8, 8, 9]
-    assert L.gysk_sort_plan(23, 100_000, plan, C.byref(npass)) == 0 and npass.value == 5      # the bench stream: 40 bits
-    assert all(plan[p][1] + plan[p][3] == 8 for p in range(5))
-    assert L.gysk_sort_plan(0, 10, plan, C.byref(npass)) == -22
+    assert L.gysk_sort_plan(0, 1 << 17, plan, C.byref(npass)) == 0 and npass.value == 3       # the bench engine: 27 bits = 9 + 9 + 9
+    assert [plan[p][1] for p in range(3)] == [9, 9, 9]
+    assert L.gysk_sort_plan(0, 1 << 20, plan, C.byref(npass)) == 0 and npass.value == 4       # 1 M services: 30 bits = 8 8 7 7
+    assert L.gysk_sort_plan(0, 0, plan, C.byref(npass)) == -22
 
 
 def test_listener_state_encoder_fields_and_limits():
@@ -249,25 +273,25 @@ def test_listener_state_encoder_fields_and_limits():
 
 def test_radix_pass_plan_sorts_keys_when_passes_are_stable():
     """the plan of gysk_sort_plan, executed with numpy's stable argsort as the pass: keys {slot | usec | port} come out ordered by
-    (slot, usec) with ties in input order — for 8-bit plans, the 9-bit plan (41 bits) and a digit that straddles the field gap"""
+    (slot, code(usec)) with ties in input order"""
     import ctypes as C
     from gyeeta_b200 import engine as ge
     L = ge.load_library()
     rng = np.random.default_rng(5)
-    for vb, nslots in ((23, 100_000), (24, 100_000), (30, 1500), (7, 3), (13, 1 << 20)):
+    for max_svcs in (100_000, 1 << 17, 1500, 3, 1 << 20):
         plan = (C.c_int32 * 4 * 8)(); npass = C.c_uint32()
-        assert L.gysk_sort_plan(vb, nslots, plan, C.byref(npass)) == 0
+        assert L.gysk_sort_plan(0, max_svcs, plan, C.byref(npass)) == 0
         n = 50_000
-        slot = rng.integers(0, nslots, n, dtype=np.uint64)
-        usec = rng.integers(0, 1 << vb, n, dtype=np.uint64)
-        port = rng.integers(0, 32, n, dtype=np.uint64)
-        keys = (slot << np.uint64(35)) | (usec << np.uint64(5)) | port
+        slot = rng.integers(0, max_svcs, n, dtype=np.uint64)
+        usec = np.minimum(np.exp(rng.normal(np.log(2000.0), 2.5, n)), 1.0e9).astype(np.uint64)
+        code = np_td_code(usec)
+        word = (slot << np.uint64(10)) | code
         order = np.arange(n)
-        cur = keys.copy()
+        cur = word.copy()
         for p in range(npass.value):
-            s1, b1, s2, b2 = (int(x) for x in plan[p])
-            digit = ((cur >> np.uint64(s1)) & np.uint64((1 << b1) - 1)) | (((cur >> np.uint64(s2)) & np.uint64((1 << b2) - 1)) << np.uint64(b1))
+            s1, b1 = int(plan[p][0]), int(plan[p][1])
+            digit = (cur >> np.uint64(s1)) & np.uint64((1 << b1) - 1)
             perm = np.argsort(digit, kind="stable")
             cur, order = cur[perm], order[perm]
-        want = np.lexsort((np.arange(n), usec, slot))             # by slot, then usec, then input order
-        assert np.array_equal(order, want), (vb, nslots)
+        want = np.lexsort((np.arange(n), code, slot))             # by slot, then code, then input order
+        assert np.array_equal(order, want), max_svcs

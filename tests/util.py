@@ -13,7 +13,7 @@ def make_pair(**kw):
     eng = ge.Engine(**kw)
     idle = kw.get("idle_evict_secs", 0)
     ocfg = dict(max_svcs=kw.get("max_svcs", 1 << 14), max_tasks=kw.get("max_tasks", 1 << 12), cms_depth=kw.get("cms_depth", 4),
-                cms_log2_width=kw.get("cms_log2_width", 20), hll_p=kw.get("hll_p", 12), td_compression=kw.get("td_compression", 100),
+                cms_log2_width=kw.get("cms_log2_width", 20), hll_p=kw.get("hll_p", 12), td_compression=kw.get("td_compression", 200),
                 flags=1 if kw.get("auto_register", True) else 0, rank=kw.get("rank", 0), world=kw.get("world", 1))
     orc = po.OracleEngine(**ocfg)
     if idle:
