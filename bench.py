@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gysketch", choices=["gysketch", "reference"])
     ap.add_argument("--events", type=int, default=100_000_000, help="events per rank per step")
-    ap.add_argument("--max-batch", type=int, default=1 << 27, help="events per device batch (value path: one batch per step)")
+    ap.add_argument("--max-batch", type=int, default=(1 << 27) - 1, help="events per device batch (value path: one batch per step)")
     ap.add_argument("--stage-batch", type=int, default=1 << 23, help="events per H2D chunk on the host-buffer path")
     ap.add_argument("--cpu-sample", type=int, default=20_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -184,11 +184,40 @@ def measured_peak_gbs():
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_port_rate(ev_np, nthreads, repeat=1):
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def shard_owner(ev_np, nthreads, mode):
+    """which host thread takes an event. "host": host_idx % T — how madhava pins a partha to an L2 thread
+    (gy_mconnhdlr.cc:16252); "balanced": hosts dealt to threads heaviest first (longest-processing-time), still one thread per
+    host; "svc": by service / task id — finer than the reference can shard, shown as the upper bound the skew allows."""
+    if nthreads == 1:
+        return np.zeros(len(ev_np), dtype=np.int32)
+    if mode == "host":
+        return (ev_np["host_idx"] % nthreads).astype(np.int32)
+    if mode == "svc":
+        return ((ev_np["svc_id"] * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)).astype(np.int64).__mod__(nthreads).astype(np.int32)
+    cnt = np.bincount(ev_np["host_idx"])
+    load = np.zeros(nthreads, dtype=np.int64)
+    host_thr = np.zeros(len(cnt), dtype=np.int32)
+    for h in np.argsort(-cnt, kind="stable"):
+        t = int(np.argmin(load))
+        host_thr[h] = t
+        load[t] += cnt[h]
+    return host_thr[ev_np["host_idx"]]
+
+
+def cpu_port_rate(ev_np, nthreads, mode="host", repeat=1):
     from oracle import pyoracle as po
     L = po.lib()
-    # pre-shard by host (mirrors l1_thr_num % maxthr, gy_mconnhdlr.cc:16252): one stable sort, then split
-    owner = (ev_np["host_idx"] % nthreads).astype(np.int32)
+    owner = shard_owner(ev_np, nthreads, mode)
     order = np.argsort(owner, kind="stable")
     cuts = np.searchsorted(owner[order], np.arange(1, nthreads))
     shards = [np.ascontiguousarray(a) for a in np.split(ev_np[order], cuts)]
@@ -203,11 +232,34 @@ def cpu_port_rate(ev_np, nthreads, repeat=1):
         best = sec if best is None else min(best, sec)
     for e in engines:
         e.close()
-    return len(ev_np) / best, best
+    return len(ev_np) / best, best, float(max(len(s) for s in shards)) / max(1, len(ev_np))
+
+
+def cpu_arm_report(ev_np, ncores):
+    """1-thread and N-thread rates of the CPU port under the three shardings, and the reference's own add_data loop"""
+    from oracle import pyoracle as po
+    one = ev_np[: max(1, len(ev_np) // 8)]
+    r1, s1, _ = cpu_port_rate(one, 1)
+    out = {"threads_1": {"events_per_s": r1, "sample_events": len(one)}}
+    for mode in ("host", "balanced", "svc"):
+        r, sec, frac = cpu_port_rate(ev_np, ncores, mode)
+        out[f"threads_{ncores}_{mode}"] = {"events_per_s": r, "speedup_vs_1": r / r1, "largest_shard_frac": frac, "sec": sec}
+    resp = ev_np[ev_np["type"] == 5]
+    if len(resp) and po.ref() is not None:
+        _, slots = np.unique(resp["svc_id"], return_inverse=True)
+        vals = (resp["value"] // 1000).astype(np.int64)
+        out["ref_gy_histogram_add_data_only"] = {"threads_1": po.ref_hist_rate(slots[: len(slots) // 4], vals[: len(slots) // 4], 1),
+                                                 f"threads_{ncores}": po.ref_hist_rate(slots, vals, ncores),
+                                                 "unit": "RESP samples/s", "what": "the reference's own GY_HISTOGRAM<int64_t, RESP_TIME_HASH>::add_data "
+                                                 "compiled from /root/reference (oracle/_ref), samples pre-sharded by slot % threads"}
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port, all host threads)."""
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port: GY_HISTOGRAM add_data + count-min +
+    HLL + t-digest per event, open-addressing id tables), all host threads, events pre-sharded by host like madhava pins a partha
+    to an L2 thread. `value` = the host-sharded N-thread rate; the balanced / by-service shardings and the 1-thread rate are listed
+    beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -220,28 +272,21 @@ def run_reference(args):
     ev = synth.gen_mixed(rng, n, NSVC, ntask=NTASK, zipf_s=ZIPF_S, nhosts=NHOSTS, nclients=NCLIENTS)
     rates = []
     for i in range(args.warmup + args.steps):
-        r, sec = cpu_port_rate(ev, ncores)
+        r, sec, _ = cpu_port_rate(ev, ncores)
         if i >= args.warmup:
             rates.append((r, sec))
     rate = float(np.mean([r for r, _ in rates]))
     ms = float(np.mean([s for _, s in rates])) * 1e3
-    extra = {}
-    R = po.ref()
-    if R is not None:       # the REFERENCE's own GY_HISTOGRAM::add_data loop (hist part of the path only), for context
-        resp = ev[ev["type"] == 5]
-        _, slots = np.unique(resp["svc_id"], return_inverse=True)
-        slots = slots.astype(np.uint32)
-        vals = (resp["value"] // 1000).astype(np.int64)
-        tot = C.c_uint64()
-        sec = R.gyref_bench_resp_hist(po._p(slots), po._p(vals), len(vals), int(slots.max()) + 1, ncores, C.byref(tot))
-        extra["ref_gy_histogram_add_data_only_events_per_s"] = len(vals) / sec
+    detail = cpu_arm_report(ev, ncores)
     print(json.dumps({
         "impl": "reference", "metric": "events/sec aggregated", "value": rate, "unit": "events/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "configs[2]: mixed RESP/TCP/TASK 70/20/10, 100K services, bounded sample", "events_per_step": n},
-        "cpu_baseline": {"value": rate, "unit": "events/s", "cores": ncores, "kind": "port",
-                         "sample": f"{n} events of the same stream, pre-sharded by host over {ncores} threads", **extra},
+        "config": {"workload": "configs[2]: mixed RESP/TCP/TASK 70/20/10, 100K services, bounded sample of the same generator "
+                               "(a rate per event: the sample bounds the run to a few minutes of CPU)", "events_per_step": n,
+                   "cpu_model": cpu_model()},
+        "cpu_baseline": {"value": rate, "unit": "events/s", "cores": ncores, "kind": "port", "cpu_model": cpu_model(),
+                         "sample": f"{n} events of the same stream, pre-sharded by host over {ncores} threads", "detail": detail},
         "e2e": {"value": rate, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -285,10 +330,15 @@ def main():
     merge_events = []
 
     def merge_step():
+        # the multi-GPU exchange: fold + ONE grouped NCCL launch + merge-compress inside libgysketch.so (gysk_merge_global),
+        # once per query window = once per timed region here, not once per batch
         if world > 1:
-            from gyeeta_b200 import dist as gd
-            gd.merge_global(eng, torch, dist, dev)
-            merge_events.append(gd.merge_global.last_events)
+            with torch.cuda.stream(stream):
+                a = torch.cuda.Event(enable_timing=True); a.record()
+            eng.merge_global()
+            with torch.cuda.stream(stream):
+                b = torch.cuda.Event(enable_timing=True); b.record()
+            merge_events.append((a, b))
 
     def setup_logical_map():
         # BASELINE configs[3]: global per-logical-service stats, 16 hosts' instances per logical service; every rank passes the
@@ -302,15 +352,17 @@ def main():
     def step_device():
         eng.ingest_device_ptr(ev_devs[step_no[0] % NB].data_ptr(), n)
         step_no[0] += 1
-        merge_step()
 
     for b in range(NB):
         eng.ingest_device_ptr(ev_devs[b].data_ptr(), n)       # registers this rank's services
     eng.sync()
     if world > 1:
+        from gyeeta_b200 import dist as gd
         setup_logical_map()
+        gd.nccl_comm_init(eng, dist)
     for _ in range(args.warmup):
         step_device()
+    merge_step()
     eng.sync()
     launches0 = eng.stats()["kernel_launches"]
     eng.profile_enable(True)
@@ -323,6 +375,7 @@ def main():
         t0.record()
     for _ in range(args.steps):
         step_device()
+    merge_step()                       # the window's one sketch merge is inside the timed region
     with torch.cuda.stream(stream):
         t1.record()
     eng.sync()
@@ -338,7 +391,7 @@ def main():
     eng.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.stats()["kernel_launches"] - launches0
-    merge_events_value = list(merge_events[-args.steps - min(args.steps, 8): len(merge_events) - min(args.steps, 8)]) if merge_events else []
+    merge_events_value = merge_events[-1:] if merge_events else []
 
     tms = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -358,7 +411,6 @@ def main():
         def step_e2e():
             eng.ingest_pinned_ptr(hosts[step_no[0] % NB].data_ptr(), n)
             step_no[0] += 1
-            merge_step()
             return eng.query_svcs(qids)         # syncs, copies the summaries device -> host
 
         for _ in range(max(1, args.warmup // 2)):
@@ -367,6 +419,7 @@ def main():
         w0 = time.perf_counter()
         for _ in range(args.steps):
             step_e2e()
+        merge_step()
         eng.sync()
         torch.cuda.synchronize()
         w1 = time.perf_counter()
@@ -429,9 +482,12 @@ def main():
         ncores = os.cpu_count() or 1
         ns = int(min(args.cpu_sample, n))
         ev_np = ev_dev[:ns].cpu().numpy().view(np.uint8).reshape(-1).view(ge.EVENT_DTYPE)
-        r, sec = cpu_port_rate(ev_np, ncores)
-        cpu = {"value": r, "unit": "events/s", "cores": ncores, "kind": "port",
-               "sample": f"first {ns} events of rank 0's stream, pre-sharded by host over {ncores} threads ({sec:.1f} s)"}
+        r, sec, frac = cpu_port_rate(ev_np, ncores)
+        r1, _s1, _ = cpu_port_rate(ev_np[: ns // 8], 1)
+        cpu = {"value": r, "unit": "events/s", "cores": ncores, "kind": "port", "cpu_model": cpu_model(), "one_thread_events_per_s": r1,
+               "largest_shard_frac": frac,
+               "sample": f"first {ns} events of rank 0's stream, pre-sharded by host over {ncores} threads ({sec:.1f} s); "
+                         "1-thread rate on an eighth of it; more shardings in `bench.py --impl reference`"}
 
     out = {
         "metric": "events/sec aggregated", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
@@ -446,8 +502,8 @@ def main():
         "roofline_whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
                                 "algorithmic_bytes_per_event": BYTES_EVENT},
         "cpu_baseline": cpu, "accuracy": acc, "per_step_spread_ms": spread,
-        "merge": ({"collective_ms_per_step_rank0": (float(np.mean([a.elapsed_time(b) for a, b in merge_events_value])) if merge_events_value else None), "logical_services": NSVC // 16,
-                   "what": "one all-reduce per reduction kind (u64 sum / i64 max / u8 max) + one all-gather of t-digest slabs, NCCL"}
+        "merge": ({"logical_services": NSVC // 16,
+                   "what": "gysk_merge_global: fold kernels + ONE ncclGroup (3 all-reduces: u64 sum / i64 max / u8 max, 1 all-gather of t-digest slabs) + merge-compress, once per timed window", "merge_ms_of_the_window": (float(merge_events_value[0][0].elapsed_time(merge_events_value[0][1])) if merge_events_value else None)}
                   if world > 1 else None),
     }
     print(json.dumps(out))

@@ -25,6 +25,20 @@ static constexpr uint32_t SLOT_INVALID = 0xFFFFFFFFu;
 struct Centroid { double mean; unsigned long long weight; };
 static constexpr int TD_CAP = 256;		// delta = 200 yields 200 ... 1.3 x 200 centroids
 
+// One log-linear value bin of one service for the batch being ingested: every RESP sample costs two 64-bit REDs,
+//   cw += 1 | (usec % 1000) << 27        {samples : 27 | sum of the sub-millisecond remainders : 37}  — a batch holds < 2^27 events
+//   us += usec
+// so that the bin's exact msec sum (GY_HISTOGRAM::add_data adds usec / 1000 per sample) is (us - remainders) / 1000 and its mean
+// us / samples. Bin index = td_code(usec) + RESP_TIME_HASH bucket of its msec value: both terms are monotone in usec, so the
+// index is too and no bin straddles a histogram bucket. The batch's merge kernel reads the bins in order and zeroes them.
+struct alignas(16) Bin { unsigned long long cw; unsigned long long us; };
+static constexpr int NBINS = 848;				// 832 codes + 15 buckets, padded to a multiple of 16
+static constexpr int BIN_CNT_BITS = 27;
+static constexpr unsigned long long BIN_CNT_MASK = (1ull << BIN_CNT_BITS) - 1;
+
+// per-service scratch of the batch being ingested: exact extremes of its RESP samples and "has bins to merge"
+struct alignas(16) SlotBatch { uint32_t minv, maxv, touched, pad; };
+
 // per-service t-digest header
 struct TdHead { unsigned long long total; double minv, maxv; uint32_t n; uint32_t pad; };
 

@@ -49,6 +49,7 @@ template <typename AfterIngest>
 int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n, AfterIngest after_ingest)
 {
 	if (!n) return 0;
+	if (n >= (1ull << BIN_CNT_BITS)) return fail(e, GYSK_ERR_INVAL, "device batch holds 2^27 or more events");
 	cudaEvent_t *pe = nullptr;
 	if (e->profiling) {
 		if (e->prof_used + 3 > e->prof_events.size()) {
@@ -62,19 +63,13 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n, Aft
 		e->prof_used += 3;
 		CU(e, cudaEventRecord(pe[0], e->stream));
 	}
-	e->kernel_launches += launch_ingest(e->st, e->tmp, d_ev, n, e->cfg.max_svcs, e->stream);
+	e->kernel_launches += launch_ingest(e->st, d_ev, n, e->stream);
 	if (pe) CU(e, cudaEventRecord(pe[1], e->stream));
 	// the events of this batch are consumed once the ingest kernel has run: callers release / refill the event buffer here,
-	// so that the next H2D copy overlaps the whole sort + t-digest chain
+	// so that the next H2D copy overlaps the merge kernels
 	{ int rc_ai = after_ingest(); if (rc_ai) return rc_ai; }
-	// No number travels back to the host between ingest and sort: the key count stays in device memory (the passes read it
-	// there, grids are sized for n keys and surplus CTAs leave at once), the digit histograms were counted by the ingest
-	// kernel, the digits cover every slot the engine could hand out. A batch is one uninterrupted run of launches.
-	{
-		const int nl = launch_tdigest_update(e->st, e->tmp, n, e->cfg.max_svcs, e->stream);
-		if (nl < 0) return fail(e, GYSK_ERR_INVAL, "device batch holds 2^30 or more events");
-		e->kernel_launches += nl;
-	}
+	// No number travels back to the host inside a batch: the list of touched services and its length stay in device memory.
+	e->kernel_launches += launch_batch_merge(e->st, e->tmp, e->cfg.max_svcs, e->stream);
 	if (pe) CU(e, cudaEventRecord(pe[2], e->stream));
 	e->batches++;
 	return post_launch(e, "ingest batch");
@@ -340,6 +335,7 @@ void gysk_destroy(gysk_engine *e)
 	cudaSetDevice(e->dev);
 	if (e->stream) cudaStreamSynchronize(e->stream);
 	if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+	merge_release(e);
 	for (int k = 0; k < NBUF; ++k) {
 		if (e->ev_copied[k]) cudaEventDestroy(e->ev_copied[k]);
 		if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
@@ -368,7 +364,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	if (!cfg.stage_batch || cfg.stage_batch > cfg.max_batch) cfg.stage_batch = std::min<uint32_t>(cfg.max_batch, 1u << 22);
 	if (cfg.max_svcs < 1 || cfg.max_svcs > (1u << 24) || cfg.max_tasks < 1 || cfg.max_tasks > (1u << 24) || cfg.cms_depth < 1 ||
 			cfg.cms_depth > 8 || cfg.cms_log2_width < 4 || cfg.cms_log2_width > 28 || cfg.hll_p < 4 || cfg.hll_p > 16 ||
-			cfg.td_compression < 10 || cfg.td_compression > 220 || cfg.max_batch < 1024 || cfg.max_batch > (1u << 28) ||
+			cfg.td_compression < 10 || cfg.td_compression > 220 || cfg.max_batch < 1024 || cfg.max_batch >= (1u << 27) ||
 			cfg.rank >= cfg.world)
 		return fail(nullptr, GYSK_ERR_INVAL, "gysk_config out of range");
 
@@ -436,18 +432,20 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 		}
 	}
 
+	A(dalloc(e, &st.bins, ns * NBINS)); A(dalloc(e, &st.slot_batch, ns));
 	SortTemp &tmp = e->tmp;
-	tmp.max_tiles = (cfg.max_batch + SORT_TILE - 1) / SORT_TILE;
-	A(dalloc(e, &tmp.keys_a, (size_t)cfg.max_batch, false)); A(dalloc(e, &tmp.keys_b, (size_t)cfg.max_batch, false));
+	const size_t nsort = std::max<size_t>(ns, nt) + 1;			// the radix sort only ranks services / tasks (top-N)
+	tmp.max_tiles = (uint32_t)((nsort + SORT_TILE - 1) / SORT_TILE);
+	A(dalloc(e, &tmp.keys_a, nsort, false)); A(dalloc(e, &tmp.keys_b, nsort, false));
 	A(dalloc(e, &tmp.tile_status, (size_t)RADIX_MAX * tmp.max_tiles));
 	tmp.epoch = &e->sort_epoch;
 	A(dalloc(e, &tmp.os_ghist, (size_t)8 * RADIX_MAX + 8));
-	A(dalloc(e, &tmp.runbits, ((size_t)cfg.max_batch >> 5) + 64)); A(dalloc(e, &tmp.runbits2, ((size_t)cfg.max_batch >> 15) + 2));
-	A(dalloc(e, &tmp.bminmax, ns));
-	A(dalloc(e, &tmp.newc_scratch, (size_t)TD_MERGE_MAX_SMS * TD_MERGE_CTAS_PER_SM * 4 * TD_CAP));
+	A(dalloc(e, &tmp.touched, ns));
+	{
+		const size_t nmw = (size_t)TD_MERGE_MAX_SMS * TD_MERGE_CTAS_PER_SM * 4;		// warps of bins_merge_kernel
+		A(dalloc(e, &tmp.items_scratch, nmw * NBINS, false)); A(dalloc(e, &tmp.big_scratch, nmw, false));
+	}
 	st.svc_tbl.insert_fail = st.counters + CTR_INSERT_FAIL; st.task_tbl.insert_fail = nullptr;
-	A(dalloc(e, &tmp.seg_start, ns)); A(dalloc(e, &tmp.seg_end, ns)); A(dalloc(e, &tmp.touched, ns));
-	A(dalloc(e, &tmp.plan_bounds, ns * (TD_CAP + 1))); A(dalloc(e, &tmp.plan_n, ns)); A(dalloc(e, &tmp.newsum, ns * TD_CAP));
 
 	for (int k = 0; k < NBUF; ++k) {
 		A(halloc(e, &e->h_stage[k], (size_t)cfg.stage_batch));
@@ -1103,7 +1101,7 @@ int gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gys
 	if (rc) return rc;
 	uint32_t nslots = 0;
 	CU(e, cudaMemcpy(&nslots, e->st.svc_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-	nslots = std::min(nslots, std::min(e->cfg.max_svcs, e->cfg.max_batch));
+	nslots = std::min(nslots, e->cfg.max_svcs);
 	gysk_topn_entry *d_out = reinterpret_cast<gysk_topn_entry *>(e->d_flowout);		// QCHUNK * 16 B >= 64 * 24 B
 	CU(e, cudaMemsetAsync(d_out, 0, sizeof(gysk_topn_entry) * n, e->stream));
 	{
@@ -1131,7 +1129,7 @@ int gysk_topn_tasks(gysk_engine *e, int metric, uint32_t n, gysk_topn_entry *out
 	if (rc) return rc;
 	uint32_t ntasks = 0;
 	CU(e, cudaMemcpy(&ntasks, e->st.task_tbl.count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-	ntasks = std::min(ntasks, std::min(e->cfg.max_tasks, e->cfg.max_batch));
+	ntasks = std::min(ntasks, e->cfg.max_tasks);
 	gysk_topn_entry *d_out = reinterpret_cast<gysk_topn_entry *>(e->d_flowout);		// QCHUNK * 16 B >= 64 * 24 B
 	CU(e, cudaMemsetAsync(d_out, 0, sizeof(gysk_topn_entry) * n, e->stream));
 	{
@@ -1181,22 +1179,6 @@ int gysk_query_cluster_state(gysk_engine *e, const uint32_t *host_idxs, uint32_t
 			if (it != e->host_summ.end()) add(it->second);
 		}
 	}
-	return GYSK_OK;
-}
-
-// The radix passes the t-digest chain runs over the RESP keys of an engine with capacity max_svcs: the sort word is
-// {slot | code(usec)} (TD_CODE_BITS = 10 value bits), out[p] = {shift, bits, 0, 0}, digit = (word >> shift) & ((1 << bits) - 1).
-// No engine, no device: the plan is host logic (tests pin that every significant bit is sorted exactly once, in order, in the
-// fewest passes of at most 9 bits). value_bits is accepted for ABI compatibility and ignored.
-int gysk_sort_plan(uint32_t value_bits, uint32_t max_svcs, int32_t out[8][4], uint32_t *npasses)
-{
-	(void)value_bits;
-	if (!out || !npasses || !max_svcs || max_svcs > (1u << 24)) return GYSK_ERR_INVAL;
-	int shift[OS_MAX_PASSES_VK], bits[OS_MAX_PASSES_VK];
-	const int np = vk_sort_plan(max_svcs, shift, bits);
-	if (np < 0) return GYSK_ERR_INVAL;
-	for (int p = 0; p < np; ++p) { out[p][0] = shift[p]; out[p][1] = bits[p]; out[p][2] = 0; out[p][3] = 0; }
-	*npasses = (uint32_t)np;
 	return GYSK_OK;
 }
 

@@ -44,6 +44,11 @@ struct MergeState
 	size_t			slab_bytes {0};
 	uint8_t			*final_slab {nullptr};			// merged over ranks
 	bool			prepared {false}, finished {false};
+	void			*comm {nullptr};			// ncclComm_t of gysk_nccl_comm_init
+	uint32_t		comm_world {0};
+	bool			comm_owned {false};
+	uint8_t			*gathered {nullptr};			// [world] slabs, target of the all-gather
+	uint32_t		gathered_world {0};
 };
 
 } // namespace gysk
@@ -100,7 +105,7 @@ struct gysk_engine
 	std::mutex		mtx;
 	std::string		err;
 	bool			sticky {false};
-	uint64_t		kernel_launches {0}, batches {0}, wire_ok {0}, wire_bad {0};
+	uint64_t		kernel_launches {0}, batches {0}, wire_ok {0}, wire_bad {0}, merges {0};
 };
 
 namespace gysk {
@@ -110,6 +115,7 @@ int post_launch(gysk_engine *e, const char *what);
 int submit_stage(gysk_engine *e);
 int sync_locked(gysk_engine *e);
 int collect_evicted(gysk_engine *e, bool wait);
+void merge_release(gysk_engine *e);
 void summarize_raw(const gysk_engine *e, const SvcRaw &r, uint64_t id, gysk_svc_summary &o);
 
 #define CU(e, call) do { cudaError_t ce__ = (call); if (ce__ != cudaSuccess) return gysk::fail((e), GYSK_ERR_CUDA, #call, ce__); } while (0)

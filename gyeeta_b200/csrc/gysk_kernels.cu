@@ -1,13 +1,14 @@
 // gysk_kernels.cu — hand-written sm_100a kernels of the streaming-sketch engine.
 //
 //   ingest_kernel        one pass over a batch of 32-byte events: id -> slot, then per event type
-//                          RESP : emit the (slot, usec, client port) sort key + the digit histograms of the radix passes
+//                          RESP : two REDs into the service's log-linear value bin {samples, usec sum, sub-msec remainders},
+//                                 CONN_BITMAP bit, batch min / max
 //                          TCP  : count-min cell adds, HLL register max, per-service exact cell
 //                          TASK : MAGGR_TASK::set_local_task_state (3 histograms)     server/gy_msocket.h:1009-1018
-//   os_pass_kernel       stable one-sweep LSD radix passes over the keys, sorted by (slot, log-linear code of usec)
-//   td_segments/plan/sums/merge
-//                        GY_HISTOGRAM::add_data (RESP_TIME_HASH) common/gy_statistics.h:596-623, :1698, CONN_BITMAP and the
-//                        batched merging t-digest (K_1 scale) from the sorted keys                     DESIGN.md §2
+//   touched_kernel       list of the services that received RESP samples in this batch
+//   bins_merge_kernel    per touched service: bins -> GY_HISTOGRAM::add_data for every sample (RESP_TIME_HASH, common/gy_statistics.h:
+//                        596-623, :1698) and -> the merging t-digest (K_1 scale)               DESIGN.md §2
+//   os_pass_kernel       stable one-sweep LSD radix sort (the top-N rankings)
 //   flush_kernel         5-s window roll                                               common/gy_socket_stat.cc:3898
 //   gather_* / query_*   read side
 #include "gysk_kernels.cuh"
@@ -22,16 +23,6 @@
 
 namespace gysk {
 
-static constexpr unsigned long long KEY_SENTINEL = ~0ull;
-static constexpr unsigned long long VALUE_MASK = (1ull << VALUE_BITS) - 1;
-__device__ __forceinline__ uint32_t key_slot(unsigned long long k) { return (uint32_t)(k >> KEY_SLOT_SHIFT); }
-__device__ __forceinline__ uint32_t key_usec(unsigned long long k) { return (uint32_t)(k >> KEY_VALUE_SHIFT) & (uint32_t)VALUE_MASK; }
-// what the radix passes sort on: {slot | log-linear code of the response time} — 10 value bits instead of 30
-__device__ __forceinline__ unsigned long long key_vk(unsigned long long k)
-{
-	return ((unsigned long long)key_slot(k) << TD_CODE_BITS) | td_code(key_usec(k));
-}
-
 // ---------------------------------------------------------------------------------------------------
 // state init / registration
 // ---------------------------------------------------------------------------------------------------
@@ -45,6 +36,7 @@ __global__ void init_state_kernel(DevState st, uint32_t max_svcs, uint32_t max_t
 		st.hist_all[(size_t)i * HIST_CELLS + HIST_MAX_CELL].sum = LLONG_MIN;
 		st.td_head[i].minv = INFINITY;
 		st.td_head[i].maxv = -INFINITY;
+		st.slot_batch[i].minv = 0xFFFFFFFFu;
 	}
 	if (i < max_tasks) {
 		for (int h = 0; h < 3; ++h) st.task_hist[((size_t)i * 3 + h) * HIST_CELLS + HIST_MAX_CELL].sum = LLONG_MIN;
@@ -171,44 +163,34 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 
 // The kernel is WARP-AUTONOMOUS: no block barrier anywhere in the event loop. A warp takes a chunk of 32 x EPT events and
 //   (1) decodes them fully converged: 2 x 128-bit load per event, shard filter, id -> slot lookup with the first table probe
-//       of all EPT events in flight together. An event then joins one of the warp's three private shared-memory queues
-//       (ballot + popc, no atomics: the queue lengths are warp-uniform registers): RESP -> its 64-bit sort key
-//       {slot, usec, client port & 31}; TCP / TASK -> a 16-byte decoded record;
-//   (2) drains a queue only in whole multiples of 32 entries, so every lane works in every iteration whatever the 70/20/10
-//       mix of the stream is: TCP = two lookup2 hashes per flow key -> four count-min REDs + HLL register + the service's
-//       exact {count, kbytes} cell; TASK = the three histograms of MAGGR_TASK::set_local_task_state with one (event,
-//       histogram) pair per lane; the < 32 left-over entries move to the queue's front;
-//   (3) hands its RESP keys to the global key array in runs of >= KQ_FLUSH (one cursor bump per run, coalesced stores) and
-//       counts, on the way out, each key's digit for every radix pass in the CTA's shared-memory histograms — the one-sweep
-//       passes need the global digit histograms up front, and this way no kernel re-reads the keys to get them.
-// The RESP histogram cell, CONN_BITMAP bit and t-digest share are all produced later from the SORTED keys, where equal cells
-// are contiguous runs (td_sums_kernel).
+//       of all EPT events in flight together;
+//   (2) RESP (70 % of the stream) is finished on the spot — two 64-bit REDs into the service's value bin (the samples of a
+//       service spread over up to ~400 bins, so even the hottest service puts no more than a few thousand REDs per batch on one
+//       address: no warp aggregation needed), the CONN_BITMAP bit and the batch extremes only when they would change;
+//   (3) TCP / TASK events join one of the warp's two private shared-memory queues (ballot + popc, no atomics: the queue
+//       lengths are warp-uniform registers) and a queue is drained only in whole multiples of 32 entries, so every lane works in
+//       every iteration whatever the mix of the stream is: TCP = two lookup2 hashes per flow key -> four count-min REDs + HLL
+//       register + the service's exact {count, kbytes} cell; TASK = the three histograms of
+//       MAGGR_TASK::set_local_task_state with one (event, histogram) pair per lane; the < 32 left-over entries move to the front.
+// The histogram cells and the t-digest of a service are produced from its bins by bins_merge_kernel after the batch.
 struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
-
-struct SortPlan { int np; int shift[OS_MAX_PASSES_VK]; int bits[OS_MAX_PASSES_VK]; };	// digit p = (vk >> shift[p]) & ((1 << bits[p]) - 1)
 
 template <int WARPS, int EPT, bool TMA>
 struct IngestSharedT
 {
 	static constexpr int CHUNK = 32 * EPT;			// events per warp and round
-	static constexpr int KQ_CAP = 256, KQ_FLUSH = KQ_CAP - CHUNK;	// flush leaves room for a whole chunk of RESP events
 	static constexpr int RQ_CAP = 32 + CHUNK;			// < 32 left over + one chunk
-	static_assert(CHUNK <= 128, "key queue sized for chunks of at most 128 events");
 	using HotTable = HotTableT<9>;
-	struct Warp {
-		unsigned long long kq[KQ_CAP];
-		IngestRec	tcp[RQ_CAP], task[RQ_CAP];
-	};
+	struct Warp { IngestRec tcp[RQ_CAP], task[RQ_CAP]; };
 	alignas(128) uint4	evbuf[TMA ? WARPS * CHUNK * 2 : 1];	// per warp: its next chunk of 32-byte events, filled by cp.async.bulk
 	unsigned long long	mbar[TMA ? WARPS : 1];
 	Warp		w[WARPS];
 	HotTable	hot;
-	uint32_t	dhist[OS_MAX_PASSES_VK][RADIX_MAX];		// digit histograms of this CTA's keys, one per radix pass
 };
 
 template <int WARPS, int MIN_CTAS, int EPT, bool TMA>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
-		unsigned long long *__restrict__ keys, uint32_t *__restrict__ ghist, SortPlan plan)
+		int unused)
 {
 	using Shared = IngestSharedT<WARPS, EPT, TMA>;
 	using HotTable = typename Shared::HotTable;
@@ -218,12 +200,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	typename Shared::Warp &W = S.w[wid];
 	const uint32_t lt = (1u << lane) - 1u;
-	uint32_t c_in = 0, c_foreign = 0;				// per thread: < 2^32 events per launch
-	uint32_t nk = 0, ntcp = 0, ntask = 0;				// queue lengths (warp-uniform)
-	unsigned long long t_resp = 0, t_tcp = 0, t_task = 0;	// queued in total (warp-uniform)
+	uint32_t c_in = 0, c_foreign = 0, n_resp = 0;			// per thread: < 2^32 events per launch
+	uint32_t ntcp = 0, ntask = 0;					// queue lengths (warp-uniform)
+	unsigned long long t_tcp = 0, t_task = 0;			// queued in total (warp-uniform)
 
 	for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
-	for (int i = threadIdx.x; i < OS_MAX_PASSES_VK * RADIX_MAX; i += WARPS * 32) (&S.dhist[0][0])[i] = 0;
 	if (TMA && lane == 0) mbar_init(&S.mbar[wid], 1);
 	__syncthreads();						// the only block barriers: here and before the retire step
 	if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");	// mbarrier init visible to the async proxy
@@ -286,23 +267,6 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 		if (mv) q[lane] = r;
 		__syncwarp();
 	};
-	auto flush_keys = [&]() {
-		unsigned long long base = 0;
-		if (lane == 0) base = atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)nk);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		for (uint32_t q = lane; q < nk; q += 32) {
-			const unsigned long long k = W.kq[q];
-			const unsigned long long vk = key_vk(k);
-#pragma unroll
-			for (int p = 0; p < OS_MAX_PASSES_VK; ++p)
-				if (p < plan.np) atomicAdd(&S.dhist[p][(uint32_t)(vk >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
-			__stcs(keys + base + q, k);
-		}
-		t_resp += nk;
-		nk = 0;
-		__syncwarp();
-	};
-
 	for (uint64_t chunk = gwarp; chunk < nchunks; chunk += nwarps) {
 		const uint64_t cbase = chunk * CHUNK;
 		uint4 ra[EPT], rb[EPT];
@@ -358,12 +322,24 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 				slot = table_resolve(is_task ? st.task_tbl : st.svc_tbl, ((unsigned long long)ra[k].y << 32) | ra[k].x, st.auto_register, rb[k].y, ppos[k], praw[k]);
 			}
 			const bool ok = slot >= 0;
-			const uint32_t m_resp = __ballot_sync(0xffffffffu, ok && is_resp), m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp),
-					m_task = __ballot_sync(0xffffffffu, ok && is_task);
+			const uint32_t m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp), m_task = __ballot_sync(0xffffffffu, ok && is_task);
 			if (ok) {
 				if (is_resp) {
-					// {slot, usec, client port & 31 (CONN_BITMAP index, common/gy_socket_stat.h:403-410)}
-					W.kq[nk + __popc(m_resp & lt)] = ((unsigned long long)(uint32_t)slot << KEY_SLOT_SHIFT) | ((unsigned long long)rb[k].x << KEY_VALUE_SHIFT) | (ra[k].z & 0x1Fu);
+					const uint32_t v = rb[k].x, ms = v / 1000u;		// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678)
+					const uint32_t b = (uint32_t)bucket_resp_time((long long)ms);
+					Bin *bin = st.bins + (size_t)slot * NBINS + td_code(v) + b;
+					red_add_u64(&bin->cw, 1ull | ((unsigned long long)(v - ms * 1000u) << BIN_CNT_BITS));
+					red_add_u64(&bin->us, v);
+					// the rest only when it changes something: one 16-byte load of the slot's batch record, one of the mask word
+					const uint4 sb = ld_cg_v4(st.slot_batch + slot);
+					if (v < sb.x) atomicMin(&st.slot_batch[slot].minv, v);
+					if (v > sb.y) atomicMax(&st.slot_batch[slot].maxv, v);
+					if (!sb.z) st_volatile_u32(&st.slot_batch[slot].touched, 1u);
+					// TCP_LISTENER::CONN_BITMAP::add_response (common/gy_socket_stat.h:403-410), transposed: per bucket a mask over client port & 31
+					uint32_t *mw = st.bm_cur + (size_t)slot * HIST_CELLS + b;
+					const uint32_t bit = 1u << (ra[k].z & 0x1Fu);
+					if (!(__ldcg(mw) & bit)) atomicOr(mw, bit);
+					n_resp++;
 				}
 				else {
 					IngestRec r; r.slot = (uint32_t)slot; r.value = rb[k].x; r.flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
@@ -371,32 +347,27 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 					else W.task[ntask + __popc(m_task & lt)] = r;
 				}
 			}
-			nk += __popc(m_resp); ntcp += __popc(m_tcp); ntask += __popc(m_task);
+			ntcp += __popc(m_tcp); ntask += __popc(m_task);
 		}
 		__syncwarp();
 
 		if (ntcp >= 32) { const uint32_t m = ntcp & ~31u; drain_tcp(m); keep_rest(W.tcp, m, ntcp); t_tcp += m; ntcp -= m; }
 		if (ntask >= 32) { const uint32_t m = ntask & ~31u; drain_task(m); keep_rest(W.task, m, ntask); t_task += m; ntask -= m; }
-		if (nk > (uint32_t)Shared::KQ_FLUSH) flush_keys();
 	}
 	// what is left in the queues
 	if (ntcp) { drain_tcp(ntcp); t_tcp += ntcp; }
 	if (ntask) { drain_task(ntask); t_task += ntask; }
-	if (nk) flush_keys();
 
 	__syncthreads();
-	// retire: one RED group per privatised cell, one RED per digit this CTA saw
+	// retire: one RED group per privatised cell
 	for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) {
 		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i]);
-	}
-	for (int i = threadIdx.x; i < plan.np * RADIX_MAX; i += WARPS * 32) {
-		const uint32_t c = (&S.dhist[0][0])[i];
-		if (c) atomicAdd(ghist + i, c);
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
 	c_in = __reduce_add_sync(0xffffffffu, c_in);
 	c_foreign = __reduce_add_sync(0xffffffffu, c_foreign);
+	const unsigned long long t_resp = __reduce_add_sync(0xffffffffu, n_resp);
 	if (lane == 0) {
 		if (c_in) atomicAdd(st.counters + CTR_IN, (unsigned long long)c_in);
 		if (c_foreign) atomicAdd(st.counters + CTR_FOREIGN, (unsigned long long)c_foreign);
@@ -412,30 +383,26 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 // ---------------------------------------------------------------------------------------------------
 // stable LSD radix sort, 8- or 9-bit digits, tile = SORT_TILE keys per CTA of 256 threads
 // ---------------------------------------------------------------------------------------------------
-// A pass sorts on a digit made of up to two bit fields: digit = ((w >> s1) & m1) | (((w >> s2) & m2) << b1), where w is the key
-// itself (plain mode: the top-N sorts) or, in VK mode, the RESP sort word {slot | code(usec)} derived from the key on the fly.
+// (used by the top-N rankings: {score | slot} keys over the registered services / tasks)
+// A pass sorts on a digit made of up to two bit fields of the key: digit = ((k >> s1) & m1) | (((k >> s2) & m2) << b1).
 struct DigitSpec { int s1, b1, s2, b2; };
-template <bool VK>
 __device__ __forceinline__ uint32_t key_digit(unsigned long long k, const DigitSpec &D)
 {
-	const unsigned long long w = VK ? key_vk(k) : k;
-	return ((uint32_t)(w >> D.s1) & ((1u << D.b1) - 1u)) | (((uint32_t)(w >> D.s2) & ((1u << D.b2) - 1u)) << D.b1);
+	return ((uint32_t)(k >> D.s1) & ((1u << D.b1) - 1u)) | (((uint32_t)(k >> D.s2) & ((1u << D.b2) - 1u)) << D.b1);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // one-sweep radix pass: 16 B of HBM traffic per key and pass (read once, write once)
 //
-//   digit histograms   the GLOBAL digit histograms of every pass are known before the first pass (a stable pass does not change
-//                      how many keys carry a digit value): for the RESP keys ingest_kernel counts them while it emits the keys,
-//                      for the small top-N sorts os_hist_kernel reads the keys once;
+//   os_hist_kernel     one read of the keys fills the GLOBAL digit histograms of every pass (a stable pass does not change how
+//                      many keys carry a digit value);
 //   os_pass_kernel     a CTA takes the next tile (ticket from an atomic counter, so every predecessor tile is already running),
 //                      ranks its keys per digit, publishes the tile's digit counts and obtains the number of keys with the same
 //                      digit in all earlier tiles by decoupled look-back over the status words of its predecessors
 //                      (status word = pass epoch : 32 | state : 2 | count : 30; state 1 = this tile's count, 2 = inclusive prefix
 //                      up to this tile; a word of another epoch reads as "not there yet", so the array is never cleared),
 //                      reorders the tile by digit in shared memory and writes every digit's run to its final place.
-// The number of keys comes from DEVICE memory (the key cursor ingest_kernel bumped): the grid is sized for the largest possible
-// count and surplus CTAs leave at once — no host read-back between ingest and sort.
+// The number of keys comes from DEVICE memory: the grid is sized for the largest possible count and surplus CTAs leave at once.
 // Stability: tiles are ordered by ticket = tile index, ranks inside a tile follow the input order (warp, round, lane).
 // ---------------------------------------------------------------------------------------------------
 static constexpr int OS_THREADS = 256;			// thread t owns digits t, t + 256 in the per-digit steps
@@ -482,8 +449,8 @@ __global__ void __launch_bounds__(512) os_hist_kernel(const unsigned long long *
 		for (int p = 0; p < OS_MAX_PASSES; ++p) {
 			if (p < P.np) {
 				uint32_t *hp = h + p * pstride + copy * stride;
-				atomicAdd(hp + key_digit<false>(k0, P.d[p]), 1u);
-				if (two) atomicAdd(hp + key_digit<false>(k1, P.d[p]), 1u);
+				atomicAdd(hp + key_digit(k0, P.d[p]), 1u);
+				if (two) atomicAdd(hp + key_digit(k1, P.d[p]), 1u);
 			}
 		}
 	}
@@ -531,7 +498,7 @@ struct OneSweepSharedT
 	uint32_t		tile;
 };
 
-template <int RBITS, bool VK>
+template <int RBITS>
 __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
 		const unsigned long long *__restrict__ d_n, DigitSpec D, const uint32_t *__restrict__ ghist /* [RADIX] of this pass */,
 		unsigned long long *__restrict__ status /* [ntiles][RADIX] */, uint32_t *__restrict__ ticket, uint32_t epoch,
@@ -587,10 +554,12 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 
 	// rank of every key among the keys of its digit inside this warp's chunk (rounds in order, lanes in order); the group
 	// leader bumps the warp's digit counter and hands the previous value to its group
+	uint32_t dg[OS_KPT / 2];			// two 16-bit digits per word (the VK digit costs a clz + shifts: computed once)
 #pragma unroll
 	for (int r = 0; r < OS_KPT; ++r) {
 		const bool valid = wbase + (uint32_t)r * 32 + lane < n;
-		const uint32_t d = valid ? key_digit<VK>(k[r], D) : ((uint32_t)RADIX + lane);
+		const uint32_t d = valid ? key_digit(k[r], D) : ((uint32_t)RADIX + lane);
+		if (r & 1) dg[r >> 1] |= d << 16; else dg[r >> 1] = d;
 		uint32_t m;
 		if (use_ballot) {
 			m = 0xffffffffu;
@@ -656,7 +625,7 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 #pragma unroll
 	for (int r = 0; r < OS_KPT; ++r) {
 		if (wbase + (uint32_t)r * 32 + lane < n) {
-			const uint32_t dd = key_digit<VK>(k[r], D);
+			const uint32_t dd = (r & 1) ? (dg[r >> 1] >> 16) : (dg[r >> 1] & 0xFFFFu);
 			const uint32_t rank = (r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xFFFFu);
 			S.keys[S.dstart[dd] + S.whist[wid][dd] + rank] = k[r];
 		}
@@ -669,386 +638,123 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 #pragma unroll 4
 	for (uint32_t i = threadIdx.x; i < nvalid; i += OS_THREADS) {
 		const unsigned long long key = S.keys[i];
-		out[S.goff[key_digit<VK>(key, D)] + i] = key;
+		out[S.goff[key_digit(key, D)] + i] = key;
 	}
 }
 
 // ---------------------------------------------------------------------------------------------------
-// batched merging t-digest + RESP histograms from the sorted keys
+// per batch: services with RESP samples -> histogram cells + t-digest, from their value bins
 // ---------------------------------------------------------------------------------------------------
-// The keys are sorted by (slot, code): a service's samples are one segment, the samples of one log-linear bin one RUN inside
-// it, in no particular order within the run. td_segments_kernel records where segments and runs start:
-//   seg_start / seg_end / touched   per service
-//   runbits   one bit per key position: a run starts here;  runbits2: one bit per 1024 positions: some run starts in there
-// (two levels so that the planner finds the run start before / after a position in a few loads even inside a bin that holds a
-// million equal samples).
-static constexpr int TSEG_V = 4;			// keys per thread: positions wbase + t * 32 + lane
-
-__global__ void __launch_bounds__(256) td_segments_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
-		uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_end, uint32_t *__restrict__ touched, unsigned long long *ntouched,
-		uint32_t *__restrict__ runbits, uint32_t *__restrict__ runbits2)
+// list of the slots ingest_kernel marked; grid covers every slot the engine can hand out
+__global__ void __launch_bounds__(256) touched_kernel(DevState st, uint32_t max_svcs, uint32_t *__restrict__ touched, unsigned long long *ntouched)
 {
-	const uint64_t n = *d_n;
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
-	const uint64_t wbase = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane) * TSEG_V;		// 128 consecutive keys per warp
-	if (wbase >= n) return;
-
-	unsigned long long g[TSEG_V + 2];		// {slot, code} of key wbase - 1 (lane 0 only), own 4 keys, successor of the last (lane 31 only)
-#pragma unroll
-	for (int t = 0; t < TSEG_V; ++t) {
-		const uint64_t i = wbase + (uint64_t)t * 32 + lane;
-		g[1 + t] = i < n ? key_vk(keys[i]) : KEY_SENTINEL;
-	}
-	g[0] = (lane == 0 && wbase) ? key_vk(keys[wbase - 1]) : KEY_SENTINEL;
-	g[TSEG_V + 1] = (lane == 31 && wbase + 128 < n) ? key_vk(keys[wbase + 128]) : KEY_SENTINEL;
-
-	uint32_t nstart = 0, anyrun = 0;
-	uint32_t isseg = 0, isend = 0;			// bit t: own key t starts / ends a service segment
-#pragma unroll
-	for (int t = 0; t < TSEG_V; ++t) {
-		const uint64_t i = wbase + (uint64_t)t * 32 + lane;
-		// predecessor: lane - 1 of the same t, lane 31 of t - 1 for lane 0; successor: lane + 1, lane 0 of t + 1 for lane 31
-		unsigned long long prev = __shfl_up_sync(0xffffffffu, g[1 + t], 1);
-		const unsigned long long prev0 = __shfl_sync(0xffffffffu, g[t], 31);		// g[t] of lane 31 = its key t - 1 (t >= 1)
-		if (lane == 0) prev = t == 0 ? g[0] : prev0;
-		unsigned long long next = __shfl_down_sync(0xffffffffu, g[1 + t], 1);
-		const unsigned long long next0 = __shfl_sync(0xffffffffu, g[2 + (t < TSEG_V - 1 ? t : 0)], 0);	// key t + 1 of lane 0
-		if (lane == 31) next = t == TSEG_V - 1 ? g[TSEG_V + 1] : next0;
-		const bool valid = i < n;
-		const bool run = valid && g[1 + t] != prev;			// i == 0: prev is the sentinel
-		const bool seg = valid && (g[1 + t] >> TD_CODE_BITS) != (prev >> TD_CODE_BITS);
-		const bool end = valid && (g[1 + t] >> TD_CODE_BITS) != (next >> TD_CODE_BITS);	// i == n - 1: next is the sentinel
-		const uint32_t word = __ballot_sync(0xffffffffu, run);
-		if (lane == 0) runbits[(wbase >> 5) + t] = word;
-		anyrun |= word;
-		nstart += seg ? 1u : 0u;
-		isseg |= (seg ? 1u : 0u) << t; isend |= (end ? 1u : 0u) << t;
-	}
-	if (lane == 0 && anyrun) atomicOr(&runbits2[wbase >> 15], 1u << ((wbase >> 10) & 31u));
-
-	// one cursor bump per warp for all the segments that start in it (the cold tail has a new service every few samples)
-	uint32_t incl = nstart;
-#pragma unroll
-	for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
-	const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+	const bool t = slot < max_svcs && st.slot_batch[slot].touched != 0;
+	const uint32_t m = __ballot_sync(0xffffffffu, t);
+	if (!m) return;
 	unsigned long long base = 0;
-	if (wtotal && lane == 0) base = atomicAdd(ntouched, (unsigned long long)wtotal);
-	base = __shfl_sync(0xffffffffu, base, 0) + (incl - nstart);
+	if (lane == 0) base = atomicAdd(ntouched, (unsigned long long)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (t) touched[base + __popc(m & ((1u << lane) - 1u))] = slot;
+}
+
+// bin index -> RESP_TIME_HASH bucket. index = td_code(usec) + bucket: for bucket b the indexes run from
+// td_code(first usec of the bucket) + b to td_code(last usec of the bucket) + b.
+__device__ __forceinline__ uint32_t bin_bucket(uint32_t idx, const uint16_t *first_idx /* [15] first index of each bucket */)
+{
+	uint32_t b = 0;
 #pragma unroll
-	for (int t = 0; t < TSEG_V; ++t) {
-		const uint64_t i = wbase + (uint64_t)t * 32 + lane;
-		const uint32_t slot = (uint32_t)(g[1 + t] >> TD_CODE_BITS);
-		if ((isseg >> t) & 1u) { seg_start[slot] = (uint32_t)i; touched[base++] = slot; }
-		if ((isend >> t) & 1u) seg_end[slot] = (uint32_t)(i + 1);
-	}
-}
-
-// largest run start <= pos (a run starts at the segment's first key, so the search never leaves the segment)
-__device__ __forceinline__ uint32_t run_start_at_or_before(const uint32_t *__restrict__ runbits, const uint32_t *__restrict__ runbits2, uint32_t pos)
-{
-	uint32_t w = pos >> 5;
-	uint32_t m = runbits[w] & (0xFFFFFFFFu >> (31u - (pos & 31u)));
-	if (m) return (w << 5) + 31u - (uint32_t)__clz((int)m);
-	const uint32_t blk0 = w & ~31u;				// rest of this 1024-key block, downwards
-	while (w > blk0) { --w; m = runbits[w]; if (m) return (w << 5) + 31u - (uint32_t)__clz((int)m); }
-	uint32_t b = w >> 5;						// earlier blocks through the second level
-	for (;;) {
-		--b;
-		uint32_t m2 = runbits2[b >> 5] & (0xFFFFFFFFu >> (31u - (b & 31u)));
-		while (!m2) { b = (b & ~31u) - 1u; m2 = runbits2[b >> 5]; }
-		b = (b & ~31u) + 31u - (uint32_t)__clz((int)m2);
-		for (w = (b << 5) + 31u; ; --w) { m = runbits[w]; if (m) return (w << 5) + 31u - (uint32_t)__clz((int)m); if (w == (b << 5)) break; }
-	}
-}
-
-// smallest run start > pos and < end, else end
-__device__ __forceinline__ uint32_t run_start_after(const uint32_t *__restrict__ runbits, const uint32_t *__restrict__ runbits2, uint32_t pos, uint32_t end)
-{
-	uint32_t p = pos + 1;
-	if (p >= end) return end;
-	uint32_t w = p >> 5;
-	uint32_t m = runbits[w] & (0xFFFFFFFFu << (p & 31u));
-	const uint32_t wend = (end - 1) >> 5;				// last word that may be looked at
-	for (;;) {
-		if (m) { const uint32_t r = (w << 5) + (uint32_t)__ffs((int)m) - 1u; return r < end ? r : end; }
-		if (w >= wend) return end;
-		++w;
-		if ((w & 31u) == 0) {					// entering a new 1024-key block: skip empty blocks through the second level
-			uint32_t b = w >> 5;
-			const uint32_t bend = wend >> 5;
-			for (;;) {
-				if (b > bend) return end;
-				const uint32_t m2 = runbits2[b >> 5] & (0xFFFFFFFFu << (b & 31u));
-				if (m2) { b = (b & ~31u) + (uint32_t)__ffs((int)m2) - 1u; break; }
-				b = (b & ~31u) + 32u;
-			}
-			if (b > bend) return end;
-			w = b << 5;
-		}
-		m = runbits[w];
-	}
+	for (int i = 1; i < 15; ++i) b += idx >= first_idx[i];
+	return b;
 }
 
 static constexpr int TD_WARPS = 4;
-static constexpr int PLAN_STRIDE = TD_CAP + 1;
 
-// (1) plan: one thread per touched service cuts its n new samples into clusters with the greedy rule over unit weights —
-// cluster [s, e) with e = the last run start <= floor(n q(k(s/n) + 1)), or the end of the first run when that lies beyond: a
-// cluster never splits a bin, because the samples inside a bin are unordered. The boundaries depend on n and on the run starts
-// only, so they are fixed before any sample is summed. A pass that would need more than TD_CAP clusters is repeated on the next
-// rung of the ladder. Also clears the cluster-sum row and the batch min / max of the service.
-__global__ void td_plan_kernel(TdParams P, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end,
-		const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p, const uint32_t *__restrict__ runbits,
-		const uint32_t *__restrict__ runbits2, uint32_t *__restrict__ plan_bounds, uint32_t *__restrict__ plan_n,
-		unsigned long long *__restrict__ newsum, uint2 *__restrict__ bminmax)
-{
-	const uint32_t ntouched = (uint32_t)*ntouched_p;
-
-	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntouched; t += gridDim.x * blockDim.x) {
-		const uint32_t slot = touched[t];
-		const uint32_t s0 = seg_start[slot];
-		const uint32_t n = seg_end[slot] - s0;
-		uint32_t *bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
-		unsigned long long *sums = newsum + (size_t)slot * TD_CAP;
-		uint32_t nnew = 0;
-
-		bminmax[slot] = make_uint2(0xFFFFFFFFu, 0u);
-		for (int k = 0; k < TD_LADDER; ++k) {
-			const bool final = k == TD_LADDER - 1;
-			bool overflow = false;
-			uint32_t s = 0;
-			nnew = 0;
-			while (s < n) {
-				const double wl = td_wlimit(s, n, P.r[k]);
-				unsigned long long ee = (unsigned long long)floor(wl);
-				uint32_t e;
-				if (ee >= n) e = n;
-				else e = run_start_at_or_before(runbits, runbits2, s0 + (uint32_t)ee) - s0;
-				if (e <= s) e = run_start_after(runbits, runbits2, s0 + s, s0 + n) - s0;	// at least the first bin
-				if (final && nnew == TD_CAP - 1) e = n;			// the last slot absorbs whatever is left
-				if (nnew == TD_CAP) { overflow = true; break; }
-				bounds[nnew] = s;
-				sums[nnew] = 0;
-				nnew++;
-				s = e;
-			}
-			if (!overflow) break;
-		}
-		bounds[nnew] = n;
-		plan_n[slot] = nnew | (nnew == n ? 0x80000000u : 0u);	// flag: every cluster is a single sample, cluster id == rank
-	}
-}
-
-// (2) sums: cluster id = position of the sample's rank in the service's bounds; histogram bucket = RESP_TIME_HASH of its msec
-// value. Runs of equal (service, cluster, bucket) are contiguous in the sorted order except inside the few bins a bucket
-// threshold cuts through (there a run merely splits into several, which the REDs add up all the same). Per group the leader issues
-//   one 64-bit RED with the exact usec sum into the cluster sum (t-digest), and
-//   GY_HISTOGRAM::add_data for the whole run (common/gy_statistics.h:596-623): count and msec sum of the bucket cell, plus the
-//   run's CONN_BITMAP bits (TCP_LISTENER::CONN_BITMAP::add_response, common/gy_socket_stat.h:403-410, transposed: one mask over
-//   (client port & 31) per bucket).
-// Batch minimum / maximum of a service (t-digest ends, max_val_seen_): the samples of its first / last bin compete with
-// atomicMin / atomicMax — everything in between cannot be either.
-// FAST PATH: a warp's 128 consecutive samples usually sit inside ONE cluster of ONE hot service and one bucket (checked on the
-// first and last sample only: the order is monotone across bins): three redux + a handful of REDs for the whole warp.
-__device__ __forceinline__ uint32_t td_cluster_of(const uint32_t *__restrict__ bounds, uint32_t nn, uint32_t r, uint32_t &lo_out, uint32_t &hi_out)
-{
-	uint32_t lo = 0, hi = nn - 1;			// largest j with bounds[j] <= r
-	while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (bounds[mid] <= r) lo = mid; else hi = mid - 1; }
-	lo_out = bounds[lo]; hi_out = bounds[lo + 1];
-	return lo;
-}
-
-static constexpr int TDS_V = 4;			// consecutive sorted samples per lane
-
-__global__ void __launch_bounds__(256) td_sums_kernel(DevState st, const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
-		const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end, const uint32_t *__restrict__ plan_bounds,
-		const uint32_t *__restrict__ plan_n, unsigned long long *__restrict__ newsum, uint2 *__restrict__ bminmax)
-{
-	const uint64_t n = *d_n;
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * TDS_V;
-	const int lane = threadIdx.x & 31;
-
-	for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane) * TDS_V; base < n; base += stride) {
-		const uint64_t i0 = base + (uint64_t)lane * TDS_V;
-		unsigned long long kk[TDS_V];
-		if (i0 + TDS_V <= n) {
-			const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0), c = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
-			kk[0] = a.x; kk[1] = a.y; kk[2] = c.x; kk[3] = c.y;
-		}
-		else {
-#pragma unroll
-			for (int t = 0; t < TDS_V; ++t) kk[t] = i0 + t < n ? keys[i0 + t] : KEY_SENTINEL;
-		}
-
-		// lane 0 looks up the cluster of the warp's first sample and the ends of its service
-		uint32_t slot0 = 0xFFFFFFFFu, j0 = 0, lo0 = 1, hi0 = 0, sstart0 = 0, cfirst0 = 0, clast0 = 0;
-		if (lane == 0 && kk[0] != KEY_SENTINEL) {
-			slot0 = key_slot(kk[0]);
-			sstart0 = seg_start[slot0];
-			const uint32_t nn = plan_n[slot0], r = (uint32_t)(i0 - sstart0);
-			if (nn & 0x80000000u) { j0 = r; lo0 = r; hi0 = r + 1; }
-			else j0 = td_cluster_of(plan_bounds + (size_t)slot0 * PLAN_STRIDE, nn, r, lo0, hi0);
-			cfirst0 = td_code(key_usec(keys[sstart0]));
-			clast0 = td_code(key_usec(keys[seg_end[slot0] - 1]));
-		}
-		slot0 = __shfl_sync(0xffffffffu, slot0, 0); j0 = __shfl_sync(0xffffffffu, j0, 0);
-		lo0 = __shfl_sync(0xffffffffu, lo0, 0); hi0 = __shfl_sync(0xffffffffu, hi0, 0);
-		sstart0 = __shfl_sync(0xffffffffu, sstart0, 0);
-		cfirst0 = __shfl_sync(0xffffffffu, cfirst0, 0); clast0 = __shfl_sync(0xffffffffu, clast0, 0);
-
-		// ---- fast path: the whole warp is one (service, cluster, bucket) group ----
-		{
-			const unsigned long long klast = __shfl_sync(0xffffffffu, kk[TDS_V - 1], 31);
-			bool uniform = false;
-			if (klast != KEY_SENTINEL && key_slot(klast) == slot0 && (uint32_t)(base + 127 - sstart0) < hi0) {
-				const unsigned long long kfirst = __shfl_sync(0xffffffffu, kk[0], 0);
-				const uint32_t cF = td_code(key_usec(kfirst)), cL = td_code(key_usec(klast));
-				uniform = bucket_resp_time((long long)(td_code_lo(cF) / 1000u)) == bucket_resp_time((long long)(td_code_hi(cL) / 1000u));
-				if (uniform) {
-					unsigned long long us = 0;
-					uint32_t ms = 0, bits = 0, vmax = 0, vmin = 0xFFFFFFFFu;
-#pragma unroll
-					for (int t = 0; t < TDS_V; ++t) {
-						const uint32_t v = key_usec(kk[t]);
-						us += v; ms += v / 1000u; bits |= 1u << ((uint32_t)kk[t] & 0x1Fu);
-					}
-					// only the warps at the two ends of a service's segment can hold its extreme samples
-					if (cL == clast0) {
-#pragma unroll
-						for (int t = 0; t < TDS_V; ++t) { const uint32_t v = key_usec(kk[t]); if (td_code(v) == clast0) vmax = max(vmax, v); }
-						vmax = __reduce_max_sync(0xffffffffu, vmax);
-					}
-					if (cF == cfirst0) {
-#pragma unroll
-						for (int t = 0; t < TDS_V; ++t) { const uint32_t v = key_usec(kk[t]); if (td_code(v) == cfirst0) vmin = min(vmin, v); }
-						vmin = __reduce_min_sync(0xffffffffu, vmin);
-					}
-					const unsigned long long gsum = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)us & 0xFFFFFu) +
-							((unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)(us >> 20)) << 20);	// us < 2^32: 20 + 12 bits, x 32 lanes fits
-					ms = __reduce_add_sync(0xffffffffu, ms);
-					bits = __reduce_or_sync(0xffffffffu, bits);
-					if (lane == 0) {
-						const uint32_t cell = slot0 * HIST_CELLS + (uint32_t)bucket_resp_time((long long)(key_usec(kfirst) / 1000u));
-						red_add_u64(newsum + (size_t)slot0 * TD_CAP + j0, gsum);
-						red_add_u64(&st.hist_cur[cell].count, 32u * TDS_V);
-						red_add_u64((unsigned long long *)&st.hist_cur[cell].sum, ms);
-						atomicOr(st.bm_cur + cell, bits);
-						if (cL == clast0) atomicMax(&bminmax[slot0].y, vmax);
-						if (cF == cfirst0) atomicMin(&bminmax[slot0].x, vmin);
-					}
-				}
-			}
-			if (uniform) continue;
-		}
-
-		// own samples -> runs of equal (service, cluster, bucket). Sample t carries the totals of its run so far; only the last
-		// sample of a run (its tail) is emitted. Everything is indexed statically (registers).
-		unsigned long long pg[TDS_V];		// (slot * TD_CAP + cluster) << 4 | bucket
-		unsigned long long ps[TDS_V];		// usec sum
-		uint32_t pc[TDS_V], pm[TDS_V], pb[TDS_V];	// samples, msec sum, CONN_BITMAP bits
-		bool tail[TDS_V];
-		uint32_t cslot = 0xFFFFFFFFu, cstart = 0, cnn = 0, clo = 1, chi = 0, cj = 0, cfirst = 0, clast = 0;	// cached lookup of the previous sample
-#pragma unroll
-		for (int t = 0; t < TDS_V; ++t) {
-			const bool valid = kk[t] != KEY_SENTINEL;
-			tail[t] = valid;
-			pg[t] = 0xFFFFFFFFFFFFFF00ull + lane; ps[t] = 0; pc[t] = 0; pm[t] = 0; pb[t] = 0;
-			if (!valid) continue;
-			const uint32_t slot = key_slot(kk[t]), v = key_usec(kk[t]), bit = 1u << ((uint32_t)kk[t] & 0x1Fu);
-			if (slot != cslot) {
-				cslot = slot; clo = 1; chi = 0;
-				if (slot == slot0) { cstart = sstart0; cfirst = cfirst0; clast = clast0; }
-				else { cstart = seg_start[slot]; cfirst = td_code(key_usec(keys[cstart])); clast = td_code(key_usec(keys[seg_end[slot] - 1])); }
-				cnn = plan_n[slot];
-			}
-			const uint32_t r = (uint32_t)(i0 + t - cstart);
-			uint32_t j;
-			if (cnn & 0x80000000u) j = r;
-			else if (slot == slot0 && r >= lo0 && r < hi0) j = j0;
-			else if (r >= clo && r < chi) j = cj;
-			else { cj = td_cluster_of(plan_bounds + (size_t)slot * PLAN_STRIDE, cnn, r, clo, chi); j = cj; }
-			const uint32_t code = td_code(v);
-			if (code == clast) atomicMax(&bminmax[slot].y, v);
-			if (code == cfirst) atomicMin(&bminmax[slot].x, v);
-			const uint32_t ms = v / 1000u;			// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678)
-			pg[t] = ((unsigned long long)(slot * (uint32_t)TD_CAP + j) << 4) | (uint32_t)bucket_resp_time((long long)ms);
-			ps[t] = v; pc[t] = 1; pm[t] = ms; pb[t] = bit;
-			if (t > 0 && pg[t] == pg[t - 1]) {		// continues the previous sample's run (an invalid predecessor never matches)
-				ps[t] += ps[t - 1]; pc[t] += pc[t - 1]; pm[t] += pm[t - 1]; pb[t] |= pb[t - 1];
-				tail[t - 1] = false;
-			}
-		}
-
-		// emit the run tails: round t handles every lane's run ending at its sample t
-#pragma unroll
-		for (int t = 0; t < TDS_V; ++t) {
-			const bool act = tail[t];
-			if (!__any_sync(0xffffffffu, act)) continue;
-			const unsigned long long gid = act ? pg[t] : (0xFFFFFFFFFFFFFF00ull + lane);
-			const unsigned long long v = act ? ps[t] : 0ull;		// < 2^34
-			uint32_t cnt = act ? pc[t] : 0u, msum = act ? pm[t] : 0u, bits = act ? pb[t] : 0u;	// msum <= 4e6 per lane
-			const uint32_t m = __match_any_sync(0xffffffffu, gid);
-			unsigned long long gsum = v;
-			const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(m));
-			uint32_t rest = m & ~(1u << lane);
-			const uint32_t cnt0 = cnt, msum0 = msum, bits0 = bits;
-			for (uint32_t u = 1; u < maxcnt; ++u) {
-				const int src = rest ? (__ffs(rest) - 1) : lane;
-				const unsigned long long ov = __shfl_sync(0xffffffffu, v, src);
-				const uint32_t oc = __shfl_sync(0xffffffffu, cnt0, src), om = __shfl_sync(0xffffffffu, msum0, src), ob = __shfl_sync(0xffffffffu, bits0, src);
-				if (rest) { gsum += ov; cnt += oc; msum += om; bits |= ob; rest &= rest - 1; }
-			}
-			if (act && (m & ((1u << lane) - 1u)) == 0) {
-				const uint32_t cj2 = (uint32_t)(gid >> 4);			// slot * TD_CAP + cluster
-				const uint32_t cell = (cj2 / (uint32_t)TD_CAP) * HIST_CELLS + ((uint32_t)gid & 15u);
-				red_add_u64(newsum + cj2, gsum);
-				red_add_u64(&st.hist_cur[cell].count, cnt);
-				red_add_u64((unsigned long long *)&st.hist_cur[cell].sum, msum);
-				atomicOr(st.bm_cur + cell, bits);
-			}
-		}
-	}
-}
-
-// (3) merge: one warp per touched service turns (sums, bounds) into the new clusters, merges them with the old centroids
-// (old first on ties) and runs the greedy pass again
-__global__ void __launch_bounds__(TD_WARPS * 32) td_merge_kernel(DevState st, const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_end,
-		const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p, const uint32_t *__restrict__ plan_bounds,
-		const uint32_t *__restrict__ plan_n, const unsigned long long *__restrict__ newsum, const uint2 *__restrict__ bminmax,
-		Centroid *__restrict__ newc_scratch /* [gridDim.x * TD_WARPS][TD_CAP] */)
+// One warp per touched service:
+//   (1) reads the service's NBINS bins in order; a non-empty bin becomes one item {mean = usec sum / samples, weight = samples} of
+//       the batch (items are in value order because the bin index is monotone) and adds {samples, msec sum} to its bucket of the
+//       window's histogram — GY_HISTOGRAM::add_data for every sample of the bin (common/gy_statistics.h:596-623); the bin is zeroed;
+//   (2) max_val_seen_ and the digest's ends from the batch's exact min / max;
+//   (3) the items are merged with the old centroids (old first on equal means) and the greedy K_1 pass cuts the list down to
+//       at most TD_CAP clusters (warp_merge_compress). Lists of up to 2 x TD_CAP entries work in shared memory; longer ones (a
+//       first batch of a service can fill several hundred bins) in the warp's L2-resident scratch — same code, same result.
+__global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p,
+		Centroid *__restrict__ items_scratch /* [nwarps][NBINS] */, TdWorkBig *__restrict__ big_scratch /* [nwarps] */)
 {
 	__shared__ TdWork work[TD_WARPS];
+	__shared__ unsigned long long hcnt[TD_WARPS][16], hsum[TD_WARPS][16];
+	__shared__ uint16_t first_idx[16];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	TdWork &S = work[wid];
-	Centroid *newc = newc_scratch + (size_t)(blockIdx.x * TD_WARPS + wid) * TD_CAP;		// this warp's list of new clusters (L2-resident)
+	const uint32_t gw = blockIdx.x * TD_WARPS + wid, nwarps = gridDim.x * TD_WARPS;
+	Centroid *items = items_scratch + (size_t)gw * NBINS;
 	const uint32_t ntouched = (uint32_t)*ntouched_p;
-	const uint32_t nwarps = gridDim.x * TD_WARPS;
-	for (uint32_t t = blockIdx.x * TD_WARPS + wid; t < ntouched; t += nwarps) {
-		const uint32_t slot = touched[t];
-		const uint32_t n = seg_end[slot] - seg_start[slot];
-		const uint32_t nnew = plan_n[slot] & 0x7FFFFFFFu;
-		const uint32_t *bounds = plan_bounds + (size_t)slot * PLAN_STRIDE;
-		const unsigned long long *sums = newsum + (size_t)slot * TD_CAP;
 
-		for (uint32_t j = lane; j < nnew; j += 32) {
-			const uint32_t w = bounds[j + 1] - bounds[j];
-			Centroid c; c.mean = __ddiv_rn((double)sums[j], (double)w); c.weight = w;	// cluster sums are exact integers
-			newc[j] = c;
-		}
-		const uint2 mm = bminmax[slot];
-		const double bmin = (double)mm.x, bmax = (double)mm.y;
-		// max_val_seen_ of GY_HISTOGRAM::add_data (gy_statistics.h:609-611)
-		if (lane == 0) atomicMax(&st.hist_cur[(size_t)slot * HIST_CELLS + HIST_MAX_CELL].sum, (long long)(mm.y / 1000u));
+	if (threadIdx.x < 15) {
+		// thresholds of RESP_TIME_HASH in msec (gy_statistics.h:1677): bucket b >= 1 starts at (thr[b-1] + 1) msec, bucket 14 at 15001
+		constexpr uint32_t thr[13] = {1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000};
+		const uint32_t b = threadIdx.x;
+		const uint32_t first_us = b == 0 ? 0u : (b == 1 ? 0u : (b == 14 ? 15001u * 1000u : (thr[b - 2] + 1u) * 1000u));
+		// bucket 0 holds negative values only (never produced: msec is unsigned); bucket 1 = 0 .. 1 msec
+		first_idx[b] = (uint16_t)(b == 0 ? 0u : td_code(first_us) + b);
+	}
+	__syncthreads();
+
+	for (uint32_t t = gw; t < ntouched; t += nwarps) {
+		const uint32_t slot = touched[t];
+		Bin *bins = st.bins + (size_t)slot * NBINS;
+		if (lane < 16) { hcnt[wid][lane] = 0; hsum[wid][lane] = 0; }
 		__syncwarp();
+		uint32_t nitems = 0;
+		unsigned long long nsamples = 0;
+		for (uint32_t i0 = 0; i0 < (uint32_t)NBINS; i0 += 32) {
+			const uint32_t i = i0 + lane;
+			Bin b {0, 0};
+			if (i < (uint32_t)NBINS) b = bins[i];
+			const bool nz = b.cw != 0;
+			const uint32_t m = __ballot_sync(0xffffffffu, nz);
+			if (nz) {
+				const unsigned long long cnt = b.cw & BIN_CNT_MASK, rem = b.cw >> BIN_CNT_BITS;
+				Centroid c; c.mean = __ddiv_rn((double)b.us, (double)cnt); c.weight = cnt;	// exact integer sum, one rounding
+				items[nitems + __popc(m & ((1u << lane) - 1u))] = c;
+				const uint32_t bk = bin_bucket(i, first_idx);
+				atomicAdd(&hcnt[wid][bk], cnt);
+				atomicAdd(&hsum[wid][bk], (b.us - rem) / 1000ull);			// sum of (usec / 1000) over the bin's samples
+				bins[i] = Bin {0, 0};
+				nsamples += cnt;
+			}
+			nitems += __popc(m);
+		}
+		__syncwarp();
+		nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 16); nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 8);
+		nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 4); nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 2);
+		nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 1);
+
+		// nobody else touches this slot's window histogram while the batch is merged (same stream as the flush): plain updates
+		const SlotBatch sb = st.slot_batch[slot];
+		if (lane < HIST_MAX_CELL) {
+			if (hcnt[wid][lane]) {
+				HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + lane;
+				c->count += hcnt[wid][lane]; c->sum += (long long)hsum[wid][lane];
+			}
+		}
+		else if (lane == HIST_MAX_CELL) {
+			HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + HIST_MAX_CELL;
+			const long long mx = (long long)(sb.maxv / 1000u);		// max_val_seen_ of add_data (gy_statistics.h:609-611)
+			if (mx > c->sum) c->sum = mx;
+			st.slot_batch[slot] = SlotBatch {0xFFFFFFFFu, 0u, 0u, 0u};
+		}
 
 		TdHead head = st.td_head[slot];
 		Centroid *cent = st.td_cent + (size_t)slot * TD_CAP;
-		const uint32_t nout = warp_merge_compress(S, cent, head.n, newc, nnew, cent, st.td);
+		uint32_t nout;
+		if (head.n + nitems <= 2u * TD_CAP) nout = warp_merge_compress(work[wid], cent, head.n, items, nitems, cent, st.td);
+		else nout = warp_merge_compress(big_scratch[gw], cent, head.n, items, nitems, cent, st.td);
 		if (lane == 0) {
 			head.n = nout;
-			head.total += n;
-			if (bmin < head.minv) head.minv = bmin;
-			if (bmax > head.maxv) head.maxv = bmax;
+			head.total += nsamples;
+			if ((double)sb.minv < head.minv) head.minv = (double)sb.minv;
+			if ((double)sb.maxv > head.maxv) head.maxv = (double)sb.maxv;
 			st.td_head[slot] = head;
 		}
 		__syncwarp();
@@ -1291,20 +997,6 @@ int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_
 	return 1;
 }
 
-// the radix passes of the RESP keys: sort word = {slot | code}, TD_CODE_BITS + slot bits significant bits cut into the fewest
-// digits of at most 9 bits, widths as even as possible (27 bits -> 9 9 9; 30 bits -> 8 8 7 7)
-int vk_sort_plan(uint32_t max_svcs, int shift[OS_MAX_PASSES_VK], int bits[OS_MAX_PASSES_VK])
-{
-	int slot_bits = 1;
-	while (slot_bits < 29 && (1ull << slot_bits) < max_svcs) slot_bits++;
-	const int T = TD_CODE_BITS + slot_bits;
-	const int np = (T + RADIX_MAX_BITS - 1) / RADIX_MAX_BITS;
-	if (np > OS_MAX_PASSES_VK) return -1;
-	int at = 0;
-	for (int p = 0; p < np; ++p) { bits[p] = T / np + (p < T % np ? 1 : 0); shift[p] = at; at += bits[p]; }
-	return np;
-}
-
 // GYSK_INGEST_VARIANT selects a shape of the warp-autonomous ingest kernel for A/B runs
 static int ingest_variant()
 {
@@ -1313,8 +1005,7 @@ static int ingest_variant()
 }
 
 template <int WARPS, int MIN_CTAS, int EPT, bool TMA>
-static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, uint32_t *ghist, const SortPlan &plan,
-		int dev, cudaStream_t s)
+static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, int dev, cudaStream_t s)
 {
 	using Shared = IngestSharedT<WARPS, EPT, TMA>;
 	static bool attr_set[MAX_DEVICES] = {};
@@ -1324,26 +1015,23 @@ static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, ui
 	}
 	const uint64_t want = (n + (uint64_t)Shared::CHUNK * WARPS - 1) / ((uint64_t)Shared::CHUNK * WARPS);
 	const uint64_t full = (uint64_t)sm_count(dev) * MIN_CTAS;
-	ingest_kernel<WARPS, MIN_CTAS, EPT, TMA><<<(uint32_t)(want < full ? want : full), WARPS * 32, sizeof(Shared), s>>>(st, d_ev, n, d_keys, ghist, plan);
+	ingest_kernel<WARPS, MIN_CTAS, EPT, TMA><<<(uint32_t)(want < full ? want : full), WARPS * 32, sizeof(Shared), s>>>(st, d_ev, n, 0);
 }
 
-int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_ev, uint64_t n, uint32_t max_svcs, cudaStream_t s)
+int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, cudaStream_t s)
 {
 	if (!n) return 0;
 	const int dev = current_device();
-	SortPlan plan {};
-	plan.np = vk_sort_plan(max_svcs, plan.shift, plan.bits);
-	// key cursor, digit histograms and tile tickets of this batch's sort
-	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, sizeof(unsigned long long), s);
-	cudaMemsetAsync(tmp.os_ghist, 0, (OS_MAX_PASSES * RADIX_MAX + OS_MAX_PASSES) * sizeof(uint32_t), s);
 	switch (ingest_variant()) {
-	case 842 : launch_ingest_variant<8, 4, 2, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
-	case 834 : launch_ingest_variant<8, 3, 4, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
-	case 832 : launch_ingest_variant<8, 3, 2, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
-	case 442 : launch_ingest_variant<4, 8, 2, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
-	case 1832 : launch_ingest_variant<8, 3, 2, true>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;	// TMA-staged chunks
-	case 1834 : launch_ingest_variant<8, 2, 4, true>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
-	default : launch_ingest_variant<8, 4, 2, false>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); break;
+	case 842 : launch_ingest_variant<8, 4, 2, false>(st, d_ev, n, dev, s); break;
+	case 852 : launch_ingest_variant<8, 5, 2, false>(st, d_ev, n, dev, s); break;
+	case 834 : launch_ingest_variant<8, 3, 4, false>(st, d_ev, n, dev, s); break;
+	case 844 : launch_ingest_variant<8, 4, 4, false>(st, d_ev, n, dev, s); break;
+	case 832 : launch_ingest_variant<8, 3, 2, false>(st, d_ev, n, dev, s); break;
+	case 482 : launch_ingest_variant<4, 8, 2, false>(st, d_ev, n, dev, s); break;
+	case 1842 : launch_ingest_variant<8, 4, 2, true>(st, d_ev, n, dev, s); break;	// TMA-staged chunks
+	case 1834 : launch_ingest_variant<8, 3, 4, true>(st, d_ev, n, dev, s); break;
+	default : launch_ingest_variant<8, 4, 2, false>(st, d_ev, n, dev, s); break;
 	}
 	return 1;
 }
@@ -1387,10 +1075,8 @@ static void os_set_attrs(int dev)
 {
 	static bool attr_set[MAX_DEVICES] = {};
 	if (attr_set[dev]) return;
-	cudaFuncSetAttribute(os_pass_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<8>));
-	cudaFuncSetAttribute(os_pass_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<9>));
-	cudaFuncSetAttribute(os_pass_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<8>));
-	cudaFuncSetAttribute(os_pass_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<9>));
+	cudaFuncSetAttribute(os_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<8>));
+	cudaFuncSetAttribute(os_pass_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<9>));
 	cudaFuncSetAttribute(os_hist_kernel<8, 257>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 8 * 257 * (int)sizeof(uint32_t));
 	cudaFuncSetAttribute(os_hist_kernel<4, 513>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 4 * 513 * (int)sizeof(uint32_t));
 	attr_set[dev] = true;
@@ -1435,8 +1121,8 @@ int launch_radix_sort(const SortTemp &tmp, const unsigned long long *d_n, uint64
 	for (int p = 0; p < P.np; ++p) {
 		const bool nine = P.d[p].b1 + P.d[p].b2 > 8;
 		const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
-		if (nine) os_pass_kernel<9, false><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], d_n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
-		else os_pass_kernel<8, false><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], d_n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
+		if (nine) os_pass_kernel<9><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], d_n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
+		else os_pass_kernel<8><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], d_n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
 		launches++;
 		w ^= 1;
 	}
@@ -1444,46 +1130,16 @@ int launch_radix_sort(const SortTemp &tmp, const unsigned long long *d_n, uint64
 	return launches;
 }
 
-// sort the keys ingest_kernel emitted by (slot, code), then fold every touched service's new samples into its histogram cells
-// and its digest. Nothing here needs a number from the device on the host: the key count lives in st.counters[CTR_NKEYS], the
-// digit histograms in tmp.os_ghist (both written by ingest_kernel); grids are sized by n_events, the largest possible key count.
-int launch_tdigest_update(const DevState &st, const SortTemp &tmp, uint64_t n_events, uint32_t max_svcs, cudaStream_t s)
+// after the ingest kernel of a batch: every service that received RESP samples gets its bins folded into its window histogram
+// and its digest. Nothing here needs a number from the device on the host: the list length stays in st.counters[CTR_NTOUCHED].
+int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint32_t max_svcs, cudaStream_t s)
 {
-	if (!n_events) return 0;
-	if (n_events >= (1ull << 30)) return -1;
-	int launches = 0;
-	unsigned long long *d_nkeys = st.counters + CTR_NKEYS, *d_ntouched = st.counters + CTR_NTOUCHED;
-	const int dev = current_device();
-	const int nsm = sm_count(dev);
-	os_set_attrs(dev);
-
-	SortPlan plan {};
-	plan.np = vk_sort_plan(max_svcs, plan.shift, plan.bits);
-	if (plan.np < 0) return -1;
-	const uint32_t ntiles = div_up(n_events, SORT_TILE);
-	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
-	uint32_t *ghist = tmp.os_ghist, *tickets = tmp.os_ghist + OS_MAX_PASSES * RADIX_MAX;
-	int w = 0;
-
-	for (int p = 0; p < plan.np; ++p) {
-		const DigitSpec D { plan.shift[p], plan.bits[p], 0, 0 };
-		const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
-		if (plan.bits[p] > 8) os_pass_kernel<9, true><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], d_nkeys, D, ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
-		else os_pass_kernel<8, true><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], d_nkeys, D, ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
-		launches++;
-		w ^= 1;
-	}
-	const unsigned long long *src = bufs[w];
-
+	const int nsm = sm_count(current_device());
+	unsigned long long *d_ntouched = st.counters + CTR_NTOUCHED;
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
-	cudaMemsetAsync(tmp.runbits2, 0, ((size_t)(n_events >> 15) + 1) * sizeof(uint32_t), s);
-	td_segments_kernel<<<div_up(n_events, 256 * TSEG_V), 256, 0, s>>>(src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.runbits, tmp.runbits2);
-	td_plan_kernel<<<nsm * 2, 128, 0, s>>>(st.td, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.runbits, tmp.runbits2, tmp.plan_bounds, tmp.plan_n,
-			tmp.newsum, tmp.bminmax);
-	td_sums_kernel<<<nsm * 8, 256, 0, s>>>(st, src, d_nkeys, tmp.seg_start, tmp.seg_end, tmp.plan_bounds, tmp.plan_n, tmp.newsum, tmp.bminmax);
-	td_merge_kernel<<<nsm * TD_MERGE_CTAS_PER_SM, TD_WARPS * 32, 0, s>>>(st, tmp.seg_start, tmp.seg_end, tmp.touched, d_ntouched, tmp.plan_bounds, tmp.plan_n,
-			tmp.newsum, tmp.bminmax, tmp.newc_scratch);
-	return launches + 4;
+	touched_kernel<<<div_up(max_svcs, 256), 256, 0, s>>>(st, max_svcs, tmp.touched, d_ntouched);
+	bins_merge_kernel<<<std::min(nsm, TD_MERGE_MAX_SMS) * TD_MERGE_CTAS_PER_SM, TD_WARPS * 32, 0, s>>>(st, tmp.touched, d_ntouched, tmp.items_scratch, tmp.big_scratch);
+	return 2;
 }
 
 // ---------------------------------------------------------------------------------------------------

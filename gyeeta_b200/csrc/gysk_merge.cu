@@ -19,6 +19,8 @@
 #include "gysk_engine.h"
 
 #include <climits>
+#include <dlfcn.h>
+#include <nccl.h>		// types only: the library is dlopen()ed, libgysketch.so carries no link-time dependency on it
 
 using namespace gysk;
 
@@ -189,6 +191,70 @@ inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) /
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 } // namespace
+
+// ---- NCCL inside the library: the whole merge step of one query window as ONE call -------------------
+//
+// A C++ madhava has no torch.distributed: it calls gysk_merge_global(engine, comm) per engine (one thread per GPU, or inside its
+// own ncclGroupStart/End when one thread drives all eight). libnccl.so.2 is resolved at first use with dlopen — a process that
+// already carries NCCL (torch) shares that copy — so single-GPU deployments and the CPU-side ABI tests need no NCCL at all.
+namespace {
+
+struct NcclApi
+{
+	void *h {nullptr};
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) {nullptr};
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) {nullptr};
+	ncclResult_t (*CommDestroy)(ncclComm_t) {nullptr};
+	ncclResult_t (*CommCount)(const ncclComm_t, int *) {nullptr};
+	ncclResult_t (*CommUserRank)(const ncclComm_t, int *) {nullptr};
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) {nullptr};
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) {nullptr};
+	ncclResult_t (*GroupStart)() {nullptr};
+	ncclResult_t (*GroupEnd)() {nullptr};
+	const char *(*GetErrorString)(ncclResult_t) {nullptr};
+	std::string err;
+};
+
+NcclApi *nccl_api()
+{
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		for (const char *name : {"libnccl.so.2", "libnccl.so"}) { api.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (api.h) break; }
+		if (!api.h) { api.err = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return; }
+		auto sym = [&](const char *n) { void *p = dlsym(api.h, n); if (!p && api.err.empty()) api.err = std::string("libnccl lacks ") + n; return p; };
+		api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+		api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+		api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+		api.CommCount = (decltype(api.CommCount))sym("ncclCommCount");
+		api.CommUserRank = (decltype(api.CommUserRank))sym("ncclCommUserRank");
+		api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+		api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+		api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+		api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+		api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+	});
+	return api.err.empty() ? &api : nullptr;
+}
+
+int nccl_fail(gysk_engine *e, const char *what, ncclResult_t r)
+{
+	NcclApi *a = nccl_api();
+	char buf[256];
+	snprintf(buf, sizeof(buf), "%s: %s", what, a && a->GetErrorString ? a->GetErrorString(r) : "nccl error");
+	return fail(e, GYSK_ERR_CUDA, buf);		// sticky, like a CUDA error
+}
+
+} // namespace
+
+namespace gysk {
+void merge_release(gysk_engine *e)
+{
+	if (e->mg.comm && e->mg.comm_owned) { NcclApi *a = nccl_api(); if (a) a->CommDestroy((ncclComm_t)e->mg.comm); }
+	e->mg.comm = nullptr;
+}
+} // namespace gysk
+
 
 extern "C" {
 
@@ -415,6 +481,72 @@ int gysk_query_flows_global(gysk_engine *e, const uint64_t *keys, uint32_t n, in
 		memcpy(out + off, e->h_flowout, (size_t)m * sizeof(gysk_flow_est));
 	}
 	return post_launch(e, "query_flows_global");
+}
+
+#define NC(e, call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return nccl_fail((e), #call, r__); } while (0)
+
+int gysk_nccl_unique_id(uint8_t out[GYSK_NCCL_UNIQUE_ID_BYTES])
+{
+	NcclApi *a = nccl_api();
+	if (!out) return GYSK_ERR_INVAL;
+	if (!a) return GYSK_ERR_NOTSUP;
+	static_assert(sizeof(ncclUniqueId) == GYSK_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+	ncclUniqueId id;
+	if (a->GetUniqueId(&id) != ncclSuccess) return GYSK_ERR_CUDA;
+	memcpy(out, &id, sizeof(id));
+	return GYSK_OK;
+}
+
+int gysk_nccl_comm_init(gysk_engine *e, const uint8_t uid[GYSK_NCCL_UNIQUE_ID_BYTES], uint32_t nranks, uint32_t rank)
+{
+	CHECK_ENGINE(e);
+	if (!uid || !nranks || rank >= nranks) return GYSK_ERR_INVAL;
+	NcclApi *a = nccl_api();
+	if (!a) return fail(e, GYSK_ERR_NOTSUP, "libnccl.so.2 could not be loaded");
+	std::lock_guard<std::mutex> lk(e->mtx);
+	CU(e, cudaSetDevice(e->dev));
+	if (e->mg.comm) { a->CommDestroy((ncclComm_t)e->mg.comm); e->mg.comm = nullptr; }
+	ncclUniqueId id;
+	memcpy(&id, uid, sizeof(id));
+	ncclComm_t c = nullptr;
+	NC(e, a->CommInitRank(&c, (int)nranks, id, (int)rank));
+	e->mg.comm = c; e->mg.comm_world = nranks; e->mg.comm_owned = true;
+	return GYSK_OK;
+}
+
+// prepare (fold) -> one grouped NCCL launch: all-reduce per reduction kind + all-gather of the t-digest slabs -> finish.
+// comm == NULL uses the communicator of gysk_nccl_comm_init. Everything is enqueued on the engine's stream; nothing blocks.
+int gysk_merge_global(gysk_engine *e, void *comm)
+{
+	CHECK_ENGINE(e);
+	NcclApi *a = nccl_api();
+	if (!a) return fail(e, GYSK_ERR_NOTSUP, "libnccl.so.2 could not be loaded");
+	ncclComm_t c = comm ? (ncclComm_t)comm : (ncclComm_t)e->mg.comm;
+	if (!c) return fail(e, GYSK_ERR_INVAL, "gysk_merge_global: no communicator (pass one or call gysk_nccl_comm_init)");
+	int rc = gysk_merge_prepare(e);
+	if (rc) return rc;
+	int world = 0;
+	{
+		std::lock_guard<std::mutex> lk(e->mtx);
+		CU(e, cudaSetDevice(e->dev));
+		MergeState &mg = e->mg;
+		NC(e, a->CommCount(c, &world));
+		if (world < 1) return fail(e, GYSK_ERR_INVAL, "gysk_merge_global: empty communicator");
+		if (mg.gathered_world != (uint32_t)world) {
+			if (mg.gathered) { cudaFree(mg.gathered); e->dallocs.erase(std::remove(e->dallocs.begin(), e->dallocs.end(), (void *)mg.gathered), e->dallocs.end()); mg.gathered = nullptr; }
+			if ((rc = dalloc(e, &mg.gathered, mg.slab_bytes * (size_t)world, false))) return rc;
+			mg.gathered_world = (uint32_t)world;
+		}
+		const size_t slab = (size_t)mg.nlogical * sizeof(SlabEntry);
+		NC(e, a->GroupStart());
+		NC(e, a->AllReduce(mg.arena + mg.off_sum, mg.arena + mg.off_sum, mg.bytes_sum / 8, ncclUint64, ncclSum, c, e->stream));
+		NC(e, a->AllReduce(mg.arena + mg.off_maxi64, mg.arena + mg.off_maxi64, mg.bytes_maxi64 / 8, ncclInt64, ncclMax, c, e->stream));
+		NC(e, a->AllReduce(mg.arena + mg.off_maxu8, mg.arena + mg.off_maxu8, mg.bytes_maxu8, ncclUint8, ncclMax, c, e->stream));
+		if (slab) NC(e, a->AllGather(mg.slab, mg.gathered, slab, ncclUint8, c, e->stream));
+		NC(e, a->GroupEnd());
+		e->merges++;
+	}
+	return gysk_merge_finish(e, e->mg.nlogical ? e->mg.gathered : nullptr, (uint32_t)world);
 }
 
 } // extern "C"

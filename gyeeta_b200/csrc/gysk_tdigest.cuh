@@ -32,13 +32,17 @@ __device__ __forceinline__ double td_wlimit(unsigned long long wsofar, unsigned 
 	return __dmul_rn((double)W, td_q_next(q0, P));
 }
 
-struct TdWork				// per warp: 10.3 KB
+template <int NMAX_>
+struct TdWorkT				// per warp; NMAX = 2 x TD_CAP: 9.7 KB
 {
-	double			mean[2 * TD_CAP];		// merged list: means ...
-	unsigned long long	pref[2 * TD_CAP + 1];		// ... and exclusive weight prefix: weight of item i = pref[i+1] - pref[i]
-	uint16_t		bounds[2 * TD_CAP + 2];
-	uint16_t		nxt[2 * TD_CAP];
+	static constexpr int NMAX = NMAX_;			// capacity of the merged list, a multiple of 32
+	double			mean[NMAX];			// merged list: means ...
+	unsigned long long	pref[NMAX + 1];			// ... and exclusive weight prefix: weight of item i = pref[i+1] - pref[i]
+	uint16_t		bounds[TD_CAP + 2];
+	uint16_t		nxt[NMAX];
 };
+using TdWork = TdWorkT<2 * TD_CAP>;			// shared memory: two lists of up to TD_CAP centroids
+using TdWorkBig = TdWorkT<1120>;			// global scratch: TD_CAP old centroids + up to NBINS (848) items of a batch
 struct TdScratch : TdWork		// + an accumulator list for the folds of the merge step: 14.3 KB
 {
 	Centroid		newc[TD_CAP];
@@ -47,12 +51,13 @@ struct TdScratch : TdWork		// + an accumulator list for the folds of the merge s
 // Stable merge by mean of two mean-sorted centroid lists (`a` first on ties), then the greedy K_1 pass; one warp.
 // Both inputs are fully consumed into S.mean / S.pref before `out` is written, so `out` may alias `a` or `b`.
 // a and b may live in shared or global memory. Returns the number of centroids written to out (<= TD_CAP).
-__device__ __forceinline__ uint32_t warp_merge_compress(TdWork &S, const Centroid *a, uint32_t na, const Centroid *b, uint32_t nb,
+template <typename Work>
+__device__ __forceinline__ uint32_t warp_merge_compress(Work &S, const Centroid *a, uint32_t na, const Centroid *b, uint32_t nb,
 		Centroid *out, const TdParams &P)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t nm = na + nb;
-	constexpr int IPL = 2 * TD_CAP / 32;		// merged items per lane
+	constexpr int IPL = Work::NMAX / 32;		// merged items per lane
 
 	for (uint32_t j = lane; j < na; j += 32) {
 		const Centroid c = a[j];

@@ -62,3 +62,12 @@ def merge_global(eng, torch, dist, device=None):
     eng.merge_finish(gathered.data_ptr(), world)
     merge_global.last_events = (t0, t1)
     return 0.0
+
+
+def nccl_comm_init(eng, dist):
+    """create the library-side NCCL communicator (gysk_nccl_comm_init): rank 0's unique id travels through torch.distributed
+    once; from then on the merge step is ONE C-ABI call, gysk_merge_global, with NCCL issued inside libgysketch.so"""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    box = [eng.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    eng.nccl_comm_init(box[0], world, rank)

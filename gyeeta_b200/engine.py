@@ -116,7 +116,6 @@ def load_library(path=None):
         "gysk_export_tdigest": (i32, [vp, u64, vp, vp, u32, vp, vp, vp]),
         "gysk_query_quantiles": (i32, [vp, u64, vp, u32, vp]),
         "gysk_tdigest_to_pgtext": (i32, [vp, vp, u32, u32, vp, u32]),
-        "gysk_sort_plan": (i32, [u32, u32, vp, vp]),
         "gysk_encode_listener_state": (i32, [vp, u32, vp, u32, vp, vp]),
         "gysk_export_tdigest_pgtext": (i32, [vp, u64, vp, u32]),
         "gysk_export_cms": (i32, [vp, i32, vp]),
@@ -133,6 +132,9 @@ def load_library(path=None):
         "gysk_merge_finish": (i32, [vp, vp, u32]),
         "gysk_query_logical": (i32, [vp, vp, u32, vp]),
         "gysk_query_flows_global": (i32, [vp, vp, u32, i32, vp]),
+        "gysk_nccl_unique_id": (i32, [vp]),
+        "gysk_nccl_comm_init": (i32, [vp, vp, u32, u32]),
+        "gysk_merge_global": (i32, [vp, vp]),
         "gysk_stream": (vp, [vp]),
         "gysk_profile_enable": (i32, [vp, i32]),
         "gysk_profile_read": (i32, [vp, vp, vp, vp]),
@@ -374,6 +376,19 @@ class Engine:
 
     def merge_finish(self, gathered_ptr=None, world=1):
         self._chk(self.L.gysk_merge_finish(self.h, C.c_void_p(gathered_ptr), world))
+
+    def nccl_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        self._chk(self.L.gysk_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def nccl_comm_init(self, uid, nranks, rank):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._chk(self.L.gysk_nccl_comm_init(self.h, buf, nranks, rank))
+
+    def merge_global(self, comm=None):
+        """fold + one grouped NCCL launch + merge-compress, all inside the library (gysk_merge_global)"""
+        self._chk(self.L.gysk_merge_global(self.h, C.c_void_p(comm)))
 
     def query_logical(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.uint64)

@@ -135,8 +135,9 @@ typedef struct gysk_config
 	uint32_t	cms_depth;		/* rows, 1..8 (default 4) */
 	uint32_t	cms_log2_width;		/* columns = 1 << this (default 20) */
 	uint32_t	hll_p;			/* registers per service = 1 << p, 4..16 (default 12) */
-	uint32_t	td_compression;		/* t-digest delta (default 100 = public.tdigest(x, 100), gy_query_common.cc:1855) */
-	uint32_t	max_batch;		/* max events per device batch = one ingest + sort + t-digest pass (default 1 << 22) */
+	uint32_t	td_compression;		/* t-digest delta, 10..220 (default 200: up to 256 centroids kept; exports for Postgres are
+						   recompressed to public.tdigest(x, 100), gy_query_common.cc:1855) */
+	uint32_t	max_batch;		/* max events per device batch = one ingest + merge pass, < 2^27 (default 1 << 22) */
 	uint32_t	flags;			/* GYSK_FLAG_* */
 	uint32_t	rank, world;		/* this engine owns events with host_idx % world == rank; world 0/1 = all */
 	uint32_t	stage_batch;		/* events per host staging buffer / H2D chunk; 0 = min(max_batch, 1 << 22) */
@@ -310,10 +311,6 @@ double		gysk_hll_estimate(const uint8_t *regs, uint32_t p);
  * NOTIFY_LISTENER_STATE message (<= 512 records, 88 bytes each) that MTCP_LISTENER::set_state / partha_listener_state consume
  * (server/gy_mconnhdlr.cc:11175-11251). Entries with found == 0 are skipped. No engine needed. */
 int		gysk_encode_listener_state(const gysk_svc_summary *sums, uint32_t n, void *buf, uint32_t cap, uint32_t *nrecs, uint32_t *nbytes);
-/* introspection: the stable LSD radix passes over the RESP sort keys {slot | usec | port} for a batch whose largest response
- * time has value_bits significant usec bits and whose engine has handed out nslots service slots. out[p] = {shift1, bits1,
- * shift2, bits2}: the pass's digit is ((key >> shift1) & ((1 << bits1) - 1)) | (((key >> shift2) & ((1 << bits2) - 1)) << bits1). */
-int		gysk_sort_plan(uint32_t value_bits, uint32_t nslots, int32_t out[8][4], uint32_t *npasses);
 /* a digest in the text form of the Postgres `tdigest` type the reference stores and queries (public.tdigest(expr, 100) /
  * tdigest_percentile, common/gy_query_common.cc:1805-1858): "flags 1 count N compression C centroids K (mean, count) ...".
  * Both return the string length, or a negative GYSK_ERR_* */
@@ -329,6 +326,16 @@ int		gysk_merge_prepare(gysk_engine *e);		/* fold per-service sketches into per-
 int		gysk_merge_buffers(gysk_engine *e, gysk_buffer_desc *out, uint32_t cap, uint32_t *n);
 int		gysk_merge_tdigest_slab(gysk_engine *e, void **dptr, uint64_t *nbytes);	/* fixed slab to all-gather */
 int		gysk_merge_finish(gysk_engine *e, const void *d_gathered_slabs, uint32_t world);
+/* The same step with NCCL inside the library (a C++ madhava has no torch.distributed): fold, then ONE grouped NCCL launch — an
+ * all-reduce per reduction kind (u64 SUM, i64 MAX, u8 MAX) and the all-gather of the t-digest slabs — then the merge-compress,
+ * all enqueued on the engine's stream. libnccl.so.2 is loaded on first use (dlopen; GYSK_ERR_NOTSUP when absent).
+ * comm: an ncclComm_t created by the caller over the engines' devices (ncclCommInitAll / ncclCommInitRank), or NULL to use the one
+ * gysk_nccl_comm_init() made: rank 0 calls gysk_nccl_unique_id(), ships the 128 bytes to its peers, every rank calls
+ * gysk_nccl_comm_init(engine, uid, nranks, rank). */
+#define GYSK_NCCL_UNIQUE_ID_BYTES	128
+int		gysk_nccl_unique_id(uint8_t out[GYSK_NCCL_UNIQUE_ID_BYTES]);
+int		gysk_nccl_comm_init(gysk_engine *e, const uint8_t uid[GYSK_NCCL_UNIQUE_ID_BYTES], uint32_t nranks, uint32_t rank);
+int		gysk_merge_global(gysk_engine *e, void *nccl_comm);
 int		gysk_query_logical(gysk_engine *e, const uint64_t *logical_ids, uint32_t n, gysk_svc_summary *out);
 int		gysk_query_flows_global(gysk_engine *e, const uint64_t *flow_keys, uint32_t n, int last_window, gysk_flow_est *out);
 

@@ -459,64 +459,42 @@ uint32_t gyo_td_code(uint32_t v)
 	return ((sh + 1u) << 5) | ((v >> sh) & 31u);
 }
 
-/* What the CUDA path does for one device batch and service:
- * (1) the n new samples, ordered by code, are cut into clusters by the greedy rule over unit weights, except that a cluster
- *     never splits a bin: a cluster that starts at rank s (a bin boundary) ends at the last bin boundary <= floor(n q(k(s/n) + 1)),
- *     or at the end of its first bin when that lies beyond. Cluster sums are exact integers, so the result does not depend
- *     on the order of the samples inside a bin;
- * (2) the new clusters are merged with the old centroids (old first on equal means) and compressed again. */
+/* What the CUDA path does for one device batch and service: the batch's samples fall into value bins — bin index =
+ * gyo_td_code(usec) + RESP_TIME_HASH bucket of usec / 1000, monotone in usec, so no bin straddles a histogram bucket — and
+ * every non-empty bin becomes ONE item {mean = exact usec sum / samples, weight = samples}. The items, in bin order, are merged
+ * with the old centroids (old first on equal means) and one greedy pass (with the ladder) cuts the list to <= GYO_TD_CAP. */
+#define GYO_NBINS	848
+
+static uint32_t td_bin_index(uint32_t usec)
+{
+	return gyo_td_code(usec) + (uint32_t)gyo_bucket(GYO_CLS_RESP_TIME, (int64_t)(usec / 1000u));
+}
+
 void gyo_td_add_batch(gyo_tdigest *t, const uint32_t *vals, uint32_t n, double delta)
 {
 	if (!n) return;
 
-	uint32_t	*sv = (uint32_t *)malloc(sizeof(uint32_t) * n);
-	uint32_t	*rstart = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n + 1));	/* rank -> start of the bin it lies in */
-	uint32_t	bounds[GYO_TD_CAP + 1];
-	gyo_centroid	newc[GYO_TD_CAP], merged[2 * GYO_TD_CAP];
-	gyo_centroid	outc[GYO_TD_CAP + 1];
-	td_params	P[TD_LADDER];
-	uint32_t	nnew = 0;
+	static __thread uint64_t	bcnt[GYO_NBINS], bsum[GYO_NBINS];
+	gyo_centroid	items[GYO_NBINS], merged[GYO_NBINS + GYO_TD_CAP], outc[GYO_TD_CAP + 1];
+	uint32_t	nitems = 0, vmin = vals[0], vmax = vals[0];
 
-	memcpy(sv, vals, sizeof(uint32_t) * n);
-	qsort(sv, n, sizeof(uint32_t), cmp_u32);
-	for (uint32_t i = 0; i < n; ++i) rstart[i] = (i && gyo_td_code(sv[i]) == gyo_td_code(sv[i - 1])) ? rstart[i - 1] : i;
-	rstart[n] = n;
+	memset(bcnt, 0, sizeof(bcnt)); memset(bsum, 0, sizeof(bsum));
+	for (uint32_t i = 0; i < n; ++i) {
+		uint32_t b = td_bin_index(vals[i]);
 
-	td_make_ladder(delta, P);
-	for (int k = 0; k < TD_LADDER; ++k) {
-		const int final = k == TD_LADDER - 1;
-		uint32_t s = 0;
-		int overflow = 0;
-
-		nnew = 0;
-		while (s < n) {
-			double wlimit = td_wlimit(s, n, &P[k]);
-			uint64_t x = (uint64_t)floor(wlimit);
-			uint32_t e;
-
-			if (x > n) x = n;
-			e = rstart[x];					/* last bin boundary <= x */
-			if (e <= s) { e = s + 1; while (e < n && rstart[e] != e) ++e; }	/* at least the first bin */
-			if (final && nnew == GYO_TD_CAP - 1) e = n;		/* the last slot absorbs whatever is left */
-			if (nnew == GYO_TD_CAP) { overflow = 1; break; }
-			bounds[nnew++] = s;
-			s = e;
-		}
-		if (!overflow) break;
+		bcnt[b]++; bsum[b] += vals[i];
+		if (vals[i] < vmin) vmin = vals[i];
+		if (vals[i] > vmax) vmax = vals[i];
 	}
-	bounds[nnew] = n;
-	for (uint32_t j = 0; j < nnew; ++j) {
-		uint64_t sum = 0;
-
-		for (uint32_t i = bounds[j]; i < bounds[j + 1]; ++i) sum += sv[i];
-		newc[j].mean = (double)sum / (double)(bounds[j + 1] - bounds[j]); newc[j].weight = bounds[j + 1] - bounds[j];
+	for (uint32_t b = 0; b < GYO_NBINS; ++b) {
+		if (!bcnt[b]) continue;
+		items[nitems].mean = (double)bsum[b] / (double)bcnt[b]; items[nitems].weight = bcnt[b];
+		nitems++;
 	}
+	if ((double)vmin < t->minv) t->minv = (double)vmin;
+	if ((double)vmax > t->maxv) t->maxv = (double)vmax;
 
-	if ((double)sv[0] < t->minv) t->minv = (double)sv[0];
-	if ((double)sv[n - 1] > t->maxv) t->maxv = (double)sv[n - 1];
-	free(sv); free(rstart);
-
-	uint32_t nm = merge_sorted(t->c, t->n, newc, nnew, merged);
+	uint32_t nm = merge_sorted(t->c, t->n, items, nitems, merged);
 	uint32_t no = gyo_td_compress(merged, nm, delta, outc, GYO_TD_CAP);
 
 	if (no > GYO_TD_CAP) no = GYO_TD_CAP;

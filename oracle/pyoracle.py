@@ -138,7 +138,7 @@ def ref():
         R.gyref_jhash.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         R.gyref_sizeof_hist_resp.restype = C.c_size_t
         R.gyref_bench_resp_hist.restype = C.c_double
-        R.gyref_bench_resp_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
+        R.gyref_bench_resp_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         _ref = R
     return _ref
 
@@ -260,3 +260,19 @@ def td_add(td, vals, delta=200.0, classic=False):
     fn = lib().gyo_td_add_classic if classic else lib().gyo_td_add_batch
     fn(C.byref(td), _p(vals), len(vals), delta)
     return td
+
+
+def ref_hist_rate(slots, vals_ms, nthreads):
+    """samples/s of the REFERENCE's own GY_HISTOGRAM::add_data (oracle/_ref), samples pre-sharded by slot % nthreads"""
+    R = ref()
+    if R is None:
+        return None
+    slots = np.ascontiguousarray(slots, dtype=np.uint32)
+    owner = (slots % nthreads).astype(np.int32)
+    order = np.argsort(owner, kind="stable")
+    s2 = np.ascontiguousarray(slots[order]); v2 = np.ascontiguousarray(np.asarray(vals_ms, dtype=np.int64)[order])
+    offs = np.concatenate([[0], np.cumsum(np.bincount(owner, minlength=nthreads))]).astype(np.uint64)
+    tot = C.c_uint64()
+    sec = R.gyref_bench_resp_hist(_p(s2), _p(v2), _p(offs), int(slots.max()) + 1, nthreads, C.byref(tot))
+    assert tot.value == len(slots)
+    return len(slots) / sec

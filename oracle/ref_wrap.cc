@@ -130,10 +130,10 @@ uint32_t gyref_jhash(const void *k, uint32_t len, uint32_t iv)		{ return jhash(k
 
 size_t gyref_sizeof_hist_resp(void)				{ return sizeof(GY_HISTOGRAM<int64_t, RESP_TIME_HASH>); }
 
-// CPU baseline ("kind": "reference"): the reference's add_data loop over (slot, value) samples,
-// sharded over nthreads by slot % nthreads (mirrors l1_thr_num % maxthr, gy_mconnhdlr.cc:16252);
-// each thread owns a private array of histograms, no sharing. Returns seconds of wall time.
-double gyref_bench_resp_hist(const uint32_t *slots, const int64_t *vals_ms, size_t n, uint32_t nslots, int nthreads, uint64_t *out_total)
+// CPU baseline ("kind": "reference"): the reference's own GY_HISTOGRAM::add_data over (slot, value) samples that the caller has
+// PRE-SHARDED: thread t owns samples [offs[t], offs[t+1]) (its slots are private to it: slot % nthreads == t, mirrors
+// l1_thr_num % maxthr, gy_mconnhdlr.cc:16252) and a private array of histograms. Nothing but add_data in the timed region.
+double gyref_bench_resp_hist(const uint32_t *slots, const int64_t *vals_ms, const uint64_t *offs, uint32_t nslots, int nthreads, uint64_t *out_total)
 {
 	using H = GY_HISTOGRAM<int64_t, RESP_TIME_HASH>;
 
@@ -147,11 +147,7 @@ double gyref_bench_resp_hist(const uint32_t *slots, const int64_t *vals_ms, size
 
 	auto work = [&](int t) {
 		auto & mine = tbl[t];
-		for (size_t i = 0; i < n; ++i) {
-			uint32_t s = slots[i];
-			if ((int)(s % nthreads) != t) continue;
-			mine[s / nthreads].add_data(vals_ms[i], 1);
-		}
+		for (uint64_t i = offs[t]; i < offs[t + 1]; ++i) mine[slots[i] / nthreads].add_data(vals_ms[i], 1);
 	};
 
 	if (nthreads == 1) work(0);

@@ -12,7 +12,7 @@ from gyeeta_b200 import engine as ge  # noqa: E402
 
 dev = torch.device("cuda", 0)
 n = 50_000_000
-eng = ge.Engine(device=0, max_svcs=1 << 17, max_tasks=1 << 15, max_batch=1 << 27, stage_batch=1 << 23)
+eng = ge.Engine(device=0, max_svcs=1 << 17, max_tasks=1 << 15, max_batch=(1 << 27) - 1, stage_batch=1 << 23)
 ev = bench.gen_events_gpu(torch, n, 1234, 0, 1, dev)
 torch.cuda.synchronize()
 eng.ingest_device_ptr(ev.data_ptr(), n)

@@ -20,7 +20,7 @@ dev = torch.device("cuda", 0)
 bench.NSVC, bench.ZIPF_S = 1_000_000, 1.0
 n = 100_000_000
 free0 = torch.cuda.mem_get_info()[0]
-eng = ge.Engine(device=0, max_svcs=1 << 20, max_tasks=1 << 15, max_batch=1 << 27, stage_batch=1 << 22, idle_evict_secs=300)
+eng = ge.Engine(device=0, max_svcs=1 << 20, max_tasks=1 << 15, max_batch=(1 << 27) - 1, stage_batch=1 << 22, idle_evict_secs=300)
 held = free0 - torch.cuda.mem_get_info()[0]
 ev = bench.gen_events_gpu(torch, n, 77, 0, 1, dev)
 torch.cuda.synchronize()

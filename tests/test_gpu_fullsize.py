@@ -1,5 +1,5 @@
-"""BASELINE.json configurations at FULL size, checked through size-independent properties (the oracle would take minutes at these
-sizes): conservation (every event lands in exactly one counter / bucket), the count-min checksum of checksums (every row sums to
+"""BASELINE.json configurations at FULL size: bit-exact against the threaded CPU oracle (events pre-sharded by host, one oracle
+engine per host core), and size-independent properties: conservation (every event lands in exactly one counter / bucket), the count-min checksum of checksums (every row sums to
 the number of TCP events and to the total kbytes), idempotence of HLL under replay and exact doubling of the additive state,
 t-digest weight conservation and rank error, sortedness of centroids."""
 import numpy as np
@@ -36,7 +36,7 @@ def test_config1_one_million_samples_one_service():
     for q, g in zip((0.5, 0.95, 0.99), eng.quantiles(id_, [0.5, 0.95, 0.99])):
         ex = float(sv[int(np.ceil(q * len(sv))) - 1])
         assert abs(np.searchsorted(sv, g) / len(sv) - q) < 0.001
-        assert abs(g - ex) / ex < (0.01 if q < 0.99 else 0.03), (q, g, ex)
+        assert abs(g - ex) / ex < 0.01, (q, g, ex)
 
 
 def test_config2_ten_million_tcp_events_10k_services():
@@ -112,3 +112,100 @@ def test_config3_hundred_million_mixed_events_properties():
     for q, g in zip((0.5, 0.95, 0.99), got):
         rank = int(torch.searchsorted(sv, torch.tensor([int(g)], device=dev))[0]) / sv.numel()
         assert abs(rank - q) < 0.001, (q, g, rank)
+
+
+def test_config2_bit_exact_vs_threaded_oracle():
+    """configs[1] at full size (10 M tcp_conn events, 10 K services): the WHOLE count-min table, the HLL registers and the exact
+    {count, kbytes} cell of EVERY service, bit for bit against the CPU oracle"""
+    import os
+    from tests.util import threaded_oracle
+    rng = np.random.default_rng(2)
+    ev = synth.gen_tcp(rng, 10_000_000, 10_000, zipf_s=1.1, nclients=1_000_000, nhosts=512)
+    eng = ge.Engine(max_svcs=1 << 14, max_tasks=8, max_batch=1 << 24)
+    _ingest(eng, ev, chunk=1 << 24)
+    nthr = max(1, min(os.cpu_count() or 1, 64))
+    orcs, _ = threaded_oracle(ev, nthr, max_svcs=1 << 14, max_tasks=8)
+    cms = np.zeros(4 << 20, dtype=np.uint64)
+    for o in orcs:
+        cms += o.cms()
+    assert np.array_equal(eng.export_cms(), cms)
+    ids, first = np.unique(ev["svc_id"], return_index=True)
+    assert len(ids) > 9000
+    for id_, i0 in zip(ids, first):
+        o = orcs[int(ev["host_idx"][i0]) % nthr]
+        assert np.array_equal(eng.export_hll(int(id_)), o.export_hll(int(id_))), hex(int(id_))
+    summ = eng.query_svcs(ids)
+    eng.flush(5)
+    for o in orcs:
+        o.flush(5)
+    summ = eng.query_svcs(ids)
+    for s_, id_, i0 in zip(summ, ids, first):
+        c = orcs[int(ev["host_idx"][i0]) % nthr].export_conn(int(id_))
+        assert (s_["nconns_5s"], s_["kbytes_5s"]) == (c[1] & 0xFFFFFFFF, c[1] >> 32)
+
+
+def test_config3_bit_exact_sampled_services_vs_threaded_oracle():
+    """configs[2] at full size (100 M mixed events, 100 K services, one device batch): count-min table, and on 1 500 sampled
+    services (hot, lukewarm and cold) the RESP histogram, CONN_BITMAP, HLL registers and the t-digest — centroid for centroid —
+    plus 300 sampled task histograms, bit for bit against the CPU oracle"""
+    import os
+    import torch
+    import bench
+    from tests.util import threaded_oracle
+    dev = torch.device("cuda", 0)
+    n = 100_000_000
+    evd = bench.gen_events_gpu(torch, n, 77, 0, 1, dev)
+    torch.cuda.synchronize()
+    eng = ge.Engine(max_svcs=1 << 17, max_tasks=1 << 15, max_batch=(1 << 27) - 1)
+    eng.ingest_device_ptr(evd.data_ptr(), n)
+    eng.sync()
+    ev = evd.cpu().numpy().view(np.uint8).reshape(-1).view(ge.EVENT_DTYPE)
+    del evd
+    torch.cuda.empty_cache()
+    nthr = max(1, min(os.cpu_count() or 1, 128))
+    orcs, _ = threaded_oracle(ev, nthr, max_svcs=bench.NSVC + 16, max_tasks=bench.NTASK + 16)
+    cms = np.zeros(4 << 20, dtype=np.uint64)
+    for o in orcs:
+        cms += o.cms()
+    assert np.array_equal(eng.export_cms(), cms)
+    st = eng.stats()
+    tot = {k: sum(o.counters()[k] for o in orcs) for k in ("in", "dropped", "resp", "tcp", "task", "nsvcs")}
+    assert (st["events_in"], st["events_dropped"], st["events_resp"], st["events_tcp"], st["events_task"], st["nsvcs"]) == \
+        tuple(tot[k] for k in ("in", "dropped", "resp", "tcp", "task", "nsvcs"))
+    head = ev[:20_000_000]
+    svc = head[head["type"] != ge.EV_TASK]
+    ids, first, cnt = np.unique(svc["svc_id"], return_index=True, return_counts=True)
+    order = np.argsort(-cnt)
+    rng = np.random.default_rng(0)
+    pick = np.concatenate([order[:200], order[2000:2300], rng.choice(order[5000:], 1000, replace=False)])
+    ntd = 0
+    for j in pick:
+        id_ = int(ids[j])
+        o = orcs[int(svc["host_idx"][first[j]]) % nthr]
+        a, b = eng.export_hist(id_, ge.HIST_RESP_CUR), o.export_hist(id_, ge.HIST_RESP_CUR)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], hex(id_)
+        assert np.array_equal(eng.export_hll(id_), o.export_hll(id_)), hex(id_)
+        g, w = eng.export_conn_bitmap(id_), o.export_conn_bitmap(id_)
+        assert np.array_equal(g[0], w[0])
+        td = o.export_tdigest(id_)
+        means, weights, mn, mx = eng.export_tdigest(id_)
+        om, ow = td.centroids()
+        assert np.array_equal(weights, ow) and np.array_equal(means, om), hex(id_)
+        if len(ow):
+            assert mn == td.minv and mx == td.maxv
+            ntd += 1
+    assert ntd > 1000
+    tasks = head[head["type"] == ge.EV_TASK]
+    tids, tfirst = np.unique(tasks["svc_id"], return_index=True)
+    # the synthetic stream spreads a task's samples over hosts: its histograms are the sum over the oracle shards
+    for j in rng.choice(len(tids), 300, replace=False):
+        for which in (ge.HIST_TASK_CPU_PCT, ge.HIST_TASK_CPU_DELAY, ge.HIST_TASK_BLKIO_DELAY):
+            a = eng.export_hist(int(tids[j]), which)
+            cnt_, sum_, tot_, max_ = np.zeros(15, dtype=np.uint64), np.zeros(15, dtype=np.int64), 0, -(1 << 31)
+            for o in orcs:
+                b = o.export_hist(int(tids[j]), which)
+                if b is not None:
+                    cnt_ += b[0]["count"]; sum_ += b[0]["sum"]; tot_ += b[1]; max_ = max(max_, b[2])
+            assert np.array_equal(a[0]["count"], cnt_) and np.array_equal(a[0]["sum"], sum_) and a[1] == tot_ and a[2] == max_

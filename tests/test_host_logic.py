@@ -196,39 +196,16 @@ def test_td_code_is_monotone_and_matches_the_oracle():
                                   [(1 << 30) - 1, 1_000_000_999]]).astype(np.uint64))
     code = np_td_code(v)
     assert np.array_equal(code, np.array([L.gyo_td_code(int(x)) for x in v], dtype=np.uint64))
-    assert np.all(np.diff(code.astype(np.int64)) >= 0) and code.max() < 1024            # monotone, 10 bits
+    assert np.all(np.diff(code.astype(np.int64)) >= 0) and code.max() <= 831            # monotone; 832 codes + 15 buckets < NBINS = 848
+    # bin index = code + RESP_TIME_HASH bucket of the msec value: monotone too, and one bucket per bin
+    idx = code + np.array([L.gyo_bucket(0, int(x) // 1000) for x in v], dtype=np.uint64)
+    assert np.all(np.diff(idx.astype(np.int64)) >= 0) and idx.max() < 848
+    for i in np.unique(idx)[::5]:
+        assert len({L.gyo_bucket(0, int(x) // 1000) for x in v[idx == i]}) == 1
     # a bin is at most 1/32 of its lower edge wide: 32 bins per octave
     for c in np.unique(code)[::7]:
         inb = v[code == c]
         assert inb.max() - inb.min() <= max(1, inb.min() // 32)
-
-
-def test_radix_pass_plan_covers_every_significant_bit_once():
-    """host logic of the one-sweep sort: the RESP keys are sorted on the word {slot | code(usec)} = 10 value bits + the slot bits
-    of the engine's capacity, each bit exactly once and in ascending order, in the fewest digits of at most 9 bits, widths even"""
-    import ctypes as C
-    from gyeeta_b200 import engine as ge
-    L = ge.load_library()
-    for max_svcs in (1, 2, 100, 1024, 3000, 100_000, 1 << 17, 1 << 20, 1 << 24):
-        plan = (C.c_int32 * 4 * 8)()
-        npass = C.c_uint32()
-        assert L.gysk_sort_plan(0, max_svcs, plan, C.byref(npass)) == 0
-        sb = max(1, int(max_svcs - 1).bit_length())
-        T = 10 + sb
-        got = []
-        for p in range(npass.value):
-            s1, b1, s2, b2 = plan[p]
-            assert 1 <= b1 <= 9 and b2 == 0
-            got += [s1 + i for i in range(b1)]
-        assert got == list(range(T)), (max_svcs, got)
-        assert npass.value == -(-T // 9)
-        widths = [plan[p][1] for p in range(npass.value)]
-        assert max(widths) - min(widths) <= 1
-    plan = (C.c_int32 * 4 * 8)(); npass = C.c_uint32()
-    assert L.gysk_sort_plan(0, 1 << 17, plan, C.byref(npass)) == 0 and npass.value == 3       # the bench engine: 27 bits = 9 + 9 + 9
-    assert [plan[p][1] for p in range(3)] == [9, 9, 9]
-    assert L.gysk_sort_plan(0, 1 << 20, plan, C.byref(npass)) == 0 and npass.value == 4       # 1 M services: 30 bits = 8 8 7 7
-    assert L.gysk_sort_plan(0, 0, plan, C.byref(npass)) == -22
 
 
 def test_listener_state_encoder_fields_and_limits():
@@ -271,27 +248,3 @@ def test_listener_state_encoder_fields_and_limits():
     assert L.gysk_encode_listener_state(sums, n, small, len(small), C.byref(nrecs), C.byref(nbytes)) == -28
 
 
-def test_radix_pass_plan_sorts_keys_when_passes_are_stable():
-    """the plan of gysk_sort_plan, executed with numpy's stable argsort as the pass: keys {slot | usec | port} come out ordered by
-    (slot, code(usec)) with ties in input order"""
-    import ctypes as C
-    from gyeeta_b200 import engine as ge
-    L = ge.load_library()
-    rng = np.random.default_rng(5)
-    for max_svcs in (100_000, 1 << 17, 1500, 3, 1 << 20):
-        plan = (C.c_int32 * 4 * 8)(); npass = C.c_uint32()
-        assert L.gysk_sort_plan(0, max_svcs, plan, C.byref(npass)) == 0
-        n = 50_000
-        slot = rng.integers(0, max_svcs, n, dtype=np.uint64)
-        usec = np.minimum(np.exp(rng.normal(np.log(2000.0), 2.5, n)), 1.0e9).astype(np.uint64)
-        code = np_td_code(usec)
-        word = (slot << np.uint64(10)) | code
-        order = np.arange(n)
-        cur = word.copy()
-        for p in range(npass.value):
-            s1, b1 = int(plan[p][0]), int(plan[p][1])
-            digit = (cur >> np.uint64(s1)) & np.uint64((1 << b1) - 1)
-            perm = np.argsort(digit, kind="stable")
-            cur, order = cur[perm], order[perm]
-        want = np.lexsort((np.arange(n), code, slot))             # by slot, then code, then input order
-        assert np.array_equal(order, want), max_svcs

@@ -45,3 +45,31 @@ def assert_hist_equal(eng, orc, id_, which):
 def exact_quantile(vals, q):
     v = np.sort(np.asarray(vals, dtype=np.float64))
     return float(v[min(len(v) - 1, max(0, int(np.ceil(q * len(v))) - 1))])
+
+
+def threaded_oracle(ev, nthreads, **ocfg):
+    """The CPU oracle over a large stream: events pre-sharded by host_idx % nthreads (every per-service / per-task sketch lives
+    wholly in one shard), one oracle engine per thread, each shard ingested as ONE device batch. Returns
+    (engines, owner) with owner(id, host_idx) -> engine; the count-min table of the whole stream is the sum of the shard tables."""
+    import ctypes as C
+    L = po.lib()
+    owner = (ev["host_idx"] % nthreads).astype(np.int32)
+    order = np.argsort(owner, kind="stable")
+    cuts = np.searchsorted(owner[order], np.arange(1, nthreads))
+    shards = [np.ascontiguousarray(a) for a in np.split(ev[order], cuts)]
+    engines = [po.OracleEngine(**ocfg) for _ in range(nthreads)]
+    eh = (C.c_void_p * nthreads)(*[e.h for e in engines])
+    sp = (C.c_void_p * nthreads)(*[s_.ctypes.data for s_ in shards])
+    cn = (C.c_uint64 * nthreads)(*[len(s_) for s_ in shards])
+    L.gyo_bench_ingest(eh, sp, cn, nthreads, 0)               # batch 0 = the whole shard in one gyo_ingest call
+    return engines, shards
+
+
+def td_p99_tolerance(n, eps=0.01):
+    """value tolerance of the digest's p99 against the EXACT sample quantile on the sigma <= 1.5 log-normal streams.
+    Two parts: the systematic interpolation error of a delta = 200 K_1 digest (~0.3 %) — and the order-statistic noise of the
+    sample itself: the p99 cluster holds n pi sqrt(.0099) / 200 samples whose individual positions the digest does not keep; the
+    exact quantile, one of them, deviates from the cluster's straight line by ~ sqrt(cluster / 4) sample spacings of
+    sigma / (phi(z_99) n) each (1 sigma = 0.5 % at n = 47 K, falling as 1 / sqrt(n)). 1 % holds from n = 150 K on; below that
+    no sketch of a few hundred centroids can promise it, and the bound is 3.5 sigma of that noise."""
+    return max(eps, 3.5 * 0.005 * float(np.sqrt(47_000.0 / n)))
