@@ -443,7 +443,10 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(dalloc(e, &tmp.touched, ns));
 	{
 		const size_t nmw = (size_t)TD_MERGE_MAX_SMS * TD_MERGE_CTAS_PER_SM * 4;		// warps of bins_merge_kernel
-		A(dalloc(e, &tmp.items_scratch, nmw * NBINS, false)); A(dalloc(e, &tmp.big_scratch, nmw, false));
+		// a batch cannot fill more bins than it has events, nor than the engine has bins
+		const size_t pool_cap = std::min<size_t>((size_t)cfg.max_batch, (size_t)cfg.max_svcs * NBINS);
+		A(dalloc(e, &tmp.pool, pool_cap, false)); A(dalloc(e, &tmp.pool_cursor, 1)); A(dalloc(e, &tmp.segs, ns));
+		A(dalloc(e, &tmp.big_scratch, nmw, false));
 	}
 	st.svc_tbl.insert_fail = st.counters + CTR_INSERT_FAIL; st.task_tbl.insert_fail = nullptr;
 

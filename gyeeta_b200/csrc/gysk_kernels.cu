@@ -313,33 +313,48 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 				}
 			}
 		}
+		// resolve every slot, then put the second round of loads (the slot's batch record and CONN_BITMAP word) of all EPT events
+		// in flight together, and fire the bin REDs — nothing below waits for them
+		int slotv[EPT];
+		uint4 sbv[EPT];
+		uint32_t mwv[EPT], bkt[EPT];
 #pragma unroll
 		for (int k = 0; k < EPT; ++k) {
-			const bool is_resp = kind[k] == GYSK_EV_RESP, is_task = kind[k] == GYSK_EV_TASK, is_tcp = kind[k] == GYSK_EV_ACCEPT;
+			const bool is_resp = kind[k] == GYSK_EV_RESP, is_task = kind[k] == GYSK_EV_TASK;
 			int slot = -1;
 			if (kind[k]) {
 				// one id lookup for all three event kinds (services and tasks live in separate tables)
 				slot = table_resolve(is_task ? st.task_tbl : st.svc_tbl, ((unsigned long long)ra[k].y << 32) | ra[k].x, st.auto_register, rb[k].y, ppos[k], praw[k]);
 			}
+			slotv[k] = slot; sbv[k] = make_uint4(0, 0, 0, 0); mwv[k] = 0; bkt[k] = 0;
+			if (slot >= 0 && is_resp) {
+				const uint32_t v = rb[k].x, ms = v / 1000u;		// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678)
+				const uint32_t b = (uint32_t)bucket_resp_time((long long)ms);
+				bkt[k] = b;
+				sbv[k] = ld_cg_v4(st.slot_batch + slot);
+				mwv[k] = __ldcg(st.bm_cur + (size_t)slot * HIST_CELLS + b);
+				Bin *bin = st.bins + (size_t)slot * NBINS + td_code(v) + b;
+				red_add_u64(&bin->cw, 1ull | ((unsigned long long)(v - ms * 1000u) << BIN_CNT_BITS));
+				red_add_u64(&bin->us, v);
+				n_resp++;
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < EPT; ++k) {
+			const bool is_resp = kind[k] == GYSK_EV_RESP, is_task = kind[k] == GYSK_EV_TASK, is_tcp = kind[k] == GYSK_EV_ACCEPT;
+			const int slot = slotv[k];
 			const bool ok = slot >= 0;
 			const uint32_t m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp), m_task = __ballot_sync(0xffffffffu, ok && is_task);
 			if (ok) {
 				if (is_resp) {
-					const uint32_t v = rb[k].x, ms = v / 1000u;		// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678)
-					const uint32_t b = (uint32_t)bucket_resp_time((long long)ms);
-					Bin *bin = st.bins + (size_t)slot * NBINS + td_code(v) + b;
-					red_add_u64(&bin->cw, 1ull | ((unsigned long long)(v - ms * 1000u) << BIN_CNT_BITS));
-					red_add_u64(&bin->us, v);
-					// the rest only when it changes something: one 16-byte load of the slot's batch record, one of the mask word
-					const uint4 sb = ld_cg_v4(st.slot_batch + slot);
-					if (v < sb.x) atomicMin(&st.slot_batch[slot].minv, v);
-					if (v > sb.y) atomicMax(&st.slot_batch[slot].maxv, v);
-					if (!sb.z) st_volatile_u32(&st.slot_batch[slot].touched, 1u);
-					// TCP_LISTENER::CONN_BITMAP::add_response (common/gy_socket_stat.h:403-410), transposed: per bucket a mask over client port & 31
-					uint32_t *mw = st.bm_cur + (size_t)slot * HIST_CELLS + b;
+					// the rest only when it changes something: batch extremes (minv != ~0 also marks the slot as touched) and the
+					// CONN_BITMAP bit — TCP_LISTENER::CONN_BITMAP::add_response (common/gy_socket_stat.h:403-410), transposed: per
+					// bucket a mask over client port & 31
+					const uint32_t v = rb[k].x;
+					if (v < sbv[k].x) atomicMin(&st.slot_batch[slot].minv, v);
+					if (v > sbv[k].y) atomicMax(&st.slot_batch[slot].maxv, v);
 					const uint32_t bit = 1u << (ra[k].z & 0x1Fu);
-					if (!(__ldcg(mw) & bit)) atomicOr(mw, bit);
-					n_resp++;
+					if (!(mwv[k] & bit)) atomicOr(st.bm_cur + (size_t)slot * HIST_CELLS + bkt[k], bit);
 				}
 				else {
 					IngestRec r; r.slot = (uint32_t)slot; r.value = rb[k].x; r.flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
@@ -650,7 +665,7 @@ __global__ void __launch_bounds__(256) touched_kernel(DevState st, uint32_t max_
 {
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
-	const bool t = slot < max_svcs && st.slot_batch[slot].touched != 0;
+	const bool t = slot < max_svcs && st.slot_batch[slot].minv != 0xFFFFFFFFu;		// a first sample always lowers the minimum
 	const uint32_t m = __ballot_sync(0xffffffffu, t);
 	if (!m) return;
 	unsigned long long base = 0;
@@ -659,103 +674,133 @@ __global__ void __launch_bounds__(256) touched_kernel(DevState st, uint32_t max_
 	if (t) touched[base + __popc(m & ((1u << lane) - 1u))] = slot;
 }
 
-// bin index -> RESP_TIME_HASH bucket. index = td_code(usec) + bucket: for bucket b the indexes run from
-// td_code(first usec of the bucket) + b to td_code(last usec of the bucket) + b.
-__device__ __forceinline__ uint32_t bin_bucket(uint32_t idx, const uint16_t *first_idx /* [15] first index of each bucket */)
+// One CTA per touched service (grid sized for every slot, surplus CTAs leave at once): reads the service's NBINS bins (4 per
+// thread, all in flight together); a non-empty bin becomes one item {mean = usec sum / samples, weight = samples} of the batch,
+// written IN BIN ORDER (= value order: the bin index is monotone) into the batch's item pool, and adds {samples, msec sum} to its
+// bucket of the window's histogram — GY_HISTOGRAM::add_data for every sample of the bin (common/gy_statistics.h:596-623); the bin
+// is zeroed. max_val_seen_ comes from the batch's exact maximum.
+static constexpr int SCAN_THREADS = 256, SCAN_BPT = (NBINS + SCAN_THREADS - 1) / SCAN_THREADS;		// 4 bins per thread
+
+struct BatchSeg { uint32_t base, nitems; unsigned long long nsamples; };		// a touched service's run in the item pool
+
+__global__ void __launch_bounds__(SCAN_THREADS) bins_scan_kernel(DevState st, const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p,
+		Centroid *__restrict__ pool, unsigned long long *__restrict__ pool_cursor, BatchSeg *__restrict__ segs)
 {
-	uint32_t b = 0;
+	__shared__ unsigned long long hcnt[16], hsum[16], ssamples;
+	__shared__ uint32_t wcnt[SCAN_BPT][SCAN_THREADS / 32], sbase;
+	__shared__ uint16_t first_idx[16];
+	const uint32_t t = blockIdx.x;
+	if (t >= (uint32_t)*ntouched_p) return;
+	const uint32_t slot = touched[t];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	Bin *bins = st.bins + (size_t)slot * NBINS;
+
+	Bin b[SCAN_BPT];
 #pragma unroll
-	for (int i = 1; i < 15; ++i) b += idx >= first_idx[i];
-	return b;
+	for (int j = 0; j < SCAN_BPT; ++j) {
+		const uint32_t i = j * SCAN_THREADS + threadIdx.x;
+		b[j] = i < (uint32_t)NBINS ? bins[i] : Bin {0, 0};
+	}
+	if (threadIdx.x < 16) {
+		hcnt[threadIdx.x] = 0; hsum[threadIdx.x] = 0;
+		// thresholds of RESP_TIME_HASH in msec (gy_statistics.h:1677): bucket b >= 2 starts at (thr[b-2] + 1) msec, bucket 1 at 0
+		constexpr uint32_t thr[13] = {1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000};
+		const uint32_t bk = threadIdx.x;
+		const uint32_t first_us = bk < 2 ? 0u : (bk > 14 ? 0xFFFFFFFFu : (thr[bk - 2] + 1u) * 1000u);
+		first_idx[bk] = (uint16_t)(bk == 0 ? 0u : (bk > 14 ? 0xFFFFu : td_code(first_us) + bk));
+		if (threadIdx.x == 0) ssamples = 0;
+	}
+	uint32_t mball[SCAN_BPT];
+#pragma unroll
+	for (int j = 0; j < SCAN_BPT; ++j) {
+		mball[j] = __ballot_sync(0xffffffffu, b[j].cw != 0);
+		if (lane == 0) wcnt[j][wid] = __popc(mball[j]);
+	}
+	__syncthreads();
+	// exclusive prefix over (j, warp) in bin order; thread 0 reserves the service's run in the pool
+	uint32_t before = 0, total = 0;
+#pragma unroll
+	for (int j = 0; j < SCAN_BPT; ++j) {
+#pragma unroll
+		for (int w = 0; w < SCAN_THREADS / 32; ++w) { const uint32_t c = wcnt[j][w]; total += c; }
+	}
+	if (threadIdx.x == 0) sbase = (uint32_t)atomicAdd(pool_cursor, (unsigned long long)total);
+	unsigned long long mysamples = 0;
+	uint32_t run = 0;
+	uint32_t rank[SCAN_BPT];
+#pragma unroll
+	for (int j = 0; j < SCAN_BPT; ++j) {
+#pragma unroll
+		for (int w = 0; w < SCAN_THREADS / 32; ++w) { if (w == wid) before = run; run += wcnt[j][w]; }
+		rank[j] = before + __popc(mball[j] & ((1u << lane) - 1u));
+	}
+	__syncthreads();
+	const uint32_t base = sbase;
+#pragma unroll
+	for (int j = 0; j < SCAN_BPT; ++j) {
+		if (b[j].cw) {
+			const uint32_t i = j * SCAN_THREADS + threadIdx.x;
+			const unsigned long long cnt = b[j].cw & BIN_CNT_MASK, rem = b[j].cw >> BIN_CNT_BITS;
+			Centroid c; c.mean = __ddiv_rn((double)b[j].us, (double)cnt); c.weight = cnt;	// exact integer sum, one rounding
+			pool[base + rank[j]] = c;
+			uint32_t bk = 0;
+#pragma unroll
+			for (int q = 1; q < 15; ++q) bk += i >= first_idx[q];
+			atomicAdd(&hcnt[bk], cnt);
+			atomicAdd(&hsum[bk], (b[j].us - rem) / 1000ull);		// sum of (usec / 1000) over the bin's samples
+			bins[i] = Bin {0, 0};
+			mysamples += cnt;
+		}
+	}
+	for (int off = 16; off > 0; off >>= 1) mysamples += __shfl_xor_sync(0xffffffffu, mysamples, off);
+	if (lane == 0 && mysamples) atomicAdd(&ssamples, mysamples);
+	__syncthreads();
+	// nobody else touches this slot's window histogram while the batch is merged (same stream as the flush): plain updates
+	if (threadIdx.x < HIST_MAX_CELL) {
+		if (hcnt[threadIdx.x]) {
+			HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + threadIdx.x;
+			c->count += hcnt[threadIdx.x]; c->sum += (long long)hsum[threadIdx.x];
+		}
+	}
+	else if (threadIdx.x == HIST_MAX_CELL) {
+		HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + HIST_MAX_CELL;
+		const long long mx = (long long)(st.slot_batch[slot].maxv / 1000u);		// max_val_seen_ of add_data (gy_statistics.h:609-611)
+		if (mx > c->sum) c->sum = mx;
+		segs[t] = BatchSeg {base, total, ssamples};
+	}
 }
 
 static constexpr int TD_WARPS = 4;
 
-// One warp per touched service:
-//   (1) reads the service's NBINS bins in order; a non-empty bin becomes one item {mean = usec sum / samples, weight = samples} of
-//       the batch (items are in value order because the bin index is monotone) and adds {samples, msec sum} to its bucket of the
-//       window's histogram — GY_HISTOGRAM::add_data for every sample of the bin (common/gy_statistics.h:596-623); the bin is zeroed;
-//   (2) max_val_seen_ and the digest's ends from the batch's exact min / max;
-//   (3) the items are merged with the old centroids (old first on equal means) and the greedy K_1 pass cuts the list down to
-//       at most TD_CAP clusters (warp_merge_compress). Lists of up to 2 x TD_CAP entries work in shared memory; longer ones (a
-//       first batch of a service can fill several hundred bins) in the warp's L2-resident scratch — same code, same result.
+// One warp per touched service: the batch's items are merged with the old centroids (old first on equal means) and the greedy
+// K_1 pass cuts the list down to at most TD_CAP clusters (warp_merge_compress). Lists of up to 2 x TD_CAP entries work in shared
+// memory; longer ones (a first batch of a service can fill several hundred bins) in the warp's L2-resident scratch — same code,
+// same result. The digest's ends come from the batch's exact min / max, which are reset for the next batch.
 __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p,
-		Centroid *__restrict__ items_scratch /* [nwarps][NBINS] */, TdWorkBig *__restrict__ big_scratch /* [nwarps] */)
+		const Centroid *__restrict__ pool, const BatchSeg *__restrict__ segs, TdWorkBig *__restrict__ big_scratch /* [nwarps] */)
 {
 	__shared__ TdWork work[TD_WARPS];
-	__shared__ unsigned long long hcnt[TD_WARPS][16], hsum[TD_WARPS][16];
-	__shared__ uint16_t first_idx[16];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * TD_WARPS + wid, nwarps = gridDim.x * TD_WARPS;
-	Centroid *items = items_scratch + (size_t)gw * NBINS;
 	const uint32_t ntouched = (uint32_t)*ntouched_p;
-
-	if (threadIdx.x < 15) {
-		// thresholds of RESP_TIME_HASH in msec (gy_statistics.h:1677): bucket b >= 1 starts at (thr[b-1] + 1) msec, bucket 14 at 15001
-		constexpr uint32_t thr[13] = {1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000};
-		const uint32_t b = threadIdx.x;
-		const uint32_t first_us = b == 0 ? 0u : (b == 1 ? 0u : (b == 14 ? 15001u * 1000u : (thr[b - 2] + 1u) * 1000u));
-		// bucket 0 holds negative values only (never produced: msec is unsigned); bucket 1 = 0 .. 1 msec
-		first_idx[b] = (uint16_t)(b == 0 ? 0u : td_code(first_us) + b);
-	}
-	__syncthreads();
 
 	for (uint32_t t = gw; t < ntouched; t += nwarps) {
 		const uint32_t slot = touched[t];
-		Bin *bins = st.bins + (size_t)slot * NBINS;
-		if (lane < 16) { hcnt[wid][lane] = 0; hsum[wid][lane] = 0; }
-		__syncwarp();
-		uint32_t nitems = 0;
-		unsigned long long nsamples = 0;
-		for (uint32_t i0 = 0; i0 < (uint32_t)NBINS; i0 += 32) {
-			const uint32_t i = i0 + lane;
-			Bin b {0, 0};
-			if (i < (uint32_t)NBINS) b = bins[i];
-			const bool nz = b.cw != 0;
-			const uint32_t m = __ballot_sync(0xffffffffu, nz);
-			if (nz) {
-				const unsigned long long cnt = b.cw & BIN_CNT_MASK, rem = b.cw >> BIN_CNT_BITS;
-				Centroid c; c.mean = __ddiv_rn((double)b.us, (double)cnt); c.weight = cnt;	// exact integer sum, one rounding
-				items[nitems + __popc(m & ((1u << lane) - 1u))] = c;
-				const uint32_t bk = bin_bucket(i, first_idx);
-				atomicAdd(&hcnt[wid][bk], cnt);
-				atomicAdd(&hsum[wid][bk], (b.us - rem) / 1000ull);			// sum of (usec / 1000) over the bin's samples
-				bins[i] = Bin {0, 0};
-				nsamples += cnt;
-			}
-			nitems += __popc(m);
-		}
-		__syncwarp();
-		nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 16); nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 8);
-		nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 4); nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 2);
-		nsamples += __shfl_xor_sync(0xffffffffu, nsamples, 1);
-
-		// nobody else touches this slot's window histogram while the batch is merged (same stream as the flush): plain updates
+		const BatchSeg seg = segs[t];
+		const Centroid *items = pool + seg.base;
 		const SlotBatch sb = st.slot_batch[slot];
-		if (lane < HIST_MAX_CELL) {
-			if (hcnt[wid][lane]) {
-				HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + lane;
-				c->count += hcnt[wid][lane]; c->sum += (long long)hsum[wid][lane];
-			}
-		}
-		else if (lane == HIST_MAX_CELL) {
-			HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + HIST_MAX_CELL;
-			const long long mx = (long long)(sb.maxv / 1000u);		// max_val_seen_ of add_data (gy_statistics.h:609-611)
-			if (mx > c->sum) c->sum = mx;
-			st.slot_batch[slot] = SlotBatch {0xFFFFFFFFu, 0u, 0u, 0u};
-		}
-
 		TdHead head = st.td_head[slot];
 		Centroid *cent = st.td_cent + (size_t)slot * TD_CAP;
 		uint32_t nout;
-		if (head.n + nitems <= 2u * TD_CAP) nout = warp_merge_compress(work[wid], cent, head.n, items, nitems, cent, st.td);
-		else nout = warp_merge_compress(big_scratch[gw], cent, head.n, items, nitems, cent, st.td);
+		if (head.n + seg.nitems <= 2u * TD_CAP) nout = warp_merge_compress(work[wid], cent, head.n, items, seg.nitems, cent, st.td);
+		else nout = warp_merge_compress(big_scratch[gw], cent, head.n, items, seg.nitems, cent, st.td);
 		if (lane == 0) {
 			head.n = nout;
-			head.total += nsamples;
+			head.total += seg.nsamples;
 			if ((double)sb.minv < head.minv) head.minv = (double)sb.minv;
 			if ((double)sb.maxv > head.maxv) head.maxv = (double)sb.maxv;
 			st.td_head[slot] = head;
+			st.slot_batch[slot] = SlotBatch {0xFFFFFFFFu, 0u, 0u, 0u};
 		}
 		__syncwarp();
 	}
@@ -1029,6 +1074,9 @@ int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, cudaSt
 	case 844 : launch_ingest_variant<8, 4, 4, false>(st, d_ev, n, dev, s); break;
 	case 832 : launch_ingest_variant<8, 3, 2, false>(st, d_ev, n, dev, s); break;
 	case 482 : launch_ingest_variant<4, 8, 2, false>(st, d_ev, n, dev, s); break;
+	case 828 : launch_ingest_variant<8, 2, 8, false>(st, d_ev, n, dev, s); break;
+	case 1824 : launch_ingest_variant<8, 2, 4, true>(st, d_ev, n, dev, s); break;
+	case 1828 : launch_ingest_variant<8, 2, 8, true>(st, d_ev, n, dev, s); break;
 	case 1842 : launch_ingest_variant<8, 4, 2, true>(st, d_ev, n, dev, s); break;	// TMA-staged chunks
 	case 1834 : launch_ingest_variant<8, 3, 4, true>(st, d_ev, n, dev, s); break;
 	default : launch_ingest_variant<8, 4, 2, false>(st, d_ev, n, dev, s); break;
@@ -1137,9 +1185,12 @@ int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint32_t max_svc
 	const int nsm = sm_count(current_device());
 	unsigned long long *d_ntouched = st.counters + CTR_NTOUCHED;
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
+	cudaMemsetAsync(tmp.pool_cursor, 0, sizeof(unsigned long long), s);
 	touched_kernel<<<div_up(max_svcs, 256), 256, 0, s>>>(st, max_svcs, tmp.touched, d_ntouched);
-	bins_merge_kernel<<<std::min(nsm, TD_MERGE_MAX_SMS) * TD_MERGE_CTAS_PER_SM, TD_WARPS * 32, 0, s>>>(st, tmp.touched, d_ntouched, tmp.items_scratch, tmp.big_scratch);
-	return 2;
+	bins_scan_kernel<<<max_svcs, SCAN_THREADS, 0, s>>>(st, tmp.touched, d_ntouched, tmp.pool, tmp.pool_cursor, reinterpret_cast<BatchSeg *>(tmp.segs));
+	bins_merge_kernel<<<std::min(nsm, TD_MERGE_MAX_SMS) * TD_MERGE_CTAS_PER_SM, TD_WARPS * 32, 0, s>>>(st, tmp.touched, d_ntouched, tmp.pool,
+			reinterpret_cast<const BatchSeg *>(tmp.segs), tmp.big_scratch);
+	return 3;
 }
 
 // ---------------------------------------------------------------------------------------------------

