@@ -63,13 +63,13 @@ int process_device_batch(gysk_engine *e, const gysk_event *d_ev, uint64_t n, Aft
 		e->prof_used += 3;
 		CU(e, cudaEventRecord(pe[0], e->stream));
 	}
-	e->kernel_launches += launch_ingest(e->st, d_ev, n, e->stream);
+	e->kernel_launches += launch_ingest(e->st, e->tmp, d_ev, n, e->cfg.max_svcs, e->stream);
 	if (pe) CU(e, cudaEventRecord(pe[1], e->stream));
 	// the events of this batch are consumed once the ingest kernel has run: callers release / refill the event buffer here,
 	// so that the next H2D copy overlaps the merge kernels
 	{ int rc_ai = after_ingest(); if (rc_ai) return rc_ai; }
 	// No number travels back to the host inside a batch: the list of touched services and its length stay in device memory.
-	e->kernel_launches += launch_batch_merge(e->st, e->tmp, e->cfg.max_svcs, e->stream);
+	e->kernel_launches += launch_batch_merge(e->st, e->tmp, n, e->cfg.max_svcs, e->stream);
 	if (pe) CU(e, cudaEventRecord(pe[2], e->stream));
 	e->batches++;
 	return post_launch(e, "ingest batch");
@@ -432,9 +432,9 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 		}
 	}
 
-	A(dalloc(e, &st.bins, ns * NBINS)); A(dalloc(e, &st.slot_batch, ns));
+	A(dalloc(e, &st.slot_batch, ns));
 	SortTemp &tmp = e->tmp;
-	const size_t nsort = std::max<size_t>(ns, nt) + 1;			// the radix sort only ranks services / tasks (top-N)
+	const size_t nsort = std::max<size_t>(std::max<size_t>(ns, nt) + 1, cfg.max_batch);	// RESP keys of a batch; the top-N sorts rank services / tasks
 	tmp.max_tiles = (uint32_t)((nsort + SORT_TILE - 1) / SORT_TILE);
 	A(dalloc(e, &tmp.keys_a, nsort, false)); A(dalloc(e, &tmp.keys_b, nsort, false));
 	A(dalloc(e, &tmp.tile_status, (size_t)RADIX_MAX * tmp.max_tiles));
@@ -443,10 +443,11 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	A(dalloc(e, &tmp.touched, ns));
 	{
 		const size_t nmw = (size_t)TD_MERGE_MAX_SMS * TD_MERGE_CTAS_PER_SM * 4;		// warps of bins_merge_kernel
-		// a batch cannot fill more bins than it has events, nor than the engine has bins
-		const size_t pool_cap = std::min<size_t>((size_t)cfg.max_batch, (size_t)cfg.max_svcs * NBINS);
-		A(dalloc(e, &tmp.pool, pool_cap, false)); A(dalloc(e, &tmp.pool_cursor, 1)); A(dalloc(e, &tmp.segs, ns));
-		A(dalloc(e, &tmp.big_scratch, nmw, false));
+		// a batch cannot have more runs than keys, nor than the engine has bins
+		const size_t pool_cap = std::min<size_t>((size_t)cfg.max_batch, (size_t)cfg.max_svcs * NBINS) + 8;
+		A(dalloc(e, &tmp.pool, pool_cap, false)); A(dalloc(e, &tmp.run_bin, pool_cap, false));
+		A(dalloc(e, &tmp.chunk_run, ((size_t)cfg.max_batch >> 7) + 16, false)); A(dalloc(e, &tmp.segs, ns));
+		A(dalloc(e, &tmp.items_scratch, nmw * NBINS, false)); A(dalloc(e, &tmp.big_scratch, nmw, false));
 	}
 	st.svc_tbl.insert_fail = st.counters + CTR_INSERT_FAIL; st.task_tbl.insert_fail = nullptr;
 

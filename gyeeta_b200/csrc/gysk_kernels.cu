@@ -23,6 +23,17 @@
 
 namespace gysk {
 
+// RESP sort key = {slot : 24 | bin index : 10 | usec : 30}. Bin index = td_code(usec) + RESP_TIME_HASH bucket of usec / 1000: both
+// terms are monotone in usec, so the index is too and no bin straddles a histogram bucket. The radix passes sort on
+// the top 10 + slot bits only: the samples of one (service, bin) end up as one contiguous RUN, in no particular order inside it.
+static constexpr int KEY_GROUP_SHIFT = 30;				// key >> 30 = {slot, bin}
+static constexpr int KEY_SLOT_SHIFT = KEY_GROUP_SHIFT + TD_CODE_BITS;
+__device__ __forceinline__ uint32_t key_usec(unsigned long long k) { return (uint32_t)k & 0x3FFFFFFFu; }
+__device__ __forceinline__ uint32_t key_slot(unsigned long long k) { return (uint32_t)(k >> KEY_SLOT_SHIFT); }
+__device__ __forceinline__ uint32_t key_bin(unsigned long long k) { return (uint32_t)(k >> KEY_GROUP_SHIFT) & ((1u << TD_CODE_BITS) - 1u); }
+
+struct SortPlan { int np; int shift[OS_MAX_PASSES_VK]; int bits[OS_MAX_PASSES_VK]; };	// digit p = (key >> shift[p]) & ((1 << bits[p]) - 1)
+
 // ---------------------------------------------------------------------------------------------------
 // state init / registration
 // ---------------------------------------------------------------------------------------------------
@@ -179,18 +190,21 @@ template <int WARPS, int EPT, bool TMA>
 struct IngestSharedT
 {
 	static constexpr int CHUNK = 32 * EPT;			// events per warp and round
+	static constexpr int KQ_CAP = EPT <= 2 ? 192 : 256, KQ_FLUSH = KQ_CAP - CHUNK;	// a flush leaves room for a whole chunk of RESP events
 	static constexpr int RQ_CAP = 32 + CHUNK;			// < 32 left over + one chunk
+	static_assert(CHUNK <= 128, "key queue sized for chunks of at most 128 events");
 	using HotTable = HotTableT<9>;
-	struct Warp { IngestRec tcp[RQ_CAP], task[RQ_CAP]; };
+	struct Warp { unsigned long long kq[KQ_CAP]; IngestRec tcp[RQ_CAP], task[RQ_CAP]; };
 	alignas(128) uint4	evbuf[TMA ? WARPS * CHUNK * 2 : 1];	// per warp: its next chunk of 32-byte events, filled by cp.async.bulk
 	unsigned long long	mbar[TMA ? WARPS : 1];
 	Warp		w[WARPS];
 	HotTable	hot;
+	uint32_t	dhist[OS_MAX_PASSES_VK][RADIX_MAX];		// digit histograms of this CTA's keys, one per radix pass
 };
 
 template <int WARPS, int MIN_CTAS, int EPT, bool TMA>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
-		int unused)
+		unsigned long long *__restrict__ keys, uint32_t *__restrict__ ghist, SortPlan plan)
 {
 	using Shared = IngestSharedT<WARPS, EPT, TMA>;
 	using HotTable = typename Shared::HotTable;
@@ -201,10 +215,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 	typename Shared::Warp &W = S.w[wid];
 	const uint32_t lt = (1u << lane) - 1u;
 	uint32_t c_in = 0, c_foreign = 0, n_resp = 0;			// per thread: < 2^32 events per launch
-	uint32_t ntcp = 0, ntask = 0;					// queue lengths (warp-uniform)
+	uint32_t nk = 0, ntcp = 0, ntask = 0;				// queue lengths (warp-uniform)
 	unsigned long long t_tcp = 0, t_task = 0;			// queued in total (warp-uniform)
 
 	for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
+	for (int i = threadIdx.x; i < OS_MAX_PASSES_VK * RADIX_MAX; i += WARPS * 32) (&S.dhist[0][0])[i] = 0;
 	if (TMA && lane == 0) mbar_init(&S.mbar[wid], 1);
 	__syncthreads();						// the only block barriers: here and before the retire step
 	if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");	// mbarrier init visible to the async proxy
@@ -267,6 +282,21 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 		if (mv) q[lane] = r;
 		__syncwarp();
 	};
+	auto flush_keys = [&]() {
+		unsigned long long base = 0;
+		if (lane == 0) base = atomicAdd(st.counters + CTR_NKEYS, (unsigned long long)nk);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		for (uint32_t q = lane; q < nk; q += 32) {
+			const unsigned long long k = W.kq[q];
+#pragma unroll
+			for (int p = 0; p < OS_MAX_PASSES_VK; ++p)
+				if (p < plan.np) atomicAdd(&S.dhist[p][(uint32_t)(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
+			__stcs(keys + base + q, k);
+		}
+		nk = 0;
+		__syncwarp();
+	};
+
 	for (uint64_t chunk = gwarp; chunk < nchunks; chunk += nwarps) {
 		const uint64_t cbase = chunk * CHUNK;
 		uint4 ra[EPT], rb[EPT];
@@ -333,9 +363,6 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 				bkt[k] = b;
 				sbv[k] = ld_cg_v4(st.slot_batch + slot);
 				mwv[k] = __ldcg(st.bm_cur + (size_t)slot * HIST_CELLS + b);
-				Bin *bin = st.bins + (size_t)slot * NBINS + td_code(v) + b;
-				red_add_u64(&bin->cw, 1ull | ((unsigned long long)(v - ms * 1000u) << BIN_CNT_BITS));
-				red_add_u64(&bin->us, v);
 				n_resp++;
 			}
 		}
@@ -344,9 +371,12 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 			const bool is_resp = kind[k] == GYSK_EV_RESP, is_task = kind[k] == GYSK_EV_TASK, is_tcp = kind[k] == GYSK_EV_ACCEPT;
 			const int slot = slotv[k];
 			const bool ok = slot >= 0;
-			const uint32_t m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp), m_task = __ballot_sync(0xffffffffu, ok && is_task);
+			const uint32_t m_resp = __ballot_sync(0xffffffffu, ok && is_resp), m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp),
+					m_task = __ballot_sync(0xffffffffu, ok && is_task);
 			if (ok) {
 				if (is_resp) {
+					W.kq[nk + __popc(m_resp & lt)] = ((unsigned long long)(uint32_t)slot << KEY_SLOT_SHIFT) |
+							((unsigned long long)(td_code(rb[k].x) + bkt[k]) << KEY_GROUP_SHIFT) | rb[k].x;
 					// the rest only when it changes something: batch extremes (minv != ~0 also marks the slot as touched) and the
 					// CONN_BITMAP bit — TCP_LISTENER::CONN_BITMAP::add_response (common/gy_socket_stat.h:403-410), transposed: per
 					// bucket a mask over client port & 31
@@ -362,21 +392,27 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 					else W.task[ntask + __popc(m_task & lt)] = r;
 				}
 			}
-			ntcp += __popc(m_tcp); ntask += __popc(m_task);
+			nk += __popc(m_resp); ntcp += __popc(m_tcp); ntask += __popc(m_task);
 		}
 		__syncwarp();
 
 		if (ntcp >= 32) { const uint32_t m = ntcp & ~31u; drain_tcp(m); keep_rest(W.tcp, m, ntcp); t_tcp += m; ntcp -= m; }
 		if (ntask >= 32) { const uint32_t m = ntask & ~31u; drain_task(m); keep_rest(W.task, m, ntask); t_task += m; ntask -= m; }
+		if (nk > (uint32_t)Shared::KQ_FLUSH) flush_keys();
 	}
 	// what is left in the queues
 	if (ntcp) { drain_tcp(ntcp); t_tcp += ntcp; }
 	if (ntask) { drain_task(ntask); t_task += ntask; }
+	if (nk) flush_keys();
 
 	__syncthreads();
-	// retire: one RED group per privatised cell
+	// retire: one RED group per privatised cell, one RED per digit this CTA saw
 	for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) {
 		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i]);
+	}
+	for (int i = threadIdx.x; i < plan.np * RADIX_MAX; i += WARPS * 32) {
+		const uint32_t c = (&S.dhist[0][0])[i];
+		if (c) atomicAdd(ghist + i, c);
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
@@ -658,149 +694,289 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 }
 
 // ---------------------------------------------------------------------------------------------------
-// per batch: services with RESP samples -> histogram cells + t-digest, from their value bins
+// per batch: sorted RESP keys -> runs (one per non-empty value bin of a service) -> histogram cells + t-digest
 // ---------------------------------------------------------------------------------------------------
-// list of the slots ingest_kernel marked; grid covers every slot the engine can hand out
-__global__ void __launch_bounds__(256) touched_kernel(DevState st, uint32_t max_svcs, uint32_t *__restrict__ touched, unsigned long long *ntouched)
+// (1) runs_mark_kernel   one sweep over the sorted keys: where do runs ({slot, bin} changes) and service segments start. A CTA
+//     covers 1024 keys; the number of runs before it comes from a decoupled look-back over one status word per CTA (as in the
+//     radix passes). Per run start: its pool entry is zeroed and its bin index recorded; per 128-key chunk: the index of the run
+//     its first key belongs to; per service: its key segment, its run range, and its place in the list of touched services.
+// (2) runs_sum_kernel    every 128-key chunk adds its samples into the pool entries of its runs: {samples | sub-msec remainders,
+//     usec sum} — consecutive chunks hit consecutive entries, so the REDs stay in L2.
+// (3) bins_merge_kernel  one warp per touched service: runs -> items {mean, weight} + GY_HISTOGRAM::add_data for every sample
+//     of the run (count and exact msec sum per bucket), then the merging t-digest step.
+struct RunRec { unsigned long long cw; unsigned long long us; };		// {samples : 27 | remainders : 37}, usec sum — as Bin
+struct BatchSeg { uint32_t run0, nruns; uint32_t key0, nkeys; };		// a touched service's runs in the pool / keys in the sorted array
+
+static constexpr int RM_THREADS = 256, RM_V = 4, RM_TILE = RM_THREADS * RM_V;	// keys per thread: positions wbase + t * 32 + lane
+
+__global__ void __launch_bounds__(RM_THREADS) runs_mark_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
+		unsigned long long *__restrict__ status, uint32_t epoch, RunRec *__restrict__ pool, uint16_t *__restrict__ run_bin,
+		uint32_t *__restrict__ chunk_run, BatchSeg *__restrict__ segs /* [slot] */, uint32_t *__restrict__ touched, unsigned long long *ntouched,
+		unsigned long long *nruns_total)
 {
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
-	const bool t = slot < max_svcs && st.slot_batch[slot].minv != 0xFFFFFFFFu;		// a first sample always lowers the minimum
-	const uint32_t m = __ballot_sync(0xffffffffu, t);
-	if (!m) return;
-	unsigned long long base = 0;
-	if (lane == 0) base = atomicAdd(ntouched, (unsigned long long)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, 0);
-	if (t) touched[base + __popc(m & ((1u << lane) - 1u))] = slot;
+	__shared__ uint32_t wsum[RM_THREADS / 32], s_excl;
+	const uint64_t n = *d_n;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint64_t tbase = (uint64_t)blockIdx.x * RM_TILE;
+	if (tbase >= n) return;
+	const uint64_t wbase = tbase + (uint64_t)wid * (32 * RM_V);		// 128 consecutive keys per warp
+	const unsigned long long etag = (unsigned long long)epoch << 32;
+
+	unsigned long long g[RM_V + 2];		// {slot, bin} of key wbase - 1 (lane 0 only), own 4 keys, successor of the last (lane 31 only)
+#pragma unroll
+	for (int t = 0; t < RM_V; ++t) {
+		const uint64_t i = wbase + (uint64_t)t * 32 + lane;
+		g[1 + t] = i < n ? (keys[i] >> KEY_GROUP_SHIFT) : ~0ull;
+	}
+	g[0] = (lane == 0 && wbase && wbase < n) ? (keys[wbase - 1] >> KEY_GROUP_SHIFT) : ~0ull;
+	g[RM_V + 1] = (lane == 31 && wbase + 32 * RM_V < n) ? (keys[wbase + 32 * RM_V] >> KEY_GROUP_SHIFT) : ~0ull;
+
+	uint32_t words[RM_V];			// run-start ballots
+	uint32_t isrun = 0, isseg = 0, isend = 0;	// bit t: own key t starts a run / starts / ends a service segment
+	uint32_t wcount = 0;
+#pragma unroll
+	for (int t = 0; t < RM_V; ++t) {
+		const uint64_t i = wbase + (uint64_t)t * 32 + lane;
+		unsigned long long prev = __shfl_up_sync(0xffffffffu, g[1 + t], 1);
+		const unsigned long long prev0 = __shfl_sync(0xffffffffu, g[t], 31);		// key t - 1 of lane 31 (t >= 1)
+		if (lane == 0) prev = t == 0 ? g[0] : prev0;
+		unsigned long long next = __shfl_down_sync(0xffffffffu, g[1 + t], 1);
+		const unsigned long long next0 = __shfl_sync(0xffffffffu, g[2 + (t < RM_V - 1 ? t : 0)], 0);	// key t + 1 of lane 0
+		if (lane == 31) next = t == RM_V - 1 ? g[RM_V + 1] : next0;
+		const bool valid = i < n;
+		const bool run = valid && g[1 + t] != prev;			// i == 0: prev is the sentinel
+		const bool seg = valid && (g[1 + t] >> TD_CODE_BITS) != (prev >> TD_CODE_BITS);
+		const bool end = valid && (g[1 + t] >> TD_CODE_BITS) != (next >> TD_CODE_BITS);	// last key: next is the sentinel
+		words[t] = __ballot_sync(0xffffffffu, run);
+		wcount += __popc(words[t]);
+		isrun |= (run ? 1u : 0u) << t; isseg |= (seg ? 1u : 0u) << t; isend |= (end ? 1u : 0u) << t;
+	}
+	if (lane == 0) wsum[wid] = wcount;
+	__syncthreads();
+	uint32_t wexcl = 0, ctotal = 0;
+#pragma unroll
+	for (int w = 0; w < RM_THREADS / 32; ++w) { const uint32_t c = wsum[w]; if (w < wid) wexcl += c; ctotal += c; }
+	// decoupled look-back over the CTAs before this one: number of run starts before the tile
+	if (threadIdx.x == 0) {
+		const uint32_t tile = blockIdx.x;
+		st_volatile_u64(status + tile, etag | (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | ctotal);
+		uint32_t excl = 0;
+		if (tile > 0) {
+			uint32_t p = tile - 1;
+			for (;;) {
+				const unsigned long long v = ld_volatile_u64(status + p);
+				if ((v >> 32) != epoch || !((uint32_t)v >> 30)) continue;
+				excl += (uint32_t)v & OS_COUNT_MASK;
+				if ((uint32_t)v & OS_FLAG_PREFIX) break;
+				--p;
+			}
+			st_volatile_u64(status + tile, etag | OS_FLAG_PREFIX | (excl + ctotal));
+		}
+		s_excl = excl;
+		if (tbase + RM_TILE >= n) *nruns_total = (unsigned long long)excl + ctotal;
+	}
+	__syncthreads();
+	const uint32_t before_warp = s_excl + wexcl;		// run starts at positions < wbase
+
+	// the run the chunk's first key belongs to: #starts at positions <= wbase, minus one
+	if (lane == 0) chunk_run[wbase >> 7] = before_warp + (words[0] & 1u) - 1u;
+
+	// one cursor bump per warp for all the service segments that start in it
+	uint32_t nstart = __popc(isseg);
+	uint32_t incl = nstart;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+	const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+	unsigned long long tb = 0;
+	if (wtotal && lane == 0) tb = atomicAdd(ntouched, (unsigned long long)wtotal);
+	tb = __shfl_sync(0xffffffffu, tb, 0) + (incl - nstart);
+
+	uint32_t acc = before_warp;
+#pragma unroll
+	for (int t = 0; t < RM_V; ++t) {
+		const uint64_t i = wbase + (uint64_t)t * 32 + lane;
+		const uint32_t incl_here = acc + __popc(words[t] & (0xFFFFFFFFu >> (31 - lane)));	// run starts at positions <= i
+		const uint32_t slot = (uint32_t)(g[1 + t] >> TD_CODE_BITS);
+		if ((isrun >> t) & 1u) {
+			pool[incl_here - 1] = RunRec {0, 0};
+			run_bin[incl_here - 1] = (uint16_t)(g[1 + t] & ((1u << TD_CODE_BITS) - 1u));
+		}
+		if ((isseg >> t) & 1u) { segs[slot].run0 = incl_here - 1; segs[slot].key0 = (uint32_t)i; touched[tb++] = slot; }
+		if ((isend >> t) & 1u) { segs[slot].nruns = incl_here; segs[slot].nkeys = (uint32_t)(i + 1); }	// ends for now: the merge kernel subtracts
+		acc += __popc(words[t]);
+	}
 }
 
-// One CTA per touched service (grid sized for every slot, surplus CTAs leave at once): reads the service's NBINS bins (4 per
-// thread, all in flight together); a non-empty bin becomes one item {mean = usec sum / samples, weight = samples} of the batch,
-// written IN BIN ORDER (= value order: the bin index is monotone) into the batch's item pool, and adds {samples, msec sum} to its
-// bucket of the window's histogram — GY_HISTOGRAM::add_data for every sample of the bin (common/gy_statistics.h:596-623); the bin
-// is zeroed. max_val_seen_ comes from the batch's exact maximum.
-static constexpr int SCAN_THREADS = 256, SCAN_BPT = (NBINS + SCAN_THREADS - 1) / SCAN_THREADS;		// 4 bins per thread
+static constexpr int RS_V = 4;			// consecutive sorted samples per lane
 
-struct BatchSeg { uint32_t base, nitems; unsigned long long nsamples; };		// a touched service's run in the item pool
-
-__global__ void __launch_bounds__(SCAN_THREADS) bins_scan_kernel(DevState st, const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p,
-		Centroid *__restrict__ pool, unsigned long long *__restrict__ pool_cursor, BatchSeg *__restrict__ segs)
+__global__ void __launch_bounds__(256) runs_sum_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
+		const uint32_t *__restrict__ chunk_run, RunRec *__restrict__ pool)
 {
-	__shared__ unsigned long long hcnt[16], hsum[16], ssamples;
-	__shared__ uint32_t wcnt[SCAN_BPT][SCAN_THREADS / 32], sbase;
-	__shared__ uint16_t first_idx[16];
-	const uint32_t t = blockIdx.x;
-	if (t >= (uint32_t)*ntouched_p) return;
-	const uint32_t slot = touched[t];
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	Bin *bins = st.bins + (size_t)slot * NBINS;
+	const uint64_t n = *d_n;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * RS_V;
+	const int lane = threadIdx.x & 31;
 
-	Bin b[SCAN_BPT];
-#pragma unroll
-	for (int j = 0; j < SCAN_BPT; ++j) {
-		const uint32_t i = j * SCAN_THREADS + threadIdx.x;
-		b[j] = i < (uint32_t)NBINS ? bins[i] : Bin {0, 0};
-	}
-	if (threadIdx.x < 16) {
-		hcnt[threadIdx.x] = 0; hsum[threadIdx.x] = 0;
-		// thresholds of RESP_TIME_HASH in msec (gy_statistics.h:1677): bucket b >= 2 starts at (thr[b-2] + 1) msec, bucket 1 at 0
-		constexpr uint32_t thr[13] = {1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000};
-		const uint32_t bk = threadIdx.x;
-		const uint32_t first_us = bk < 2 ? 0u : (bk > 14 ? 0xFFFFFFFFu : (thr[bk - 2] + 1u) * 1000u);
-		first_idx[bk] = (uint16_t)(bk == 0 ? 0u : (bk > 14 ? 0xFFFFu : td_code(first_us) + bk));
-		if (threadIdx.x == 0) ssamples = 0;
-	}
-	uint32_t mball[SCAN_BPT];
-#pragma unroll
-	for (int j = 0; j < SCAN_BPT; ++j) {
-		mball[j] = __ballot_sync(0xffffffffu, b[j].cw != 0);
-		if (lane == 0) wcnt[j][wid] = __popc(mball[j]);
-	}
-	__syncthreads();
-	// exclusive prefix over (j, warp) in bin order; thread 0 reserves the service's run in the pool
-	uint32_t before = 0, total = 0;
-#pragma unroll
-	for (int j = 0; j < SCAN_BPT; ++j) {
-#pragma unroll
-		for (int w = 0; w < SCAN_THREADS / 32; ++w) { const uint32_t c = wcnt[j][w]; total += c; }
-	}
-	if (threadIdx.x == 0) sbase = (uint32_t)atomicAdd(pool_cursor, (unsigned long long)total);
-	unsigned long long mysamples = 0;
-	uint32_t run = 0;
-	uint32_t rank[SCAN_BPT];
-#pragma unroll
-	for (int j = 0; j < SCAN_BPT; ++j) {
-#pragma unroll
-		for (int w = 0; w < SCAN_THREADS / 32; ++w) { if (w == wid) before = run; run += wcnt[j][w]; }
-		rank[j] = before + __popc(mball[j] & ((1u << lane) - 1u));
-	}
-	__syncthreads();
-	const uint32_t base = sbase;
-#pragma unroll
-	for (int j = 0; j < SCAN_BPT; ++j) {
-		if (b[j].cw) {
-			const uint32_t i = j * SCAN_THREADS + threadIdx.x;
-			const unsigned long long cnt = b[j].cw & BIN_CNT_MASK, rem = b[j].cw >> BIN_CNT_BITS;
-			Centroid c; c.mean = __ddiv_rn((double)b[j].us, (double)cnt); c.weight = cnt;	// exact integer sum, one rounding
-			pool[base + rank[j]] = c;
-			uint32_t bk = 0;
-#pragma unroll
-			for (int q = 1; q < 15; ++q) bk += i >= first_idx[q];
-			atomicAdd(&hcnt[bk], cnt);
-			atomicAdd(&hsum[bk], (b[j].us - rem) / 1000ull);		// sum of (usec / 1000) over the bin's samples
-			bins[i] = Bin {0, 0};
-			mysamples += cnt;
+	for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x - lane) * RS_V; base < n; base += stride) {
+		const uint64_t i0 = base + (uint64_t)lane * RS_V;
+		unsigned long long kk[RS_V];
+		if (i0 + RS_V <= n) {
+			const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0), c = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
+			kk[0] = a.x; kk[1] = a.y; kk[2] = c.x; kk[3] = c.y;
 		}
-	}
-	for (int off = 16; off > 0; off >>= 1) mysamples += __shfl_xor_sync(0xffffffffu, mysamples, off);
-	if (lane == 0 && mysamples) atomicAdd(&ssamples, mysamples);
-	__syncthreads();
-	// nobody else touches this slot's window histogram while the batch is merged (same stream as the flush): plain updates
-	if (threadIdx.x < HIST_MAX_CELL) {
-		if (hcnt[threadIdx.x]) {
-			HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + threadIdx.x;
-			c->count += hcnt[threadIdx.x]; c->sum += (long long)hsum[threadIdx.x];
+		else {
+#pragma unroll
+			for (int t = 0; t < RS_V; ++t) kk[t] = i0 + t < n ? keys[i0 + t] : ~0ull;
 		}
-	}
-	else if (threadIdx.x == HIST_MAX_CELL) {
-		HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + HIST_MAX_CELL;
-		const long long mx = (long long)(st.slot_batch[slot].maxv / 1000u);		// max_val_seen_ of add_data (gy_statistics.h:609-611)
-		if (mx > c->sum) c->sum = mx;
-		segs[t] = BatchSeg {base, total, ssamples};
+		const uint32_t run_first = chunk_run[base >> 7];
+
+		// whole chunk inside one run (a popular bin of a hot service): one RED pair for 128 samples
+		const unsigned long long gfirst = __shfl_sync(0xffffffffu, kk[0], 0) >> KEY_GROUP_SHIFT, glast = __shfl_sync(0xffffffffu, kk[RS_V - 1], 31) >> KEY_GROUP_SHIFT;
+		if (gfirst == glast && glast != (~0ull >> KEY_GROUP_SHIFT)) {
+			unsigned long long us = 0;
+			uint32_t rem = 0;
+#pragma unroll
+			for (int t = 0; t < RS_V; ++t) { const uint32_t v = key_usec(kk[t]); us += v; rem += v - (v / 1000u) * 1000u; }
+			const unsigned long long gsum = (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)us & 0xFFFFFu) +
+					((unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)(us >> 20)) << 20);	// us < 2^32: 20 + 12 bits, x 32 lanes fits
+			rem = __reduce_add_sync(0xffffffffu, rem);
+			if (lane == 0) {
+				red_add_u64(&pool[run_first].cw, (unsigned long long)(32 * RS_V) | ((unsigned long long)rem << BIN_CNT_BITS));
+				red_add_u64(&pool[run_first].us, gsum);
+			}
+			continue;
+		}
+
+		// run index of every own sample: run of the chunk's first key + run starts at later positions up to the sample
+		unsigned long long gprev = __shfl_up_sync(0xffffffffu, kk[RS_V - 1], 1) >> KEY_GROUP_SHIFT;		// last key of the previous lane
+		uint32_t heads = 0, nh = 0;
+#pragma unroll
+		for (int t = 0; t < RS_V; ++t) {
+			const unsigned long long gcur = kk[t] >> KEY_GROUP_SHIFT;
+			const bool head = kk[t] != ~0ull && !(lane == 0 && t == 0) && gcur != gprev;
+			heads |= (head ? 1u : 0u) << t; nh += head ? 1u : 0u;
+			gprev = gcur;
+		}
+		uint32_t incl = nh;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+		uint32_t run = run_first + (incl - nh);
+
+		// own samples -> lane-local runs; sample t carries the totals of its run so far, only the last one of a run is emitted
+		uint32_t pr[RS_V], pc[RS_V], prem[RS_V];
+		unsigned long long ps[RS_V];
+		bool tail[RS_V];
+#pragma unroll
+		for (int t = 0; t < RS_V; ++t) {
+			const bool valid = kk[t] != ~0ull;
+			tail[t] = valid;
+			if ((heads >> t) & 1u) ++run;
+			const uint32_t v = key_usec(kk[t]);
+			pr[t] = valid ? run : (0x80000000u | (uint32_t)lane); pc[t] = valid ? 1u : 0u; ps[t] = valid ? v : 0u; prem[t] = valid ? v - (v / 1000u) * 1000u : 0u;
+			if (t > 0 && valid && pr[t] == pr[t - 1]) { pc[t] += pc[t - 1]; ps[t] += ps[t - 1]; prem[t] += prem[t - 1]; tail[t - 1] = false; }
+		}
+#pragma unroll
+		for (int t = 0; t < RS_V; ++t) {
+			const bool act = tail[t];
+			if (!__any_sync(0xffffffffu, act)) continue;
+			const uint32_t rid = act ? pr[t] : (0x80000000u | (uint32_t)lane);
+			const unsigned long long v = act ? ps[t] : 0ull;
+			uint32_t cnt = act ? pc[t] : 0u, rem = act ? prem[t] : 0u;
+			const uint32_t m = __match_any_sync(0xffffffffu, rid);
+			unsigned long long gsum = v;
+			const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(m));
+			uint32_t rest = m & ~(1u << lane);
+			const uint32_t cnt0 = cnt, rem0 = rem;
+			for (uint32_t u = 1; u < maxcnt; ++u) {
+				const int src = rest ? (__ffs(rest) - 1) : lane;
+				const unsigned long long ov = __shfl_sync(0xffffffffu, v, src);
+				const uint32_t oc = __shfl_sync(0xffffffffu, cnt0, src), orr = __shfl_sync(0xffffffffu, rem0, src);
+				if (rest) { gsum += ov; cnt += oc; rem += orr; rest &= rest - 1; }
+			}
+			if (act && (m & ((1u << lane) - 1u)) == 0) {
+				red_add_u64(&pool[rid].cw, (unsigned long long)cnt | ((unsigned long long)rem << BIN_CNT_BITS));
+				red_add_u64(&pool[rid].us, gsum);
+			}
+		}
 	}
 }
 
 static constexpr int TD_WARPS = 4;
 
-// One warp per touched service: the batch's items are merged with the old centroids (old first on equal means) and the greedy
-// K_1 pass cuts the list down to at most TD_CAP clusters (warp_merge_compress). Lists of up to 2 x TD_CAP entries work in shared
-// memory; longer ones (a first batch of a service can fill several hundred bins) in the warp's L2-resident scratch — same code,
-// same result. The digest's ends come from the batch's exact min / max, which are reset for the next batch.
+// One warp per touched service. Its runs become the batch's items {mean = exact usec sum / samples, weight = samples} — in value
+// order, because the bin index is monotone — and every run adds {samples, exact msec sum} to its bucket of the window histogram:
+// GY_HISTOGRAM::add_data for each of its samples (common/gy_statistics.h:596-623); max_val_seen_ and the digest's ends come from
+// the batch's exact extremes. The items are then merged with the old centroids (old first on equal means) and the greedy K_1
+// pass cuts the list to at most TD_CAP clusters (warp_merge_compress). Lists of up to 2 x TD_CAP entries work in shared memory;
+// longer ones (a first batch can fill several hundred bins) in the warp's L2-resident scratch — same code, same result.
 __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p,
-		const Centroid *__restrict__ pool, const BatchSeg *__restrict__ segs, TdWorkBig *__restrict__ big_scratch /* [nwarps] */)
+		const RunRec *__restrict__ pool, const uint16_t *__restrict__ run_bin, const BatchSeg *__restrict__ segs,
+		Centroid *__restrict__ items_scratch /* [nwarps][NBINS] */, TdWorkBig *__restrict__ big_scratch /* [nwarps] */)
 {
 	__shared__ TdWork work[TD_WARPS];
+	__shared__ unsigned long long hcnt[TD_WARPS][16], hsum[TD_WARPS][16];
+	__shared__ uint16_t first_idx[16];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * TD_WARPS + wid, nwarps = gridDim.x * TD_WARPS;
+	Centroid *items = items_scratch + (size_t)gw * NBINS;
 	const uint32_t ntouched = (uint32_t)*ntouched_p;
+
+	if (threadIdx.x < 16) {
+		// thresholds of RESP_TIME_HASH in msec (gy_statistics.h:1677): bucket b >= 2 starts at (thr[b-2] + 1) msec, bucket 1 at 0;
+		// bin index = td_code(usec) + bucket, so bucket b's bins start at td_code(first usec of the bucket) + b
+		constexpr uint32_t thr[13] = {1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000};
+		const uint32_t bk = threadIdx.x;
+		const uint32_t first_us = bk < 2 ? 0u : (bk > 14 ? 0u : (thr[bk - 2] + 1u) * 1000u);
+		first_idx[bk] = (uint16_t)(bk == 0 ? 0u : (bk > 14 ? 0xFFFFu : td_code(first_us) + bk));
+	}
+	__syncthreads();
 
 	for (uint32_t t = gw; t < ntouched; t += nwarps) {
 		const uint32_t slot = touched[t];
-		const BatchSeg seg = segs[t];
-		const Centroid *items = pool + seg.base;
+		const BatchSeg seg = segs[slot];
+		const uint32_t nitems = seg.nruns - seg.run0;			// runs_mark_kernel left the END positions in nruns / nkeys
+		const uint32_t nsamples = seg.nkeys - seg.key0;
+		if (lane < 16) { hcnt[wid][lane] = 0; hsum[wid][lane] = 0; }
+		__syncwarp();
+		for (uint32_t j = lane; j < nitems; j += 32) {
+			const RunRec r = pool[seg.run0 + j];
+			const unsigned long long cnt = r.cw & BIN_CNT_MASK, rem = r.cw >> BIN_CNT_BITS;
+			Centroid c; c.mean = __ddiv_rn((double)r.us, (double)cnt); c.weight = cnt;	// exact integer sum, one rounding
+			items[j] = c;
+			const uint32_t bin = run_bin[seg.run0 + j];
+			uint32_t bk = 0;
+#pragma unroll
+			for (int q = 1; q < 15; ++q) bk += bin >= first_idx[q];
+			atomicAdd(&hcnt[wid][bk], cnt);
+			atomicAdd(&hsum[wid][bk], (r.us - rem) / 1000ull);		// sum of (usec / 1000) over the run's samples
+		}
+		__syncwarp();
+		// nobody else touches this slot's window histogram while the batch is merged (same stream as the flush): plain updates
 		const SlotBatch sb = st.slot_batch[slot];
+		if (lane < HIST_MAX_CELL) {
+			if (hcnt[wid][lane]) {
+				HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + lane;
+				c->count += hcnt[wid][lane]; c->sum += (long long)hsum[wid][lane];
+			}
+		}
+		else if (lane == HIST_MAX_CELL) {
+			HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + HIST_MAX_CELL;
+			const long long mx = (long long)(sb.maxv / 1000u);		// max_val_seen_ of add_data (gy_statistics.h:609-611)
+			if (mx > c->sum) c->sum = mx;
+			st.slot_batch[slot] = SlotBatch {0xFFFFFFFFu, 0u, 0u, 0u};
+		}
+		__syncwarp();
+
 		TdHead head = st.td_head[slot];
 		Centroid *cent = st.td_cent + (size_t)slot * TD_CAP;
 		uint32_t nout;
-		if (head.n + seg.nitems <= 2u * TD_CAP) nout = warp_merge_compress(work[wid], cent, head.n, items, seg.nitems, cent, st.td);
-		else nout = warp_merge_compress(big_scratch[gw], cent, head.n, items, seg.nitems, cent, st.td);
+		if (head.n + nitems <= 2u * TD_CAP) nout = warp_merge_compress(work[wid], cent, head.n, items, nitems, cent, st.td);
+		else nout = warp_merge_compress(big_scratch[gw], cent, head.n, items, nitems, cent, st.td);
 		if (lane == 0) {
 			head.n = nout;
-			head.total += seg.nsamples;
+			head.total += nsamples;
 			if ((double)sb.minv < head.minv) head.minv = (double)sb.minv;
 			if ((double)sb.maxv > head.maxv) head.maxv = (double)sb.maxv;
 			st.td_head[slot] = head;
-			st.slot_batch[slot] = SlotBatch {0xFFFFFFFFu, 0u, 0u, 0u};
 		}
 		__syncwarp();
 	}
@@ -1049,8 +1225,24 @@ static int ingest_variant()
 	return v;
 }
 
+// the radix passes of the RESP keys sort on {slot | bin} = key bits [30, 40 + slot bits): TD_CODE_BITS + slot bits significant
+// bits cut into the fewest digits of at most 9 bits, widths as even as possible (27 bits -> 9 9 9; 30 bits -> 8 8 7 7)
+static int key_sort_plan(uint32_t max_svcs, SortPlan &P)
+{
+	int slot_bits = 1;
+	while (slot_bits < 24 && (1ull << slot_bits) < max_svcs) slot_bits++;
+	const int T = TD_CODE_BITS + slot_bits;
+	const int np = (T + RADIX_MAX_BITS - 1) / RADIX_MAX_BITS;
+	if (np > OS_MAX_PASSES_VK) return -1;
+	int at = KEY_GROUP_SHIFT;
+	for (int p = 0; p < np; ++p) { P.bits[p] = T / np + (p < T % np ? 1 : 0); P.shift[p] = at; at += P.bits[p]; }
+	P.np = np;
+	return np;
+}
+
 template <int WARPS, int MIN_CTAS, int EPT, bool TMA>
-static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, int dev, cudaStream_t s)
+static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, uint32_t *ghist, const SortPlan &plan,
+		int dev, cudaStream_t s)
 {
 	using Shared = IngestSharedT<WARPS, EPT, TMA>;
 	static bool attr_set[MAX_DEVICES] = {};
@@ -1060,27 +1252,31 @@ static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, ui
 	}
 	const uint64_t want = (n + (uint64_t)Shared::CHUNK * WARPS - 1) / ((uint64_t)Shared::CHUNK * WARPS);
 	const uint64_t full = (uint64_t)sm_count(dev) * MIN_CTAS;
-	ingest_kernel<WARPS, MIN_CTAS, EPT, TMA><<<(uint32_t)(want < full ? want : full), WARPS * 32, sizeof(Shared), s>>>(st, d_ev, n, 0);
+	ingest_kernel<WARPS, MIN_CTAS, EPT, TMA><<<(uint32_t)(want < full ? want : full), WARPS * 32, sizeof(Shared), s>>>(st, d_ev, n, d_keys, ghist, plan);
 }
 
-int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, cudaStream_t s)
+int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_ev, uint64_t n, uint32_t max_svcs, cudaStream_t s)
 {
 	if (!n) return 0;
 	const int dev = current_device();
+	SortPlan plan {};
+	if (key_sort_plan(max_svcs, plan) < 0) return -1;
+	// key cursor, digit histograms and tile tickets of this batch's sort
+	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, sizeof(unsigned long long), s);
+	cudaMemsetAsync(tmp.os_ghist, 0, (OS_MAX_PASSES * RADIX_MAX + OS_MAX_PASSES) * sizeof(uint32_t), s);
+#define GYSK_LI(W, C, E, T) launch_ingest_variant<W, C, E, T>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s)
 	switch (ingest_variant()) {
-	case 842 : launch_ingest_variant<8, 4, 2, false>(st, d_ev, n, dev, s); break;
-	case 852 : launch_ingest_variant<8, 5, 2, false>(st, d_ev, n, dev, s); break;
-	case 834 : launch_ingest_variant<8, 3, 4, false>(st, d_ev, n, dev, s); break;
-	case 844 : launch_ingest_variant<8, 4, 4, false>(st, d_ev, n, dev, s); break;
-	case 832 : launch_ingest_variant<8, 3, 2, false>(st, d_ev, n, dev, s); break;
-	case 482 : launch_ingest_variant<4, 8, 2, false>(st, d_ev, n, dev, s); break;
-	case 828 : launch_ingest_variant<8, 2, 8, false>(st, d_ev, n, dev, s); break;
-	case 1824 : launch_ingest_variant<8, 2, 4, true>(st, d_ev, n, dev, s); break;
-	case 1828 : launch_ingest_variant<8, 2, 8, true>(st, d_ev, n, dev, s); break;
-	case 1842 : launch_ingest_variant<8, 4, 2, true>(st, d_ev, n, dev, s); break;	// TMA-staged chunks
-	case 1834 : launch_ingest_variant<8, 3, 4, true>(st, d_ev, n, dev, s); break;
-	default : launch_ingest_variant<8, 4, 2, false>(st, d_ev, n, dev, s); break;
+	case 842 : GYSK_LI(8, 4, 2, false); break;
+	case 852 : GYSK_LI(8, 5, 2, false); break;
+	case 834 : GYSK_LI(8, 3, 4, false); break;
+	case 844 : GYSK_LI(8, 4, 4, false); break;
+	case 832 : GYSK_LI(8, 3, 2, false); break;
+	case 482 : GYSK_LI(4, 8, 2, false); break;
+	case 1832 : GYSK_LI(8, 3, 2, true); break;	// TMA-staged chunks
+	case 1834 : GYSK_LI(8, 3, 4, true); break;
+	default : GYSK_LI(8, 3, 2, false); break;
 	}
+#undef GYSK_LI
 	return 1;
 }
 
@@ -1178,19 +1374,43 @@ int launch_radix_sort(const SortTemp &tmp, const unsigned long long *d_n, uint64
 	return launches;
 }
 
-// after the ingest kernel of a batch: every service that received RESP samples gets its bins folded into its window histogram
-// and its digest. Nothing here needs a number from the device on the host: the list length stays in st.counters[CTR_NTOUCHED].
-int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint32_t max_svcs, cudaStream_t s)
+// after the ingest kernel of a batch: sort its RESP keys by {slot, bin}, reduce them to one record per run and fold every touched
+// service's runs into its window histogram and its digest. Nothing here needs a number from the device on the host: the key
+// count lives in st.counters[CTR_NKEYS], the digit histograms in tmp.os_ghist (both written by ingest_kernel); grids are sized by
+// n_events, the largest possible key count, and surplus CTAs leave at once.
+int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint64_t n_events, uint32_t max_svcs, cudaStream_t s)
 {
-	const int nsm = sm_count(current_device());
-	unsigned long long *d_ntouched = st.counters + CTR_NTOUCHED;
+	if (!n_events) return 0;
+	int launches = 0;
+	unsigned long long *d_nkeys = st.counters + CTR_NKEYS, *d_ntouched = st.counters + CTR_NTOUCHED;
+	const int dev = current_device();
+	const int nsm = sm_count(dev);
+	os_set_attrs(dev);
+
+	SortPlan plan {};
+	if (key_sort_plan(max_svcs, plan) < 0) return -1;
+	const uint32_t ntiles = div_up(n_events, SORT_TILE);
+	unsigned long long *bufs[2] = { tmp.keys_a, tmp.keys_b };
+	uint32_t *ghist = tmp.os_ghist, *tickets = tmp.os_ghist + OS_MAX_PASSES * RADIX_MAX;
+	int w = 0;
+	for (int p = 0; p < plan.np; ++p) {
+		const DigitSpec D { plan.shift[p], plan.bits[p], 0, 0 };
+		const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
+		if (plan.bits[p] > 8) os_pass_kernel<9><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], d_nkeys, D, ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
+		else os_pass_kernel<8><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], d_nkeys, D, ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
+		launches++;
+		w ^= 1;
+	}
+	const unsigned long long *src = bufs[w];
+
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
-	cudaMemsetAsync(tmp.pool_cursor, 0, sizeof(unsigned long long), s);
-	touched_kernel<<<div_up(max_svcs, 256), 256, 0, s>>>(st, max_svcs, tmp.touched, d_ntouched);
-	bins_scan_kernel<<<max_svcs, SCAN_THREADS, 0, s>>>(st, tmp.touched, d_ntouched, tmp.pool, tmp.pool_cursor, reinterpret_cast<BatchSeg *>(tmp.segs));
-	bins_merge_kernel<<<std::min(nsm, TD_MERGE_MAX_SMS) * TD_MERGE_CTAS_PER_SM, TD_WARPS * 32, 0, s>>>(st, tmp.touched, d_ntouched, tmp.pool,
-			reinterpret_cast<const BatchSeg *>(tmp.segs), tmp.big_scratch);
-	return 3;
+	const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
+	runs_mark_kernel<<<div_up(n_events, RM_TILE), RM_THREADS, 0, s>>>(src, d_nkeys, tmp.tile_status, epoch, reinterpret_cast<RunRec *>(tmp.pool), tmp.run_bin,
+			tmp.chunk_run, reinterpret_cast<BatchSeg *>(tmp.segs), tmp.touched, d_ntouched, st.counters + CTR_NRUNS);
+	runs_sum_kernel<<<nsm * 8, 256, 0, s>>>(src, d_nkeys, tmp.chunk_run, reinterpret_cast<RunRec *>(tmp.pool));
+	bins_merge_kernel<<<std::min(nsm, TD_MERGE_MAX_SMS) * TD_MERGE_CTAS_PER_SM, TD_WARPS * 32, 0, s>>>(st, tmp.touched, d_ntouched,
+			reinterpret_cast<const RunRec *>(tmp.pool), tmp.run_bin, reinterpret_cast<const BatchSeg *>(tmp.segs), tmp.items_scratch, tmp.big_scratch);
+	return launches + 3;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -22,7 +22,6 @@ struct DevState
 	unsigned long long	*evict_ids;
 	unsigned long long	*conn_all_cnt, *conn_all_kb;
 	uint32_t		*bm_cur, *bm_last;			// [max_svcs][16] CONN_BITMAP transposed: per bucket a mask over (client port & 31)
-	Bin			*bins;					// [max_svcs][NBINS] value bins of the batch being ingested (zero between batches)
 	SlotBatch		*slot_batch;				// [max_svcs] batch extremes + "has bins to merge"
 	uint8_t			*hll;					// [max_svcs][1 << hll_p]
 	Centroid		*td_cent;				// [max_svcs][TD_CAP]
@@ -43,14 +42,16 @@ struct DevState
 
 struct SortTemp
 {
-	unsigned long long	*keys_a, *keys_b;	// [max(max_svcs, max_tasks)] top-N sort keys
+	unsigned long long	*keys_a, *keys_b;	// [max_batch] RESP sort keys of the batch (also the top-N sort keys)
 	unsigned long long	*tile_status;		// [max_tiles][512] look-back status words {pass epoch | state | count}: never cleared
 	uint32_t		*epoch;			// HOST counter of radix passes launched (tags the status words)
 	uint32_t		*os_ghist;		// [8][512] global digit histograms of the one-sweep passes + [8] tile tickets
 	uint32_t		*touched;		// [max_svcs] services with RESP samples in the batch
-	Centroid		*pool;			// [pool_cap] items (non-empty bins) of the batch, one run per touched service
-	unsigned long long	*pool_cursor;
-	ulonglong2		*segs;			// [max_svcs] BatchSeg of each touched service
+	ulonglong2		*pool;			// [pool_cap] RunRec: one record per run (non-empty bin of a service) of the batch
+	uint16_t		*run_bin;		// [pool_cap] bin index of each run
+	uint32_t		*chunk_run;		// [max_batch / 128] run of the first key of every 128-key chunk
+	uint4			*segs;			// [max_svcs] BatchSeg of each touched service
+	Centroid		*items_scratch;		// [merge warps][NBINS] a warp's list of batch items
 	TdWorkBig		*big_scratch;		// [merge warps] work arrays for merged lists beyond 2 x TD_CAP entries
 	uint32_t		max_tiles;
 };
@@ -83,13 +84,14 @@ static constexpr int NSLOTS = 10;			// slots per level (gy_statistics.h:1105)
 static constexpr int SORT_TILE = 4096;		// keys per CTA tile in the radix passes
 static constexpr int RADIX_MAX_BITS = 9;
 static constexpr int RADIX_MAX = 1 << RADIX_MAX_BITS;
+static constexpr int OS_MAX_PASSES_VK = 4;		// {slot : <= 24 | bin : 10} in digits of <= 9 bits
 static constexpr int TD_MERGE_CTAS_PER_SM = 5, TD_MERGE_MAX_SMS = 192;	// bins_merge_kernel grid (4 warps per CTA)
 
 // every launcher returns the number of kernel launches it issued
 int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks, cudaStream_t s);
 int launch_register(const DevState &st, const unsigned long long *d_ids, uint32_t n, int is_task, cudaStream_t s);
-int launch_ingest(const DevState &st, const gysk_event *d_ev, uint64_t n, cudaStream_t s);
-int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint32_t max_svcs, cudaStream_t s);
+int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_ev, uint64_t n, uint32_t max_svcs, cudaStream_t s);
+int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint64_t n_events, uint32_t max_svcs, cudaStream_t s);
 int launch_radix_sort(const SortTemp &tmp, const unsigned long long *d_n, uint64_t n_max, int lo1, int hi1, int lo2, int hi2, int *which, cudaStream_t s);
 int radix_sort_plan(int lo1, int hi1, int lo2, int hi2, int out[][4], int cap);
 int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int metric, int host_filter, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
