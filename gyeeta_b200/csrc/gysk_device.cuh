@@ -36,6 +36,10 @@ static constexpr int NBINS = 848;				// 832 codes + 15 buckets, padded to a mult
 static constexpr int BIN_CNT_BITS = 27;
 static constexpr unsigned long long BIN_CNT_MASK = (1ull << BIN_CNT_BITS) - 1;
 
+// per-service counters beside the histograms: ACTIVE_CONN_STATS roll-up {active conns : 32 | kbytes : 32}, max rtt (float bits),
+// API_TRAN error counters {client errors : 32 | server errors : 32}; cur = window being filled, last = last closed window
+struct alignas(8) SlotAux { unsigned long long act_cur, act_last, err_cur, err_last; uint32_t rtt_cur, rtt_last; };
+
 // per-service scratch of the batch being ingested: exact extremes of its RESP samples and "has bins to merge"
 struct alignas(16) SlotBatch { uint32_t minv, maxv, touched, pad; };
 

@@ -12,6 +12,7 @@ using namespace gysk;
 namespace {
 
 thread_local std::string g_create_error;
+std::atomic<uint64_t> g_engine_uid {1};
 
 } // namespace
 
@@ -96,23 +97,44 @@ int gysk::collect_evicted(gysk_engine *e, bool wait)
 	return 0;
 }
 
-// hand the filled part of the current staging buffer to the device
+// ---- staging: per-thread page-locked buffers -> device event buffer -> kernels -------------------------------------
+//
+// Up to 16 handle_l2_misc threads call gysk_ingest concurrently (server/gy_mconnhdlr.h:53-63, routing :16252). Each calling
+// thread owns a ThreadStage: two page-locked chunks it fills WITHOUT the engine mutex — validation, record walk and compaction of
+// the wire records run in parallel across threads. Only a full chunk takes the engine mutex, for as long as it takes to enqueue
+// one asynchronous H2D copy into the current device event buffer (and, when that buffer is full, the batch's kernel launches).
+// Readers (sync, flush, queries) first drain every thread's partial chunk, so "all events handed in before the call are applied".
+// Lock order: ThreadStage::m, then gysk_engine::mtx; drain_all takes tstage_mtx, then each ThreadStage::m in turn.
+
+// device event buffer k holds stage_fill events whose copies are enqueued on copy_stream: run the batch
 int gysk::submit_stage(gysk_engine *e)
 {
 	const int k = e->stage_cur;
 	const uint32_t n = e->stage_fill;
 
 	if (!n) return 0;
-	CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_done[k], 0));		// device buffer k no longer read by kernels
-	CU(e, cudaMemcpyAsync(e->d_events[k], e->h_stage[k], (size_t)n * sizeof(gysk_event), cudaMemcpyHostToDevice, e->copy_stream));
 	CU(e, cudaEventRecord(e->ev_copied[k], e->copy_stream));
 	CU(e, cudaStreamWaitEvent(e->stream, e->ev_copied[k], 0));
 	int rc = process_device_batch(e, e->d_events[k], n, [&]() -> int { CU(e, cudaEventRecord(e->ev_done[k], e->stream)); return 0; });
 	if (rc) return rc;
-
 	e->stage_cur = (k + 1) % NBUF;
 	e->stage_fill = 0;
-	CU(e, cudaEventSynchronize(e->ev_copied[e->stage_cur]));		// host may overwrite the next staging buffer
+	return 0;
+}
+
+// enqueue the copy of n events from page-locked host memory behind what the current device buffer already holds (engine mutex held)
+int gysk::append_chunk(gysk_engine *e, const gysk_event *src, uint64_t n)
+{
+	while (n) {
+		const int k = e->stage_cur;
+		const uint32_t room = e->cfg.stage_batch - e->stage_fill;
+		const uint32_t m = (uint32_t)std::min<uint64_t>(room, n);
+
+		if (e->stage_fill == 0) CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_done[k], 0));	// the kernels that last read buffer k have run
+		CU(e, cudaMemcpyAsync(e->d_events[k] + e->stage_fill, src, (size_t)m * sizeof(gysk_event), cudaMemcpyHostToDevice, e->copy_stream));
+		e->stage_fill += m; src += m; n -= m;
+		if (e->stage_fill == e->cfg.stage_batch) { int rc = submit_stage(e); if (rc) return rc; }
+	}
 	return 0;
 }
 
@@ -127,24 +149,75 @@ int gysk::sync_locked(gysk_engine *e)
 
 namespace {
 
-int stage_events(gysk_engine *e, const gysk_event *ev, uint64_t n)
+thread_local std::vector<std::pair<uint64_t, ThreadStage *>> tls_stages;
+
+// the calling thread's stage of this engine (created on first use)
+ThreadStage *get_stage(gysk_engine *e)
+{
+	for (auto &kv : tls_stages) if (kv.first == e->uid) return kv.second;
+	std::lock_guard<std::mutex> lk(e->tstage_mtx);
+	auto ts = std::make_unique<ThreadStage>();
+	ts->cap = std::min<uint32_t>(e->cfg.stage_batch, THREAD_STAGE_EVENTS);
+	if (cudaSetDevice(e->dev) != cudaSuccess) return nullptr;
+	for (int i = 0; i < 2; ++i) {
+		if (cudaHostAlloc((void **)&ts->buf[i], (size_t)ts->cap * sizeof(gysk_event), cudaHostAllocDefault) != cudaSuccess) return nullptr;
+		if (cudaEventCreateWithFlags(&ts->copied[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+	}
+	ThreadStage *raw = ts.get();
+	e->tstages.push_back(std::move(ts));
+	if (tls_stages.size() > 64) tls_stages.erase(tls_stages.begin());		// engines long gone
+	tls_stages.emplace_back(e->uid, raw);
+	return raw;
+}
+
+// hand the filled part of the thread's current chunk to the device (ThreadStage::m held by the caller)
+int flush_stage(gysk_engine *e, ThreadStage *ts)
+{
+	if (!ts->fill) return 0;
+	{
+		std::lock_guard<std::mutex> lk(e->mtx);
+		CU(e, cudaSetDevice(e->dev));
+		int rc = append_chunk(e, ts->buf[ts->cur], ts->fill);
+		if (rc) return rc;
+		CU(e, cudaEventRecord(ts->copied[ts->cur], e->copy_stream));
+	}
+	ts->cur ^= 1; ts->fill = 0;
+	CU(e, cudaEventSynchronize(ts->copied[ts->cur]));		// the other chunk's copy (issued a whole chunk ago) has left the host
+	return 0;
+}
+
+inline gysk_event *stage_slot(gysk_engine *e, ThreadStage *ts, int *rc)
+{
+	if (ts->fill == ts->cap) { *rc = flush_stage(e, ts); if (*rc) return nullptr; }
+	return ts->buf[ts->cur] + ts->fill++;
+}
+
+int stage_events(gysk_engine *e, ThreadStage *ts, const gysk_event *ev, uint64_t n)
 {
 	while (n) {
-		const uint32_t room = e->cfg.stage_batch - e->stage_fill;
-		const uint32_t m = (uint32_t)std::min<uint64_t>(room, n);
-
-		memcpy(e->h_stage[e->stage_cur] + e->stage_fill, ev, (size_t)m * sizeof(gysk_event));
-		e->stage_fill += m; ev += m; n -= m;
-		if (e->stage_fill == e->cfg.stage_batch) { int rc = submit_stage(e); if (rc) return rc; }
+		if (ts->fill == ts->cap) { int rc = flush_stage(e, ts); if (rc) return rc; }
+		const uint32_t m = (uint32_t)std::min<uint64_t>(ts->cap - ts->fill, n);
+		memcpy(ts->buf[ts->cur] + ts->fill, ev, (size_t)m * sizeof(gysk_event));
+		ts->fill += m; ev += m; n -= m;
 	}
 	return 0;
 }
 
-inline gysk_event *stage_slot(gysk_engine *e, int *rc)
+} // namespace
+
+// every thread's partial chunk goes to the device (called by readers BEFORE they take the engine mutex)
+int gysk::drain_all(gysk_engine *e)
 {
-	if (e->stage_fill == e->cfg.stage_batch) { *rc = submit_stage(e); if (*rc) return nullptr; }
-	return e->h_stage[e->stage_cur] + e->stage_fill++;
+	std::lock_guard<std::mutex> lk(e->tstage_mtx);
+	for (auto &ts : e->tstages) {
+		std::lock_guard<std::mutex> l2(ts->m);
+		int rc = flush_stage(e, ts.get());
+		if (rc) return rc;
+	}
+	return 0;
 }
+
+namespace {
 
 // ---- pure host helpers: the reference's percentile rule and the estimators -------------------------------
 
@@ -287,6 +360,9 @@ void gysk::summarize_raw(const gysk_engine *e, const SvcRaw &r, uint64_t id, gys
 	o.nconns_5s = (uint32_t)r.conn_last; o.kbytes_5s = (uint32_t)(r.conn_last >> 32);
 	o.nconns_all = r.conn_all_cnt; o.kbytes_all = r.conn_all_kb;
 	o.distinct_clients = hll_estimate_from_hist(r.hll_hist, e->cfg.hll_p);
+	o.nconns_active = (uint32_t)r.aux.act_last; o.active_kbytes = (uint32_t)(r.aux.act_last >> 32);
+	memcpy(&o.max_rtt_msec, &r.aux.rtt_last, 4);
+	o.cli_errors = (uint32_t)r.aux.err_last; o.ser_errors = (uint32_t)(r.aux.err_last >> 32);
 
 	double means[TD_CAP]; uint64_t w[TD_CAP];
 	const uint32_t nc = std::min<uint32_t>(r.td.n, TD_CAP);
@@ -339,6 +415,11 @@ void gysk_destroy(gysk_engine *e)
 	for (int k = 0; k < NBUF; ++k) {
 		if (e->ev_copied[k]) cudaEventDestroy(e->ev_copied[k]);
 		if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
+		if (e->ev_raw_copied[k]) cudaEventDestroy(e->ev_raw_copied[k]);
+		if (e->ev_raw_done[k]) cudaEventDestroy(e->ev_raw_done[k]);
+	}
+	for (auto &ts : e->tstages) {
+		for (int i = 0; i < 2; ++i) { if (ts->buf[i]) cudaFreeHost(ts->buf[i]); if (ts->copied[i]) cudaEventDestroy(ts->copied[i]); }
 	}
 	for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
 	if (e->ev_evict) cudaEventDestroy(e->ev_evict);
@@ -379,7 +460,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 
 	gysk_engine *e = new (std::nothrow) gysk_engine;
 	if (!e) return fail(nullptr, GYSK_ERR_NOMEM, "new gysk_engine");
-	e->cfg = cfg; e->dev = cfg.device;
+	e->cfg = cfg; e->dev = cfg.device; e->uid = g_engine_uid.fetch_add(1);
 	memset(e->ring_epoch, 0xFF, sizeof(e->ring_epoch));
 
 	int rc = 0;
@@ -432,7 +513,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 		}
 	}
 
-	A(dalloc(e, &st.slot_batch, ns));
+	A(dalloc(e, &st.slot_batch, ns)); A(dalloc(e, &st.slot_aux, ns));
 	SortTemp &tmp = e->tmp;
 	const size_t nsort = std::max<size_t>(std::max<size_t>(ns, nt) + 1, cfg.max_batch);	// RESP keys of a batch; the top-N sorts rank services / tasks
 	tmp.max_tiles = (uint32_t)((nsort + SORT_TILE - 1) / SORT_TILE);
@@ -452,9 +533,12 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	st.svc_tbl.insert_fail = st.counters + CTR_INSERT_FAIL; st.task_tbl.insert_fail = nullptr;
 
 	for (int k = 0; k < NBUF; ++k) {
-		A(halloc(e, &e->h_stage[k], (size_t)cfg.stage_batch));
 		A(dalloc(e, &e->d_events[k], (size_t)cfg.stage_batch, false));
+		e->raw_bytes = (size_t)cfg.stage_batch * 32;				// a raw piece never expands into more than one event buffer
+		A(dalloc(e, &e->d_raw[k], e->raw_bytes, false));
 		if ((ce = cudaEventCreateWithFlags(&e->ev_copied[k], cudaEventDisableTiming)) != cudaSuccess ||
+				(ce = cudaEventCreateWithFlags(&e->ev_raw_copied[k], cudaEventDisableTiming)) != cudaSuccess ||
+				(ce = cudaEventCreateWithFlags(&e->ev_raw_done[k], cudaEventDisableTiming)) != cudaSuccess ||
 				(ce = cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming)) != cudaSuccess) {
 			fail(e, GYSK_ERR_CUDA, "cudaEventCreate", ce); return bail(GYSK_ERR_CUDA);
 		}
@@ -481,7 +565,7 @@ void *gysk_stream(gysk_engine *e) { return e ? (void *)e->stream : nullptr; }
 int gysk_profile_enable(gysk_engine *e, int on)
 {
 	CHECK_ENGINE(e);
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = sync_locked(e);
 	if (rc) return rc;
@@ -493,7 +577,7 @@ int gysk_profile_enable(gysk_engine *e, int on)
 int gysk_profile_read(gysk_engine *e, double *ms_ingest, double *ms_tdigest, uint64_t *nbatches)
 {
 	CHECK_ENGINE(e);
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = sync_locked(e);
 	if (rc) return rc;
@@ -515,7 +599,7 @@ int gysk_get_stats(gysk_engine *e, gysk_stats *out)
 {
 	CHECK_ENGINE(e);
 	if (!out) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = sync_locked(e);
 	if (rc) return rc;
@@ -541,7 +625,7 @@ int gysk_register_ids(gysk_engine *e, const uint64_t *ids, uint32_t n, int is_ta
 {
 	CHECK_ENGINE(e);
 	if (!ids && n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	for (uint32_t off = 0; off < n; off += QCHUNK) {
 		const uint32_t m = std::min(QCHUNK, n - off);
@@ -559,7 +643,7 @@ int gysk_ingest_device(gysk_engine *e, const gysk_event *d_events, uint64_t n)
 {
 	CHECK_ENGINE(e);
 	if (!d_events && n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);					// keep arrival order
 	if (rc) return rc;
@@ -574,94 +658,243 @@ int gysk_ingest_pinned(gysk_engine *e, const gysk_event *pinned, uint64_t n)
 {
 	CHECK_ENGINE(e);
 	if (!pinned && n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
-	int rc = submit_stage(e);
-	if (rc) return rc;
-	// software pipeline over stage_batch chunks: the H2D copy of chunk c+1 is enqueued as soon as the ingest kernel of chunk c is
-	// launched, so the PCIe link never waits for the host readback or the sort + t-digest chain of chunk c
-	const uint64_t sb = e->cfg.stage_batch;
-	auto issue_copy = [&](uint64_t off, int k) -> int {
-		const uint64_t m = std::min<uint64_t>(sb, n - off);
-		CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_done[k], 0));		// ingest kernel that last read buffer k has run
-		CU(e, cudaMemcpyAsync(e->d_events[k], pinned + off, (size_t)m * sizeof(gysk_event), cudaMemcpyHostToDevice, e->copy_stream));
-		CU(e, cudaEventRecord(e->ev_copied[k], e->copy_stream));
-		return 0;
-	};
-	if (n && (rc = issue_copy(0, e->stage_cur))) return rc;
-	for (uint64_t off = 0; off < n; off += sb) {
-		const uint64_t m = std::min<uint64_t>(sb, n - off);
-		const int k = e->stage_cur, knext = (k + 1) % NBUF;
-		CU(e, cudaStreamWaitEvent(e->stream, e->ev_copied[k], 0));
-		rc = process_device_batch(e, e->d_events[k], m, [&]() -> int {
-			CU(e, cudaEventRecord(e->ev_done[k], e->stream));
-			return off + sb < n ? issue_copy(off + sb, knext) : 0;
-		});
-		if (rc) return rc;
-		e->stage_cur = knext;
-	}
-	return GYSK_OK;
+	// zero copy on the host: the H2D copies read the caller's page-locked buffer directly, chunk by chunk into the two device
+	// event buffers; the copy of chunk c+1 is enqueued as soon as the ingest kernel of chunk c is, so the link never idles
+	return append_chunk(e, pinned, n);
 }
+
+} // extern "C"
+
+// ---- raw records: decoded into the canonical 32-byte event — by the same inline functions on the host (a few records: the
+// calling thread's stage) and on the device (bulk: the raw bytes cross the link, a kernel expands them) ----------
+namespace gysk {
+
+__host__ __device__ inline uint32_t bswap16(uint32_t v) { return ((v & 0xFFu) << 8) | ((v >> 8) & 0xFFu); }
+
+// listener id of a raw eBPF record: the reference keys listeners by NS_IP_PORT {ip, port, netns} (gy_socket_stat.cc:1529) and
+// derives glob_id_ with CityHash (:1824); the id is opaque to the engine, so any deterministic 64-bit fold of the same triple
+// serves: two lookup2 words. IPv6 addresses are folded to 32 bits first.
+__host__ __device__ inline uint64_t raw_svc_id(uint32_t ip, uint32_t netns, uint32_t port)
+{
+	uint64_t id = ((uint64_t)jhash_2words(ip, netns, GY_SEED) << 32) | jhash_2words(port, netns, GY_SEED ^ ip);
+	return id ? id : 1;
+}
+__host__ __device__ inline uint32_t fold_ip6(const uint32_t w[4]) { return jhash_2words(w[2], w[3], jhash_2words(w[0], w[1], GY_SEED)); }
+
+__host__ __device__ inline void ev_pad(gysk_event &o) { o.svc_id = 0; o.flow_key = 0; o.value = 0; o.host_idx = 0; o.tsec = 0; o.type = 0xFFFF; o.flags = 0; }
+
+// TCP_SOCK_HANDLER::handle_ipv4_resp_event / handle_ipv6_resp_event, common/gy_socket_stat.cc:1517-1552: tresp = lsndtime - lrcvtime
+// (msec), dropped when (uint32_t)tresp > 1 000 000; ports arrive in network byte order (ntohs :1526-1527); the client port keys
+// CONN_BITMAP (gy_socket_stat.h:403-410)
+__host__ __device__ inline void decode_resp(uint32_t sip, uint32_t cip, uint32_t netns, uint32_t sport_be, uint32_t dport_be, uint32_t lsnd, uint32_t lrcv,
+		uint32_t host_idx, gysk_event &o)
+{
+	const uint32_t tresp = lsnd - lrcv;
+	if (tresp > 1000000u) { ev_pad(o); return; }
+	const uint32_t sport = bswap16(sport_be), dport = bswap16(dport_be);
+	o.svc_id = raw_svc_id(sip, netns, sport);
+	o.flow_key = ((uint64_t)cip << 32) | dport;
+	o.value = tresp * 1000u; o.host_idx = host_idx; o.tsec = 0; o.type = GYSK_EV_RESP; o.flags = 0;
+}
+
+// TCP_SOCK_HANDLER::handle_ipv4_conn_event / handle_ipv6_conn_event, common/gy_socket_stat.cc:241-294: type 1..4; on close the
+// byte counters are added to the listener totals (handle_bpf_close_ser :850)
+__host__ __device__ inline void decode_conn(uint32_t saddr, uint32_t daddr, uint32_t netns, uint32_t sport_be, uint32_t dport_be, uint32_t type,
+		uint64_t bytes, uint64_t ts_ns, uint32_t host_idx, gysk_event &o)
+{
+	if (type < GYSK_EV_CONNECT || type > GYSK_EV_CLOSE_SER) { ev_pad(o); return; }
+	const bool ser_side = (type == GYSK_EV_ACCEPT || type == GYSK_EV_CLOSE_SER);
+	const uint32_t hs = bswap16(sport_be), hd = bswap16(dport_be);
+	const uint32_t sip = ser_side ? saddr : daddr, sport = ser_side ? hs : hd;
+	const uint32_t cip = ser_side ? daddr : saddr, cport = ser_side ? hd : hs;
+	o.svc_id = raw_svc_id(sip, netns, sport);
+	o.flow_key = ((uint64_t)cip << 32) | cport;
+	o.value = bytes > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bytes;
+	o.host_idx = host_idx; o.tsec = (uint32_t)(ts_ns / 1000000000ull); o.type = (uint16_t)type; o.flags = 0;
+}
+
+__host__ __device__ inline uint32_t raw_stride(uint32_t kind)
+{
+	switch (kind) {
+	case GYSK_RAW_EVENT32 : return 32;
+	case GYSK_RAW_TCP_IPV4_EVENT : return sizeof(wire::tcp_ipv4_event_t);
+	case GYSK_RAW_TCP_IPV4_RESP : return sizeof(wire::tcp_ipv4_resp_event_t);
+	case GYSK_RAW_TCP_IPV6_EVENT : return sizeof(wire::tcp_ipv6_event_t);
+	case GYSK_RAW_TCP_IPV6_RESP : return sizeof(wire::tcp_ipv6_resp_event_t);
+	case GYSK_RAW_RESP16 : return sizeof(gysk_resp16);
+	case GYSK_RAW_TCP24 : return sizeof(gysk_tcp24);
+	case GYSK_RAW_TASK24 : return sizeof(gysk_task24);
+	default : return 0;
+	}
+}
+
+__host__ __device__ inline void decode_raw(uint32_t kind, const void *rec, uint32_t host_idx, gysk_event &o)
+{
+	switch (kind) {
+	case GYSK_RAW_TCP_IPV4_RESP : {
+		const wire::tcp_ipv4_resp_event_t &p = *static_cast<const wire::tcp_ipv4_resp_event_t *>(rec);
+		decode_resp(p.saddr, p.daddr, p.netns, p.sport, p.dport, p.lsndtime, p.lrcvtime, host_idx, o);
+		break;
+	}
+	case GYSK_RAW_TCP_IPV6_RESP : {
+		const wire::tcp_ipv6_resp_event_t &p = *static_cast<const wire::tcp_ipv6_resp_event_t *>(rec);
+		decode_resp(fold_ip6(p.saddr), fold_ip6(p.daddr), p.netns, p.sport, p.dport, p.lsndtime, p.lrcvtime, host_idx, o);
+		break;
+	}
+	case GYSK_RAW_TCP_IPV4_EVENT : {
+		const wire::tcp_ipv4_event_t &p = *static_cast<const wire::tcp_ipv4_event_t *>(rec);
+		decode_conn(p.saddr, p.daddr, p.netns, p.sport, p.dport, p.type, p.bytes_received + p.bytes_acked, p.ts_ns, host_idx, o);
+		break;
+	}
+	case GYSK_RAW_TCP_IPV6_EVENT : {
+		const wire::tcp_ipv6_event_t &p = *static_cast<const wire::tcp_ipv6_event_t *>(rec);
+		decode_conn(fold_ip6(p.saddr), fold_ip6(p.daddr), p.netns, p.sport, p.dport, p.type, p.bytes_received + p.bytes_acked, p.ts_ns, host_idx, o);
+		break;
+	}
+	case GYSK_RAW_RESP16 : {
+		const gysk_resp16 &p = *static_cast<const gysk_resp16 *>(rec);
+		o.svc_id = p.svc_id; o.flow_key = p.cli_port; o.value = p.usec; o.host_idx = p.host_idx; o.tsec = 0; o.type = GYSK_EV_RESP; o.flags = p.flags;
+		break;
+	}
+	case GYSK_RAW_TCP24 : {
+		const gysk_tcp24 &p = *static_cast<const gysk_tcp24 *>(rec);
+		o.svc_id = p.svc_id; o.flow_key = p.flow_key; o.value = p.bytes; o.host_idx = p.host_idx; o.tsec = 0; o.type = p.type; o.flags = 0;
+		break;
+	}
+	case GYSK_RAW_TASK24 : {
+		const gysk_task24 &p = *static_cast<const gysk_task24 *>(rec);
+		o.svc_id = p.aggr_task_id; o.flow_key = (uint64_t)p.cpu_delay_msec | ((uint64_t)p.blkio_delay_msec << 32); o.value = p.cpu_pct;
+		o.host_idx = p.host_idx; o.tsec = 0; o.type = GYSK_EV_TASK; o.flags = 0;
+		break;
+	}
+	default : ev_pad(o); break;
+	}
+}
+
+// one thread per raw record: 16-byte stores of the expanded event
+__global__ void __launch_bounds__(256) decode_raw_kernel(uint32_t kind, const uint8_t *__restrict__ raw, uint32_t n, uint32_t host_idx, gysk_event *__restrict__ out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	gysk_event o;
+	decode_raw(kind, raw + (size_t)i * raw_stride(kind), host_idx, o);
+	uint4 *d = reinterpret_cast<uint4 *>(out + i);
+	d[0] = make_uint4((uint32_t)o.svc_id, (uint32_t)(o.svc_id >> 32), (uint32_t)o.flow_key, (uint32_t)(o.flow_key >> 32));
+	d[1] = make_uint4(o.value, o.host_idx, o.tsec, (uint32_t)o.type | ((uint32_t)o.flags << 16));
+}
+
+} // namespace gysk
+
+namespace {
+
+// bulk path of a fixed-stride raw kind: raw bytes H2D (straight from the caller's buffer when that is page-locked, else through
+// the thread's stage), expansion on the device into the current device event buffer, batch kernels when it is full
+int ingest_raw_bulk(gysk_engine *e, ThreadStage *ts, uint32_t kind, uint32_t host_idx, const uint8_t *src, uint64_t n)
+{
+	const uint32_t stride = raw_stride(kind);
+	cudaPointerAttributes pa {};
+	const bool pinned = cudaPointerGetAttributes(&pa, src) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	int rc = flush_stage(e, ts);				// keep this thread's arrival order
+	if (rc) return rc;
+	const uint64_t per_stage = (uint64_t)ts->cap * sizeof(gysk_event) / stride;		// records per thread chunk (as bytes)
+	while (n) {
+		std::unique_lock<std::mutex> lk(e->mtx);
+		CU(e, cudaSetDevice(e->dev));
+		const int k = e->stage_cur;
+		const uint64_t room = e->cfg.stage_batch - e->stage_fill;
+		uint64_t m = std::min<uint64_t>(room, n);
+		if (m * stride > e->raw_bytes) m = e->raw_bytes / stride;
+		if (!pinned) m = std::min<uint64_t>(m, per_stage);
+		const int r = e->raw_cur;
+		const uint8_t *hsrc = src;
+		if (!pinned) {
+			lk.unlock();
+			CU(e, cudaEventSynchronize(ts->copied[ts->cur]));
+			memcpy(ts->buf[ts->cur], src, (size_t)m * stride);
+			hsrc = reinterpret_cast<const uint8_t *>(ts->buf[ts->cur]);
+			lk.lock();
+			if (e->stage_cur != k || e->raw_cur != r || e->cfg.stage_batch - e->stage_fill < m) continue;	// another thread moved on: size the piece again
+		}
+		if (e->stage_fill == 0) CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_done[k], 0));
+		CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_raw_done[r], 0));		// the decode kernel that last read raw buffer r has run
+		CU(e, cudaMemcpyAsync(e->d_raw[r], hsrc, (size_t)m * stride, cudaMemcpyHostToDevice, e->copy_stream));
+		if (!pinned) { CU(e, cudaEventRecord(ts->copied[ts->cur], e->copy_stream)); ts->cur ^= 1; }
+		CU(e, cudaEventRecord(e->ev_raw_copied[r], e->copy_stream));
+		// the expansion runs on the COPY stream too: buffer k's events are complete in copy-stream order, as append_chunk's are
+		decode_raw_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, e->copy_stream>>>(kind, e->d_raw[r], (uint32_t)m, host_idx, e->d_events[k] + e->stage_fill);
+		CU(e, cudaEventRecord(e->ev_raw_done[r], e->copy_stream));
+		e->kernel_launches++;
+		e->raw_cur = (r + 1) % NBUF;
+		e->stage_fill += (uint32_t)m; src += m * stride; n -= m;
+		if (e->stage_fill == e->cfg.stage_batch && (rc = submit_stage(e))) return rc;
+	}
+	return post_launch(e, "raw decode");
+}
+
+// API_TRAN, common/gy_proto_common.h:140-204 (probe-confirmed offsets: response_usec_ 48, glob_id_ 120, errorcode_ 152, cliport_ 166,
+// request_len_ 170, lenext_ 172, padlen_ 174, sizeof 176; get_elem_size() = sizeof + request_len_ + lenext_ + padlen_).
+// SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678-2694): nrequests_++, resp_cache_.add_cache(response_usec_ / 1000),
+// error counters. is_error / is_serv_err are the parser's verdict; the record carries errorcode_: != 0 is an error, >= 500 a
+// server error (HTTP status convention of the reference's http parser).
+struct ApiTranView
+{
+	static constexpr size_t SIZE = 176;
+	static uint64_t u64(const uint8_t *p, size_t off) { uint64_t v; memcpy(&v, p + off, 8); return v; }
+	static uint32_t u32(const uint8_t *p, size_t off) { uint32_t v; memcpy(&v, p + off, 4); return v; }
+	static uint16_t u16(const uint8_t *p, size_t off) { uint16_t v; memcpy(&v, p + off, 2); return v; }
+};
+
+} // namespace
+
+extern "C" {
 
 int gysk_ingest_raw(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, uint32_t kind, const void *events, uint32_t n)
 {
 	CHECK_ENGINE(e);
 	(void)host_id;
 	if (!events && n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
-	CU(e, cudaSetDevice(e->dev));
+	ThreadStage *ts = get_stage(e);
+	if (!ts) return fail(e, GYSK_ERR_NOMEM, "thread stage");
+	std::lock_guard<std::mutex> tl(ts->m);
 	int rc = 0;
 
-	switch (kind) {
+	if (kind == GYSK_RAW_EVENT32) return stage_events(e, ts, static_cast<const gysk_event *>(events), n);
 
-	case GYSK_RAW_EVENT32 :
-		return stage_events(e, static_cast<const gysk_event *>(events), n);
-
-	case GYSK_RAW_TCP_IPV4_RESP : {
-		// TCP_SOCK_HANDLER::handle_ipv4_resp_event, common/gy_socket_stat.cc:1517-1552: tresp = lsndtime - lrcvtime (msec),
-		// dropped when (uint32_t)tresp > 1 000 000. The listener key is (netns, server ip, server port); the client port keys CONN_BITMAP.
-		const wire::tcp_ipv4_resp_event_t *p = static_cast<const wire::tcp_ipv4_resp_event_t *>(events);
+	if (kind == GYSK_RAW_API_TRAN) {
+		const uint8_t *p = static_cast<const uint8_t *>(events);
 		for (uint32_t i = 0; i < n; ++i) {
-			const uint32_t tresp = p[i].lsndtime - p[i].lrcvtime;
-			if (tresp > 1000000u) continue;
-			gysk_event *o = stage_slot(e, &rc);
+			gysk_event *o = stage_slot(e, ts, &rc);
 			if (!o) return rc;
-			// inet_sport / skc_dport are in network byte order: ntohs() first, as the reference does (gy_socket_stat.cc:1526-1527)
-			const uint32_t sport = __builtin_bswap16(p[i].sport), dport = __builtin_bswap16(p[i].dport);
-			const uint32_t words[3] = { p[i].saddr, p[i].netns, sport };
-			o->svc_id = ((uint64_t)jhash_2words(words[0], words[1], GY_SEED) << 32) | jhash_2words(words[2], words[1], GY_SEED ^ words[0]);
-			if (!o->svc_id) o->svc_id = 1;
-			o->flow_key = ((uint64_t)p[i].daddr << 32) | dport;		// CONN_BITMAP index = client port & 0x1F (gy_socket_stat.h:403-410)
-			o->value = tresp * 1000u; o->host_idx = host_idx; o->tsec = 0; o->type = GYSK_EV_RESP; o->flags = 0;
+			const uint64_t usec = ApiTranView::u64(p, 48);
+			const int32_t err = (int32_t)ApiTranView::u32(p, 152);
+			o->svc_id = ApiTranView::u64(p, 120);
+			o->flow_key = ApiTranView::u16(p, 166);				// cliport_ (host order): CONN_BITMAP index
+			o->value = usec > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)usec;	// beyond 1 000 000 msec: dropped by the validity rule on the device
+			o->host_idx = host_idx; o->tsec = (uint32_t)(ApiTranView::u64(p, 16) / 1000000ull);	// tupd_usec_
+			o->type = GYSK_EV_RESP;
+			o->flags = err == 0 ? 0 : (err >= 500 ? GYSK_EVF_SER_ERROR : GYSK_EVF_CLI_ERROR);
+			p += ApiTranView::SIZE + ApiTranView::u16(p, 170) + ApiTranView::u16(p, 172) + p[174];
 		}
 		return GYSK_OK;
 	}
 
-	case GYSK_RAW_TCP_IPV4_EVENT : {
-		// TCP_SOCK_HANDLER::handle_ipv4_conn_event, common/gy_socket_stat.cc:241-294: type 1..4; on close the byte counters
-		// are added to the listener totals (handle_bpf_close_ser :850)
-		const wire::tcp_ipv4_event_t *p = static_cast<const wire::tcp_ipv4_event_t *>(events);
-		for (uint32_t i = 0; i < n; ++i) {
-			if (p[i].type < GYSK_EV_CONNECT || p[i].type > GYSK_EV_CLOSE_SER) continue;
-			gysk_event *o = stage_slot(e, &rc);
-			if (!o) return rc;
-			const bool ser_side = (p[i].type == GYSK_EV_ACCEPT || p[i].type == GYSK_EV_CLOSE_SER);
-			const uint32_t hs = __builtin_bswap16(p[i].sport), hd = __builtin_bswap16(p[i].dport);	// ntohs, gy_socket_stat.cc:258-262
-			const uint32_t sip = ser_side ? p[i].saddr : p[i].daddr, sport = ser_side ? hs : hd;
-			const uint32_t cip = ser_side ? p[i].daddr : p[i].saddr, cport = ser_side ? hd : hs;
-			o->svc_id = ((uint64_t)jhash_2words(sip, p[i].netns, GY_SEED) << 32) | jhash_2words(sport, p[i].netns, GY_SEED ^ sip);
-			if (!o->svc_id) o->svc_id = 1;
-			o->flow_key = ((uint64_t)cip << 32) | cport;
-			const uint64_t bytes = p[i].bytes_received + p[i].bytes_acked;
-			o->value = bytes > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bytes;
-			o->host_idx = host_idx; o->tsec = (uint32_t)(p[i].ts_ns / 1000000000ull); o->type = p[i].type; o->flags = 0;
-		}
-		return GYSK_OK;
+	const uint32_t stride = raw_stride(kind);
+	if (!stride) return fail(e, GYSK_ERR_INVAL, "gysk_ingest_raw: unknown kind");
+	if (n >= RAW_BULK_MIN) return ingest_raw_bulk(e, ts, kind, host_idx, static_cast<const uint8_t *>(events), n);
+	// a handful of records (one perf-buffer wake-up): expanded by the calling thread
+	const uint8_t *p = static_cast<const uint8_t *>(events);
+	for (uint32_t i = 0; i < n; ++i, p += stride) {
+		gysk_event tmp;
+		decode_raw(kind, p, host_idx, tmp);
+		if (tmp.type == 0xFFFF) continue;
+		gysk_event *o = stage_slot(e, ts, &rc);
+		if (!o) return rc;
+		*o = tmp;
 	}
-
-	default :
-		return fail(e, GYSK_ERR_INVAL, "gysk_ingest_raw: unknown kind");
-	}
+	return GYSK_OK;
 }
 
 // One wire message body, exactly the arguments handle_l2_misc hands to partha_<kind>() (gy_mconnhdlr.cc:4745-4800).
@@ -670,8 +903,9 @@ int gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, ui
 	CHECK_ENGINE(e);
 	(void)host_id;
 	if (!recs || !endptr || (const uint8_t *)endptr < (const uint8_t *)recs) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
-	CU(e, cudaSetDevice(e->dev));
+	ThreadStage *ts = get_stage(e);
+	if (!ts) return fail(e, GYSK_ERR_NOMEM, "thread stage");
+	std::lock_guard<std::mutex> tl(ts->m);
 	const uint8_t *pend = static_cast<const uint8_t *>(endptr);
 	int rc = 0;
 
@@ -692,7 +926,7 @@ int gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, ui
 			if (pone->is_tcp_accept_event_) type = closed ? GYSK_EV_CLOSE_SER : GYSK_EV_ACCEPT;
 			else if (pone->is_tcp_connect_event_) type = closed ? GYSK_EV_CLOSE_CLI : GYSK_EV_CONNECT;
 			else continue;
-			gysk_event *o = stage_slot(e, &rc);
+			gysk_event *o = stage_slot(e, ts, &rc);
 			if (!o) return rc;
 			const uint64_t bytes = closed ? pone->bytes_sent_ + pone->bytes_rcvd_ : 0;
 			o->svc_id = pone->ser_glob_id_; o->flow_key = pone->cli_task_aggr_id_;
@@ -712,14 +946,46 @@ int gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, ui
 			return fail(e, GYSK_ERR_INVAL, "AGGR_TASK_STATE_NOTIFY::validate failed");
 		}
 		// partha_aggr_task_state (gy_mconnhdlr.cc:9959) -> MAGGR_TASK::set_local_task_state (gy_msocket.h:1009)
+		{
+			std::lock_guard<std::mutex> lk(e->host_mtx);
+			HostTaskTopn tt;						// the seven per-host rankings of :10012-10079
+			const T *q = pone;
+			for (uint32_t i = 0; i < nevents && (const uint8_t *)q < pend; ++i, q = (const T *)((const uint8_t *)q + q->get_elem_size())) tt.offer(*q);
+			e->host_task_topn[host_idx] = std::move(tt);
+		}
 		for (uint32_t i = 0; i < nevents && (const uint8_t *)pone < pend; ++i, pone = (T *)((uint8_t *)pone + pone->get_elem_size())) {
 			if (!pone->aggr_task_id_) continue;
-			gysk_event *o = stage_slot(e, &rc);
+			gysk_event *o = stage_slot(e, ts, &rc);
 			if (!o) return rc;
 			o->svc_id = pone->aggr_task_id_;
 			o->flow_key = (uint64_t)pone->cpu_delay_msec_ | ((uint64_t)pone->blkio_delay_msec_ << 32);
 			o->value = (uint32_t)(int)pone->total_cpu_pct_;				// (int)ptask->total_cpu_pct_ , gy_msocket.h:1014
 			o->host_idx = host_idx; o->tsec = 0; o->type = GYSK_EV_TASK; o->flags = 0;
+		}
+		e->wire_ok++;
+		return GYSK_OK;
+	}
+
+	case GYSK_NOTIFY_ACTIVE_CONN_STATS : {
+		// ACTIVE_CONN_STATS::validate (common/gy_comm_proto.h:2806): fixed stride, nevents <= MAX_NUM_CONNS, all records inside the message
+		using T = wire::ACTIVE_CONN_STATS;
+		const T *pone = static_cast<const T *>(recs);
+		if (nevents > T::MAX_NUM_CONNS || (const uint8_t *)(pone + nevents) > pend) {
+			e->wire_bad++;
+			return fail(e, GYSK_ERR_INVAL, "ACTIVE_CONN_STATS::validate failed");
+		}
+		// handle_partha_active_conns (gy_mconnhdlr.cc:7705) -> insert_active_conns (:7788): one record per {listener, client process}
+		for (uint32_t i = 0; i < nevents; ++i, ++pone) {
+			if (!pone->listener_glob_id_) continue;
+			gysk_event *o = stage_slot(e, ts, &rc);
+			if (!o) return rc;
+			const uint64_t kb = (pone->bytes_sent_ + pone->bytes_received_) >> 10;
+			o->svc_id = pone->listener_glob_id_; o->flow_key = pone->cli_aggr_task_id_;
+			o->value = kb > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)kb;
+			o->host_idx = host_idx;
+			const float rtt = pone->max_rtt_msec_ > 0 ? pone->max_rtt_msec_ : 0.0f;
+			memcpy(&o->tsec, &rtt, 4);
+			o->type = GYSK_EV_ACTIVE; o->flags = pone->active_conns_;
 		}
 		e->wire_ok++;
 		return GYSK_OK;
@@ -734,10 +1000,11 @@ int gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, ui
 		}
 		// Pre-aggregated 5-s listener state. With the per-sample reduction lifted onto the GPU the per-listener fields are
 		// derived by the engine itself; what these records still feed is the per-host roll-up of partha_listener_state
-		// (gy_mconnhdlr.cc:11175-11251): summstats.update(*pone) per record == LISTEN_SUMM_STATS::update, gy_msocket.h:854-866.
-		// <= 512 records per host per 5 s: host-side integer adds, nothing for a GPU to do.
+		// (gy_mconnhdlr.cc:11175-11251): summstats.update(*pone) per record == LISTEN_SUMM_STATS::update, gy_msocket.h:854-866,
+		// and the per-host top-N queues (:11262-11304). <= 512 records per host per 5 s: host-side integer work.
 		gysk_host_summary hs;
 		memset(&hs, 0, sizeof(hs));
+		HostTopn topn;
 		for (uint32_t i = 0; i < nevents && (const uint8_t *)pone < pend; ++i, pone = (T *)((uint8_t *)pone + pone->get_elem_size())) {
 			// gy_mconnhdlr.cc:11183-11251: LISTEN_FLAG_DELETE records only delete the listener, records with
 			// curr_state_ > STATE_DOWN count as errors; neither reaches summstats.update()
@@ -750,8 +1017,13 @@ int gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, ui
 			hs.tot_ser_errors += (int32_t)pone->ser_errors_;
 			hs.nlisteners++;
 			hs.nactive += !!pone->nqrys_5s_;
+			topn.offer(*pone);
 		}
-		e->host_summ[host_idx] = hs;
+		{
+			std::lock_guard<std::mutex> lk(e->host_mtx);
+			e->host_summ[host_idx] = hs;
+			e->host_topn[host_idx] = topn;
+		}
 		e->wire_ok++;
 		return GYSK_OK;
 	}
@@ -771,7 +1043,6 @@ int gysk_ingest_msg(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx
 	if (phdr->magic_ != wire::PM_HDR_MAGIC || phdr->data_type_ != wire::COMM_EVENT_NOTIFY || phdr->total_sz_ > msglen ||
 			phdr->total_sz_ >= wire::MAX_COMM_DATA_SZ || phdr->padding_sz_ > phdr->total_sz_ ||
 			phdr->get_act_len() < sizeof(wire::COMM_HEADER) + sizeof(wire::EVENT_NOTIFY)) {
-		std::lock_guard<std::mutex> lk(e->mtx);
 		e->wire_bad++;
 		return fail(e, GYSK_ERR_INVAL, "COMM_HEADER::validate failed");
 	}
@@ -784,7 +1055,7 @@ int gysk_ingest_msg(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx
 int gysk_sync(gysk_engine *e)
 {
 	CHECK_ENGINE(e);
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	return sync_locked(e);
 }
@@ -792,7 +1063,7 @@ int gysk_sync(gysk_engine *e)
 int gysk_flush(gysk_engine *e, uint32_t tsec)
 {
 	CHECK_ENGINE(e);
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
@@ -837,7 +1108,7 @@ int gysk_evicted_ids(gysk_engine *e, uint64_t *out, uint32_t cap, uint32_t *n)
 {
 	CHECK_ENGINE(e);
 	if (!n || (!out && cap)) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = collect_evicted(e, true);
 	if (rc) return rc;
@@ -852,7 +1123,7 @@ int gysk_query_svcs(gysk_engine *e, const uint64_t *ids, uint32_t n, gysk_svc_su
 {
 	CHECK_ENGINE(e);
 	if ((!ids || !out) && n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
@@ -875,7 +1146,7 @@ int gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial ou
 	if (which >= GYSK_HIST_TASK_CPU_PCT && which <= GYSK_HIST_TASK_BLKIO_DELAY) return gysk_export_task_hist(e, id, which, out, total, maxv);
 	if (which > GYSK_HIST_RESP_5DAY) return GYSK_ERR_INVAL;
 	if (which < 0) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
@@ -895,7 +1166,7 @@ int gysk_export_task_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_seri
 {
 	CHECK_ENGINE(e);
 	if (!out || !total || !maxv || which < GYSK_HIST_TASK_CPU_PCT || which > GYSK_HIST_TASK_BLKIO_DELAY) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
@@ -916,7 +1187,7 @@ int gysk_export_conn_bitmap(gysk_engine *e, uint64_t id, int last_window, uint32
 {
 	CHECK_ENGINE(e);
 	if (!masks || !nconn_arr) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
@@ -932,7 +1203,7 @@ int gysk_export_hll(gysk_engine *e, uint64_t id, uint8_t *regs)
 {
 	CHECK_ENGINE(e);
 	if (!regs) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
@@ -950,7 +1221,7 @@ int gysk_export_tdigest(gysk_engine *e, uint64_t id, double *means, uint64_t *we
 {
 	CHECK_ENGINE(e);
 	if (!means || !weights || !n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
@@ -991,6 +1262,8 @@ int gysk_encode_listener_state(const gysk_svc_summary *sums, uint32_t n, void *b
 		r.p95_5s_resp_ms_ = clampms(sums[i].p95_5s_resp_ms);
 		r.p95_5min_resp_ms_ = clampms(sums[i].p95_5min_resp_ms);
 		r.nconns_ = sums[i].nconns_5s;
+		r.nconns_active_ = sums[i].nconns_active;
+		r.ser_errors_ = sums[i].ser_errors; r.cli_errors_ = sums[i].cli_errors;
 		r.curr_kbytes_inbound_ = sums[i].kbytes_5s;
 		r.curr_state_ = sums[i].nqrys_5s ? 2 : 0;
 		memcpy(p + (size_t)k * sizeof(r), &r, sizeof(r));
@@ -1079,7 +1352,7 @@ int gysk_query_flows(gysk_engine *e, const uint64_t *keys, uint32_t n, int last_
 {
 	CHECK_ENGINE(e);
 	if ((!keys || !out) && n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = submit_stage(e);
 	if (rc) return rc;
@@ -1099,7 +1372,7 @@ int gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gys
 {
 	CHECK_ENGINE(e);
 	if (!out || !nout || n == 0 || n > 64 || metric < GYSK_TOPN_QPS || metric > GYSK_TOPN_NET) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = sync_locked(e);
 	if (rc) return rc;
@@ -1127,7 +1400,7 @@ int gysk_topn_tasks(gysk_engine *e, int metric, uint32_t n, gysk_topn_entry *out
 {
 	CHECK_ENGINE(e);
 	if (!out || !nout || n == 0 || n > 64 || metric < GYSK_TOPN_TASK_CPU || metric > GYSK_TOPN_TASK_BLKIO_DELAY) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = sync_locked(e);
 	if (rc) return rc;
@@ -1155,7 +1428,7 @@ int gysk_query_host_summary(gysk_engine *e, uint32_t host_idx, gysk_host_summary
 {
 	CHECK_ENGINE(e);
 	if (!out) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	std::lock_guard<std::mutex> lk(e->host_mtx);
 	auto it = e->host_summ.find(host_idx);
 	if (it == e->host_summ.end()) return GYSK_ERR_NOENT;
 	*out = it->second;
@@ -1166,7 +1439,7 @@ int gysk_query_cluster_state(gysk_engine *e, const uint32_t *host_idxs, uint32_t
 {
 	CHECK_ENGINE(e);
 	if (!out || (!host_idxs && n)) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	std::lock_guard<std::mutex> lk(e->host_mtx);
 	memset(out, 0, sizeof(*out));
 	auto add = [&](const gysk_host_summary & hs) {
 		const uint32_t issues = (uint32_t)(hs.nstates[3] + hs.nstates[4] + hs.nstates[5]);	// STATE_BAD, STATE_SEVERE, STATE_DOWN
@@ -1186,11 +1459,32 @@ int gysk_query_cluster_state(gysk_engine *e, const uint32_t *host_idxs, uint32_t
 	return GYSK_OK;
 }
 
+// the per-host rankings the reference keeps in PARTHA_INFO (BOUNDED_PRIO_QUEUE, 10 entries per host, gy_mconnhdlr.h:961,975), as
+// of each host's last NOTIFY_LISTENER_STATE / NOTIFY_AGGR_TASK_STATE message; host_idx < 0 merges the hosts of this engine
+int gysk_topn_host(gysk_engine *e, int what, int32_t host_idx, uint32_t n, gysk_topn_entry *out, uint32_t *nout)
+{
+	CHECK_ENGINE(e);
+	if (!out || !nout || !n || n > 64 || what < 0 || what > GYSK_HOSTTOP_TASK_BLKIO_DELAY) return GYSK_ERR_INVAL;
+	std::lock_guard<std::mutex> lk(e->host_mtx);
+	std::vector<gysk_topn_entry> all;
+	auto take = [&](uint32_t h, const TopQueue &q) { for (const TopEntry &t : q.v) all.push_back(gysk_topn_entry {t.id, t.score, h, 0}); };
+	if (what <= GYSK_HOSTTOP_SVC_NET) {
+		for (const auto &kv : e->host_topn) if (host_idx < 0 || kv.first == (uint32_t)host_idx) take(kv.first, kv.second.q[what]);
+	}
+	else {
+		for (const auto &kv : e->host_task_topn) if (host_idx < 0 || kv.first == (uint32_t)host_idx) take(kv.first, kv.second.q[what - GYSK_HOSTTOP_TASK_ISSUE]);
+	}
+	std::sort(all.begin(), all.end(), [](const gysk_topn_entry &a, const gysk_topn_entry &b) { return a.score != b.score ? a.score > b.score : a.glob_id < b.glob_id; });
+	*nout = (uint32_t)std::min<size_t>(all.size(), n);
+	for (uint32_t i = 0; i < *nout; ++i) out[i] = all[i];
+	return GYSK_OK;
+}
+
 int gysk_export_cms(gysk_engine *e, int last_window, uint64_t *cells)
 {
 	CHECK_ENGINE(e);
 	if (!cells) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = sync_locked(e);
 	if (rc) return rc;

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	typename Shared::Warp &W = S.w[wid];
 	const uint32_t lt = (1u << lane) - 1u;
-	uint32_t c_in = 0, c_foreign = 0, n_resp = 0;			// per thread: < 2^32 events per launch
+	uint32_t c_in = 0, c_foreign = 0, n_resp = 0, n_active = 0;	// per thread: < 2^32 events per launch
 	uint32_t nk = 0, ntcp = 0, ntask = 0;				// queue lengths (warp-uniform)
 	unsigned long long t_tcp = 0, t_task = 0;			// queued in total (warp-uniform)
 
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 			const uint32_t value = rb[k].x, host_idx = rb[k].y;
 			const uint32_t type = rb[k].w & 0xFFFFu;
 			const bool is_resp = type == GYSK_EV_RESP, is_task = type == GYSK_EV_TASK;
-			const bool is_tcp = type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER;
+			const bool is_tcp = type >= GYSK_EV_CONNECT && type <= GYSK_EV_CLOSE_SER, is_active = type == GYSK_EV_ACTIVE;
 			bool mine = type != 0xFFFFu;
 
 			kind[k] = 0; ppos[k] = 0; praw[k] = make_uint4(0, 0, 0, 0);
@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 				c_in++;
 				// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678); validity rule of
 				// handle_ipv4_resp_event (gy_socket_stat.cc:1519-1524): drop beyond 1 000 000 msec
-				if (svc + 1ull > 1ull && (is_tcp || is_task || (is_resp && value < 1000001000u))) {	// id not 0 / ~0 (tombstone); msec <= 1 000 000
-					kind[k] = is_resp ? (uint32_t)GYSK_EV_RESP : (is_task ? (uint32_t)GYSK_EV_TASK : (uint32_t)GYSK_EV_ACCEPT);
+				if (svc + 1ull > 1ull && (is_tcp || is_task || is_active || (is_resp && value < 1000001000u))) {	// id not 0 / ~0 (tombstone); msec <= 1 000 000
+					kind[k] = is_resp ? (uint32_t)GYSK_EV_RESP : (is_task ? (uint32_t)GYSK_EV_TASK : (is_active ? (uint32_t)GYSK_EV_ACTIVE : (uint32_t)GYSK_EV_ACCEPT));
 					praw[k] = table_probe_first(is_task ? st.task_tbl : st.svc_tbl, svc, ppos[k]);
 				}
 			}
@@ -385,6 +385,23 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 					if (v > sbv[k].y) atomicMax(&st.slot_batch[slot].maxv, v);
 					const uint32_t bit = 1u << (ra[k].z & 0x1Fu);
 					if (!(mwv[k] & bit)) atomicOr(st.bm_cur + (size_t)slot * HIST_CELLS + bkt[k], bit);
+					const uint32_t ef = rb[k].w >> 16;			// API_TRAN error flags: rare
+					if (ef & 3u) red_add_u64(&st.slot_aux[slot].err_cur, (unsigned long long)(ef & 1u) | ((unsigned long long)((ef >> 1) & 1u) << 32));
+				}
+				else if (kind[k] == GYSK_EV_ACTIVE) {
+					// one pre-aggregated {listener, client process} record of the 15-s inet_diag scan (gy_socket_stat.cc:6156-6194): a few
+					// per flow and minute — handled on the spot. The flow sketch takes its connections and kbytes, the service its totals.
+					const unsigned long long fk = ((unsigned long long)ra[k].w << 32) | ra[k].z;
+					const unsigned long long inc = (unsigned long long)(rb[k].w >> 16) | ((unsigned long long)rb[k].x << 32);
+					uint32_t h1, h2, idx, rank;
+					flow_hashes(fk, h1, h2);
+					for (uint32_t row = 0; row < st.cms_depth; ++row)
+						red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index2(h1, h2, row, st.cms_wmask), inc);
+					hll_idx_rank2(h1, h2, st.hll_p, idx, rank);
+					hll_update(st.hll + ((size_t)slot << st.hll_p), idx, rank);
+					red_add_u64(&st.slot_aux[slot].act_cur, inc);
+					atomicMax(&st.slot_aux[slot].rtt_cur, rb[k].z);		// non-negative floats order like their bit patterns
+					n_active++;
 				}
 				else {
 					IngestRec r; r.slot = (uint32_t)slot; r.value = rb[k].x; r.flow_key = ((unsigned long long)ra[k].w << 32) | ra[k].z;
@@ -419,6 +436,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 	c_in = __reduce_add_sync(0xffffffffu, c_in);
 	c_foreign = __reduce_add_sync(0xffffffffu, c_foreign);
 	const unsigned long long t_resp = __reduce_add_sync(0xffffffffu, n_resp);
+	t_tcp += __reduce_add_sync(0xffffffffu, n_active);		// counted with the connection events
 	if (lane == 0) {
 		if (c_in) atomicAdd(st.counters + CTR_IN, (unsigned long long)c_in);
 		if (c_foreign) atomicAdd(st.counters + CTR_FOREIGN, (unsigned long long)c_foreign);
@@ -1004,7 +1022,9 @@ __global__ void flush_kernel(DevState st, uint32_t nslots, HistCell *__restrict_
 		if (cell == HIST_MAX_CELL) cc = st.conn_cur[slot];
 	}
 	// did the closing window hold any event of this service? (16 lanes = the 15 buckets + the max / conn cell)
-	const uint32_t bal = __ballot_sync(0xffffffffu, valid && (cell == HIST_MAX_CELL ? cc != 0 : c.count != 0));
+	bool auxact = false;				// ACTIVE_CONN_STATS records / API_TRAN errors count as activity of the window too
+	if (valid && cell == HIST_MAX_CELL) { const SlotAux a0 = st.slot_aux[slot]; auxact = (a0.act_cur | a0.err_cur) != 0; }
+	const uint32_t bal = __ballot_sync(0xffffffffu, valid && (cell == HIST_MAX_CELL ? (cc != 0 || auxact) : c.count != 0));
 	const bool active = ((bal >> (threadIdx.x & 16)) & 0xFFFFu) != 0;
 	if (!valid) return;
 
@@ -1027,6 +1047,11 @@ __global__ void flush_kernel(DevState st, uint32_t nslots, HistCell *__restrict_
 		st.conn_all_cnt[slot] += (uint32_t)cc;
 		st.conn_all_kb[slot] += cc >> 32;
 		st.conn_cur[slot] = 0;
+		{
+			SlotAux a = st.slot_aux[slot];
+			a.act_last = a.act_cur; a.act_cur = 0; a.err_last = a.err_cur; a.err_cur = 0; a.rtt_last = a.rtt_cur; a.rtt_cur = 0;
+			st.slot_aux[slot] = a;
+		}
 
 		const unsigned long long id = st.slot_id[slot];
 		if (id) {
@@ -1066,6 +1091,7 @@ __global__ void __launch_bounds__(256) evict_kernel(DevState st, uint32_t max_sv
 			}
 			st.slot_id[slot] = 0; st.slot_host[slot] = 0; st.slot_first_seen[slot] = 0; st.slot_last_active[slot] = 0;
 			st.conn_cur[slot] = 0; st.conn_last[slot] = 0; st.conn_all_cnt[slot] = 0; st.conn_all_kb[slot] = 0;
+			st.slot_aux[slot] = SlotAux {0, 0, 0, 0, 0, 0};
 			TdHead h; h.total = 0; h.minv = INFINITY; h.maxv = -INFINITY; h.n = 0; h.pad = 0;
 			st.td_head[slot] = h;
 			const int32_t f = atomicAdd(st.svc_tbl.free_n, 1);
@@ -1142,6 +1168,7 @@ __global__ void __launch_bounds__(128) gather_svcs_kernel(DevState st, const uns
 		o.conn_cur = st.conn_cur[slot]; o.conn_last = st.conn_last[slot];
 		o.conn_all_cnt = st.conn_all_cnt[slot]; o.conn_all_kb = st.conn_all_kb[slot];
 		o.td = st.td_head[slot];
+		o.aux = st.slot_aux[slot];
 	}
 	for (int i = lane; i < TD_CAP; i += 32) o.cent[i] = st.td_cent[(size_t)slot * TD_CAP + i];
 

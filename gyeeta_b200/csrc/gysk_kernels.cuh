@@ -22,7 +22,8 @@ struct DevState
 	unsigned long long	*evict_ids;
 	unsigned long long	*conn_all_cnt, *conn_all_kb;
 	uint32_t		*bm_cur, *bm_last;			// [max_svcs][16] CONN_BITMAP transposed: per bucket a mask over (client port & 31)
-	SlotBatch		*slot_batch;				// [max_svcs] batch extremes + "has bins to merge"
+	SlotBatch		*slot_batch;				// [max_svcs] exact extremes of the batch's RESP samples
+	SlotAux			*slot_aux;				// [max_svcs] active-conn roll-up, error counters
 	uint8_t			*hll;					// [max_svcs][1 << hll_p]
 	Centroid		*td_cent;				// [max_svcs][TD_CAP]
 	TdHead			*td_head;				// [max_svcs]
@@ -68,6 +69,7 @@ struct SvcRaw
 	uint32_t		bm_cur[HIST_CELLS], bm_last[HIST_CELLS];
 	uint32_t		hll_hist[64];
 	TdHead			td;
+	SlotAux			aux;
 	Centroid		cent[TD_CAP];
 };
 

@@ -262,7 +262,7 @@ int gysk_set_logical_map(gysk_engine *e, const uint64_t *glob_ids, const uint64_
 {
 	CHECK_ENGINE(e);
 	if ((!glob_ids || !logical_ids) && n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = sync_locked(e);
 	if (rc) return rc;
@@ -359,7 +359,7 @@ int gysk_set_logical_map(gysk_engine *e, const uint64_t *glob_ids, const uint64_
 int gysk_merge_prepare(gysk_engine *e)
 {
 	CHECK_ENGINE(e);
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	MergeState &mg = e->mg;
 	if (!mg.arena) return fail(e, GYSK_ERR_INVAL, "gysk_merge_prepare: call gysk_set_logical_map first");
@@ -393,7 +393,7 @@ int gysk_merge_buffers(gysk_engine *e, gysk_buffer_desc *out, uint32_t cap, uint
 {
 	CHECK_ENGINE(e);
 	if (!out || !n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	MergeState &mg = e->mg;
 	if (!mg.arena) return fail(e, GYSK_ERR_INVAL, "gysk_merge_buffers: call gysk_set_logical_map first");
 	if (cap < 3) return GYSK_ERR_NOSPC;
@@ -408,7 +408,7 @@ int gysk_merge_tdigest_slab(gysk_engine *e, void **dptr, uint64_t *nbytes)
 {
 	CHECK_ENGINE(e);
 	if (!dptr || !nbytes) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	if (!e->mg.slab) return fail(e, GYSK_ERR_INVAL, "gysk_merge_tdigest_slab: call gysk_set_logical_map first");
 	*dptr = e->mg.slab; *nbytes = (uint64_t)e->mg.nlogical * sizeof(SlabEntry);
 	return GYSK_OK;
@@ -417,7 +417,7 @@ int gysk_merge_tdigest_slab(gysk_engine *e, void **dptr, uint64_t *nbytes)
 int gysk_merge_finish(gysk_engine *e, const void *d_gathered, uint32_t world)
 {
 	CHECK_ENGINE(e);
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	MergeState &mg = e->mg;
 	if (!mg.prepared) return fail(e, GYSK_ERR_INVAL, "gysk_merge_finish: call gysk_merge_prepare first");
@@ -437,7 +437,7 @@ int gysk_query_logical(gysk_engine *e, const uint64_t *logical_ids, uint32_t n, 
 {
 	CHECK_ENGINE(e);
 	if ((!logical_ids || !out) && n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	MergeState &mg = e->mg;
 	if (!mg.finished) return fail(e, GYSK_ERR_INVAL, "gysk_query_logical: no finished merge");
@@ -465,7 +465,7 @@ int gysk_query_flows_global(gysk_engine *e, const uint64_t *keys, uint32_t n, in
 {
 	CHECK_ENGINE(e);
 	if ((!keys || !out) && n) return GYSK_ERR_INVAL;
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	MergeState &mg = e->mg;
 	if (!mg.prepared) return fail(e, GYSK_ERR_INVAL, "gysk_query_flows_global: no merge");
@@ -503,7 +503,7 @@ int gysk_nccl_comm_init(gysk_engine *e, const uint8_t uid[GYSK_NCCL_UNIQUE_ID_BY
 	if (!uid || !nranks || rank >= nranks) return GYSK_ERR_INVAL;
 	NcclApi *a = nccl_api();
 	if (!a) return fail(e, GYSK_ERR_NOTSUP, "libnccl.so.2 could not be loaded");
-	std::lock_guard<std::mutex> lk(e->mtx);
+	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	if (e->mg.comm) { a->CommDestroy((ncclComm_t)e->mg.comm); e->mg.comm = nullptr; }
 	ncclUniqueId id;
@@ -527,7 +527,7 @@ int gysk_merge_global(gysk_engine *e, void *comm)
 	if (rc) return rc;
 	int world = 0;
 	{
-		std::lock_guard<std::mutex> lk(e->mtx);
+		GYSK_ENTER(e);
 		CU(e, cudaSetDevice(e->dev));
 		MergeState &mg = e->mg;
 		NC(e, a->CommCount(c, &world));

@@ -147,6 +147,49 @@ struct tcp_ipv4_resp_event_t
 };
 static_assert(sizeof(tcp_ipv4_resp_event_t) == 24, "tcp_ipv4_resp_event_t");
 
+struct alignas(16) tcp_ipv6_event_t					// common/gy_ebpf_kernel.h:54-68 (unsigned __int128 addresses)
+{
+	uint64_t	ts_ns, bytes_received, bytes_acked;
+	uint32_t	pid, tid;
+	char		comm[16];
+	uint32_t	saddr[4], daddr[4];
+	uint32_t	netns;
+	uint16_t	sport, dport;
+	uint8_t		ipver, type;
+};
+static_assert(sizeof(tcp_ipv6_event_t) == 96 && offsetof(tcp_ipv6_event_t, saddr) == 48 && offsetof(tcp_ipv6_event_t, type) == 89, "tcp_ipv6_event_t");
+
+struct alignas(16) tcp_ipv6_resp_event_t				// common/gy_ebpf_kernel.h:113-118 over ipv6_tuple_t (gy_ebpf_bpf_common.h:32-39)
+{
+	uint32_t	saddr[4], daddr[4];
+	uint32_t	netns;
+	uint16_t	sport, dport;
+	uint32_t	pad_[2];						// ipv6_tuple_t is padded to its 16-byte alignment
+	uint32_t	lsndtime, lrcvtime;
+};
+static_assert(sizeof(tcp_ipv6_resp_event_t) == 64 && offsetof(tcp_ipv6_resp_event_t, lsndtime) == 48, "tcp_ipv6_resp_event_t");
+
+struct alignas(8) ACTIVE_CONN_STATS					// common/gy_comm_proto.h:2766-2810 (fixed stride)
+{
+	uint64_t	listener_glob_id_;
+	uint64_t	cli_aggr_task_id_;
+	char		ser_comm_[16];
+	char		cli_comm_[16];
+	uint64_t	remote_machine_id_[2];					// GY_MACHINE_ID
+	uint64_t	remote_madhava_id_;
+	uint64_t	bytes_sent_;
+	uint64_t	bytes_received_;
+	uint32_t	cli_delay_msec_;
+	uint32_t	ser_delay_msec_;
+	float		max_rtt_msec_;
+	uint16_t	active_conns_;
+	uint8_t		flags_;							// cli_listener_proc_ : 1, is_remote_listen_ : 1, is_remote_cli_ : 1
+	uint8_t		pad_;
+
+	static constexpr size_t MAX_NUM_CONNS = 2048;			// :2786
+};
+static_assert(sizeof(ACTIVE_CONN_STATS) == 104 && offsetof(ACTIVE_CONN_STATS, bytes_sent_) == 72 && offsetof(ACTIVE_CONN_STATS, active_conns_) == 100, "ACTIVE_CONN_STATS");
+
 // The shape shared by TCP_CONN_NOTIFY::validate / AGGR_TASK_STATE_NOTIFY::validate / LISTENER_STATE_NOTIFY::validate
 // (common/gy_comm_proto.cc:840-881, :912-953, :955-996): nevents <= MAX, every element size a multiple of 8 and
 // inside the remaining length, trailing string NUL-forced in place, success iff all nevents were walked.

@@ -13,10 +13,17 @@ assert EVENT_DTYPE.itemsize == 32
 SERIAL_DTYPE = np.dtype([("count", "<u8"), ("sum", "<i8")])
 FLOW_EST_DTYPE = np.dtype([("flow_key", "<u8"), ("count", "<u4"), ("kbytes", "<u4")])
 
-EV_CONNECT, EV_ACCEPT, EV_CLOSE_CLI, EV_CLOSE_SER, EV_RESP, EV_TASK = 1, 2, 3, 4, 5, 6
+EV_CONNECT, EV_ACCEPT, EV_CLOSE_CLI, EV_CLOSE_SER, EV_RESP, EV_TASK, EV_ACTIVE = 1, 2, 3, 4, 5, 6, 7
+EVF_CLI_ERROR, EVF_SER_ERROR = 1, 2
 HIST_RESP_CUR, HIST_RESP_LAST, HIST_RESP_ALL, HIST_TASK_CPU_PCT, HIST_TASK_CPU_DELAY, HIST_TASK_BLKIO_DELAY, HIST_RESP_5MIN, HIST_RESP_5DAY = range(8)
-RAW_EVENT32, RAW_TCP_IPV4_EVENT, RAW_TCP_IPV4_RESP = 0, 1, 2
-NOTIFY_LISTENER_STATE, NOTIFY_TCP_CONN, NOTIFY_AGGR_TASK_STATE = 0x309, 0x30C, 0x310
+RAW_EVENT32, RAW_TCP_IPV4_EVENT, RAW_TCP_IPV4_RESP, RAW_TCP_IPV6_EVENT, RAW_TCP_IPV6_RESP, RAW_API_TRAN, RAW_RESP16, RAW_TCP24, RAW_TASK24 = range(9)
+RESP16_DTYPE = np.dtype([("svc_id", "<u8"), ("usec", "<u4"), ("host_idx", "<u2"), ("cli_port", "u1"), ("flags", "u1")])
+TCP24_DTYPE = np.dtype([("svc_id", "<u8"), ("flow_key", "<u8"), ("bytes", "<u4"), ("host_idx", "<u2"), ("type", "u1"), ("pad", "u1")])
+TASK24_DTYPE = np.dtype([("aggr_task_id", "<u8"), ("cpu_pct", "<u4"), ("cpu_delay_msec", "<u4"), ("blkio_delay_msec", "<u4"), ("host_idx", "<u2"), ("pad", "<u2")])
+assert RESP16_DTYPE.itemsize == 16 and TCP24_DTYPE.itemsize == 24 and TASK24_DTYPE.itemsize == 24
+NOTIFY_LISTENER_STATE, NOTIFY_TCP_CONN, NOTIFY_AGGR_TASK_STATE, NOTIFY_ACTIVE_CONN_STATS = 0x309, 0x30C, 0x310, 0x312
+(HOSTTOP_SVC_ISSUE, HOSTTOP_SVC_QPS, HOSTTOP_SVC_CONNS, HOSTTOP_SVC_NET, HOSTTOP_TASK_ISSUE, HOSTTOP_TASK_NET, HOSTTOP_TASK_CPU, HOSTTOP_TASK_RSS,
+ HOSTTOP_TASK_CPU_DELAY, HOSTTOP_TASK_VM_DELAY, HOSTTOP_TASK_BLKIO_DELAY) = range(11)
 FLAG_AUTO_REGISTER = 1
 TD_CAP = 256
 
@@ -42,7 +49,9 @@ class SvcSummary(C.Structure):
                 ("p95_all_resp_ms", C.c_int64), ("p99_all_resp_ms", C.c_int64), ("nqrys_all", C.c_uint64),
                 ("max_resp_ms", C.c_int64), ("nconns_5s", C.c_uint32), ("kbytes_5s", C.c_uint32), ("nconns_all", C.c_uint64),
                 ("kbytes_all", C.c_uint64), ("distinct_clients", C.c_double), ("td_p50_us", C.c_double),
-                ("td_p95_us", C.c_double), ("td_p99_us", C.c_double), ("td_count", C.c_uint64)]
+                ("td_p95_us", C.c_double), ("td_p99_us", C.c_double), ("td_count", C.c_uint64),
+                ("nconns_active", C.c_uint32), ("active_kbytes", C.c_uint32), ("max_rtt_msec", C.c_float),
+                ("cli_errors", C.c_uint32), ("ser_errors", C.c_uint32), ("pad", C.c_uint32)]
 
     def asdict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -108,6 +117,7 @@ def load_library(path=None):
         "gysk_query_host_summary": (i32, [vp, u32, vp]),
         "gysk_topn_svcs": (i32, [vp, i32, C.c_int32, u32, vp, vp]),
         "gysk_topn_tasks": (i32, [vp, i32, u32, vp, vp]),
+        "gysk_topn_host": (i32, [vp, i32, C.c_int32, u32, vp, vp]),
         "gysk_query_cluster_state": (i32, [vp, vp, u32, vp]),
         "gysk_export_hist": (i32, [vp, u64, i32, vp, vp, vp]),
         "gysk_export_task_hist": (i32, [vp, u64, i32, vp, vp, vp]),
@@ -282,6 +292,12 @@ class Engine:
         k = C.c_uint32()
         self._chk(self.L.gysk_topn_tasks(self.h, metric, n, out, C.byref(k)))
         return [(o.glob_id, o.score) for o in out[: k.value]]
+
+    def topn_host(self, what, n=10, host_idx=-1):
+        out = (TopnEntry * n)()
+        k = C.c_uint32()
+        self._chk(self.L.gysk_topn_host(self.h, what, host_idx, n, out, C.byref(k)))
+        return [(o.glob_id, o.score, o.host_idx) for o in out[: k.value]]
 
     def cluster_state(self, host_idxs=None):
         cs = ClusterState()

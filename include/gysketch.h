@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GYSK_ABI_VERSION		1
+#define GYSK_ABI_VERSION		2
 
 /* ---- error codes ---- */
 #define GYSK_OK				0
@@ -62,18 +62,26 @@ enum {
 	GYSK_EV_CLOSE_SER	= 4,	/* TCP_EVENT_TYPE_CLOSE_SER */
 	GYSK_EV_RESP		= 5,	/* service response-time sample (tcp_ipv4_resp_event_t / API_TRAN) */
 	GYSK_EV_TASK		= 6,	/* per-process 5-s sample (AGGR_TASK_STATE_NOTIFY) */
+	GYSK_EV_ACTIVE		= 7,	/* one ACTIVE_CONN_STATS record (common/gy_comm_proto.h:2766): the 15-s inet_diag group-by
+					   {ser_glob_id, cli_task_aggr_id} of upd_conn_from_diag (common/gy_socket_stat.cc:6156-6194) */
 };
+
+/* gysk_event.flags of a GYSK_EV_RESP event that came from an API_TRAN (SVC_INFO_CAP::upd_stats_on_req, gy_proto_parser.cc:2678-2694) */
+#define GYSK_EVF_CLI_ERROR		0x1u	/* stats_.ncli_errors_++ */
+#define GYSK_EVF_SER_ERROR		0x2u	/* stats_.nser_errors_++ */
 
 typedef struct gysk_event
 {
 	uint64_t	svc_id;		/* ser_glob_id_ ; for GYSK_EV_TASK: aggr_task_id_. 0 is invalid (dropped) */
 	uint64_t	flow_key;	/* TCP/RESP: cli_task_aggr_id_ or a 64-bit fold of the 5-tuple.
 					   TASK: low 32 = cpu_delay_msec_, high 32 = blkio_delay_msec_ */
-	uint32_t	value;		/* RESP: response time in usec; TCP: bytes; TASK: (int)total_cpu_pct_ */
+	uint32_t	value;		/* RESP: response time in usec; TCP: bytes; TASK: (int)total_cpu_pct_; ACTIVE: kbytes sent + received */
 	uint32_t	host_idx;	/* dense index of the sending partha (shard key: host_idx % world) */
-	uint32_t	tsec;		/* event time, seconds */
+	uint32_t	tsec;		/* event time, seconds — informational: a sample lands in the window that is open when it ARRIVES,
+					   as in the reference (handle_tcp_resp_event stamps samples with time(nullptr) of their
+					   processing, common/gy_socket_stat.cc:1560-1579). ACTIVE: IEEE-754 bits of max_rtt_msec_ */
 	uint16_t	type;		/* GYSK_EV_* */
-	uint16_t	flags;		/* reserved, 0 */
+	uint16_t	flags;		/* RESP: GYSK_EVF_*; ACTIVE: active_conns_; else 0 */
 } gysk_event;
 
 /* ---- histogram classes (bucket thresholds of common/gy_statistics.h:1674-2063) ---- */
@@ -114,12 +122,27 @@ enum {
 	GYSK_RAW_EVENT32	= 0,	/* gysk_event[] */
 	GYSK_RAW_TCP_IPV4_EVENT	= 1,	/* tcp_ipv4_event_t[]      72 B  common/gy_ebpf_kernel.h:37  */
 	GYSK_RAW_TCP_IPV4_RESP	= 2,	/* tcp_ipv4_resp_event_t[] 24 B  common/gy_ebpf_kernel.h:106 */
+	GYSK_RAW_TCP_IPV6_EVENT	= 3,	/* tcp_ipv6_event_t[]      96 B  common/gy_ebpf_kernel.h:54  (handle_ipv6_conn_event, gy_socket_stat.cc:269) */
+	GYSK_RAW_TCP_IPV6_RESP	= 4,	/* tcp_ipv6_resp_event_t[] 64 B  common/gy_ebpf_kernel.h:113 (handle_ipv6_resp_event, gy_socket_stat.cc:1535) */
+	GYSK_RAW_API_TRAN	= 5,	/* API_TRAN records, variable stride (common/gy_proto_common.h:140-204; nevents records walked with
+					   get_elem_size()); `events` must stay readable for nevents strides */
+	GYSK_RAW_RESP16		= 6,	/* gysk_resp16[]  packed response samples */
+	GYSK_RAW_TCP24		= 7,	/* gysk_tcp24[]   packed conn events */
+	GYSK_RAW_TASK24		= 8,	/* gysk_task24[]  packed process samples */
 };
+
+/* Packed per-kind records: what a feeder that already knows the kind of a batch ships instead of the 32-byte canonical record
+ * (18.4 bytes per event on the 70 / 20 / 10 mix instead of 32 — the host link is the end-to-end limit). Decoded ON THE DEVICE
+ * into the canonical record, as are the fixed-stride eBPF structs above: gysk_ingest_raw copies the raw bytes, a kernel expands them. */
+typedef struct gysk_resp16 { uint64_t svc_id; uint32_t usec; uint16_t host_idx; uint8_t cli_port; uint8_t flags; } gysk_resp16;
+typedef struct gysk_tcp24 { uint64_t svc_id; uint64_t flow_key; uint32_t bytes; uint16_t host_idx; uint8_t type; uint8_t pad; } gysk_tcp24;
+typedef struct gysk_task24 { uint64_t aggr_task_id; uint32_t cpu_pct; uint32_t cpu_delay_msec; uint32_t blkio_delay_msec; uint16_t host_idx; uint16_t pad; } gysk_task24;
 
 /* ---- wire subtypes accepted by gysk_ingest (NOTIFY_TYPE_E, common/gy_comm_proto.h:155-200) ---- */
 #define GYSK_NOTIFY_LISTENER_STATE	0x309u
 #define GYSK_NOTIFY_TCP_CONN		0x30Cu
 #define GYSK_NOTIFY_AGGR_TASK_STATE	0x310u
+#define GYSK_NOTIFY_ACTIVE_CONN_STATS	0x312u	/* handle_partha_active_conns, server/gy_mconnhdlr.cc:7705 (dispatched at :5250) */
 
 /* ---- configuration ---- */
 #define GYSK_FLAG_AUTO_REGISTER		0x1u	/* unknown svc/task ids are inserted on first sight (device side);
@@ -175,6 +198,11 @@ typedef struct gysk_svc_summary
 	double		distinct_clients;	/* HLL estimate */
 	double		td_p50_us, td_p95_us, td_p99_us;	/* t-digest quantiles (usec); NaN when empty */
 	uint64_t	td_count;
+	uint32_t	nconns_active;		/* ACTIVE_CONN_STATS of the last window: sum of active_conns_ (-> LISTENER_STATE_NOTIFY::nconns_active_) */
+	uint32_t	active_kbytes;		/* ... sum of (bytes_sent_ + bytes_received_) >> 10 */
+	float		max_rtt_msec;		/* ... max of max_rtt_msec_ */
+	uint32_t	cli_errors, ser_errors;	/* API_TRAN error counters of the last window (-> ::cli_errors_, ::ser_errors_) */
+	uint32_t	pad;
 } gysk_svc_summary;
 
 /* per-host roll-up of the listener states of one 5-s tick: LISTEN_SUMM_STATS<int>, server/gy_msocket.h:840-866 */
@@ -218,6 +246,16 @@ typedef struct gysk_topn_entry
 	uint32_t	host_idx;
 	uint32_t	pad;
 } gysk_topn_entry;
+
+/* per-host rankings of gysk_topn_host: the four listener queues of partha_listener_state (server/gy_mconnhdlr.cc:11262-11304) and the
+ * seven process queues of partha_aggr_task_state (:10012-10079), as of the host's last message of that kind (10 entries each,
+ * BOUNDED_PRIO_QUEUE::try_emplace_locked semantics). score: SVC_ISSUE = curr_state_ << 32 | tasks_delay_usec_; TASK_ISSUE = severe << 32 |
+ * ntasks_issue_ + 1; TASK_CPU = IEEE bits of total_cpu_pct_ (orders like the float); else the raw field */
+enum {
+	GYSK_HOSTTOP_SVC_ISSUE = 0, GYSK_HOSTTOP_SVC_QPS, GYSK_HOSTTOP_SVC_CONNS, GYSK_HOSTTOP_SVC_NET,
+	GYSK_HOSTTOP_TASK_ISSUE, GYSK_HOSTTOP_TASK_NET, GYSK_HOSTTOP_TASK_CPU, GYSK_HOSTTOP_TASK_RSS, GYSK_HOSTTOP_TASK_CPU_DELAY,
+	GYSK_HOSTTOP_TASK_VM_DELAY, GYSK_HOSTTOP_TASK_BLKIO_DELAY,
+};
 
 typedef struct gysk_flow_est
 {
@@ -285,6 +323,7 @@ int		gysk_query_flows(gysk_engine *e, const uint64_t *flow_keys, uint32_t n, int
 /* host_idx < 0: over all hosts of this engine; n <= 64 */
 int		gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gysk_topn_entry *out, uint32_t *nout);
 int		gysk_topn_tasks(gysk_engine *e, int metric, uint32_t n, gysk_topn_entry *out, uint32_t *nout);
+int		gysk_topn_host(gysk_engine *e, int what /* GYSK_HOSTTOP_* */, int32_t host_idx /* < 0: all hosts */, uint32_t n, gysk_topn_entry *out, uint32_t *nout);
 /* roll-up over the given hosts (the hosts of one cluster_name_; host_idxs NULL = every host of this engine): what
  * MCONN_HANDLER::send_cluster_state (server/gy_mconnhdlr.cc:16052) sends to shyama per cluster */
 int		gysk_query_cluster_state(gysk_engine *e, const uint32_t *host_idxs, uint32_t n, gysk_cluster_state *out);	/* n <= 64; glob_id = aggr_task_id */

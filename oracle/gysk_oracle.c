@@ -587,6 +587,9 @@ typedef struct svc_state
 	uint32_t	*pend;			/* RESP samples (usec) of the batch being ingested */
 	uint32_t	npend, cappend;
 	uint32_t	first_seen, last_active;	/* tsec of the first flush that saw the service / of the last window with events */
+	uint64_t	act_cur, act_last;	/* ACTIVE_CONN_STATS roll-up {active conns : 32 | kbytes : 32} */
+	uint64_t	err_cur, err_last;	/* API_TRAN error counters {client : 32 | server : 32} */
+	uint32_t	rtt_cur, rtt_last;	/* max of max_rtt_msec_ (float bits; non-negative floats order like their bits) */
 } svc_state;
 
 typedef struct task_state
@@ -746,6 +749,8 @@ int gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n)
 				int b = gyo_hist_add(&s->cur, (int64_t)ms);
 				s->bm_cur[b] |= 1u << (uint32_t)(p->flow_key & 0x1F);
 			}
+			/* SVC_INFO_CAP::upd_stats_on_req, gy_proto_parser.cc:2685-2692: stats_.ncli_errors_++ / nser_errors_++ */
+			if (p->flags & 3u) s->err_cur += (uint64_t)(p->flags & 1u) | ((uint64_t)((p->flags >> 1) & 1u) << 32);
 			if (s->npend == 0) e->touched[e->ntouched++] = (uint32_t)(s - e->svcs);
 			if (s->npend == s->cappend) {
 				s->cappend = s->cappend ? s->cappend * 2 : 16;
@@ -768,6 +773,25 @@ int gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n)
 			gyo_hll_idx_rank(p->flow_key, e->hll_p, &idx, &rank);
 			if (s->hll[idx] < rank) s->hll[idx] = rank;
 			s->conn_cur += inc;
+			e->n_tcp++;
+			break;
+		}
+
+		case 7 : {	/* ACTIVE: one ACTIVE_CONN_STATS record = the 15-s inet_diag group-by {ser_glob_id, cli_task_aggr_id} of
+				   upd_conn_from_diag (common/gy_socket_stat.cc:6156-6194: bytes +=, active conns +=, max rtt) as madhava
+				   receives it (handle_partha_active_conns, server/gy_mconnhdlr.cc:7705). value = kbytes, flags = active_conns_,
+				   tsec = float bits of max_rtt_msec_. Flow sketch: conns and kbytes of the flow; service: totals of the window */
+			svc_state *s = get_svc(e, p->svc_id, autoreg);
+			if (!s) { e->n_drop++; break; }
+			uint64_t inc = (uint64_t)p->flags | ((uint64_t)p->value << 32);
+			for (uint32_t r = 0; r < e->depth; ++r) {
+				e->cms_cur[((size_t)r << e->log2w) + (gyo_cms_index(p->flow_key, r, e->log2w) & wmask)] += inc;
+			}
+			uint32_t idx; uint8_t rank;
+			gyo_hll_idx_rank(p->flow_key, e->hll_p, &idx, &rank);
+			if (s->hll[idx] < rank) s->hll[idx] = rank;
+			s->act_cur += inc;
+			if (p->tsec > s->rtt_cur) s->rtt_cur = p->tsec;
 			e->n_tcp++;
 			break;
 		}
@@ -825,7 +849,7 @@ void gyo_flush(gyo_engine *e, uint32_t tsec)
 		if (!s->id) continue;		/* evicted, slot waiting for reuse */
 		/* idle-service rule (ours, after common/gy_socket_stat.cc:3968-3982: tclock != 0, tclock + 300 s < now, tstart + 600 s < now) */
 		{
-			int active = (uint32_t)s->conn_cur != 0 || (s->conn_cur >> 32) != 0;
+			int active = (uint32_t)s->conn_cur != 0 || (s->conn_cur >> 32) != 0 || s->act_cur != 0 || s->err_cur != 0;
 			for (int b = 0; b < 15 && !active; ++b) active = s->cur.stats[b].count != 0;
 			if (!s->first_seen) s->first_seen = tsec ? tsec : 1u;
 			if (active) s->last_active = tsec ? tsec : 1u;
@@ -843,6 +867,7 @@ void gyo_flush(gyo_engine *e, uint32_t tsec)
 		s->conn_all_cnt += (uint32_t)s->conn_cur;
 		s->conn_all_kb += s->conn_cur >> 32;
 		s->conn_cur = 0;
+		s->act_last = s->act_cur; s->act_cur = 0; s->err_last = s->err_cur; s->err_cur = 0; s->rtt_last = s->rtt_cur; s->rtt_cur = 0;
 
 		if (e->idle_evict_secs && s->last_active && (uint64_t)s->last_active + e->idle_evict_secs < tsec &&
 				(uint64_t)s->first_seen + 2ull * e->idle_evict_secs < tsec) {
@@ -952,6 +977,16 @@ int gyo_export_conn(gyo_engine *e, uint64_t id, uint64_t *cur, uint64_t *last, u
 	if (slot < 0) return -2;
 	*cur = e->svcs[slot].conn_cur; *last = e->svcs[slot].conn_last;
 	*all_cnt = e->svcs[slot].conn_all_cnt; *all_kb = e->svcs[slot].conn_all_kb;
+	return 0;
+}
+
+/* out[0..5] = act_cur, act_last, err_cur, err_last, rtt_cur (float bits), rtt_last */
+int gyo_export_aux(gyo_engine *e, uint64_t id, uint64_t out[6])
+{
+	int slot = idmap_find(&e->smap, id, 0, 0);
+	if (slot < 0) return -2;
+	const svc_state *s = &e->svcs[slot];
+	out[0] = s->act_cur; out[1] = s->act_last; out[2] = s->err_cur; out[3] = s->err_last; out[4] = s->rtt_cur; out[5] = s->rtt_last;
 	return 0;
 }
 

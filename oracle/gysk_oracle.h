@@ -122,6 +122,7 @@ int	gyo_export_hist(gyo_engine *e, uint64_t id, int which, gyo_serial *out15, ui
 int	gyo_export_hll(gyo_engine *e, uint64_t id, uint8_t *regs);
 int	gyo_export_tdigest(gyo_engine *e, uint64_t id, gyo_tdigest *out);
 int	gyo_export_conn(gyo_engine *e, uint64_t id, uint64_t *cur, uint64_t *last, uint64_t *all_cnt, uint64_t *all_kb);
+int	gyo_export_aux(gyo_engine *e, uint64_t id, uint64_t out[6]);	/* ACTIVE_CONN_STATS roll-up, API_TRAN error counters, max rtt */
 int	gyo_export_conn_bitmap(gyo_engine *e, uint64_t id, int last_window, uint32_t *masks15, uint8_t *nconn15);
 const uint64_t *gyo_cms_table(gyo_engine *e, int last_window);
 void	gyo_counters(gyo_engine *e, uint64_t out[8]);	/* in, dropped, resp, tcp, task, nsvcs, ntasks, foreign */

@@ -103,6 +103,7 @@ def lib():
         L.gyo_export_tdigest.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.gyo_export_conn.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
         L.gyo_export_conn_bitmap.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.gyo_export_aux.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.gyo_cms_table.restype = C.c_void_p
         L.gyo_cms_table.argtypes = [C.c_void_p, C.c_int]
         L.gyo_counters.argtypes = [C.c_void_p, C.c_void_p]
@@ -224,6 +225,14 @@ class OracleEngine:
         v = [C.c_uint64() for _ in range(4)]
         rc = self.L.gyo_export_conn(self.h, int(id_), *[C.byref(x) for x in v])
         return None if rc else tuple(x.value for x in v)
+
+    def export_aux(self, id_):
+        """dict(act_cur, act_last, err_cur, err_last: packed {lo32, hi32}; rtt_cur, rtt_last: float)"""
+        out = np.zeros(6, dtype=np.uint64)
+        if self.L.gyo_export_aux(self.h, int(id_), _p(out)):
+            return None
+        f = lambda b: float(np.array([b], dtype=np.uint32).view(np.float32)[0])
+        return dict(act_cur=int(out[0]), act_last=int(out[1]), err_cur=int(out[2]), err_last=int(out[3]), rtt_cur=f(int(out[4])), rtt_last=f(int(out[5])))
 
     def export_conn_bitmap(self, id_, last_window=False):
         masks = np.zeros(15, dtype=np.uint32)

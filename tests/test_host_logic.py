@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(ge.LIB_PATH)
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
-    assert ge.load_library().gysk_abi_version() == 1
+    assert ge.load_library().gysk_abi_version() == 2
 
 
 def test_no_gpu_fails_loudly():
