@@ -445,7 +445,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	if (!cfg.stage_batch || cfg.stage_batch > cfg.max_batch) cfg.stage_batch = std::min<uint32_t>(cfg.max_batch, 1u << 22);
 	if (cfg.max_svcs < 1 || cfg.max_svcs > (1u << 24) || cfg.max_tasks < 1 || cfg.max_tasks > (1u << 24) || cfg.cms_depth < 1 ||
 			cfg.cms_depth > 8 || cfg.cms_log2_width < 4 || cfg.cms_log2_width > 28 || cfg.hll_p < 4 || cfg.hll_p > 16 ||
-			cfg.td_compression < 10 || cfg.td_compression > 220 || cfg.max_batch < 1024 || cfg.max_batch >= (1u << 27) ||
+			cfg.td_compression < 10 || cfg.td_compression > (uint32_t)TD_CAP || cfg.max_batch < 1024 || cfg.max_batch >= (1u << 27) ||
 			cfg.rank >= cfg.world)
 		return fail(nullptr, GYSK_ERR_INVAL, "gysk_config out of range");
 
@@ -505,14 +505,15 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	st.rank = cfg.rank; st.world = cfg.world; st.auto_register = (cfg.flags & GYSK_FLAG_AUTO_REGISTER) ? 1 : 0;
 	st.td_delta = (double)cfg.td_compression;
 	{
-		// coarser rungs for greedy passes that would not fit TD_CAP clusters (same table in oracle/gysk_oracle.c)
-		static const double ladder[TD_LADDER] = { 1.0, 0.92, 0.85, 0.78, 0.72, 0.66 };
-		for (int k = 0; k < TD_LADDER; ++k) {
-			const double d = st.td_delta * ladder[k];
-			st.td.r[k].C = cos(M_PI / d); st.td.r[k].S = sin(M_PI / d); st.td.r[k].qclamp = (1.0 + st.td.r[k].C) / 2.0;
-		}
+		// the unit grid of the K_1 scale: q_j = (sin(pi (j/delta - 1/2)) + 1)/2 — libm on the host, the same expression as the oracle
+		std::vector<double> qtab(cfg.td_compression + 1);
+		for (uint32_t j = 0; j <= cfg.td_compression; ++j) qtab[j] = 0.5 * (sin(M_PI * ((double)j / (double)cfg.td_compression - 0.5)) + 1.0);
+		qtab[0] = 0.0; qtab[cfg.td_compression] = 1.0;
+		double *d_q = nullptr;
+		A(dalloc(e, &d_q, qtab.size(), false));
+		if ((ce = cudaMemcpy(d_q, qtab.data(), qtab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) { fail(e, GYSK_ERR_CUDA, "qtab", ce); return bail(GYSK_ERR_CUDA); }
+		st.td.qtab = d_q; st.td.delta = cfg.td_compression; st.td.pad = 0;
 	}
-
 	A(dalloc(e, &st.slot_batch, ns)); A(dalloc(e, &st.slot_aux, ns));
 	SortTemp &tmp = e->tmp;
 	const size_t nsort = std::max<size_t>(std::max<size_t>(ns, nt) + 1, cfg.max_batch);	// RESP keys of a batch; the top-N sorts rank services / tasks
@@ -1297,28 +1298,24 @@ int gysk_tdigest_to_pgtext(const double *means, const uint64_t *weights, uint32_
 
 // The engine keeps delta = 200 internally; the Postgres side of the reference aggregates with public.tdigest(expr, 100)
 // (common/gy_query_common.cc:1855) and the extension refuses to combine digests of different compression, so the export is one
-// more greedy K_1 pass at compression 100 (host side, same rule as the device: a cluster that starts after weight P takes items
-// while the running total stays <= W q(k(P/W) + 1)).
-static uint32_t host_td_compress(const double *means, const uint64_t *w, uint32_t n, double delta, double *om, uint64_t *ow)
+// more fixed-grid K_1 compress at compression 100 (host side, same rule as the device).
+static uint32_t host_td_compress(const double *means, const uint64_t *w, uint32_t n, uint32_t delta, double *om, uint64_t *ow)
 {
 	if (!n) return 0;
-	const double C = cos(M_PI / delta), S = sin(M_PI / delta), qclamp = (1.0 + C) / 2.0;
-	uint64_t W = 0, wsofar = 0, cw = w[0];
+	std::vector<double> qtab(delta + 1);
+	for (uint32_t j = 0; j <= delta; ++j) qtab[j] = 0.5 * (sin(M_PI * ((double)j / (double)delta - 0.5)) + 1.0);
+	qtab[0] = 0.0; qtab[delta] = 1.0;
+	uint64_t W = 0, pref = 0, cw = 0;
 	for (uint32_t i = 0; i < n; ++i) W += w[i];
-	auto wlimit = [&](uint64_t sofar) {
-		const double q0 = sofar ? (double)sofar / (double)W : 0.0;
-		if (q0 >= qclamp) return (double)W;
-		return (double)W * ((((2.0 * q0 - 1.0) * C + 2.0 * sqrt(q0 * (1.0 - q0)) * S) + 1.0) * 0.5);
-	};
-	double csum = means[0] * (double)w[0], wl = wlimit(0);
-	uint32_t nout = 0;
-	for (uint32_t i = 1; i < n; ++i) {
-		if ((double)(wsofar + cw + w[i]) <= wl) { cw += w[i]; csum += means[i] * (double)w[i]; }
-		else {
-			om[nout] = csum / (double)cw; ow[nout++] = cw;
-			wsofar += cw; wl = wlimit(wsofar);
-			cw = w[i]; csum = means[i] * (double)w[i];
-		}
+	uint32_t nout = 0, cur = 0;
+	double csum = 0.0;
+	for (uint32_t i = 0; i < n; ++i) {
+		const double q = (double)pref / (double)W;
+		uint32_t lo = 0, hi = delta - 1;
+		while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (qtab[mid] <= q) lo = mid; else hi = mid - 1; }
+		if (i && lo != cur) { om[nout] = csum / (double)cw; ow[nout++] = cw; cw = 0; csum = 0.0; }
+		cur = lo;
+		csum += means[i] * (double)w[i]; cw += w[i]; pref += w[i];
 	}
 	om[nout] = csum / (double)cw; ow[nout++] = cw;
 	return nout;
@@ -1331,7 +1328,7 @@ int gysk_export_tdigest_pgtext(gysk_engine *e, uint64_t id, char *buf, uint32_t 
 	uint32_t n = 0;
 	int rc = gysk_export_tdigest(e, id, means, w, TD_CAP, &n, &minv, &maxv);
 	if (rc) return rc;
-	const uint32_t no = host_td_compress(means, w, n, 100.0, om, ow);
+	const uint32_t no = host_td_compress(means, w, n, 100, om, ow);
 	return gysk_tdigest_to_pgtext(om, ow, no, 100, buf, cap);
 }
 

@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 struct RunRec { unsigned long long cw; unsigned long long us; };		// {samples : 27 | remainders : 37}, usec sum — as Bin
 struct BatchSeg { uint32_t run0, nruns; uint32_t key0, nkeys; };		// a touched service's runs in the pool / keys in the sorted array
 
-static constexpr int RM_THREADS = 256, RM_V = 4, RM_TILE = RM_THREADS * RM_V;	// keys per thread: positions wbase + t * 32 + lane
+static constexpr int RM_THREADS = 256, RM_V = 8, RM_TILE = RM_THREADS * RM_V;	// keys per thread: positions wbase + t * 32 + lane
 
 __global__ void __launch_bounds__(RM_THREADS) runs_mark_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
 		unsigned long long *__restrict__ status, uint32_t epoch, RunRec *__restrict__ pool, uint16_t *__restrict__ run_bin,
@@ -774,30 +774,42 @@ __global__ void __launch_bounds__(RM_THREADS) runs_mark_kernel(const unsigned lo
 	uint32_t wexcl = 0, ctotal = 0;
 #pragma unroll
 	for (int w = 0; w < RM_THREADS / 32; ++w) { const uint32_t c = wsum[w]; if (w < wid) wexcl += c; ctotal += c; }
-	// decoupled look-back over the CTAs before this one: number of run starts before the tile
-	if (threadIdx.x == 0) {
+	// decoupled look-back over the CTAs before this one (warp 0, 32 predecessors per step): number of run starts before the tile
+	if (wid == 0) {
 		const uint32_t tile = blockIdx.x;
-		st_volatile_u64(status + tile, etag | (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | ctotal);
+		if (lane == 0) st_volatile_u64(status + tile, etag | (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | ctotal);
 		uint32_t excl = 0;
-		if (tile > 0) {
-			uint32_t p = tile - 1;
-			for (;;) {
-				const unsigned long long v = ld_volatile_u64(status + p);
-				if ((v >> 32) != epoch || !((uint32_t)v >> 30)) continue;
-				excl += (uint32_t)v & OS_COUNT_MASK;
-				if ((uint32_t)v & OS_FLAG_PREFIX) break;
-				--p;
-			}
-			st_volatile_u64(status + tile, etag | OS_FLAG_PREFIX | (excl + ctotal));
+		int p = (int)tile - 1;
+		while (p >= 0) {
+			const int idx = p - lane;
+			const unsigned long long v = idx >= 0 ? ld_volatile_u64(status + idx) : (etag | OS_FLAG_PREFIX);	// before tile 0: prefix 0
+			const bool ok = (v >> 32) == epoch && ((uint32_t)v >> 30) != 0;
+			const uint32_t ready = __ballot_sync(0xffffffffu, ok), pfx = __ballot_sync(0xffffffffu, ok && ((uint32_t)v & OS_FLAG_PREFIX));
+			const uint32_t upto = pfx ? (uint32_t)__ffs((int)pfx) : 32u;				// lanes 0 .. upto - 1 count
+			const uint32_t need = upto == 32 ? 0xffffffffu : ((1u << upto) - 1u);
+			if ((ready & need) != need) continue;							// a predecessor has its ticket, its count will come
+			excl += __reduce_add_sync(0xffffffffu, (uint32_t)lane < upto ? ((uint32_t)v & OS_COUNT_MASK) : 0u);
+			if (pfx) break;
+			p -= 32;
 		}
-		s_excl = excl;
-		if (tbase + RM_TILE >= n) *nruns_total = (unsigned long long)excl + ctotal;
+		if (lane == 0) {
+			if (tile > 0) st_volatile_u64(status + tile, etag | OS_FLAG_PREFIX | (excl + ctotal));
+			s_excl = excl;
+			if (tbase + RM_TILE >= n) *nruns_total = (unsigned long long)excl + ctotal;
+		}
 	}
 	__syncthreads();
 	const uint32_t before_warp = s_excl + wexcl;		// run starts at positions < wbase
 
-	// the run the chunk's first key belongs to: #starts at positions <= wbase, minus one
-	if (lane == 0) chunk_run[wbase >> 7] = before_warp + (words[0] & 1u) - 1u;
+	// the run the first key of each 128-key chunk belongs to: #starts at positions <= the chunk's first, minus one
+	if (lane == 0) {
+		uint32_t before = before_warp;
+#pragma unroll
+		for (int c = 0; c < RM_V / 4; ++c) {
+			chunk_run[(wbase >> 7) + c] = before + (words[4 * c] & 1u) - 1u;
+			before += __popc(words[4 * c]) + __popc(words[4 * c + 1]) + __popc(words[4 * c + 2]) + __popc(words[4 * c + 3]);
+		}
+	}
 
 	// one cursor bump per warp for all the service segments that start in it
 	uint32_t nstart = __popc(isseg);
@@ -1253,13 +1265,16 @@ static int ingest_variant()
 }
 
 // the radix passes of the RESP keys sort on {slot | bin} = key bits [30, 40 + slot bits): TD_CODE_BITS + slot bits significant
-// bits cut into the fewest digits of at most 9 bits, widths as even as possible (27 bits -> 9 9 9; 30 bits -> 8 8 7 7)
+// bits cut into the fewest digits of at most KEY_DIGIT_MAX bits, widths as even as possible (27 bits -> 7 7 7 6). 8-bit passes run
+// at 0.39-0.49 ms per 70 M keys, a 9-bit pass (two look-back rows per thread, nine ballots per key) at 0.76 ms (profiles/): four
+// of the former beat three of the latter.
 static int key_sort_plan(uint32_t max_svcs, SortPlan &P)
 {
 	int slot_bits = 1;
 	while (slot_bits < 24 && (1ull << slot_bits) < max_svcs) slot_bits++;
 	const int T = TD_CODE_BITS + slot_bits;
-	const int np = (T + RADIX_MAX_BITS - 1) / RADIX_MAX_BITS;
+	static const int dmax = []{ const char *e = getenv("GYSK_KEY_DIGIT_MAX"); const int v = e ? atoi(e) : 8; return v == 9 ? 9 : 8; }();
+	const int np = (T + dmax - 1) / dmax;
 	if (np > OS_MAX_PASSES_VK) return -1;
 	int at = KEY_GROUP_SHIFT;
 	for (int p = 0; p < np; ++p) { P.bits[p] = T / np + (p < T % np ? 1 : 0); P.shift[p] = at; at += P.bits[p]; }

@@ -86,7 +86,7 @@ static constexpr int NSLOTS = 10;			// slots per level (gy_statistics.h:1105)
 static constexpr int SORT_TILE = 4096;		// keys per CTA tile in the radix passes
 static constexpr int RADIX_MAX_BITS = 9;
 static constexpr int RADIX_MAX = 1 << RADIX_MAX_BITS;
-static constexpr int OS_MAX_PASSES_VK = 4;		// {slot : <= 24 | bin : 10} in digits of <= 9 bits
+static constexpr int OS_MAX_PASSES_VK = 5;		// {slot : <= 24 | bin : 10} = <= 34 bits in digits of <= 8 bits
 static constexpr int TD_MERGE_CTAS_PER_SM = 5, TD_MERGE_MAX_SMS = 192;	// bins_merge_kernel grid (4 warps per CTA)
 
 // every launcher returns the number of kernel launches it issued

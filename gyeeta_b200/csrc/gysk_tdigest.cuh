@@ -6,30 +6,20 @@
 
 namespace gysk {
 
-// K_1 scale function of the merging t-digest (Dunning), k spanning [-delta/2, delta/2]: k(q) = delta/pi asin(2q - 1).
-// td_q_next(q0) = q(k(q0) + 1), the upper end of the unit-k interval starting at q0, without inverse trig:
-// sin(asin(2 q0 - 1) + pi/delta) = (2 q0 - 1) cos(pi/delta) + 2 sqrt(q0 (1 - q0)) sin(pi/delta). Only IEEE + - * / sqrt with
-// explicit round-to-nearest (no FMA contraction), in the same order as oracle/gysk_oracle.c::td_q_next => identical bits.
-struct TdRung { double C, S, qclamp; };		// cos(pi/delta'), sin(pi/delta'), (1 + C)/2 — computed once on the host
-// A greedy pass over items that cannot be split needs up to ~1.3 delta clusters; a pass that would exceed TD_CAP is repeated on
-// the next, coarser rung (delta' = delta x {1, .92, .85, .78, .72, .66}); only the last rung lets the last slot absorb the rest.
-static constexpr int TD_LADDER = 6;
-struct TdParams { TdRung r[TD_LADDER]; };
+// K_1 scale function of the merging t-digest (Dunning), k spanning [-delta/2, delta/2]: k(q) = delta/pi asin(2q - 1). The compress
+// step works on the FIXED unit grid of k: cell j = [q_j, q_j+1) with q_j = q(k = -delta/2 + j) = (sin(pi (j/delta - 1/2)) + 1)/2, and
+// an item of the merged list (sorted by mean, exclusive weight prefix P_i, total W) belongs to the cell that holds its start
+// position P_i / W. All items of one cell become one cluster: at most delta clusters, each no wider than one unit of k plus its
+// last item — the t-digest size bound — with no data-dependent chain: every item finds its cell on its own (one division, one
+// binary search in a table of delta + 1 doubles), which is what makes the step parallel. The table is computed once on the host
+// (libm sin, same expression in oracle/gysk_oracle.c) so that device, host and oracle compare against identical doubles.
+struct TdParams { const double *qtab; uint32_t delta; uint32_t pad; };		// qtab[0 .. delta], device memory
 
-__device__ __forceinline__ double td_q_next(double q0, const TdRung &P)
+__device__ __forceinline__ uint32_t td_cell(double q, const TdParams &P)
 {
-	if (q0 >= P.qclamp) return 1.0;
-	const double t = __dsub_rn(__dmul_rn(2.0, q0), 1.0);
-	const double r = __dsqrt_rn(__dmul_rn(q0, __dsub_rn(1.0, q0)));
-	const double a = __dmul_rn(t, P.C);
-	const double b = __dmul_rn(__dmul_rn(2.0, r), P.S);
-	return __dmul_rn(__dadd_rn(__dadd_rn(a, b), 1.0), 0.5);
-}
-
-__device__ __forceinline__ double td_wlimit(unsigned long long wsofar, unsigned long long W, const TdRung &P)
-{
-	const double q0 = wsofar ? __ddiv_rn((double)wsofar, (double)W) : 0.0;
-	return __dmul_rn((double)W, td_q_next(q0, P));
+	uint32_t lo = 0, hi = P.delta - 1;		// largest j in [0, delta - 1] with qtab[j] <= q
+	while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (__ldg(P.qtab + mid) <= q) lo = mid; else hi = mid - 1; }
+	return lo;
 }
 
 template <int NMAX_>
@@ -89,38 +79,24 @@ __device__ __forceinline__ uint32_t warp_merge_compress(Work &S, const Centroid 
 	}
 	__syncwarp();
 
-	// greedy chain over the merged list: a cluster that starts at item i (after weight P = pref[i]) takes items while the
-	// running total stays <= W q(k(P/W) + 1), and at least one item. The successor nxt[i] of EVERY possible start is
-	// evaluated in parallel (the expensive double sqrt/div part); the chain itself is then a pointer walk by lane 0.
+	// cell of every item (independent of each other), then the cluster boundaries = the places where the cell changes
 	uint32_t nout = 0;
 	if (nm) {
-		const unsigned long long W = S.pref[nm];
-		for (int k = 0; k < TD_LADDER; ++k) {
-			const TdRung R = P.r[k];
-			for (uint32_t i = lane; i < nm; i += 32) {
-				const double wl = td_wlimit(S.pref[i], W, R);
-				uint32_t e = i + 1;				// largest e in [i+1, nm] with pref[e] <= wl
-				while (e < nm && (double)S.pref[e + 1] <= wl) ++e;
-				S.nxt[i] = (uint16_t)e;
-			}
-			__syncwarp();
-			if (lane == 0) {
-				const bool final = k == TD_LADDER - 1;
-				uint32_t cs = 0;
-				nout = 0;
-				while (cs < nm) {
-					if (nout == TD_CAP) { nout = TD_CAP + 1; break; }		// would need more than TD_CAP clusters
-					uint32_t e = S.nxt[cs];
-					if (final && nout == TD_CAP - 1) e = nm;			// the last slot absorbs whatever is left
-					S.bounds[nout++] = (uint16_t)cs;
-					cs = e;
-				}
-				if (nout <= TD_CAP) S.bounds[nout] = (uint16_t)nm;
-			}
-			nout = __shfl_sync(0xffffffffu, nout, 0);
-			__syncwarp();
-			if (nout <= TD_CAP) break;
-		}
+		const double W = (double)S.pref[nm];
+		for (uint32_t i = lane; i < nm; i += 32) S.nxt[i] = (uint16_t)td_cell(__ddiv_rn((double)S.pref[i], W), P);
+		__syncwarp();
+		// lane owns IPL consecutive items: count its cluster starts, scan over the lanes, write the starts in order
+		const uint32_t i0 = lane * IPL, i1 = i0 + IPL < nm ? i0 + IPL : nm;
+		uint32_t nh = 0;
+		for (uint32_t i = i0; i < i1; ++i) nh += (i == 0 || S.nxt[i] != S.nxt[i - 1]) ? 1u : 0u;
+		uint32_t incl = nh;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+		nout = __shfl_sync(0xffffffffu, incl, 31);
+		uint32_t r = incl - nh;
+		for (uint32_t i = i0; i < i1; ++i) if (i == 0 || S.nxt[i] != S.nxt[i - 1]) S.bounds[r++] = (uint16_t)i;
+		if (lane == 0) S.bounds[nout] = (uint16_t)nm;
+		__syncwarp();
 	}
 
 	for (uint32_t c = lane; c < nout; c += 32) {

@@ -341,38 +341,26 @@ double gyo_hll_estimate(const uint8_t *regs, uint32_t p)
  * inverse trig: with theta = asin(2 q0 - 1), sin(theta + pi/delta) = (2 q0 - 1) cos(pi/delta) + 2 sqrt(q0 (1 - q0)) sin(pi/delta).
  * Only IEEE +,-,*,/ and sqrt, each rounded on its own, in this order — the CUDA path performs the identical sequence, so both
  * produce the same bits. */
-typedef struct td_params { double C, S, qclamp; } td_params;
-
-/* A greedy pass over weighted items that cannot be split yields up to ~1.3 delta clusters. When a pass would need more than
- * the capacity, it is repeated with the next, coarser rung of this ladder (delta * f): the tail resolution degrades by a few
- * per cent instead of the last centroid swallowing the whole upper tail. Only the last rung keeps that guard. */
-#define TD_LADDER	6
-static const double g_td_ladder[TD_LADDER] = { 1.0, 0.92, 0.85, 0.78, 0.72, 0.66 };
-
-static void td_make_ladder(double delta, td_params P[TD_LADDER])
+/* The compress step works on the FIXED unit grid of k: cell j = [q_j, q_j+1), q_j = q(k = -delta/2 + j) = (sin(pi (j/delta - 1/2)) + 1)/2.
+ * An item of the merged list (sorted by mean; exclusive weight prefix P_i, total W) belongs to the cell that holds its start
+ * position P_i / W; all items of one cell become one cluster: at most delta clusters, each no wider than one unit of k plus its
+ * last item (the t-digest size bound), and no data-dependent chain — every item finds its cell on its own. The table is
+ * computed with libm by this expression here and in gyeeta_b200/csrc/gysk_engine.cu (same host, same bits). */
+#define GYO_TD_MAX_DELTA	256
+static void td_qtab(double delta, double *qtab /* [delta + 1] */)
 {
-	for (int k = 0; k < TD_LADDER; ++k) {
-		const double d = delta * g_td_ladder[k];
+	const uint32_t d = (uint32_t)delta;
 
-		P[k].C = cos(M_PI / d); P[k].S = sin(M_PI / d); P[k].qclamp = (1.0 + P[k].C) / 2.0;
-	}
+	for (uint32_t j = 0; j <= d; ++j) qtab[j] = 0.5 * (sin(M_PI * ((double)j / (double)d - 0.5)) + 1.0);
+	qtab[0] = 0.0; qtab[d] = 1.0;
 }
 
-static inline double td_q_next(double q0, const td_params *P)
+static uint32_t td_cell(double q, const double *qtab, uint32_t d)
 {
-	if (q0 >= P->qclamp) return 1.0;			/* k(q0) + 1 >= delta/2 */
-	double t = 2.0 * q0 - 1.0;
-	double r = sqrt(q0 * (1.0 - q0));
-	double a = t * P->C;
-	double b = (2.0 * r) * P->S;
-	return ((a + b) + 1.0) * 0.5;
-}
+	uint32_t lo = 0, hi = d - 1;		/* largest j in [0, d - 1] with qtab[j] <= q */
 
-static inline double td_wlimit(uint64_t wsofar, uint64_t W, const td_params *P)
-{
-	const double q0 = wsofar ? (double)wsofar / (double)W : 0.0;
-
-	return (double)W * td_q_next(q0, P);
+	while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (qtab[mid] <= q) lo = mid; else hi = mid - 1; }
+	return lo;
 }
 
 void gyo_td_init(gyo_tdigest *t)
@@ -381,53 +369,34 @@ void gyo_td_init(gyo_tdigest *t)
 	t->minv = INFINITY; t->maxv = -INFINITY;
 }
 
-/* One greedy pass over centroids sorted by mean. A cluster that starts after weight P absorbs items while the running total
- * stays <= W * q(k(P/W) + 1); it always takes at least its first item. Cluster mean is sum(mean*weight)/sum(weight)
- * accumulated in double in input order. Returns the number of clusters, or cap + 1 when more than cap would be needed
- * (final: the last slot absorbs whatever is left instead). */
-static uint32_t td_compress_once(const gyo_centroid *in, uint32_t n, const td_params *P, gyo_centroid *out, uint32_t cap, int final)
-{
-	uint64_t W = 0, wsofar = 0, cw;
-	uint32_t nout = 0;
-	double csum, wlimit;
-
-	for (uint32_t i = 0; i < n; ++i) W += in[i].weight;
-
-	wlimit = td_wlimit(0, W, P);
-	cw = in[0].weight; csum = in[0].mean * (double)in[0].weight;
-
-	for (uint32_t i = 1; i < n; ++i) {
-		double projected = (double)(wsofar + cw + in[i].weight);
-
-		if (projected <= wlimit || (final && nout + 1 == cap)) {
-			cw += in[i].weight;
-			csum += in[i].mean * (double)in[i].weight;
-		}
-		else {
-			if (nout + 1 >= cap && !final) return cap + 1;	/* this cluster is number cap, and another one follows */
-			out[nout].mean = csum / (double)cw; out[nout].weight = cw;
-			nout++;
-			wsofar += cw;
-			wlimit = td_wlimit(wsofar, W, P);
-			cw = in[i].weight; csum = in[i].mean * (double)in[i].weight;
-		}
-	}
-	out[nout].mean = csum / (double)cw; out[nout].weight = cw;
-	nout++;
-	return nout;
-}
-
+/* cluster mean = sum(mean * weight) / sum(weight), accumulated in double in input order */
 uint32_t gyo_td_compress(const gyo_centroid *in, uint32_t n, double delta, gyo_centroid *out, uint32_t cap)
 {
-	td_params P[TD_LADDER];
-	uint32_t nout = 0;
+	double		qtab[GYO_TD_MAX_DELTA + 1];
+	const uint32_t	d = (uint32_t)delta;
+	uint64_t	W = 0, pref = 0, cw = 0;
+	uint32_t	nout = 0, cur = 0;
+	double		csum = 0.0;
 
 	if (!n) return 0;
-	td_make_ladder(delta, P);
-	for (int k = 0; k < TD_LADDER; ++k) {
-		nout = td_compress_once(in, n, &P[k], out, cap, k == TD_LADDER - 1);
-		if (nout <= cap) break;
+	td_qtab(delta, qtab);
+	for (uint32_t i = 0; i < n; ++i) W += in[i].weight;
+
+	for (uint32_t i = 0; i < n; ++i) {
+		uint32_t cell = td_cell((double)pref / (double)W, qtab, d);
+
+		if (i && cell != cur) {
+			if (nout < cap) { out[nout].mean = csum / (double)cw; out[nout].weight = cw; }
+			nout++;
+			cw = 0; csum = 0.0;
+		}
+		cur = cell;
+		csum += in[i].mean * (double)in[i].weight;
+		cw += in[i].weight;
+		pref += in[i].weight;
 	}
+	if (nout < cap) { out[nout].mean = csum / (double)cw; out[nout].weight = cw; }
+	nout++;
 	return nout;
 }
 

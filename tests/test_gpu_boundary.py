@@ -19,7 +19,7 @@ ACTIVE = np.dtype([("listener_glob_id", "<u8"), ("cli_aggr_task_id", "<u8"), ("s
                    ("ser_delay_msec", "<u4"), ("max_rtt_msec", "<f4"), ("active_conns", "<u2"), ("flags", "u1"), ("pad", "u1")])
 RESP4 = np.dtype([("saddr", "<u4"), ("daddr", "<u4"), ("netns", "<u4"), ("sport", "<u2"), ("dport", "<u2"), ("lsndtime", "<u4"), ("lrcvtime", "<u4")])
 RESP6 = np.dtype([("saddr", "<u4", 4), ("daddr", "<u4", 4), ("netns", "<u4"), ("sport", "<u2"), ("dport", "<u2"), ("pad", "<u4", 2),
-                  ("lsndtime", "<u4"), ("lrcvtime", "<u4")])
+                  ("lsndtime", "<u4"), ("lrcvtime", "<u4"), ("tail", "<u4", 2)])
 CONN6 = np.dtype([("ts_ns", "<u8"), ("bytes_received", "<u8"), ("bytes_acked", "<u8"), ("pid", "<u4"), ("tid", "<u4"), ("comm", "S16"),
                   ("saddr", "<u4", 4), ("daddr", "<u4", 4), ("netns", "<u4"), ("sport", "<u2"), ("dport", "<u2"), ("ipver", "u1"), ("type", "u1"),
                   ("pad", "u1", 6)])
