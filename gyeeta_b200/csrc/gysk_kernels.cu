@@ -930,7 +930,7 @@ __global__ void __launch_bounds__(256) runs_sum_kernel(const unsigned long long 
 	}
 }
 
-static constexpr int TD_WARPS = 4;
+static constexpr int TD_WARPS = 3;		// 3 x 13.8 KB of work area per CTA (static shared memory)
 
 // One warp per touched service. Its runs become the batch's items {mean = exact usec sum / samples, weight = samples} — in value
 // order, because the bin index is monotone — and every run adds {samples, exact msec sum} to its bucket of the window histogram:

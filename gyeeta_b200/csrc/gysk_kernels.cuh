@@ -87,7 +87,7 @@ static constexpr int SORT_TILE = 4096;		// keys per CTA tile in the radix passes
 static constexpr int RADIX_MAX_BITS = 9;
 static constexpr int RADIX_MAX = 1 << RADIX_MAX_BITS;
 static constexpr int OS_MAX_PASSES_VK = 5;		// {slot : <= 24 | bin : 10} = <= 34 bits in digits of <= 8 bits
-static constexpr int TD_MERGE_CTAS_PER_SM = 5, TD_MERGE_MAX_SMS = 192;	// bins_merge_kernel grid (4 warps per CTA)
+static constexpr int TD_MERGE_CTAS_PER_SM = 5, TD_MERGE_MAX_SMS = 192;	// bins_merge_kernel grid (<= 4 warps per CTA)
 
 // every launcher returns the number of kernel launches it issued
 int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks, cudaStream_t s);

@@ -92,7 +92,7 @@ __global__ void fold_hll_kernel(DevState st, const uint32_t *__restrict__ offs, 
 	l_hll[i] = acc;
 }
 
-static constexpr int MG_WARPS = 2;		// 2 x 14.3 KB of scratch: static shared memory
+static constexpr int MG_WARPS = 2;		// 2 x 17.8 KB of scratch: static shared memory
 
 // one warp per logical service: fold member digests one after the other (member order = slot order of the map call)
 __global__ void __launch_bounds__(MG_WARPS * 32) fold_td_kernel(DevState st, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ members,

@@ -30,8 +30,9 @@ struct TdWorkT				// per warp; NMAX = 2 x TD_CAP: 9.7 KB
 	unsigned long long	pref[NMAX + 1];			// ... and exclusive weight prefix: weight of item i = pref[i+1] - pref[i]
 	uint16_t		bounds[TD_CAP + 2];
 	uint16_t		nxt[NMAX];
+	double			src[NMAX];			// the means of both input lists, staged for the rank searches
 };
-using TdWork = TdWorkT<2 * TD_CAP>;			// shared memory: two lists of up to TD_CAP centroids
+using TdWork = TdWorkT<2 * TD_CAP>;			// shared memory (13.8 KB): two lists of together up to 2 x TD_CAP centroids
 using TdWorkBig = TdWorkT<1120>;			// global scratch: TD_CAP old centroids + up to NBINS (848) items of a batch
 struct TdScratch : TdWork		// + an accumulator list for the folds of the merge step: 14.3 KB
 {
@@ -49,17 +50,24 @@ __device__ __forceinline__ uint32_t warp_merge_compress(Work &S, const Centroid 
 	const uint32_t nm = na + nb;
 	constexpr int IPL = Work::NMAX / 32;		// merged items per lane
 
+	// rank of every item in the merged list = own index + number of items of the other list in front of it. The searches probe the
+	// other list ~log2(n) times each: the means of both lists are staged in S.src first (one coalesced read per list) so that the
+	// probes hit the work area (shared memory on the usual path) instead of global memory.
+	double *am = S.src, *bm = S.src + na;
+	for (uint32_t j = lane; j < na; j += 32) am[j] = a[j].mean;
+	for (uint32_t j = lane; j < nb; j += 32) bm[j] = b[j].mean;
+	__syncwarp();
 	for (uint32_t j = lane; j < na; j += 32) {
-		const Centroid c = a[j];
-		uint32_t lo = 0, hi = nb;			// # of b with mean < c.mean
-		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (b[mid].mean < c.mean) lo = mid + 1; else hi = mid; }
-		S.mean[j + lo] = c.mean; S.pref[j + lo + 1] = c.weight;
+		const double m = am[j];
+		uint32_t lo = 0, hi = nb;			// # of b with mean < m
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (bm[mid] < m) lo = mid + 1; else hi = mid; }
+		S.mean[j + lo] = m; S.pref[j + lo + 1] = a[j].weight;
 	}
 	for (uint32_t j = lane; j < nb; j += 32) {
-		const Centroid c = b[j];
-		uint32_t lo = 0, hi = na;			// # of a with mean <= c.mean
-		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid].mean <= c.mean) lo = mid + 1; else hi = mid; }
-		S.mean[j + lo] = c.mean; S.pref[j + lo + 1] = c.weight;
+		const double m = bm[j];
+		uint32_t lo = 0, hi = na;			// # of a with mean <= m
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (am[mid] <= m) lo = mid + 1; else hi = mid; }
+		S.mean[j + lo] = m; S.pref[j + lo + 1] = b[j].weight;
 	}
 	__syncwarp();
 

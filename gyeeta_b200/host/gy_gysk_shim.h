@@ -4,6 +4,7 @@
 //     MCONN_HANDLER::partha_tcp_conn_info     server/gy_mconnhdlr.h:2091   (definition gy_mconnhdlr.cc:9052)
 //     MCONN_HANDLER::partha_aggr_task_state   server/gy_mconnhdlr.h:2098   (definition gy_mconnhdlr.cc:9959)
 //     MCONN_HANDLER::partha_listener_state    server/gy_mconnhdlr.h:2129   (definition gy_mconnhdlr.cc:10993)
+//     MCONN_HANDLER::handle_partha_active_conns server/gy_mconnhdlr.h:2155 (definition gy_mconnhdlr.cc:7705)
 // and forward the record batch to the B200 engine through the C ABI of include/gysketch.h. The template parameters
 // stand for the reference's own types (std::shared_ptr<PARTHA_INFO>, comm::TCP_CONN_NOTIFY, POOL_ALLOC_ARRAY, PGConnPool) so
 // that this header compiles both inside gy_mconnhdlr.cc (with the real types) and stand-alone in this repository's tests (with
@@ -54,6 +55,40 @@ public :
 	{
 		if (isdummycall) return true;
 		return forward(partha_shr, GYSK_NOTIFY_LISTENER_STATE, const_cast<ListenerStateNotify *>(plist), nitems, pendptr);
+	}
+
+	// bool handle_partha_active_conns(const std::shared_ptr<PARTHA_INFO> &, const comm::ACTIVE_CONN_STATS *, int nitems, uint8_t *pendptr,
+	//                                 POOL_ALLOC_ARRAY *, PGConnPool &)
+	template <typename ParthaInfo, typename ActiveConnStats, typename PoolArr, typename DbPool>
+	bool handle_partha_active_conns(const std::shared_ptr<ParthaInfo> & partha_shr, const ActiveConnStats *pconn, int nitems, uint8_t *pendptr,
+			PoolArr * /*pthrpoolarr*/, DbPool & /*dbpool*/) noexcept
+	{
+		return forward(partha_shr, GYSK_NOTIFY_ACTIVE_CONN_STATS, const_cast<ActiveConnStats *>(pconn), nitems, pendptr);
+	}
+
+	// the lifted per-sample paths (partha built with -DGYSK_RAW_FORWARD ships its perf-buffer pages unreduced): the callbacks of
+	// GY_EBPF::tcp_response_ipv4/ipv6_thread and tcp_conn_ipv4/ipv6_thread (partha/gy_ebpf_bpf.cc:181-199,316-323) ->
+	// TCP_SOCK_HANDLER::handle_ipv4_resp_event / handle_ipv6_resp_event / handle_ipv4_conn_event / handle_ipv6_conn_event
+	template <typename ParthaInfo, typename RespEvent>
+	bool handle_resp_events(const std::shared_ptr<ParthaInfo> & partha_shr, const RespEvent *pevents, uint32_t n) noexcept
+	{
+		static_assert(sizeof(RespEvent) == 24 || sizeof(RespEvent) == 64, "tcp_ipv4_resp_event_t / tcp_ipv6_resp_event_t");
+		return partha_shr && 0 == gysk_ingest_raw(engine_, partha_traits<ParthaInfo>::machine_id(*partha_shr), partha_traits<ParthaInfo>::host_index(*partha_shr),
+				sizeof(RespEvent) == 24 ? GYSK_RAW_TCP_IPV4_RESP : GYSK_RAW_TCP_IPV6_RESP, pevents, n);
+	}
+	template <typename ParthaInfo, typename ConnEvent>
+	bool handle_conn_events(const std::shared_ptr<ParthaInfo> & partha_shr, const ConnEvent *pevents, uint32_t n) noexcept
+	{
+		static_assert(sizeof(ConnEvent) == 72 || sizeof(ConnEvent) == 96, "tcp_ipv4_event_t / tcp_ipv6_event_t");
+		return partha_shr && 0 == gysk_ingest_raw(engine_, partha_traits<ParthaInfo>::machine_id(*partha_shr), partha_traits<ParthaInfo>::host_index(*partha_shr),
+				sizeof(ConnEvent) == 72 ? GYSK_RAW_TCP_IPV4_EVENT : GYSK_RAW_TCP_IPV6_EVENT, pevents, n);
+	}
+	// SVC_INFO_CAP::upd_stats_on_req (common/gy_proto_parser.cc:2678): a run of API_TRAN records (variable stride) of one host
+	template <typename ParthaInfo>
+	bool handle_api_trans(const std::shared_ptr<ParthaInfo> & partha_shr, const void *ptran, uint32_t n) noexcept
+	{
+		return partha_shr && 0 == gysk_ingest_raw(engine_, partha_traits<ParthaInfo>::machine_id(*partha_shr), partha_traits<ParthaInfo>::host_index(*partha_shr),
+				GYSK_RAW_API_TRAN, ptran, n);
 	}
 
 	// the 5-s reducer tick (TCP_SOCK_HANDLER::listener_stats_update cadence, common/gy_socket_stat.cc:3898)

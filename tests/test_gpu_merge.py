@@ -4,6 +4,8 @@ merged logical-service answers must equal (integers: bit-exact) a single engine 
 import numpy as np
 import pytest
 
+from tests.util import td_p99_tolerance
+
 from gyeeta_b200 import dist as gd
 from gyeeta_b200 import engine as ge
 from gyeeta_b200 import synth
@@ -87,7 +89,7 @@ def test_two_shards_merge_to_global_answers():
         if x["td_count"] >= 2000:
             for f in ("td_p50_us", "td_p95_us"):
                 assert abs(x[f] - z[f]) / z[f] < 0.01, (f, x[f], z[f])
-            assert abs(x["td_p99_us"] - z["td_p99_us"]) / z["td_p99_us"] < 0.03
+            assert abs(x["td_p99_us"] - z["td_p99_us"]) / z["td_p99_us"] < max(0.03, 2 * td_p99_tolerance(x["td_count"]))   # two clusterings of a few thousand samples
             assert x["td_p50_us"] == y["td_p50_us"]                                          # both ranks computed the same merge
             nonzero += 1
     assert nonzero >= 3

@@ -28,14 +28,15 @@ def test_shim_compiles_and_fails_loudly_without_gpu():
         pytest.skip("GPU present: covered by the gpu test")
     r = subprocess.run([_build()], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "rc=-19" in r.stdout and "handlers: 0 0 0" in r.stdout and "tick: 0 deletes: 0 records: -1" in r.stdout
+    assert "rc=-19" in r.stdout and "handlers: 0 0 0" in r.stdout and "more handlers: 0 0 0" in r.stdout and "tick: 0 deletes: 0 records: -1" in r.stdout
 
 
 @pytest.mark.gpu
 def test_shim_end_to_end_on_gpu():
     r = subprocess.run([_build()], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "handlers: 1 1 1" in r.stdout and "found=1 nconns_5s=1 kbytes_5s=4" in r.stdout
+    assert "handlers: 1 1 1" in r.stdout and "more handlers: 1 1 1" in r.stdout and "found=1 nconns_5s=1 kbytes_5s=4" in r.stdout
+    assert "nconns_active=3 active_kbytes=10 max_rtt=1.5" in r.stdout and "stats: resp=1 tcp=3 svcs=3" in r.stdout
 
 
 def test_wire_validators_accept_and_reject_like_the_reference():
