@@ -1310,9 +1310,8 @@ static uint32_t host_td_compress(const double *means, const uint64_t *w, uint32_
 	uint32_t nout = 0, cur = 0;
 	double csum = 0.0;
 	for (uint32_t i = 0; i < n; ++i) {
-		const double q = (double)pref / (double)W;
-		uint32_t lo = 0, hi = delta - 1;
-		while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (qtab[mid] <= q) lo = mid; else hi = mid - 1; }
+		uint32_t lo = cur;
+		while (lo + 1 < delta && (uint64_t)(qtab[lo + 1] * (double)W) <= pref) ++lo;		// cell j starts at weight (uint64) (q_j W)
 		if (i && lo != cur) { om[nout] = csum / (double)cw; ow[nout++] = cw; cw = 0; csum = 0.0; }
 		cur = lo;
 		csum += means[i] * (double)w[i]; cw += w[i]; pref += w[i];

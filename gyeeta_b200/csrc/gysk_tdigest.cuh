@@ -7,20 +7,14 @@
 namespace gysk {
 
 // K_1 scale function of the merging t-digest (Dunning), k spanning [-delta/2, delta/2]: k(q) = delta/pi asin(2q - 1). The compress
-// step works on the FIXED unit grid of k: cell j = [q_j, q_j+1) with q_j = q(k = -delta/2 + j) = (sin(pi (j/delta - 1/2)) + 1)/2, and
-// an item of the merged list (sorted by mean, exclusive weight prefix P_i, total W) belongs to the cell that holds its start
-// position P_i / W. All items of one cell become one cluster: at most delta clusters, each no wider than one unit of k plus its
-// last item — the t-digest size bound — with no data-dependent chain: every item finds its cell on its own (one division, one
-// binary search in a table of delta + 1 doubles), which is what makes the step parallel. The table is computed once on the host
-// (libm sin, same expression in oracle/gysk_oracle.c) so that device, host and oracle compare against identical doubles.
+// step works on the FIXED unit grid of k: cell j = [q_j, q_j+1) with q_j = q(k = -delta/2 + j) = (sin(pi (j/delta - 1/2)) + 1)/2. In
+// weight units cell j starts at T_j = (uint64) (q_j * W) (W = total weight, one double multiply, truncated), and an item of the
+// merged list (sorted by mean, exclusive weight prefix P_i) belongs to the cell that holds its START: T_j <= P_i < T_j+1. All items
+// of one cell become one cluster: at most delta clusters, each no wider than one unit of k plus its last item — the t-digest size
+// bound — with no data-dependent chain: the first item of cell j is lower_bound(P, T_j), delta independent binary searches over
+// the prefix array, which is what makes the step parallel. q_j is computed once on the host (libm sin, same expression in
+// oracle/gysk_oracle.c) so that device, host and oracle use identical doubles.
 struct TdParams { const double *qtab; uint32_t delta; uint32_t pad; };		// qtab[0 .. delta], device memory
-
-__device__ __forceinline__ uint32_t td_cell(double q, const TdParams &P)
-{
-	uint32_t lo = 0, hi = P.delta - 1;		// largest j in [0, delta - 1] with qtab[j] <= q
-	while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (__ldg(P.qtab + mid) <= q) lo = mid; else hi = mid - 1; }
-	return lo;
-}
 
 template <int NMAX_>
 struct TdWorkT				// per warp; NMAX = 2 x TD_CAP: 9.7 KB
@@ -87,22 +81,25 @@ __device__ __forceinline__ uint32_t warp_merge_compress(Work &S, const Centroid 
 	}
 	__syncwarp();
 
-	// cell of every item (independent of each other), then the cluster boundaries = the places where the cell changes
+	// first item of every cell: lower_bound of the cell's start weight in the prefix array; empty cells drop out
 	uint32_t nout = 0;
 	if (nm) {
-		const double W = (double)S.pref[nm];
-		for (uint32_t i = lane; i < nm; i += 32) S.nxt[i] = (uint16_t)td_cell(__ddiv_rn((double)S.pref[i], W), P);
+		const unsigned long long Wt = S.pref[nm];
+		const double W = (double)Wt;
+		for (uint32_t j = lane; j <= P.delta; j += 32) {
+			const unsigned long long T = j == P.delta ? Wt : (unsigned long long)__dmul_rn(__ldg(P.qtab + j), W);
+			uint32_t lo = 0, hi = nm;			// first i in [0, nm) with pref[i] >= T, nm if none
+			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.pref[mid] < T) lo = mid + 1; else hi = mid; }
+			S.nxt[j] = (uint16_t)lo;
+		}
 		__syncwarp();
-		// lane owns IPL consecutive items: count its cluster starts, scan over the lanes, write the starts in order
-		const uint32_t i0 = lane * IPL, i1 = i0 + IPL < nm ? i0 + IPL : nm;
-		uint32_t nh = 0;
-		for (uint32_t i = i0; i < i1; ++i) nh += (i == 0 || S.nxt[i] != S.nxt[i - 1]) ? 1u : 0u;
-		uint32_t incl = nh;
-#pragma unroll
-		for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
-		nout = __shfl_sync(0xffffffffu, incl, 31);
-		uint32_t r = incl - nh;
-		for (uint32_t i = i0; i < i1; ++i) if (i == 0 || S.nxt[i] != S.nxt[i - 1]) S.bounds[r++] = (uint16_t)i;
+		for (uint32_t j0 = 0; j0 < P.delta; j0 += 32) {
+			const uint32_t j = j0 + lane;
+			const bool ne = j < P.delta && S.nxt[j + 1] > S.nxt[j];
+			const uint32_t m = __ballot_sync(0xffffffffu, ne);
+			if (ne) S.bounds[nout + __popc(m & ((1u << lane) - 1u))] = S.nxt[j];
+			nout += __popc(m);
+		}
 		if (lane == 0) S.bounds[nout] = (uint16_t)nm;
 		__syncwarp();
 	}

@@ -342,8 +342,8 @@ double gyo_hll_estimate(const uint8_t *regs, uint32_t p)
  * Only IEEE +,-,*,/ and sqrt, each rounded on its own, in this order — the CUDA path performs the identical sequence, so both
  * produce the same bits. */
 /* The compress step works on the FIXED unit grid of k: cell j = [q_j, q_j+1), q_j = q(k = -delta/2 + j) = (sin(pi (j/delta - 1/2)) + 1)/2.
- * An item of the merged list (sorted by mean; exclusive weight prefix P_i, total W) belongs to the cell that holds its start
- * position P_i / W; all items of one cell become one cluster: at most delta clusters, each no wider than one unit of k plus its
+ * In weight units cell j starts at T_j = (uint64) (q_j * W); an item of the merged list (sorted by mean; exclusive weight prefix
+ * P_i, total W) belongs to the cell that holds its start: T_j <= P_i < T_j+1; all items of one cell become one cluster: at most delta clusters, each no wider than one unit of k plus its
  * last item (the t-digest size bound), and no data-dependent chain — every item finds its cell on its own. The table is
  * computed with libm by this expression here and in gyeeta_b200/csrc/gysk_engine.cu (same host, same bits). */
 #define GYO_TD_MAX_DELTA	256
@@ -355,27 +355,20 @@ static void td_qtab(double delta, double *qtab /* [delta + 1] */)
 	qtab[0] = 0.0; qtab[d] = 1.0;
 }
 
-static uint32_t td_cell(double q, const double *qtab, uint32_t d)
-{
-	uint32_t lo = 0, hi = d - 1;		/* largest j in [0, d - 1] with qtab[j] <= q */
-
-	while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (qtab[mid] <= q) lo = mid; else hi = mid - 1; }
-	return lo;
-}
-
 void gyo_td_init(gyo_tdigest *t)
 {
 	memset(t, 0, sizeof(*t));
 	t->minv = INFINITY; t->maxv = -INFINITY;
 }
 
-/* cluster mean = sum(mean * weight) / sum(weight), accumulated in double in input order */
+/* cell j starts at weight T_j = (uint64) (q_j * W); an item belongs to the cell that holds its start position (exclusive prefix);
+ * cluster mean = sum(mean * weight) / sum(weight), accumulated in double in input order */
 uint32_t gyo_td_compress(const gyo_centroid *in, uint32_t n, double delta, gyo_centroid *out, uint32_t cap)
 {
 	double		qtab[GYO_TD_MAX_DELTA + 1];
 	const uint32_t	d = (uint32_t)delta;
 	uint64_t	W = 0, pref = 0, cw = 0;
-	uint32_t	nout = 0, cur = 0;
+	uint32_t	nout = 0, cell = 0;
 	double		csum = 0.0;
 
 	if (!n) return 0;
@@ -383,14 +376,16 @@ uint32_t gyo_td_compress(const gyo_centroid *in, uint32_t n, double delta, gyo_c
 	for (uint32_t i = 0; i < n; ++i) W += in[i].weight;
 
 	for (uint32_t i = 0; i < n; ++i) {
-		uint32_t cell = td_cell((double)pref / (double)W, qtab, d);
+		uint32_t c = cell;
 
-		if (i && cell != cur) {
+		/* advance to the cell that holds pref: T_c <= pref < T_c+1 (T_d = W) */
+		while (c + 1 < d && (uint64_t)(qtab[c + 1] * (double)W) <= pref) ++c;
+		if (i && c != cell) {
 			if (nout < cap) { out[nout].mean = csum / (double)cw; out[nout].weight = cw; }
 			nout++;
 			cw = 0; csum = 0.0;
 		}
-		cur = cell;
+		cell = c;
 		csum += in[i].mean * (double)in[i].weight;
 		cw += in[i].weight;
 		pref += in[i].weight;
