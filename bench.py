@@ -4,14 +4,18 @@
     python bench.py --gpus N --steps K --warmup W            # product arm
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on this box's host cores
 
-One STEP = one pass of the hot path over one batch of synthetic events (ingest kernel + radix sort + t-digest update,
-plus the sketch-merge collective when N > 1). Workload = BASELINE.json configs[2] ("100 M mixed TCP/syscall events,
+One STEP = one pass of the hot path over one batch of synthetic events: ingest_kernel (count-min / HLL / process histograms + one
+sort key per response sample), 4 one-sweep radix passes, runs_mark / runs_sum (per-(service, bin) counts and sums), bins_merge
+(histogram cells + t-digest merge). N > 1 adds ONE sketch merge (gysk_merge_global: fold + one NCCL group + merge-compress) per timed
+window, as a deployment merges once per query window. Workload = BASELINE.json configs[2] ("100 M mixed TCP/syscall events,
 100 K services, t-digest p50/p95/p99 on 1xB200"), the largest single-GPU configuration: per rank EVENTS_PER_STEP
 events of the 70/20/10 RESP/TCP/TASK mix over 100 K services (weak scaling: each rank ingests its own host shard).
 
 `value`  : whole-job events/s with the batch already resident in HBM (device timed, CUDA events, max over ranks).
 `e2e`    : same metric through the C-ABI call a user makes with HOST (page-locked) buffers: H2D inside the timed region,
-           plus a device->host read of per-service summaries.
+           plus a device->host read of per-service summaries. Records = the packed per-kind structs of include/gysketch.h
+           (18.4 B/event); `e2e_event32` = 32-byte canonical records; `e2e_wire` = 16 host threads calling gysk_ingest_msg /
+           gysk_ingest_raw with TCP_CONN_NOTIFY / AGGR_TASK_STATE_NOTIFY messages and raw tcp_ipv4_resp_event_t arrays.
 `roofline`: dominant kernel, algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json.
 `cpu_baseline`: the CPU oracle port (all host cores, events pre-sharded by host) on a bounded sample of the same stream.
 """
@@ -37,7 +41,7 @@ ZIPF_S = 1.05
 # algorithmic bytes per event, SURVEY.md §8(d): RESP 98 = 32 + 32 + 16 + 18(t-digest), TCP 98, TASK 128.
 # split per kernel group: the ingest kernel reads every record (32 B) and carries the TCP (count-min + HLL) and TASK state; the
 # RESP histogram cell (32 B), per-service counter (16 B) and t-digest share (18 B) are produced from the sorted keys by the
-# sort + t-digest chain.
+# sort + runs + bins-merge chain.
 BYTES_INGEST = 0.7 * 32 + 0.2 * 98 + 0.1 * 128                      # 54.8 B / event
 BYTES_TDIGEST = 0.7 * (32 + 16 + 18)                                  # 46.2 B / event
 BYTES_EVENT = BYTES_INGEST + BYTES_TDIGEST                            # 101.0 B / event
@@ -110,6 +114,117 @@ def gen_events_gpu(torch, n, seed, rank, world, dev):
         out[off: off + m, 1] = w1
         out[off: off + m, 2] = value | (host << 32)
         out[off: off + m, 3] = 1 | (etype << 32)
+    return out
+
+
+def pack_kinds_pinned(torch, ev):
+    """the events of one batch as three page-locked arrays of packed per-kind records (gysk_resp16 / gysk_tcp24 / gysk_task24):
+    -> [(raw kind, pinned int64 tensor, record count)]"""
+    from gyeeta_b200 import engine as ge
+    w0, w1, w2, w3 = ev[:, 0], ev[:, 1], ev[:, 2], ev[:, 3]
+    etype = (w3 >> 32) & 0xFFFF
+    host = (w2 >> 32) & 0xFFFF
+    val = w2 & 0xFFFFFFFF
+    out = []
+    m = etype == 5
+    r = torch.stack([w0[m], val[m] | (host[m] << 32) | ((w1[m] & 0xFF) << 48)], dim=1)             # flags byte 0
+    out.append((ge.RAW_RESP16, r))
+    m = (etype >= 1) & (etype <= 4)
+    t = torch.stack([w0[m], w1[m], val[m] | (host[m] << 32) | (etype[m] << 48)], dim=1)
+    out.append((ge.RAW_TCP24, t))
+    m = etype == 6
+    k = torch.stack([w0[m], val[m] | ((w1[m] & 0xFFFFFFFF) << 32), ((w1[m] >> 32) & 0xFFFFFFFF) | (host[m] << 32)], dim=1)
+    out.append((ge.RAW_TASK24, k))
+    res = []
+    for kind, d in out:
+        h = torch.empty(d.shape, dtype=torch.int64, pin_memory=True)
+        h.copy_(d)
+        res.append((kind, h, d.shape[0]))
+    return res
+
+
+def wire_leg(ge, local, nthreads=16, rounds_per_thread=8, total_events=32_000_000):
+    """e2e_wire: the boundary call itself under madhava's threading model — `nthreads` host threads (the L2 handle_l2_misc threads,
+    server/gy_mconnhdlr.cc:5128), each handing the engine what its partha connections deliver: whole COMM_HEADER messages of
+    TCP_CONN_NOTIFY (280-byte records, 2048 per message = MAX_NUM_CONNS) and AGGR_TASK_STATE_NOTIFY (72-byte records) through
+    gysk_ingest_msg, and arrays of the 24-byte tcp_ipv4_resp_event_t through gysk_ingest_raw, 70 / 20 / 10 by events. Pageable host
+    memory (messages arrive in socket buffers); validation, 280 B -> 32 B compaction on the calling thread, per-thread page-locked
+    staging, H2D and the device batches are all inside the wall-clock region; one query + sync closes it."""
+    from gyeeta_b200 import synth, wire
+    rng = np.random.default_rng(77)
+    svc_ids = rank_service_ids(0)
+    task_ids = synth.splitmix64(np.arange(1, NTASK + 1, dtype=np.uint64) + np.uint64(1 << 40))
+    cdf_s, cdf_t = synth.zipf_cdf(NSVC, ZIPF_S), synth.zipf_cdf(NTASK, ZIPF_S)
+    NT, NK, NR = 2048, 1024, 7168                       # records per round: TCP_CONN, AGGR_TASK_STATE, resp events
+    per_round = NT + NK + NR
+    eng = ge.Engine(device=local, max_svcs=1 << 18, max_tasks=1 << 15, max_batch=1 << 24)
+    work = []
+    for t in range(nthreads):
+        rounds = []
+        for _r in range(rounds_per_thread):
+            srank = np.minimum(np.searchsorted(cdf_s, rng.random(NT)), NSVC - 1)
+            c = np.zeros(NT, dtype=wire.TCP_CONN)
+            c["ser_glob_id"] = svc_ids[srank]
+            c["cli_task_aggr_id"] = synth.splitmix64(rng.integers(1, NCLIENTS, NT).astype(np.uint64) + np.uint64(1 << 48))
+            closed = rng.random(NT) < 0.5
+            c["is_accept"] = 1
+            c["tusec_start"] = 1_700_000_000_000_000
+            c["tusec_close"] = np.where(closed, 1_700_000_005_000_000, 0)
+            c["bytes_sent"] = np.exp(rng.normal(np.log(4096.0), 2.0, NT)).astype(np.uint64)
+            c["bytes_rcvd"] = np.exp(rng.normal(np.log(1024.0), 2.0, NT)).astype(np.uint64)
+            k = np.zeros(NK, dtype=wire.TASK)
+            k["aggr_task_id"] = task_ids[np.minimum(np.searchsorted(cdf_t, rng.random(NK)), NTASK - 1)]
+            k["total_cpu_pct"] = rng.random(NK) * 400.0
+            k["cpu_delay_msec"] = np.minimum(np.exp(rng.normal(np.log(30.0), 2.0, NK)), 1e5).astype(np.uint32)
+            k["blkio_delay_msec"] = np.minimum(np.exp(rng.normal(np.log(5.0), 2.5, NK)), 1e5).astype(np.uint32)
+            rr = np.minimum(np.searchsorted(cdf_s, rng.random(NR)), NSVC - 1)
+            r = np.zeros(NR, dtype=wire.RESP4)
+            r["saddr"] = 0x0A000000 + rr
+            r["daddr"] = rng.integers(1, 1 << 32, NR, dtype=np.uint64).astype(np.uint32)
+            r["netns"] = 4026531840
+            r["sport"] = 0x901F                           # htons(8080)
+            r["dport"] = rng.integers(1024, 65536, NR).astype(np.uint16)
+            r["lrcvtime"] = rng.integers(0, 1 << 31, NR).astype(np.uint32)
+            r["lsndtime"] = r["lrcvtime"] + np.minimum(np.exp(rng.normal(np.log(2.0), 1.5, NR)), 9.0e5).astype(np.uint32)
+            rounds.append((wire.build_msg_fixed(ge.NOTIFY_TCP_CONN, c), wire.build_msg_fixed(ge.NOTIFY_AGGR_TASK_STATE, k), r))
+        work.append(rounds)
+    iters = max(1, total_events // (nthreads * per_round))
+    L, h, hid = eng.L, eng.h, eng._host_id
+    errs = []
+
+    def producer(t, count):
+        rounds = work[t]
+        for i in range(count):
+            m1, m2, r = rounds[i % len(rounds)]
+            rc = L.gysk_ingest_msg(h, hid, t, m1.ctypes.data_as(C.c_void_p), len(m1))
+            rc |= L.gysk_ingest_msg(h, hid, t, m2.ctypes.data_as(C.c_void_p), len(m2))
+            rc |= L.gysk_ingest_raw(h, hid, t, ge.RAW_TCP_IPV4_RESP, r.ctypes.data_as(C.c_void_p), len(r))
+            if rc:
+                errs.append(rc)
+                return
+
+    def run(count):
+        thr = [threading.Thread(target=producer, args=(t, count)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        for x in thr:
+            x.start()
+        for x in thr:
+            x.join()
+        eng.query_svcs(svc_ids[:256])
+        eng.sync()
+        return time.perf_counter() - t0
+
+    run(max(1, iters // 8))                              # registers the ids, faults the stages in
+    sec = run(iters)
+    nev = nthreads * iters * per_round
+    st = eng.stats()
+    out = {"value": nev / sec, "unit": "events/s", "threads": nthreads, "events": nev, "sec": sec, "errors": len(errs),
+           "wire_bytes_per_event": (len(work[0][0][0]) + len(work[0][0][1]) + work[0][0][2].nbytes) / per_round,
+           "h2d_bytes_per_event": (NT * 32 + NK * 32 + NR * 24) / per_round,
+           "what": "16 threads x (TCP_CONN_NOTIFY 2048 x 280 B + AGGR_TASK_STATE_NOTIFY 1024 x 72 B via gysk_ingest_msg, 7168 x 24 B "
+                   "tcp_ipv4_resp_event_t via gysk_ingest_raw), pageable memory, host wall clock incl. final query + sync",
+           "wire_msgs_ok": st.get("wire_msgs_ok")}
+    eng.close()
     return out
 
 
@@ -214,31 +329,45 @@ def shard_owner(ev_np, nthreads, mode):
     return host_thr[ev_np["host_idx"]]
 
 
+class CpuPort:
+    """the oracle port on `nthreads` host threads: events pre-sharded (shard_owner), one engine per thread, ids registered and state
+    faulted in by an untimed first pass; timed() = one pass of every thread over its shard (gyo_bench_ingest, oracle/gysk_oracle.c)"""
+
+    def __init__(self, ev_np, nthreads, mode="host"):
+        from oracle import pyoracle as po
+        self.L = po.lib()
+        owner = shard_owner(ev_np, nthreads, mode)
+        order = np.argsort(owner, kind="stable")
+        cuts = np.searchsorted(owner[order], np.arange(1, nthreads))
+        self.shards = [np.ascontiguousarray(a) for a in np.split(ev_np[order], cuts)]
+        self.engines = [po.OracleEngine(max_svcs=NSVC + 16, max_tasks=NTASK + 16) for _ in range(nthreads)]
+        self.nthreads, self.n = nthreads, len(ev_np)
+        self.eh = (C.c_void_p * nthreads)(*[e.h for e in self.engines])
+        self.sp = (C.c_void_p * nthreads)(*[s.ctypes.data for s in self.shards])
+        self.cn = (C.c_uint64 * nthreads)(*[len(s) for s in self.shards])
+        self.largest_shard_frac = float(max(len(s) for s in self.shards)) / max(1, self.n)
+        self.timed()
+
+    def timed(self):
+        return self.L.gyo_bench_ingest(self.eh, self.sp, self.cn, self.nthreads, 1 << 22)
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+
 def cpu_port_rate(ev_np, nthreads, mode="host", repeat=1):
-    from oracle import pyoracle as po
-    L = po.lib()
-    owner = shard_owner(ev_np, nthreads, mode)
-    order = np.argsort(owner, kind="stable")
-    cuts = np.searchsorted(owner[order], np.arange(1, nthreads))
-    shards = [np.ascontiguousarray(a) for a in np.split(ev_np[order], cuts)]
-    engines = [po.OracleEngine(max_svcs=NSVC + 16, max_tasks=NTASK + 16) for _ in range(nthreads)]
-    eh = (C.c_void_p * nthreads)(*[e.h for e in engines])
-    sp = (C.c_void_p * nthreads)(*[s.ctypes.data for s in shards])
-    cn = (C.c_uint64 * nthreads)(*[len(s) for s in shards])
-    L.gyo_bench_ingest(eh, sp, cn, nthreads, 1 << 22)          # untimed pass: registers every id, faults the state in
-    best = None
-    for _ in range(repeat):
-        sec = L.gyo_bench_ingest(eh, sp, cn, nthreads, 1 << 22)
-        best = sec if best is None else min(best, sec)
-    for e in engines:
-        e.close()
-    return len(ev_np) / best, best, float(max(len(s) for s in shards)) / max(1, len(ev_np))
+    cp = CpuPort(ev_np, nthreads, mode)
+    best = min(cp.timed() for _ in range(repeat))
+    frac = cp.largest_shard_frac
+    cp.close()
+    return len(ev_np) / best, best, frac
 
 
 def cpu_arm_report(ev_np, ncores):
     """1-thread and N-thread rates of the CPU port under the three shardings, and the reference's own add_data loop"""
     from oracle import pyoracle as po
-    one = ev_np[: max(1, len(ev_np) // 8)]
+    one = ev_np[: max(1, min(len(ev_np), max(len(ev_np) // 4, 1_000_000)))]
     r1, s1, _ = cpu_port_rate(one, 1)
     out = {"threads_1": {"events_per_s": r1, "sample_events": len(one)}}
     for mode in ("host", "balanced", "svc"):
@@ -270,13 +399,13 @@ def run_reference(args):
     n = int(min(args.cpu_sample, args.events))
     rng = np.random.default_rng(3)
     ev = synth.gen_mixed(rng, n, NSVC, ntask=NTASK, zipf_s=ZIPF_S, nhosts=NHOSTS, nclients=NCLIENTS)
-    rates = []
-    for i in range(args.warmup + args.steps):
-        r, sec, _ = cpu_port_rate(ev, ncores)
-        if i >= args.warmup:
-            rates.append((r, sec))
-    rate = float(np.mean([r for r, _ in rates]))
-    ms = float(np.mean([s for _, s in rates])) * 1e3
+    cp = CpuPort(ev, ncores)
+    for _ in range(args.warmup):
+        cp.timed()
+    secs = [cp.timed() for _ in range(args.steps)]
+    cp.close()
+    rate = n * len(secs) / float(np.sum(secs))
+    ms = float(np.mean(secs)) * 1e3
     detail = cpu_arm_report(ev, ncores)
     print(json.dumps({
         "impl": "reference", "metric": "events/sec aggregated", "value": rate, "unit": "events/s", "n_gpus": args.gpus,
@@ -400,35 +529,57 @@ def main():
     value = world * n * args.steps / (max_ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI, H2D in the timed region + D2H of summaries --------------------------
-    e2e = None
+    # headline `e2e`: the packed per-kind records (gysk_resp16 / gysk_tcp24 / gysk_task24, include/gysketch.h) a feeder that knows the
+    # kind of a batch ships: 18.4 B/event on this mix; expanded on the device. `e2e_event32`: the same events as 32-byte canonical
+    # records through gysk_ingest_pinned (round 1's path).
+    e2e = e2e32 = None
     if not args.no_e2e:
+        qids = ev_dev[:4096, 0].cpu().numpy().view(np.uint64)[:256].copy()
+
+        def timed_e2e(step_fn, h2d_bytes):
+            for _ in range(max(1, args.warmup // 2)):
+                step_fn()
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_fn()
+            merge_step()
+            eng.sync()
+            torch.cuda.synchronize()
+            w1 = time.perf_counter()
+            te = torch.tensor([w1 - w0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return {"value": world * n * args.steps / float(te.item()), "unit": "events/s",
+                    "h2d_bytes_per_step": int(h2d_bytes + len(qids) * 8), "d2h_bytes_per_step": int(len(qids) * C.sizeof(ge.SvcSummary)),
+                    "timed_with": "host wall clock around the C-ABI calls incl. final sync (max over ranks)"}
+
+        packed = [pack_kinds_pinned(torch, e_) for e_ in ev_devs]
+        torch.cuda.synchronize()
+
+        def step_packed():
+            for kind, arr, cnt in packed[step_no[0] % NB]:
+                eng.ingest_raw_ptr(kind, arr.data_ptr(), cnt)
+            step_no[0] += 1
+            return eng.query_svcs(qids)         # syncs, copies the summaries device -> host
+
+        e2e = timed_e2e(step_packed, sum(arr.numel() * 8 for _k, arr, _c in packed[0]))
+        e2e["records"] = "gysk_resp16 / gysk_tcp24 / gysk_task24 via gysk_ingest_raw, page-locked, decoded on the device"
+        e2e["bytes_per_event"] = e2e["h2d_bytes_per_step"] / n
+        del packed
+
         hosts = [torch.empty((n, 4), dtype=torch.int64, pin_memory=True) for _ in range(NB)]
         for b in range(NB):
             hosts[b].copy_(ev_devs[b])
         torch.cuda.synchronize()
-        qids = ev_dev[:4096, 0].cpu().numpy().view(np.uint64)[:256].copy()
 
-        def step_e2e():
+        def step_e2e32():
             eng.ingest_pinned_ptr(hosts[step_no[0] % NB].data_ptr(), n)
             step_no[0] += 1
-            return eng.query_svcs(qids)         # syncs, copies the summaries device -> host
+            return eng.query_svcs(qids)
 
-        for _ in range(max(1, args.warmup // 2)):
-            step_e2e()
-        barrier()
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        merge_step()
-        eng.sync()
-        torch.cuda.synchronize()
-        w1 = time.perf_counter()
-        te = torch.tensor([w1 - w0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * args.steps / float(te.item()), "unit": "events/s",
-               "h2d_bytes_per_step": int(n * 32 + len(qids) * 8), "d2h_bytes_per_step": int(len(qids) * 3400),
-               "timed_with": "host wall clock around the C-ABI calls incl. final sync (max over ranks)"}
+        e2e32 = timed_e2e(step_e2e32, n * 32)
+        e2e32["records"] = "32-byte gysk_event via gysk_ingest_pinned"
         del hosts
 
     # ---- accuracy: t-digest p99 vs exact on the hottest services --------------------------------------------------
@@ -439,7 +590,7 @@ def main():
         u, cnt = torch.unique(w0col[:2_000_000][is_resp[:2_000_000]], return_counts=True)
         order = torch.argsort(cnt, descending=True)
         hot = torch.cat([u[order[:4]], u[order[40:44]], u[order[400:404]]])
-        errs = []
+        rows = []
         for sid in hot.tolist():
             vals = torch.cat([(e_[:, 2][(e_[:, 0] == sid) & (((e_[:, 3] >> 32) & 0xFFFF) == 5)] & 0xFFFFFFFF) for e_ in ev_devs]).double()
             if vals.numel() < 10_000:
@@ -448,23 +599,39 @@ def main():
             ex = torch.quantile(vals[: 16_000_000], torch.tensor([0.5, 0.95, 0.99], device=dev, dtype=torch.float64),
                                 interpolation="lower").cpu().numpy()
             got = eng.quantiles(sid & 0xFFFFFFFFFFFFFFFF, [0.5, 0.95, 0.99])
-            errs.append(np.abs(got - ex) / ex)
-        if errs:
-            e = np.max(np.array(errs), axis=0)
-            acc = {"services_checked": len(errs), "max_rel_err_p50": float(e[0]), "max_rel_err_p95": float(e[1]),
-                   "max_rel_err_p99": float(e[2]), "against": "exact sorted quantile of the same samples"}
+            rows.append((int(vals.numel()), np.abs(got - ex) / ex))
+        if rows:
+            # by sample count: the exact p99 of n draws is itself an order statistic with relative 1-sigma noise
+            # ~ 0.5 % x sqrt(47000 / n) on this log-normal (sigma 1.5) stream, so the small classes measure that noise, the hot one the digest
+            acc = {"against": "exact sorted quantile of the same samples", "classes": {}}
+            for name, lo, hi in (("n_ge_1M", 1_000_000, 1 << 62), ("n_100K_1M", 100_000, 1_000_000), ("n_10K_100K", 10_000, 100_000)):
+                sel = [r for r in rows if lo <= r[0] < hi]
+                if not sel:
+                    continue
+                e = np.max(np.array([r[1] for r in sel]), axis=0)
+                nmin = min(r[0] for r in sel)
+                acc["classes"][name] = {"services": len(sel), "min_samples": nmin, "max_rel_err_p50": float(e[0]), "max_rel_err_p95": float(e[1]),
+                                        "max_rel_err_p99": float(e[2]), "p99_order_statistic_noise_1sigma": float(0.005 * np.sqrt(47000.0 / nmin))}
+            e = np.max(np.array([r[1] for r in rows]), axis=0)
+            acc.update({"services_checked": len(rows), "max_rel_err_p50": float(e[0]), "max_rel_err_p95": float(e[1]), "max_rel_err_p99": float(e[2])})
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    wire = None
+    if not args.no_e2e and world == 1:
+        del ev_devs[1:]
+        torch.cuda.empty_cache()
+        wire = wire_leg(ge, local)
+
     peak, peak_src = measured_peak_gbs()
     nev_total = n * args.steps
     roof = []
     traffic = ncu_traffic_per_event()
     for name, key, ms, bpe in (("ingest_kernel", "ingest_kernel", ms_ing, BYTES_INGEST),
-                               ("sort + histogram/t-digest chain (os_hist/os_pass/td_*)", "chain", ms_td, BYTES_TDIGEST)):
+                               ("sort + runs + bins-merge chain (os_pass x4, runs_mark, runs_sum, bins_merge)", "chain", ms_td, BYTES_TDIGEST)):
         if ms > 0:
             ach = nev_total * bpe / (ms * 1e-3) / 1e9
             tr = traffic.get(key, {}).get("dram_bytes_per_event")
@@ -473,7 +640,7 @@ def main():
                          "algorithmic_bytes_per_launch": bpe * n, "ms_per_launch": ms / max(nb, 1),
                          "ms_total": ms, "launch_groups": nb, "algorithmic_bytes_per_event": bpe, "peak_source": peak_src})
     # `roofline` = the dominant SINGLE kernel: ingest_kernel is one launch per device batch and holds the largest share of any
-    # individual kernel (profiles/r01_launches_*.csv); the sort + t-digest chain is 10 launches of 6 kernels
+    # individual kernel (profiles/r02_launches_*.csv); the chain is 7 launches of 4 kernels
     roof.sort(key=lambda r: 0 if r["kernel"] == "ingest_kernel" else 1)
     whole = nev_total * BYTES_EVENT / (max_ms * 1e-3) / 1e9
 
@@ -483,21 +650,21 @@ def main():
         ns = int(min(args.cpu_sample, n))
         ev_np = ev_dev[:ns].cpu().numpy().view(np.uint8).reshape(-1).view(ge.EVENT_DTYPE)
         r, sec, frac = cpu_port_rate(ev_np, ncores)
-        r1, _s1, _ = cpu_port_rate(ev_np[: ns // 8], 1)
+        r1, _s1, _ = cpu_port_rate(ev_np[: max(ns // 4, min(ns, 1_000_000))], 1)
         cpu = {"value": r, "unit": "events/s", "cores": ncores, "kind": "port", "cpu_model": cpu_model(), "one_thread_events_per_s": r1,
                "largest_shard_frac": frac,
                "sample": f"first {ns} events of rank 0's stream, pre-sharded by host over {ncores} threads ({sec:.1f} s); "
-                         "1-thread rate on an eighth of it; more shardings in `bench.py --impl reference`"}
+                         "1-thread rate on a quarter of it; more shardings in `bench.py --impl reference`"}
 
     out = {
         "metric": "events/sec aggregated", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "configs[2]: 100M mixed RESP/TCP/TASK (70/20/10) events, 100K services, count-min + HLL + "
-                               "fixed-bucket histograms + t-digest(100)", "events_per_step_per_gpu": n, "services": NSVC,
+                               "fixed-bucket histograms + t-digest(200)", "events_per_step_per_gpu": n, "services": NSVC,
                    "zipf_s": ZIPF_S, "max_batch": args.max_batch, "stage_batch": args.stage_batch, "parallelism": f"host-shard x{world}",
                    "l2": "inputs (3.2 GB/step) larger than L2, no flush needed"},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": e2e, "e2e_event32": e2e32, "e2e_wire": wire, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof[0] if roof else None, "roofline_other": roof[1:] or None,
         "roofline_whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
                                 "algorithmic_bytes_per_event": BYTES_EVENT},

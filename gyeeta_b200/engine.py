@@ -218,6 +218,10 @@ class Engine:
     def ingest_raw(self, kind, buf, n, host_idx=0):
         self._chk(self.L.gysk_ingest_raw(self.h, self._host_id, host_idx, kind, _p(buf), n))
 
+    def ingest_raw_ptr(self, kind, ptr, n, host_idx=0):
+        """ingest_raw on a raw host address (e.g. a page-locked torch tensor's data_ptr())"""
+        self._chk(self.L.gysk_ingest_raw(self.h, self._host_id, host_idx, kind, C.c_void_p(ptr), n))
+
     def ingest_pinned_ptr(self, ptr, n):
         self._chk(self.L.gysk_ingest_pinned(self.h, C.c_void_p(ptr), n))
 

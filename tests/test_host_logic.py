@@ -83,6 +83,7 @@ def test_host_helpers_match_oracle():
 
 
 def test_tdigest_oracle_properties():
+    from tests.util import td_p99_tolerance
     rng = np.random.default_rng(4)
     for sigma, n in ((1.2, 200_000), (1.5, 50_000), (0.5, 10_000)):
         x = np.minimum(np.exp(rng.normal(np.log(2000.0), sigma, n)), 9e8).astype(np.uint32)
@@ -99,7 +100,7 @@ def test_tdigest_oracle_properties():
             for td in (tb, tc):
                 g = po.td_quantile(td, q)
                 assert abs(np.searchsorted(xs, g) / n - q) < 0.002, (sigma, n, q)          # rank error: what a t-digest bounds
-                assert abs(g - ex) / ex < 0.01, (sigma, n, q, g, ex)
+                assert abs(g - ex) / ex < (0.01 if q < 0.99 else td_p99_tolerance(n)), (sigma, n, q, g, ex)
     # tiny inputs
     t = po.td_add(po.td_new(), np.array([7], dtype=np.uint32))
     assert t.n == 1 and po.td_quantile(t, 0.5) == 7.0
