@@ -1,4 +1,5 @@
-"""Builds gyeeta_b200/libgysketch.so (in-tree, so it travels to the GPU box) with nvcc for sm_100a only."""
+"""Builds gyeeta_b200/libgysketch.so (in-tree, so it travels to the GPU box) with nvcc for sm_100a only, and libgysynth.so, the
+on-device synthetic event source the sustained-stream run uses (a bench utility, not linked into the product library)."""
 import os
 import subprocess
 import sys
@@ -6,6 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgysketch.so")
+SYNTH_LIB = os.path.join(HERE, "libgysynth.so")
 SOURCES = ["gysk_kernels.cu", "gysk_engine.cu", "gysk_merge.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
@@ -19,7 +21,7 @@ def _nvcc():
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(SYNTH_LIB):
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(HERE), "include", "gysketch.h")]
@@ -45,6 +47,12 @@ def build(force=False, verbose=False):
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc link failed")
+    cmd = [_nvcc()] + flags + ["-shared", os.path.join(CSRC, "gysk_synth.cu"), "-o", SYNTH_LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed for gysk_synth.cu")
     return LIB
 
 

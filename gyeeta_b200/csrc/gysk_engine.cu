@@ -798,7 +798,7 @@ int ingest_raw_bulk(gysk_engine *e, ThreadStage *ts, uint32_t kind, uint32_t hos
 	cudaPointerAttributes pa {};
 	const bool pinned = cudaPointerGetAttributes(&pa, src) == cudaSuccess && pa.type == cudaMemoryTypeHost;
 	cudaGetLastError();
-	int rc = flush_stage(e, ts);				// keep this thread's arrival order
+	int rc = pinned ? 0 : flush_stage(e, ts);		// pageable input bounces through the thread's chunk: hand over what it holds first
 	if (rc) return rc;
 	const uint64_t per_stage = (uint64_t)ts->cap * sizeof(gysk_event) / stride;		// records per thread chunk (as bytes)
 	while (n) {
@@ -948,10 +948,10 @@ int gysk_ingest(gysk_engine *e, const uint8_t host_id[16], uint32_t host_idx, ui
 		}
 		// partha_aggr_task_state (gy_mconnhdlr.cc:9959) -> MAGGR_TASK::set_local_task_state (gy_msocket.h:1009)
 		{
-			std::lock_guard<std::mutex> lk(e->host_mtx);
 			HostTaskTopn tt;						// the seven per-host rankings of :10012-10079
 			const T *q = pone;
 			for (uint32_t i = 0; i < nevents && (const uint8_t *)q < pend; ++i, q = (const T *)((const uint8_t *)q + q->get_elem_size())) tt.offer(*q);
+			std::lock_guard<std::mutex> lk(e->host_mtx);
 			e->host_task_topn[host_idx] = std::move(tt);
 		}
 		for (uint32_t i = 0; i < nevents && (const uint8_t *)pone < pend; ++i, pone = (T *)((uint8_t *)pone + pone->get_elem_size())) {

@@ -22,7 +22,9 @@ namespace gysk {
 constexpr int NBUF = 2;
 constexpr uint32_t QCHUNK = 1024;		// ids per query kernel launch
 constexpr uint32_t THREAD_STAGE_EVENTS = 1u << 16;	// events per per-thread staging chunk (2 MB page-locked, two chunks per thread)
-constexpr uint32_t RAW_BULK_MIN = 4096;		// raw fixed-stride batches from this size on are expanded on the device
+constexpr uint32_t RAW_BULK_MIN = 16384;		// raw fixed-stride batches from this size on are expanded on the device: below it the
+							// per-call copy / launch / event calls under the engine mutex cost more than the
+							// ~20 ns per record of expanding on the calling thread (bench.py e2e_wire)
 
 // a calling thread's page-locked staging: filled without the engine mutex (see gysk_engine.cu)
 struct ThreadStage

@@ -175,9 +175,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 // The kernel is WARP-AUTONOMOUS: no block barrier anywhere in the event loop. A warp takes a chunk of 32 x EPT events and
 //   (1) decodes them fully converged: 2 x 128-bit load per event, shard filter, id -> slot lookup with the first table probe
 //       of all EPT events in flight together;
-//   (2) RESP (70 % of the stream) is finished on the spot — two 64-bit REDs into the service's value bin (the samples of a
-//       service spread over up to ~400 bins, so even the hottest service puts no more than a few thousand REDs per batch on one
-//       address: no warp aggregation needed), the CONN_BITMAP bit and the batch extremes only when they would change;
+//   (2) a RESP sample (70 % of the stream) becomes ONE 64-bit sort key {slot : 24 | value bin : 10 | usec : 30} in the warp's key
+//       queue (ballot + popc placement; the queue leaves as a coalesced run, and its digits are counted into the CTA's radix
+//       histograms on the way out); beside it only what would change state: the batch extremes of the slot and the CONN_BITMAP bit,
+//       each behind a load so that the atomic is issued only while the value still moves;
 //   (3) TCP / TASK events join one of the warp's two private shared-memory queues (ballot + popc, no atomics: the queue
 //       lengths are warp-uniform registers) and a queue is drained only in whole multiples of 32 entries, so every lane works in
 //       every iteration whatever the mix of the stream is: TCP = two lookup2 hashes per flow key -> four count-min REDs + HLL

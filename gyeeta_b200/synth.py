@@ -85,3 +85,41 @@ def gen_resp_config1(rng, n=1_000_000, svc_id=None):
 def shard_by_host(ev, world):
     """the partition of SURVEY.md §8e: events of host_idx % world == rank belong to rank"""
     return [ev[(ev["host_idx"] % world) == r] for r in range(world)]
+
+
+class DeviceSynth:
+    """ctypes binding of libgysynth.so (csrc/gysk_synth.cu): the on-device Philox event source of the sustained-stream run. The id and
+    CDF arrays are torch device tensors kept alive by this object; fill() enqueues one generator launch on `stream`."""
+
+    def __init__(self, torch, dev, svc_ids, task_ids, zipf_s, rank=0, world=1, nhosts=4096, nclients=1_000_000, seed=1,
+                 tail_start=0, churn_groups=0, churn_epoch=1, resp_mu=float(np.log(2000.0)), resp_sigma=1.5):
+        import ctypes as C
+        import os
+
+        class Params(C.Structure):
+            _fields_ = [("seed", C.c_uint64), ("rank", C.c_uint32), ("world", C.c_uint32), ("nsvc", C.c_uint32), ("ntask", C.c_uint32),
+                        ("d_svc_ids", C.c_void_p), ("d_task_ids", C.c_void_p), ("d_cdf_svc", C.c_void_p), ("d_cdf_task", C.c_void_p),
+                        ("nhosts", C.c_uint32), ("nclients", C.c_uint32), ("tsec", C.c_uint32), ("tail_start", C.c_uint32),
+                        ("churn_groups", C.c_uint32), ("churn_epoch", C.c_uint32), ("window", C.c_uint32), ("resp_mu", C.c_float),
+                        ("resp_sigma", C.c_float)]
+
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgysynth.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `python -m gyeeta_b200.build`")
+        self.L = C.CDLL(path)
+        self.L.gysyn_fill.restype = C.c_int
+        self.L.gysyn_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(Params), C.c_void_p]
+        self._keep = [torch.from_numpy(np.ascontiguousarray(svc_ids).view(np.int64)).to(dev),
+                      torch.from_numpy(np.ascontiguousarray(task_ids).view(np.int64)).to(dev),
+                      torch.from_numpy(zipf_cdf(len(svc_ids), zipf_s)).to(dev), torch.from_numpy(zipf_cdf(len(task_ids), zipf_s)).to(dev)]
+        self.p = Params(seed=seed, rank=rank, world=world, nsvc=len(svc_ids), ntask=len(task_ids), d_svc_ids=self._keep[0].data_ptr(),
+                        d_task_ids=self._keep[1].data_ptr(), d_cdf_svc=self._keep[2].data_ptr(), d_cdf_task=self._keep[3].data_ptr(),
+                        nhosts=nhosts, nclients=nclients, tsec=0, tail_start=tail_start, churn_groups=churn_groups, churn_epoch=churn_epoch,
+                        window=0, resp_mu=resp_mu, resp_sigma=resp_sigma)
+        self._C = C
+
+    def fill(self, dptr, n, counter_base, stream, window=0, tsec=0):
+        self.p.window, self.p.tsec = window, tsec
+        rc = self.L.gysyn_fill(self._C.c_void_p(dptr), n, counter_base, self._C.byref(self.p), self._C.c_void_p(stream))
+        if rc:
+            raise RuntimeError(f"gysyn_fill failed: {rc}")

@@ -148,6 +148,27 @@ def test_flush_window_roll_and_summary():
     assert eng.query_svcs([424242])[0]["found"] == 0
 
 
+def test_window_membership_is_by_arrival():
+    """the tsec contract (include/gysketch.h): a sample belongs to the window that is open when it ARRIVES, whatever its own tsec says —
+    the reference stamps response samples with time(nullptr) of their processing (common/gy_socket_stat.cc:1560-1579) and
+    gysk_flush(tsec) closes the window. Events stamped in the past, the future and with garbage land in the window they were fed in."""
+    rng = np.random.default_rng(9)
+    eng, orc = make_pair(max_svcs=256, max_tasks=16, max_batch=1 << 14)
+    evs = []
+    for w, stamp in enumerate((lambda n: np.zeros(n), lambda n: np.full(n, 10_000), lambda n: rng.integers(0, 1 << 32, n))):
+        ev = synth.gen_mixed(rng, 20_000, 50, ntask=8, nhosts=4, nclients=1000)
+        ev["tsec"] = stamp(len(ev)).astype(np.uint32)
+        ev["tsec"][ev["type"] == ge.EV_ACTIVE] = 0
+        evs.append(ev)
+        feed_both(eng, orc, ev, 1 << 14)
+        eng.flush(100 + 5 * w); orc.flush(100 + 5 * w)
+        resp = ev[ev["type"] == ge.EV_RESP]
+        for id_ in np.unique(resp["svc_id"])[:20]:
+            assert_hist_equal(eng, orc, int(id_), ge.HIST_RESP_LAST)
+            _cells, total, _mx = eng.export_hist(int(id_), ge.HIST_RESP_LAST)
+            assert total == int((resp["svc_id"] == id_).sum())               # exactly this window's samples, none of the others'
+
+
 def test_tdigest_quantiles_config1_shape():
     """config 1 shape (scaled to 200 K samples here; the 1 M version lives in the full-size test): one service"""
     rng = np.random.default_rng(1)
