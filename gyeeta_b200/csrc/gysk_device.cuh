@@ -42,6 +42,9 @@ struct alignas(8) SlotAux { unsigned long long act_cur, act_last, err_cur, err_l
 
 // per-service scratch of the batch being ingested: exact extremes of its RESP samples and "has bins to merge"
 struct alignas(16) SlotBatch { uint32_t minv, maxv, touched, pad; };
+// listener state of the last evaluated window (gysk_state.cuh): curr_state_, curr_issue_, issue_bit_hist_, high_resp_bit_hist_ and the
+// active connection count last reported by an ACTIVE_CONN_STATS record (kept between the 15-s reports)
+struct alignas(8) SlotState { uint8_t state, issue, issue_bits, high_bits; uint32_t nconn_active; };
 
 // per-service t-digest header
 struct TdHead { unsigned long long total; double minv, maxv; uint32_t n; uint32_t pad; };

@@ -5,6 +5,7 @@
 // server/gy_mconnhdlr.h:424-431) and hand full batches to the device: H2D on a copy stream, kernels on the compute
 // stream, two device event buffers so the copy of batch k+1 overlaps the kernels of batch k.
 #include "gysk_engine.h"
+#include "gysk_state.cuh"
 #include "gysk_wire.h"
 
 using namespace gysk;
@@ -363,6 +364,7 @@ void gysk::summarize_raw(const gysk_engine *e, const SvcRaw &r, uint64_t id, gys
 	o.nconns_active = (uint32_t)r.aux.act_last; o.active_kbytes = (uint32_t)(r.aux.act_last >> 32);
 	memcpy(&o.max_rtt_msec, &r.aux.rtt_last, 4);
 	o.cli_errors = (uint32_t)r.aux.err_last; o.ser_errors = (uint32_t)(r.aux.err_last >> 32);
+	o.curr_state = r.sst.state; o.curr_issue = r.sst.issue; o.issue_bit_hist = r.sst.issue_bits; o.high_resp_bit_hist = r.sst.high_bits;
 
 	double means[TD_CAP]; uint64_t w[TD_CAP];
 	const uint32_t nc = std::min<uint32_t>(r.td.n, TD_CAP);
@@ -515,6 +517,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 		st.td.qtab = d_q; st.td.delta = cfg.td_compression; st.td.pad = 0;
 	}
 	A(dalloc(e, &st.slot_batch, ns)); A(dalloc(e, &st.slot_aux, ns));
+	A(dalloc(e, &st.qps_hist, ns * HIST_CELLS)); A(dalloc(e, &st.act_hist, ns * HIST_CELLS)); A(dalloc(e, &st.slot_state, ns));
 	SortTemp &tmp = e->tmp;
 	const size_t nsort = std::max<size_t>(std::max<size_t>(ns, nt) + 1, cfg.max_batch);	// RESP keys of a batch; the top-N sorts rank services / tasks
 	tmp.max_tiles = (uint32_t)((nsort + SORT_TILE - 1) / SORT_TILE);
@@ -1090,7 +1093,7 @@ int gysk_flush(gysk_engine *e, uint32_t tsec)
 		e->kernel_launches += launch_rebuild_table(e->st, e->cfg.max_svcs, e->stream);
 		e->tombstones = 0; e->insert_fail_seen = e->h_evict_fail;
 	}
-	e->kernel_launches += launch_flush(e->st, e->cfg.max_svcs, planes[0], planes[1], tsec, e->cfg.idle_evict_secs, e->stream);
+	e->kernel_launches += launch_flush(e->st, e->cfg.max_svcs, planes[0], planes[1], tsec, e->cfg.idle_evict_secs, live_mask(e, 0), live_mask(e, 1), e->stream);
 	e->kernel_launches += launch_task_flush(e->st, e->cfg.max_tasks, e->stream);
 	if (e->cfg.idle_evict_secs) {
 		// count + ids travel to the host behind the kernels; nobody waits for them here
@@ -1145,7 +1148,7 @@ int gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial ou
 	CHECK_ENGINE(e);
 	if (!out || !total || !maxv) return GYSK_ERR_INVAL;
 	if (which >= GYSK_HIST_TASK_CPU_PCT && which <= GYSK_HIST_TASK_BLKIO_DELAY) return gysk_export_task_hist(e, id, which, out, total, maxv);
-	if (which > GYSK_HIST_RESP_5DAY) return GYSK_ERR_INVAL;
+	if (which > GYSK_HIST_ACTIVE_CONN) return GYSK_ERR_INVAL;
 	if (which < 0) return GYSK_ERR_INVAL;
 	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
@@ -1159,6 +1162,8 @@ int gysk_export_hist(gysk_engine *e, uint64_t id, int which, gysk_hist_serial ou
 		if (*total == 0) *maxv = INT64_MIN;
 		return GYSK_OK;
 	}
+	if (which == GYSK_HIST_QPS) { hist_from_cells(r.qps, 15, out, total, maxv, true); return GYSK_OK; }
+	if (which == GYSK_HIST_ACTIVE_CONN) { hist_from_cells(r.act, 14, out, total, maxv, true); return GYSK_OK; }
 	hist_from_cells(which == GYSK_HIST_RESP_CUR ? r.cur : (which == GYSK_HIST_RESP_LAST ? r.last : r.all), 15, out, total, maxv, false);
 	return GYSK_OK;
 }
@@ -1266,7 +1271,8 @@ int gysk_encode_listener_state(const gysk_svc_summary *sums, uint32_t n, void *b
 		r.nconns_active_ = sums[i].nconns_active;
 		r.ser_errors_ = sums[i].ser_errors; r.cli_errors_ = sums[i].cli_errors;
 		r.curr_kbytes_inbound_ = sums[i].kbytes_5s;
-		r.curr_state_ = sums[i].nqrys_5s ? 2 : 0;
+		r.curr_state_ = sums[i].curr_state; r.curr_issue_ = sums[i].curr_issue;		// the device-side get_curr_state of the window
+		r.issue_bit_hist_ = sums[i].issue_bit_hist; r.high_resp_bit_hist_ = sums[i].high_resp_bit_hist;
 		memcpy(p + (size_t)k * sizeof(r), &r, sizeof(r));
 		k++;
 	}
@@ -1367,7 +1373,7 @@ int gysk_query_flows(gysk_engine *e, const uint64_t *keys, uint32_t n, int last_
 int gysk_topn_svcs(gysk_engine *e, int metric, int32_t host_idx, uint32_t n, gysk_topn_entry *out, uint32_t *nout)
 {
 	CHECK_ENGINE(e);
-	if (!out || !nout || n == 0 || n > 64 || metric < GYSK_TOPN_QPS || metric > GYSK_TOPN_NET) return GYSK_ERR_INVAL;
+	if (!out || !nout || n == 0 || n > 64 || metric < GYSK_TOPN_QPS || metric > GYSK_TOPN_ISSUE) return GYSK_ERR_INVAL;
 	GYSK_ENTER(e);
 	CU(e, cudaSetDevice(e->dev));
 	int rc = sync_locked(e);
@@ -1531,6 +1537,14 @@ int gysk_hist_percentiles(int cls, int t_is_int, const gysk_hist_serial *stats, 
 		int64_t v = bucket_max_threshold(d, !!t_is_int, i < nb ? i : (total_count > 0 ? nb : 0));
 		out[n] = t_is_int ? (int64_t)(int32_t)v : v;
 	}
+	return GYSK_OK;
+}
+
+// TCP_LISTENER::get_curr_state for a caller that has the inputs from outside the path (process status, host state, dependencies)
+int gysk_classify_listener(const gysk_listener_state_in *in, uint8_t *high_resp_bit_hist, uint8_t *state, uint8_t *issue)
+{
+	if (!in || !high_resp_bit_hist || !state || !issue) return GYSK_ERR_INVAL;
+	classify_listener(*in, *high_resp_bit_hist, *state, *issue);
 	return GYSK_OK;
 }
 

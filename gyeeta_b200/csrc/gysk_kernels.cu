@@ -12,6 +12,7 @@
 //   flush_kernel         5-s window roll                                               common/gy_socket_stat.cc:3898
 //   gather_* / query_*   read side
 #include "gysk_kernels.cuh"
+#include "gysk_state.cuh"
 
 #include <cfloat>
 #include <climits>
@@ -48,6 +49,9 @@ __global__ void init_state_kernel(DevState st, uint32_t max_svcs, uint32_t max_t
 		st.td_head[i].minv = INFINITY;
 		st.td_head[i].maxv = -INFINITY;
 		st.slot_batch[i].minv = 0xFFFFFFFFu;
+		st.qps_hist[(size_t)i * HIST_CELLS + HIST_MAX_CELL].sum = INT_MIN;	// GY_HISTOGRAM<int, ...>: numeric_limits<int>::min()
+		st.act_hist[(size_t)i * HIST_CELLS + HIST_MAX_CELL].sum = INT_MIN;
+		st.slot_state[i] = SlotState {GYSK_STATE_OK, GYSK_ISSUE_NONE, 0, 0, 0};
 	}
 	if (i < max_tasks) {
 		for (int h = 0; h < 3; ++h) st.task_hist[((size_t)i * 3 + h) * HIST_CELLS + HIST_MAX_CELL].sum = LLONG_MIN;
@@ -931,7 +935,7 @@ __global__ void __launch_bounds__(256) runs_sum_kernel(const unsigned long long 
 	}
 }
 
-static constexpr int TD_WARPS = 3;		// 3 x 13.8 KB of work area per CTA (static shared memory)
+static constexpr int TD_WARPS = 3;		// warps (= services in flight) per CTA; work area per warp: 10.4 KB at 384 entries, 13.8 KB at 512
 
 // One warp per touched service. Its runs become the batch's items {mean = exact usec sum / samples, weight = samples} — in value
 // order, because the bin index is monotone — and every run adds {samples, exact msec sum} to its bucket of the window histogram:
@@ -939,12 +943,17 @@ static constexpr int TD_WARPS = 3;		// 3 x 13.8 KB of work area per CTA (static 
 // the batch's exact extremes. The items are then merged with the old centroids (old first on equal means) and the greedy K_1
 // pass cuts the list to at most TD_CAP clusters (warp_merge_compress). Lists of up to 2 x TD_CAP entries work in shared memory;
 // longer ones (a first batch can fill several hundred bins) in the warp's L2-resident scratch — same code, same result.
+// SMEM_N = longest merged list (old centroids + batch items) that works in shared memory: the smaller the work area, the more
+// services a SM has in flight (the kernel is latency-bound: ~2 600 dependent warp instructions per service, ncu profiles/).
+template <int SMEM_N>
 __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, const uint32_t *__restrict__ touched, const unsigned long long *__restrict__ ntouched_p,
 		const RunRec *__restrict__ pool, const uint16_t *__restrict__ run_bin, const BatchSeg *__restrict__ segs,
 		Centroid *__restrict__ items_scratch /* [nwarps][NBINS] */, TdWorkBig *__restrict__ big_scratch /* [nwarps] */)
 {
-	__shared__ TdWork work[TD_WARPS];
-	__shared__ unsigned long long hcnt[TD_WARPS][16], hsum[TD_WARPS][16];
+	__shared__ TdWorkT<SMEM_N> work[TD_WARPS];
+	// window histogram of the service's batch: 32-bit shared-memory atomics (native; a 64-bit shared atomicAdd is a CAS loop). A bucket's
+	// sample count of one batch fits 32 bits (max_batch < 2^27); the msec sum is kept as {low word, carries + high words}
+	__shared__ uint32_t hcnt[TD_WARPS][16], hsum_lo[TD_WARPS][16], hsum_hi[TD_WARPS][16];
 	__shared__ uint16_t first_idx[16];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * TD_WARPS + wid, nwarps = gridDim.x * TD_WARPS;
@@ -966,7 +975,7 @@ __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, 
 		const BatchSeg seg = segs[slot];
 		const uint32_t nitems = seg.nruns - seg.run0;			// runs_mark_kernel left the END positions in nruns / nkeys
 		const uint32_t nsamples = seg.nkeys - seg.key0;
-		if (lane < 16) { hcnt[wid][lane] = 0; hsum[wid][lane] = 0; }
+		if (lane < 16) { hcnt[wid][lane] = 0; hsum_lo[wid][lane] = 0; hsum_hi[wid][lane] = 0; }
 		__syncwarp();
 		for (uint32_t j = lane; j < nitems; j += 32) {
 			const RunRec r = pool[seg.run0 + j];
@@ -977,8 +986,12 @@ __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, 
 			uint32_t bk = 0;
 #pragma unroll
 			for (int q = 1; q < 15; ++q) bk += bin >= first_idx[q];
-			atomicAdd(&hcnt[wid][bk], cnt);
-			atomicAdd(&hsum[wid][bk], (r.us - rem) / 1000ull);		// sum of (usec / 1000) over the run's samples
+			atomicAdd(&hcnt[wid][bk], (uint32_t)cnt);
+			const unsigned long long ms = (r.us - rem) / 1000ull;		// sum of (usec / 1000) over the run's samples
+			const uint32_t mlo = (uint32_t)ms, mhi = (uint32_t)(ms >> 32);
+			const uint32_t old = atomicAdd(&hsum_lo[wid][bk], mlo);
+			const uint32_t up = mhi + (old + mlo < old ? 1u : 0u);		// carry out of the low word
+			if (up) atomicAdd(&hsum_hi[wid][bk], up);
 		}
 		__syncwarp();
 		// nobody else touches this slot's window histogram while the batch is merged (same stream as the flush): plain updates
@@ -986,7 +999,7 @@ __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, 
 		if (lane < HIST_MAX_CELL) {
 			if (hcnt[wid][lane]) {
 				HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + lane;
-				c->count += hcnt[wid][lane]; c->sum += (long long)hsum[wid][lane];
+				c->count += hcnt[wid][lane]; c->sum += (long long)(((unsigned long long)hsum_hi[wid][lane] << 32) | hsum_lo[wid][lane]);
 			}
 		}
 		else if (lane == HIST_MAX_CELL) {
@@ -1000,7 +1013,7 @@ __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, 
 		TdHead head = st.td_head[slot];
 		Centroid *cent = st.td_cent + (size_t)slot * TD_CAP;
 		uint32_t nout;
-		if (head.n + nitems <= 2u * TD_CAP) nout = warp_merge_compress(work[wid], cent, head.n, items, nitems, cent, st.td);
+		if (head.n + nitems <= (uint32_t)SMEM_N) nout = warp_merge_compress(work[wid], cent, head.n, items, nitems, cent, st.td);
 		else nout = warp_merge_compress(big_scratch[gw], cent, head.n, items, nitems, cent, st.td);
 		if (lane == 0) {
 			head.n = nout;
@@ -1085,6 +1098,102 @@ __global__ void flush_kernel(DevState st, uint32_t nslots, HistCell *__restrict_
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The state decision of the 5-s reducer, one thread per service slot, right behind flush_kernel: what listener_stats_update does per
+// listener around get_curr_state (common/gy_socket_stat.cc:4111-4130 samples of qps_hist_ / active_conn_hist_, :4158-4173 connection
+// counts, :4222-4233 level statistics + get_curr_state, :4242-4272 issue_bit_hist_). A slot whose closing window held no event is
+// "stale" (:4098-4107): the reference leaves such a listener's state alone, and so does this kernel.
+// ---------------------------------------------------------------------------------------------------
+struct LevelStat { int64_t p95, p99, p25; uint64_t cnt, sum; double mean; };
+
+__device__ __forceinline__ LevelStat level_stat(const uint64_t *counts, uint64_t sum)
+{
+	LevelStat r;
+	uint64_t c = 0;
+	for (int b = 0; b < HIST_MAX_CELL; ++b) c += counts[b];
+	r.p95 = resp_bucket_value(hist_pct_bucket(counts, HIST_MAX_CELL, c, 95.0f), c);
+	r.p99 = resp_bucket_value(hist_pct_bucket(counts, HIST_MAX_CELL, c, 99.0f), c);
+	r.p25 = resp_bucket_value(hist_pct_bucket(counts, HIST_MAX_CELL, c, 25.0f), c);
+	r.cnt = c; r.sum = sum;
+	r.mean = (double)(long long)sum / (double)(c ? (long long)c : 1ll);		// TIME_HISTOGRAM::get_stats, gy_statistics.h:1358
+	return r;
+}
+
+__global__ void __launch_bounds__(128) state_kernel(DevState st, uint32_t nslots, uint32_t tsec, uint32_t live0, uint32_t live1)
+{
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= nslots || !st.slot_id[slot]) return;
+	if (st.slot_last_active[slot] != (tsec ? tsec : 1u)) return;			// stale window: state stays
+
+	const size_t base = (size_t)slot * HIST_CELLS;
+	uint64_t cnt[HIST_MAX_CELL];
+	uint64_t sum;
+	gysk_listener_state_in in;
+	memset(&in, 0, sizeof(in));
+
+	sum = 0;
+	for (int b = 0; b < HIST_MAX_CELL; ++b) { const HistCell c = st.hist_last[base + b]; cnt[b] = c.count; sum += (uint64_t)c.sum; }
+	const LevelStat s5 = level_stat(cnt, sum);
+	LevelStat lv[NLEVELS];
+	for (int l = 0; l < NLEVELS; ++l) {
+		const uint32_t live = l ? live1 : live0;
+		for (int b = 0; b < HIST_MAX_CELL; ++b) cnt[b] = 0;
+		sum = 0;
+		for (int k = 0; k < NSLOTS; ++k) {
+			if (!((live >> k) & 1u)) continue;
+			const HistCell *ring = st.hist_ring + (((size_t)l * NSLOTS + k) * nslots + slot) * HIST_CELLS;
+			for (int b = 0; b < HIST_MAX_CELL; ++b) { const HistCell c = ring[b]; cnt[b] += c.count; sum += (uint64_t)c.sum; }
+		}
+		lv[l] = level_stat(cnt, sum);
+	}
+	sum = 0;
+	for (int b = 0; b < HIST_MAX_CELL; ++b) { const HistCell c = st.hist_all[base + b]; cnt[b] = c.count; sum += (uint64_t)c.sum; }
+	const LevelStat sa = level_stat(cnt, sum);
+
+	in.r5p95 = s5.p95; in.r5p99 = s5.p99; in.nqrys_5s = s5.cnt; in.total_resp_msec = s5.sum; in.mean5 = s5.mean;
+	in.r300p95 = lv[0].p95; in.r300p99 = lv[0].p99; in.mean300 = lv[0].mean;
+	in.r5dp95 = lv[1].p95; in.r5dp99 = lv[1].p99; in.r5dp25 = lv[1].p25; in.tcount_5d = lv[1].cnt; in.mean5d = lv[1].mean;
+	in.rallp95 = sa.p95; in.rallp99 = sa.p99; in.meanall = sa.mean;
+
+	SlotState ss = st.slot_state[slot];
+	const SlotAux aux = st.slot_aux[slot];
+	in.last_qps_count = (int32_t)(s5.cnt / 5);
+	if ((uint32_t)aux.act_last) ss.nconn_active = (uint32_t)aux.act_last;		// an ACTIVE_CONN_STATS report arrived in this window
+
+	// GY_HISTOGRAM<int, ...>::add_data of the two per-window samples, then their p95 / p25
+	{
+		HistCell *q = st.qps_hist + base, *a = st.act_hist + base;
+		const int qv = in.last_qps_count, av = (int)ss.nconn_active;
+		const int qb = bucket_semi_log_lo(qv), ab = bucket_hash_1_3000(av);
+		q[qb].count += 1; q[qb].sum += qv; if ((long long)qv > q[HIST_MAX_CELL].sum) q[HIST_MAX_CELL].sum = qv;
+		a[ab].count += 1; a[ab].sum += av; if ((long long)av > a[HIST_MAX_CELL].sum) a[HIST_MAX_CELL].sum = av;
+		uint64_t tot = 0;
+		for (int b = 0; b < HIST_MAX_CELL; ++b) { cnt[b] = q[b].count; tot += cnt[b]; }
+		in.qps_p95 = qps_bucket_value(hist_pct_bucket(cnt, HIST_MAX_CELL, tot, 95.0f), tot);
+		in.qps_p25 = qps_bucket_value(hist_pct_bucket(cnt, HIST_MAX_CELL, tot, 25.0f), tot);
+		tot = 0;
+		for (int b = 0; b < HIST_MAX_CELL; ++b) { cnt[b] = b < 14 ? a[b].count : 0; tot += cnt[b]; }
+		in.act_p95 = act_bucket_value(hist_pct_bucket(cnt, 14, tot, 95.0f), tot);
+		in.act_p25 = act_bucket_value(hist_pct_bucket(cnt, 14, tot, 25.0f), tot);
+	}
+
+	in.nconn = (int32_t)ss.nconn_active;
+	in.curr_active_conn = in.nconn;
+	for (int b = 0; b < HIST_MAX_CELL; ++b) {
+		const int c = __popc(st.bm_last[base + b]);					// CONN_BITMAP::get_conn_breakup
+		in.nactive_conn_arr[b] = (uint8_t)c;
+		if (in.curr_active_conn < c) in.curr_active_conn = c;
+	}
+	in.ser_errors = (uint32_t)(aux.err_last >> 32);
+	const uint32_t first = st.slot_first_seen[slot];
+	const uint32_t age = tsec > first ? tsec - first : 0u;
+	in.secs_5d = age + 1u < 432000u ? age + 1u : 432000u;
+
+	classify_listener(in, ss.high_bits, ss.state, ss.issue);
+	apply_issue_history(age, in.ser_errors, ss.state, ss.issue, ss.issue_bits);
+	st.slot_state[slot] = ss;
+}
+
 // one CTA per evicted slot (grid-stride): the id's table entry becomes a tombstone, every per-slot array returns to its
 // just-created state and the slot number goes on the free stack for the next unknown id
 __global__ void __launch_bounds__(256) evict_kernel(DevState st, uint32_t max_svcs)
@@ -1105,6 +1214,7 @@ __global__ void __launch_bounds__(256) evict_kernel(DevState st, uint32_t max_sv
 			st.slot_id[slot] = 0; st.slot_host[slot] = 0; st.slot_first_seen[slot] = 0; st.slot_last_active[slot] = 0;
 			st.conn_cur[slot] = 0; st.conn_last[slot] = 0; st.conn_all_cnt[slot] = 0; st.conn_all_kb[slot] = 0;
 			st.slot_aux[slot] = SlotAux {0, 0, 0, 0, 0, 0};
+			st.slot_state[slot] = SlotState {GYSK_STATE_OK, GYSK_ISSUE_NONE, 0, 0, 0};
 			TdHead h; h.total = 0; h.minv = INFINITY; h.maxv = -INFINITY; h.n = 0; h.pad = 0;
 			st.td_head[slot] = h;
 			const int32_t f = atomicAdd(st.svc_tbl.free_n, 1);
@@ -1116,6 +1226,8 @@ __global__ void __launch_bounds__(256) evict_kernel(DevState st, uint32_t max_sv
 			const HistCell z {0, threadIdx.x == HIST_MAX_CELL ? LLONG_MIN : 0};
 			st.hist_cur[c] = z; st.hist_last[c] = z; st.hist_all[c] = z;
 			st.bm_cur[c] = 0; st.bm_last[c] = 0;
+			const HistCell zi {0, threadIdx.x == HIST_MAX_CELL ? (long long)INT_MIN : 0};
+			st.qps_hist[c] = zi; st.act_hist[c] = zi;
 			for (int pl = 0; pl < NLEVELS * NSLOTS; ++pl) st.hist_ring[((size_t)pl * max_svcs + slot) * HIST_CELLS + threadIdx.x] = HistCell {0, 0};
 		}
 		uint32_t *hw = reinterpret_cast<uint32_t *>(st.hll + ((size_t)slot << st.hll_p));
@@ -1182,7 +1294,9 @@ __global__ void __launch_bounds__(128) gather_svcs_kernel(DevState st, const uns
 		o.conn_all_cnt = st.conn_all_cnt[slot]; o.conn_all_kb = st.conn_all_kb[slot];
 		o.td = st.td_head[slot];
 		o.aux = st.slot_aux[slot];
+		o.sst = st.slot_state[slot];
 	}
+	if (lane < HIST_CELLS) { o.qps[lane] = st.qps_hist[(size_t)slot * HIST_CELLS + lane]; o.act[lane] = st.act_hist[(size_t)slot * HIST_CELLS + lane]; }
 	for (int i = lane; i < TD_CAP; i += 32) o.cent[i] = st.td_cent[(size_t)slot * TD_CAP + i];
 
 	hh[wid][lane] = 0; hh[wid][lane + 32] = 0;
@@ -1451,7 +1565,12 @@ int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint64_t n_event
 	runs_mark_kernel<<<div_up(n_events, RM_TILE), RM_THREADS, 0, s>>>(src, d_nkeys, tmp.tile_status, epoch, reinterpret_cast<RunRec *>(tmp.pool), tmp.run_bin,
 			tmp.chunk_run, reinterpret_cast<BatchSeg *>(tmp.segs), tmp.touched, d_ntouched, st.counters + CTR_NRUNS);
 	runs_sum_kernel<<<nsm * 8, 256, 0, s>>>(src, d_nkeys, tmp.chunk_run, reinterpret_cast<RunRec *>(tmp.pool));
-	bins_merge_kernel<<<std::min(nsm, TD_MERGE_MAX_SMS) * TD_MERGE_CTAS_PER_SM, TD_WARPS * 32, 0, s>>>(st, tmp.touched, d_ntouched,
+	// GYSK_MERGE_SMEM_N=512 selects the larger work area (A/B runs)
+	static const int merge_smem_n = []{ const char *e = getenv("GYSK_MERGE_SMEM_N"); return e && atoi(e) == 512 ? 512 : 384; }();
+	const int merge_ctas = std::min(nsm, TD_MERGE_MAX_SMS) * (merge_smem_n == 512 ? 5 : TD_MERGE_CTAS_PER_SM);
+	if (merge_smem_n == 512) bins_merge_kernel<512><<<merge_ctas, TD_WARPS * 32, 0, s>>>(st, tmp.touched, d_ntouched,
+			reinterpret_cast<const RunRec *>(tmp.pool), tmp.run_bin, reinterpret_cast<const BatchSeg *>(tmp.segs), tmp.items_scratch, tmp.big_scratch);
+	else bins_merge_kernel<384><<<merge_ctas, TD_WARPS * 32, 0, s>>>(st, tmp.touched, d_ntouched,
 			reinterpret_cast<const RunRec *>(tmp.pool), tmp.run_bin, reinterpret_cast<const BatchSeg *>(tmp.segs), tmp.items_scratch, tmp.big_scratch);
 	return launches + 3;
 }
@@ -1473,6 +1592,12 @@ __global__ void topn_score_kernel(DevState st, uint32_t nslots, int metric, int 
 			for (int b = 0; b < HIST_MAX_CELL; ++b) score += st.hist_last[(size_t)slot * HIST_CELLS + b].count;
 		}
 		else if (metric == GYSK_TOPN_CONNS) score = (uint32_t)st.conn_last[slot];
+		else if (metric == GYSK_TOPN_ISSUE) {
+			// ptopissue of partha_listener_state (gy_mconnhdlr.cc:11262-11271): listeners with curr_state_ > STATE_OK, worse state first
+			// (LISTEN_TOPN::is_comp_issue, gy_msocket.h:745; its tie-break, tasks_delay_usec_, is not on this path)
+			const SlotState ss = st.slot_state[slot];
+			score = ss.state > GYSK_STATE_OK && ss.state <= GYSK_STATE_DOWN ? ss.state : 0;
+		}
 		else score = st.conn_last[slot] >> 32;
 	}
 	if (score > 0xFFFFFFFFull) score = 0xFFFFFFFFull;
@@ -1563,14 +1688,16 @@ int launch_topn_tasks(const DevState &st, const SortTemp &tmp, uint32_t ntasks, 
 	return launches;
 }
 
-int launch_flush(const DevState &st, uint32_t nslots, HistCell *ring_plane0, HistCell *ring_plane1, uint32_t tsec, uint32_t idle_secs, cudaStream_t s)
+int launch_flush(const DevState &st, uint32_t nslots, HistCell *ring_plane0, HistCell *ring_plane1, uint32_t tsec, uint32_t idle_secs,
+		uint32_t live_mask0, uint32_t live_mask1, cudaStream_t s)
 {
 	if (!nslots) return 0;
 	cudaMemsetAsync(st.counters + CTR_NEVICT, 0, sizeof(unsigned long long), s);
 	flush_kernel<<<div_up((uint64_t)nslots * HIST_CELLS, 256), 256, 0, s>>>(st, nslots, ring_plane0, ring_plane1, tsec, idle_secs);
-	if (!idle_secs) return 1;
+	state_kernel<<<div_up(nslots, 128), 128, 0, s>>>(st, nslots, tsec, live_mask0, live_mask1);
+	if (!idle_secs) return 2;
 	evict_kernel<<<296, 256, 0, s>>>(st, nslots);		// grid-stride over the (device-side) eviction list
-	return 2;
+	return 3;
 }
 
 int launch_rebuild_table(const DevState &st, uint32_t max_svcs, cudaStream_t s)

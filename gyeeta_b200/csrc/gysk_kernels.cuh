@@ -24,6 +24,8 @@ struct DevState
 	uint32_t		*bm_cur, *bm_last;			// [max_svcs][16] CONN_BITMAP transposed: per bucket a mask over (client port & 31)
 	SlotBatch		*slot_batch;				// [max_svcs] exact extremes of the batch's RESP samples
 	SlotAux			*slot_aux;				// [max_svcs] active-conn roll-up, error counters
+	HistCell		*qps_hist, *act_hist;			// [max_svcs][16] TCP_LISTENER::qps_hist_ / active_conn_hist_: one sample per closed window
+	SlotState		*slot_state;				// [max_svcs] listener state of the last evaluated window
 	uint8_t			*hll;					// [max_svcs][1 << hll_p]
 	Centroid		*td_cent;				// [max_svcs][TD_CAP]
 	TdHead			*td_head;				// [max_svcs]
@@ -70,6 +72,8 @@ struct SvcRaw
 	uint32_t		hll_hist[64];
 	TdHead			td;
 	SlotAux			aux;
+	SlotState		sst;
+	HistCell		qps[HIST_CELLS], act[HIST_CELLS];
 	Centroid		cent[TD_CAP];
 };
 
@@ -87,7 +91,7 @@ static constexpr int SORT_TILE = 4096;		// keys per CTA tile in the radix passes
 static constexpr int RADIX_MAX_BITS = 9;
 static constexpr int RADIX_MAX = 1 << RADIX_MAX_BITS;
 static constexpr int OS_MAX_PASSES_VK = 5;		// {slot : <= 24 | bin : 10} = <= 34 bits in digits of <= 8 bits
-static constexpr int TD_MERGE_CTAS_PER_SM = 5, TD_MERGE_MAX_SMS = 192;	// bins_merge_kernel grid (<= 4 warps per CTA)
+static constexpr int TD_MERGE_CTAS_PER_SM = 7, TD_MERGE_MAX_SMS = 192;	// bins_merge_kernel grid (<= 4 warps per CTA)
 
 // every launcher returns the number of kernel launches it issued
 int launch_init_state(const DevState &st, uint32_t max_svcs, uint32_t max_tasks, cudaStream_t s);
@@ -99,7 +103,8 @@ int radix_sort_plan(int lo1, int hi1, int lo2, int hi2, int out[][4], int cap);
 int launch_topn(const DevState &st, const SortTemp &tmp, uint32_t nslots, int metric, int host_filter, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
 int launch_topn_tasks(const DevState &st, const SortTemp &tmp, uint32_t ntasks, int metric, uint32_t want, gysk_topn_entry *d_out, cudaStream_t s);
 int launch_task_flush(const DevState &st, uint32_t max_tasks, cudaStream_t s);
-int launch_flush(const DevState &st, uint32_t max_svcs, HistCell *ring_plane0, HistCell *ring_plane1, uint32_t tsec, uint32_t idle_secs, cudaStream_t s);
+int launch_flush(const DevState &st, uint32_t max_svcs, HistCell *ring_plane0, HistCell *ring_plane1, uint32_t tsec, uint32_t idle_secs,
+		uint32_t live_mask0, uint32_t live_mask1, cudaStream_t s);
 int launch_rebuild_table(const DevState &st, uint32_t max_svcs, cudaStream_t s);
 int launch_gather_svcs(const DevState &st, const unsigned long long *d_ids, uint32_t n, uint32_t max_svcs, uint32_t live_mask0, uint32_t live_mask1,
 		SvcRaw *d_out, cudaStream_t s);

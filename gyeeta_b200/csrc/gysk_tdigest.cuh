@@ -17,14 +17,14 @@ namespace gysk {
 struct TdParams { const double *qtab; uint32_t delta; uint32_t pad; };		// qtab[0 .. delta], device memory
 
 template <int NMAX_>
-struct TdWorkT				// per warp; NMAX = 2 x TD_CAP: 9.7 KB
+struct TdWorkT				// per warp; NMAX = 2 x TD_CAP: 13.8 KB
 {
-	static constexpr int NMAX = NMAX_;			// capacity of the merged list, a multiple of 32
+	static constexpr int NMAX = NMAX_;			// capacity of the merged list
 	double			mean[NMAX];			// merged list: means ...
 	unsigned long long	pref[NMAX + 1];			// ... and exclusive weight prefix: weight of item i = pref[i+1] - pref[i]
 	uint16_t		bounds[TD_CAP + 2];
 	uint16_t		nxt[NMAX];
-	double			src[NMAX];			// the means of both input lists, staged for the rank searches
+	double			src[NMAX];			// the means of both input lists, staged for the merge
 };
 using TdWork = TdWorkT<2 * TD_CAP>;			// shared memory (13.8 KB): two lists of together up to 2 x TD_CAP centroids
 using TdWorkBig = TdWorkT<1120>;			// global scratch: TD_CAP old centroids + up to NBINS (848) items of a batch
@@ -42,33 +42,35 @@ __device__ __forceinline__ uint32_t warp_merge_compress(Work &S, const Centroid 
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t nm = na + nb;
-	constexpr int IPL = Work::NMAX / 32;		// merged items per lane
 
-	// rank of every item in the merged list = own index + number of items of the other list in front of it. The searches probe the
-	// other list ~log2(n) times each: the means of both lists are staged in S.src first (one coalesced read per list) so that the
-	// probes hit the work area (shared memory on the usual path) instead of global memory.
+	// The means of both lists are staged in S.src (one coalesced read per list), then the warp merges them by MERGE PATH: lane l
+	// produces the outputs [l * per, (l + 1) * per) of the merged list. One binary search along its diagonal tells the lane how many
+	// entries of each list lie in front of its first output; from there it is a plain two-finger merge. Order = stable merge by mean,
+	// `a` first on equal means — the same list a rank-by-binary-search of every entry gives, at ~1/4 of the instructions.
 	double *am = S.src, *bm = S.src + na;
 	for (uint32_t j = lane; j < na; j += 32) am[j] = a[j].mean;
 	for (uint32_t j = lane; j < nb; j += 32) bm[j] = b[j].mean;
 	__syncwarp();
-	for (uint32_t j = lane; j < na; j += 32) {
-		const double m = am[j];
-		uint32_t lo = 0, hi = nb;			// # of b with mean < m
-		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (bm[mid] < m) lo = mid + 1; else hi = mid; }
-		S.mean[j + lo] = m; S.pref[j + lo + 1] = a[j].weight;
+	const uint32_t per = (nm + 31u) >> 5;
+	const uint32_t d0 = lane * per < nm ? lane * per : nm, d1 = d0 + per < nm ? d0 + per : nm;
+	unsigned long long tot = 0;
+	if (d0 < d1) {
+		uint32_t lo = d0 > nb ? d0 - nb : 0u, hi = d0 < na ? d0 : na;		// entries of `a` in front of output d0
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (am[mid] <= bm[d0 - 1u - mid]) lo = mid + 1; else hi = mid; }
+		uint32_t i = lo, k = d0 - lo;
+		double av = i < na ? am[i] : 0.0, bv = k < nb ? bm[k] : 0.0;
+		for (uint32_t pos = d0; pos < d1; ++pos) {
+			const bool ta = i < na && (k >= nb || av <= bv);
+			const unsigned long long w = ta ? a[i].weight : b[k].weight;
+			S.mean[pos] = ta ? av : bv;
+			S.pref[pos + 1] = w;
+			tot += w;
+			if (ta) { ++i; av = i < na ? am[i] : 0.0; }
+			else { ++k; bv = k < nb ? bm[k] : 0.0; }
+		}
 	}
-	for (uint32_t j = lane; j < nb; j += 32) {
-		const double m = bm[j];
-		uint32_t lo = 0, hi = na;			// # of a with mean <= m
-		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (am[mid] <= m) lo = mid + 1; else hi = mid; }
-		S.mean[j + lo] = m; S.pref[j + lo + 1] = b[j].weight;
-	}
-	__syncwarp();
-
-	// in-place weight prefix: pref[i+1] holds w_i on entry and sum(w_0..w_i) on exit; lane owns IPL consecutive items
+	// in-place weight prefix: pref[i+1] holds w_i on entry and sum(w_0..w_i) on exit; every lane scans the outputs it produced
 	{
-		unsigned long long tot = 0;
-		for (int j = 0; j < IPL; ++j) { const uint32_t i = lane * IPL + j; if (i < nm) tot += S.pref[i + 1]; }
 		unsigned long long incl = tot;
 #pragma unroll
 		for (int off = 1; off < 32; off <<= 1) {
@@ -76,7 +78,7 @@ __device__ __forceinline__ uint32_t warp_merge_compress(Work &S, const Centroid 
 			if (lane >= off) incl += tt;
 		}
 		unsigned long long run = incl - tot;
-		for (int j = 0; j < IPL; ++j) { const uint32_t i = lane * IPL + j; if (i < nm) { run += S.pref[i + 1]; S.pref[i + 1] = run; } }
+		for (uint32_t pos = d0; pos < d1; ++pos) { run += S.pref[pos + 1]; S.pref[pos + 1] = run; }
 		if (lane == 0) S.pref[0] = 0;
 	}
 	__syncwarp();
@@ -86,10 +88,19 @@ __device__ __forceinline__ uint32_t warp_merge_compress(Work &S, const Centroid 
 	if (nm) {
 		const unsigned long long Wt = S.pref[nm];
 		const double W = (double)Wt;
-		for (uint32_t j = lane; j <= P.delta; j += 32) {
+		// lane l owns the consecutive cells [l * cj, (l + 1) * cj): the cell starts T_j grow with j, so after one binary search for
+		// its first cell a lane walks forward from the previous answer (a cell holds nm / delta items on average)
+		const uint32_t cj = (P.delta + 32u) >> 5;				// ceil((delta + 1) / 32)
+		uint32_t lo = 0;
+		for (uint32_t j = lane * cj, jn = 0; jn < cj && j <= P.delta; ++j, ++jn) {
 			const unsigned long long T = j == P.delta ? Wt : (unsigned long long)__dmul_rn(__ldg(P.qtab + j), W);
-			uint32_t lo = 0, hi = nm;			// first i in [0, nm) with pref[i] >= T, nm if none
-			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.pref[mid] < T) lo = mid + 1; else hi = mid; }
+			// first i in [0, nm) with pref[i] >= T, nm if none
+			uint32_t steps = jn ? 0u : 8u;
+			while (steps < 8u && lo < nm && S.pref[lo] < T) { ++lo; ++steps; }
+			if (steps == 8u) {
+				uint32_t hi = nm;
+				while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.pref[mid] < T) lo = mid + 1; else hi = mid; }
+			}
 			S.nxt[j] = (uint16_t)lo;
 		}
 		__syncwarp();

@@ -15,7 +15,10 @@ FLOW_EST_DTYPE = np.dtype([("flow_key", "<u8"), ("count", "<u4"), ("kbytes", "<u
 
 EV_CONNECT, EV_ACCEPT, EV_CLOSE_CLI, EV_CLOSE_SER, EV_RESP, EV_TASK, EV_ACTIVE = 1, 2, 3, 4, 5, 6, 7
 EVF_CLI_ERROR, EVF_SER_ERROR = 1, 2
-HIST_RESP_CUR, HIST_RESP_LAST, HIST_RESP_ALL, HIST_TASK_CPU_PCT, HIST_TASK_CPU_DELAY, HIST_TASK_BLKIO_DELAY, HIST_RESP_5MIN, HIST_RESP_5DAY = range(8)
+HIST_RESP_CUR, HIST_RESP_LAST, HIST_RESP_ALL, HIST_TASK_CPU_PCT, HIST_TASK_CPU_DELAY, HIST_TASK_BLKIO_DELAY, HIST_RESP_5MIN, HIST_RESP_5DAY, HIST_QPS, HIST_ACTIVE_CONN = range(10)
+STATE_IDLE, STATE_GOOD, STATE_OK, STATE_BAD, STATE_SEVERE, STATE_DOWN = range(6)
+ISSUE_NONE, ISSUE_LISTENER_TASKS, ISSUE_QPS_HIGH, ISSUE_ACTIVE_CONN_HIGH, ISSUE_SERVER_ERRORS, ISSUE_OS_CPU, ISSUE_OS_MEMORY, ISSUE_DEPENDENT, ISSUE_UNKNOWN = range(9)
+TOPN_QPS, TOPN_CONNS, TOPN_NET, TOPN_ISSUE = range(4)
 RAW_EVENT32, RAW_TCP_IPV4_EVENT, RAW_TCP_IPV4_RESP, RAW_TCP_IPV6_EVENT, RAW_TCP_IPV6_RESP, RAW_API_TRAN, RAW_RESP16, RAW_TCP24, RAW_TASK24 = range(9)
 RESP16_DTYPE = np.dtype([("svc_id", "<u8"), ("usec", "<u4"), ("host_idx", "<u2"), ("cli_port", "u1"), ("flags", "u1")])
 TCP24_DTYPE = np.dtype([("svc_id", "<u8"), ("flow_key", "<u8"), ("bytes", "<u4"), ("host_idx", "<u2"), ("type", "u1"), ("pad", "u1")])
@@ -51,10 +54,33 @@ class SvcSummary(C.Structure):
                 ("kbytes_all", C.c_uint64), ("distinct_clients", C.c_double), ("td_p50_us", C.c_double),
                 ("td_p95_us", C.c_double), ("td_p99_us", C.c_double), ("td_count", C.c_uint64),
                 ("nconns_active", C.c_uint32), ("active_kbytes", C.c_uint32), ("max_rtt_msec", C.c_float),
-                ("cli_errors", C.c_uint32), ("ser_errors", C.c_uint32), ("pad", C.c_uint32)]
+                ("cli_errors", C.c_uint32), ("ser_errors", C.c_uint32), ("curr_state", C.c_uint8), ("curr_issue", C.c_uint8),
+                ("issue_bit_hist", C.c_uint8), ("high_resp_bit_hist", C.c_uint8)]
 
     def asdict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class ListenerStateIn(C.Structure):
+    """gysk_listener_state_in: the inputs of TCP_LISTENER::get_curr_state (include/gysketch.h)"""
+    _fields_ = [(n, C.c_int64) for n in ("r5p95", "r5p99", "r300p95", "r300p99", "r5dp95", "r5dp99", "r5dp25", "rallp95", "rallp99")] + \
+               [(n, C.c_uint64) for n in ("nqrys_5s", "total_resp_msec", "tcount_5d")] + \
+               [(n, C.c_double) for n in ("mean5", "mean300", "mean5d", "meanall")] + \
+               [(n, C.c_int64) for n in ("qps_p95", "qps_p25", "act_p95", "act_p25", "secs_5d")] + \
+               [("last_qps_count", C.c_int32), ("nconn", C.c_int32), ("curr_active_conn", C.c_int32), ("ser_errors", C.c_uint32),
+                ("nactive_conn_arr", C.c_uint8 * 16), ("task_issue", C.c_uint8), ("task_severe", C.c_uint8), ("task_delay", C.c_uint8),
+                ("cpu_issue", C.c_uint8), ("mem_issue", C.c_uint8), ("pad0", C.c_uint8 * 3), ("ntasks_issue", C.c_int32),
+                ("ntasks_noissue", C.c_int32), ("tasks_delay_msec", C.c_uint64), ("nserdepends", C.c_uint32), ("pad1", C.c_uint32)]
+
+
+def classify_listener(inp, high_resp_bit_hist=0):
+    """gysk_classify_listener: -> (state, issue, new high_resp_bit_hist)"""
+    L = load_library()
+    hb, st, iss = C.c_uint8(high_resp_bit_hist), C.c_uint8(), C.c_uint8()
+    rc = L.gysk_classify_listener(C.byref(inp), C.byref(hb), C.byref(st), C.byref(iss))
+    if rc:
+        raise GyskError(rc, "gysk_classify_listener")
+    return st.value, iss.value, hb.value
 
 
 class HostSummary(C.Structure):
@@ -132,6 +158,7 @@ def load_library(path=None):
         "gysk_hist_nbuckets": (i32, [i32]),
         "gysk_hist_bucket": (i32, [i32, C.c_int64]),
         "gysk_hist_percentiles": (i32, [i32, i32, vp, u64, vp, u32, vp]),
+        "gysk_classify_listener": (i32, [vp, vp, vp, vp]),
         "gysk_hll_estimate": (C.c_double, [vp, u32]),
         "gysk_tdigest_quantile": (C.c_double, [vp, vp, u32, C.c_double, C.c_double, C.c_double]),
         "gysk_uint64_hash": (u32, [u64]),

@@ -115,7 +115,47 @@ enum {
 	GYSK_HIST_TASK_BLKIO_DELAY = 5,	/* task: blkio_delay_histogram_			(DURATION_HASH, T=int) */
 	GYSK_HIST_RESP_5MIN	= 6,	/* service: 300-s level    (Level_5s_5min_5days_all, gy_statistics.h:1545-1551; 10 slots, :1105) */
 	GYSK_HIST_RESP_5DAY	= 7,	/* service: 432000-s level */
+	GYSK_HIST_QPS		= 8,	/* service: TCP_LISTENER::qps_hist_		(SEMI_LOG_HASH_LO, T=int) common/gy_socket_stat.h:548,633: one
+					   sample per closed window = queries / 5, common/gy_socket_stat.cc:4111-4121 */
+	GYSK_HIST_ACTIVE_CONN	= 9,	/* service: active_conn_hist_			(HASH_1_3000, T=int) :549,635: one sample per closed window =
+					   the listener's active connections, :4124-4130 */
 };
+
+/* ---- listener state (OBJ_STATE_E, common/gy_json_field_maps.h:242-250) and issue source (LISTENER_ISSUE_SRC, :419-435) ---- */
+enum { GYSK_STATE_IDLE = 0, GYSK_STATE_GOOD = 1, GYSK_STATE_OK = 2, GYSK_STATE_BAD = 3, GYSK_STATE_SEVERE = 4, GYSK_STATE_DOWN = 5 };
+enum { GYSK_ISSUE_NONE = 0, GYSK_ISSUE_LISTENER_TASKS = 1, GYSK_ISSUE_QPS_HIGH = 2, GYSK_ISSUE_ACTIVE_CONN_HIGH = 3, GYSK_ISSUE_SERVER_ERRORS = 4,
+       GYSK_ISSUE_OS_CPU = 5, GYSK_ISSUE_OS_MEMORY = 6, GYSK_ISSUE_DEPENDENT_SERVER_LISTENER = 7, GYSK_ISSUE_SRC_UNKNOWN = 8 };
+
+/* Inputs of TCP_LISTENER::get_curr_state (common/gy_socket_stat.cc:2020-2875), the once-per-window state decision of a listener.
+ * gysk_flush() evaluates it on the device for every service from the engine's own state, with the block "outside the path" zero;
+ * gysk_classify_listener() is the same code for a caller that has those inputs. Response values in msec. */
+typedef struct gysk_listener_state_in
+{
+	int64_t		r5p95, r5p99;			/* last 5-s window: p95 / p99 bucket thresholds		(:2082-2083) */
+	int64_t		r300p95, r300p99;		/* 300-s level						(:2084-2085) */
+	int64_t		r5dp95, r5dp99, r5dp25;		/* 5-day level						(:2086-2088) */
+	int64_t		rallp95, rallp99;		/* all-time level					(:2089-2090) */
+	uint64_t	nqrys_5s;			/* histstat_[n5].tcount_ */
+	uint64_t	total_resp_msec;		/* histstat_[n5].tsum_ */
+	uint64_t	tcount_5d;			/* histstat_[n5days].tcount_ */
+	double		mean5, mean300, mean5d, meanall;	/* tsum / max(tcount, 1), common/gy_statistics.h:1358 */
+	int64_t		qps_p95, qps_p25;		/* qps_hist_ percentiles				(:2097) */
+	int64_t		act_p95, act_p25;		/* active_conn_hist_ percentiles			(:2098) */
+	int64_t		secs_5d;			/* seconds the 5-day level covers so far: min(432000, age)	(:2067-2074) */
+	int32_t		last_qps_count;			/* last_qps_count_: queries per second of the window	(:4121) */
+	int32_t		nconn;				/* last_chk_nconn_					(:2036) */
+	int32_t		curr_active_conn;		/* (:4158-4170) max of nconn_recent_active_ and the CONN_BITMAP bucket counts */
+	uint32_t	ser_errors;
+	uint8_t		nactive_conn_arr[16];		/* CONN_BITMAP::get_conn_breakup of the window, per response bucket (:4160-4163) */
+	/* outside the path: the engine passes zeros */
+	uint8_t		task_issue, task_severe, task_delay;	/* TCP_LISTENER::is_task_issue (:1914) verdicts */
+	uint8_t		cpu_issue, mem_issue;		/* host state */
+	uint8_t		pad0[3];
+	int32_t		ntasks_issue, ntasks_noissue;
+	uint64_t	tasks_delay_msec;
+	uint32_t	nserdepends;			/* related_listen_->id_depends_ count (:2820-2823) */
+	uint32_t	pad1;
+} gysk_listener_state_in;
 
 /* ---- raw record kinds for gysk_ingest_raw ---- */
 enum {
@@ -202,7 +242,10 @@ typedef struct gysk_svc_summary
 	uint32_t	active_kbytes;		/* ... sum of (bytes_sent_ + bytes_received_) >> 10 */
 	float		max_rtt_msec;		/* ... max of max_rtt_msec_ */
 	uint32_t	cli_errors, ser_errors;	/* API_TRAN error counters of the last window (-> ::cli_errors_, ::ser_errors_) */
-	uint32_t	pad;
+	uint8_t		curr_state;		/* GYSK_STATE_*: get_curr_state of the last closed window (-> ::curr_state_) */
+	uint8_t		curr_issue;		/* GYSK_ISSUE_* (-> ::curr_issue_) */
+	uint8_t		issue_bit_hist;		/* one bit per window, 1 = state >= BAD (-> ::issue_bit_hist_, gy_socket_stat.cc:4242-4249) */
+	uint8_t		high_resp_bit_hist;	/* one bit per window, 1 = response above the 5-day level (-> ::high_resp_bit_hist_) */
 } gysk_svc_summary;
 
 /* per-host roll-up of the listener states of one 5-s tick: LISTEN_SUMM_STATS<int>, server/gy_msocket.h:840-866 */
@@ -234,7 +277,7 @@ typedef struct gysk_cluster_state
 } gysk_cluster_state;
 
 /* top-N services of the last closed window (BOUNDED_PRIO_QUEUE users of partha_listener_state, gy_mconnhdlr.cc:11262-11304) */
-enum { GYSK_TOPN_QPS = 0, GYSK_TOPN_CONNS = 1, GYSK_TOPN_NET = 2 };
+enum { GYSK_TOPN_QPS = 0, GYSK_TOPN_CONNS = 1, GYSK_TOPN_NET = 2, GYSK_TOPN_ISSUE = 3 /* curr_state > OK, worst first: LISTEN_TOPN::is_comp_issue, server/gy_msocket.h:745 */ };
 /* top-N aggregated processes of the last closed window: atask_top_cpu_ / atask_top_cpu_delay_ / atask_top_io_delay_ of
  * partha_aggr_task_state (server/gy_mconnhdlr.cc:10020-10065; a task whose metric is zero never enters a queue).
  * score = the window's sum of cpu_pct / cpu_delay msec / blkio_delay msec samples */
@@ -346,6 +389,8 @@ int		gysk_hist_bucket(int cls, int64_t value);	/* RESP_TIME_HASH::get_bucket_fro
 int		gysk_hist_percentiles(int cls, int t_is_int, const gysk_hist_serial *stats, uint64_t total_count,
 				const float *pcts, uint32_t npct, int64_t *out);
 double		gysk_hll_estimate(const uint8_t *regs, uint32_t p);
+/* TCP_LISTENER::get_curr_state (common/gy_socket_stat.cc:2020-2875): shifts / sets *high_resp_bit_hist, writes GYSK_STATE_* / GYSK_ISSUE_* */
+int		gysk_classify_listener(const gysk_listener_state_in *in, uint8_t *high_resp_bit_hist, uint8_t *state, uint8_t *issue);
 /* per-service summaries -> LISTENER_STATE_NOTIFY records (common/gy_comm_proto.h:2183-2254), the body of one
  * NOTIFY_LISTENER_STATE message (<= 512 records, 88 bytes each) that MTCP_LISTENER::set_state / partha_listener_state consume
  * (server/gy_mconnhdlr.cc:11175-11251). Entries with found == 0 are skipped. No engine needed. */

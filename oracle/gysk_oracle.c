@@ -554,6 +554,9 @@ typedef struct svc_state
 	uint64_t	act_cur, act_last;	/* ACTIVE_CONN_STATS roll-up {active conns : 32 | kbytes : 32} */
 	uint64_t	err_cur, err_last;	/* API_TRAN error counters {client : 32 | server : 32} */
 	uint32_t	rtt_cur, rtt_last;	/* max of max_rtt_msec_ (float bits; non-negative floats order like their bits) */
+	gyo_hist	qps_hist, act_hist;	/* TCP_LISTENER::qps_hist_ (SEMI_LOG_HASH_LO, int) / active_conn_hist_ (HASH_1_3000, int), gy_socket_stat.h:548-549 */
+	uint8_t		state, issue, issue_bits, high_bits;	/* curr_state_, curr_issue_, issue_bit_hist_, high_resp_bit_hist_ (gy_socket_stat.h:654-657) */
+	uint32_t	nconn_active;		/* last reported active connection count (kept between ACTIVE_CONN_STATS reports) */
 } svc_state;
 
 typedef struct task_state
@@ -657,6 +660,9 @@ static svc_state *get_svc(gyo_engine *e, uint64_t id, int insert)
 		gyo_hist_init(&s->last, GYO_CLS_RESP_TIME, GYO_T_INT64);
 		gyo_hist_init(&s->all, GYO_CLS_RESP_TIME, GYO_T_INT64);
 		for (int l = 0; l < GYO_NLEVELS; ++l) for (int k = 0; k < GYO_NSLOTS; ++k) gyo_hist_init(&s->ring[l][k], GYO_CLS_RESP_TIME, GYO_T_INT64);
+		gyo_hist_init(&s->qps_hist, GYO_CLS_SEMI_LOG_LO, GYO_T_INT);
+		gyo_hist_init(&s->act_hist, GYO_CLS_HASH_1_3000, GYO_T_INT);
+		s->state = GYO_STATE_OK; s->issue = 0; s->issue_bits = 0; s->high_bits = 0; s->nconn_active = 0;
 		s->hll = (uint8_t *)calloc(1u << e->hll_p, 1);
 		gyo_td_init(&s->td);
 	}
@@ -794,6 +800,192 @@ int gyo_ingest(gyo_engine *e, const gyo_event *ev, uint64_t n)
  * a level's answer = sum of the slots whose epoch lies within the last 10 epochs. The 5-s level is the window itself. */
 static const uint32_t g_level_width[GYO_NLEVELS] = { 30, 43200 };
 
+static void level_sum(const gyo_engine *e, const svc_state *s, int l, gyo_hist *out);
+
+/* ---- listener state ---------------------------------------------------------------------------------------------------------
+ * TCP_LISTENER::get_curr_state, common/gy_socket_stat.cc:2020-2875, without the sentence it formats. Statement order and operand
+ * types as in the reference (ser_errors uint32, curr_qps int, data_value int64, mean_val_ double, 0.8f / 1.1f / 1.2f float
+ * constants). Line numbers cite the condition each rule restates. */
+static int resp_bucketid(int64_t thr)		/* get_bucketid_from_threshold<RESP_TIME_HASH>, common/gy_statistics.h:517-531 */
+{
+	const int64_t *t = g_cls[GYO_CLS_RESP_TIME].thr;
+	for (int i = 0; i < 13; ++i) if (thr == t[i]) return i + 1;
+	if (thr < 0) return 0;
+	return 14;
+}
+
+#define OUT(st_, is_)	do { *state = (uint8_t)(st_); *issue = (uint8_t)(is_); return; } while (0)
+#define OK_OR_ERRORS()	OUT(GYO_STATE_OK, ser ? GYO_ISSUE_SERVER_ERRORS : GYO_ISSUE_NONE)
+
+void gyo_listener_state(const gyo_state_in *in, uint8_t *high, uint8_t *state, uint8_t *issue)
+{
+	const uint32_t	ser = in->ser_errors;
+	const size_t	nq = (size_t)in->nqrys_5s;
+	const int	tissue = in->task_issue, severe = in->task_severe, delay = in->task_delay;
+	const int	nbad = in->ntasks_issue, ngood = in->ntasks_noissue;
+	const int	b5 = resp_bucketid(in->r5p95), b300 = resp_bucketid(in->r300p95), b5d = resp_bucketid(in->r5dp95);	/* :2094-2096 */
+	int		qps = (int)(in->nqrys_5s / 5);
+	if (in->last_qps_count > qps) qps = in->last_qps_count;						/* :2092 */
+	const int	worse = (b5 > b5d + 2) && (b5 > b300);
+
+	*high = (uint8_t)(*high << 1);										/* :2120 */
+
+	if (qps == 0 && (!tissue || !severe || !ser)) OUT(GYO_STATE_IDLE, GYO_ISSUE_NONE);			/* :2122-2136 */
+
+	if (b5 == 1 || in->r5p95 < in->r5dp95) {								/* :2139 */
+		if (qps <= in->qps_p25 && in->qps_p25 < in->qps_p95) {						/* :2143 */
+			if (!tissue) {
+				if (!ser) OUT(GYO_STATE_IDLE, GYO_ISSUE_NONE);					/* :2145 */
+				if ((size_t)(uint32_t)(ser * 2u) > nq) OUT(GYO_STATE_SEVERE, GYO_ISSUE_SERVER_ERRORS);	/* :2154 */
+				if ((size_t)(uint32_t)(ser * 5u) > nq) OUT(GYO_STATE_BAD, GYO_ISSUE_SERVER_ERRORS);	/* :2162 */
+				if (ser < nq * 0.1) OUT(GYO_STATE_OK, GYO_ISSUE_SERVER_ERRORS);			/* :2170 */
+			}
+			else {
+				if ((size_t)(uint32_t)(ser * 2u) > nq) OUT(GYO_STATE_SEVERE, GYO_ISSUE_SERVER_ERRORS);	/* :2181 */
+				if ((size_t)(uint32_t)(ser * 5u) > nq) OUT(GYO_STATE_BAD, GYO_ISSUE_SERVER_ERRORS);	/* :2189 */
+				if (ser) OUT(GYO_STATE_BAD, GYO_ISSUE_TASKS);						/* :2197 */
+				if (severe && nbad > 0 && ngood == 0) OUT(GYO_STATE_BAD, GYO_ISSUE_TASKS);		/* :2206 */
+				if (in->nconn > in->act_p25) OUT(GYO_STATE_OK, GYO_ISSUE_TASKS);			/* :2216 */
+			}
+		}
+		if (ser) {											/* :2229 */
+			if ((size_t)(uint32_t)(ser * 2u) > nq) OUT(GYO_STATE_SEVERE, GYO_ISSUE_SERVER_ERRORS);
+			if ((size_t)(uint32_t)(ser * 5u) > nq) OUT(GYO_STATE_BAD, GYO_ISSUE_SERVER_ERRORS);
+		}
+		if (tissue && severe && nbad > 0 && ngood == 0) OUT(GYO_STATE_BAD, GYO_ISSUE_TASKS);		/* :2260 */
+		if (ser) OUT(GYO_STATE_OK, GYO_ISSUE_SERVER_ERRORS);						/* :2294 */
+		if (qps <= in->qps_p95 || b5 + 2 <= b5d) OUT(GYO_STATE_GOOD, GYO_ISSUE_NONE);			/* :2276 */
+		OUT(GYO_STATE_OK, GYO_ISSUE_QPS_HIGH);								/* :2287 */
+	}
+
+	if (in->r5p95 == in->r5dp95) {										/* :2307 */
+		if (ser) {
+			if ((size_t)(uint32_t)(ser * 2u) > nq) OUT(GYO_STATE_SEVERE, GYO_ISSUE_SERVER_ERRORS);
+			if ((size_t)(uint32_t)(ser * 5u) > nq) OUT(GYO_STATE_BAD, GYO_ISSUE_SERVER_ERRORS);
+		}
+		if (in->mean5 <= in->mean5d * 0.8f) {								/* :2340 */
+			if (qps <= in->qps_p25) {								/* :2342 */
+				if (ser) OUT(GYO_STATE_BAD, GYO_ISSUE_SERVER_ERRORS);
+				if (!tissue) OUT(GYO_STATE_IDLE, GYO_ISSUE_NONE);
+				if (nbad > 0 && ngood == 0) OUT(GYO_STATE_BAD, GYO_ISSUE_TASKS);
+				if (nbad > 0 && in->tasks_delay_msec >= 1000) OUT(GYO_STATE_BAD, GYO_ISSUE_TASKS);
+			}
+			if (!tissue && !ser) OUT(GYO_STATE_GOOD, GYO_ISSUE_NONE);				/* :2386 */
+			if (ser && tissue) OUT(GYO_STATE_BAD, GYO_ISSUE_TASKS);					/* :2394-2395 */
+			/* :2402-2415: the {SERVER_ERRORS, OK} assignment for errors without a process issue has no return and is overwritten */
+			OUT(GYO_STATE_OK, GYO_ISSUE_TASKS);
+		}
+		if (in->mean5 <= in->mean5d * 1.2f) OUT(GYO_STATE_OK, GYO_ISSUE_NONE);				/* :2419 */
+	}
+
+	*high |= 1;												/* :2430 */
+
+	if (ser) {
+		if ((size_t)(uint32_t)(ser * 2u) > nq) OUT(GYO_STATE_SEVERE, GYO_ISSUE_SERVER_ERRORS);		/* :2433 */
+		if ((size_t)(uint32_t)(ser * 5u) > nq) OUT(GYO_STATE_BAD, GYO_ISSUE_SERVER_ERRORS);
+	}
+	if (qps > in->qps_p95 && qps - in->qps_p95 > 5 && qps > in->qps_p95 * 1.1f)				/* :2464 */
+		OUT(worse ? GYO_STATE_SEVERE : GYO_STATE_BAD, GYO_ISSUE_QPS_HIGH);
+	if (tissue || (delay && nbad + ngood > 2 && in->tasks_delay_msec * 4 > in->total_resp_msec))		/* :2494 */
+		OUT(worse ? GYO_STATE_SEVERE : GYO_STATE_BAD, GYO_ISSUE_TASKS);
+	if (in->curr_active_conn > in->act_p95 && in->curr_active_conn - in->act_p95 > 1)			/* :2525 */
+		OUT(worse && in->curr_active_conn > 10 ? GYO_STATE_SEVERE : GYO_STATE_BAD, GYO_ISSUE_ACTIVE_CONN_HIGH);
+	if (in->r5p95 == in->r5dp95 && in->r5p99 > in->r5dp99) OK_OR_ERRORS();					/* :2552-2554 */
+	if (qps <= in->qps_p25 && in->nconn <= in->act_p25) {							/* :2576 */
+		if (delay && in->cpu_issue && in->mem_issue) OUT(GYO_STATE_BAD, GYO_ISSUE_TASKS);
+		if (delay && (in->cpu_issue || in->mem_issue) && in->tasks_delay_msec * 4 > in->total_resp_msec) OUT(GYO_STATE_BAD, GYO_ISSUE_TASKS);
+		OK_OR_ERRORS();
+	}
+	{
+		const int avg5d = (int)((int64_t)in->tcount_5d / (in->secs_5d > 0 ? in->secs_5d : 1));	/* :2638 */
+		if (avg5d < (qps >> 1) && in->r5p95 <= in->rallp95 && in->mean5 <= in->meanall * 1.1f) OK_OR_ERRORS();
+	}
+	if (qps <= in->qps_p25 && in->curr_active_conn <= in->act_p25 && b5 <= b5d + 1) OK_OR_ERRORS();	/* :2661 */
+	if (b5 <= b5d + 1 && b300 == b5d && in->mean5 > in->mean300 && in->mean300 < in->mean5d * 1.1f) OK_OR_ERRORS();	/* :2684-2685 */
+	if (in->curr_active_conn >= 15 && b5 == b5d + 1) {							/* :2710 */
+		int b = b5;
+		while (b < 15 && in->nactive_conn_arr[b] <= 3) b++;
+		if (b > b5) OK_OR_ERRORS();
+	}
+	if (__builtin_popcount(*high) < 5) OK_OR_ERRORS();							/* :2748-2749 */
+	{
+		const int st = worse ? GYO_STATE_SEVERE : GYO_STATE_BAD;					/* :2774 */
+		if (in->tasks_delay_msec * 4 > in->total_resp_msec && st == GYO_STATE_BAD) OUT(st, GYO_ISSUE_TASKS);	/* :2791 */
+		if (in->nserdepends > 0) OUT(st, GYO_ISSUE_DEPENDENT);						/* :2825 */
+		if (in->tasks_delay_msec * 10 > in->total_resp_msec) OUT(st, GYO_ISSUE_TASKS);			/* :2829 */
+		OUT(st, ser ? GYO_ISSUE_SERVER_ERRORS : GYO_ISSUE_UNKNOWN);					/* :2855-2860 */
+	}
+}
+#undef OUT
+#undef OK_OR_ERRORS
+
+/* statistics of one response level as TIME_HISTOGRAM::get_stats hands them out (common/gy_statistics.h:1333-1362; percentile rule:
+ * GY_HISTOGRAM::get_percentiles — folly's level percentile is un-vendored) */
+static void level_stats(const gyo_hist *h, int64_t *p95, int64_t *p99, int64_t *p25, uint64_t *cnt, uint64_t *sum, double *mean)
+{
+	const float pcts[3] = {95, 99, 25};
+	int64_t v[3];
+	uint64_t c = 0, sm = 0;
+
+	gyo_hist_percentiles(h, pcts, 3, v, NULL);
+	for (int b = 0; b < 15; ++b) { c += h->stats[b].count; sm += (uint64_t)h->stats[b].sum; }
+	for (int k = 0; k < 3; ++k) if (v[k] < 0) v[k] = 0;
+	*p95 = v[0]; *p99 = v[1]; if (p25) *p25 = v[2];
+	*cnt = c; *sum = sm; *mean = (double)(int64_t)sm / (double)(c ? (int64_t)c : 1);
+}
+
+/* the part of listener_stats_update (common/gy_socket_stat.cc:4045-4272) around the state decision, for one service whose closing
+ * window was not stale: qps / active-connection samples (:4111-4130), the connection counts (:4158-4173), get_curr_state (:4233),
+ * issue_bit_hist_ and the young-listener override (:4242-4272). Called by gyo_flush after the window has rolled. */
+static void svc_update_state(const gyo_engine *e, svc_state *s, uint32_t tsec)
+{
+	gyo_state_in in;
+	gyo_hist l300, l5d;
+	uint64_t c, sm;
+	const float pq[2] = {95, 25};
+	int64_t v[2];
+
+	memset(&in, 0, sizeof(in));
+	level_stats(&s->last, &in.r5p95, &in.r5p99, NULL, &in.nqrys_5s, &in.total_resp_msec, &in.mean5);
+	level_sum(e, s, 0, &l300); level_sum(e, s, 1, &l5d);
+	level_stats(&l300, &in.r300p95, &in.r300p99, NULL, &c, &sm, &in.mean300);
+	level_stats(&l5d, &in.r5dp95, &in.r5dp99, &in.r5dp25, &in.tcount_5d, &sm, &in.mean5d);
+	level_stats(&s->all, &in.rallp95, &in.rallp99, NULL, &c, &sm, &in.meanall);
+
+	in.last_qps_count = (int32_t)(in.nqrys_5s / 5);
+	gyo_hist_add(&s->qps_hist, in.last_qps_count);								/* :4113 */
+	if ((uint32_t)s->act_last) s->nconn_active = (uint32_t)s->act_last;					/* a report arrived in this window */
+	gyo_hist_add(&s->act_hist, (int64_t)(int32_t)s->nconn_active);					/* :4128 */
+	gyo_hist_percentiles(&s->qps_hist, pq, 2, v, NULL); in.qps_p95 = v[0]; in.qps_p25 = v[1];
+	gyo_hist_percentiles(&s->act_hist, pq, 2, v, NULL); in.act_p95 = v[0]; in.act_p25 = v[1];
+
+	in.nconn = (int32_t)s->nconn_active;
+	in.curr_active_conn = in.nconn;
+	for (int b = 0; b < 15; ++b) {										/* :4160-4168 */
+		in.nactive_conn_arr[b] = (uint8_t)__builtin_popcount(s->bm_last[b]);
+		if (in.curr_active_conn < in.nactive_conn_arr[b]) in.curr_active_conn = in.nactive_conn_arr[b];
+	}
+	in.ser_errors = (uint32_t)(s->err_last >> 32);
+	const uint32_t age = tsec > s->first_seen ? tsec - s->first_seen : 0;
+	in.secs_5d = age + 1 < 432000 ? age + 1 : 432000;							/* :2033-2034, :2067-2074 */
+
+	gyo_listener_state(&in, &s->high_bits, &s->state, &s->issue);
+	if (age > 100 || in.ser_errors) {									/* :4242 */
+		s->issue_bits = (uint8_t)(s->issue_bits << 1);
+		if (s->state >= GYO_STATE_BAD) s->issue_bits |= 1;
+	}
+	else { s->issue_bits = 0; s->issue = GYO_ISSUE_NONE; s->state = GYO_STATE_OK; }			/* :4262-4270 */
+}
+
+int gyo_export_state(gyo_engine *e, uint64_t id, uint32_t out[5])
+{
+	int slot = idmap_find(&e->smap, id, 0, 0);
+	if (slot < 0) return -2;
+	const svc_state *s = &e->svcs[slot];
+	out[0] = s->state; out[1] = s->issue; out[2] = s->issue_bits; out[3] = s->high_bits; out[4] = s->nconn_active;
+	return 0;
+}
+
 void gyo_flush(gyo_engine *e, uint32_t tsec)
 {
 	int clear[GYO_NLEVELS], slot[GYO_NLEVELS];
@@ -812,12 +1004,10 @@ void gyo_flush(gyo_engine *e, uint32_t tsec)
 
 		if (!s->id) continue;		/* evicted, slot waiting for reuse */
 		/* idle-service rule (ours, after common/gy_socket_stat.cc:3968-3982: tclock != 0, tclock + 300 s < now, tstart + 600 s < now) */
-		{
-			int active = (uint32_t)s->conn_cur != 0 || (s->conn_cur >> 32) != 0 || s->act_cur != 0 || s->err_cur != 0;
-			for (int b = 0; b < 15 && !active; ++b) active = s->cur.stats[b].count != 0;
-			if (!s->first_seen) s->first_seen = tsec ? tsec : 1u;
-			if (active) s->last_active = tsec ? tsec : 1u;
-		}
+		int active = (uint32_t)s->conn_cur != 0 || (s->conn_cur >> 32) != 0 || s->act_cur != 0 || s->err_cur != 0;
+		for (int b = 0; b < 15 && !active; ++b) active = s->cur.stats[b].count != 0;
+		if (!s->first_seen) s->first_seen = tsec ? tsec : 1u;
+		if (active) s->last_active = tsec ? tsec : 1u;
 
 		s->last = s->cur;
 		gyo_hist_merge(&s->all, &s->cur);
@@ -832,6 +1022,8 @@ void gyo_flush(gyo_engine *e, uint32_t tsec)
 		s->conn_all_kb += s->conn_cur >> 32;
 		s->conn_cur = 0;
 		s->act_last = s->act_cur; s->act_cur = 0; s->err_last = s->err_cur; s->err_cur = 0; s->rtt_last = s->rtt_cur; s->rtt_cur = 0;
+		/* a window without any event of the service is "stale" (:4098-4107): the reference leaves the listener's state as it is */
+		if (active) svc_update_state(e, s, tsec);
 
 		if (e->idle_evict_secs && s->last_active && (uint64_t)s->last_active + e->idle_evict_secs < tsec &&
 				(uint64_t)s->first_seen + 2ull * e->idle_evict_secs < tsec) {
@@ -907,6 +1099,11 @@ int gyo_export_hist(gyo_engine *e, uint64_t id, int which, gyo_serial *out15, ui
 		if (slot < 0) return -2;
 		level_sum(e, &e->svcs[slot], which - 6, &lvl);
 		h = &lvl;
+	}
+	else if (which == 8 || which == 9) {
+		int slot = idmap_find(&e->smap, id, 0, 0);
+		if (slot < 0) return -2;
+		h = which == 8 ? &e->svcs[slot].qps_hist : &e->svcs[slot].act_hist;
 	}
 	else {
 		int slot = idmap_find(&e->tmap, id, 0, 0);

@@ -131,6 +131,29 @@ void	gyo_merge_from(gyo_engine *dst, const gyo_engine *src);	/* additive roll-up
 /* CPU baseline: nthreads engines each ingest their own pre-sharded event array; returns wall seconds */
 double	gyo_bench_ingest(gyo_engine **engines, const gyo_event **shards, const uint64_t *counts, int nthreads, uint64_t batch);
 
+/* ---- listener state: TCP_LISTENER::get_curr_state, common/gy_socket_stat.cc:2020-2875 (OBJ_STATE_E / LISTENER_ISSUE_SRC,
+ * common/gy_json_field_maps.h:242-250, :419-435) ---- */
+enum { GYO_STATE_IDLE = 0, GYO_STATE_GOOD, GYO_STATE_OK, GYO_STATE_BAD, GYO_STATE_SEVERE, GYO_STATE_DOWN };
+enum { GYO_ISSUE_NONE = 0, GYO_ISSUE_TASKS, GYO_ISSUE_QPS_HIGH, GYO_ISSUE_ACTIVE_CONN_HIGH, GYO_ISSUE_SERVER_ERRORS, GYO_ISSUE_OS_CPU,
+       GYO_ISSUE_OS_MEMORY, GYO_ISSUE_DEPENDENT, GYO_ISSUE_UNKNOWN };
+typedef struct gyo_state_in		/* same layout as gysk_listener_state_in (include/gysketch.h) */
+{
+	int64_t		r5p95, r5p99, r300p95, r300p99, r5dp95, r5dp99, r5dp25, rallp95, rallp99;
+	uint64_t	nqrys_5s, total_resp_msec, tcount_5d;
+	double		mean5, mean300, mean5d, meanall;
+	int64_t		qps_p95, qps_p25, act_p95, act_p25, secs_5d;
+	int32_t		last_qps_count, nconn, curr_active_conn;
+	uint32_t	ser_errors;
+	uint8_t		nactive_conn_arr[16];
+	uint8_t		task_issue, task_severe, task_delay, cpu_issue, mem_issue, pad0[3];
+	int32_t		ntasks_issue, ntasks_noissue;
+	uint64_t	tasks_delay_msec;
+	uint32_t	nserdepends, pad1;
+} gyo_state_in;
+void	gyo_listener_state(const gyo_state_in *in, uint8_t *high_resp_bit_hist, uint8_t *state, uint8_t *issue);
+/* what the flush derived for a service: out = {state, issue, issue_bit_hist, high_resp_bit_hist, nconn_active} */
+int	gyo_export_state(gyo_engine *e, uint64_t id, uint32_t out[5]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,9 @@ def lib():
         L.gyo_export_conn.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
         L.gyo_export_conn_bitmap.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         L.gyo_export_aux.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.gyo_export_state.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.gyo_listener_state.restype = None
+        L.gyo_listener_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gyo_cms_table.restype = C.c_void_p
         L.gyo_cms_table.argtypes = [C.c_void_p, C.c_int]
         L.gyo_counters.argtypes = [C.c_void_p, C.c_void_p]
@@ -226,6 +229,13 @@ class OracleEngine:
         rc = self.L.gyo_export_conn(self.h, int(id_), *[C.byref(x) for x in v])
         return None if rc else tuple(x.value for x in v)
 
+    def export_state(self, id_):
+        """{state, issue, issue_bit_hist, high_resp_bit_hist, nconn_active} the last flush derived, None if the id is unknown"""
+        out = np.zeros(5, dtype=np.uint32)
+        if self.L.gyo_export_state(self.h, int(id_), _p(out)):
+            return None
+        return tuple(int(x) for x in out)
+
     def export_aux(self, id_):
         """dict(act_cur, act_last, err_cur, err_last: packed {lo32, hi32}; rtt_cur, rtt_last: float)"""
         out = np.zeros(6, dtype=np.uint64)
@@ -285,3 +295,10 @@ def ref_hist_rate(slots, vals_ms, nthreads):
     sec = R.gyref_bench_resp_hist(_p(s2), _p(v2), _p(offs), int(slots.max()) + 1, nthreads, C.byref(tot))
     assert tot.value == len(slots)
     return len(slots) / sec
+
+
+def listener_state(inp, high_resp_bit_hist=0):
+    """gyo_listener_state on a struct with gysk_listener_state_in's layout -> (state, issue, new high_resp_bit_hist)"""
+    hb, st, iss = C.c_uint8(high_resp_bit_hist), C.c_uint8(), C.c_uint8()
+    lib().gyo_listener_state(C.byref(inp), C.byref(hb), C.byref(st), C.byref(iss))
+    return st.value, iss.value, hb.value

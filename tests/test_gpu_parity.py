@@ -451,3 +451,49 @@ def test_full_value_range_keys():
             continue
         om, ow = td.centroids()
         assert np.array_equal(got[0], om) and np.array_equal(got[1], ow) and got[2] == td.minv and got[3] == td.maxv
+
+
+def test_listener_state_per_window_equals_oracle():
+    """row a10: the state decision of the 5-s reducer (TCP_LISTENER::get_curr_state behind listener_stats_update,
+    common/gy_socket_stat.cc:4111-4272) evaluated on the device at every flush: qps_hist_ / active_conn_hist_ samples, level statistics,
+    connection counts from ACTIVE_CONN_STATS and CONN_BITMAP, server errors, the two bit histories. Engine == oracle for every service
+    and window; the stream turns slow / error-prone / busy half way so that several rules fire."""
+    rng = np.random.default_rng(31)
+    nsvc = 40
+    eng, orc = make_pair(max_svcs=256, max_tasks=16, max_batch=1 << 14)
+    ids = synth.service_ids(nsvc)
+    seen_states = set()
+    for w in range(30):
+        n = 6000
+        ev = np.zeros(n, dtype=ge.EVENT_DTYPE)
+        k = rng.integers(0, nsvc, n)
+        ev["svc_id"] = ids[k]
+        ev["type"] = ge.EV_RESP
+        slow = (w >= 14) & (k % 4 == 0)                                   # every 4th service turns 8x slower from window 14 on
+        ev["value"] = np.minimum(np.exp(rng.normal(np.log(20_000.0), 1.0, n)) * np.where(slow, 8.0, 1.0), 9e8).astype(np.uint32)
+        ev["flow_key"] = rng.integers(0, 1 << 16, n)
+        err = (w >= 10) & (k % 5 == 1) & (rng.random(n) < (0.7 if w % 2 else 0.15))   # some services answer with server errors
+        ev["flags"] = np.where(err, ge.EVF_SER_ERROR, 0)
+        if w >= 18:                                                       # services 2, 6, 10 ... get 6x the queries
+            extra = ev[(k % 4 == 2)]
+            ev = np.concatenate([ev] + [extra] * 5)
+        act = np.zeros(nsvc, dtype=ge.EVENT_DTYPE)
+        act["svc_id"] = ids; act["type"] = ge.EV_ACTIVE; act["flow_key"] = 77
+        act["flags"] = np.where((np.arange(nsvc) % 8 == 3) & (w >= 20), 400, 3 + (np.arange(nsvc) % 5)) if w % 3 == 0 else 0
+        act = act[act["flags"] > 0]
+        feed_both(eng, orc, np.concatenate([ev, act]), 1 << 14)
+        eng.flush(1000 + 5 * (w + 1)); orc.flush(1000 + 5 * (w + 1))
+        summ = eng.query_svcs(ids)
+        for s_, id_ in zip(summ, ids):
+            want = orc.export_state(int(id_))
+            got = (s_["curr_state"], s_["curr_issue"], s_["issue_bit_hist"], s_["high_resp_bit_hist"])
+            assert got == want[:4], (w, int(id_), got, want)
+            seen_states.add(got[:2])
+        for id_ in ids[:12]:
+            for which in (ge.HIST_QPS, ge.HIST_ACTIVE_CONN):
+                assert_hist_equal(eng, orc, int(id_), which)
+    assert len(seen_states) >= 6, seen_states                             # idle / good / ok / bad / severe outcomes of several sources
+    # issue ranking of the last window (a13): listeners with curr_state > OK, worst first
+    bad = {int(id_): orc.export_state(int(id_))[0] for id_ in ids if orc.export_state(int(id_))[0] > ge.STATE_OK}
+    top = eng.topn(ge.TOPN_ISSUE, 64)
+    assert sorted((sid, sc) for sid, sc, _h in top) == sorted(bad.items()) and [sc for _s, sc, _h in top] == sorted(bad.values(), reverse=True)

@@ -232,6 +232,7 @@ def test_listener_state_encoder_fields_and_limits():
         sums[i].p95_5min_resp_ms = 60
         sums[i].nconns_5s = i
         sums[i].kbytes_5s = 2 * i
+        sums[i].curr_state, sums[i].curr_issue, sums[i].issue_bit_hist, sums[i].high_resp_bit_hist = i % 5, i % 9, i & 0xFF, (3 * i) & 0xFF
     buf = C.create_string_buffer(88 * 512)
     nrecs, nbytes = C.c_uint32(), C.c_uint32()
     assert L.gysk_encode_listener_state(sums, n, buf, len(buf), C.byref(nrecs), C.byref(nbytes)) == 0
@@ -243,9 +244,104 @@ def test_listener_state_encoder_fields_and_limits():
     assert by[1001]["total_resp_5sec"] == 0xFFFFFFFF and by[1002]["p95_5s"] == 0     # clamps
     r = by[1011]
     assert (r["nqrys_5s"], r["total_resp_5sec"], r["p95_5s"], r["p95_5min"], r["nconns"], r["kb_in"]) == (110, 33, 30, 60, 11, 22)
-    assert r["curr_state"] == 2 and by[1005]["curr_state"] == 0                 # STATE_OK with queries, STATE_IDLE without
+    assert (r["curr_state"], r["curr_issue"], r["issue_bit_hist"], r["high_resp_bit_hist"]) == (11 % 5, 11 % 9, 11, 33)   # the classifier's outputs
     assert r["issue_string_len"] == 0 and r["padding_len"] == 0
     small = C.create_string_buffer(88 * 3)
     assert L.gysk_encode_listener_state(sums, n, small, len(small), C.byref(nrecs), C.byref(nbytes)) == -28
 
 
+
+
+def _state_in(**kw):
+    from gyeeta_b200 import engine as ge
+    x = ge.ListenerStateIn()
+    for k, v in kw.items():
+        setattr(x, k, v)
+    return x
+
+
+def test_listener_state_classifier_hand_cases():
+    """TCP_LISTENER::get_curr_state (common/gy_socket_stat.cc:2020-2875), outcomes read off the reference for inputs that single out one
+    rule each; product (gysk_classify_listener, host build of gysk_state.cuh) and oracle (gyo_listener_state) must both give them"""
+    from gyeeta_b200 import engine as ge
+    from oracle import pyoracle as po
+    base = dict(r5p95=30, r5p99=60, r300p95=30, r300p99=60, r5dp95=30, r5dp99=60, r5dp25=10, rallp95=30, rallp99=60, nqrys_5s=500,
+                total_resp_msec=10_000, tcount_5d=1_000_000, mean5=20.0, mean300=20.0, mean5d=20.0, meanall=20.0, qps_p95=200, qps_p25=50,
+                act_p95=100, act_p25=10, secs_5d=10_000, last_qps_count=100, nconn=20, curr_active_conn=20)
+    cases = [
+        # :2122 no queries at all -> idle
+        (dict(nqrys_5s=0, last_qps_count=0), 0, (ge.STATE_IDLE, ge.ISSUE_NONE, 0)),
+        # :2139/:2143/:2145 response below the 5-day p95, QPS at or below its p25, nothing wrong -> idle
+        (dict(r5p95=10, last_qps_count=40, nqrys_5s=200), 0, (ge.STATE_IDLE, ge.ISSUE_NONE, 0)),
+        # :2139/:2229 fast responses but more than half of the queries are server errors -> severe
+        (dict(r5p95=10, ser_errors=300), 0, (ge.STATE_SEVERE, ge.ISSUE_SERVER_ERRORS, 0)),
+        # :2275-2277 faster than usual, QPS below its p95 -> good
+        (dict(r5p95=10), 0b1, (ge.STATE_GOOD, ge.ISSUE_NONE, 0b10)),
+        # :2287 faster than usual but QPS above its p95 (and less than two buckets faster) -> ok, QPS high
+        (dict(r5p95=10, last_qps_count=300, nqrys_5s=1500), 0, (ge.STATE_OK, ge.ISSUE_QPS_HIGH, 0)),
+        # :2307/:2419 same bucket as the 5-day p95, mean within 20 % -> ok
+        (dict(), 0, (ge.STATE_OK, ge.ISSUE_NONE, 0)),
+        # :2307/:2340/:2386 same bucket, mean 20 % below the 5-day mean -> good
+        (dict(mean5=10.0), 0, (ge.STATE_GOOD, ge.ISSUE_NONE, 0)),
+        # :2430/:2464 p95 three buckets above the 5-day and the 300-s p95, QPS 50 % above its p95 -> severe, QPS high; the high bit is set
+        (dict(r5p95=150, r5p99=300, last_qps_count=300, nqrys_5s=1500, mean5=90.0), 0, (ge.STATE_SEVERE, ge.ISSUE_QPS_HIGH, 1)),
+        # :2525 one bucket up, active connections above their p95 -> bad, active conns high
+        (dict(r5p95=60, mean5=40.0, curr_active_conn=150, nconn=150), 0, (ge.STATE_BAD, ge.ISSUE_ACTIVE_CONN_HIGH, 1)),
+        # :2748 one bucket up, nothing else unusual, high in only 3 of the last 8 windows -> ok
+        (dict(r5p95=60, mean5=40.0, r300p95=60, curr_active_conn=10, nconn=10), 0b0101, (ge.STATE_OK, ge.ISSUE_NONE, 0b1011)),
+        # :2771-2860 the same with the response high in 5 of the last 8 windows -> bad, source unknown
+        (dict(r5p95=60, mean5=40.0, r300p95=60, curr_active_conn=10, nconn=10), 0b1111, (ge.STATE_BAD, ge.ISSUE_UNKNOWN, 0b11111)),
+        # :2825 ... and the listener depends on other listeners -> their issue
+        (dict(r5p95=60, mean5=40.0, r300p95=60, nserdepends=2, curr_active_conn=10, nconn=10), 0b1111, (ge.STATE_BAD, ge.ISSUE_DEPENDENT, 0b11111)),
+        # :2710 ... or the slow buckets hold at most 3 connections each of 20 active ones -> a local effect, ok
+        (dict(r5p95=60, mean5=40.0, r300p95=60), 0b1111, (ge.STATE_OK, ge.ISSUE_NONE, 0b11111)),
+        # :2494 a process issue with a slow response -> listener tasks
+        (dict(r5p95=60, mean5=40.0, task_issue=1, ntasks_issue=2), 0, (ge.STATE_BAD, ge.ISSUE_LISTENER_TASKS, 1)),
+        # :2402-2415 the reference's fall-through: same bucket, lower mean, server errors without a process issue end as {ok, tasks}
+        (dict(mean5=10.0, ser_errors=5), 0, (ge.STATE_OK, ge.ISSUE_LISTENER_TASKS, 0)),
+    ]
+    for i, (delta, hb, want) in enumerate(cases):
+        x = _state_in(**{**base, **delta})
+        assert ge.classify_listener(x, hb) == want, (i, delta)
+        assert po.listener_state(x, hb) == want, (i, delta)
+
+
+def test_listener_state_classifier_random_inputs_agree():
+    """product and oracle restatements of the decision tree agree on 60 000 random inputs that reach every rule (operand types matter:
+    uint32 products of ser_errors, float / double constants)"""
+    from gyeeta_b200 import engine as ge
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(21)
+    vals = [0, 1, 10, 30, 60, 100, 150, 200, 300, 450, 700, 1000, 3000, 15000, 32767]
+    qv = [-1, 1, 10, 50, 200, 500, 1000, 3000, 6000, 2147483647]
+    av = [-1, 1, 5, 10, 25, 50, 75, 100, 32767]
+    seen = set()
+    for _ in range(60_000):
+        x = ge.ListenerStateIn()
+        base = int(rng.integers(1, 13))
+        for f in ("r5p95", "r5p99", "r300p95", "r300p99", "r5dp95", "r5dp99", "r5dp25", "rallp95", "rallp99"):
+            setattr(x, f, vals[int(np.clip(base + rng.integers(-2, 3), 0, 14))])
+        x.nqrys_5s = int(rng.choice([0, 3, 40, 500, 20_000]))
+        x.total_resp_msec = int(x.nqrys_5s * rng.integers(1, 200))
+        x.tcount_5d = int(rng.integers(0, 10_000_000))
+        m = float(rng.integers(1, 300))
+        x.mean5, x.mean300, x.mean5d, x.meanall = m, m * float(rng.choice([0.7, 0.95, 1.0, 1.3])), m * float(rng.choice([0.7, 1.0, 1.15, 1.5])), m * float(rng.choice([0.8, 1.0, 1.2]))
+        q = sorted(int(v) for v in rng.choice(qv, 2)); a = sorted(int(v) for v in rng.choice(av, 2))
+        x.qps_p25, x.qps_p95, x.act_p25, x.act_p95 = q[0], q[1], a[0], a[1]
+        x.secs_5d = int(rng.choice([1, 300, 432000]))
+        x.last_qps_count = int(rng.choice([0, 2, 45, 210, 5000]))
+        x.nconn, x.curr_active_conn = int(rng.integers(0, 200)), int(rng.integers(0, 200))
+        x.ser_errors = int(rng.choice([0, 0, 0, 1, 30, 400, 0x90000000]))
+        for b in range(15):
+            x.nactive_conn_arr[b] = int(rng.integers(0, 6))
+        if rng.random() < 0.4:
+            x.task_issue, x.task_severe, x.task_delay = int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 2))
+            x.cpu_issue, x.mem_issue = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+            x.ntasks_issue, x.ntasks_noissue = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+            x.tasks_delay_msec = int(rng.choice([0, 500, 5000, 10 ** 7]))
+            x.nserdepends = int(rng.integers(0, 2))
+        hb = int(rng.integers(0, 256))
+        g, o = ge.classify_listener(x, hb), po.listener_state(x, hb)
+        assert g == o, (g, o)
+        seen.add(g[:2])
+    assert len(seen) == 18, sorted(seen)            # every (state, issue) pair the tree can produce
