@@ -189,27 +189,29 @@ def wire_leg(ge, local, nthreads=16, rounds_per_thread=8, total_events=32_000_00
             rounds.append((wire.build_msg_fixed(ge.NOTIFY_TCP_CONN, c), wire.build_msg_fixed(ge.NOTIFY_AGGR_TASK_STATE, k), r))
         work.append(rounds)
     iters = max(1, total_events // (nthreads * per_round))
-    L, h, hid = eng.L, eng.h, eng._host_id
+    # the producers are native threads (libgysynth.so's gysyn_wire_run): Python threads would time the interpreter lock, not the library
+
+    class Round(C.Structure):
+        _fields_ = [("msg1", C.c_void_p), ("msg2", C.c_void_p), ("raw", C.c_void_p), ("len1", C.c_uint32), ("len2", C.c_uint32),
+                    ("nraw", C.c_uint32), ("raw_kind", C.c_uint32)]
+
+    S = C.CDLL(os.path.join(ROOT, "gyeeta_b200", "libgysynth.so"))
+    S.gysyn_wire_run.restype = C.c_double
+    S.gysyn_wire_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    rounds = (Round * (nthreads * rounds_per_thread))()
+    for t in range(nthreads):
+        for r_, (m1, m2, r) in enumerate(work[t]):
+            rounds[t * rounds_per_thread + r_] = Round(m1.ctypes.data, m2.ctypes.data, r.ctypes.data, len(m1), len(m2), len(r), ge.RAW_TCP_IPV4_RESP)
+    fmsg = C.cast(eng.L.gysk_ingest_msg, C.c_void_p)
+    fraw = C.cast(eng.L.gysk_ingest_raw, C.c_void_p)
+    nerr = C.c_int(0)
     errs = []
 
-    def producer(t, count):
-        rounds = work[t]
-        for i in range(count):
-            m1, m2, r = rounds[i % len(rounds)]
-            rc = L.gysk_ingest_msg(h, hid, t, m1.ctypes.data_as(C.c_void_p), len(m1))
-            rc |= L.gysk_ingest_msg(h, hid, t, m2.ctypes.data_as(C.c_void_p), len(m2))
-            rc |= L.gysk_ingest_raw(h, hid, t, ge.RAW_TCP_IPV4_RESP, r.ctypes.data_as(C.c_void_p), len(r))
-            if rc:
-                errs.append(rc)
-                return
-
     def run(count):
-        thr = [threading.Thread(target=producer, args=(t, count)) for t in range(nthreads)]
         t0 = time.perf_counter()
-        for x in thr:
-            x.start()
-        for x in thr:
-            x.join()
+        S.gysyn_wire_run(eng.h, fmsg, fraw, C.cast(eng._host_id, C.c_void_p), C.cast(rounds, C.c_void_p), nthreads, rounds_per_thread, count, C.byref(nerr))
+        if nerr.value:
+            errs.append(nerr.value)
         eng.query_svcs(svc_ids[:256])
         eng.sync()
         return time.perf_counter() - t0
@@ -221,7 +223,7 @@ def wire_leg(ge, local, nthreads=16, rounds_per_thread=8, total_events=32_000_00
     out = {"value": nev / sec, "unit": "events/s", "threads": nthreads, "events": nev, "sec": sec, "errors": len(errs),
            "wire_bytes_per_event": (len(work[0][0][0]) + len(work[0][0][1]) + work[0][0][2].nbytes) / per_round,
            "h2d_bytes_per_event": (NT * 32 + NK * 32 + NR * 24) / per_round,
-           "what": "16 threads x (TCP_CONN_NOTIFY 2048 x 280 B + AGGR_TASK_STATE_NOTIFY 1024 x 72 B via gysk_ingest_msg, 7168 x 24 B "
+           "what": "16 native threads x (TCP_CONN_NOTIFY 2048 x 280 B + AGGR_TASK_STATE_NOTIFY 1024 x 72 B via gysk_ingest_msg, 7168 x 24 B "
                    "tcp_ipv4_resp_event_t via gysk_ingest_raw), pageable memory, host wall clock incl. final query + sync",
            "wire_msgs_ok": st.get("wire_msgs_ok")}
     eng.close()

@@ -4,7 +4,11 @@
 // (70 / 20 / 10 RESP / TCP / TASK, Zipf services, log-normal values), plus service churn so that idle eviction has work to do.
 //
 // Event i of a fill is a pure function of (seed, rank, counter_base + i): Philox4x32-10, three calls per event.
+#include <atomic>
+#include <chrono>
 #include <cstdint>
+#include <thread>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "../../include/gysketch.h"
@@ -131,4 +135,44 @@ extern "C" int gysyn_fill(void *d_out, uint64_t n, uint64_t counter_base, const 
 	if (blocks > 0x7FFFFFFFull) return -1;
 	synth_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<gysk_event *>(d_out), n, counter_base, *p);
 	return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---- producer threads of bench.py's e2e_wire leg -----------------------------------------------------------------------------
+// N native threads (madhava's L2 handle_l2_misc threads, server/gy_mconnhdlr.cc:5128), each handing its own prebuilt rounds of
+// {TCP_CONN_NOTIFY message, AGGR_TASK_STATE_NOTIFY message, raw tcp_ipv4_resp_event_t array} to the engine through the C ABI's
+// function pointers (this utility does not link libgysketch.so). Returns the seconds from the common start to the last thread's
+// return; the caller adds the closing query + sync.
+extern "C" {
+typedef int (*gysyn_ingest_msg_fn)(void *e, const uint8_t *host_id, uint32_t host_idx, void *msg, uint32_t msglen);
+typedef int (*gysyn_ingest_raw_fn)(void *e, const uint8_t *host_id, uint32_t host_idx, uint32_t kind, const void *events, uint32_t n);
+typedef struct gysyn_wire_round { void *msg1; void *msg2; const void *raw; uint32_t len1, len2, nraw, raw_kind; } gysyn_wire_round;
+
+double gysyn_wire_run(void *engine, gysyn_ingest_msg_fn fmsg, gysyn_ingest_raw_fn fraw, const uint8_t *host_id, const gysyn_wire_round *rounds,
+		uint32_t nthreads, uint32_t nrounds, uint32_t iters, int *nerr)
+{
+	std::atomic<int> ready {0}, errors {0};
+	std::atomic<bool> go {false};
+	std::vector<std::thread> thr;
+	for (uint32_t t = 0; t < nthreads; ++t) {
+		thr.emplace_back([&, t]() {
+			const gysyn_wire_round *mine = rounds + (size_t)t * nrounds;
+			ready.fetch_add(1);
+			while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+			for (uint32_t i = 0; i < iters; ++i) {
+				const gysyn_wire_round &r = mine[i % nrounds];
+				int rc = fmsg(engine, host_id, t, r.msg1, r.len1);
+				rc |= fmsg(engine, host_id, t, r.msg2, r.len2);
+				rc |= fraw(engine, host_id, t, r.raw_kind, r.raw, r.nraw);
+				if (rc) { errors.fetch_add(1); return; }
+			}
+		});
+	}
+	while (ready.load() < (int)nthreads) std::this_thread::yield();
+	const auto t0 = std::chrono::steady_clock::now();
+	go.store(true, std::memory_order_release);
+	for (auto &x : thr) x.join();
+	const auto t1 = std::chrono::steady_clock::now();
+	if (nerr) *nerr = errors.load();
+	return std::chrono::duration<double>(t1 - t0).count();
+}
 }
