@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgysketch.so")
 SYNTH_LIB = os.path.join(HERE, "libgysynth.so")
-SOURCES = ["gysk_kernels.cu", "gysk_engine.cu", "gysk_merge.cu"]
+SOURCES = ["gysk_kernels.cu", "gysk_engine.cu", "gysk_merge.cu", "gysk_groupby.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 

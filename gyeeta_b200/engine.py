@@ -23,6 +23,11 @@ RAW_EVENT32, RAW_TCP_IPV4_EVENT, RAW_TCP_IPV4_RESP, RAW_TCP_IPV6_EVENT, RAW_TCP_
 RESP16_DTYPE = np.dtype([("svc_id", "<u8"), ("usec", "<u4"), ("host_idx", "<u2"), ("cli_port", "u1"), ("flags", "u1")])
 TCP24_DTYPE = np.dtype([("svc_id", "<u8"), ("flow_key", "<u8"), ("bytes", "<u4"), ("host_idx", "<u2"), ("type", "u1"), ("pad", "u1")])
 TASK24_DTYPE = np.dtype([("aggr_task_id", "<u8"), ("cpu_pct", "<u4"), ("cpu_delay_msec", "<u4"), ("blkio_delay_msec", "<u4"), ("host_idx", "<u2"), ("pad", "<u2")])
+PROC_SAMPLE_DTYPE = np.dtype([("aggr_task_id", "<u8"), ("pid", "<i4"), ("cpu_pct", "<f4"), ("rss_mb", "<u4"), ("cpu_delay_msec", "<u4"),
+                              ("vm_delay_msec", "<u4"), ("blkio_delay_msec", "<u4"), ("tcp_kbytes", "<u4"), ("tcp_conns", "<u4"), ("state", "u1"),
+                              ("issue", "u1"), ("issue_bit_hist", "u1"), ("severe_issue_bit_hist", "u1"), ("is_issue", "u1"), ("pad", "u1", 3),
+                              ("comm", "S16")])
+assert PROC_SAMPLE_DTYPE.itemsize == 64
 assert RESP16_DTYPE.itemsize == 16 and TCP24_DTYPE.itemsize == 24 and TASK24_DTYPE.itemsize == 24
 NOTIFY_LISTENER_STATE, NOTIFY_TCP_CONN, NOTIFY_AGGR_TASK_STATE, NOTIFY_ACTIVE_CONN_STATS = 0x309, 0x30C, 0x310, 0x312
 (HOSTTOP_SVC_ISSUE, HOSTTOP_SVC_QPS, HOSTTOP_SVC_CONNS, HOSTTOP_SVC_NET, HOSTTOP_TASK_ISSUE, HOSTTOP_TASK_NET, HOSTTOP_TASK_CPU, HOSTTOP_TASK_RSS,
@@ -159,6 +164,7 @@ def load_library(path=None):
         "gysk_hist_bucket": (i32, [i32, C.c_int64]),
         "gysk_hist_percentiles": (i32, [i32, i32, vp, u64, vp, u32, vp]),
         "gysk_classify_listener": (i32, [vp, vp, vp, vp]),
+        "gysk_task_groupby": (i32, [vp, vp, u32, vp, u32, vp]),
         "gysk_hll_estimate": (C.c_double, [vp, u32]),
         "gysk_tdigest_quantile": (C.c_double, [vp, vp, u32, C.c_double, C.c_double, C.c_double]),
         "gysk_uint64_hash": (u32, [u64]),
@@ -323,6 +329,16 @@ class Engine:
         k = C.c_uint32()
         self._chk(self.L.gysk_topn_tasks(self.h, metric, n, out, C.byref(k)))
         return [(o.glob_id, o.score) for o in out[: k.value]]
+
+    def task_groupby(self, samples, cap=None):
+        """gysk_task_groupby: PROC_SAMPLE_DTYPE array -> (wire.TASK records of the groups in order of first appearance, number of groups)"""
+        from .wire import TASK
+        samples = np.ascontiguousarray(samples, dtype=PROC_SAMPLE_DTYPE)
+        cap = len(samples) if cap is None else cap
+        out = np.zeros(max(cap, 1), dtype=TASK)
+        ng = C.c_uint32()
+        self._chk(self.L.gysk_task_groupby(self.h, _p(samples), len(samples), _p(out), cap, C.byref(ng)))
+        return out[: min(ng.value, cap)].copy(), ng.value
 
     def topn_host(self, what, n=10, host_idx=-1):
         out = (TopnEntry * n)()

@@ -383,6 +383,30 @@ int		gysk_export_tdigest(gysk_engine *e, uint64_t glob_id, double *means, uint64
 int		gysk_query_quantiles(gysk_engine *e, uint64_t glob_id, const double *qs, uint32_t nq, double *out);
 int		gysk_export_cms(gysk_engine *e, int last_window, uint64_t *cells /* depth << log2_width entries */);
 
+/* ---- row a15b: the per-process -> per-aggregate-process group-by in front of partha_aggr_task_state ----
+ * One record per process and 5-s tick, holding what TASK_HANDLER's walk has at hand when it folds the process into
+ * aggrnotmap.try_emplace(aggr_task_id) (common/gy_task_handler.cc:752-880). */
+typedef struct gysk_proc_sample
+{
+	uint64_t	aggr_task_id;		/* ptask->aggr_task_id_ */
+	int32_t		pid;			/* ptask->task_pid */
+	float		cpu_pct;		/* avg_cpu_pct / npct: this tick's cpu % averaged with the ticks the server missed (:826-839) */
+	uint32_t	rss_mb;
+	uint32_t	cpu_delay_msec, vm_delay_msec, blkio_delay_msec;	/* last_*_delay_nsec / GY_NSEC_PER_MSEC (:858-860) */
+	uint32_t	tcp_kbytes, tcp_conns;	/* last_sent_tcp_kbytes_ / _conns_: non-zero in the 15-s network ticks only (:791-813) */
+	uint8_t		state;			/* pext->issue_hist_[0].state (OBJ_STATE_E) */
+	uint8_t		issue;			/* pext->issue_hist_[0].issue */
+	uint8_t		issue_bit_hist, severe_issue_bit_hist;
+	uint8_t		is_issue;
+	uint8_t		pad[3];
+	char		comm[16];		/* ptask->task_comm */
+} gysk_proc_sample;
+/* Folds the samples by aggr_task_id IN ARRAY ORDER with the reference's statement order (the float cpu sum sees the same sequence of
+ * additions) and writes one AGGR_TASK_STATE_NOTIFY record (72 bytes, common/gy_comm_proto.h:2114-2170, no issue string) per group,
+ * groups in order of first appearance: the body of a NOTIFY_AGGR_TASK_STATE message, ready for gysk_ingest(). *ngroups = number of
+ * groups found; at most `cap` records are written. n <= gysk_config.max_batch. */
+int		gysk_task_groupby(gysk_engine *e, const gysk_proc_sample *samples, uint32_t n, void *out_records, uint32_t cap, uint32_t *ngroups);
+
 /* ---- pure helpers (host side, no engine): the reference's percentile rule and the sketch estimators ---- */
 int		gysk_hist_nbuckets(int cls);
 int		gysk_hist_bucket(int cls, int64_t value);	/* RESP_TIME_HASH::get_bucket_from_data & siblings */

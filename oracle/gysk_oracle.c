@@ -1238,3 +1238,62 @@ double gyo_bench_ingest(gyo_engine **engines, const gyo_event **shards, const ui
 	free(th); free(args);
 	return (double)(t1.tv_sec - t0.tv_sec) + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-9;
 }
+
+
+/* ---- a15b ------------------------------------------------------------------------------------------------------------------ */
+typedef struct aggr_rec			/* comm::AGGR_TASK_STATE_NOTIFY, common/gy_comm_proto.h:2114-2170 */
+{
+	uint64_t	aggr_task_id;
+	char		onecomm[16];
+	int32_t		pid_arr[2];
+	uint32_t	tcp_kbytes, tcp_conns;
+	float		total_cpu_pct;
+	uint32_t	rss_mb, cpu_delay_msec, vm_delay_msec, blkio_delay_msec;
+	uint16_t	ntasks_total, ntasks_issue;
+	uint8_t		curr_state, curr_issue, issue_bit_hist, severe_issue_bit_hist, issue_string_len, padding_len, pad[2];
+} aggr_rec;
+
+uint32_t gyo_task_groupby(const gyo_proc_sample *recs, uint64_t n, void *out72, uint32_t cap)
+{
+	_Static_assert(sizeof(aggr_rec) == 72 && sizeof(gyo_proc_sample) == 64, "wire sizes");
+	uint64_t	tcap = 16;
+	while (tcap < 2 * n + 2) tcap <<= 1;
+	uint64_t	*keys = (uint64_t *)calloc(tcap, 8);
+	uint32_t	*vals = (uint32_t *)calloc(tcap, 4);
+	aggr_rec	*grp = (aggr_rec *)calloc(n ? n : 1, sizeof(aggr_rec));
+	uint32_t	ng = 0;
+
+	for (uint64_t i = 0; i < n; ++i) {
+		const gyo_proc_sample *p = &recs[i];
+		uint64_t pos = (p->aggr_task_id * 0x9E3779B97F4A7C15ull) >> 20 & (tcap - 1);
+		int fresh = 0;
+		while (keys[pos] != p->aggr_task_id || !vals[pos]) {
+			if (!vals[pos]) { keys[pos] = p->aggr_task_id; vals[pos] = ++ng; fresh = 1; break; }
+			pos = (pos + 1) & (tcap - 1);
+		}
+		aggr_rec *a = &grp[vals[pos] - 1];
+
+		if (p->is_issue) {								/* :763-788 */
+			if (a->ntasks_issue < 2) a->pid_arr[a->ntasks_issue] = p->pid;
+			a->ntasks_issue++;
+			a->curr_issue = p->issue;
+			a->issue_bit_hist |= p->issue_bit_hist;
+			a->severe_issue_bit_hist |= p->severe_issue_bit_hist;
+		}
+		if (a->curr_state < p->state) a->curr_state = p->state;				/* :790 */
+		a->tcp_kbytes += p->tcp_kbytes; a->tcp_conns += p->tcp_conns;			/* :803-804 */
+		a->total_cpu_pct += p->cpu_pct;							/* :839: float accumulate in walk order */
+		a->rss_mb += p->rss_mb;								/* :840 */
+		a->cpu_delay_msec += p->cpu_delay_msec; a->vm_delay_msec += p->vm_delay_msec; a->blkio_delay_msec += p->blkio_delay_msec;	/* :858-860 */
+		a->ntasks_total++;								/* :862 */
+		if (a->ntasks_total == 2) a->pid_arr[1] = p->pid;				/* :864 */
+		if (fresh) {									/* :868-872 */
+			a->aggr_task_id = p->aggr_task_id;
+			memcpy(a->onecomm, p->comm, sizeof(a->onecomm));
+			a->pid_arr[0] = p->pid;
+		}
+	}
+	memcpy(out72, grp, sizeof(aggr_rec) * (ng < cap ? ng : cap));
+	free(keys); free(vals); free(grp);
+	return ng;
+}

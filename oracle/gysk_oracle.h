@@ -154,6 +154,23 @@ void	gyo_listener_state(const gyo_state_in *in, uint8_t *high_resp_bit_hist, uin
 /* what the flush derived for a service: out = {state, issue, issue_bit_hist, high_resp_bit_hist, nconn_active} */
 int	gyo_export_state(gyo_engine *e, uint64_t id, uint32_t out[5]);
 
+/* ---- a15b: the per-process -> per-aggregate-process group-by of TASK_HANDLER's 5-s tick, common/gy_task_handler.cc:752-880:
+ * aggrnotmap.try_emplace(aggr_task_id) per process, in the order the processes are walked ---- */
+typedef struct gyo_proc_sample		/* same layout as gysk_proc_sample (include/gysketch.h), 64 bytes */
+{
+	uint64_t	aggr_task_id;
+	int32_t		pid;
+	float		cpu_pct;		/* avg_cpu_pct / npct, :826-839 */
+	uint32_t	rss_mb;
+	uint32_t	cpu_delay_msec, vm_delay_msec, blkio_delay_msec;	/* nsec / GY_NSEC_PER_MSEC per process, :858-860 */
+	uint32_t	tcp_kbytes, tcp_conns;	/* non-zero only in the 15-s network ticks, :791-813 */
+	uint8_t		state, issue, issue_bit_hist, severe_issue_bit_hist, is_issue, pad[3];
+	char		comm[16];
+} gyo_proc_sample;
+/* out: AGGR_TASK_STATE_NOTIFY records (72 bytes each, common/gy_comm_proto.h:2114-2170), groups in order of first appearance;
+ * returns the number of groups (records beyond cap are not written) */
+uint32_t gyo_task_groupby(const gyo_proc_sample *recs, uint64_t n, void *out72, uint32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -302,3 +302,14 @@ def listener_state(inp, high_resp_bit_hist=0):
     hb, st, iss = C.c_uint8(high_resp_bit_hist), C.c_uint8(), C.c_uint8()
     lib().gyo_listener_state(C.byref(inp), C.byref(hb), C.byref(st), C.byref(iss))
     return st.value, iss.value, hb.value
+
+
+def task_groupby(samples, rec_dtype):
+    """gyo_task_groupby: the CPU statement of row a15b -> records of rec_dtype (72 bytes), groups in order of first appearance"""
+    samples = np.ascontiguousarray(samples)
+    out = np.zeros(max(len(samples), 1), dtype=rec_dtype)
+    L = lib()
+    L.gyo_task_groupby.restype = C.c_uint32
+    L.gyo_task_groupby.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    ng = L.gyo_task_groupby(_p(samples), len(samples), _p(out), len(out))
+    return out[:ng].copy()

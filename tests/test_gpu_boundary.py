@@ -331,3 +331,50 @@ def test_per_host_topn_queues():
         assert [s for _, s, _ in eng.topn_host(what, 10, 4)] == ttop(trows[col], trows[col] > 0)
     sev = ((trows["severe_issue_bit_hist"] & 1).astype(np.int64) * (trows["ntasks_issue"] > 0)) << 32
     assert [s for _, s, _ in eng.topn_host(ge.HOSTTOP_TASK_ISSUE, 10, 4)] == ttop(sev | (trows["ntasks_issue"].astype(np.int64) + 1), trows["curr_state"] > 2)
+
+
+def _proc_samples(rng, n, ngroups):
+    s = np.zeros(n, dtype=ge.PROC_SAMPLE_DTYPE)
+    s["aggr_task_id"] = synth.splitmix64(rng.integers(1, ngroups + 1, n).astype(np.uint64) + np.uint64(1 << 41))
+    s["pid"] = rng.integers(2, 1 << 22, n)
+    # cpu percentages whose float sum depends on the order of the additions
+    s["cpu_pct"] = (rng.random(n) ** 6 * 3000.0 + rng.random(n) * 1e-3).astype(np.float32)
+    s["rss_mb"] = rng.integers(0, 1 << 14, n)
+    for f in ("cpu_delay_msec", "vm_delay_msec", "blkio_delay_msec"):
+        s[f] = np.minimum(np.exp(rng.normal(2.0, 2.5, n)), 1e6).astype(np.uint32)
+    net = rng.random(n) < 0.3
+    s["tcp_kbytes"] = np.where(net, rng.integers(0, 1 << 20, n), 0); s["tcp_conns"] = np.where(net, rng.integers(0, 500, n), 0)
+    s["state"] = rng.integers(0, 5, n); s["issue"] = rng.integers(0, 12, n)
+    s["is_issue"] = rng.random(n) < 0.15
+    s["issue_bit_hist"] = rng.integers(0, 256, n); s["severe_issue_bit_hist"] = rng.integers(0, 256, n)
+    s["comm"] = [b"proc%d" % (i % 97) for i in range(n)]
+    return s
+
+
+def test_task_groupby_equals_the_walk_of_the_reference():
+    """row a15b: per-process samples folded by aggr_task_id in arrival order (common/gy_task_handler.cc:752-880) on the device; every
+    field of every AGGR_TASK_STATE_NOTIFY record — incl. the order-dependent float cpu sum and the pid slots — equals the CPU statement
+    of the walk, groups in order of first appearance; the records are a valid NOTIFY_AGGR_TASK_STATE body for gysk_ingest"""
+    from gyeeta_b200 import wire
+    rng = np.random.default_rng(41)
+    eng = ge.Engine(max_svcs=64, max_tasks=1 << 14, max_batch=1 << 18)
+    for n, ngroups in ((1, 1), (37, 5), (5000, 1200), (200_000, 9000)):
+        s = _proc_samples(rng, n, ngroups)
+        want = po.task_groupby(s, wire.TASK)
+        got, ng = eng.task_groupby(s)
+        assert ng == len(want) == len(np.unique(s["aggr_task_id"]))
+        assert got.tobytes() == want.tobytes(), (n, ngroups)
+        # the float sum really is order-dependent on this data: a sorted-order sum differs somewhere
+        if n >= 5000:
+            resum = np.array([np.sum(np.sort(s["cpu_pct"][s["aggr_task_id"] == g]), dtype=np.float32) for g in want["aggr_task_id"][:300]])
+            assert (resum != want["total_cpu_pct"][:300]).any()
+    # cap smaller than the number of groups: the first `cap` groups, the count still complete
+    part, ng = eng.task_groupby(s, cap=100)
+    assert ng == len(want) and part.tobytes() == want[:100].tobytes()
+    # feed the first 1200 records (MAX_NUM_TASKS per message) to the engine as partha would send them
+    recs = want[:1200]
+    msg = wire.build_msg_fixed(ge.NOTIFY_AGGR_TASK_STATE, recs)
+    assert eng.ingest_msg(msg, host_idx=1) == 0
+    eng.sync()
+    st = eng.stats()
+    assert st["events_task"] == int((recs["aggr_task_id"] != 0).sum()) and st["wire_msgs_ok"] == 1

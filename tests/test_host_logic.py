@@ -345,3 +345,30 @@ def test_listener_state_classifier_random_inputs_agree():
         assert g == o, (g, o)
         seen.add(g[:2])
     assert len(seen) == 18, sorted(seen)            # every (state, issue) pair the tree can produce
+
+
+def test_task_groupby_oracle_hand_case():
+    """the CPU statement of row a15b on a hand-made walk (common/gy_task_handler.cc:763-872): pid slots, issue fields, float order"""
+    from gyeeta_b200 import engine as ge, wire
+    from oracle import pyoracle as po
+    s = np.zeros(5, dtype=ge.PROC_SAMPLE_DTYPE)
+    s["aggr_task_id"] = [7, 9, 7, 7, 9]
+    s["pid"] = [100, 200, 101, 102, 201]
+    s["cpu_pct"] = np.array([1e8, 3.0, 1.0, -1e8, 0.5], dtype=np.float32)      # (1e8 + 1) - 1e8 = 0 in float, 1 in any other order
+    s["is_issue"] = [0, 1, 1, 1, 0]
+    s["issue"] = [0, 4, 5, 6, 0]
+    s["state"] = [2, 3, 4, 1, 2]
+    s["issue_bit_hist"] = [1, 2, 4, 8, 16]; s["severe_issue_bit_hist"] = [1, 2, 4, 8, 16]
+    s["rss_mb"] = [10, 20, 30, 40, 50]; s["cpu_delay_msec"] = [1, 2, 3, 4, 5]; s["tcp_kbytes"] = [0, 7, 0, 9, 0]
+    s["comm"] = [b"a", b"b", b"c", b"d", b"e"]
+    out = po.task_groupby(s, wire.TASK)
+    assert list(out["aggr_task_id"]) == [7, 9]                                 # order of first appearance
+    g7, g9 = out[0], out[1]
+    assert g7["total_cpu_pct"] == np.float32(0.0) and g9["total_cpu_pct"] == np.float32(3.5)
+    assert g7["ntasks_total"] == 3 and g7["ntasks_issue"] == 2 and g7["curr_state"] == 4 and g7["curr_issue"] == 6
+    # pid slots: first process -> [0]; first issue process overwrites [0] (:764-766), second issue process -> [1]; the second
+    # process of the group also lands in [1] (:864) before that
+    assert list(g7["pid_arr"]) == [101, 102] and list(g9["pid_arr"]) == [200, 201]
+    assert g7["issue_bit_hist"] == 12 and g7["severe_issue_bit_hist"] == 12 and g9["issue_bit_hist"] == 2
+    assert g7["rss_mb"] == 80 and g7["cpu_delay_msec"] == 8 and g7["tcp_kbytes"] == 9 and g9["tcp_kbytes"] == 7
+    assert g7["onecomm"] == b"a" and g9["onecomm"] == b"b"
