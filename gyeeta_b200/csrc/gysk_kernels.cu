@@ -191,7 +191,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 // The histogram cells and the t-digest of a service are produced from its bins by bins_merge_kernel after the batch.
 struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
 
-template <int WARPS, int EPT, bool TMA>
+template <int WARPS, int EPT, bool TMA, int DH>
 struct IngestSharedT
 {
 	static constexpr int CHUNK = 32 * EPT;			// events per warp and round
@@ -204,14 +204,14 @@ struct IngestSharedT
 	unsigned long long	mbar[TMA ? WARPS : 1];
 	Warp		w[WARPS];
 	HotTable	hot;
-	uint32_t	dhist[OS_MAX_PASSES_VK][RADIX_MAX];		// digit histograms of this CTA's keys, one per radix pass
+	uint32_t	dhist[OS_MAX_PASSES_VK][DH];			// digit histograms of this CTA's keys, one per radix pass (DH = 256 unless a pass has 9-bit digits)
 };
 
-template <int WARPS, int MIN_CTAS, int EPT, bool TMA>
+template <int WARPS, int MIN_CTAS, int EPT, bool TMA, int DH>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
 		unsigned long long *__restrict__ keys, uint32_t *__restrict__ ghist, SortPlan plan)
 {
-	using Shared = IngestSharedT<WARPS, EPT, TMA>;
+	using Shared = IngestSharedT<WARPS, EPT, TMA, DH>;
 	using HotTable = typename Shared::HotTable;
 	constexpr int CHUNK = Shared::CHUNK;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 	unsigned long long t_tcp = 0, t_task = 0;			// queued in total (warp-uniform)
 
 	for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) { S.hot.tag[i] = 0; S.hot.count[i] = 0; S.hot.sum[i] = 0; S.hot.vmax[i] = INT_MIN; }
-	for (int i = threadIdx.x; i < OS_MAX_PASSES_VK * RADIX_MAX; i += WARPS * 32) (&S.dhist[0][0])[i] = 0;
+	for (int i = threadIdx.x; i < OS_MAX_PASSES_VK * DH; i += WARPS * 32) (&S.dhist[0][0])[i] = 0;
 	if (TMA && lane == 0) mbar_init(&S.mbar[wid], 1);
 	__syncthreads();						// the only block barriers: here and before the retire step
 	if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");	// mbarrier init visible to the async proxy
@@ -432,9 +432,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 	for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) {
 		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i]);
 	}
-	for (int i = threadIdx.x; i < plan.np * RADIX_MAX; i += WARPS * 32) {
+	for (int i = threadIdx.x; i < plan.np * DH; i += WARPS * 32) {
 		const uint32_t c = (&S.dhist[0][0])[i];
-		if (c) atomicAdd(ghist + i, c);
+		if (c) atomicAdd(ghist + (i / DH) * RADIX_MAX + (i % DH), c);		// the passes read their histogram at stride RADIX_MAX
 	}
 
 	// statsmap-style counters (gy_mconnhdlr.cc:4708-4715): warp-reduce, one atomic per warp and counter
@@ -1397,19 +1397,19 @@ static int key_sort_plan(uint32_t max_svcs, SortPlan &P)
 	return np;
 }
 
-template <int WARPS, int MIN_CTAS, int EPT, bool TMA>
+template <int WARPS, int MIN_CTAS, int EPT, bool TMA, int DH>
 static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, uint32_t *ghist, const SortPlan &plan,
 		int dev, cudaStream_t s)
 {
-	using Shared = IngestSharedT<WARPS, EPT, TMA>;
+	using Shared = IngestSharedT<WARPS, EPT, TMA, DH>;
 	static bool attr_set[MAX_DEVICES] = {};
 	if (!attr_set[dev]) {
-		cudaFuncSetAttribute(ingest_kernel<WARPS, MIN_CTAS, EPT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+		cudaFuncSetAttribute(ingest_kernel<WARPS, MIN_CTAS, EPT, TMA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
 		attr_set[dev] = true;
 	}
 	const uint64_t want = (n + (uint64_t)Shared::CHUNK * WARPS - 1) / ((uint64_t)Shared::CHUNK * WARPS);
 	const uint64_t full = (uint64_t)sm_count(dev) * MIN_CTAS;
-	ingest_kernel<WARPS, MIN_CTAS, EPT, TMA><<<(uint32_t)(want < full ? want : full), WARPS * 32, sizeof(Shared), s>>>(st, d_ev, n, d_keys, ghist, plan);
+	ingest_kernel<WARPS, MIN_CTAS, EPT, TMA, DH><<<(uint32_t)(want < full ? want : full), WARPS * 32, sizeof(Shared), s>>>(st, d_ev, n, d_keys, ghist, plan);
 }
 
 int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_ev, uint64_t n, uint32_t max_svcs, cudaStream_t s)
@@ -1421,7 +1421,10 @@ int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_e
 	// key cursor, digit histograms and tile tickets of this batch's sort
 	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, sizeof(unsigned long long), s);
 	cudaMemsetAsync(tmp.os_ghist, 0, (OS_MAX_PASSES * RADIX_MAX + OS_MAX_PASSES) * sizeof(uint32_t), s);
-#define GYSK_LI(W, C, E, T) launch_ingest_variant<W, C, E, T>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s)
+	bool wide = false;
+	for (int p = 0; p < plan.np; ++p) wide |= plan.bits[p] > 8;
+#define GYSK_LI(W, C, E, T) do { if (wide) launch_ingest_variant<W, C, E, T, 512>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); \
+		else launch_ingest_variant<W, C, E, T, 256>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); } while (0)
 	switch (ingest_variant()) {
 	case 842 : GYSK_LI(8, 4, 2, false); break;
 	case 852 : GYSK_LI(8, 5, 2, false); break;

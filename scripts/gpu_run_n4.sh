@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_nccl.py -x -q > gpurun_out/r02e_nccl_tests.log 2>&1; tail -5 gpurun_out/r02e_nccl_tests.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 tests/run_config3.py > gpurun_out/r02e_config3_n4.out 2>&1; grep '^{"config' gpurun_out/r02e_config3_n4.out > gpurun_out/r02e_config3_n4.json; tail -c 1200 gpurun_out/r02e_config3_n4.json; tail -5 gpurun_out/r02e_config3_n4.out | cut -c1-300
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02e_bench_n4.out 2>&1; grep '^{"metric' gpurun_out/r02e_bench_n4.out > gpurun_out/r02e_bench_n4.json; tail -c 300 gpurun_out/r02e_bench_n4.json
+echo done

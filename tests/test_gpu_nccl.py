@@ -111,9 +111,10 @@ def test_two_engines_on_two_devices_in_one_process():
     for e_, o_ in zip(engs, orcs):
         e_.ingest_events(ev); e_.sync(); o_.ingest(ev)
         e_.flush(5); o_.flush(5)
-    ids = np.unique(ev["svc_id"][ev["type"] == ge.EV_RESP])
+    resp = ev[ev["type"] == ge.EV_RESP]
+    ids, first = np.unique(resp["svc_id"], return_index=True)
     checked = 0
-    for id_, h in zip(ids, ev["host_idx"][np.unique(ev["svc_id"][ev["type"] == ge.EV_RESP], return_index=True)[1]]):
+    for id_, h in zip(ids, resp["host_idx"][first]):
         e_, o_ = engs[int(h) % 2], orcs[int(h) % 2]
         a, b = e_.export_hist(int(id_), ge.HIST_RESP_LAST), o_.export_hist(int(id_), ge.HIST_RESP_LAST)
         assert (a is None) == (b is None)
