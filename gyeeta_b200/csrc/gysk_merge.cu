@@ -28,23 +28,21 @@ namespace gysk {
 
 struct SlabEntry { TdHead head; Centroid cent[TD_CAP]; };
 
-__global__ void resolve_slots_kernel(DevState st, const unsigned long long *__restrict__ ids, uint32_t n, int32_t *__restrict__ slots)
-{
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) slots[i] = ids[i] ? table_lookup(st.svc_tbl, ids[i], false) : -1;
-}
-
-// a member whose slot was evicted (or recycled for another id) since the map was set folds the engine's null slot instead
-// (index max_svcs: always in its just-created state)
-__global__ void validate_members_kernel(DevState st, uint32_t *__restrict__ members, const unsigned long long *__restrict__ member_ids, uint32_t n,
+// The map keeps every {glob_id, logical} pair it was given; which of them live on this GPU, and in which slot, is looked up at
+// every merge: a service that registers after gysk_set_logical_map takes part from its first window on, one that was evicted (or whose
+// slot now belongs to another id) drops out. An id without a slot maps to the engine's null slot (index max_svcs: always in its
+// just-created state, the identity of every fold), which the fold kernels skip.
+__global__ void resolve_members_kernel(DevState st, const unsigned long long *__restrict__ member_ids, uint32_t n, uint32_t *__restrict__ members,
 		uint32_t null_slot)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n && members[i] != null_slot && st.slot_id[members[i]] != member_ids[i]) members[i] = null_slot;
+	if (i >= n) return;
+	const int slot = member_ids[i] ? table_lookup(st.svc_tbl, member_ids[i], false) : -1;
+	members[i] = slot >= 0 ? (uint32_t)slot : null_slot;
 }
 
 // one thread per (logical, cell)
-__global__ void fold_hist_kernel(DevState st, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ members, uint32_t nl,
+__global__ void fold_hist_kernel(DevState st, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ members, uint32_t nl, uint32_t null_slot,
 		HistCell *__restrict__ l_last, HistCell *__restrict__ l_all, unsigned long long *__restrict__ l_conn, long long *__restrict__ l_hmax)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,6 +54,7 @@ __global__ void fold_hist_kernel(DevState st, const uint32_t *__restrict__ offs,
 	if (cell < HIST_MAX_CELL) {
 		HistCell a {0, 0}, c {0, 0};
 		for (uint32_t m = b; m < e; ++m) {
+			if (members[m] == null_slot) continue;
 			const HistCell x = st.hist_last[(size_t)members[m] * HIST_CELLS + cell], y = st.hist_all[(size_t)members[m] * HIST_CELLS + cell];
 			a.count += x.count; a.sum += x.sum; c.count += y.count; c.sum += y.sum;
 		}
@@ -66,6 +65,7 @@ __global__ void fold_hist_kernel(DevState st, const uint32_t *__restrict__ offs,
 		unsigned long long lc = 0, lk = 0, ac = 0, ak = 0;
 		for (uint32_t m = b; m < e; ++m) {
 			const uint32_t s = members[m];
+			if (s == null_slot) continue;
 			ml = max(ml, st.hist_last[(size_t)s * HIST_CELLS + HIST_MAX_CELL].sum);
 			ma = max(ma, st.hist_all[(size_t)s * HIST_CELLS + HIST_MAX_CELL].sum);
 			const unsigned long long cl = st.conn_last[s];
@@ -78,7 +78,8 @@ __global__ void fold_hist_kernel(DevState st, const uint32_t *__restrict__ offs,
 }
 
 // one thread per (logical, 4 registers): per-byte max over the member services
-__global__ void fold_hll_kernel(DevState st, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ members, uint32_t nl, uint32_t *__restrict__ l_hll)
+__global__ void fold_hll_kernel(DevState st, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ members, uint32_t nl, uint32_t null_slot,
+		uint32_t *__restrict__ l_hll)
 {
 	const uint32_t words = 1u << (st.hll_p - 2);
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,6 +88,7 @@ __global__ void fold_hll_kernel(DevState st, const uint32_t *__restrict__ offs, 
 	uint32_t acc = 0;
 
 	for (uint32_t m = offs[l]; m < offs[l + 1]; ++m) {
+		if (members[m] == null_slot) continue;
 		acc = __vmaxu4(acc, reinterpret_cast<const uint32_t *>(st.hll + ((size_t)members[m] << st.hll_p))[w]);
 	}
 	l_hll[i] = acc;
@@ -96,7 +98,7 @@ static constexpr int MG_WARPS = 2;		// 2 x 17.8 KB of scratch: static shared mem
 
 // one warp per logical service: fold member digests one after the other (member order = slot order of the map call)
 __global__ void __launch_bounds__(MG_WARPS * 32) fold_td_kernel(DevState st, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ members,
-		uint32_t nl, SlabEntry *__restrict__ slab)
+		uint32_t nl, uint32_t null_slot, SlabEntry *__restrict__ slab)
 {
 	__shared__ TdScratch scratch[MG_WARPS];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(MG_WARPS * 32) fold_td_kernel(DevState st, con
 
 		for (uint32_t m = offs[l]; m < offs[l + 1]; ++m) {
 			const uint32_t s = members[m];
+			if (s == null_slot) continue;
 			const TdHead h = st.td_head[s];
 			if (!h.n) continue;
 			nacc = warp_merge_compress(S, S.newc, nacc, st.td_cent + (size_t)s * TD_CAP, h.n, S.newc, st.td);
@@ -282,31 +285,14 @@ int gysk_set_logical_map(gysk_engine *e, const uint64_t *glob_ids, const uint64_
 	}
 	const uint32_t nl = (uint32_t)mg.logical_ids.size();
 
-	// resolve glob_id -> slot on the device (the table lives there)
-	std::vector<int32_t> slots(n, -1);
-	{
-		unsigned long long *d_ids = nullptr; int32_t *d_slots = nullptr;
-		if (n) {
-			CU(e, cudaMalloc(&d_ids, (size_t)n * sizeof(uint64_t)));
-			CU(e, cudaMalloc(&d_slots, (size_t)n * sizeof(int32_t)));
-			CU(e, cudaMemcpyAsync(d_ids, glob_ids, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
-			resolve_slots_kernel<<<div_up(n, 256), 256, 0, e->stream>>>(e->st, d_ids, n, d_slots);
-			e->kernel_launches++;
-			CU(e, cudaMemcpyAsync(slots.data(), d_slots, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-			CU(e, cudaStreamSynchronize(e->stream));
-			cudaFree(d_ids); cudaFree(d_slots);
-		}
-	}
-
-	// CSR logical -> member slots present on this GPU
-	std::vector<uint32_t> offs(nl + 1, 0), members;
-	std::vector<uint64_t> member_ids;
-	for (uint32_t i = 0; i < n; ++i) if (slots[i] >= 0) offs[lidx[i] + 1]++;
+	// CSR logical -> every {glob_id} mapped to it, in map order; the slots are looked up at merge time (resolve_members_kernel)
+	std::vector<uint32_t> offs(nl + 1, 0), members(n, e->cfg.max_svcs);
+	std::vector<uint64_t> member_ids(n);
+	for (uint32_t i = 0; i < n; ++i) offs[lidx[i] + 1]++;
 	for (uint32_t l = 0; l < nl; ++l) offs[l + 1] += offs[l];
-	members.resize(offs[nl]); member_ids.resize(offs[nl]);
 	{
 		std::vector<uint32_t> cur(offs.begin(), offs.end() - 1);
-		for (uint32_t i = 0; i < n; ++i) if (slots[i] >= 0) { member_ids[cur[lidx[i]]] = glob_ids[i]; members[cur[lidx[i]]++] = (uint32_t)slots[i]; }
+		for (uint32_t i = 0; i < n; ++i) member_ids[cur[lidx[i]]++] = glob_ids[i];
 	}
 
 	// (re)allocate the arena
@@ -372,15 +358,16 @@ int gysk_merge_prepare(gysk_engine *e)
 	CU(e, cudaMemcpyAsync(mg.g_cms_cur, e->st.cms_cur, b_cms, cudaMemcpyDeviceToDevice, e->stream));
 	CU(e, cudaMemcpyAsync(mg.g_cms_last, e->st.cms_last, b_cms, cudaMemcpyDeviceToDevice, e->stream));
 	if (nl) {
-		if (mg.nmembers && e->cfg.idle_evict_secs) {
-			validate_members_kernel<<<div_up(mg.nmembers, 256), 256, 0, e->stream>>>(e->st, mg.d_members, mg.d_member_ids, mg.nmembers, e->cfg.max_svcs);
+		const uint32_t null_slot = e->cfg.max_svcs;
+		if (mg.nmembers) {
+			resolve_members_kernel<<<div_up(mg.nmembers, 256), 256, 0, e->stream>>>(e->st, mg.d_member_ids, mg.nmembers, mg.d_members, null_slot);
 			e->kernel_launches++;
 		}
-		fold_hist_kernel<<<div_up((uint64_t)nl * HIST_CELLS, 256), 256, 0, e->stream>>>(e->st, mg.d_offsets, mg.d_members, nl,
+		fold_hist_kernel<<<div_up((uint64_t)nl * HIST_CELLS, 256), 256, 0, e->stream>>>(e->st, mg.d_offsets, mg.d_members, nl, null_slot,
 				mg.l_hist_last, mg.l_hist_all, mg.l_conn, mg.l_hmax);
-		fold_hll_kernel<<<div_up((uint64_t)nl << (e->cfg.hll_p - 2), 256), 256, 0, e->stream>>>(e->st, mg.d_offsets, mg.d_members, nl,
+		fold_hll_kernel<<<div_up((uint64_t)nl << (e->cfg.hll_p - 2), 256), 256, 0, e->stream>>>(e->st, mg.d_offsets, mg.d_members, nl, null_slot,
 				reinterpret_cast<uint32_t *>(mg.l_hll));
-		fold_td_kernel<<<std::min<uint32_t>(div_up(nl, MG_WARPS), 148 * 8), MG_WARPS * 32, 0, e->stream>>>(e->st, mg.d_offsets, mg.d_members, nl,
+		fold_td_kernel<<<std::min<uint32_t>(div_up(nl, MG_WARPS), 148 * 8), MG_WARPS * 32, 0, e->stream>>>(e->st, mg.d_offsets, mg.d_members, nl, null_slot,
 				reinterpret_cast<SlabEntry *>(mg.slab));
 		e->kernel_launches += 3;
 	}

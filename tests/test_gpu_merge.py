@@ -99,3 +99,27 @@ def test_two_shards_merge_to_global_answers():
     gc = one.query_flows(keys, last_window=True)
     assert np.array_equal(ga["count"], gc["count"]) and np.array_equal(ga["kbytes"], gc["kbytes"])
     assert shards[0].query_logical([999999])[0]["found"] == 0
+
+
+def test_logical_map_set_before_the_services_register():
+    """gysk_set_logical_map keeps every {glob_id, logical} pair and looks the slots up at every merge: a map handed over before any
+    event arrived (or naming services that register later) gives the same merged answers as one set afterwards"""
+    import torch
+    rng = np.random.default_rng(23)
+    nsvc = 200
+    ids = synth.service_ids(nsvc)
+    logical = (np.arange(nsvc, dtype=np.uint64) // np.uint64(8)) + np.uint64(500)
+    kw = dict(max_svcs=512, max_tasks=32, max_batch=1 << 15, cms_log2_width=12)
+    early, late = ge.Engine(**kw), ge.Engine(**kw)
+    early.set_logical_map(ids, logical)                              # nothing is registered yet
+    for w in range(2):
+        ev = synth.gen_mixed(rng, 40_000, nsvc // 2 if w == 0 else nsvc, ntask=8, nhosts=16, nclients=2000)   # half of the services appear in window 2
+        for e in (early, late):
+            e.ingest_events(ev); e.sync(); e.flush(5 * (w + 1))
+        if w == 0:
+            late.set_logical_map(ids, logical)                      # after the first half registered, before the second
+        _emulate_collectives(torch, [early]); _emulate_collectives(torch, [late])
+        lids = np.unique(logical)
+        a, b = early.query_logical(lids), late.query_logical(lids)
+        assert a == b
+        assert sum(x["nqrys_5s"] for x in a) == int((ev["type"] == ge.EV_RESP).sum())
