@@ -121,5 +121,5 @@ def test_logical_map_set_before_the_services_register():
         _emulate_collectives(torch, [early]); _emulate_collectives(torch, [late])
         lids = np.unique(logical)
         a, b = early.query_logical(lids), late.query_logical(lids)
-        assert a == b
+        assert repr(a) == repr(b)                                   # (NaN quantiles of empty logical services compare by text)
         assert sum(x["nqrys_5s"] for x in a) == int((ev["type"] == ge.EV_RESP).sum())
