@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 		int rank_mode /* 0 auto, 1 match.any, 2 ballots */)
 {
 	constexpr int RADIX = 1 << RBITS;
-	constexpr int DPT = RADIX / OS_THREADS;		// digits per thread in the per-digit steps
+	constexpr int DPT = RADIX >= OS_THREADS ? RADIX / OS_THREADS : 1;	// digits per thread in the per-digit steps (threads >= RADIX idle there)
 	extern __shared__ __align__(16) unsigned char os_smem[];
 	OneSweepSharedT<RBITS> &S = *reinterpret_cast<OneSweepSharedT<RBITS> *>(os_smem);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -611,6 +611,7 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 		float distinct = 0.f;
 #pragma unroll
 		for (int j = 0; j < DPT; ++j) {
+			if (threadIdx.x + j * OS_THREADS >= RADIX) continue;
 			const float pd = (float)ghist[threadIdx.x + j * OS_THREADS] / (float)n;
 			float q = 1.f - pd; q *= q; q *= q; q *= q; q *= q; q *= q;		// (1 - p)^32
 			distinct += 1.f - q;
@@ -663,6 +664,8 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 	for (int j = 0; j < DPT; ++j) {
 		const uint32_t d = threadIdx.x + j * OS_THREADS;
 		uint32_t run = 0;
+		dtotal[j] = 0;
+		if (d >= RADIX) continue;
 #pragma unroll
 		for (int w = 0; w < OS_WARPS; ++w) { const uint32_t t = S.whist[w][d]; S.whist[w][d] = run; run += t; }
 		dtotal[j] = run;
@@ -674,8 +677,10 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 		const uint32_t d = threadIdx.x + j * OS_THREADS;
 		unsigned long long tot = 0;
 		// {global count of digit d, tile count of digit d} -> exclusive scans over the digits in one go
-		const unsigned long long sc = carry + os_block_exclusive_scan(((unsigned long long)ghist[d] << 16) | dtotal[j], S.scan[j], DPT > 1 ? &tot : nullptr);
+		const bool own = d < RADIX;
+		const unsigned long long sc = carry + os_block_exclusive_scan(own ? (((unsigned long long)ghist[d] << 16) | dtotal[j]) : 0ull, S.scan[j], DPT > 1 ? &tot : nullptr);
 		carry += tot;
+		if (!own) continue;
 		const uint32_t gexcl = (uint32_t)(sc >> 16), dstart = (uint32_t)(sc & 0xFFFFu);
 		// decoupled look-back: keys with digit d in the tiles before this one
 		uint32_t excl = 0;
@@ -1479,6 +1484,8 @@ static void os_set_attrs(int dev)
 {
 	static bool attr_set[MAX_DEVICES] = {};
 	if (attr_set[dev]) return;
+	cudaFuncSetAttribute(os_pass_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<6>));
+	cudaFuncSetAttribute(os_pass_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<7>));
 	cudaFuncSetAttribute(os_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<8>));
 	cudaFuncSetAttribute(os_pass_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSweepSharedT<9>));
 	cudaFuncSetAttribute(os_hist_kernel<8, 257>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_MAX_PASSES * 8 * 257 * (int)sizeof(uint32_t));
@@ -1497,6 +1504,18 @@ static uint32_t next_epoch(const SortTemp &tmp, uint32_t max_tiles, cudaStream_t
 }
 
 static const int g_rank_mode = []{ const char *e = getenv("GYSK_OS_RANK"); return e ? atoi(e) : 0; }();
+
+// one radix pass with the kernel instantiation of the digit's width: a 7-bit digit has half the per-digit work (per-warp counters to
+// clear and prefix, status words to publish and look back through, ballots per key) of an 8-bit one
+static void launch_os_pass(int bits, uint32_t ntiles, const unsigned long long *in, unsigned long long *out, const unsigned long long *d_n, const DigitSpec &D,
+		const uint32_t *ghist, unsigned long long *status, uint32_t *ticket, uint32_t epoch, cudaStream_t s)
+{
+	static const bool narrow = []{ const char *e = getenv("GYSK_OS_NARROW"); return !e || atoi(e) != 0; }();
+	if (bits > 8) os_pass_kernel<9><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(in, out, d_n, D, ghist, status, ticket, epoch, g_rank_mode);
+	else if (bits == 8 || !narrow) os_pass_kernel<8><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(in, out, d_n, D, ghist, status, ticket, epoch, g_rank_mode);
+	else if (bits == 7) os_pass_kernel<7><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<7>), s>>>(in, out, d_n, D, ghist, status, ticket, epoch, g_rank_mode);
+	else os_pass_kernel<6><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<6>), s>>>(in, out, d_n, D, ghist, status, ticket, epoch, g_rank_mode);
+}
 
 // stable LSD radix sort of the *d_n keys in keys_a on their own bits (plain mode, the top-N sorts): n_max >= *d_n sizes the grids
 int launch_radix_sort(const SortTemp &tmp, const unsigned long long *d_n, uint64_t n_max, int lo1, int hi1, int lo2, int hi2, int *which, cudaStream_t s)
@@ -1525,8 +1544,8 @@ int launch_radix_sort(const SortTemp &tmp, const unsigned long long *d_n, uint64
 	for (int p = 0; p < P.np; ++p) {
 		const bool nine = P.d[p].b1 + P.d[p].b2 > 8;
 		const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
-		if (nine) os_pass_kernel<9><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], d_n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
-		else os_pass_kernel<8><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], d_n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
+		(void)nine;
+		launch_os_pass(P.d[p].b1 + P.d[p].b2, ntiles, bufs[w], bufs[w ^ 1], d_n, P.d[p], ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, s);
 		launches++;
 		w ^= 1;
 	}
@@ -1556,8 +1575,7 @@ int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint64_t n_event
 	for (int p = 0; p < plan.np; ++p) {
 		const DigitSpec D { plan.shift[p], plan.bits[p], 0, 0 };
 		const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
-		if (plan.bits[p] > 8) os_pass_kernel<9><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(bufs[w], bufs[w ^ 1], d_nkeys, D, ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
-		else os_pass_kernel<8><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(bufs[w], bufs[w ^ 1], d_nkeys, D, ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, g_rank_mode);
+		launch_os_pass(plan.bits[p], ntiles, bufs[w], bufs[w ^ 1], d_nkeys, D, ghist + p * RADIX_MAX, tmp.tile_status, tickets + p, epoch, s);
 		launches++;
 		w ^= 1;
 	}
