@@ -512,6 +512,7 @@ def main():
     eng.sync()
     barrier()
     dev_ms = t0.elapsed_time(t1)
+    launches = eng.stats()["kernel_launches"] - launches0           # kernels of libgysketch.so launched inside the timed region
     ms_ing, ms_td, nb = eng.profile_read()
     # diagnostic (outside the timed region): per-step spread of the two kernel groups
     spread = {"ingest_ms": [], "chain_ms": []}
@@ -521,7 +522,6 @@ def main():
         spread["ingest_ms"].append(round(a, 3)); spread["chain_ms"].append(round(b, 3))
     eng.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
-    launches = eng.stats()["kernel_launches"] - launches0
     merge_events_value = merge_events[-1:] if merge_events else []
 
     tms = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
