@@ -253,9 +253,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -263,8 +263,12 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        # samples that arrived while the timed region ran; when the region is shorter than the sampler's reaction time, the samples of
+        # the whole loaded period (warm-up steps, timed region, diagnostic steps) stand in — all of them under the same load
+        inside = [r for t, r in self.rows if t_begin is not None and t_begin <= t <= t_end + 0.03]
+        use = inside if len(inside) >= 2 else [r for _t, r in self.rows]
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        for r in use:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -276,7 +280,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
 def ncu_traffic_per_event():
@@ -491,16 +495,17 @@ def main():
         from gyeeta_b200 import dist as gd
         setup_logical_map()
         gd.nccl_comm_init(eng, dist)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                # before the warm-up steps: nvidia-smi needs a few hundred ms to deliver its first sample
     for _ in range(args.warmup):
         step_device()
     merge_step()
     eng.sync()
     launches0 = eng.stats()["kernel_launches"]
     eng.profile_enable(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
+    wall_begin = time.perf_counter()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         t0.record()
@@ -510,6 +515,7 @@ def main():
     with torch.cuda.stream(stream):
         t1.record()
     eng.sync()
+    wall_end = time.perf_counter()
     barrier()
     dev_ms = t0.elapsed_time(t1)
     launches = eng.stats()["kernel_launches"] - launches0           # kernels of libgysketch.so launched inside the timed region
@@ -521,7 +527,7 @@ def main():
         a, b, _nb = eng.profile_read()
         spread["ingest_ms"].append(round(a, 3)); spread["chain_ms"].append(round(b, 3))
     eng.profile_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall_begin, wall_end) if rank == 0 else None
     merge_events_value = merge_events[-1:] if merge_events else []
 
     tms = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
