@@ -1,16 +1,19 @@
 // gysk_kernels.cu — hand-written sm_100a kernels of the streaming-sketch engine.
 //
 //   ingest_kernel        one pass over a batch of 32-byte events: id -> slot, then per event type
-//                          RESP : two REDs into the service's log-linear value bin {samples, usec sum, sub-msec remainders},
-//                                 CONN_BITMAP bit, batch min / max
+//                          RESP : one 64-bit sort key {slot | value bin | usec}; CONN_BITMAP bit, batch min / max when they change
 //                          TCP  : count-min cell adds, HLL register max, per-service exact cell
 //                          TASK : MAGGR_TASK::set_local_task_state (3 histograms)     server/gy_msocket.h:1009-1018
-//   touched_kernel       list of the services that received RESP samples in this batch
-//   bins_merge_kernel    per touched service: bins -> GY_HISTOGRAM::add_data for every sample (RESP_TIME_HASH, common/gy_statistics.h:
+//                          ACTIVE : ACTIVE_CONN_STATS records                          server/gy_mconnhdlr.cc:7705
+//   os_pass_kernel       stable one-sweep LSD radix pass (RESP keys of a batch on {slot, bin}; the top-N rankings)
+//   runs_mark_kernel     sorted keys -> runs (one per non-empty value bin of a service), service segments, touched list
+//   runs_sum_kernel      per run: samples, exact usec sum
+//   bins_merge_kernel    per touched service: runs -> GY_HISTOGRAM::add_data for every sample (RESP_TIME_HASH, common/gy_statistics.h:
 //                        596-623, :1698) and -> the merging t-digest (K_1 scale)               DESIGN.md §2
-//   os_pass_kernel       stable one-sweep LSD radix sort (the top-N rankings)
 //   flush_kernel         5-s window roll                                               common/gy_socket_stat.cc:3898
-//   gather_* / query_*   read side
+//   state_kernel         listener state of the closed window (get_curr_state)          common/gy_socket_stat.cc:2020-2875
+//   evict_kernel         idle listeners leave, slots recycled                          common/gy_socket_stat.cc:3968-4037
+//   gather_* / query_* / topn_*   read side
 #include "gysk_kernels.cuh"
 #include "gysk_state.cuh"
 
