@@ -428,6 +428,9 @@ double		gysk_tdigest_quantile(const double *means, const uint64_t *weights, uint
 uint32_t	gysk_uint64_hash(uint64_t key);		/* get_uint64_hash, common/gy_common_inc.h:1120 */
 
 /* ---- multi-GPU merge ---- */
+/* Which services form a logical service (the reference's svc-mesh cluster id). The same list on every rank; dense logical indices
+ * follow first appearance. Ids need not be registered (or owned by this rank): the map keeps every pair and looks the slots up at
+ * every gysk_merge_prepare / gysk_merge_global. */
 int		gysk_set_logical_map(gysk_engine *e, const uint64_t *glob_ids, const uint64_t *logical_ids, uint32_t n);
 int		gysk_merge_prepare(gysk_engine *e);		/* fold per-service sketches into per-logical-service arrays; asynchronous on
 							   gysk_stream(e): enqueue the collectives on that stream, or gysk_sync() first */
