@@ -36,7 +36,9 @@ __device__ __forceinline__ uint32_t key_usec(unsigned long long k) { return (uin
 __device__ __forceinline__ uint32_t key_slot(unsigned long long k) { return (uint32_t)(k >> KEY_SLOT_SHIFT); }
 __device__ __forceinline__ uint32_t key_bin(unsigned long long k) { return (uint32_t)(k >> KEY_GROUP_SHIFT) & ((1u << TD_CODE_BITS) - 1u); }
 
-struct SortPlan { int np; int shift[OS_MAX_PASSES_VK]; int bits[OS_MAX_PASSES_VK]; };	// digit p = (key >> shift[p]) & ((1 << bits[p]) - 1)
+struct SortPlan { int np; int shift[OS_MAX_PASSES_VK]; int bits[OS_MAX_PASSES_VK]; int exp; };	// digit p = (key >> shift[p]) & ((1 << bits[p]) - 1)
+// exp: ABLATION switches for timing runs only (GYSK_EXP_ABLATE; results are wrong when set): 1 = no batch-extreme / CONN_BITMAP loads and
+// atomics, 2 = no digit histograms, 4 = no TCP drain, 8 = no TASK drain
 
 // ---------------------------------------------------------------------------------------------------
 // state init / registration
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 			const unsigned long long k = W.kq[q];
 #pragma unroll
 			for (int p = 0; p < OS_MAX_PASSES_VK; ++p)
-				if (p < plan.np) atomicAdd(&S.dhist[p][(uint32_t)(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
+				if (p < plan.np && !(plan.exp & 2)) atomicAdd(&S.dhist[p][(uint32_t)(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
 			__stcs(keys + base + q, k);
 		}
 		nk = 0;
@@ -369,8 +371,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 				const uint32_t v = rb[k].x, ms = v / 1000u;		// usec -> msec as SVC_INFO_CAP::upd_stats_on_req (gy_proto_parser.cc:2678)
 				const uint32_t b = (uint32_t)bucket_resp_time((long long)ms);
 				bkt[k] = b;
-				sbv[k] = ld_cg_v4(st.slot_batch + slot);
-				mwv[k] = __ldcg(st.bm_cur + (size_t)slot * HIST_CELLS + b);
+				if (!(plan.exp & 1)) {
+					sbv[k] = ld_cg_v4(st.slot_batch + slot);
+					mwv[k] = __ldcg(st.bm_cur + (size_t)slot * HIST_CELLS + b);
+				}
+				else { sbv[k] = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u); mwv[k] = 0xFFFFFFFFu; }
 				n_resp++;
 			}
 		}
@@ -421,8 +426,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 		}
 		__syncwarp();
 
-		if (ntcp >= 32) { const uint32_t m = ntcp & ~31u; drain_tcp(m); keep_rest(W.tcp, m, ntcp); t_tcp += m; ntcp -= m; }
-		if (ntask >= 32) { const uint32_t m = ntask & ~31u; drain_task(m); keep_rest(W.task, m, ntask); t_task += m; ntask -= m; }
+		if (ntcp >= 32) { const uint32_t m = ntcp & ~31u; if (!(plan.exp & 4)) drain_tcp(m); keep_rest(W.tcp, m, ntcp); t_tcp += m; ntcp -= m; }
+		if (ntask >= 32) { const uint32_t m = ntask & ~31u; if (!(plan.exp & 8)) drain_task(m); keep_rest(W.task, m, ntask); t_task += m; ntask -= m; }
 		if (nk > (uint32_t)Shared::KQ_FLUSH) flush_keys();
 	}
 	// what is left in the queues
@@ -1402,6 +1407,8 @@ static int key_sort_plan(uint32_t max_svcs, SortPlan &P)
 	int at = KEY_GROUP_SHIFT;
 	for (int p = 0; p < np; ++p) { P.bits[p] = T / np + (p < T % np ? 1 : 0); P.shift[p] = at; at += P.bits[p]; }
 	P.np = np;
+	static const int exp = []{ const char *e = getenv("GYSK_EXP_ABLATE"); return e ? atoi(e) : 0; }();
+	P.exp = exp;
 	return np;
 }
 
