@@ -64,7 +64,7 @@ struct IdTable
 static constexpr unsigned long long KEY_TOMBSTONE = ~0ull;	// table entry of an evicted id: never matches, never ends a probe chain
 
 // device counters (index into Engine::d_counters)
-enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_INSERT_FAIL, CTR_NTOUCHED, CTR_NRUNS, CTR_NEVICT, CTR_EVICTED_TOTAL, CTR_MAX = 16 };
+enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_INSERT_FAIL, CTR_NTOUCHED, CTR_NRUNS, CTR_NEVICT, CTR_EVICTED_TOTAL, CTR_NTCPQ, CTR_NTASKQ, CTR_MAX = 16 };
 
 // ---------------------------------------------------------------------------------------------------
 // jhash: Bob Jenkins lookup2 in the form the reference uses (common/jhash.h:22-35,121-134); seed 0xceedfead

@@ -123,7 +123,8 @@ struct gysk_engine
 {
 	gysk_config		cfg {};
 	int			dev {0};
-	cudaStream_t		stream {nullptr}, copy_stream {nullptr};
+	cudaStream_t		stream {nullptr}, copy_stream {nullptr}, side_stream {nullptr};
+	cudaEvent_t		ev_ingested {nullptr}, ev_side_done {nullptr};	// main -> side after ingest_kernel, side -> main at the end of the batch
 	gysk::DevState		st {};
 	gysk::SortTemp		tmp {};
 	std::vector<void *>	dallocs;

@@ -97,7 +97,9 @@ __device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cel
 	if (cell & CELL_TASK) {
 		HistCell *c = st.task_hist + (cell & ~CELL_TASK);
 		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
-		atomicMax(&st.task_hist[(cell & ~CELL_TASK) | 15u].sum, (long long)vmax);
+		// max_val_seen_ of the histogram: every update of every bucket would hit this one word — look first, the atomic only moves it up
+		long long *mx = &st.task_hist[(cell & ~CELL_TASK) | 15u].sum;
+		if ((long long)vmax > __ldcg(mx)) atomicMax(mx, (long long)vmax);
 	}
 	else red_add_u64(st.conn_cur + cell, (unsigned long long)cnt + (sum << 32));	// packed {count, kbytes}
 }
@@ -195,15 +197,61 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 //       MAGGR_TASK::set_local_task_state with one (event, histogram) pair per lane; the < 32 left-over entries move to the front.
 // The histogram cells and the t-digest of a service are produced from its bins by bins_merge_kernel after the batch.
 struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
+static_assert(sizeof(IngestRec) == 16, "IngestRec travels as one uint4");
 
-template <int WARPS, int EPT, bool TMA, int DH>
+// m queued connection records (all 32 lanes call; q in shared or global memory): two lookup2 hashes per flow key -> four count-min
+// REDs + the HLL register + the service's exact {count, kbytes} cell
+template <typename HotTable>
+__device__ __forceinline__ void drain_tcp_recs(const DevState &st, HotTable &hot, const IngestRec *q, uint32_t m, int lane)
+{
+	for (uint32_t i = lane; i < ((m + 31u) & ~31u); i += 32) {
+		const bool act = i < m;
+		uint32_t cell = 0; int kb = 0;
+		if (act) {
+			const IngestRec r = q[i];
+			uint32_t h1, h2, idx, rank;
+			flow_hashes(r.flow_key, h1, h2);
+			const unsigned long long inc = cms_increment(r.value);
+			for (uint32_t row = 0; row < st.cms_depth; ++row)
+				red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index2(h1, h2, row, st.cms_wmask), inc);
+			hll_idx_rank2(h1, h2, st.hll_p, idx, rank);
+			hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
+			cell = r.slot;
+			kb = (int)(r.value >> 10);
+		}
+		cell_add(st, hot, act, cell, kb);
+	}
+}
+
+// m queued process records: the three histograms of MAGGR_TASK::set_local_task_state with one (record, histogram) pair per lane
+template <typename HotTable, bool BACKWARDS = false>
+__device__ __forceinline__ void drain_task_recs(const DevState &st, HotTable &hot, const IngestRec *q, uint32_t m, int lane)
+{
+	const uint32_t ntrip = m * 3u;
+	for (uint32_t p = lane; p < ((ntrip + 31u) & ~31u); p += 32) {
+		const bool act = p < ntrip;
+		uint32_t cell = 0; int d = 0;
+		if (act) {
+			const uint32_t e = p / 3u, h = p - e * 3u;
+			const IngestRec r = BACKWARDS ? *(q - (long long)e) : q[e];
+			// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
+			d = h == 0 ? (int)r.value : (h == 1 ? (int)(uint32_t)r.flow_key : (int)(uint32_t)(r.flow_key >> 32));
+			const uint32_t b = h == 0 ? (uint32_t)bucket_hash_1_3000(d) : (uint32_t)bucket_duration(d);
+			cell = CELL_TASK | (r.slot * 3u * HIST_CELLS + h * HIST_CELLS + b);
+		}
+		cell_add(st, hot, act, cell, d);
+	}
+}
+
+
+template <int WARPS, int EPT, bool TMA, int DH, bool SIDE>
 struct IngestSharedT
 {
 	static constexpr int CHUNK = 32 * EPT;			// events per warp and round
 	static constexpr int KQ_CAP = EPT <= 2 ? 192 : 256, KQ_FLUSH = KQ_CAP - CHUNK;	// a flush leaves room for a whole chunk of RESP events
 	static constexpr int RQ_CAP = 32 + CHUNK;			// < 32 left over + one chunk
 	static_assert(CHUNK <= 128, "key queue sized for chunks of at most 128 events");
-	using HotTable = HotTableT<9>;
+	using HotTable = HotTableT<SIDE ? 1 : 9>;			// with the side drain the cells are privatised there
 	struct Warp { unsigned long long kq[KQ_CAP]; IngestRec tcp[RQ_CAP], task[RQ_CAP]; };
 	alignas(128) uint4	evbuf[TMA ? WARPS * CHUNK * 2 : 1];	// per warp: its next chunk of 32-byte events, filled by cp.async.bulk
 	unsigned long long	mbar[TMA ? WARPS : 1];
@@ -212,11 +260,11 @@ struct IngestSharedT
 	uint32_t	dhist[OS_MAX_PASSES_VK][DH];			// digit histograms of this CTA's keys, one per radix pass (DH = 256 unless a pass has 9-bit digits)
 };
 
-template <int WARPS, int MIN_CTAS, int EPT, bool TMA, int DH>
+template <int WARPS, int MIN_CTAS, int EPT, bool TMA, int DH, bool SIDE>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState st, const gysk_event *__restrict__ ev, uint64_t n,
-		unsigned long long *__restrict__ keys, uint32_t *__restrict__ ghist, SortPlan plan)
+		unsigned long long *__restrict__ keys, uint32_t *__restrict__ ghist, SortPlan plan, uint4 *__restrict__ tcpq, uint4 *__restrict__ taskq)
 {
-	using Shared = IngestSharedT<WARPS, EPT, TMA, DH>;
+	using Shared = IngestSharedT<WARPS, EPT, TMA, DH, SIDE>;
 	using HotTable = typename Shared::HotTable;
 	constexpr int CHUNK = Shared::CHUNK;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -248,41 +296,26 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 	};
 	if (TMA && lane == 0 && gwarp < nchunks) tma_issue(gwarp);
 
-	// ---- queue drains (all 32 lanes, m = multiple of 32 except in the final drain) ----
-	auto drain_tcp = [&](uint32_t m) {
-		for (uint32_t q = lane; q < ((m + 31u) & ~31u); q += 32) {
-			const bool act = q < m;
-			uint32_t cell = 0; int kb = 0;
-			if (act) {
-				const IngestRec r = W.tcp[q];
-				uint32_t h1, h2, idx, rank;
-				flow_hashes(r.flow_key, h1, h2);
-				const unsigned long long inc = cms_increment(r.value);
-				for (uint32_t row = 0; row < st.cms_depth; ++row)
-					red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index2(h1, h2, row, st.cms_wmask), inc);
-				hll_idx_rank2(h1, h2, st.hll_p, idx, rank);
-				hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
-				cell = r.slot;
-				kb = (int)(r.value >> 10);
-			}
-			cell_add(st, S.hot, act, cell, kb);
+	// ---- queue drains (all 32 lanes, m = multiple of 32 except in the final drain): applied here, or — SIDE — handed as one
+	//      coalesced run to the batch's record queues, which side_drain_kernel works off while the radix passes run ----
+	// one buffer holds both queues: connection records grow from its front, process records from its back (taskq points at the last
+	// entry; together they never exceed the batch's event count)
+	auto hand_over = [&](const IngestRec *q, uint32_t m, uint4 *gq, int ctr, bool backwards) {
+		unsigned long long base = 0;
+		if (lane == 0) base = atomicAdd(st.counters + ctr, (unsigned long long)m);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		for (uint32_t i = lane; i < m; i += 32) {
+			const uint4 v = *reinterpret_cast<const uint4 *>(q + i);
+			if (backwards) __stcs(gq - (long long)(base + i), v); else __stcs(gq + base + i, v);
 		}
 	};
+	auto drain_tcp = [&](uint32_t m) {
+		if (plan.exp & 4) return;
+		if (SIDE) hand_over(W.tcp, m, tcpq, CTR_NTCPQ, false); else drain_tcp_recs(st, S.hot, W.tcp, m, lane);
+	};
 	auto drain_task = [&](uint32_t m) {
-		const uint32_t ntrip = m * 3u;
-		for (uint32_t p = lane; p < ((ntrip + 31u) & ~31u); p += 32) {
-			const bool act = p < ntrip;
-			uint32_t cell = 0; int d = 0;
-			if (act) {
-				const uint32_t e = p / 3u, h = p - e * 3u;
-				const IngestRec r = W.task[e];
-				// GY_HISTOGRAM<int, ...>::add_data(int): the three values narrow to int (server/gy_msocket.h:1014-1016)
-				d = h == 0 ? (int)r.value : (h == 1 ? (int)(uint32_t)r.flow_key : (int)(uint32_t)(r.flow_key >> 32));
-				const uint32_t b = h == 0 ? (uint32_t)bucket_hash_1_3000(d) : (uint32_t)bucket_duration(d);
-				cell = CELL_TASK | (r.slot * 3u * HIST_CELLS + h * HIST_CELLS + b);
-			}
-			cell_add(st, S.hot, act, cell, d);
-		}
+		if (plan.exp & 8) return;
+		if (SIDE) hand_over(W.task, m, taskq, CTR_NTASKQ, true); else drain_task_recs(st, S.hot, W.task, m, lane);
 	};
 	auto keep_rest = [&](IngestRec *q, uint32_t m, uint32_t total) {		// entries [m, total) move to the front (total - m < 32)
 		IngestRec r;
@@ -426,8 +459,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 		}
 		__syncwarp();
 
-		if (ntcp >= 32) { const uint32_t m = ntcp & ~31u; if (!(plan.exp & 4)) drain_tcp(m); keep_rest(W.tcp, m, ntcp); t_tcp += m; ntcp -= m; }
-		if (ntask >= 32) { const uint32_t m = ntask & ~31u; if (!(plan.exp & 8)) drain_task(m); keep_rest(W.task, m, ntask); t_task += m; ntask -= m; }
+		if (ntcp >= 32) { const uint32_t m = ntcp & ~31u; drain_tcp(m); keep_rest(W.tcp, m, ntcp); t_tcp += m; ntcp -= m; }
+		if (ntask >= 32) { const uint32_t m = ntask & ~31u; drain_task(m); keep_rest(W.task, m, ntask); t_task += m; ntask -= m; }
 		if (nk > (uint32_t)Shared::KQ_FLUSH) flush_keys();
 	}
 	// what is left in the queues
@@ -437,7 +470,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 
 	__syncthreads();
 	// retire: one RED group per privatised cell, one RED per digit this CTA saw
-	for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) {
+	if (!SIDE) for (int i = threadIdx.x; i < HotTable::N; i += WARPS * 32) {
 		if (S.hot.tag[i] && S.hot.count[i]) cell_add_global(st, S.hot.tag[i] - 1, S.hot.count[i], S.hot.sum[i], S.hot.vmax[i]);
 	}
 	for (int i = threadIdx.x; i < plan.np * DH; i += WARPS * 32) {
@@ -459,6 +492,35 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 		// dropped = taken in but not queued (svc_id 0, bad type or value, table full, unknown id); two's complement arithmetic
 		const unsigned long long q = t_resp + t_tcp + t_task;
 		if (c_in != q) atomicAdd(st.counters + CTR_DROPPED, (unsigned long long)c_in - q);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The connection and process records ingest_kernel queued, applied NEXT TO the sort chain: the radix passes are bound by instruction
+// issue and leave the L2 atomic units idle, the ~85 M REDs of these two drains (ablation: 0.8 + 0.75 ms inside ingest_kernel,
+// profiles/r02_ablation.json) are bound by exactly those units. Runs on the engine's side stream between the ingest kernel and the
+// end of the batch's chain. Persistent grid; a warp takes 32 records at a time; hot cells are privatised per CTA as before.
+// ---------------------------------------------------------------------------------------------------
+static constexpr int SD_WARPS = 8;
+
+__global__ void __launch_bounds__(SD_WARPS * 32) side_drain_kernel(DevState st, const uint4 *__restrict__ tcpq, const uint4 *__restrict__ taskq)
+{
+	using HotTable = HotTableT<9>;
+	__shared__ HotTable hot;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (int i = threadIdx.x; i < HotTable::N; i += SD_WARPS * 32) { hot.tag[i] = 0; hot.count[i] = 0; hot.sum[i] = 0; hot.vmax[i] = INT_MIN; }
+	__syncthreads();
+	const unsigned long long ntcp = st.counters[CTR_NTCPQ], ntask = st.counters[CTR_NTASKQ];
+	const unsigned long long gw = (unsigned long long)blockIdx.x * SD_WARPS + wid, nw = (unsigned long long)gridDim.x * SD_WARPS;
+
+	for (unsigned long long base = gw * 32; base < ntcp; base += nw * 32)
+		drain_tcp_recs(st, hot, reinterpret_cast<const IngestRec *>(tcpq) + base, (uint32_t)(ntcp - base < 32 ? ntcp - base : 32), lane);
+	for (unsigned long long base = gw * 32; base < ntask; base += nw * 32)
+		drain_task_recs<HotTable, true>(st, hot, reinterpret_cast<const IngestRec *>(taskq) - (long long)base, (uint32_t)(ntask - base < 32 ? ntask - base : 32), lane);
+
+	__syncthreads();
+	for (int i = threadIdx.x; i < HotTable::N; i += SD_WARPS * 32) {
+		if (hot.tag[i] && hot.count[i]) cell_add_global(st, hot.tag[i] - 1, hot.count[i], hot.sum[i], hot.vmax[i]);
 	}
 }
 
@@ -1412,19 +1474,26 @@ static int key_sort_plan(uint32_t max_svcs, SortPlan &P)
 	return np;
 }
 
-template <int WARPS, int MIN_CTAS, int EPT, bool TMA, int DH>
-static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, uint32_t *ghist, const SortPlan &plan,
-		int dev, cudaStream_t s)
+// GYSK_SIDE_DRAIN=0: the connection / process records are applied inside ingest_kernel (A/B runs)
+bool side_drain_enabled()
 {
-	using Shared = IngestSharedT<WARPS, EPT, TMA, DH>;
+	static const bool on = []{ const char *e = getenv("GYSK_SIDE_DRAIN"); return !e || atoi(e) != 0; }();
+	return on;
+}
+
+template <int WARPS, int MIN_CTAS, int EPT, bool TMA, int DH, bool SIDE>
+static void launch_ingest_variant(const DevState &st, const gysk_event *d_ev, uint64_t n, unsigned long long *d_keys, uint32_t *ghist, const SortPlan &plan,
+		uint4 *tcpq, uint4 *taskq, int dev, cudaStream_t s)
+{
+	using Shared = IngestSharedT<WARPS, EPT, TMA, DH, SIDE>;
 	static bool attr_set[MAX_DEVICES] = {};
 	if (!attr_set[dev]) {
-		cudaFuncSetAttribute(ingest_kernel<WARPS, MIN_CTAS, EPT, TMA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+		cudaFuncSetAttribute(ingest_kernel<WARPS, MIN_CTAS, EPT, TMA, DH, SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
 		attr_set[dev] = true;
 	}
 	const uint64_t want = (n + (uint64_t)Shared::CHUNK * WARPS - 1) / ((uint64_t)Shared::CHUNK * WARPS);
 	const uint64_t full = (uint64_t)sm_count(dev) * MIN_CTAS;
-	ingest_kernel<WARPS, MIN_CTAS, EPT, TMA, DH><<<(uint32_t)(want < full ? want : full), WARPS * 32, sizeof(Shared), s>>>(st, d_ev, n, d_keys, ghist, plan);
+	ingest_kernel<WARPS, MIN_CTAS, EPT, TMA, DH, SIDE><<<(uint32_t)(want < full ? want : full), WARPS * 32, sizeof(Shared), s>>>(st, d_ev, n, d_keys, ghist, plan, tcpq, taskq);
 }
 
 int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_ev, uint64_t n, uint32_t max_svcs, cudaStream_t s)
@@ -1438,8 +1507,17 @@ int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_e
 	cudaMemsetAsync(tmp.os_ghist, 0, (OS_MAX_PASSES * RADIX_MAX + OS_MAX_PASSES) * sizeof(uint32_t), s);
 	bool wide = false;
 	for (int p = 0; p < plan.np; ++p) wide |= plan.bits[p] > 8;
-#define GYSK_LI(W, C, E, T) do { if (wide) launch_ingest_variant<W, C, E, T, 512>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); \
-		else launch_ingest_variant<W, C, E, T, 256>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, dev, s); } while (0)
+	const bool side = side_drain_enabled();
+	if (side) cudaMemsetAsync(st.counters + CTR_NTCPQ, 0, 2 * sizeof(unsigned long long), s);
+#define GYSK_LI2(W, C, E, T, D, SD) launch_ingest_variant<W, C, E, T, D, SD>(st, d_ev, n, tmp.keys_a, tmp.os_ghist, plan, tmp.tcpq, tmp.taskq, dev, s)
+#define GYSK_LI(W, C, E, T) do { if (wide) GYSK_LI2(W, C, E, T, 512, false); else GYSK_LI2(W, C, E, T, 256, false); } while (0)
+	if (side) {			// the shipped shapes; the experiment variants below keep the in-kernel drains
+		const int v = ingest_variant();
+		if (wide) GYSK_LI2(8, 3, 2, false, 512, true);
+		else if (v == 842) GYSK_LI2(8, 4, 2, false, 256, true);
+		else GYSK_LI2(8, 3, 2, false, 256, true);
+		return 1;
+	}
 	switch (ingest_variant()) {
 	case 842 : GYSK_LI(8, 4, 2, false); break;
 	case 852 : GYSK_LI(8, 5, 2, false); break;
@@ -1452,6 +1530,18 @@ int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_e
 	default : GYSK_LI(8, 3, 2, false); break;
 	}
 #undef GYSK_LI
+#undef GYSK_LI2
+	return 1;
+}
+
+// the batch's queued connection / process records -> count-min, HLL, exact cells, process histograms (side stream)
+int launch_side_drain(const DevState &st, const SortTemp &tmp, uint64_t n_events, cudaStream_t s)
+{
+	if (!n_events || !side_drain_enabled()) return 0;
+	static const int per_sm = []{ const char *e = getenv("GYSK_SIDE_CTAS"); const int v = e ? atoi(e) : 1; return v >= 1 && v <= 8 ? v : 1; }();
+	const uint64_t want = (n_events + SD_WARPS * 32 - 1) / (SD_WARPS * 32);
+	const uint64_t full = (uint64_t)sm_count(current_device()) * per_sm;
+	side_drain_kernel<<<(uint32_t)(want < full ? want : full), SD_WARPS * 32, 0, s>>>(st, tmp.tcpq, tmp.taskq);
 	return 1;
 }
 
