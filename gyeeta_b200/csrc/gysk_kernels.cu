@@ -196,7 +196,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 //       register + the service's exact {count, kbytes} cell; TASK = the three histograms of
 //       MAGGR_TASK::set_local_task_state with one (event, histogram) pair per lane; the < 32 left-over entries move to the front.
 // The histogram cells and the t-digest of a service are produced from its bins by bins_merge_kernel after the batch.
-struct IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };
+struct alignas(16) IngestRec { uint32_t slot; uint32_t value; unsigned long long flow_key; };		// moved as one 128-bit word
 static_assert(sizeof(IngestRec) == 16, "IngestRec travels as one uint4");
 
 // m queued connection records (all 32 lanes call; q in shared or global memory): two lookup2 hashes per flow key -> four count-min
