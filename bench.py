@@ -4,9 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # product arm
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on this box's host cores
 
-One STEP = one pass of the hot path over one batch of synthetic events: ingest_kernel (id lookup, one sort key per response sample,
-connection / process records queued), then on two streams 4 one-sweep radix passes + runs_mark / runs_sum (per-(service, bin) counts
-and sums) + bins_merge (histogram cells + t-digest merge) next to side_drain_kernel (count-min / HLL / process histograms). N > 1 adds ONE sketch merge (gysk_merge_global: fold + one NCCL group + merge-compress) per timed
+One STEP = one pass of the hot path over one batch of synthetic events: ingest_kernel (count-min / HLL / process histograms + one
+sort key per response sample), 4 one-sweep radix passes, runs_mark / runs_sum (per-(service, bin) counts and sums), bins_merge
+(histogram cells + t-digest merge). N > 1 adds ONE sketch merge (gysk_merge_global: fold + one NCCL group + merge-compress) per timed
 window, as a deployment merges once per query window. Workload = BASELINE.json configs[2] ("100 M mixed TCP/syscall events,
 100 K services, t-digest p50/p95/p99 on 1xB200"), the largest single-GPU configuration: per rank EVENTS_PER_STEP
 events of the 70/20/10 RESP/TCP/TASK mix over 100 K services (weak scaling: each rank ingests its own host shard).
@@ -42,10 +42,10 @@ ZIPF_S = 1.05
 # split per kernel group: the ingest kernel reads every record (32 B) and carries the TCP (count-min + HLL) and TASK state; the
 # RESP histogram cell (32 B), per-service counter (16 B) and t-digest share (18 B) are produced from the sorted keys by the
 # sort + runs + bins-merge chain.
-# With the side drain (default) ingest_kernel only reads the records (32 B each) and queues keys / records; the connection state
-# (64 + 2 B per TCP event) and the process histograms (96 B per TASK sample) are applied by side_drain_kernel next to the chain, so
-# their bytes count with the chain group. GYSK_SIDE_DRAIN=0 puts them back into ingest_kernel (54.8 / 46.2).
-SIDE_DRAIN = os.environ.get("GYSK_SIDE_DRAIN", "1") != "0"
+# With the side-drain experiment (GYSK_SIDE_DRAIN=1, not the default) ingest_kernel only reads the records (32 B each) and queues keys /
+# records; the connection state (64 + 2 B per TCP event) and the process histograms (96 B per TASK sample) are applied by
+# side_drain_kernel, so their bytes count with the chain group.
+SIDE_DRAIN = os.environ.get("GYSK_SIDE_DRAIN", "0") != "0"
 BYTES_INGEST = 32.0 if SIDE_DRAIN else 0.7 * 32 + 0.2 * 98 + 0.1 * 128                      # 32.0 (54.8) B / event
 BYTES_TDIGEST = 0.7 * (32 + 16 + 18) + (0.2 * 66 + 0.1 * 96 if SIDE_DRAIN else 0.0)        # 69.0 (46.2) B / event
 BYTES_EVENT = BYTES_INGEST + BYTES_TDIGEST                                                  # 101.0 B / event

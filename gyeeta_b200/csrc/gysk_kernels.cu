@@ -496,10 +496,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The connection and process records ingest_kernel queued, applied NEXT TO the sort chain: the radix passes are bound by instruction
-// issue and leave the L2 atomic units idle, the ~85 M REDs of these two drains (ablation: 0.8 + 0.75 ms inside ingest_kernel,
-// profiles/r02_ablation.json) are bound by exactly those units. Runs on the engine's side stream between the ingest kernel and the
-// end of the batch's chain. Persistent grid; a warp takes 32 records at a time; hot cells are privatised per CTA as before.
+// EXPERIMENT (GYSK_SIDE_DRAIN=1, off by default): the connection and process records ingest_kernel queued, applied next to the sort
+// chain on the engine's side stream. Idea: the radix passes are bound by instruction issue and leave the L2 atomic units idle, the ~85 M
+// REDs of the two drains (ablation: 0.8 + 0.75 ms inside ingest_kernel, profiles/r02_ablation.json) are bound by exactly those units.
+// Outcome: correct (the whole GPU suite passes with it on) but slower, see side_drain_enabled(). Persistent grid; a warp takes 32
+// records at a time; hot cells are privatised per CTA as in ingest_kernel.
 // ---------------------------------------------------------------------------------------------------
 static constexpr int SD_WARPS = 8;
 
@@ -1474,10 +1475,13 @@ static int key_sort_plan(uint32_t max_svcs, SortPlan &P)
 	return np;
 }
 
-// GYSK_SIDE_DRAIN=0: the connection / process records are applied inside ingest_kernel (A/B runs)
+// GYSK_SIDE_DRAIN=1: the connection / process records are queued by ingest_kernel and applied by side_drain_kernel on a second
+// stream next to the sort chain. Measured and NOT the default (profiles/r02_side_drain_ab.json): ingest_kernel gets 0.4 ms faster,
+// but the block scheduler does not interleave the side kernel with the radix passes (they fill every SM's register file), so its
+// 1.5 - 2.5 ms land behind the chain: 8.1 ms per batch against 6.9 ms with the drains inside ingest_kernel.
 bool side_drain_enabled()
 {
-	static const bool on = []{ const char *e = getenv("GYSK_SIDE_DRAIN"); return !e || atoi(e) != 0; }();
+	static const bool on = []{ const char *e = getenv("GYSK_SIDE_DRAIN"); return e && atoi(e) != 0; }();
 	return on;
 }
 
