@@ -806,13 +806,15 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 struct RunRec { unsigned long long cw; unsigned long long us; };		// {samples : 27 | remainders : 37}, usec sum — as Bin
 struct BatchSeg { uint32_t run0, nruns; uint32_t key0, nkeys; };		// a touched service's runs in the pool / keys in the sorted array
 
-static constexpr int RM_THREADS = 256, RM_V = 8, RM_TILE = RM_THREADS * RM_V;	// keys per thread: positions wbase + t * 32 + lane
+static constexpr int RM_V = 8;	// keys per thread: positions wbase + t * 32 + lane; a CTA of RM_THREADS threads covers RM_THREADS * RM_V keys
 
+template <int RM_THREADS>
 __global__ void __launch_bounds__(RM_THREADS) runs_mark_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ d_n,
 		unsigned long long *__restrict__ status, uint32_t epoch, RunRec *__restrict__ pool, uint16_t *__restrict__ run_bin,
 		uint32_t *__restrict__ chunk_run, BatchSeg *__restrict__ segs /* [slot] */, uint32_t *__restrict__ touched, unsigned long long *ntouched,
 		unsigned long long *nruns_total)
 {
+	constexpr int RM_TILE = RM_THREADS * RM_V;
 	__shared__ uint32_t wsum[RM_THREADS / 32], s_excl;
 	const uint64_t n = *d_n;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1687,8 +1689,13 @@ int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint64_t n_event
 
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
 	const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
-	runs_mark_kernel<<<div_up(n_events, RM_TILE), RM_THREADS, 0, s>>>(src, d_nkeys, tmp.tile_status, epoch, reinterpret_cast<RunRec *>(tmp.pool), tmp.run_bin,
-			tmp.chunk_run, reinterpret_cast<BatchSeg *>(tmp.segs), tmp.touched, d_ntouched, st.counters + CTR_NRUNS);
+	// GYSK_RM_THREADS=256: tiles of 2048 keys (twice the look-back steps)
+	static const int rm_threads = []{ const char *e = getenv("GYSK_RM_THREADS"); return e && atoi(e) == 256 ? 256 : 512; }();
+#define RM_ARGS src, d_nkeys, tmp.tile_status, epoch, reinterpret_cast<RunRec *>(tmp.pool), tmp.run_bin, tmp.chunk_run, \
+		reinterpret_cast<BatchSeg *>(tmp.segs), tmp.touched, d_ntouched, st.counters + CTR_NRUNS
+	if (rm_threads == 256) runs_mark_kernel<256><<<div_up(n_events, 256 * RM_V), 256, 0, s>>>(RM_ARGS);
+	else runs_mark_kernel<512><<<div_up(n_events, 512 * RM_V), 512, 0, s>>>(RM_ARGS);
+#undef RM_ARGS
 	runs_sum_kernel<<<nsm * 8, 256, 0, s>>>(src, d_nkeys, tmp.chunk_run, reinterpret_cast<RunRec *>(tmp.pool));
 	// GYSK_MERGE_SMEM_N=512 selects the larger work area (A/B runs)
 	static const int merge_smem_n = []{ const char *e = getenv("GYSK_MERGE_SMEM_N"); return e && atoi(e) == 512 ? 512 : 384; }();
