@@ -1689,8 +1689,8 @@ int launch_batch_merge(const DevState &st, const SortTemp &tmp, uint64_t n_event
 
 	cudaMemsetAsync(d_ntouched, 0, sizeof(unsigned long long), s);
 	const uint32_t epoch = next_epoch(tmp, tmp.max_tiles, s);
-	// GYSK_RM_THREADS=256: tiles of 2048 keys (twice the look-back steps)
-	static const int rm_threads = []{ const char *e = getenv("GYSK_RM_THREADS"); return e && atoi(e) == 256 ? 256 : 512; }();
+	// GYSK_RM_THREADS=512: tiles of 4096 keys (half the look-back steps) — A/B runs
+	static const int rm_threads = []{ const char *e = getenv("GYSK_RM_THREADS"); return e && atoi(e) == 512 ? 512 : 256; }();
 #define RM_ARGS src, d_nkeys, tmp.tile_status, epoch, reinterpret_cast<RunRec *>(tmp.pool), tmp.run_bin, tmp.chunk_run, \
 		reinterpret_cast<BatchSeg *>(tmp.segs), tmp.touched, d_ntouched, st.counters + CTR_NRUNS
 	if (rm_threads == 256) runs_mark_kernel<256><<<div_up(n_events, 256 * RM_V), 256, 0, s>>>(RM_ARGS);
