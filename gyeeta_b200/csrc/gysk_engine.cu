@@ -549,7 +549,9 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 		A(dalloc(e, &tmp.pool, pool_cap, false)); A(dalloc(e, &tmp.run_bin, pool_cap, false));
 		A(dalloc(e, &tmp.chunk_run, ((size_t)cfg.max_batch >> 7) + 16, false)); A(dalloc(e, &tmp.segs, ns));
 		A(dalloc(e, &tmp.items_scratch, nmw * NBINS, false)); A(dalloc(e, &tmp.big_scratch, nmw, false));
-		A(dalloc(e, &tmp.tcpq, (size_t)cfg.max_batch + 64, false)); tmp.taskq = tmp.tcpq + ((size_t)cfg.max_batch + 63);	// one buffer, filled from both ends
+		if (side_drain_enabled()) {		// the experiment's record queue: one buffer, filled from both ends
+			A(dalloc(e, &tmp.tcpq, (size_t)cfg.max_batch + 64, false)); tmp.taskq = tmp.tcpq + ((size_t)cfg.max_batch + 63);
+		}
 	}
 	st.svc_tbl.insert_fail = st.counters + CTR_INSERT_FAIL; st.task_tbl.insert_fail = nullptr;
 
