@@ -25,23 +25,34 @@ static constexpr uint32_t SLOT_INVALID = 0xFFFFFFFFu;
 struct Centroid { double mean; unsigned long long weight; };
 static constexpr int TD_CAP = 256;		// delta = 200 yields 200 ... 1.3 x 200 centroids
 
-// One log-linear value bin of one service for the batch being ingested: every RESP sample costs two 64-bit REDs,
+// One log-linear value bin of one service for the batch being ingested:
 //   cw += 1 | (usec % 1000) << 27        {samples : 27 | sum of the sub-millisecond remainders : 37}  — a batch holds < 2^27 events
 //   us += usec
 // so that the bin's exact msec sum (GY_HISTOGRAM::add_data adds usec / 1000 per sample) is (us - remainders) / 1000 and its mean
 // us / samples. Bin index = td_code(usec) + RESP_TIME_HASH bucket of its msec value: both terms are monotone in usec, so the
-// index is too and no bin straddles a histogram bucket. The batch's merge kernel reads the bins in order and zeroes them.
+// index is too and no bin straddles a histogram bucket. Two ways lead to the same numbers: the samples of most services travel as
+// sort keys and are summed per run of equal {slot, bin} (RunRec, gysk_kernels.cu); a HOT service — one that brought at least
+// hot_min samples in an earlier batch — owns a dense row of such bins (DevState::hot_rows, L2-resident; layout below) and
+// every one of its samples is two 64-bit REDs into it, no key, no sort. The batch's merge kernel reads a row in order and zeroes it.
 struct alignas(16) Bin { unsigned long long cw; unsigned long long us; };
 static constexpr int NBINS = 848;				// 832 codes + 15 buckets, padded to a multiple of 16
 static constexpr int BIN_CNT_BITS = 27;
 static constexpr unsigned long long BIN_CNT_MASK = (1ull << BIN_CNT_BITS) - 1;
+// A hot service's row: HOT_ROW_BINS words {samples | remainders} followed by HOT_ROW_BINS words of usec sums (the two REDs of a
+// sample go to different lines), bin b at word hot_word(b) — the 32 x 32 transpose of the index, so that neighbouring bins, which
+// fill up together around the mode of a service's response times, lie two 128-byte lines apart: same-line atomics are serialised
+// in L2 and the fullest line of the busiest service is what the ingest kernel ends up waiting for (profiles/r02_hot_rows_ab.json).
+static constexpr int HOT_ROW_BINS = 1024, HOT_ROW_WORDS = 2 * HOT_ROW_BINS;
+static_assert(NBINS <= HOT_ROW_BINS, "a row holds every bin");
+__host__ __device__ __forceinline__ uint32_t hot_word(uint32_t bin) { return ((bin & 31u) << 5) | (bin >> 5); }
 
 // per-service counters beside the histograms: ACTIVE_CONN_STATS roll-up {active conns : 32 | kbytes : 32}, max rtt (float bits),
 // API_TRAN error counters {client errors : 32 | server errors : 32}; cur = window being filled, last = last closed window
 struct alignas(8) SlotAux { unsigned long long act_cur, act_last, err_cur, err_last; uint32_t rtt_cur, rtt_last; };
 
 // per-service scratch of the batch being ingested: exact extremes of its RESP samples and "has bins to merge"
-struct alignas(16) SlotBatch { uint32_t minv, maxv, touched, pad; };
+// hot = 1 + the service's row of DevState::hot_rows, 0 = its samples travel as sort keys (set by bins_merge_kernel, read by the next batch)
+struct alignas(16) SlotBatch { uint32_t minv, maxv, touched, hot; };
 // listener state of the last evaluated window (gysk_state.cuh): curr_state_, curr_issue_, issue_bit_hist_, high_resp_bit_hist_ and the
 // active connection count last reported by an ACTIVE_CONN_STATS record (kept between the 15-s reports)
 struct alignas(8) SlotState { uint8_t state, issue, issue_bits, high_bits; uint32_t nconn_active; };
@@ -64,7 +75,8 @@ struct IdTable
 static constexpr unsigned long long KEY_TOMBSTONE = ~0ull;	// table entry of an evicted id: never matches, never ends a probe chain
 
 // device counters (index into Engine::d_counters)
-enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_INSERT_FAIL, CTR_NTOUCHED, CTR_NRUNS, CTR_NEVICT, CTR_EVICTED_TOTAL, CTR_NTCPQ, CTR_NTASKQ, CTR_MAX = 16 };
+enum { CTR_IN = 0, CTR_DROPPED, CTR_RESP, CTR_TCP, CTR_TASK, CTR_FOREIGN, CTR_NKEYS, CTR_INSERT_FAIL, CTR_NTOUCHED, CTR_NRUNS, CTR_NEVICT, CTR_EVICTED_TOTAL, CTR_NTCPQ, CTR_NTASKQ,
+	CTR_NHOT /* hot rows in use by the batch in flight */, CTR_NHOT_NEXT /* rows handed out so far */, CTR_MAX = 16 };
 
 // ---------------------------------------------------------------------------------------------------
 // jhash: Bob Jenkins lookup2 in the form the reference uses (common/jhash.h:22-35,121-134); seed 0xceedfead

@@ -159,13 +159,36 @@ int gysk::sync_locked(gysk_engine *e)
 
 namespace {
 
-thread_local std::vector<std::pair<uint64_t, ThreadStage *>> tls_stages;
+// engines alive (uid): a thread that exits hands its stages back to the engines that still exist
+std::mutex g_live_mtx;
+std::vector<uint64_t> g_live;
 
-// the calling thread's stage of this engine (created on first use)
+struct TlsStages
+{
+	std::vector<std::pair<uint64_t, ThreadStage *>> v;
+	~TlsStages()
+	{
+		std::lock_guard<std::mutex> lk(g_live_mtx);
+		for (auto &kv : v) if (std::find(g_live.begin(), g_live.end(), kv.first) != g_live.end()) kv.second->orphan.store(true, std::memory_order_release);
+	}
+};
+thread_local TlsStages tls_stages_holder;
+#define tls_stages tls_stages_holder.v
+
+// the calling thread's stage of this engine: its own, else one whose thread is gone (madhava's handler threads live as long as the
+// process, but a pool that recycles threads must not pay two cudaHostAlloc calls per new thread), else a new one
 ThreadStage *get_stage(gysk_engine *e)
 {
 	for (auto &kv : tls_stages) if (kv.first == e->uid) return kv.second;
 	std::lock_guard<std::mutex> lk(e->tstage_mtx);
+	for (auto &old : e->tstages) {
+		bool want = true;
+		if (old->orphan.compare_exchange_strong(want, false, std::memory_order_acq_rel)) {
+			if (tls_stages.size() > 64) tls_stages.erase(tls_stages.begin());
+			tls_stages.emplace_back(e->uid, old.get());
+			return old.get();
+		}
+	}
 	auto ts = std::make_unique<ThreadStage>();
 	ts->cap = std::min<uint32_t>(e->cfg.stage_batch, THREAD_STAGE_EVENTS);
 	if (cudaSetDevice(e->dev) != cudaSuccess) return nullptr;
@@ -419,6 +442,7 @@ const char *gysk_last_error(gysk_engine *e)
 void gysk_destroy(gysk_engine *e)
 {
 	if (!e) return;
+	{ std::lock_guard<std::mutex> lk(g_live_mtx); g_live.erase(std::remove(g_live.begin(), g_live.end(), e->uid), g_live.end()); }
 	cudaSetDevice(e->dev);
 	if (e->stream) cudaStreamSynchronize(e->stream);
 	if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
@@ -476,6 +500,7 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 	gysk_engine *e = new (std::nothrow) gysk_engine;
 	if (!e) return fail(nullptr, GYSK_ERR_NOMEM, "new gysk_engine");
 	e->cfg = cfg; e->dev = cfg.device; e->uid = g_engine_uid.fetch_add(1);
+	{ std::lock_guard<std::mutex> lk(g_live_mtx); g_live.push_back(e->uid); }
 	memset(e->ring_epoch, 0xFF, sizeof(e->ring_epoch));
 
 	int rc = 0;
@@ -533,6 +558,22 @@ int gysk_create(const gysk_config *ucfg, gysk_engine **out)
 		st.td.qtab = d_q; st.td.delta = cfg.td_compression; st.td.pad = 0;
 	}
 	A(dalloc(e, &st.slot_batch, ns)); A(dalloc(e, &st.slot_aux, ns));
+	{
+		// dense value bins of the hot services: GYSK_HOT_ROWS rows of 16 KB (default 2048, 0 switches the path off); a
+		// service turns hot with GYSK_HOT_MIN (default 4096) .. GYSK_HOT_MAX samples in one batch unless its fullest bin holds more
+		// than GYSK_HOT_BIN_MAX (default 131072) of them. Routing only: results do not depend on any of these.
+		auto envl = [](const char *name, long dflt) { const char *v = getenv(name); return v ? atol(v) : dflt; };
+		long rows = envl("GYSK_HOT_ROWS", 2048);
+		if (rows < 0) rows = 0;
+		if (rows > 65536) rows = 65536;
+		if ((size_t)rows > ns) rows = (long)ns;
+		st.hot_cap = (uint32_t)rows;
+		st.hot_min = (uint32_t)std::max(1l, envl("GYSK_HOT_MIN", 4096));
+		st.hot_max = (uint32_t)std::min<long>(0xFFFFFFFFl, std::max(1l, envl("GYSK_HOT_MAX", 0xFFFFFFFFl)));
+		st.hot_bin_max = (uint32_t)std::min<long>(0xFFFFFFFFl, std::max(1l, envl("GYSK_HOT_BIN_MAX", 131072)));
+		st.hot_rows = nullptr; st.hot_slot = nullptr;
+		if (rows) { A(dalloc(e, &st.hot_rows, (size_t)rows * HOT_ROW_WORDS)); A(dalloc(e, &st.hot_slot, (size_t)rows)); }
+	}
 	A(dalloc(e, &st.qps_hist, ns * HIST_CELLS)); A(dalloc(e, &st.act_hist, ns * HIST_CELLS)); A(dalloc(e, &st.slot_state, ns));
 	SortTemp &tmp = e->tmp;
 	const size_t nsort = std::max<size_t>(std::max<size_t>(ns, nt) + 1, cfg.max_batch);	// RESP keys of a batch; the top-N sorts rank services / tasks
@@ -642,6 +683,20 @@ int gysk_get_stats(gysk_engine *e, gysk_stats *out)
 	out->batches = e->batches; out->kernel_launches = e->kernel_launches;
 	out->wire_msgs_ok = e->wire_ok; out->wire_msgs_bad = e->wire_bad;
 	return GYSK_OK;
+}
+
+// diagnostic: rows of dense value bins handed out to hot services so far (results never depend on it)
+int64_t gysk_hot_rows_in_use(gysk_engine *e)
+{
+	if (!e) return GYSK_ERR_INVAL;
+	GYSK_ENTER(e);
+	if (cudaSetDevice(e->dev) != cudaSuccess) return GYSK_ERR_CUDA;
+	int rc = sync_locked(e);
+	if (rc) return rc;
+	if (!e->st.hot_rows) return 0;
+	unsigned long long n = 0;
+	if (cudaMemcpy(&n, e->st.counters + CTR_NHOT_NEXT, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) return GYSK_ERR_CUDA;
+	return (int64_t)n;
 }
 
 int gysk_register_ids(gysk_engine *e, const uint64_t *ids, uint32_t n, int is_task)

@@ -34,6 +34,7 @@ struct ThreadStage
 	cudaEvent_t		copied[2] {};
 	int			cur {0};
 	uint32_t		fill {0}, cap {0};
+	std::atomic<bool>	orphan {false};		// its thread has exited: the next new thread of this engine takes it over
 };
 
 // bounded top-N of one host's last message: BOUNDED_PRIO_QUEUE::try_emplace_locked semantics (common/gy_statistics.h:385-414:

@@ -417,12 +417,22 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) ingest_kernel(DevState s
 			const bool is_resp = kind[k] == GYSK_EV_RESP, is_task = kind[k] == GYSK_EV_TASK, is_tcp = kind[k] == GYSK_EV_ACCEPT;
 			const int slot = slotv[k];
 			const bool ok = slot >= 0;
-			const uint32_t m_resp = __ballot_sync(0xffffffffu, ok && is_resp), m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp),
+			// a hot service (sbv.w = 1 + its row of dense value bins, handed out by bins_merge_kernel after an earlier batch) takes its
+			// sample as two REDs into the L2-resident row; everybody else's sample becomes a sort key
+			const uint32_t hotrow = (ok && is_resp) ? sbv[k].w : 0u;
+			const uint32_t m_resp = __ballot_sync(0xffffffffu, ok && is_resp && !hotrow), m_tcp = __ballot_sync(0xffffffffu, ok && is_tcp),
 					m_task = __ballot_sync(0xffffffffu, ok && is_task);
 			if (ok) {
 				if (is_resp) {
-					W.kq[nk + __popc(m_resp & lt)] = ((unsigned long long)(uint32_t)slot << KEY_SLOT_SHIFT) |
-							((unsigned long long)(td_code(rb[k].x) + bkt[k]) << KEY_GROUP_SHIFT) | rb[k].x;
+					const uint32_t bin = td_code(rb[k].x) + bkt[k];
+					if (hotrow) {
+						unsigned long long *hb = st.hot_rows + (size_t)(hotrow - 1u) * HOT_ROW_WORDS + hot_word(bin);
+						const uint32_t us = rb[k].x;
+						red_add_u64(hb, 1ull | ((unsigned long long)(us - (us / 1000u) * 1000u) << BIN_CNT_BITS));
+						red_add_u64(hb + HOT_ROW_BINS, (unsigned long long)us);
+					}
+					else W.kq[nk + __popc(m_resp & lt)] = ((unsigned long long)(uint32_t)slot << KEY_SLOT_SHIFT) |
+							((unsigned long long)bin << KEY_GROUP_SHIFT) | rb[k].x;
 					// the rest only when it changes something: batch extremes (minv != ~0 also marks the slot as touched) and the
 					// CONN_BITMAP bit — TCP_LISTENER::CONN_BITMAP::add_response (common/gy_socket_stat.h:403-410), transposed: per
 					// bucket a mask over client port & 31
@@ -658,11 +668,15 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 	const uint32_t n = (uint32_t)*d_n;
 	const unsigned long long etag = (unsigned long long)epoch << 32;
 
+	// persistent CTAs: the grid fills the machine once and every CTA keeps taking tile tickets until the keys are used up. The host
+	// sizes nothing by the key count (it never reads it back): with most samples on the hot rows a batch may leave a fraction of
+	// the tiles its event count would allow, and a CTA per POSSIBLE tile would spend more time starting and leaving than sorting.
+	for (;;) {
 	if (threadIdx.x == 0) S.tile = atomicAdd(ticket, 1u);
 	for (int i = threadIdx.x; i < OS_WARPS * RADIX; i += OS_THREADS) (&S.whist[0][0])[i] = 0;
 	__syncthreads();
 	const uint32_t tile = S.tile;
-	if ((uint64_t)tile * SORT_TILE >= n) return;		// surplus CTA of a grid sized for the largest possible key count
+	if ((uint64_t)tile * SORT_TILE >= n) return;		// no tile left
 	const uint32_t wbase = tile * (uint32_t)SORT_TILE + (uint32_t)wid * (OS_KPT * 32);
 
 	unsigned long long k[OS_KPT];
@@ -789,6 +803,8 @@ __global__ void __launch_bounds__(OS_THREADS, 4) os_pass_kernel(const unsigned l
 	for (uint32_t i = threadIdx.x; i < nvalid; i += OS_THREADS) {
 		const unsigned long long key = S.keys[i];
 		out[S.goff[key_digit(key, D)] + i] = key;
+	}
+	__syncthreads();		// the tile's shared state is free for the next ticket
 	}
 }
 
@@ -1048,32 +1064,68 @@ __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, 
 	}
 	__syncthreads();
 
-	for (uint32_t t = gw; t < ntouched; t += nwarps) {
-		const uint32_t slot = touched[t];
-		const BatchSeg seg = segs[slot];
-		const uint32_t nitems = seg.nruns - seg.run0;			// runs_mark_kernel left the END positions in nruns / nkeys
-		const uint32_t nsamples = seg.nkeys - seg.key0;
+	// the batch's work list: first the hot services (rows in use; the heavy ones start first), then the services runs_mark_kernel found
+	// in the sorted keys. CTR_NHOT does not move while this kernel runs: rows handed out below count in CTR_NHOT_NEXT.
+	const uint32_t nhot = st.hot_rows ? (uint32_t)st.counters[CTR_NHOT] : 0u;
+	const uint32_t lt = (1u << lane) - 1u;
+	for (uint32_t t = gw; t < nhot + ntouched; t += nwarps) {
+		const bool is_hot = t < nhot;
+		const uint32_t slot = is_hot ? st.hot_slot[t] : touched[t - nhot];
+		const SlotBatch sb = st.slot_batch[slot];
+		if (is_hot && sb.minv == 0xFFFFFFFFu) continue;			// a hot service without a sample in this batch (warp-uniform)
 		if (lane < 16) { hcnt[wid][lane] = 0; hsum_lo[wid][lane] = 0; hsum_hi[wid][lane] = 0; }
 		__syncwarp();
-		for (uint32_t j = lane; j < nitems; j += 32) {
-			const RunRec r = pool[seg.run0 + j];
-			const unsigned long long cnt = r.cw & BIN_CNT_MASK, rem = r.cw >> BIN_CNT_BITS;
-			Centroid c; c.mean = __ddiv_rn((double)r.us, (double)cnt); c.weight = cnt;	// exact integer sum, one rounding
+		// one non-empty bin {samples | remainders, usec sum} -> item j of the batch + GY_HISTOGRAM::add_data of its samples
+		auto take_bin = [&](uint32_t j, unsigned long long cw, unsigned long long us, uint32_t bin) {
+			const unsigned long long cnt = cw & BIN_CNT_MASK, rem = cw >> BIN_CNT_BITS;
+			Centroid c; c.mean = __ddiv_rn((double)us, (double)cnt); c.weight = cnt;	// exact integer sum, one rounding
 			items[j] = c;
-			const uint32_t bin = run_bin[seg.run0 + j];
 			uint32_t bk = 0;
 #pragma unroll
 			for (int q = 1; q < 15; ++q) bk += bin >= first_idx[q];
 			atomicAdd(&hcnt[wid][bk], (uint32_t)cnt);
-			const unsigned long long ms = (r.us - rem) / 1000ull;		// sum of (usec / 1000) over the run's samples
+			const unsigned long long ms = (us - rem) / 1000ull;		// sum of (usec / 1000) over the bin's samples
 			const uint32_t mlo = (uint32_t)ms, mhi = (uint32_t)(ms >> 32);
 			const uint32_t old = atomicAdd(&hsum_lo[wid][bk], mlo);
 			const uint32_t up = mhi + (old + mlo < old ? 1u : 0u);		// carry out of the low word
 			if (up) atomicAdd(&hsum_hi[wid][bk], up);
+		};
+		uint32_t nitems, nsamples, binmax = 0;		// binmax: samples in the fullest bin (per lane, reduced when needed)
+		if (!is_hot) {
+			const BatchSeg seg = segs[slot];
+			nitems = seg.nruns - seg.run0;				// runs_mark_kernel left the END positions in nruns / nkeys
+			nsamples = seg.nkeys - seg.key0;
+			for (uint32_t j = lane; j < nitems; j += 32) {
+				const RunRec r = pool[seg.run0 + j];
+				take_bin(j, r.cw, r.us, run_bin[seg.run0 + j]);
+				binmax = max(binmax, (uint32_t)(r.cw & BIN_CNT_MASK));
+			}
 		}
+		else {
+			// the service's dense row, in bin order (= value order); the row is left zeroed for the next batch
+			unsigned long long *row = st.hot_rows + (size_t)t * HOT_ROW_WORDS;
+			uint32_t mine = 0;
+			nitems = 0;
+			for (uint32_t b0 = 0; b0 < (uint32_t)NBINS; b0 += 32) {
+				const uint32_t bin = b0 + lane;
+				const uint32_t i0 = hot_word(bin), i1 = i0 + (uint32_t)HOT_ROW_BINS;
+				ulonglong2 v = make_ulonglong2(0ull, 0ull);
+				if (bin < (uint32_t)NBINS) { v.x = __ldcg(row + i0); v.y = __ldcg(row + i1); }
+				const bool ne = (v.x & BIN_CNT_MASK) != 0;
+				const uint32_t m = __ballot_sync(0xffffffffu, ne);
+				if (ne) {
+					take_bin(nitems + __popc(m & lt), v.x, v.y, bin);
+					row[i0] = 0ull; row[i1] = 0ull;
+					mine += (uint32_t)(v.x & BIN_CNT_MASK);
+					binmax = max(binmax, (uint32_t)(v.x & BIN_CNT_MASK));
+				}
+				nitems += __popc(m);
+			}
+			nsamples = __reduce_add_sync(0xffffffffu, mine);
+		}
+		binmax = __reduce_max_sync(0xffffffffu, binmax);
 		__syncwarp();
 		// nobody else touches this slot's window histogram while the batch is merged (same stream as the flush): plain updates
-		const SlotBatch sb = st.slot_batch[slot];
 		if (lane < HIST_MAX_CELL) {
 			if (hcnt[wid][lane]) {
 				HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + lane;
@@ -1084,7 +1136,18 @@ __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, 
 			HistCell *c = st.hist_cur + (size_t)slot * HIST_CELLS + HIST_MAX_CELL;
 			const long long mx = (long long)(sb.maxv / 1000u);		// max_val_seen_ of add_data (gy_statistics.h:609-611)
 			if (mx > c->sum) c->sum = mx;
-			st.slot_batch[slot] = SlotBatch {0xFFFFFFFFu, 0u, 0u, 0u};
+			// a service that brought hot_min samples in one batch gets a row of dense bins for the batches to come (rows are never
+			// taken back: a row belongs to the SLOT, whoever lives in it — routing only, the numbers are the same either way).
+			// Not one whose fullest bin holds more than hot_bin_max samples: atomics on one 128-byte line are applied one after the
+			// other (measured: ~8 ns each), a few hundred thousand of them on one line would outlast the rest of ingest_kernel —
+			// such a service sorts well instead (its keys form long runs).
+			uint32_t hot = sb.hot;
+			if (!hot && st.hot_rows && nsamples >= st.hot_min && nsamples <= st.hot_max && binmax <= st.hot_bin_max) {
+				const unsigned long long h = atomicAdd(st.counters + CTR_NHOT_NEXT, 1ull);
+				if (h < (unsigned long long)st.hot_cap) { st.hot_slot[h] = slot; hot = (uint32_t)h + 1u; }
+				else atomicAdd(st.counters + CTR_NHOT_NEXT, ~0ull);
+			}
+			st.slot_batch[slot] = SlotBatch {0xFFFFFFFFu, 0u, 0u, hot};
 		}
 		__syncwarp();
 
@@ -1508,6 +1571,8 @@ int launch_ingest(const DevState &st, const SortTemp &tmp, const gysk_event *d_e
 	const int dev = current_device();
 	SortPlan plan {};
 	if (key_sort_plan(max_svcs, plan) < 0) return -1;
+	// the hot rows handed out by the batches so far are in use from this batch on
+	if (st.hot_rows) cudaMemcpyAsync(st.counters + CTR_NHOT, st.counters + CTR_NHOT_NEXT, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s);
 	// key cursor, digit histograms and tile tickets of this batch's sort
 	cudaMemsetAsync(st.counters + CTR_NKEYS, 0, sizeof(unsigned long long), s);
 	cudaMemsetAsync(tmp.os_ghist, 0, (OS_MAX_PASSES * RADIX_MAX + OS_MAX_PASSES) * sizeof(uint32_t), s);
@@ -1617,6 +1682,9 @@ static void launch_os_pass(int bits, uint32_t ntiles, const unsigned long long *
 		const uint32_t *ghist, unsigned long long *status, uint32_t *ticket, uint32_t epoch, cudaStream_t s)
 {
 	static const bool narrow = []{ const char *e = getenv("GYSK_OS_NARROW"); return !e || atoi(e) != 0; }();
+	// GYSK_OS_PERSIST=0: one CTA per possible tile (A/B runs)
+	static const bool persist = []{ const char *e = getenv("GYSK_OS_PERSIST"); return !e || atoi(e) != 0; }();
+	if (persist) ntiles = std::min<uint32_t>(ntiles, (uint32_t)sm_count(current_device()) * 4u);		// __launch_bounds__(OS_THREADS, 4)
 	if (bits > 8) os_pass_kernel<9><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<9>), s>>>(in, out, d_n, D, ghist, status, ticket, epoch, g_rank_mode);
 	else if (bits == 8 || !narrow) os_pass_kernel<8><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<8>), s>>>(in, out, d_n, D, ghist, status, ticket, epoch, g_rank_mode);
 	else if (bits == 7) os_pass_kernel<7><<<ntiles, OS_THREADS, sizeof(OneSweepSharedT<7>), s>>>(in, out, d_n, D, ghist, status, ticket, epoch, g_rank_mode);

@@ -22,7 +22,10 @@ struct DevState
 	unsigned long long	*evict_ids;
 	unsigned long long	*conn_all_cnt, *conn_all_kb;
 	uint32_t		*bm_cur, *bm_last;			// [max_svcs][16] CONN_BITMAP transposed: per bucket a mask over (client port & 31)
-	SlotBatch		*slot_batch;				// [max_svcs] exact extremes of the batch's RESP samples
+	SlotBatch		*slot_batch;				// [max_svcs] exact extremes of the batch's RESP samples, hot row
+	unsigned long long	*hot_rows;				// [hot_cap][HOT_ROW_WORDS] dense value bins of the hot services (nullptr: feature off)
+	uint32_t		*hot_slot;				// [hot_cap] row -> slot
+	uint32_t		hot_cap, hot_min, hot_max, hot_bin_max;	// rows; a service turns hot with hot_min..hot_max samples in one batch, its fullest bin <= hot_bin_max
 	SlotAux			*slot_aux;				// [max_svcs] active-conn roll-up, error counters
 	HistCell		*qps_hist, *act_hist;			// [max_svcs][16] TCP_LISTENER::qps_hist_ / active_conn_hist_: one sample per closed window
 	SlotState		*slot_state;				// [max_svcs] listener state of the last evaluated window

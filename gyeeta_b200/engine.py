@@ -134,6 +134,7 @@ def load_library(path=None):
         "gysk_destroy": (None, [vp]),
         "gysk_last_error": (C.c_char_p, [vp]),
         "gysk_get_stats": (i32, [vp, vp]),
+        "gysk_hot_rows_in_use": (C.c_int64, [vp]),
         "gysk_register_ids": (i32, [vp, vp, u32, i32]),
         "gysk_ingest": (i32, [vp, vp, u32, u32, vp, u32, vp]),
         "gysk_ingest_msg": (i32, [vp, vp, u32, vp, u32]),
@@ -295,6 +296,13 @@ class Engine:
         s = Stats()
         self._chk(self.L.gysk_get_stats(self.h, C.byref(s)))
         return s.asdict()
+
+    def hot_rows_in_use(self):
+        """rows of dense value bins handed out to hot services so far (diagnostic; results never depend on it)"""
+        n = self.L.gysk_hot_rows_in_use(self.h)
+        if n < 0:
+            self._chk(int(n))
+        return int(n)
 
     def query_svcs(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.uint64)

@@ -337,6 +337,10 @@ int		gysk_create(const gysk_config *cfg, gysk_engine **out);
 void		gysk_destroy(gysk_engine *e);
 const char *	gysk_last_error(gysk_engine *e);		/* e may be NULL: error of the last failed gysk_create */
 int		gysk_get_stats(gysk_engine *e, gysk_stats *out);	/* synchronises the ingest stream */
+/* diagnostic: rows of dense value bins handed out so far to "hot" services — services that brought GYSK_HOT_MIN (environment, default
+ * 4096) response samples in one device batch take their later samples as direct updates of an L2-resident row instead of sort keys
+ * (GYSK_HOT_ROWS rows, default 2048, 0 = off). Routing only: no result depends on it. Negative = GYSK_ERR_*. */
+int64_t		gysk_hot_rows_in_use(gysk_engine *e);
 
 /* ---- registration (control path; mirrors partha_listener_info registering listeners before state arrives) ---- */
 int		gysk_register_ids(gysk_engine *e, const uint64_t *ids, uint32_t n, int is_task);
