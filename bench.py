@@ -524,6 +524,13 @@ def main():
     dev_ms = t0.elapsed_time(t1)
     launches = eng.stats()["kernel_launches"] - launches0           # kernels of libgysketch.so launched inside the timed region
     ms_ing, ms_td, nb = eng.profile_read()
+    # share of the events that took the hot-row way (two REDs into the service's dense value bins inside ingest_kernel instead of a
+    # sort key): read from the engine after the timed region — response samples of the last batch minus its sort keys
+    resp0 = eng.stats()["events_resp"]
+    eng.ingest_device_ptr(ev_devs[step_no[0] % NB].data_ptr(), n)
+    hot_share = max(0.0, (eng.stats()["events_resp"] - resp0 - eng.last_batch_keys()) / float(n))
+    hot_rows = eng.hot_rows_in_use()
+    eng.profile_read()                 # drop that batch's timings
     # diagnostic (outside the timed region): per-step spread of the two kernel groups
     spread = {"ingest_ms": [], "chain_ms": []}
     for i in range(min(args.steps, 8)):
@@ -642,8 +649,11 @@ def main():
     nev_total = n * args.steps
     roof = []
     traffic = ncu_traffic_per_event()
-    for name, key, ms, bpe in (("ingest_kernel", "ingest_kernel", ms_ing, BYTES_INGEST),
-                               ("sort + runs + bins-merge chain (os_pass x4, runs_mark, runs_sum, bins_merge)" + (" with side_drain_kernel beside it" if SIDE_DRAIN else ""), "chain", ms_td, BYTES_TDIGEST)):
+    # a hot response sample's histogram-cell read-modify-write (32 of its 98 B) happens in ingest_kernel — the two
+    # 64-bit REDs into its value bin — not in the chain: those bytes move from one kernel group to the other, the sum stays 101 B
+    moved = 32.0 * hot_share
+    for name, key, ms, bpe in (("ingest_kernel", "ingest_kernel", ms_ing, BYTES_INGEST + moved),
+                               ("sort + runs + bins-merge chain (os_pass x4, runs_mark, runs_sum, bins_merge)" + (" with side_drain_kernel beside it" if SIDE_DRAIN else ""), "chain", ms_td, BYTES_TDIGEST - moved)):
         if ms > 0:
             ach = nev_total * bpe / (ms * 1e-3) / 1e9
             tr = traffic.get(key, {}).get("dram_bytes_per_event")
@@ -680,6 +690,10 @@ def main():
         "roofline": roof[0] if roof else None, "roofline_other": roof[1:] or None,
         "roofline_whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
                                 "algorithmic_bytes_per_event": BYTES_EVENT},
+        "hot_rows": {"rows_in_use": hot_rows, "share_of_events": hot_share,
+                     "what": "response samples of services with >= 4096 samples in an earlier batch: two REDs into the service's dense "
+                             "L2-resident value bins inside ingest_kernel instead of a sort key; their 32 B/sample of histogram-cell "
+                             "traffic are counted with ingest_kernel (54.8 + 32 x share B/event), not with the chain"},
         "cpu_baseline": cpu, "accuracy": acc, "per_step_spread_ms": spread,
         "merge": ({"logical_services": NSVC // 16,
                    "what": "gysk_merge_global: fold kernels + ONE ncclGroup (3 all-reduces: u64 sum / i64 max / u8 max, 1 all-gather of t-digest slabs) + merge-compress, once per timed window", "merge_ms_of_the_window": (float(merge_events_value[0][0].elapsed_time(merge_events_value[0][1])) if merge_events_value else None)}

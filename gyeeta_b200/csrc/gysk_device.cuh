@@ -217,6 +217,11 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long
 	asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ void red_max_s64(long long *p, long long v)
+{
+	asm volatile("red.global.max.s64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ uint4 ld_cg_v4(const void *p)
 {
 	uint4 v;

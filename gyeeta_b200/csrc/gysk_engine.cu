@@ -699,6 +699,19 @@ int64_t gysk_hot_rows_in_use(gysk_engine *e)
 	return (int64_t)n;
 }
 
+// diagnostic: response samples of the last device batch that travelled as sort keys (the others went to hot rows)
+int64_t gysk_last_batch_keys(gysk_engine *e)
+{
+	if (!e) return GYSK_ERR_INVAL;
+	GYSK_ENTER(e);
+	if (cudaSetDevice(e->dev) != cudaSuccess) return GYSK_ERR_CUDA;
+	int rc = sync_locked(e);
+	if (rc) return rc;
+	unsigned long long n = 0;
+	if (cudaMemcpy(&n, e->st.counters + CTR_NKEYS, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) return GYSK_ERR_CUDA;
+	return (int64_t)n;
+}
+
 int gysk_register_ids(gysk_engine *e, const uint64_t *ids, uint32_t n, int is_task)
 {
 	CHECK_ENGINE(e);

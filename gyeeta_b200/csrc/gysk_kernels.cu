@@ -97,9 +97,10 @@ __device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cel
 	if (cell & CELL_TASK) {
 		HistCell *c = st.task_hist + (cell & ~CELL_TASK);
 		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
-		// max_val_seen_ of the histogram: every update of every bucket would hit this one word — look first, the atomic only moves it up
-		long long *mx = &st.task_hist[(cell & ~CELL_TASK) | 15u].sum;
-		if ((long long)vmax > __ldcg(mx)) atomicMax(mx, (long long)vmax);
+		// max_val_seen_ of the histogram: a fire-and-forget RED.MAX — looking first (to skip the atomic) made every process record wait
+		// for an L2 round trip (7.7 % of the kernel's stall samples, profiles/r02_ncu_full_raw_hot.csv); the busy processes' cells
+		// live in the CTA's hot table and reach this point once per CTA
+		red_max_s64(&st.task_hist[(cell & ~CELL_TASK) | 15u].sum, (long long)vmax);
 	}
 	else red_add_u64(st.conn_cur + cell, (unsigned long long)cnt + (sum << 32));	// packed {count, kbytes}
 }
@@ -148,11 +149,16 @@ __device__ __forceinline__ void cell_add(const DevState &st, HotTable &hot, bool
 	else cell_add_global(st, cell, cnt, (unsigned long long)sum, gmax);
 }
 
-__device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t rank)
+// HLL register update in two halves, so that the caller can put other work between the load of the register word and its use
+__device__ __forceinline__ uint32_t hll_peek(const uint8_t *regs, uint32_t idx)
+{
+	return __ldca(reinterpret_cast<const uint32_t *>(regs) + (idx >> 2));	// stale is harmless: the CAS re-validates
+}
+
+__device__ __forceinline__ void hll_raise(uint8_t *regs, uint32_t idx, uint32_t rank, uint32_t w)
 {
 	uint32_t *wp = reinterpret_cast<uint32_t *>(regs) + (idx >> 2);
 	const uint32_t sh = (idx & 3u) * 8u;
-	uint32_t w = __ldca(wp);				// stale is harmless: the CAS re-validates
 
 	while (((w >> sh) & 0xFFu) < rank) {
 		const uint32_t nw = (w & ~(0xFFu << sh)) | (rank << sh);
@@ -160,6 +166,11 @@ __device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t
 		if (old == w) break;
 		w = old;
 	}
+}
+
+__device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t idx, uint32_t rank)
+{
+	hll_raise(regs, idx, rank, hll_peek(regs, idx));
 }
 
 // ---- TMA (bulk async copy) of a warp's next event chunk into shared memory, completion on the warp's own mbarrier ----
@@ -206,20 +217,22 @@ __device__ __forceinline__ void drain_tcp_recs(const DevState &st, HotTable &hot
 {
 	for (uint32_t i = lane; i < ((m + 31u) & ~31u); i += 32) {
 		const bool act = i < m;
-		uint32_t cell = 0; int kb = 0;
+		uint32_t cell = 0, idx = 0, rank = 0, hw = 0; int kb = 0;
 		if (act) {
 			const IngestRec r = q[i];
-			uint32_t h1, h2, idx, rank;
+			uint32_t h1, h2;
 			flow_hashes(r.flow_key, h1, h2);
+			// the HLL register word is asked for first and looked at last: the count-min REDs and the cell update hide its latency
+			hll_idx_rank2(h1, h2, st.hll_p, idx, rank);
+			hw = hll_peek(st.hll + ((size_t)r.slot << st.hll_p), idx);
 			const unsigned long long inc = cms_increment(r.value);
 			for (uint32_t row = 0; row < st.cms_depth; ++row)
 				red_add_u64(st.cms_cur + ((size_t)row << st.cms_log2w) + cms_index2(h1, h2, row, st.cms_wmask), inc);
-			hll_idx_rank2(h1, h2, st.hll_p, idx, rank);
-			hll_update(st.hll + ((size_t)r.slot << st.hll_p), idx, rank);
 			cell = r.slot;
 			kb = (int)(r.value >> 10);
 		}
 		cell_add(st, hot, act, cell, kb);
+		if (act) hll_raise(st.hll + ((size_t)cell << st.hll_p), idx, rank, hw);
 	}
 }
 
@@ -1051,6 +1064,7 @@ __global__ void __launch_bounds__(TD_WARPS * 32) bins_merge_kernel(DevState st, 
 	__shared__ uint16_t first_idx[16];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * TD_WARPS + wid, nwarps = gridDim.x * TD_WARPS;
+
 	Centroid *items = items_scratch + (size_t)gw * NBINS;
 	const uint32_t ntouched = (uint32_t)*ntouched_p;
 

@@ -135,6 +135,7 @@ def load_library(path=None):
         "gysk_last_error": (C.c_char_p, [vp]),
         "gysk_get_stats": (i32, [vp, vp]),
         "gysk_hot_rows_in_use": (C.c_int64, [vp]),
+        "gysk_last_batch_keys": (C.c_int64, [vp]),
         "gysk_register_ids": (i32, [vp, vp, u32, i32]),
         "gysk_ingest": (i32, [vp, vp, u32, u32, vp, u32, vp]),
         "gysk_ingest_msg": (i32, [vp, vp, u32, vp, u32]),
@@ -300,6 +301,13 @@ class Engine:
     def hot_rows_in_use(self):
         """rows of dense value bins handed out to hot services so far (diagnostic; results never depend on it)"""
         n = self.L.gysk_hot_rows_in_use(self.h)
+        if n < 0:
+            self._chk(int(n))
+        return int(n)
+
+    def last_batch_keys(self):
+        """response samples of the last device batch that travelled as sort keys (diagnostic)"""
+        n = self.L.gysk_last_batch_keys(self.h)
         if n < 0:
             self._chk(int(n))
         return int(n)

@@ -341,6 +341,8 @@ int		gysk_get_stats(gysk_engine *e, gysk_stats *out);	/* synchronises the ingest
  * 4096) response samples in one device batch take their later samples as direct updates of an L2-resident row instead of sort keys
  * (GYSK_HOT_ROWS rows, default 2048, 0 = off). Routing only: no result depends on it. Negative = GYSK_ERR_*. */
 int64_t		gysk_hot_rows_in_use(gysk_engine *e);
+/* diagnostic: response samples of the last device batch that travelled as sort keys (the rest updated hot rows). Negative = GYSK_ERR_*. */
+int64_t		gysk_last_batch_keys(gysk_engine *e);
 
 /* ---- registration (control path; mirrors partha_listener_info registering listeners before state arrives) ---- */
 int		gysk_register_ids(gysk_engine *e, const uint64_t *ids, uint32_t n, int is_task);

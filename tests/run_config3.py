@@ -67,6 +67,8 @@ eng.register_ids(ids)
 eng.set_logical_map(ids_all, logical_all)
 if world > 1:
     gd.nccl_comm_init(eng, dist)
+    eng.merge_global()                 # NCCL sets up its channels inside the first collective of a communicator (~1.2 s on 4 GPUs):
+    eng.sync()                         # an empty merge before the timed window, as a long-running madhava has long done
 stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
 barrier()
 t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
