@@ -98,7 +98,7 @@ __device__ __forceinline__ void cell_add_global(const DevState &st, uint32_t cel
 		HistCell *c = st.task_hist + (cell & ~CELL_TASK);
 		red_add_u64(&c->count, cnt); red_add_u64((unsigned long long *)&c->sum, sum);
 		// max_val_seen_ of the histogram: a fire-and-forget RED.MAX — looking first (to skip the atomic) made every process record wait
-		// for an L2 round trip (7.7 % of the kernel's stall samples, profiles/r02_ncu_full_raw_hot.csv); the busy processes' cells
+		// for an L2 round trip (7.7 % of the kernel's stall samples, profiles/r02_ncu_full_raw_final.csv); the busy processes' cells
 		// live in the CTA's hot table and reach this point once per CTA
 		red_max_s64(&st.task_hist[(cell & ~CELL_TASK) | 15u].sum, (long long)vmax);
 	}
