@@ -372,3 +372,17 @@ def test_task_groupby_oracle_hand_case():
     assert g7["issue_bit_hist"] == 12 and g7["severe_issue_bit_hist"] == 12 and g9["issue_bit_hist"] == 2
     assert g7["rss_mb"] == 80 and g7["cpu_delay_msec"] == 8 and g7["tcp_kbytes"] == 9 and g9["tcp_kbytes"] == 7
     assert g7["onecomm"] == b"a" and g9["onecomm"] == b"b"
+
+
+def test_every_profile_named_in_the_docs_exists():
+    """README.md / DESIGN.md / profiles/README.md quote measured numbers by file: a quoted file that is not in profiles/ is a number
+    without evidence (gpurun_out/ is scratch and does not survive a session)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in ("README.md", "DESIGN.md", os.path.join("profiles", "README.md"), "INTEGRATION.md"):
+        t = open(os.path.join(root, f)).read()
+        names |= set(m.group(1) for m in re.finditer(r"`(?:profiles/)?((?:r0\d|ncu)_[A-Za-z0-9_.]+\.(?:json|csv|md|log|txt))`", t))
+    assert len(names) > 20
+    missing = sorted(n for n in names if not os.path.exists(os.path.join(root, "profiles", n)))
+    assert not missing, missing
