@@ -394,6 +394,14 @@ def cpu_arm_report(ev_np, ncores):
     return out
 
 
+def workload_config(args, world):
+    """the `config` of the JSON line: the same for the product arm and for `--impl reference` (which times a bounded sample of it)"""
+    return {"workload": "configs[2]: 100M mixed RESP/TCP/TASK (70/20/10) events, 100K services, count-min + HLL + "
+                        "fixed-bucket histograms + t-digest(200)", "events_per_step_per_gpu": args.events, "services": NSVC,
+            "zipf_s": ZIPF_S, "max_batch": args.max_batch, "stage_batch": args.stage_batch, "parallelism": f"host-shard x{world}",
+            "l2": "inputs (3.2 GB/step) larger than L2, no flush needed"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (the oracle port: GY_HISTOGRAM add_data + count-min +
     HLL + t-digest per event, open-addressing id tables), all host threads, events pre-sharded by host like madhava pins a partha
@@ -421,11 +429,11 @@ def run_reference(args):
         "impl": "reference", "metric": "events/sec aggregated", "value": rate, "unit": "events/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "configs[2]: mixed RESP/TCP/TASK 70/20/10, 100K services, bounded sample of the same generator "
-                               "(a rate per event: the sample bounds the run to a few minutes of CPU)", "events_per_step": n,
-                   "cpu_model": cpu_model()},
+        "config": workload_config(args, max(1, args.gpus)),
+        "sample_events_per_step": n,
         "cpu_baseline": {"value": rate, "unit": "events/s", "cores": ncores, "kind": "port", "cpu_model": cpu_model(),
-                         "sample": f"{n} events of the same stream, pre-sharded by host over {ncores} threads", "detail": detail},
+                         "sample": f"each step = {n} events of the same generator and mix (a rate per event: the bounded sample keeps the run "
+                                   f"to a few minutes of CPU), pre-sharded by host over {ncores} threads", "detail": detail},
         "e2e": {"value": rate, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -682,10 +690,7 @@ def main():
         "metric": "events/sec aggregated", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "configs[2]: 100M mixed RESP/TCP/TASK (70/20/10) events, 100K services, count-min + HLL + "
-                               "fixed-bucket histograms + t-digest(200)", "events_per_step_per_gpu": n, "services": NSVC,
-                   "zipf_s": ZIPF_S, "max_batch": args.max_batch, "stage_batch": args.stage_batch, "parallelism": f"host-shard x{world}",
-                   "l2": "inputs (3.2 GB/step) larger than L2, no flush needed"},
+        "config": workload_config(args, world),
         "e2e": e2e, "e2e_event32": e2e32, "e2e_wire": wire, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof[0] if roof else None, "roofline_other": roof[1:] or None,
         "roofline_whole_step": {"achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
