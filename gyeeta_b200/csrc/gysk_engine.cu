@@ -699,6 +699,13 @@ int64_t gysk_hot_rows_in_use(gysk_engine *e)
 	return (int64_t)n;
 }
 
+// introspection (no device needed): word of value bin `bin` inside a hot row's {samples | remainders} half; the usec sum of the bin
+// lies GYSK_HOT_ROW_BINS words further on. ~0 for a bin the engine does not have.
+uint32_t gysk_hot_row_word(uint32_t bin)
+{
+	return bin < (uint32_t)NBINS ? hot_word(bin) : 0xFFFFFFFFu;
+}
+
 // diagnostic: response samples of the last device batch that travelled as sort keys (the others went to hot rows)
 int64_t gysk_last_batch_keys(gysk_engine *e)
 {

@@ -341,6 +341,11 @@ int		gysk_get_stats(gysk_engine *e, gysk_stats *out);	/* synchronises the ingest
  * 4096) response samples in one device batch take their later samples as direct updates of an L2-resident row instead of sort keys
  * (GYSK_HOT_ROWS rows, default 2048, 0 = off). Routing only: no result depends on it. Negative = GYSK_ERR_*. */
 int64_t		gysk_hot_rows_in_use(gysk_engine *e);
+/* introspection (host only, no device needed): the 64-bit word of value bin `bin` (0 .. 847) inside a hot row's first half
+ * {samples | sub-msec remainders}; the bin's usec sum lies GYSK_HOT_ROW_BINS words further on. Neighbouring bins are two 128-byte
+ * lines apart. ~0 for a bin the engine does not have. */
+#define GYSK_HOT_ROW_BINS	1024u
+uint32_t	gysk_hot_row_word(uint32_t bin);
 /* diagnostic: response samples of the last device batch that travelled as sort keys (the rest updated hot rows). Negative = GYSK_ERR_*. */
 int64_t		gysk_last_batch_keys(gysk_engine *e);
 

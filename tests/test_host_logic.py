@@ -386,3 +386,20 @@ def test_every_profile_named_in_the_docs_exists():
     assert len(names) > 20
     missing = sorted(n for n in names if not os.path.exists(os.path.join(root, "profiles", n)))
     assert not missing, missing
+
+
+def test_hot_row_layout_keeps_neighbouring_bins_on_different_lines():
+    """L2 applies same-line atomics one after the other, and neighbouring value bins fill up together — the row layout
+    must be a bijection of the 848 bins into the 1024 words of a half row with neighbours at least two 128-byte lines (32 words) apart"""
+    L = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gyeeta_b200", "libgysketch.so"))
+    L.gysk_hot_row_word.restype = C.c_uint32
+    L.gysk_hot_row_word.argtypes = [C.c_uint32]
+    words = [L.gysk_hot_row_word(b) for b in range(848)]
+    assert len(set(words)) == 848 and max(words) < 1024
+    assert L.gysk_hot_row_word(848) == 0xFFFFFFFF
+    for d in range(1, 9):                                  # the bins around a mode: none of them shares a line with another
+        assert all(abs(words[b + d] - words[b]) // 16 >= 1 for b in range(848 - d)), d
+    assert all(abs(words[b + 1] - words[b]) >= 32 for b in range(847) if (b & 31) != 31)
+    lines = [w // 16 for w in words]
+    for b in range(0, 848 - 16):
+        assert len(set(lines[b: b + 16])) == 16, b         # any 16 consecutive bins: 16 different lines
