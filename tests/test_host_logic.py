@@ -403,3 +403,26 @@ def test_hot_row_layout_keeps_neighbouring_bins_on_different_lines():
     lines = [w // 16 for w in words]
     for b in range(0, 848 - 16):
         assert len(set(lines[b: b + 16])) == 16, b         # any 16 consecutive bins: 16 different lines
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the product arm): one JSON line with the product arm's metric,
+    unit, direction and config, its own cpu_baseline and an e2e that repeats the value with no host-device bytes"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample", "60000"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "events/sec aggregated" and d["unit"] == "events/s" and d["higher_is_better"] is True
+    assert d["config"]["workload"].startswith("configs[2]") and d["config"]["events_per_step_per_gpu"] == 100_000_000
+    assert d["sample_events_per_step"] == 60000 and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 leave without work
+    r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=120, cwd=root, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert r2.returncode == 0 and not r2.stdout.strip()
