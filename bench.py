@@ -4,9 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # product arm
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on this box's host cores
 
-One STEP = one pass of the hot path over one batch of synthetic events: ingest_kernel (count-min / HLL / process histograms + one
-sort key per response sample), 4 one-sweep radix passes, runs_mark / runs_sum (per-(service, bin) counts and sums), bins_merge
-(histogram cells + t-digest merge). N > 1 adds ONE sketch merge (gysk_merge_global: fold + one NCCL group + merge-compress) per timed
+One STEP = one pass of the hot path over one batch of synthetic events: ingest_kernel (count-min / HLL / process histograms; a
+response sample of a hot service updates its dense row of value bins, any other becomes a sort key), 4 one-sweep radix passes,
+runs_mark / runs_sum (per-(service, bin) counts and sums of the keys), bins_merge (histogram cells + t-digest merge from rows and runs). N > 1 adds ONE sketch merge (gysk_merge_global: fold + one NCCL group + merge-compress) per timed
 window, as a deployment merges once per query window. Workload = BASELINE.json configs[2] ("100 M mixed TCP/syscall events,
 100 K services, t-digest p50/p95/p99 on 1xB200"), the largest single-GPU configuration: per rank EVENTS_PER_STEP
 events of the 70/20/10 RESP/TCP/TASK mix over 100 K services (weak scaling: each rank ingests its own host shard).
@@ -16,7 +16,8 @@ events of the 70/20/10 RESP/TCP/TASK mix over 100 K services (weak scaling: each
            plus a device->host read of per-service summaries. Records = the packed per-kind structs of include/gysketch.h
            (18.4 B/event); `e2e_event32` = 32-byte canonical records; `e2e_wire` = 16 host threads calling gysk_ingest_msg /
            gysk_ingest_raw with TCP_CONN_NOTIFY / AGGR_TASK_STATE_NOTIFY messages and raw tcp_ipv4_resp_event_t arrays.
-`roofline`: dominant kernel, algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json.
+`roofline`: dominant kernel, algorithmic bytes (54.8 B/event + 32 B per event that took the hot-row way, `hot_rows`)
+           / CUDA-event time, against MEASURED_PEAKS.json.
 `cpu_baseline`: the CPU oracle port (all host cores, events pre-sharded by host) on a bounded sample of the same stream.
 """
 import argparse
